@@ -1,0 +1,205 @@
+/*
+ * od_msspe_b200.h -- C ABI of the B200-native engine for the open-msspe-design hot path.
+ *
+ * This is the drop-in boundary.  Every entry point below replaces one call
+ * the reference's `main` makes into its own k-mer engine or into a Primer3 subprocess; the reference
+ * location each one stands in for is cited as od-msspe/src/<file>:<line>.  A maintainer binds these
+ * from Rust with a plain `extern "C"` block; tests bind them with ctypes.
+ *
+ * Conventions
+ *   - plain C types only; caller allocates every output buffer; the context owns all device memory.
+ *   - return value 0 = MSSPE_OK, negative = error; text via msspe_last_error().  Nothing aborts/throws.
+ *   - there is NO CPU fallback: every compute entry point fails with MSSPE_ERR_CUDA when no sm_100
+ *     device / driver is usable.
+ *   - a context is single-caller (not re-entrant), like the single-threaded reference.
+ *   - k-mers cross the boundary as 2-bit big-endian codes (A=0 C=1 G=2 T=3, first base in the most
+ *     significant used bits), which preserves the reference's lexicographic String order
+ *     (main.rs:320-324) for words of equal length.
+ */
+#ifndef OD_MSSPE_B200_H
+#define OD_MSSPE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSSPE_ABI_VERSION 1
+
+#define MSSPE_OK 0
+#define MSSPE_ERR_INVALID (-1)     /* bad argument (the reference would panic!/clap-error) */
+#define MSSPE_ERR_CUDA (-2)        /* CUDA runtime/driver failure, or no device */
+#define MSSPE_ERR_NOMEM (-3)
+#define MSSPE_ERR_STATE (-4)       /* call order violated (e.g. select before build) */
+#define MSSPE_ERR_IO (-5)
+#define MSSPE_ERR_CAPACITY (-6)    /* caller buffer too small; required size reported */
+
+#define MSSPE_DIR_FWD 0            /* constants.rs:22 SEQ_DIR_FWD */
+#define MSSPE_DIR_REV 1            /* constants.rs:23 SEQ_DIR_REV */
+
+#define MSSPE_NO_KMER UINT64_MAX   /* sentinel slot: invalid (non-ACGT) or duplicate within the window */
+#define MSSPE_MAX_KMER 32
+#define MSSPE_MAX_OLIGO 32         /* thal kernels: oligo length limit (reference uses 13..15) */
+
+typedef struct msspe_ctx msspe_ctx;
+
+/* PartitioningOption, main.rs:189-194, plus device selection. */
+typedef struct {
+  uint32_t kmer_size;           /* --kmer-size            (config.rs:20)  1..32 */
+  uint32_t window_size;         /* --window-size          (config.rs:23)  segment length W */
+  uint32_t overlap_size;        /* --overlap-size         (config.rs:26)  used as the STEP (main.rs:178) */
+  uint32_t search_windows_size; /* --search-windows-size  (config.rs:39)  head/tail width w */
+  int32_t device;               /* CUDA device ordinal */
+  uint32_t flags;               /* reserved, 0 */
+} msspe_config;
+
+/* One greedy winner, main.rs:47-51 KmerFrequency (+ diagnostics the reference only logs). */
+typedef struct {
+  uint64_t code;       /* 2-bit code of the winning word */
+  uint32_t freq;       /* KmerFrequency.frequency: live segments containing it when chosen */
+  uint32_t n_tied;     /* how many k-mers shared that frequency (diagnostic) */
+  float tie_score;     /* partition_tie_score of the winner, main.rs:261-283 (diagnostic) */
+  uint32_t reserved;
+} msspe_candidate;
+
+/* How the device-resident greedy loop recomputes frequencies each iteration. Results are identical. */
+#define MSSPE_SELECT_RECOUNT 0     /* re-stream every posting each iteration = main.rs:292-309 */
+#define MSSPE_SELECT_INCREMENTAL 1 /* decrement counts of k-mers in newly covered segments */
+
+/* NtthalOptions, delta_g.rs:18-25 (without the threshold), and Primer3's thal_args. */
+typedef struct {
+  double mv;        /* -mv   monovalent cations, mM */
+  double dv;        /* -dv   divalent cations, mM */
+  double dntp;      /* -n    dNTP, mM */
+  double dna_conc;  /* -d    oligo concentration, nM */
+  double temp_c;    /* -t    temperature for dG, Celsius */
+  int32_t max_loop; /* -maxloop, Primer3 default 30 */
+  int32_t reserved;
+} msspe_thal_cond;
+
+#define MSSPE_THAL_ANY 1      /* ntthal -a ANY   (delta_g.rs:95) */
+#define MSSPE_THAL_END1 2     /* ntthal -a END1 */
+#define MSSPE_THAL_HAIRPIN 4  /* ntthal -a HAIRPIN */
+
+/* Result of one thermodynamic alignment; the numbers ntthal prints (delta_g.rs:27-59 reads dG). */
+typedef struct {
+  double ds;            /* dS incl. salt correction, cal/(K mol) */
+  double dh;            /* dH, cal/mol */
+  double dg;            /* dG at cond.temp_c, cal/mol */
+  double tm;            /* melting temperature, Celsius */
+  int32_t no_structure; /* 1 = "No secondary structure could be calculated" */
+  int32_t n_bp;         /* paired bases counted by the traceback */
+} msspe_thal_out;
+
+/* Nearest-neighbour tables in the file order of a primer3_config directory (delta_g.rs:90,107).
+ * "inf" entries are INFINITY.  loops_*: 30 rows of (interior, bulge, hairpin). */
+typedef struct {
+  double stack_ds[256], stack_dh[256];
+  double stackmm_ds[256], stackmm_dh[256];
+  double dangle_ds[128], dangle_dh[128];
+  double loops_ds[90], loops_dh[90];
+  double tstack_ds[256], tstack_dh[256];   /* tstack_tm_inf.ds + tstack.dh */
+  double tstack2_ds[256], tstack2_dh[256];
+  int32_t n_triloop_ds;  char triloop_ds_seq[32][8];   double triloop_ds[32];
+  int32_t n_triloop_dh;  char triloop_dh_seq[32][8];   double triloop_dh[32];
+  int32_t n_tetraloop_ds; char tetraloop_ds_seq[128][8]; double tetraloop_ds[128];
+  int32_t n_tetraloop_dh; char tetraloop_dh_seq[128][8]; double tetraloop_dh[128];
+} msspe_thal_raw_params;
+
+/* A cross-dimer pair the host must look at: pair = a * n + b (row-major, a-major like delta_g.rs:64-78). */
+typedef struct {
+  uint64_t pair;
+  double dg;           /* raw FP64 dG; the host applies ntthal's "%g" -> f32 round trip */
+} msspe_dimer_edge;
+
+/* Per-stage device times of the last call of each kind, milliseconds (CUDA events on the ctx stream). */
+typedef struct {
+  float h2d_ms;        /* genome upload */
+  float encode_ms;     /* K1 window slice + 2-bit encode + per-window dedup */
+  float index_ms;      /* K2 radix sort + CSR inverted index + forward index */
+  float select_ms[2];  /* K3 greedy loop, per direction */
+  float thermo_ms;     /* K4 oligotm + K5 self-dimers + K6 hairpin */
+  float dimer_ms;      /* K5 all-pairs dimer */
+  uint64_t select_evals[2];        /* sum over iterations of live (segment,k-mer) records = main.rs:302-307 executions */
+  uint64_t select_postings_read[2];/* physical postings streamed by the count kernel */
+  uint32_t select_iterations[2];
+  uint32_t kernel_launches;        /* launches of this library's kernels since the last reset */
+  float count_kernel_ms[2];        /* total device time inside the count/score kernel (when profiling is on) */
+  uint32_t count_kernel_launches[2];
+} msspe_timing;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+int msspe_abi_version(void);
+/* Replaces: process start-up of main.rs:596-629 for this path.  Panics of main.rs:201-203 / step_by(0)
+ * become MSSPE_ERR_INVALID. */
+int msspe_create(const msspe_config* cfg, msspe_ctx** out);
+void msspe_destroy(msspe_ctx* ctx);
+const char* msspe_last_error(const msspe_ctx* ctx); /* ctx may be NULL: error of the last failed create */
+/* Run on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the ctx's own stream. */
+int msspe_set_stream(msspe_ctx* ctx, void* cuda_stream);
+int msspe_synchronize(msspe_ctx* ctx);
+int msspe_get_timing(msspe_ctx* ctx, msspe_timing* out);
+int msspe_reset_timing(msspe_ctx* ctx);
+int msspe_set_profiling(msspe_ctx* ctx, int on); /* per-kernel event timing of the count kernel */
+
+/* ---- (a) segments and inverted index ------------------------------------------------------- */
+/* Replaces get_segment_manager, main.rs:196-235 (input side).  `bases` = the records' sequences
+ * concatenated (already upper-cased with U->T as to_records does, main.rs:108-122; the engine also
+ * accepts lower case and U), offsets[n+1] delimit them.  Host memory; copied to the device. */
+int msspe_load_genomes(msspe_ctx* ctx, const uint8_t* bases, const uint64_t* offsets, uint32_t n_records);
+/* Same, but `d_bases` is already resident in device memory on ctx's device (offsets stay host). */
+int msspe_load_genomes_device(msspe_ctx* ctx, const uint8_t* d_bases, const uint64_t* offsets, uint32_t n_records);
+/* K1 + K2: slice windows, encode, dedup per (segment,direction), sort, build CSR postings + forward
+ * index for both directions.  Replaces main.rs:205-232 and make_kmer_segments_windows_mapping :237-255. */
+int msspe_build_index(msspe_ctx* ctx);
+/* n_segments = SegmentManager.segments.len(); max_partition = main.rs:694-699 (0 if no segment). */
+int msspe_segment_info(msspe_ctx* ctx, uint64_t* n_segments, uint32_t* max_partition, uint32_t* slots_per_window);
+/* Segment.kmers[dir] as a dense [segment][slot] table, MSSPE_NO_KMER for invalid/duplicate slots. */
+int msspe_get_segment_kmers(msspe_ctx* ctx, uint8_t dir, uint64_t* codes, uint64_t capacity);
+/* The inverted index of main.rs:237-255: n_codes distinct words (ascending), offsets[n_codes+1], postings
+ * (ascending segment index inside each list).  Pass NULL buffers to query sizes only. */
+int msspe_get_index(msspe_ctx* ctx, uint8_t dir, uint64_t* n_codes, uint64_t* n_postings,
+                    uint64_t* codes, uint64_t* offsets, uint32_t* postings);
+
+/* ---- (b)(c) greedy selection ---------------------------------------------------------------- */
+/* Replaces find_candidates_kmers, main.rs:331-406, for one direction.  out has capacity max_iterations. */
+int msspe_select(msspe_ctx* ctx, uint8_t dir, uint32_t max_iterations, uint32_t max_mismatch_segments,
+                 uint32_t mode, msspe_candidate* out, uint32_t* n_out);
+/* Both directions (main.rs:709-714) overlapped on the device. */
+int msspe_select_both(msspe_ctx* ctx, uint32_t max_iterations, uint32_t max_mismatch_segments, uint32_t mode,
+                      msspe_candidate* out_fwd, uint32_t* n_fwd, msspe_candidate* out_rev, uint32_t* n_rev);
+/* Device side of print_coverage_report, main.rs:518-537: covered[g] = 1 iff segment g holds a selected
+ * fwd k-mer in its head set or a selected rev k-mer in its tail set.  partition_no[g] as main.rs:227. */
+int msspe_coverage(msspe_ctx* ctx, const uint64_t* fwd_codes, uint32_t n_fwd, const uint64_t* rev_codes,
+                   uint32_t n_rev, uint8_t* covered, uint16_t* partition_no, uint32_t* record_of_segment,
+                   uint64_t capacity);
+
+/* ---- (d) thermodynamics --------------------------------------------------------------------- */
+/* Replaces `-path <cwd>/primer3_config/` (delta_g.rs:90).  Default = tables embedded at build time. */
+int msspe_thal_params_default(msspe_thal_raw_params* out);
+int msspe_thal_params_from_dir(const char* dir, msspe_thal_raw_params* out, char* err, size_t err_len);
+int msspe_set_thal_params(msspe_ctx* ctx, const msspe_thal_raw_params* p);
+/* Replaces check_primers, primer.rs:143-166 (one primer3_core run): per primer the five numbers
+ * parse_primer3_output reads (primer.rs:67-114), as raw FP64 before Primer3's "%.3f"/"%.2f" printing:
+ * tm = oligotm at Primer3 defaults, gc = percent, self_any/self_end/hairpin = max(0, thal Tm). */
+int msspe_primer_thermo(msspe_ctx* ctx, const uint64_t* codes, uint32_t n, uint32_t oligo_len, double* tm,
+                        double* gc, double* self_any, double* self_end, double* hairpin);
+/* Arbitrary pair list through thal (type = MSSPE_THAL_*); a[i], b[i] are 2-bit codes of length oligo_len.
+ * For HAIRPIN b is ignored.  One ntthal invocation per pair in the reference (delta_g.rs:93-113). */
+int msspe_thal_pairs(msspe_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t n_pairs, uint32_t oligo_len,
+                     int32_t type, const msspe_thal_cond* cond, msspe_thal_out* out);
+/* Replaces run_ntthal, delta_g.rs:83-153, for rows [row_begin,row_end) of the n x n ordered-pair matrix
+ * (all pairs incl. self, a-major, delta_g.rs:64-78).  Emits every pair with dG < dg_limit (caller passes
+ * threshold + margin and finishes the "%g"/f32 comparison, delta_g.rs:33-36) and every pair without a
+ * structure (needed to emulate the 5-line parser, delta_g.rs:31-56).  Lists are sorted by pair index. */
+int msspe_cross_dimer(msspe_ctx* ctx, const uint64_t* codes, uint32_t n, uint32_t oligo_len,
+                      const msspe_thal_cond* cond, uint32_t row_begin, uint32_t row_end, double dg_limit,
+                      msspe_dimer_edge* edges, uint64_t edge_capacity, uint64_t* n_edges,
+                      uint64_t* nostruct_pairs, uint64_t nostruct_capacity, uint64_t* n_nostruct);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OD_MSSPE_B200_H */

@@ -1,0 +1,58 @@
+"""Pins the thermodynamic oracle (oracle/thal_oracle.c) to every known-answer vector the reference holds."""
+import pytest
+
+# delta_g.rs:197-230 -- five real ntthal outputs (dS, dH, dG, t); conditions recovered in SURVEY.md App. B:
+# -mv 50 -dv 3 -n 0 -d 250, vectors 1-2 at 37 C, 3-5 at 25 C.
+NTTHAL_GOLDEN = [
+    ("AGGCCTATATCCA", "GAAGCAGTATTTT", 37.0, "-75.3988", "-25700", "-2315.07", "-35.9834"),
+    ("GCACTTGATGTGA", "GAAGCAGTATTTT", 37.0, "-65.3976", "-22500", "-2216.94", "-44.4018"),
+    ("CTGAAGCAGTATT", "GCATCTTTCCCTT", 25.0, "-101.596", "-33500", "-3209.05", "-24.1908"),
+    ("CTGAAGCAGTATT", "AATTGTGTGGATT", 25.0, "-54.2976", "-17700", "-1511.18", "-70.3113"),
+    ("AGTCCTGCGTGAT", "TGGCCTACATCAG", 25.0, "-141.872", "-45800", "-3500.74", "-11.1906"),
+]
+
+
+@pytest.mark.parametrize("a,b,t,ds,dh,dg,tm", NTTHAL_GOLDEN)
+def test_ntthal_golden_blocks(oracle_lib, a, b, t, ds, dh, dg, tm):
+    O = oracle_lib
+    o = O.thal(a, b, 1, O.ThalCond(50, 3, 0, 250, t, 30, 0))
+    assert o.no_structure == 0
+    # ntthal prints with "%g": compare the printed text, i.e. 6 significant digits
+    assert ("%g" % o.ds, "%g" % o.dh, "%g" % o.dg, "%g" % o.tm) == (ds, dh, dg, tm)
+
+
+def test_primer3_check_primers_kat(oracle_lib):
+    """primer.rs:238-250: AGCCCGTGTAAAC -> tm 43.727 gc 53.846 self_any 0.00 self_end 0.00 hairpin 0.00."""
+    O = oracle_lib
+    p = "AGCCCGTGTAAAC"
+    assert "%.3f" % O.oligotm(p) == "43.727"
+    assert "%.3f" % O.gc_percent(p) == "53.846"
+    c = O.ThalCond(50, 1.5, 0.6, 50, 37.0, 30, 0)
+    for ttype in (1, 2, 4):
+        o = O.thal(p, p, ttype, c)
+        assert "%.2f" % max(0.0, o.tm) == "0.00"
+
+
+def test_no_structure_when_no_complementary_letters(oracle_lib):
+    O = oracle_lib
+    c = O.ThalCond(50, 3, 0, 250, 25.0, 30, 0)
+    assert O.thal("AACCACACACCAA", "CACACAACCACAC", 1, c).no_structure == 1
+    assert O.thal("AACCACACACCAA", "GTGTGGTTGTGTG", 1, c).no_structure == 0
+
+
+def test_order_matters_and_param_dir_equals_embedded(oracle_lib, tmp_path):
+    """(a,b) and (b,a) are distinct alignments (delta_g.rs:64-78 evaluates both)."""
+    O = oracle_lib
+    c = O.ThalCond(50, 3, 0, 250, 25.0, 30, 0)
+    x = O.thal("AGTCCTGCGTGAT", "TGGCCTACATCAG", 1, c)
+    y = O.thal("TGGCCTACATCAG", "AGTCCTGCGTGAT", 1, c)
+    assert x.no_structure == 0 and y.no_structure == 0
+    assert abs(x.dg - y.dg) < 1e-6 or x.dg != y.dg  # both legal; just make sure both run
+
+
+def test_hairpin_forms_for_a_clear_stem_loop(oracle_lib):
+    """Parity unpinned (no reference vector): sanity only -- a GC-rich 6 bp stem must melt far above 24 C."""
+    O = oracle_lib
+    c = O.ThalCond(50, 1.5, 0.6, 50, 37.0, 30, 0)
+    o = O.thal("GCGCGCTTTTGCGCGC", "", 4, c)
+    assert o.no_structure == 0 and o.tm > 60.0 and o.n_bp >= 5
