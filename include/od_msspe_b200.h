@@ -40,14 +40,14 @@ extern "C" {
 #define MSSPE_DIR_REV 1            /* constants.rs:23 SEQ_DIR_REV */
 
 #define MSSPE_NO_KMER UINT64_MAX   /* sentinel slot: invalid (non-ACGT) or duplicate within the window */
-#define MSSPE_MAX_KMER 32
+#define MSSPE_MAX_KMER 31         /* 2-bit codes in a u64 with UINT64_MAX free as the sentinel */
 #define MSSPE_MAX_OLIGO 32         /* thal kernels: oligo length limit (reference uses 13..15) */
 
 typedef struct msspe_ctx msspe_ctx;
 
 /* PartitioningOption, main.rs:189-194, plus device selection. */
 typedef struct {
-  uint32_t kmer_size;           /* --kmer-size            (config.rs:20)  1..32 */
+  uint32_t kmer_size;           /* --kmer-size            (config.rs:20)  1..31 */
   uint32_t window_size;         /* --window-size          (config.rs:23)  segment length W */
   uint32_t overlap_size;        /* --overlap-size         (config.rs:26)  used as the STEP (main.rs:178) */
   uint32_t search_windows_size; /* --search-windows-size  (config.rs:39)  head/tail width w */

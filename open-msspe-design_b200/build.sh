@@ -1,0 +1,12 @@
+#!/usr/bin/env bash
+# Builds libodmsspe_b200.so (CUDA kernels + C ABI) for sm_100a, in-tree.
+# -fmad=false / -ffp-contract=off: FP64 thermodynamics must round like scalar C without FMA contraction.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+OUT="$HERE/libodmsspe_b200.so"
+SRCS=("$HERE"/csrc/ctx.cu "$HERE"/csrc/kmer_build.cu "$HERE"/csrc/select.cu "$HERE"/csrc/thal_params.cu "$HERE"/csrc/thal.cu)
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false \
+  -Xcompiler -fPIC,-ffp-contract=off,-Wall,-Wno-unused-function ${MSSPE_PTXAS_V:+-Xptxas -v} \
+  -shared -o "$OUT" "${SRCS[@]}" -lcudart
+echo "built $OUT"

@@ -1,0 +1,116 @@
+// engine.cuh -- internal declarations shared by the translation units of libodmsspe_b200.so.
+// Nothing here is part of the ABI (that is include/od_msspe_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/od_msspe_b200.h"
+
+#define MSSPE_CUDA_TRY(ctx, expr)                                                                       \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      (ctx)->set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);     \
+      return MSSPE_ERR_CUDA;                                                                            \
+    }                                                                                                   \
+  } while (0)
+
+// One direction's inverted index + greedy state, all device-resident.
+struct DirIndex {
+  uint64_t n_records = 0;     // R: valid (segment, k-mer) records
+  uint64_t n_codes = 0;       // D: distinct words
+  uint64_t* codes = nullptr;  // [D] ascending 2-bit codes
+  uint32_t* post_off = nullptr;  // [D+1] CSR offsets into postings
+  uint32_t* postings = nullptr;  // [R] segment ids, ascending inside each list
+  uint32_t* fwd_ids = nullptr;   // [G*s] code id per (segment, slot), 0xFFFFFFFF if none (forward index)
+  // greedy state
+  uint32_t* freq = nullptr;      // [D] live count per code
+  unsigned long long* acc = nullptr;  // [D] arrival-counter|partial-sum for lists that span count tiles
+  uint32_t* ignored = nullptr;   // [ceil(G/32)] covered-segment bitmask
+  uint32_t* cov = nullptr;       // [65536] partition_coverage
+  uint32_t* pmark = nullptr;     // [2048] scratch partition bitmap
+  struct SelectCtl* ctl = nullptr;  // device control block
+  msspe_candidate* out = nullptr;   // [max_iterations] winners, device
+  uint32_t out_capacity = 0;
+  uint32_t* tile_first = nullptr;   // [n_tiles] first code whose postings reach into each count tile
+  uint32_t n_tiles = 0;
+};
+
+constexpr int MSSPE_CNT_THREADS = 512, MSSPE_CNT_ITEMS = 16, MSSPE_CNT_TILE = MSSPE_CNT_THREADS * MSSPE_CNT_ITEMS;
+
+// Device control block of the greedy loop (one per direction).
+struct SelectCtl {
+  unsigned int gmax;               // max live frequency of this iteration
+  unsigned int n_tied;
+  unsigned long long best_key;     // (f32 score bits << 32) | ~code_id
+  unsigned int done;               // 1 = loop finished
+  unsigned int n_out;              // winners pushed
+  unsigned int iterations;         // find_most_freq_kmer calls made
+  unsigned int pad;
+  unsigned long long evals;        // sum of live records counted (reference inner-loop executions)
+  unsigned long long postings_read;
+};
+
+struct msspe_ctx {
+  msspe_config cfg{};
+  int device = 0;
+  int sm_count = 148;
+  size_t smem_optin = 48 * 1024;
+  cudaStream_t stream = nullptr;      // main stream (own or caller's)
+  cudaStream_t stream2 = nullptr;     // second direction
+  bool own_stream = true;
+  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::string err;
+  // genomes
+  uint32_t n_records = 0;
+  std::vector<uint64_t> h_offsets;    // [n+1]
+  std::vector<uint64_t> h_seg_base;   // [n+1] first segment index of each record
+  uint8_t* d_bases = nullptr;         // device bases (owned unless borrowed)
+  bool bases_borrowed = false;
+  uint64_t bases_bytes = 0;
+  uint64_t* d_offsets = nullptr;      // [n+1]
+  uint64_t* d_seg_base = nullptr;     // [n+1]
+  uint64_t n_segments = 0;            // G
+  uint32_t slots = 0;                 // s = w - k + 1
+  uint32_t max_partition = 0;
+  uint16_t* d_seg_part = nullptr;     // [G]
+  uint32_t* d_seg_rec = nullptr;      // [G]
+  bool loaded = false, built = false;
+  DirIndex dir[2];
+  // thermodynamic tables
+  msspe_thal_raw_params raw{};
+  bool raw_set = false;
+  struct ThalDeviceTables* d_thal = nullptr;  // device copy of static tables
+  // pinned staging
+  SelectCtl* h_ctl = nullptr;  // [2] pinned
+  msspe_timing timing{};
+  bool profiling = false;
+
+  void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+  }
+};
+
+// ---- device scan / sort utilities (kmer_build.cu) ----
+int msspe_exclusive_scan_u32(msspe_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* d_total,
+                             cudaStream_t st);
+
+// ---- stages ----
+int msspe_free_index(msspe_ctx* ctx);
+int msspe_select_prepare_static(msspe_ctx* ctx, int dir, cudaStream_t st);  // select.cu: tile tables
+int msspe_thal_upload_tables(msspe_ctx* ctx);
+void msspe_thal_free_tables(msspe_ctx* ctx);
+
+static inline uint64_t div_up_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }

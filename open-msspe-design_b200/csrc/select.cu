@@ -1,0 +1,487 @@
+// select.cu -- K3: the device-resident greedy set-cover loop.  Replaces find_candidates_kmers
+// (od-msspe/src/main.rs:331-406), find_most_freq_kmer (:285-329) and partition_tie_score (:261-283).
+//
+// Per iteration (one find_most_freq_kmer call of the reference) three kernels run back to back on one stream,
+// with no host round trip; a device-side `done` flag turns the remaining launches of a batch into no-ops:
+//   count_kernel   streams the CSR postings once (4 B per (segment,k-mer) record, 128-bit coalesced loads),
+//                  gathers the covered-segment bit of every posting from a shared-memory copy of the bitmask,
+//                  reduces per k-mer (segmented sum via a tile prefix), writes freq[], and atomically maxes the
+//                  best frequency.  This is the reference's recount, main.rs:292-309: one "coverage eval" per
+//                  live record.  HBM/L2-bound: algorithmic traffic 4 B per record.
+//   tie_kernel     scans freq[] for k-mers at the maximum and computes the partition-diversity score of each
+//                  with one warp per tied k-mer: sequential f32 adds in postings order over first-seen live
+//                  partitions, exactly main.rs:268-281; atomicMax on (score bits, ~code id) implements
+//                  `s1.partial_cmp(s2).then(k2.word.cmp(&k1.word))` under max_by (main.rs:320-324).
+//   update_kernel  applies main.rs:353-390: stop tests, push, mark every posting of the winner covered,
+//                  partition_coverage += 1 for each distinct partition of those postings.
+// MSSPE_SELECT_INCREMENTAL replaces count_kernel after the first iteration by decrements of freq[] through the
+// forward index for the newly covered segments (identical results, far less traffic).
+#include "engine.cuh"
+
+namespace {
+
+constexpr int CNT_THREADS = MSSPE_CNT_THREADS, CNT_ITEMS = MSSPE_CNT_ITEMS, CNT_TILE = MSSPE_CNT_TILE;  // 8192 postings = 32 KB
+constexpr int TIE_THREADS = 256, UPD_THREADS = 1024;
+
+__device__ __forceinline__ unsigned int ld_volatile(const unsigned int* p) { return *reinterpret_cast<const volatile unsigned int*>(p); }
+
+__global__ void tile_first_kernel(const uint32_t* __restrict__ post_off, uint32_t n_codes, uint32_t n_tiles,
+                                  uint32_t* __restrict__ tile_first) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const uint32_t start = t * (uint32_t)CNT_TILE;
+  uint32_t lo = 0, hi = n_codes;  // post_off[lo] <= start < post_off[hi]
+  while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (post_off[mid] <= start) lo = mid; else hi = mid; }
+  tile_first[t] = lo;
+}
+
+template <bool SMEM_MASK>
+__global__ void __launch_bounds__(CNT_THREADS)
+count_kernel(const uint32_t* __restrict__ postings, const uint32_t* __restrict__ post_off,
+             const uint32_t* __restrict__ tile_first, uint32_t n_codes, uint32_t n_post, uint32_t n_tiles,
+             const uint32_t* __restrict__ ignored, uint32_t mask_words, uint32_t* __restrict__ freq,
+             unsigned long long* __restrict__ acc, SelectCtl* ctl) {
+  if (ld_volatile(&ctl->done)) return;
+  extern __shared__ uint32_t smask[];
+  __shared__ __align__(16) uint8_t nib[CNT_TILE / 4];
+  __shared__ uint16_t bits[CNT_THREADS];
+  __shared__ uint32_t tbase[CNT_THREADS + 1];
+  __shared__ uint32_t wsum[CNT_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (SMEM_MASK) {
+    for (uint32_t i = tid; i < mask_words; i += CNT_THREADS) smask[i] = ignored[i];
+    __syncthreads();
+  }
+  const uint32_t* mask = SMEM_MASK ? smask : ignored;
+  uint32_t mymax = 0;
+  unsigned long long live_total = 0;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t tile_start = tile * (uint32_t)CNT_TILE;
+    const uint32_t tile_end = min(n_post, tile_start + (uint32_t)CNT_TILE);
+    // phase 1: coalesced 128-bit loads; one live-bit nibble per uint4
+#pragma unroll
+    for (int j = 0; j < CNT_ITEMS / 4; j++) {
+      const uint32_t n = j * CNT_THREADS + tid;
+      const uint32_t pos = tile_start + 4u * n;
+      uint32_t nibble = 0;
+      if (pos + 3u < tile_end) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(postings + pos));
+        nibble = ((~mask[v.x >> 5] >> (v.x & 31u)) & 1u) | (((~mask[v.y >> 5] >> (v.y & 31u)) & 1u) << 1) |
+                 (((~mask[v.z >> 5] >> (v.z & 31u)) & 1u) << 2) | (((~mask[v.w >> 5] >> (v.w & 31u)) & 1u) << 3);
+      } else {
+        for (uint32_t e = 0; e < 4u; e++)
+          if (pos + e < tile_end) { const uint32_t s = postings[pos + e]; nibble |= ((~mask[s >> 5] >> (s & 31u)) & 1u) << e; }
+      }
+      nib[n] = (uint8_t)nibble;
+    }
+    __syncthreads();
+    // phase 2: per-thread 16-posting bit groups and their exclusive prefix over the tile
+    const uint32_t wv = *reinterpret_cast<const uint32_t*>(&nib[4 * tid]);
+    const uint32_t b16 = (wv & 0xFu) | (((wv >> 8) & 0xFu) << 4) | (((wv >> 16) & 0xFu) << 8) | (((wv >> 24) & 0xFu) << 12);
+    const uint32_t cnt = __popc(b16);
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t ws = lane < CNT_THREADS / 32 ? wsum[lane] : 0u, wi = ws;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+      if (lane < CNT_THREADS / 32) wsum[lane] = wi - ws;
+      if (lane == CNT_THREADS / 32 - 1) tbase[CNT_THREADS] = wi;
+    }
+    __syncthreads();
+    bits[tid] = (uint16_t)b16;
+    tbase[tid] = wsum[warp] + inc - cnt;
+    __syncthreads();
+    if (tid == 0) live_total += tbase[CNT_THREADS];
+    // phase 3: per-k-mer sums from prefix differences
+    for (uint32_t c = tile_first[tile] + tid; c < n_codes; c += CNT_THREADS) {
+      const uint32_t a = post_off[c];
+      if (a >= tile_end) break;
+      const uint32_t b = post_off[c + 1];
+      const uint32_t lo = max(a, tile_start) - tile_start, hi = min(b, tile_end) - tile_start;
+      const uint32_t plo = tbase[lo >> 4] + __popc((uint32_t)bits[lo >> 4] & ((1u << (lo & 15u)) - 1u));
+      const uint32_t phi = hi == (uint32_t)CNT_TILE ? tbase[CNT_THREADS]
+                                                    : tbase[hi >> 4] + __popc((uint32_t)bits[hi >> 4] & ((1u << (hi & 15u)) - 1u));
+      const uint32_t sum = phi - plo;
+      if (a >= tile_start && b <= tile_end) {
+        freq[c] = sum;
+        mymax = max(mymax, sum);
+      } else {  // list spans tiles: the last arriving tile owns the total
+        const uint32_t first_tile = a / (uint32_t)CNT_TILE;
+        const uint32_t parts = (b - 1u) / (uint32_t)CNT_TILE - first_tile + 1u;
+        const unsigned long long old = atomicAdd(&acc[first_tile], (1ull << 32) | (unsigned long long)sum);
+        if ((uint32_t)(old >> 32) + 1u == parts) {
+          const uint32_t total = (uint32_t)old + sum;
+          freq[c] = total;
+          acc[first_tile] = 0ull;
+          mymax = max(mymax, total);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // block max -> global max
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
+  if (lane == 0) wsum[warp] = mymax;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t m = 0;
+    for (int w2 = 0; w2 < CNT_THREADS / 32; w2++) m = max(m, wsum[w2]);
+    if (m) atomicMax(&ctl->gmax, m);
+    if (live_total) atomicAdd(&ctl->evals, live_total);
+  }
+}
+
+// max over freq[] (incremental mode: freq is maintained by decrements, so only the max is needed)
+__global__ void __launch_bounds__(256)
+freq_max_kernel(const uint32_t* __restrict__ freq, uint32_t n_codes, SelectCtl* ctl) {
+  if (ld_volatile(&ctl->done)) return;
+  uint32_t m = 0;
+  unsigned long long s = 0;
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_codes; c += gridDim.x * blockDim.x) {
+    const uint32_t f = freq[c]; m = max(m, f); s += f;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  }
+  if ((threadIdx.x & 31) == 0) { if (m) atomicMax(&ctl->gmax, m); if (s) atomicAdd(&ctl->evals, s); }
+}
+
+// Warp-cooperative partition_tie_score (main.rs:261-283) of code c.  `seen` = this warp's partition bitmap.
+__device__ float warp_tie_score(uint32_t c, const uint32_t* __restrict__ post_off, const uint32_t* __restrict__ postings,
+                                const uint32_t* __restrict__ ignored, const uint16_t* __restrict__ seg_part,
+                                const uint32_t* __restrict__ cov, uint32_t* seen, uint32_t p_words, int lane) {
+  for (uint32_t w = lane; w < p_words; w += 32) seen[w] = 0u;
+  __syncwarp();
+  const uint32_t a = post_off[c], b = post_off[c + 1];
+  float score = 0.0f;
+  for (uint32_t base = a; base < b; base += 32) {
+    const uint32_t i = base + lane;
+    const bool valid = i < b;
+    const uint32_t seg = valid ? postings[i] : 0u;
+    const bool live = valid && !((ignored[seg >> 5] >> (seg & 31u)) & 1u);
+    const uint32_t p = live ? (uint32_t)seg_part[seg] : 0xFFFF0000u + (uint32_t)lane;
+    const unsigned peers = __match_any_sync(0xffffffffu, p);
+    const bool first = live && (lane == __ffs(peers) - 1);
+    const bool isnew = first && !((seen[p >> 5] >> (p & 31u)) & 1u);
+    const unsigned newmask = __ballot_sync(0xffffffffu, isnew);
+    float term = 0.0f;
+    if (isnew) {
+      atomicOr(&seen[p >> 5], 1u << (p & 31u));
+      term = __fdiv_rn(1.0f, __fadd_rn(__uint2float_rn(cov[p]), 1.0f));  // 1.0 / (already_covered as f32 + 1.0)
+    }
+    __syncwarp();
+    unsigned mm = newmask;
+    while (mm) {  // score += term, strictly in postings order
+      const int l = __ffs(mm) - 1;
+      mm &= mm - 1;
+      score = __fadd_rn(score, __shfl_sync(0xffffffffu, term, l));
+    }
+  }
+  return score;
+}
+
+__global__ void __launch_bounds__(TIE_THREADS)
+tie_kernel(const uint32_t* __restrict__ freq, uint32_t n_codes, const uint32_t* __restrict__ post_off,
+           const uint32_t* __restrict__ postings, const uint32_t* __restrict__ ignored,
+           const uint16_t* __restrict__ seg_part, const uint32_t* __restrict__ cov, SelectCtl* ctl, uint32_t p_words) {
+  if (ld_volatile(&ctl->done)) return;
+  const uint32_t gmax = ld_volatile(&ctl->gmax);
+  if (gmax == 0) return;
+  extern __shared__ uint32_t seen_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* seen = seen_all + (size_t)warp * p_words;
+  const uint32_t n_chunks = (n_codes + 31u) / 32u;
+  const uint32_t warps_total = gridDim.x * (TIE_THREADS / 32);
+  for (uint32_t chunk = blockIdx.x * (TIE_THREADS / 32) + warp; chunk < n_chunks; chunk += warps_total) {
+    const uint32_t c = chunk * 32u + lane;
+    const bool tied = c < n_codes && freq[c] == gmax;
+    unsigned m = __ballot_sync(0xffffffffu, tied);
+    if (m == 0) continue;
+    if (lane == 0) atomicAdd(&ctl->n_tied, (unsigned)__popc(m));
+    while (m) {
+      const int l = __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t cc = chunk * 32u + l;
+      const float score = warp_tie_score(cc, post_off, postings, ignored, seg_part, cov, seen, p_words, lane);
+      if (lane == 0) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(score) << 32) | (unsigned long long)(0xFFFFFFFFu - cc);
+        atomicMax(&ctl->best_key, key);
+      }
+    }
+  }
+}
+
+template <bool INCREMENTAL>
+__global__ void __launch_bounds__(UPD_THREADS)
+update_kernel(const uint64_t* __restrict__ codes, const uint32_t* __restrict__ post_off,
+              const uint32_t* __restrict__ postings, uint32_t* ignored, const uint16_t* __restrict__ seg_part,
+              uint32_t* cov, uint32_t* pmark, SelectCtl* ctl, msspe_candidate* out, uint32_t max_iterations,
+              uint32_t mms, const uint32_t* __restrict__ fwd_ids, uint32_t slots, uint32_t* freq) {
+  if (ld_volatile(&ctl->done)) return;
+  const uint32_t gmax = ld_volatile(&ctl->gmax);
+  const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(&ctl->best_key);
+  const uint32_t n_tied = ld_volatile(&ctl->n_tied);
+  const uint32_t n_out = ld_volatile(&ctl->n_out);
+  __syncthreads();
+  const bool stop_before = gmax <= 1u;  // None (no live k-mer) or freq == 1: main.rs:353-366
+  if (threadIdx.x == 0) {
+    ctl->iterations += 1;
+    if (stop_before) ctl->done = 1;
+  }
+  if (stop_before) return;
+  const uint32_t c = 0xFFFFFFFFu - (uint32_t)key;
+  const uint32_t a = post_off[c], b = post_off[c + 1];
+  // main.rs:371-378: every posting (also already covered ones) is inserted; distinct partitions get +1
+  for (uint32_t i = a + threadIdx.x; i < b; i += UPD_THREADS) {
+    const uint32_t seg = postings[i];
+    const uint32_t bit = 1u << (seg & 31u);
+    const uint32_t oldw = atomicOr(&ignored[seg >> 5], bit);
+    if (INCREMENTAL && !(oldw & bit)) {  // newly covered: its k-mers lose one live segment
+      for (uint32_t q = 0; q < slots; q++) {
+        const uint32_t id = fwd_ids[(uint64_t)seg * slots + q];
+        if (id != 0xFFFFFFFFu) atomicSub(&freq[id], 1u);
+      }
+    }
+    const uint32_t p = seg_part[seg];
+    const uint32_t pbit = 1u << (p & 31u);
+    const uint32_t old = atomicOr(&pmark[p >> 5], pbit);
+    if (!(old & pbit)) atomicAdd(&cov[p], 1u);
+  }
+  __syncthreads();
+  for (uint32_t i = a + threadIdx.x; i < b; i += UPD_THREADS) pmark[seg_part[postings[i]] >> 5] = 0u;
+  if (threadIdx.x == 0) {
+    msspe_candidate w;
+    w.code = codes[c]; w.freq = gmax; w.n_tied = n_tied; w.tie_score = __uint_as_float((uint32_t)(key >> 32)); w.reserved = 0;
+    out[n_out] = w;
+    ctl->n_out = n_out + 1;
+    if (gmax < mms || n_out + 1 >= max_iterations) ctl->done = 1;  // main.rs:387-390 and the for-loop bound :344
+    ctl->gmax = 0; ctl->best_key = 0ull; ctl->n_tied = 0;
+  }
+}
+
+struct DirRun {
+  DirIndex* D; cudaStream_t st; uint32_t* tile_first; uint32_t n_tiles; bool smem_mask; uint32_t mask_words;
+  unsigned count_grid; size_t count_smem; unsigned tie_grid; size_t tie_smem; uint32_t p_words;
+};
+
+int prepare_dir(msspe_ctx* c, int dir, uint32_t max_iter, cudaStream_t st, DirRun* r) {
+  DirIndex& D = c->dir[dir];
+  r->D = &D; r->st = st;
+  const uint64_t G = c->n_segments;
+  if (D.out_capacity < max_iter) {
+    cudaFree(D.out); D.out = nullptr;
+    MSSPE_CUDA_TRY(c, cudaMalloc(&D.out, (uint64_t)(max_iter ? max_iter : 1) * sizeof(msspe_candidate)));
+    D.out_capacity = max_iter;
+  }
+  r->mask_words = (uint32_t)div_up_u64(G, 32) + 1u;
+  MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.ignored, 0, (size_t)r->mask_words * 4, st));
+  MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.cov, 0, 65536 * 4, st));
+  MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.pmark, 0, 2048 * 4, st));
+  MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.ctl, 0, sizeof(SelectCtl), st));
+  r->n_tiles = D.n_tiles;
+  r->tile_first = D.tile_first;
+  MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.acc, 0, (uint64_t)(r->n_tiles + 1) * 8, st));
+  struct { int multiProcessorCount; size_t sharedMemPerBlockOptin; } prop = {c->sm_count, c->smem_optin};
+  const size_t mask_bytes = (size_t)r->mask_words * 4;
+  r->smem_mask = mask_bytes + 8192 <= (size_t)prop.sharedMemPerBlockOptin;
+  r->count_smem = r->smem_mask ? mask_bytes : 0;
+  int per_sm = 1;
+  if (r->smem_mask) {
+    MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mask_bytes));
+    MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<true>, CNT_THREADS, r->count_smem));
+  } else {
+    MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<false>, CNT_THREADS, 0));
+  }
+  if (per_sm < 1) per_sm = 1;
+  const unsigned resident = (unsigned)prop.multiProcessorCount * (unsigned)per_sm;
+  r->count_grid = r->n_tiles < resident ? r->n_tiles : resident;
+  r->p_words = (c->max_partition + 32u) / 32u;
+  r->tie_smem = (size_t)r->p_words * 4 * (TIE_THREADS / 32);
+  const uint32_t n_chunks = (uint32_t)div_up_u64(D.n_codes, 32);
+  const unsigned tie_blocks = (n_chunks + (TIE_THREADS / 32) - 1) / (TIE_THREADS / 32);
+  r->tie_grid = tie_blocks < (unsigned)prop.multiProcessorCount * 8u ? tie_blocks : (unsigned)prop.multiProcessorCount * 8u;
+  if (r->tie_smem > 48 * 1024)
+    MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(tie_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r->tie_smem));
+  return MSSPE_OK;
+}
+
+void launch_iteration(msspe_ctx* c, DirRun& r, uint32_t max_iter, uint32_t mms, uint32_t mode, bool first) {
+  DirIndex& D = *r.D;
+  const uint32_t nc = (uint32_t)D.n_codes, np = (uint32_t)D.n_records;
+  const bool recount = mode == MSSPE_SELECT_RECOUNT || first;
+  if (recount) {
+    if (r.n_tiles) {
+      if (r.smem_mask)
+        count_kernel<true><<<r.count_grid, CNT_THREADS, r.count_smem, r.st>>>(D.postings, D.post_off, r.tile_first, nc, np, r.n_tiles,
+                                                                               D.ignored, r.mask_words, D.freq, D.acc, D.ctl);
+      else
+        count_kernel<false><<<r.count_grid, CNT_THREADS, 0, r.st>>>(D.postings, D.post_off, r.tile_first, nc, np, r.n_tiles,
+                                                                     D.ignored, r.mask_words, D.freq, D.acc, D.ctl);
+      c->timing.kernel_launches++;
+    }
+  } else if (nc) {
+    freq_max_kernel<<<min(592u, (nc + 255u) / 256u), 256, 0, r.st>>>(D.freq, nc, D.ctl);
+    c->timing.kernel_launches++;
+  }
+  if (nc) {
+    tie_kernel<<<r.tie_grid, TIE_THREADS, r.tie_smem, r.st>>>(D.freq, nc, D.post_off, D.postings, D.ignored, c->d_seg_part, D.cov,
+                                                             D.ctl, r.p_words);
+    c->timing.kernel_launches++;
+  }
+  if (mode == MSSPE_SELECT_INCREMENTAL)
+    update_kernel<true><<<1, UPD_THREADS, 0, r.st>>>(D.codes, D.post_off, D.postings, D.ignored, c->d_seg_part, D.cov, D.pmark, D.ctl,
+                                                      D.out, max_iter, mms, D.fwd_ids, c->slots, D.freq);
+  else
+    update_kernel<false><<<1, UPD_THREADS, 0, r.st>>>(D.codes, D.post_off, D.postings, D.ignored, c->d_seg_part, D.cov, D.pmark, D.ctl,
+                                                       D.out, max_iter, mms, D.fwd_ids, c->slots, D.freq);
+  c->timing.kernel_launches++;
+}
+
+int run_select(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max_iter, uint32_t mms, uint32_t mode,
+               msspe_candidate** outs, uint32_t** n_outs) {
+  if (!c->built) { c->set_error("msspe_select: index not built"); return MSSPE_ERR_STATE; }
+  if (mode > MSSPE_SELECT_INCREMENTAL) { c->set_error("msspe_select: unknown mode %u", mode); return MSSPE_ERR_INVALID; }
+  MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
+  DirRun runs[2];
+  cudaStream_t streams[2] = {c->stream, c->stream2};
+  cudaEvent_t ev_b[2] = {c->ev[2], c->ev[4]}, ev_e[2] = {c->ev[3], c->ev[5]};
+  if (ndirs == 2) {  // fork the second stream off the main one
+    MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev_fork, c->stream));
+    MSSPE_CUDA_TRY(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+  }
+  for (int i = 0; i < ndirs; i++) {
+    MSSPE_CUDA_TRY(c, cudaEventRecord(ev_b[i], streams[i]));
+    int rc = prepare_dir(c, dirs[i], max_iter, streams[i], &runs[i]);
+    if (rc) return rc;
+  }
+  bool finished[2] = {max_iter == 0, max_iter == 0};
+  uint32_t issued = 0;
+  const uint32_t BATCH = 32;
+  while (issued < max_iter && !(finished[0] && (ndirs == 1 || finished[1]))) {
+    const uint32_t nb = (max_iter - issued) < BATCH ? (max_iter - issued) : BATCH;
+    for (uint32_t it = 0; it < nb; it++)
+      for (int i = 0; i < ndirs; i++)
+        if (!finished[i]) launch_iteration(c, runs[i], max_iter, mms, mode, issued + it == 0);
+    issued += nb;
+    for (int i = 0; i < ndirs; i++)
+      if (!finished[i]) MSSPE_CUDA_TRY(c, cudaMemcpyAsync(&c->h_ctl[i], runs[i].D->ctl, sizeof(SelectCtl), cudaMemcpyDeviceToHost, streams[i]));
+    for (int i = 0; i < ndirs; i++)
+      if (!finished[i]) {
+        MSSPE_CUDA_TRY(c, cudaStreamSynchronize(streams[i]));
+        if (c->h_ctl[i].done) finished[i] = true;
+      }
+  }
+  MSSPE_CUDA_TRY(c, cudaGetLastError());
+  for (int i = 0; i < ndirs; i++) {
+    MSSPE_CUDA_TRY(c, cudaMemcpyAsync(&c->h_ctl[i], runs[i].D->ctl, sizeof(SelectCtl), cudaMemcpyDeviceToHost, streams[i]));
+    MSSPE_CUDA_TRY(c, cudaEventRecord(ev_e[i], streams[i]));
+    MSSPE_CUDA_TRY(c, cudaStreamSynchronize(streams[i]));
+    const uint32_t n = c->h_ctl[i].n_out;
+    if (n) MSSPE_CUDA_TRY(c, cudaMemcpy(outs[i], runs[i].D->out, (size_t)n * sizeof(msspe_candidate), cudaMemcpyDeviceToHost));
+    *n_outs[i] = n;
+    const int d = dirs[i];
+    MSSPE_CUDA_TRY(c, cudaEventElapsedTime(&c->timing.select_ms[d], ev_b[i], ev_e[i]));
+    c->timing.select_evals[d] = c->h_ctl[i].evals;
+    c->timing.select_iterations[d] = c->h_ctl[i].iterations;
+    const uint64_t count_launches = mode == MSSPE_SELECT_RECOUNT ? c->h_ctl[i].iterations : (c->h_ctl[i].iterations ? 1 : 0);
+    c->timing.select_postings_read[d] = count_launches * runs[i].D->n_records;
+    c->timing.count_kernel_launches[d] = (uint32_t)count_launches;
+  }
+  if (ndirs == 2) {  // join
+    MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev_join, c->stream2));
+    MSSPE_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  }
+  return MSSPE_OK;
+}
+
+}  // namespace
+
+int msspe_select_prepare_static(msspe_ctx* c, int dir, cudaStream_t st) {
+  DirIndex& D = c->dir[dir];
+  D.n_tiles = (uint32_t)div_up_u64(D.n_records, CNT_TILE);
+  MSSPE_CUDA_TRY(c, cudaMalloc(&D.acc, (uint64_t)(D.n_tiles + 1) * 8));
+  MSSPE_CUDA_TRY(c, cudaMalloc(&D.tile_first, (uint64_t)(D.n_tiles + 1) * 4));
+  if (D.n_tiles) {
+    tile_first_kernel<<<(D.n_tiles + 255) / 256, 256, 0, st>>>(D.post_off, (uint32_t)D.n_codes, D.n_tiles, D.tile_first);
+    c->timing.kernel_launches++;
+    MSSPE_CUDA_TRY(c, cudaGetLastError());
+  }
+  return MSSPE_OK;
+}
+
+extern "C" int msspe_select(msspe_ctx* c, uint8_t dir, uint32_t max_iterations, uint32_t mms, uint32_t mode,
+                            msspe_candidate* out, uint32_t* n_out) {
+  if (!c) return MSSPE_ERR_INVALID;
+  if (dir > 1 || !n_out || (max_iterations && !out)) { c->set_error("msspe_select: bad argument"); return MSSPE_ERR_INVALID; }
+  int dirs[1] = {dir};
+  msspe_candidate* outs[1] = {out};
+  uint32_t* ns[1] = {n_out};
+  *n_out = 0;
+  return run_select(c, 1, dirs, max_iterations, mms, mode, outs, ns);
+}
+
+extern "C" int msspe_select_both(msspe_ctx* c, uint32_t max_iterations, uint32_t mms, uint32_t mode,
+                                 msspe_candidate* out_fwd, uint32_t* n_fwd, msspe_candidate* out_rev, uint32_t* n_rev) {
+  if (!c) return MSSPE_ERR_INVALID;
+  if (!n_fwd || !n_rev || (max_iterations && (!out_fwd || !out_rev))) { c->set_error("msspe_select_both: bad argument"); return MSSPE_ERR_INVALID; }
+  int dirs[2] = {0, 1};
+  msspe_candidate* outs[2] = {out_fwd, out_rev};
+  uint32_t* ns[2] = {n_fwd, n_rev};
+  *n_fwd = *n_rev = 0;
+  return run_select(c, 2, dirs, max_iterations, mms, mode, outs, ns);
+}
+
+// ---- coverage of the final primer set: device side of print_coverage_report (main.rs:518-537) ----
+namespace {
+__global__ void coverage_mark_kernel(const uint64_t* __restrict__ sel, uint32_t n_sel, const uint64_t* __restrict__ codes,
+                                     uint32_t n_codes, const uint32_t* __restrict__ post_off,
+                                     const uint32_t* __restrict__ postings, uint8_t* __restrict__ covered) {
+  const uint32_t s = blockIdx.x;
+  if (s >= n_sel || n_codes == 0) return;
+  const uint64_t want = sel[s];
+  uint32_t lo = 0, hi = n_codes;  // first index with codes[idx] >= want
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (codes[mid] < want) lo = mid + 1; else hi = mid; }
+  if (lo >= n_codes || codes[lo] != want) return;
+  for (uint32_t i = post_off[lo] + threadIdx.x; i < post_off[lo + 1]; i += blockDim.x) covered[postings[i]] = 1;
+}
+}  // namespace
+
+extern "C" int msspe_coverage(msspe_ctx* c, const uint64_t* fwd_codes, uint32_t n_fwd, const uint64_t* rev_codes, uint32_t n_rev,
+                              uint8_t* covered, uint16_t* partition_no, uint32_t* record_of_segment, uint64_t capacity) {
+  if (!c) return MSSPE_ERR_INVALID;
+  if (!c->built) { c->set_error("msspe_coverage: index not built"); return MSSPE_ERR_STATE; }
+  const uint64_t G = c->n_segments;
+  if (capacity < G || (G && !covered)) { c->set_error("msspe_coverage: need capacity for %llu segments", (unsigned long long)G); return MSSPE_ERR_CAPACITY; }
+  if ((n_fwd && !fwd_codes) || (n_rev && !rev_codes)) { c->set_error("msspe_coverage: null argument"); return MSSPE_ERR_INVALID; }
+  if (G == 0) return MSSPE_OK;
+  MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  uint8_t* d_cov = nullptr; uint64_t* d_sel = nullptr;
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&d_cov, G, st));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&d_sel, (size_t)(n_fwd + n_rev + 1) * 8, st));
+  MSSPE_CUDA_TRY(c, cudaMemsetAsync(d_cov, 0, G, st));
+  if (n_fwd) MSSPE_CUDA_TRY(c, cudaMemcpyAsync(d_sel, fwd_codes, (size_t)n_fwd * 8, cudaMemcpyHostToDevice, st));
+  if (n_rev) MSSPE_CUDA_TRY(c, cudaMemcpyAsync(d_sel + n_fwd, rev_codes, (size_t)n_rev * 8, cudaMemcpyHostToDevice, st));
+  for (int d = 0; d < 2; d++) {
+    const uint32_t ns = d == 0 ? n_fwd : n_rev;
+    if (!ns) continue;
+    DirIndex& D = c->dir[d];
+    coverage_mark_kernel<<<ns, 256, 0, st>>>(d_sel + (d == 0 ? 0 : n_fwd), ns, D.codes, (uint32_t)D.n_codes, D.post_off, D.postings, d_cov);
+    c->timing.kernel_launches++;
+  }
+  MSSPE_CUDA_TRY(c, cudaGetLastError());
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(covered, d_cov, G, cudaMemcpyDeviceToHost, st));
+  if (partition_no) MSSPE_CUDA_TRY(c, cudaMemcpyAsync(partition_no, c->d_seg_part, G * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+  if (record_of_segment) MSSPE_CUDA_TRY(c, cudaMemcpyAsync(record_of_segment, c->d_seg_rec, G * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  MSSPE_CUDA_TRY(c, cudaFreeAsync(d_cov, st));
+  MSSPE_CUDA_TRY(c, cudaFreeAsync(d_sel, st));
+  MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+  return MSSPE_OK;
+}

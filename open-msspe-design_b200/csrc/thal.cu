@@ -1,0 +1,1021 @@
+// thal.cu -- K4/K5/K6: nearest-neighbour thermodynamics on the device.
+//   K5 thal_dimer_kernel : Primer3's thermodynamic alignment of two oligos (ntthal -a ANY / END1), the work the
+//                          reference sends to an `ntthal` subprocess pair by pair (od-msspe/src/delta_g.rs:83-153)
+//                          and to primer3_core for SELF_ANY_TH / SELF_END_TH (primer.rs:125-166).
+//   K6 thal_mono_kernel  : hairpin (ntthal -a HAIRPIN / PRIMER_LEFT_0_HAIRPIN_TH).
+//   K4 oligotm_kernel    : PRIMER_LEFT_0_TM (oligotm, SantaLucia 1998 + SantaLucia salt correction at Primer3's
+//                          default concentrations, primer.rs:125-140 passes no salt tags) and GC percent.
+// All arithmetic is FP64 and this file is compiled with -fmad=false so every expression rounds exactly like
+// scalar C without contraction; the tensor cores are not involved (nothing here is a contraction).
+//
+// Dimer kernel design (SM-issue bound, not HBM bound: 16 B in, <= 48 B out per pair):
+//   * a group of 16 lanes (oligos <= 16 nt) or 32 lanes (<= 32 nt) owns one ordered pair; a block holds
+//     8 resp. 4 groups and loops over pairs (persistent grid), so the tables are staged once per block;
+//   * tables in shared memory: stack / 1x1-mismatch / terminal-mismatch (256 entries x S,H each), loop
+//     penalties, and the LEFT/RIGHT end-of-duplex terms pre-tabulated on the host over their 2x2 base
+//     context for this run's RC (they are ~60 % of the scalar algorithm's work when recomputed per use);
+//   * the DP matrix (S,H per cell, k x k x 16 B) lives in shared memory; rows are filled in order; inside a
+//     row the end/stack terms of all cells are computed lane-parallel, then for each paired cell the
+//     bulge/internal-loop candidates are spread over the lanes by inner row and reduced with shuffles to the
+//     first minimum of dG in the scalar scan order (so the result equals the sequential scan);
+//   * best-cell selection, traceback (needed for the salt correction: N paired bases) and dS/dH/dG/Tm follow.
+#include <algorithm>
+#include <cmath>
+
+#include "engine.cuh"
+#include "thal_tables.cuh"
+
+void msspe_thal_expand(const msspe_thal_raw_params* p, ThalDeviceTables* T);
+
+namespace {
+
+constexpr double kR = 1.9872, kAbsZero = 273.15, kTK = 310.15, kMinEntropyCutoff = -2500.0, kMinEntropy = -3224.0;
+constexpr double kSmallNonZero = 0.000001, kDHi = 200.0, kDSi = -5.7;
+#define K_ILAS (-300 / 310.15)
+#define K_ILAH 0.0
+constexpr int DIMER_THREADS = 128;
+
+// ---------------------------------------------------------------- host: per-run end-of-duplex tables
+struct EndSel { double S, H; };
+EndSel end_choice(const ThalDeviceTables& T, double RC, double S1, double H1, bool has_opt, double So, double Ho, int a, int b) {
+  double G1 = H1 - kTK * S1, T1 = -INFINITY, S2, H2, G2, T2;
+  if (!std::isfinite(H1) || G1 > 0) { H1 = INFINITY; S1 = -1.0; G1 = 1.0; }
+  if (has_opt) {
+    S2 = So; H2 = Ho; G2 = H2 - kTK * S2;
+    if (!std::isfinite(H2) || G2 > 0) { H2 = INFINITY; S2 = -1.0; G2 = 1.0; }
+    T2 = (H2 + kDHi) / (S2 + kDSi + RC);
+    if (std::isfinite(H1) && G1 < 0) {
+      T1 = (H1 + kDHi) / (S1 + kDSi + RC);
+      if (T1 < T2 && G2 < 0) { S1 = S2; H1 = H2; T1 = T2; }
+    } else if (G2 < 0) { S1 = S2; H1 = H2; T1 = T2; }
+  }
+  S2 = T.atpS[a * 5 + b]; H2 = T.atpH[a * 5 + b];
+  T2 = (H2 + kDHi) / (S2 + kDSi + RC);
+  if (std::isfinite(H1)) { if (T1 < T2) return {S2, H2}; return {S1, H1}; }
+  return {S2, H2};
+}
+
+void build_dimer_consts(const ThalDeviceTables& T, const msspe_thal_cond& c, ThalDimerConsts* K) {
+  memset(K, 0, sizeof *K);
+  K->RC[0] = kR * log(c.dna_conc / 4000000000.0);
+  K->RC[1] = kR * log(c.dna_conc / 1000000000.0);
+  double dntp = c.dntp;
+  if (c.dv <= 0) dntp = c.dv;
+  K->saltCorr = 0.368 * (log((c.mv + 120 * (sqrt(fmax(0.0, c.dv - dntp)))) / 1000));
+  K->t_user_K = c.temp_c + kAbsZero;
+  K->maxLoop = c.max_loop;
+  for (int sym = 0; sym < 2; sym++)
+    for (int a = 0; a < 4; a++) {
+      const int b = 3 - a;
+      for (int x = 0; x < 5; x++)      // neighbour on strand 1 (i+1 for RIGHT, i-1 for LEFT)
+        for (int y = 0; y < 5; y++) {  // neighbour on strand 2 (j+1 for RIGHT, j-1 for LEFT)
+          const int idx = (a * 5 + x) * 5 + y;
+          const bool nb_pair = (x + y == 3) && x < 4 && y < 4;
+          {  // RIGHT end: tstack2[a][x][b][y], dangle3[a][x][b], dangle5[a][b][y]
+            double S1 = T.atpS[a * 5 + b] + T.tstack2S[THAL_IDX4(a, x, b, y)];
+            double H1 = T.atpH[a * 5 + b] + T.tstack2H[THAL_IDX4(a, x, b, y)];
+            bool has = false; double So = 0, Ho = 0;
+            if (!nb_pair) {
+              const double h3 = T.dangle3H[THAL_IDX3(a, x, b)], h5 = T.dangle5H[THAL_IDX3(a, b, y)];
+              if (std::isfinite(h3) && std::isfinite(h5)) {
+                So = T.atpS[a * 5 + b] + T.dangle3S[THAL_IDX3(a, x, b)] + T.dangle5S[THAL_IDX3(a, b, y)];
+                Ho = T.atpH[a * 5 + b] + h3 + h5; has = true;
+              } else if (std::isfinite(h3)) { So = T.atpS[a * 5 + b] + T.dangle3S[THAL_IDX3(a, x, b)]; Ho = T.atpH[a * 5 + b] + h3; has = true; }
+              else if (std::isfinite(h5)) { So = T.atpS[a * 5 + b] + T.dangle5S[THAL_IDX3(a, b, y)]; Ho = T.atpH[a * 5 + b] + h5; has = true; }
+            }
+            EndSel e = end_choice(T, K->RC[sym], S1, H1, has, So, Ho, a, b);
+            K->rshS[sym][idx] = e.S; K->rshH[sym][idx] = e.H;
+          }
+          {  // LEFT end: tstack2[b][y][a][x], dangle3[b][y][a], dangle5[b][a][x]
+            double S1 = T.atpS[a * 5 + b] + T.tstack2S[THAL_IDX4(b, y, a, x)];
+            double H1 = T.atpH[a * 5 + b] + T.tstack2H[THAL_IDX4(b, y, a, x)];
+            bool has = false; double So = 0, Ho = 0;
+            if (!nb_pair) {
+              const double h3 = T.dangle3H[THAL_IDX3(b, y, a)], h5 = T.dangle5H[THAL_IDX3(b, a, x)];
+              if (std::isfinite(h3) && std::isfinite(h5)) {
+                So = T.atpS[a * 5 + b] + T.dangle3S[THAL_IDX3(b, y, a)] + T.dangle5S[THAL_IDX3(b, a, x)];
+                Ho = T.atpH[a * 5 + b] + h3 + h5; has = true;
+              } else if (std::isfinite(h3)) { So = T.atpS[a * 5 + b] + T.dangle3S[THAL_IDX3(b, y, a)]; Ho = T.atpH[a * 5 + b] + h3; has = true; }
+              else if (std::isfinite(h5)) { So = T.atpS[a * 5 + b] + T.dangle5S[THAL_IDX3(b, a, x)]; Ho = T.atpH[a * 5 + b] + h5; has = true; }
+            }
+            EndSel e = end_choice(T, K->RC[sym], S1, H1, has, So, Ho, a, b);
+            K->lshS[sym][idx] = e.S; K->lshH[sym][idx] = e.H;
+          }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- device: dimer
+struct DimerArgs {
+  const uint64_t* a; const uint64_t* b;  // pair list: a[p], b[p].  matrix: a = b = codes[n]
+  unsigned long long n_pairs;
+  uint32_t n, row_begin;
+  int matrix, k, type;
+  const ThalDeviceTables* T; const ThalDimerConsts* C;
+  msspe_thal_out* out;
+  double dg_limit;
+  msspe_dimer_edge* edges; unsigned long long edge_cap; unsigned long long* n_edges;
+  uint64_t* nostruct; unsigned long long nostruct_cap; unsigned long long* n_nostruct;
+};
+
+struct DimerShared {  // per block
+  double stackS[256], stackH[256], int2S[256], int2H[256], tstS[256], tstH[256];
+  double lshS[2][100], lshH[2][100], rshS[2][100], rshH[2][100];
+  double interiorS[30], interiorH[30], bulgeS[30], bulgeH[30];
+  double atpS[16], atpH[16];
+};
+
+__device__ __forceinline__ int i4(int a, int b, int c, int d) { return (a << 6) | (b << 4) | (c << 2) | d; }
+__device__ __forceinline__ bool eq2(double a, double b) { return isfinite(a) && isfinite(b) && fabs(a - b) < 1e-5; }
+
+struct PairView {  // per group, in shared memory
+  double2* cell;       // [k*k] (S,H)
+  uint32_t* rowmask;   // [k+2]: bit (j-1) set <=> n1[i] pairs with n2[j]
+  uint8_t* n1; uint8_t* n2;  // [k+2]
+  int k;
+};
+
+// (S,H) of the bulge / internal loop closed by (i,j) with inner pair (ii,jj), including the inner cell's value.
+// H = +inf marks "not possible".
+__device__ __forceinline__ void loop_candidate(const DimerShared& sh, const PairView& pv, int i, int j, int ii, int jj,
+                                               double* outS, double* outH) {
+  const uint8_t* n1 = pv.n1; const uint8_t* n2 = pv.n2;
+  const int l1 = i - ii - 1, l2 = j - jj - 1, ls = l1 + l2 - 1;
+  const double2 inner = pv.cell[(ii - 1) * pv.k + (jj - 1)];
+  double S, H;
+  if (l1 == 0 || l2 == 0) {      // bulge (l1 + l2 >= 1 guaranteed by the caller)
+    if (l1 + l2 == 1) {          // size 1: the flanking pairs still stack
+      H = sh.bulgeH[ls] + sh.stackH[i4(n1[ii], n1[i], n2[jj], n2[j])];
+      S = sh.bulgeS[ls] + sh.stackS[i4(n1[ii], n1[i], n2[jj], n2[j])];
+      if (H > 0 || S > 0) { H = INFINITY; S = -1.0; }
+      H += inner.y; S += inner.x;
+      if (!isfinite(H)) { H = INFINITY; S = -1.0; }
+    } else {
+      H = sh.bulgeH[ls] + sh.atpH[n1[ii] * 4 + n2[jj]] + sh.atpH[n1[i] * 4 + n2[j]];
+      H += inner.y;
+      S = sh.bulgeS[ls] + sh.atpS[n1[ii] * 4 + n2[jj]] + sh.atpS[n1[i] * 4 + n2[j]];
+      S += inner.x;
+      if (!isfinite(H)) { H = INFINITY; S = -1.0; }
+      if (H > 0 && S > 0) { H = INFINITY; S = -1.0; }
+    }
+  } else if (l1 == 1 && l2 == 1) {
+    S = sh.int2S[i4(n1[ii], n1[ii + 1], n2[jj], n2[jj + 1])] + sh.int2S[i4(n2[j], n2[j - 1], n1[i], n1[i - 1])];
+    S += inner.x;
+    H = sh.int2H[i4(n1[ii], n1[ii + 1], n2[jj], n2[jj + 1])] + sh.int2H[i4(n2[j], n2[j - 1], n1[i], n1[i - 1])];
+    H += inner.y;
+    if (!isfinite(H)) { H = INFINITY; S = -1.0; }
+    if (H > 0 && S > 0) { H = INFINITY; S = -1.0; }
+  } else {
+    const int asym = l1 > l2 ? l1 - l2 : l2 - l1;
+    H = sh.interiorH[ls] + sh.tstH[i4(n1[ii], n1[ii + 1], n2[jj], n2[jj + 1])] + sh.tstH[i4(n2[j], n2[j - 1], n1[i], n1[i - 1])] +
+        (K_ILAH * asym);
+    H += inner.y;
+    S = sh.interiorS[ls] + sh.tstS[i4(n1[ii], n1[ii + 1], n2[jj], n2[jj + 1])] + sh.tstS[i4(n2[j], n2[j - 1], n1[i], n1[i - 1])] +
+        (K_ILAS * asym);
+    S += inner.x;
+    if (!isfinite(H)) { H = INFINITY; S = -1.0; }
+    if (H > 0 && S > 0) { H = INFINITY; S = -1.0; }
+  }
+  *outS = S; *outH = H;
+}
+
+__device__ __forceinline__ uint64_t revcomp_code(uint64_t code, int k) {
+  uint64_t r = 0;
+  for (int t = 0; t < k; t++) { r = (r << 2) | (3u - (code & 3u)); code >>= 2; }
+  return r;
+}
+
+template <int GROUP>
+__global__ void __launch_bounds__(DIMER_THREADS)
+thal_dimer_kernel(const DimerArgs A) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  DimerShared& sh = *reinterpret_cast<DimerShared*>(dyn_smem);
+  const int k = A.k;
+  const int tid = threadIdx.x;
+  {  // stage tables
+    const ThalDeviceTables* T = A.T;
+    for (int x = tid; x < 256; x += DIMER_THREADS) {
+      const int a = x >> 6, b = (x >> 4) & 3, c = (x >> 2) & 3, d = x & 3;
+      const int g = THAL_IDX4(a, b, c, d);
+      sh.stackS[x] = T->stackS[g]; sh.stackH[x] = T->stackH[g];
+      sh.int2S[x] = T->stackint2S[g]; sh.int2H[x] = T->stackint2H[g];
+      sh.tstS[x] = T->tstackS[g]; sh.tstH[x] = T->tstackH[g];
+    }
+    for (int x = tid; x < 200; x += DIMER_THREADS) {
+      (&sh.lshS[0][0])[x] = (&A.C->lshS[0][0])[x]; (&sh.lshH[0][0])[x] = (&A.C->lshH[0][0])[x];
+      (&sh.rshS[0][0])[x] = (&A.C->rshS[0][0])[x]; (&sh.rshH[0][0])[x] = (&A.C->rshH[0][0])[x];
+    }
+    for (int x = tid; x < 30; x += DIMER_THREADS) {
+      sh.interiorS[x] = T->interiorS[x]; sh.interiorH[x] = T->interiorH[x];
+      sh.bulgeS[x] = T->bulgeS[x]; sh.bulgeH[x] = T->bulgeH[x];
+    }
+    for (int x = tid; x < 16; x += DIMER_THREADS) { sh.atpS[x] = T->atpS[(x >> 2) * 5 + (x & 3)]; sh.atpH[x] = T->atpH[(x >> 2) * 5 + (x & 3)]; }
+  }
+  __syncthreads();
+  constexpr int GROUPS = DIMER_THREADS / GROUP;
+  const int grp = tid / GROUP, gl = tid % GROUP, lane = tid & 31;
+  const unsigned gmask = GROUP == 32 ? 0xffffffffu : (0xFFFFu << (lane & 16));
+  const size_t cell_bytes = (size_t)k * k * sizeof(double2);
+  const size_t grp_bytes = (cell_bytes + (size_t)(k + 2) * 4 + 2 * (size_t)(k + 2) + 15) & ~(size_t)15;
+  unsigned char* gbase = dyn_smem + ((sizeof(DimerShared) + 15) & ~(size_t)15) + grp * grp_bytes;
+  PairView pv;
+  pv.cell = reinterpret_cast<double2*>(gbase);
+  pv.rowmask = reinterpret_cast<uint32_t*>(gbase + cell_bytes);
+  pv.n1 = reinterpret_cast<uint8_t*>(pv.rowmask + (k + 2));
+  pv.n2 = pv.n1 + (k + 2);
+  pv.k = k;
+  const int maxLoop = A.C->maxLoop;
+  const double saltCorr = A.C->saltCorr, t_user = A.C->t_user_K;
+
+  for (unsigned long long p = (unsigned long long)blockIdx.x * GROUPS + grp; p < A.n_pairs; p += (unsigned long long)gridDim.x * GROUPS) {
+    uint64_t ca, cb;
+    if (A.matrix) { ca = A.a[A.row_begin + p / A.n]; cb = A.b[p % A.n]; }
+    else { ca = A.a[p]; cb = A.b[p]; }
+    __syncwarp(gmask);
+    // numSeq1 = oligo1 5'->3'; numSeq2 = oligo2 REVERSED (not complemented); N sentinels at both ends
+    for (int t = gl; t < k; t += GROUP) {
+      pv.n1[t + 1] = (uint8_t)((ca >> (2 * (k - 1 - t))) & 3u);
+      pv.n2[t + 1] = (uint8_t)((cb >> (2 * t)) & 3u);
+    }
+    if (gl == 0) { pv.n1[0] = 4; pv.n1[k + 1] = 4; pv.n2[0] = 4; pv.n2[k + 1] = 4; }
+    __syncwarp(gmask);
+    {  // rowmask[i] = positions j whose base pairs with n1[i]
+      uint32_t cm[4] = {0u, 0u, 0u, 0u};
+      for (int j = 1; j <= k; j++) cm[pv.n2[j]] |= 1u << (j - 1);
+      for (int i = gl + 1; i <= k; i += GROUP) pv.rowmask[i] = cm[3 - pv.n1[i]];
+      if (gl == 0) { pv.rowmask[0] = 0; pv.rowmask[k + 1] = 0; }
+    }
+    const int sym = ((k & 1) == 0 && revcomp_code(ca, k) == ca && revcomp_code(cb, k) == cb) ? 1 : 0;
+    const double RC = A.C->RC[sym];
+    const double* lshS = sh.lshS[sym]; const double* lshH = sh.lshH[sym];
+    const double* rshS = sh.rshS[sym]; const double* rshH = sh.rshH[sym];
+    __syncwarp(gmask);
+
+    // ---------------- fill ----------------
+    for (int i = 1; i <= k; i++) {
+      const uint32_t rm = pv.rowmask[i];
+      const int a = pv.n1[i];
+      for (int j = gl + 1; j <= k; j += GROUP) {
+        if (!((rm >> (j - 1)) & 1u)) continue;
+        const int li = (a * 5 + pv.n1[i - 1]) * 5 + pv.n2[j - 1];
+        double S = lshS[li], H = lshH[li];
+        if (i > 1 && j > 1) {
+          const int ri = (a * 5 + pv.n1[i + 1]) * 5 + pv.n2[j + 1];
+          const double rS = rshS[ri], rH = rshH[ri];
+          double S0 = S, H0 = H, S1, H1, T1;
+          const double T0 = (H0 + kDHi + rH) / (S0 + kDSi + rS + RC);
+          const int si = i4(pv.n1[i - 1], a, pv.n2[j - 1], pv.n2[j]);
+          const double stH = sh.stackH[si];
+          const bool prev_bp = (pv.rowmask[i - 1] >> (j - 2)) & 1u;
+          if (prev_bp && isfinite(stH)) {
+            const double2 pc = pv.cell[(i - 2) * k + (j - 2)];
+            S1 = pc.x + sh.stackS[si];
+            H1 = pc.y + stH;
+            T1 = (H1 + kDHi + rH) / (S1 + kDSi + rS + RC);
+          } else {
+            S1 = -1.0; H1 = INFINITY;
+            T1 = (H1 + kDHi) / (S1 + kDSi + RC);
+          }
+          if (S1 < kMinEntropyCutoff) { S1 = kMinEntropy; H1 = 0.0; }
+          if (S0 < kMinEntropyCutoff) { S0 = kMinEntropy; H0 = 0.0; }
+          if (T1 > T0) { S = S1; H = H1; } else if (T0 >= T1) { S = S0; H = H0; }
+        }
+        pv.cell[(i - 1) * k + (j - 1)] = make_double2(S, H);
+      }
+      __syncwarp(gmask);
+      if (i > 1) {
+        for (uint32_t bj = rm & ~1u; bj; bj &= bj - 1u) {
+          const int j = __ffs(bj);
+          const int ri = (a * 5 + pv.n1[i + 1]) * 5 + pv.n2[j + 1];
+          const double rS = rshS[ri], rH = rshH[ri];
+          const double2 cur = pv.cell[(i - 1) * k + (j - 1)];
+          const double Gcur = cur.y + rH - kTK * (cur.x + rS);
+          double bG = INFINITY, bS = -1.0, bH = INFINITY;
+          int bkey = 0x7fffffff;
+          bool clamp = false;
+          for (int l1 = gl; l1 <= i - 2; l1 += GROUP) {
+            const int ii = i - 1 - l1;
+            uint32_t cand = pv.rowmask[ii] & ((1u << (j - 1)) - 1u);
+            if (l1 == 0) cand &= ~(1u << (j - 2));
+            while (cand) {
+              const int jj = __ffs(cand);
+              cand &= cand - 1u;
+              const int l2 = j - jj - 1;
+              if (l1 + l2 > maxLoop) continue;
+              double S, H;
+              loop_candidate(sh, pv, i, j, ii, jj, &S, &H);
+              if (isfinite(H)) {
+                if (S < kMinEntropyCutoff) clamp = true;
+                const double G1 = H + rH - kTK * (S + rS);
+                const int key = (l1 + l2) * 64 + l1;
+                if (G1 < bG || (G1 == bG && key < bkey)) { bG = G1; bkey = key; bS = S; bH = H; }
+              }
+            }
+          }
+          if (__any_sync(gmask, clamp)) {
+            // An entropy below the cutoff re-bases the cell mid-scan: replay the scan sequentially in one lane.
+            if (gl == 0) {
+              double cS = cur.x, cH = cur.y;
+              for (int d = 3; d <= maxLoop + 2; d++) {
+                int ii = i - 1, jj = -ii - d + (j + i);
+                if (jj < 1) { ii -= (1 - jj); jj = 1; }
+                for (; ii > 0 && jj < j; --ii, ++jj) {
+                  if (!((pv.rowmask[ii] >> (jj - 1)) & 1u)) continue;
+                  double S, H;
+                  loop_candidate(sh, pv, i, j, ii, jj, &S, &H);
+                  const double G1 = H + rH - kTK * (S + rS), G2 = cH + rH - kTK * (cS + rS);
+                  if (!(G1 < G2)) { S = -1.0; H = INFINITY; }
+                  if (S < kMinEntropyCutoff) { S = kMinEntropy; H = 0.0; }
+                  if (isfinite(H)) { cS = S; cH = H; }
+                }
+              }
+              pv.cell[(i - 1) * k + (j - 1)] = make_double2(cS, cH);
+            }
+          } else {
+            double mG = bG;
+#pragma unroll
+            for (int o = GROUP / 2; o > 0; o >>= 1) mG = fmin(mG, __shfl_xor_sync(gmask, mG, o, GROUP));
+            if (mG < Gcur) {
+              int mk = (bG == mG) ? bkey : 0x7fffffff;
+#pragma unroll
+              for (int o = GROUP / 2; o > 0; o >>= 1) mk = min(mk, __shfl_xor_sync(gmask, mk, o, GROUP));
+              if (bG == mG && bkey == mk) pv.cell[(i - 1) * k + (j - 1)] = make_double2(bS, bH);
+            }
+          }
+        }
+        __syncwarp(gmask);
+      }
+    }
+
+    // ---------------- best terminal pair ----------------
+    double bG = INFINITY; int bkey = 0x7fffffff;
+    {
+      const int i_lo = A.type == MSSPE_THAL_ANY ? 1 : k;
+      for (int i = i_lo + gl; i <= k; i += GROUP) {
+        const int a = pv.n1[i];
+        for (uint32_t bj = pv.rowmask[i]; bj; bj &= bj - 1u) {
+          const int j = __ffs(bj);
+          const int ri = (a * 5 + pv.n1[i + 1]) * 5 + pv.n2[j + 1];
+          double rS = rshS[ri], rH = rshH[ri];
+          rS = rS + kSmallNonZero; rH = rH + kSmallNonZero;
+          const double2 c = pv.cell[(i - 1) * k + (j - 1)];
+          const double G1 = (c.y + rH + kDHi) - kTK * (c.x + rS + kDSi);
+          const int key = i * 64 + j;
+          if (G1 < bG || (G1 == bG && key < bkey)) { bG = G1; bkey = key; }
+        }
+      }
+      double mG = bG;
+#pragma unroll
+      for (int o = GROUP / 2; o > 0; o >>= 1) mG = fmin(mG, __shfl_xor_sync(gmask, mG, o, GROUP));
+      int mk = (bG == mG && isfinite(bG)) ? bkey : 0x7fffffff;
+#pragma unroll
+      for (int o = GROUP / 2; o > 0; o >>= 1) mk = min(mk, __shfl_xor_sync(gmask, mk, o, GROUP));
+      bG = mG; bkey = mk;
+    }
+    const bool none = !isfinite(bG);  // no base pair anywhere (for END1: none in the last row)
+    int bi = none ? (A.type == MSSPE_THAL_ANY ? 1 : k) : (bkey >> 6);
+    int bjx = none ? 1 : (bkey & 63);
+    if (none && A.type != MSSPE_THAL_ANY) { bi = 1; bjx = 1; }  // `if (!isFinite(bestG)) bestI = bestJ = 1`
+    const bool has_struct = (pv.rowmask[bi] >> (bjx - 1)) & 1u;
+    msspe_thal_out res;
+    res.ds = 0; res.dh = 0; res.dg = 0; res.tm = 0; res.no_structure = 1; res.n_bp = 0;
+    if (has_struct) {
+      const int ri = (pv.n1[bi] * 5 + pv.n1[bi + 1]) * 5 + pv.n2[bjx + 1];
+      const double2 bc = pv.cell[(bi - 1) * k + (bjx - 1)];
+      const double dH = bc.y + rshH[ri] + kDHi;
+      const double dS = bc.x + rshS[ri] + kDSi;
+      // ---------------- traceback: count paired positions ----------------
+      int i = bi, j = bjx, pairs = 1;
+      for (int guard = 0; guard < 2 * k + 2; guard++) {
+        const int li = (pv.n1[i] * 5 + pv.n1[i - 1]) * 5 + pv.n2[j - 1];
+        const double2 c = pv.cell[(i - 1) * k + (j - 1)];
+        if (eq2(c.x, lshS[li]) && eq2(c.y, lshH[li])) break;
+        if (i > 1 && j > 1 && ((pv.rowmask[i - 1] >> (j - 2)) & 1u)) {
+          const int si = i4(pv.n1[i - 1], pv.n1[i], pv.n2[j - 1], pv.n2[j]);
+          const double2 pc = pv.cell[(i - 2) * k + (j - 2)];
+          if (eq2(c.x, sh.stackS[si] + pc.x) && eq2(c.y, sh.stackH[si] + pc.y)) { i--; j--; pairs++; continue; }
+        }
+        int key = 0x7fffffff;
+        for (int l1 = gl; l1 <= i - 2; l1 += GROUP) {
+          const int ii = i - 1 - l1;
+          uint32_t cand = j >= 2 ? (pv.rowmask[ii] & ((1u << (j - 1)) - 1u)) : 0u;
+          if (l1 == 0 && j >= 2) cand &= ~(1u << (j - 2));
+          while (cand) {
+            const int jj = __ffs(cand);
+            cand &= cand - 1u;
+            const int l2 = j - jj - 1;
+            if (l1 + l2 > maxLoop) continue;
+            double S, H;
+            loop_candidate(sh, pv, i, j, ii, jj, &S, &H);
+            if (eq2(c.x, S) && eq2(c.y, H)) key = min(key, (l1 + l2) * 64 + l1);
+          }
+        }
+#pragma unroll
+        for (int o = GROUP / 2; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(gmask, key, o, GROUP));
+        if (key == 0x7fffffff) break;
+        const int l1 = key & 63, l2 = (key >> 6) - l1;
+        i = i - 1 - l1; j = j - 1 - l2; pairs++;
+      }
+      const int N = pairs - 1;  // (#paired bases in both strands)/2 - 1
+      const double t = (dH / (dS + (N * saltCorr) + RC)) - kAbsZero;
+      res.dg = dH - (t_user * (dS + (N * saltCorr)));
+      res.ds = dS + (N * saltCorr);
+      res.dh = dH;
+      res.tm = t;
+      res.no_structure = 0;
+      res.n_bp = pairs;
+    }
+    if (gl == 0) {
+      if (A.out) A.out[p] = res;
+      if (A.matrix) {
+        const unsigned long long pair = (unsigned long long)(A.row_begin + p / A.n) * A.n + (p % A.n);
+        if (res.no_structure) {
+          const unsigned long long at = atomicAdd(A.n_nostruct, 1ull);
+          if (at < A.nostruct_cap) A.nostruct[at] = pair;
+        } else if (res.dg < A.dg_limit) {
+          const unsigned long long at = atomicAdd(A.n_edges, 1ull);
+          if (at < A.edge_cap) { A.edges[at].pair = pair; A.edges[at].dg = res.dg; }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- device: monomer (hairpin), one thread per oligo
+constexpr int MONO_MAX = MSSPE_MAX_OLIGO;
+constexpr int MIN_HRPN_LOOP = 3;
+
+struct MonoWork {
+  int n1[MONO_MAX + 2];
+  int len;
+  double Sm[MONO_MAX + 2][MONO_MAX + 2], Hm[MONO_MAX + 2][MONO_MAX + 2];
+  double send5[MONO_MAX + 2], hend5[MONO_MAX + 2];
+  int maxLoop;
+};
+// dplx_init_H = 0, dplx_init_S = -1e-11, RC = 0 for unimolecular folding
+#define M_DHI 0.0
+#define M_DSI (-0.00000000001)
+#define M_RC 0.0
+
+__device__ __forceinline__ bool m_bp(int a, int b) { return a + b == 3 && a < 4 && b < 4; }
+
+__device__ double m_Ss(const ThalDeviceTables* T, const MonoWork& w, int i, int j) {
+  if (i >= j) return -1.0;
+  if (i == w.len || j == w.len + 1) return -1.0;
+  return T->stackS[THAL_IDX4(w.n1[i], w.n1[i + 1], w.n1[j], w.n1[j - 1])];
+}
+__device__ double m_Hs(const ThalDeviceTables* T, const MonoWork& w, int i, int j) {
+  if (i >= j) return INFINITY;
+  if (i == w.len || j == w.len + 1) return INFINITY;
+  const double h = T->stackH[THAL_IDX4(w.n1[i], w.n1[i + 1], w.n1[j], w.n1[j - 1])];
+  return isfinite(h) ? h : (double)INFINITY;
+}
+
+__device__ bool m_find(const uint32_t* keys, const double* vals, int n, uint32_t key, double* v) {
+  int lo = 0, hi = n - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    if (keys[mid] == key) { *v = vals[mid]; return true; }
+    if (keys[mid] < key) lo = mid + 1; else hi = mid - 1;
+  }
+  return false;
+}
+
+__device__ void m_hairpin_loop(const ThalDeviceTables* T, const MonoWork& w, int i, int j, double* S, double* H, int tb) {
+  const int* n1 = w.n1;
+  const int loopSize = j - i - 1;
+  if (loopSize < MIN_HRPN_LOOP) { *S = -1.0; *H = INFINITY; return; }
+  if (i <= w.len && w.len < j) { *S = -1.0; *H = INFINITY; return; }
+  if (loopSize <= 30) { *H = T->hairpinH[loopSize - 1]; *S = T->hairpinS[loopSize - 1]; }
+  else { *H = T->hairpinH[29]; *S = T->hairpinS[29]; }
+  if (loopSize > 3) {
+    *H += T->tstack2H[THAL_IDX4(n1[i], n1[i + 1], n1[j], n1[j - 1])];
+    *S += T->tstack2S[THAL_IDX4(n1[i], n1[i + 1], n1[j], n1[j - 1])];
+  } else if (loopSize == 3) {
+    *H += T->atpH[n1[i] * 5 + n1[j]];
+    *S += T->atpS[n1[i] * 5 + n1[j]];
+  }
+  if (loopSize == 3) {
+    uint32_t key = 0;
+    for (int c = 0; c < 5; c++) key = key * 5u + (uint32_t)n1[i + c];
+    double v;
+    if (T->nTriH && m_find(T->triKeyH, T->triH, T->nTriH, key, &v)) *H += v;
+    if (T->nTriS && m_find(T->triKeyS, T->triS, T->nTriS, key, &v)) *S += v;
+  } else if (loopSize == 4) {
+    uint32_t key = 0;
+    for (int c = 0; c < 6; c++) key = key * 5u + (uint32_t)n1[i + c];
+    double v;
+    if (T->nTetraH && m_find(T->tetraKeyH, T->tetraH, T->nTetraH, key, &v)) *H += v;
+    if (T->nTetraS && m_find(T->tetraKeyS, T->tetraS, T->nTetraS, key, &v)) *S += v;
+  }
+  if (!isfinite(*H)) { *H = INFINITY; *S = -1.0; }
+  if (*H > 0 && *S > 0 && (!(w.Hm[i][j] > 0) || !(w.Sm[i][j] > 0))) { *H = INFINITY; *S = -1.0; }
+  const double T1 = (*H + M_DHI) / ((*S + M_DSI + M_RC));
+  const double T2 = (w.Hm[i][j] + M_DHI) / ((w.Sm[i][j]) + M_DSI + M_RC);
+  if (T1 < T2 && tb == 0) { *S = w.Sm[i][j]; *H = w.Hm[i][j]; }
+}
+
+__device__ void m_bulge_internal(const ThalDeviceTables* T, const MonoWork& w, int i, int j, int ii, int jj, double* outS,
+                                 double* outH, int tb) {
+  const int* n1 = w.n1;
+  const int l1 = ii - i - 1, l2 = j - jj - 1;
+  double S, H, T1, T2;
+  if (l1 + l2 > w.maxLoop) { *outS = -1.0; *outH = INFINITY; return; }
+  const int ls = l1 + l2 - 1;
+  if ((l1 == 0 && l2 > 0) || (l2 == 0 && l1 > 0)) {
+    if (l2 == 1 || l1 == 1) {
+      H = T->bulgeH[ls] + T->stackH[THAL_IDX4(n1[i], n1[ii], n1[j], n1[jj])];
+      S = T->bulgeS[ls] + T->stackS[THAL_IDX4(n1[i], n1[ii], n1[j], n1[jj])];
+    } else {
+      H = T->bulgeH[ls] + T->atpH[n1[i] * 5 + n1[j]] + T->atpH[n1[ii] * 5 + n1[jj]];
+      S = T->bulgeS[ls] + T->atpS[n1[i] * 5 + n1[j]] + T->atpS[n1[ii] * 5 + n1[jj]];
+    }
+    if (tb != 1) { H += w.Hm[ii][jj]; S += w.Sm[ii][jj]; }
+    if (!isfinite(H)) { H = INFINITY; S = -1.0; }
+    T1 = (H + M_DHI) / ((S + M_DSI) + M_RC);
+    T2 = (w.Hm[i][j] + M_DHI) / ((w.Sm[i][j]) + M_DSI + M_RC);
+    if ((T1 > T2) || ((tb && T1 >= T2) || tb == 1)) { *outS = S; *outH = H; }
+  } else if (l1 == 1 && l2 == 1) {
+    S = T->stackint2S[THAL_IDX4(n1[i], n1[i + 1], n1[j], n1[j - 1])] + T->stackint2S[THAL_IDX4(n1[jj], n1[jj + 1], n1[ii], n1[ii - 1])];
+    if (tb != 1) S += w.Sm[ii][jj];
+    H = T->stackint2H[THAL_IDX4(n1[i], n1[i + 1], n1[j], n1[j - 1])] + T->stackint2H[THAL_IDX4(n1[jj], n1[jj + 1], n1[ii], n1[ii - 1])];
+    if (tb != 1) H += w.Hm[ii][jj];
+    if (!isfinite(H)) { H = INFINITY; S = -1.0; }
+    T1 = (H + M_DHI) / ((S + M_DSI) + M_RC);
+    T2 = (w.Hm[i][j] + M_DHI) / ((w.Sm[i][j]) + M_DSI + M_RC);
+    if ((T1 - T2 >= 0.000001) || tb) {
+      if ((T1 > T2) || ((tb && T1 >= T2) || tb == 1)) { *outS = S; *outH = H; }
+    }
+  } else {
+    const int asym = l1 > l2 ? l1 - l2 : l2 - l1;
+    H = T->interiorH[ls] + T->tstackH[THAL_IDX4(n1[i], n1[i + 1], n1[j], n1[j - 1])] +
+        T->tstackH[THAL_IDX4(n1[jj], n1[jj + 1], n1[ii], n1[ii - 1])] + (K_ILAH * asym);
+    if (tb != 1) H += w.Hm[ii][jj];
+    S = T->interiorS[ls] + T->tstackS[THAL_IDX4(n1[i], n1[i + 1], n1[j], n1[j - 1])] +
+        T->tstackS[THAL_IDX4(n1[jj], n1[jj + 1], n1[ii], n1[ii - 1])] + (K_ILAS * asym);
+    if (tb != 1) S += w.Sm[ii][jj];
+    if (!isfinite(H)) { H = INFINITY; S = -1.0; }
+    T1 = (H + M_DHI) / ((S + M_DSI) + M_RC);
+    T2 = (w.Hm[i][j] + M_DHI) / ((w.Sm[i][j]) + M_DSI + M_RC);
+    if ((T1 > T2) || ((tb && T1 >= T2) || (tb == 1))) { *outS = S; *outH = H; }
+  }
+}
+
+__device__ void m_loops(const ThalDeviceTables* T, MonoWork& w, int i, int j, double* S, double* H, int tb) {
+  for (int d = j - i - 3; d >= MIN_HRPN_LOOP + 1 && d >= j - i - 2 - w.maxLoop; --d)
+    for (int ii = i + 1; ii < j - d && ii <= w.len; ++ii) {
+      const int jj = d + ii;
+      if (tb == 0) { *S = -1.0; *H = INFINITY; }
+      if (isfinite(w.Hm[ii][jj]) && isfinite(w.Hm[i][j])) {
+        m_bulge_internal(T, w, i, j, ii, jj, S, H, tb);
+        if (isfinite(*H)) {
+          if (*S < kMinEntropyCutoff) { *S = kMinEntropy; *H = 0.0; }
+          if (tb == 0) { w.Hm[i][j] = *H; w.Sm[i][j] = *S; }
+        }
+      }
+    }
+}
+
+// exterior-fragment recursion: variant 1 = plain pair (k+1,i); 2 = 5' dangle; 3 = 3' dangle; 4 = terminal mismatch
+__device__ void m_end5_term(const ThalDeviceTables* T, const MonoWork& w, int i, int k, int variant, double* eS, double* eH) {
+  const int* n1 = w.n1;
+  switch (variant) {
+    case 1: *eH = T->atpH[n1[k + 1] * 5 + n1[i]] + w.Hm[k + 1][i]; *eS = T->atpS[n1[k + 1] * 5 + n1[i]] + w.Sm[k + 1][i]; break;
+    case 2: *eH = T->atpH[n1[k + 2] * 5 + n1[i]] + T->dangle5H[THAL_IDX3(n1[i], n1[k + 2], n1[k + 1])] + w.Hm[k + 2][i];
+            *eS = T->atpS[n1[k + 2] * 5 + n1[i]] + T->dangle5S[THAL_IDX3(n1[i], n1[k + 2], n1[k + 1])] + w.Sm[k + 2][i]; break;
+    case 3: *eH = T->atpH[n1[k + 1] * 5 + n1[i - 1]] + T->dangle3H[THAL_IDX3(n1[i - 1], n1[i], n1[k + 1])] + w.Hm[k + 1][i - 1];
+            *eS = T->atpS[n1[k + 1] * 5 + n1[i - 1]] + T->dangle3S[THAL_IDX3(n1[i - 1], n1[i], n1[k + 1])] + w.Sm[k + 1][i - 1]; break;
+    default: *eH = T->atpH[n1[k + 2] * 5 + n1[i - 1]] + T->tstack2H[THAL_IDX4(n1[i - 1], n1[i], n1[k + 2], n1[k + 1])] + w.Hm[k + 2][i - 1];
+             *eS = T->atpS[n1[k + 2] * 5 + n1[i - 1]] + T->tstack2S[THAL_IDX4(n1[i - 1], n1[i], n1[k + 2], n1[k + 1])] + w.Sm[k + 2][i - 1]; break;
+  }
+}
+__device__ __forceinline__ int m_end5_kmax(int i, int variant) {
+  return variant == 1 ? i - MIN_HRPN_LOOP - 2 : (variant == 4 ? i - MIN_HRPN_LOOP - 4 : i - MIN_HRPN_LOOP - 3);
+}
+__device__ void m_end5(const ThalDeviceTables* T, const MonoWork& w, int i, int variant, double* outH, double* outS) {
+  double H_max = INFINITY, S_max = -1.0, max_tm = -INFINITY;
+  const int kmax = m_end5_kmax(i, variant);
+  for (int k = 0; k <= kmax; ++k) {
+    double T1 = (w.hend5[k] + M_DHI) / (w.send5[k] + M_DSI + M_RC);
+    const double T2 = (0 + M_DHI) / (0 + M_DSI + M_RC);
+    double eH, eS, H, S;
+    m_end5_term(T, w, i, k, variant, &eS, &eH);
+    if (T1 >= T2) { H = w.hend5[k] + eH; S = w.send5[k] + eS; } else { H = 0 + eH; S = 0 + eS; }
+    if (!isfinite(H) || H > 0 || S > 0) { H = INFINITY; S = -1.0; }
+    T1 = (H + M_DHI) / (S + M_DSI + M_RC);
+    if (max_tm < T1) {
+      if (S > kMinEntropyCutoff) { H_max = H; S_max = S; max_tm = T1; }
+    }
+  }
+  *outH = H_max; *outS = S_max;
+}
+
+__device__ void mono_run(const ThalDeviceTables* T, MonoWork& w, double saltCorr, double temp_K, msspe_thal_out* out) {
+  const int* n1 = w.n1;
+  const int len = w.len;
+  out->ds = 0; out->dh = 0; out->dg = 0; out->tm = 0; out->no_structure = 1; out->n_bp = 0;
+  for (int i = 1; i <= len; ++i)
+    for (int j = i; j <= len; ++j) {
+      if (j - i < MIN_HRPN_LOOP + 1 || !m_bp(n1[i], n1[j])) { w.Hm[i][j] = INFINITY; w.Sm[i][j] = -1.0; }
+      else { w.Hm[i][j] = 0.0; w.Sm[i][j] = kMinEntropy; }
+    }
+  for (int j = 2; j <= len; ++j)
+    for (int i = j - MIN_HRPN_LOOP - 1; i >= 1; --i) {
+      if (!isfinite(w.Hm[i][j])) continue;
+      double S0 = w.Sm[i][j], H0 = w.Hm[i][j];
+      const double T0 = (H0 + M_DHI) / (S0 + M_DSI + M_RC);
+      double S1 = w.Sm[i + 1][j - 1] + m_Ss(T, w, i, j);
+      double H1 = w.Hm[i + 1][j - 1] + m_Hs(T, w, i, j);
+      const double T1 = (H1 + M_DHI) / (S1 + M_DSI + M_RC);
+      if (S1 < kMinEntropyCutoff) { S1 = kMinEntropy; H1 = 0.0; }
+      if (S0 < kMinEntropyCutoff) { S0 = kMinEntropy; H0 = 0.0; }
+      if (T1 > T0) { w.Sm[i][j] = S1; w.Hm[i][j] = H1; } else { w.Sm[i][j] = S0; w.Hm[i][j] = H0; }
+      double s = -1.0, h = INFINITY;
+      m_loops(T, w, i, j, &s, &h, 0);
+      s = -1.0; h = INFINITY;
+      m_hairpin_loop(T, w, i, j, &s, &h, 0);
+      if (isfinite(h)) {
+        if (s < kMinEntropyCutoff) { s = kMinEntropy; h = 0.0; }
+        w.Sm[i][j] = s; w.Hm[i][j] = h;
+      }
+    }
+  // exterior fragments
+  w.send5[0] = w.send5[1] = -1.0;
+  w.hend5[0] = w.hend5[1] = INFINITY;
+  for (int i = 2; i <= len; i++) { w.send5[i] = kMinEntropy; w.hend5[i] = 0; }
+  for (int i = 2; i <= len; ++i) {
+    double eh[5], es[5], Tm[6];
+    Tm[1] = (w.hend5[i - 1] + M_DHI) / (w.send5[i - 1] + M_DSI + M_RC);
+    for (int v = 1; v <= 4; v++) {
+      m_end5(T, w, i, v, &eh[v], &es[v]);
+      Tm[v + 1] = (eh[v] + M_DHI) / (es[v] + M_DSI + M_RC);
+    }
+    int mx;
+    if (Tm[1] > Tm[2] && Tm[1] > Tm[3] && Tm[1] > Tm[4] && Tm[1] > Tm[5]) mx = 1;
+    else if (Tm[2] > Tm[3] && Tm[2] > Tm[4] && Tm[2] > Tm[5]) mx = 2;
+    else if (Tm[3] > Tm[4] && Tm[3] > Tm[5]) mx = 3;
+    else if (Tm[4] > Tm[5]) mx = 4;
+    else mx = 5;
+    if (mx == 1) { w.send5[i] = w.send5[i - 1]; w.hend5[i] = w.hend5[i - 1]; }
+    else {
+      const int v = mx - 1;
+      const double G = eh[v] - (temp_K * (es[v]));
+      if (G < 0.0) { w.send5[i] = es[v]; w.hend5[i] = eh[v]; }
+      else { w.send5[i] = w.send5[i - 1]; w.hend5[i] = w.hend5[i - 1]; }
+    }
+  }
+  const double mh = w.hend5[len], ms = w.send5[len];
+  if (!isfinite(mh) || !isfinite(ms)) return;
+  // traceback with an explicit stack
+  int bpv[MONO_MAX + 2];
+  for (int t = 0; t < len; ++t) bpv[t] = 0;
+  struct { short i, j, m; } stk[4 * MONO_MAX];
+  int sp = 0;
+#define M_PUSH(a_, b_, c_) do { if (sp < 4 * MONO_MAX) { stk[sp].i = (short)(a_); stk[sp].j = (short)(b_); stk[sp].m = (short)(c_); sp++; } } while (0)
+  M_PUSH(len, 0, 1);
+  while (sp > 0) {
+    sp--;
+    int i = stk[sp].i;
+    const int j = stk[sp].j, m = stk[sp].m;
+    if (m == 1) {
+      while (i >= 1 && eq2(w.send5[i], w.send5[i - 1]) && eq2(w.hend5[i], w.hend5[i - 1])) --i;
+      if (i == 0) continue;
+      bool handled = false;
+      for (int v = 1; v <= 4 && !handled; v++) {
+        double eh, es;
+        m_end5(T, w, i, v, &eh, &es);
+        if (!(eq2(w.send5[i], es) && eq2(w.hend5[i], eh))) continue;
+        handled = true;
+        const int kmax = m_end5_kmax(i, v);
+        for (int k = 0; k <= kmax; ++k) {
+          double xS, xH;
+          m_end5_term(T, w, i, k, v, &xS, &xH);
+          const int pi = (v == 1 || v == 3) ? k + 1 : k + 2;
+          const int pj = (v <= 2) ? i : i - 1;
+          if (eq2(w.send5[i], xS) && eq2(w.hend5[i], xH)) { M_PUSH(pi, pj, 0); break; }
+          else if (eq2(w.send5[i], w.send5[k] + xS) && eq2(w.hend5[i], w.hend5[k] + xH)) { M_PUSH(pi, pj, 0); M_PUSH(k, 0, 1); break; }
+        }
+      }
+    } else {
+      bpv[i - 1] = j; bpv[j - 1] = i;
+      double s1 = -1.0, h1 = INFINITY, s2 = -1.0, h2 = INFINITY;
+      m_hairpin_loop(T, w, i, j, &s1, &h1, 1);
+      m_loops(T, w, i, j, &s2, &h2, 2);
+      if (eq2(w.Sm[i][j], m_Ss(T, w, i, j) + w.Sm[i + 1][j - 1]) && eq2(w.Hm[i][j], m_Hs(T, w, i, j) + w.Hm[i + 1][j - 1])) {
+        M_PUSH(i + 1, j - 1, 0);
+      } else if (eq2(w.Sm[i][j], s1) && eq2(w.Hm[i][j], h1)) {
+        // hairpin loop closes here
+      } else if (eq2(w.Sm[i][j], s2) && eq2(w.Hm[i][j], h2)) {
+        bool done = false;
+        for (int d = j - i - 3; d >= MIN_HRPN_LOOP + 1 && d >= j - i - 2 - w.maxLoop && !done; --d)
+          for (int ii = i + 1; ii < j - d; ++ii) {
+            const int jj = d + ii;
+            double es = -1.0, eh = INFINITY;
+            m_bulge_internal(T, w, i, j, ii, jj, &es, &eh, 1);
+            if (eq2(w.Sm[i][j], es + w.Sm[ii][jj]) && eq2(w.Hm[i][j], eh + w.Hm[ii][jj])) { M_PUSH(ii, jj, 0); done = true; break; }
+          }
+      }
+    }
+  }
+#undef M_PUSH
+  int N = 0;
+  for (int i = 1; i < len; ++i) if (bpv[i - 1] > 0) N++;
+  out->n_bp = N / 2;
+  const double t = (mh / (ms + (((N / 2) - 1) * saltCorr))) - kAbsZero;
+  out->dg = mh - (temp_K * (ms + (((N / 2) - 1) * saltCorr)));
+  out->ds = ms + (((N / 2) - 1) * saltCorr);
+  out->dh = mh;
+  out->tm = t;
+  out->no_structure = 0;
+}
+
+__global__ void __launch_bounds__(64)
+thal_mono_kernel(const uint64_t* __restrict__ codes, uint32_t n, int k, const ThalDeviceTables* T, double saltCorr, double temp_K,
+                 int maxLoop, MonoWork* work, msspe_thal_out* out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  MonoWork& w = work[t];
+  const uint64_t c = codes[t];
+  w.len = k; w.maxLoop = maxLoop;
+  for (int x = 0; x < k; x++) w.n1[x + 1] = (int)((c >> (2 * (k - 1 - x))) & 3u);
+  w.n1[0] = 4; w.n1[k + 1] = 4;
+  msspe_thal_out r;
+  mono_run(T, w, saltCorr, temp_K, &r);
+  out[t] = r;
+}
+
+// ---------------------------------------------------------------- device: oligotm + GC
+struct OligoTmConsts { double salt_term; double conc_term[2]; };  // 0.368*(len-1)*ln(K/1000); 1.987*ln(C/4e9 | C/1e9)
+
+__global__ void oligotm_kernel(const uint64_t* __restrict__ codes, uint32_t n, int k, const ThalDeviceTables* T, OligoTmConsts K,
+                               double* __restrict__ tm, double* __restrict__ gc) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint64_t c = codes[t];
+  double dh = 0, ds = 0;
+  const int sym = ((k & 1) == 0 && revcomp_code(c, k) == c) ? 1 : 0;
+  if (sym) ds += -1.4;
+  const int f = (int)((c >> (2 * (k - 1))) & 3u), l = (int)(c & 3u);
+  if (f == 0 || f == 3) { ds += 4.1; dh += 2300; } else { ds += -2.8; dh += 100; }
+  if (l == 0 || l == 3) { ds += 4.1; dh += 2300; } else { ds += -2.8; dh += 100; }
+  int ngc = 0;
+  for (int i = 0; i < k; i++) {
+    const int a = (int)((c >> (2 * (k - 1 - i))) & 3u);
+    if (a == 1 || a == 2) ngc++;
+    if (i + 1 < k) {
+      const int b = (int)((c >> (2 * (k - 2 - i))) & 3u);
+      dh += T->stackH[THAL_IDX4(a, b, 3 - a, 3 - b)];
+      ds += T->stackS[THAL_IDX4(a, b, 3 - a, 3 - b)];
+    }
+  }
+  ds = ds + K.salt_term;
+  tm[t] = dh / (ds + K.conc_term[sym]) - 273.15;
+  gc[t] = 100.0 * ngc / k;
+}
+
+// ---------------------------------------------------------------- host side
+int ensure_tables(msspe_ctx* c) {
+  if (c->d_thal) return MSSPE_OK;
+  if (!c->raw_set) { msspe_thal_params_default(&c->raw); c->raw_set = true; }
+  return msspe_thal_upload_tables(c);
+}
+
+struct DeviceBuf {
+  void* p = nullptr;
+  ~DeviceBuf() { if (p) cudaFree(p); }
+};
+
+int launch_dimer(msspe_ctx* c, DimerArgs& A, cudaStream_t st) {
+  if (A.n_pairs == 0) return MSSPE_OK;
+  const int k = A.k;
+  const int group = k <= 16 ? 16 : 32;
+  const int groups = DIMER_THREADS / group;
+  const size_t cell_bytes = (size_t)k * k * 16;
+  const size_t grp_bytes = (cell_bytes + (size_t)(k + 2) * 4 + 2 * (size_t)(k + 2) + 15) & ~(size_t)15;
+  const size_t smem = ((sizeof(DimerShared) + 15) & ~(size_t)15) + groups * grp_bytes;
+  if (smem > c->smem_optin) { c->set_error("thal dimer: %zu B shared memory needed, device offers %zu", smem, c->smem_optin); return MSSPE_ERR_CAPACITY; }
+  int per_sm = 1;
+  unsigned long long blocks_needed = (A.n_pairs + groups - 1) / groups;
+  if (group == 16) {
+    MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(thal_dimer_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, thal_dimer_kernel<16>, DIMER_THREADS, smem));
+  } else {
+    MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(thal_dimer_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, thal_dimer_kernel<32>, DIMER_THREADS, smem));
+  }
+  if (per_sm < 1) per_sm = 1;
+  const unsigned long long resident = (unsigned long long)c->sm_count * per_sm;
+  const unsigned grid = (unsigned)(blocks_needed < resident ? blocks_needed : resident);
+  if (group == 16) thal_dimer_kernel<16><<<grid, DIMER_THREADS, smem, st>>>(A);
+  else thal_dimer_kernel<32><<<grid, DIMER_THREADS, smem, st>>>(A);
+  c->timing.kernel_launches++;
+  MSSPE_CUDA_TRY(c, cudaGetLastError());
+  return MSSPE_OK;
+}
+
+int check_thal_args(msspe_ctx* c, uint32_t oligo_len, const msspe_thal_cond* cond) {
+  if (oligo_len < 1 || oligo_len > MSSPE_MAX_OLIGO) { c->set_error("oligo length %u outside 1..%d", oligo_len, MSSPE_MAX_OLIGO); return MSSPE_ERR_INVALID; }
+  if (cond && (cond->max_loop < 0 || cond->max_loop > 30)) { c->set_error("max_loop %d outside 0..30", cond->max_loop); return MSSPE_ERR_INVALID; }
+  return MSSPE_OK;
+}
+
+}  // namespace
+
+int msspe_thal_upload_tables(msspe_ctx* c) {
+  ThalDeviceTables* h = new ThalDeviceTables();
+  msspe_thal_expand(&c->raw, h);
+  if (!c->d_thal) {
+    cudaError_t e = cudaMalloc(&c->d_thal, sizeof(ThalDeviceTables));
+    if (e != cudaSuccess) { delete h; c->set_error("cudaMalloc thal tables: %s", cudaGetErrorString(e)); return MSSPE_ERR_CUDA; }
+  }
+  cudaError_t e = cudaMemcpy(c->d_thal, h, sizeof(ThalDeviceTables), cudaMemcpyHostToDevice);
+  delete h;
+  if (e != cudaSuccess) { c->set_error("upload thal tables: %s", cudaGetErrorString(e)); return MSSPE_ERR_CUDA; }
+  return MSSPE_OK;
+}
+
+void msspe_thal_free_tables(msspe_ctx* c) {
+  if (c->d_thal) cudaFree(c->d_thal);
+  c->d_thal = nullptr;
+}
+
+extern "C" int msspe_set_thal_params(msspe_ctx* c, const msspe_thal_raw_params* p) {
+  if (!c || !p) return MSSPE_ERR_INVALID;
+  MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
+  c->raw = *p;
+  c->raw_set = true;
+  return msspe_thal_upload_tables(c);
+}
+
+extern "C" int msspe_thal_pairs(msspe_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t n_pairs, uint32_t oligo_len,
+                                int32_t type, const msspe_thal_cond* cond, msspe_thal_out* out) {
+  if (!c) return MSSPE_ERR_INVALID;
+  if (!cond || (n_pairs && (!a || !out))) { c->set_error("msspe_thal_pairs: null argument"); return MSSPE_ERR_INVALID; }
+  if (type != MSSPE_THAL_ANY && type != MSSPE_THAL_END1 && type != MSSPE_THAL_HAIRPIN) { c->set_error("msspe_thal_pairs: unsupported type %d", type); return MSSPE_ERR_INVALID; }
+  if (type != MSSPE_THAL_HAIRPIN && n_pairs && !b) { c->set_error("msspe_thal_pairs: null argument"); return MSSPE_ERR_INVALID; }
+  int rc = check_thal_args(c, oligo_len, cond);
+  if (rc) return rc;
+  if (n_pairs == 0) return MSSPE_OK;
+  MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
+  rc = ensure_tables(c);
+  if (rc) return rc;
+  cudaStream_t st = c->stream;
+  ThalDeviceTables* hT = new ThalDeviceTables();
+  msspe_thal_expand(&c->raw, hT);
+  ThalDimerConsts K;
+  build_dimer_consts(*hT, *cond, &K);
+  delete hT;
+  DeviceBuf da, db, dout, dK, dwork;
+  MSSPE_CUDA_TRY(c, cudaMalloc(&da.p, n_pairs * 8));
+  MSSPE_CUDA_TRY(c, cudaMalloc(&dout.p, n_pairs * sizeof(msspe_thal_out)));
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(da.p, a, n_pairs * 8, cudaMemcpyHostToDevice, st));
+  if (type == MSSPE_THAL_HAIRPIN) {
+    MSSPE_CUDA_TRY(c, cudaMalloc(&dwork.p, n_pairs * sizeof(MonoWork)));
+    thal_mono_kernel<<<(unsigned)div_up_u64(n_pairs, 64), 64, 0, st>>>((const uint64_t*)da.p, (uint32_t)n_pairs, (int)oligo_len, c->d_thal,
+                                                                     K.saltCorr, K.t_user_K, K.maxLoop, (MonoWork*)dwork.p,
+                                                                     (msspe_thal_out*)dout.p);
+    c->timing.kernel_launches++;
+    MSSPE_CUDA_TRY(c, cudaGetLastError());
+  } else {
+    MSSPE_CUDA_TRY(c, cudaMalloc(&db.p, n_pairs * 8));
+    MSSPE_CUDA_TRY(c, cudaMalloc(&dK.p, sizeof(ThalDimerConsts)));
+    MSSPE_CUDA_TRY(c, cudaMemcpyAsync(db.p, b, n_pairs * 8, cudaMemcpyHostToDevice, st));
+    MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dK.p, &K, sizeof K, cudaMemcpyHostToDevice, st));
+    DimerArgs A{};
+    A.a = (const uint64_t*)da.p; A.b = (const uint64_t*)db.p; A.n_pairs = n_pairs; A.matrix = 0; A.k = (int)oligo_len; A.type = type;
+    A.T = c->d_thal; A.C = (const ThalDimerConsts*)dK.p; A.out = (msspe_thal_out*)dout.p;
+    rc = launch_dimer(c, A, st);
+    if (rc) return rc;
+  }
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(out, dout.p, n_pairs * sizeof(msspe_thal_out), cudaMemcpyDeviceToHost, st));
+  MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+  return MSSPE_OK;
+}
+
+extern "C" int msspe_primer_thermo(msspe_ctx* c, const uint64_t* codes, uint32_t n, uint32_t oligo_len, double* tm, double* gc,
+                                   double* self_any, double* self_end, double* hairpin) {
+  if (!c) return MSSPE_ERR_INVALID;
+  if (n && (!codes || !tm || !gc || !self_any || !self_end || !hairpin)) { c->set_error("msspe_primer_thermo: null argument"); return MSSPE_ERR_INVALID; }
+  int rc = check_thal_args(c, oligo_len, nullptr);
+  if (rc) return rc;
+  if (n == 0) return MSSPE_OK;
+  MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
+  rc = ensure_tables(c);
+  if (rc) return rc;
+  cudaStream_t st = c->stream;
+  // Primer3 defaults (primer.rs:125-140 sends no salt tags): mv 50, dv 1.5, dNTP 0.6, DNA 50 nM; thal at 37 C, maxLoop 30
+  const msspe_thal_cond p3{50.0, 1.5, 0.6, 50.0, 37.0, 30, 0};
+  ThalDeviceTables* hT = new ThalDeviceTables();
+  msspe_thal_expand(&c->raw, hT);
+  ThalDimerConsts K;
+  build_dimer_consts(*hT, p3, &K);
+  delete hT;
+  OligoTmConsts OK;
+  {
+    double dv = p3.dv, dntp = p3.dntp;
+    if (dv == 0) dntp = 0;
+    if (dv < dntp) dv = dntp;
+    const double Ksalt = p3.mv + 120 * sqrt(dv - dntp);
+    OK.salt_term = 0.368 * ((int)oligo_len - 1) * log(Ksalt / 1000.0);
+    OK.conc_term[0] = 1.987 * log(p3.dna_conc / 4000000000.0);
+    OK.conc_term[1] = 1.987 * log(p3.dna_conc / 1000000000.0);
+  }
+  DeviceBuf dcodes, dK, dtm, dgc, dout, dwork;
+  MSSPE_CUDA_TRY(c, cudaMalloc(&dcodes.p, (size_t)n * 8));
+  MSSPE_CUDA_TRY(c, cudaMalloc(&dK.p, sizeof K));
+  MSSPE_CUDA_TRY(c, cudaMalloc(&dtm.p, (size_t)n * 8));
+  MSSPE_CUDA_TRY(c, cudaMalloc(&dgc.p, (size_t)n * 8));
+  MSSPE_CUDA_TRY(c, cudaMalloc(&dout.p, (size_t)n * 3 * sizeof(msspe_thal_out)));
+  MSSPE_CUDA_TRY(c, cudaMalloc(&dwork.p, (size_t)n * sizeof(MonoWork)));
+  MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[6], st));
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dcodes.p, codes, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dK.p, &K, sizeof K, cudaMemcpyHostToDevice, st));
+  oligotm_kernel<<<(n + 127) / 128, 128, 0, st>>>((const uint64_t*)dcodes.p, n, (int)oligo_len, c->d_thal, OK, (double*)dtm.p, (double*)dgc.p);
+  c->timing.kernel_launches++;
+  msspe_thal_out* o3 = (msspe_thal_out*)dout.p;
+  for (int pass = 0; pass < 2; pass++) {  // SELF_ANY_TH, SELF_END_TH: thal(s, s)
+    DimerArgs A{};
+    A.a = (const uint64_t*)dcodes.p; A.b = (const uint64_t*)dcodes.p; A.n_pairs = n; A.matrix = 0; A.k = (int)oligo_len;
+    A.type = pass == 0 ? MSSPE_THAL_ANY : MSSPE_THAL_END1;
+    A.T = c->d_thal; A.C = (const ThalDimerConsts*)dK.p; A.out = o3 + (size_t)pass * n;
+    rc = launch_dimer(c, A, st);
+    if (rc) return rc;
+  }
+  thal_mono_kernel<<<(n + 63) / 64, 64, 0, st>>>((const uint64_t*)dcodes.p, n, (int)oligo_len, c->d_thal, K.saltCorr, K.t_user_K, K.maxLoop,
+                                                (MonoWork*)dwork.p, o3 + (size_t)2 * n);
+  c->timing.kernel_launches++;
+  MSSPE_CUDA_TRY(c, cudaGetLastError());
+  std::vector<msspe_thal_out> h((size_t)n * 3);
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(tm, dtm.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(gc, dgc.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(h.data(), dout.p, h.size() * sizeof(msspe_thal_out), cudaMemcpyDeviceToHost, st));
+  MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[7], st));
+  MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+  MSSPE_CUDA_TRY(c, cudaEventElapsedTime(&c->timing.thermo_ms, c->ev[6], c->ev[7]));
+  for (uint32_t i = 0; i < n; i++) {  // align_thermod: negative or absent structure temperatures report 0
+    const double a = h[i].tm, e = h[(size_t)n + i].tm, hp = h[(size_t)2 * n + i].tm;
+    self_any[i] = a < 0.0 ? 0.0 : a;
+    self_end[i] = e < 0.0 ? 0.0 : e;
+    hairpin[i] = hp < 0.0 ? 0.0 : hp;
+  }
+  return MSSPE_OK;
+}
+
+extern "C" int msspe_cross_dimer(msspe_ctx* c, const uint64_t* codes, uint32_t n, uint32_t oligo_len, const msspe_thal_cond* cond,
+                                 uint32_t row_begin, uint32_t row_end, double dg_limit, msspe_dimer_edge* edges,
+                                 uint64_t edge_capacity, uint64_t* n_edges, uint64_t* nostruct_pairs, uint64_t nostruct_capacity,
+                                 uint64_t* n_nostruct) {
+  if (!c) return MSSPE_ERR_INVALID;
+  if (!cond || !n_edges || !n_nostruct || (n && !codes) || row_begin > row_end || row_end > n) { c->set_error("msspe_cross_dimer: bad argument"); return MSSPE_ERR_INVALID; }
+  int rc = check_thal_args(c, oligo_len, cond);
+  if (rc) return rc;
+  *n_edges = 0; *n_nostruct = 0;
+  const unsigned long long n_pairs = (unsigned long long)(row_end - row_begin) * n;
+  if (n_pairs == 0) return MSSPE_OK;
+  MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
+  rc = ensure_tables(c);
+  if (rc) return rc;
+  cudaStream_t st = c->stream;
+  ThalDeviceTables* hT = new ThalDeviceTables();
+  msspe_thal_expand(&c->raw, hT);
+  ThalDimerConsts K;
+  build_dimer_consts(*hT, *cond, &K);
+  delete hT;
+  DeviceBuf dcodes, dK, dedges, dnos, dcnt;
+  MSSPE_CUDA_TRY(c, cudaMalloc(&dcodes.p, (size_t)n * 8));
+  MSSPE_CUDA_TRY(c, cudaMalloc(&dK.p, sizeof K));
+  MSSPE_CUDA_TRY(c, cudaMalloc(&dedges.p, (size_t)(edge_capacity ? edge_capacity : 1) * sizeof(msspe_dimer_edge)));
+  MSSPE_CUDA_TRY(c, cudaMalloc(&dnos.p, (size_t)(nostruct_capacity ? nostruct_capacity : 1) * 8));
+  MSSPE_CUDA_TRY(c, cudaMalloc(&dcnt.p, 16));
+  MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[6], st));
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dcodes.p, codes, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dK.p, &K, sizeof K, cudaMemcpyHostToDevice, st));
+  MSSPE_CUDA_TRY(c, cudaMemsetAsync(dcnt.p, 0, 16, st));
+  DimerArgs A{};
+  A.a = (const uint64_t*)dcodes.p; A.b = (const uint64_t*)dcodes.p; A.n_pairs = n_pairs; A.n = n; A.row_begin = row_begin; A.matrix = 1;
+  A.k = (int)oligo_len; A.type = MSSPE_THAL_ANY; A.T = c->d_thal; A.C = (const ThalDimerConsts*)dK.p; A.out = nullptr;
+  A.dg_limit = dg_limit; A.edges = (msspe_dimer_edge*)dedges.p; A.edge_cap = edge_capacity; A.n_edges = (unsigned long long*)dcnt.p;
+  A.nostruct = (uint64_t*)dnos.p; A.nostruct_cap = nostruct_capacity; A.n_nostruct = (unsigned long long*)dcnt.p + 1;
+  rc = launch_dimer(c, A, st);
+  if (rc) return rc;
+  unsigned long long cnt[2] = {0, 0};
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(cnt, dcnt.p, 16, cudaMemcpyDeviceToHost, st));
+  MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[7], st));
+  MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+  MSSPE_CUDA_TRY(c, cudaEventElapsedTime(&c->timing.dimer_ms, c->ev[6], c->ev[7]));
+  *n_edges = cnt[0]; *n_nostruct = cnt[1];
+  if (cnt[0] > edge_capacity || cnt[1] > nostruct_capacity) {
+    c->set_error("msspe_cross_dimer: %llu edges / %llu structure-less pairs exceed the caller's capacity (%llu / %llu)", cnt[0], cnt[1],
+                 (unsigned long long)edge_capacity, (unsigned long long)nostruct_capacity);
+    return MSSPE_ERR_CAPACITY;
+  }
+  if (cnt[0]) {
+    MSSPE_CUDA_TRY(c, cudaMemcpy(edges, dedges.p, cnt[0] * sizeof(msspe_dimer_edge), cudaMemcpyDeviceToHost));
+    std::sort(edges, edges + cnt[0], [](const msspe_dimer_edge& x, const msspe_dimer_edge& y) { return x.pair < y.pair; });
+  }
+  if (cnt[1]) {
+    MSSPE_CUDA_TRY(c, cudaMemcpy(nostruct_pairs, dnos.p, cnt[1] * 8, cudaMemcpyDeviceToHost));
+    std::sort(nostruct_pairs, nostruct_pairs + cnt[1]);
+  }
+  return MSSPE_OK;
+}

@@ -1,0 +1,287 @@
+"""msspe_b200 -- ctypes binding of libodmsspe_b200.so (the C ABI in include/od_msspe_b200.h).
+
+This is the Python-side mirror of the reference's call sites (od-msspe/src/main.rs:693-752); the product is
+the shared library, this module only marshals buffers.  There is no CPU fallback: if the CUDA library is
+missing or no device is usable, every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_PKG), "libodmsspe_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_IO, ERR_CAPACITY = 0, -1, -2, -3, -4, -5, -6
+DIR_FWD, DIR_REV = 0, 1
+NO_KMER = np.uint64(0xFFFFFFFFFFFFFFFF)
+SELECT_RECOUNT, SELECT_INCREMENTAL = 0, 1
+THAL_ANY, THAL_END1, THAL_HAIRPIN = 1, 2, 4
+
+# every symbol include/od_msspe_b200.h declares
+ABI_SYMBOLS = [
+    "msspe_abi_version", "msspe_create", "msspe_destroy", "msspe_last_error", "msspe_set_stream", "msspe_synchronize",
+    "msspe_get_timing", "msspe_reset_timing", "msspe_set_profiling", "msspe_load_genomes", "msspe_load_genomes_device",
+    "msspe_build_index", "msspe_segment_info", "msspe_get_segment_kmers", "msspe_get_index", "msspe_select",
+    "msspe_select_both", "msspe_coverage", "msspe_thal_params_default", "msspe_thal_params_from_dir",
+    "msspe_set_thal_params", "msspe_primer_thermo", "msspe_thal_pairs", "msspe_cross_dimer",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("kmer_size", C.c_uint32), ("window_size", C.c_uint32), ("overlap_size", C.c_uint32),
+                ("search_windows_size", C.c_uint32), ("device", C.c_int32), ("flags", C.c_uint32)]
+
+
+class Candidate(C.Structure):
+    _fields_ = [("code", C.c_uint64), ("freq", C.c_uint32), ("n_tied", C.c_uint32), ("tie_score", C.c_float),
+                ("reserved", C.c_uint32)]
+
+
+class ThalCond(C.Structure):
+    _fields_ = [("mv", C.c_double), ("dv", C.c_double), ("dntp", C.c_double), ("dna_conc", C.c_double),
+                ("temp_c", C.c_double), ("max_loop", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ThalOut(C.Structure):
+    _fields_ = [("ds", C.c_double), ("dh", C.c_double), ("dg", C.c_double), ("tm", C.c_double),
+                ("no_structure", C.c_int32), ("n_bp", C.c_int32)]
+
+
+class DimerEdge(C.Structure):
+    _fields_ = [("pair", C.c_uint64), ("dg", C.c_double)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("encode_ms", C.c_float), ("index_ms", C.c_float), ("select_ms", C.c_float * 2),
+                ("thermo_ms", C.c_float), ("dimer_ms", C.c_float), ("select_evals", C.c_uint64 * 2),
+                ("select_postings_read", C.c_uint64 * 2), ("select_iterations", C.c_uint32 * 2),
+                ("kernel_launches", C.c_uint32), ("count_kernel_ms", C.c_float * 2),
+                ("count_kernel_launches", C.c_uint32 * 2)]
+
+
+CANDIDATE_DTYPE = np.dtype([("code", "<u8"), ("freq", "<u4"), ("n_tied", "<u4"), ("tie_score", "<f4"), ("reserved", "<u4")])
+THAL_OUT_DTYPE = np.dtype([("ds", "<f8"), ("dh", "<f8"), ("dg", "<f8"), ("tm", "<f8"), ("no_structure", "<i4"), ("n_bp", "<i4")])
+EDGE_DTYPE = np.dtype([("pair", "<u8"), ("dg", "<f8")])
+
+_lib = None
+
+
+class MsspeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("msspe error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load_library():
+    """dlopen the CUDA engine; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MsspeError(ERR_IO, "%s not built -- run open-msspe-design_b200/build.sh (no CPU fallback exists)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.msspe_last_error.restype = C.c_char_p
+    L.msspe_last_error.argtypes = [C.c_void_p]
+    L.msspe_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    L.msspe_destroy.argtypes = [C.c_void_p]
+    L.msspe_destroy.restype = None
+    L.msspe_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.msspe_synchronize.argtypes = [C.c_void_p]
+    L.msspe_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
+    L.msspe_reset_timing.argtypes = [C.c_void_p]
+    L.msspe_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    L.msspe_load_genomes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.msspe_load_genomes_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.msspe_build_index.argtypes = [C.c_void_p]
+    L.msspe_segment_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.msspe_get_segment_kmers.argtypes = [C.c_void_p, C.c_uint8, C.c_void_p, C.c_uint64]
+    L.msspe_get_index.argtypes = [C.c_void_p, C.c_uint8, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p,
+                                  C.c_void_p, C.c_void_p]
+    L.msspe_select.argtypes = [C.c_void_p, C.c_uint8, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
+    L.msspe_select_both.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32),
+                                    C.c_void_p, C.POINTER(C.c_uint32)]
+    L.msspe_coverage.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_uint64]
+    L.msspe_thal_params_default.argtypes = [C.c_void_p]
+    L.msspe_thal_params_from_dir.argtypes = [C.c_char_p, C.c_void_p, C.c_char_p, C.c_size_t]
+    L.msspe_set_thal_params.argtypes = [C.c_void_p, C.c_void_p]
+    L.msspe_primer_thermo.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32] + [C.c_void_p] * 5
+    L.msspe_thal_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32,
+                                   C.POINTER(ThalCond), C.c_void_p]
+    L.msspe_cross_dimer.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(ThalCond), C.c_uint32,
+                                    C.c_uint32, C.c_double, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p,
+                                    C.c_uint64, C.POINTER(C.c_uint64)]
+    _lib = L
+    return L
+
+
+RAW_PARAMS_BYTES = 25024  # sizeof(msspe_thal_raw_params); checked by tests/test_abi.py
+
+
+def encode_word(word: str) -> int:
+    v = 0
+    for ch in word:
+        v = (v << 2) | "ACGT".index(ch)
+    return v
+
+
+def decode_word(code: int, k: int) -> str:
+    return "".join("ACGT"[(int(code) >> (2 * (k - 1 - i))) & 3] for i in range(k))
+
+
+def pack_records(seqs) -> tuple[np.ndarray, np.ndarray]:
+    """Concatenate record sequences (bytes) and build the offsets array msspe_load_genomes expects."""
+    offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
+    bases = np.frombuffer(b"".join(seqs), dtype=np.uint8).copy() if seqs else np.zeros(0, dtype=np.uint8)
+    return bases, offs
+
+
+class Engine:
+    """One msspe_ctx.  Method names follow the reference functions they replace."""
+
+    def __init__(self, kmer_size=13, window_size=500, overlap_size=250, search_windows_size=50, device=0):
+        self.L = load_library()
+        self.k = kmer_size
+        cfg = Config(kmer_size, window_size, overlap_size, search_windows_size, device, 0)
+        h = C.c_void_p()
+        rc = self.L.msspe_create(C.byref(cfg), C.byref(h))
+        if rc != OK:
+            raise MsspeError(rc, self.L.msspe_last_error(None).decode())
+        self.h = h
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.msspe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise MsspeError(rc, self.L.msspe_last_error(self.h).decode())
+
+    # -- get_segment_manager (main.rs:196-235) --
+    def load_genomes(self, bases: np.ndarray, offsets: np.ndarray):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._check(self.L.msspe_load_genomes(self.h, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1))
+
+    def load_genomes_device(self, device_ptr: int, offsets: np.ndarray, keepalive=None):
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._keep = keepalive
+        self._check(self.L.msspe_load_genomes_device(self.h, C.c_void_p(device_ptr), offsets.ctypes.data, len(offsets) - 1))
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.L.msspe_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def build_index(self):
+        self._check(self.L.msspe_build_index(self.h))
+
+    def segment_info(self):
+        g, mp, s = C.c_uint64(), C.c_uint32(), C.c_uint32()
+        self._check(self.L.msspe_segment_info(self.h, C.byref(g), C.byref(mp), C.byref(s)))
+        return g.value, mp.value, s.value
+
+    def segment_kmers(self, direction: int) -> np.ndarray:
+        g, _, s = self.segment_info()
+        out = np.empty(max(1, g * s), dtype=np.uint64)
+        self._check(self.L.msspe_get_segment_kmers(self.h, direction, out.ctypes.data, g * s))
+        return out[:g * s].reshape(g, s) if s else out[:0].reshape(g, 0)
+
+    # -- make_kmer_segments_windows_mapping (main.rs:237-255) --
+    def index(self, direction: int):
+        nc, npost = C.c_uint64(), C.c_uint64()
+        self._check(self.L.msspe_get_index(self.h, direction, C.byref(nc), C.byref(npost), None, None, None))
+        codes = np.empty(max(1, nc.value), dtype=np.uint64)
+        offs = np.empty(nc.value + 1, dtype=np.uint64)
+        post = np.empty(max(1, npost.value), dtype=np.uint32)
+        self._check(self.L.msspe_get_index(self.h, direction, C.byref(nc), C.byref(npost), codes.ctypes.data,
+                                           offs.ctypes.data, post.ctypes.data))
+        return codes[:nc.value], offs, post[:npost.value]
+
+    # -- find_candidates_kmers (main.rs:331-406) --
+    def select(self, direction: int, max_iterations: int, max_mismatch_segments: int, mode=SELECT_RECOUNT) -> np.ndarray:
+        out = np.zeros(max(1, max_iterations), dtype=CANDIDATE_DTYPE)
+        n = C.c_uint32()
+        self._check(self.L.msspe_select(self.h, direction, max_iterations, max_mismatch_segments, mode, out.ctypes.data, C.byref(n)))
+        return out[:n.value]
+
+    def select_both(self, max_iterations: int, max_mismatch_segments: int, mode=SELECT_RECOUNT):
+        a = np.zeros(max(1, max_iterations), dtype=CANDIDATE_DTYPE)
+        b = np.zeros(max(1, max_iterations), dtype=CANDIDATE_DTYPE)
+        na, nb = C.c_uint32(), C.c_uint32()
+        self._check(self.L.msspe_select_both(self.h, max_iterations, max_mismatch_segments, mode, a.ctypes.data, C.byref(na),
+                                             b.ctypes.data, C.byref(nb)))
+        return a[:na.value], b[:nb.value]
+
+    def coverage(self, fwd_codes, rev_codes):
+        g, _, _ = self.segment_info()
+        f = np.ascontiguousarray(fwd_codes, dtype=np.uint64)
+        r = np.ascontiguousarray(rev_codes, dtype=np.uint64)
+        cov = np.zeros(max(1, g), dtype=np.uint8)
+        part = np.zeros(max(1, g), dtype=np.uint16)
+        rec = np.zeros(max(1, g), dtype=np.uint32)
+        self._check(self.L.msspe_coverage(self.h, f.ctypes.data, len(f), r.ctypes.data, len(r), cov.ctypes.data,
+                                          part.ctypes.data, rec.ctypes.data, g))
+        return cov[:g], part[:g], rec[:g]
+
+    # -- check_primers (primer.rs:143-166) --
+    def primer_thermo(self, codes, oligo_len=None):
+        codes = np.ascontiguousarray(codes, dtype=np.uint64)
+        n = len(codes)
+        outs = [np.zeros(max(1, n), dtype=np.float64) for _ in range(5)]
+        self._check(self.L.msspe_primer_thermo(self.h, codes.ctypes.data, n, oligo_len or self.k, *[o.ctypes.data for o in outs]))
+        return dict(zip(("tm", "gc", "self_any", "self_end", "hairpin"), [o[:n] for o in outs]))
+
+    def thal_pairs(self, a, b, ttype, cond: ThalCond, oligo_len=None) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        b = np.ascontiguousarray(b if b is not None else a, dtype=np.uint64)
+        out = np.zeros(max(1, len(a)), dtype=THAL_OUT_DTYPE)
+        self._check(self.L.msspe_thal_pairs(self.h, a.ctypes.data, b.ctypes.data, len(a), oligo_len or self.k, ttype,
+                                            C.byref(cond), out.ctypes.data))
+        return out[:len(a)]
+
+    # -- run_ntthal (delta_g.rs:83-153) --
+    def cross_dimer(self, codes, cond: ThalCond, dg_limit: float, row_begin=0, row_end=None, oligo_len=None,
+                    edge_capacity=None, nostruct_capacity=None):
+        codes = np.ascontiguousarray(codes, dtype=np.uint64)
+        n = len(codes)
+        row_end = n if row_end is None else row_end
+        rows = row_end - row_begin
+        ecap = edge_capacity if edge_capacity is not None else max(1024, rows * n)
+        ncap = nostruct_capacity if nostruct_capacity is not None else max(1024, rows * n)
+        edges = np.zeros(ecap, dtype=EDGE_DTYPE)
+        nos = np.zeros(ncap, dtype=np.uint64)
+        ne, nn = C.c_uint64(), C.c_uint64()
+        self._check(self.L.msspe_cross_dimer(self.h, codes.ctypes.data, n, oligo_len or self.k, C.byref(cond), row_begin,
+                                             row_end, dg_limit, edges.ctypes.data, ecap, C.byref(ne), nos.ctypes.data,
+                                             ncap, C.byref(nn)))
+        return edges[:ne.value], nos[:nn.value]
+
+    def set_thal_params_dir(self, path: str):
+        buf = C.create_string_buffer(RAW_PARAMS_BYTES + 64)
+        err = C.create_string_buffer(512)
+        rc = self.L.msspe_thal_params_from_dir(path.encode(), buf, err, 512)
+        if rc != OK:
+            raise MsspeError(rc, err.value.decode())
+        self._check(self.L.msspe_set_thal_params(self.h, buf))
+
+    def timing(self) -> Timing:
+        t = Timing()
+        self._check(self.L.msspe_get_timing(self.h, C.byref(t)))
+        return t
+
+    def reset_timing(self):
+        self._check(self.L.msspe_reset_timing(self.h))
+
+    def synchronize(self):
+        self._check(self.L.msspe_synchronize(self.h))

@@ -1,0 +1,226 @@
+"""GPU parity tests, through the C ABI, for the k-mer engine: K1 (segments), K2 (inverted index), K3 (greedy
+selection).  Bit-exact against the oracle (integer/index work; the f32 tie score is compared by bit pattern)."""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import kmer_oracle as ko  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _fasta_to_arrays(fa: bytes):
+    import msspe_b200 as m
+    recs = ko.to_records(fa)
+    return recs, m.pack_records([r.sequence.encode() for r in recs])
+
+
+def _check_select(eng, O, fa, W, S, w, k, max_iter, mms, mode):
+    for d in (0, 1):
+        got = eng.select(d, max_iter, mms, mode)
+        want = O.select(fa, W, S, w, k, d, max_iter, mms)
+        assert got["code"].tolist() == want["codes"].tolist(), "direction %d winners differ" % d
+        assert got["freq"].tolist() == want["freqs"].tolist()
+        assert got["n_tied"].tolist() == want["n_tied"].tolist()
+        assert got["tie_score"].astype(np.float32).tobytes() == want["scores"].tobytes()
+        t = eng.timing()
+        assert t.select_evals[d] == want["evals"], "coverage evals differ from the reference-equivalent count"
+
+
+@pytest.fixture(scope="module")
+def zika_engine(zika_fasta, oracle_lib):
+    import msspe_b200 as m
+    recs, (bases, offs) = _fasta_to_arrays(zika_fasta)
+    eng = m.Engine(13, 500, 250, 50)
+    eng.load_genomes(bases, offs)
+    eng.build_index()
+    yield eng, recs
+    eng.close()
+
+
+def test_zika_segments_match_oracle(zika_engine, zika_fasta, oracle_lib):
+    eng, recs = zika_engine
+    g, maxp, s = eng.segment_info()
+    assert (g, maxp, s) == (5088, 52, 38)
+    for d in (0, 1):
+        want, part = oracle_lib.segment_slots(zika_fasta, 500, 250, 50, 13, d)
+        got = eng.segment_kmers(d)
+        assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_zika_inverted_index_matches_reference_mapping(zika_engine):
+    eng, recs = zika_engine
+    segs = ko.get_segment_manager(recs, 500, 250, 50, 13)
+    mp = ko.make_kmer_segments_windows_mapping(segs)
+    for d in (0, 1):
+        codes, offs, post = eng.index(d)
+        want = {ko.encode(w): v for (w, dd), v in mp.items() if dd == d}
+        assert len(codes) == len(want) == (7471 if d == 0 else 7737)
+        assert np.all(np.diff(codes.astype(np.int64)) > 0)
+        assert int(offs[-1]) == len(post) == (129943 if d == 0 else 139451)
+        for i in list(range(0, len(codes), 97)) + [len(codes) - 1]:
+            assert post[int(offs[i]):int(offs[i + 1])].tolist() == want[int(codes[i])]
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_zika_greedy_selection_bit_exact(zika_engine, zika_fasta, oracle_lib, mode):
+    eng, _ = zika_engine
+    _check_select(eng, oracle_lib, zika_fasta, 500, 250, 50, 13, 1000, 2, mode)
+    with open(os.path.join(GOLDEN, "zika96_candidates.json")) as f:
+        gold = json.load(f)
+    fwd, rev = eng.select_both(1000, 2, mode)
+    assert [[ko.decode(int(c), 13), int(f)] for c, f in zip(fwd["code"], fwd["freq"])] == gold["fwd"]
+    assert [[ko.decode(int(c), 13), int(f)] for c, f in zip(rev["code"], rev["freq"])] == gold["rev"]
+
+
+def test_zika_stop_rules(zika_engine, zika_fasta, oracle_lib):
+    """max_iterations bound (main.rs:344) and the frequency threshold break after the push (main.rs:387-390)."""
+    eng, _ = zika_engine
+    _check_select(eng, oracle_lib, zika_fasta, 500, 250, 50, 13, 7, 2, 0)
+    _check_select(eng, oracle_lib, zika_fasta, 500, 250, 50, 13, 1000, 94, 0)
+    _check_select(eng, oracle_lib, zika_fasta, 500, 250, 50, 13, 0, 2, 0)
+
+
+def test_reference_unit_vectors_through_the_engine(oracle_lib):
+    """main.rs:897-947 (test_get_segments): 3 records, window 10 / step 5 / search 5 / k 3 -> 6 segments."""
+    import msspe_b200 as m
+    fa = b">seq1\nAACCTTGGAACCTTGG\n>seq2\nAACCTTGGAACCTTG-\n>seq3\n-ACCTTGGAACCTT-G\n"
+    recs, (bases, offs) = _fasta_to_arrays(fa)
+    eng = m.Engine(3, 10, 5, 5)
+    eng.load_genomes(bases, offs)
+    eng.build_index()
+    g, maxp, s = eng.segment_info()
+    assert (g, maxp, s) == (6, 1, 3)
+    f = eng.segment_kmers(0)
+    r = eng.segment_kmers(1)
+    assert [ko.decode(int(c), 3) for c in f[0] if c != m.NO_KMER] == ["AAC", "ACC", "CCT"]
+    assert len([c for c in r[1] if c != m.NO_KMER]) == 3
+    _check_select(eng, oracle_lib, fa, 10, 5, 5, 3, 10, 1, 0)
+    eng.close()
+
+
+def _random_alignment(seed, n, L, p=0.03, gaps=True):
+    rng = np.random.default_rng(seed)
+    anc = rng.integers(0, 4, L)
+    out = []
+    for i in range(n):
+        s = anc.copy()
+        mut = rng.random(L) < p
+        s[mut] = rng.integers(0, 4, int(mut.sum()))
+        ch = np.array(list("ACGT"))[s]
+        if gaps:
+            ch[rng.random(L) < 0.004] = "-"
+            ch[rng.random(L) < 0.002] = "N"
+            ch[rng.random(L) < 0.001] = "R"
+            ch[rng.random(L) < 0.002] = "u"   # lower case / U are normalised by to_records
+        out.append(">g%d x y\n%s\n" % (i, "".join(ch)))
+    return "".join(out).encode()
+
+
+@pytest.mark.parametrize("seed,n,L,W,S,w,k,mms", [
+    (0, 12, 700, 100, 50, 20, 7, 1),
+    (1, 40, 2000, 200, 100, 60, 9, 1),
+    (2, 30, 1501, 500, 250, 50, 13, 1),     # ragged tail: only full windows count
+    (3, 64, 1000, 128, 64, 64, 5, 2),       # tiny k: heavy within-window duplicates, massive ties
+    (4, 20, 1200, 300, 150, 100, 31, 1),    # maximum k
+    (5, 25, 900, 90, 45, 45, 17, 1),        # k > 16: 64-bit codes
+])
+def test_random_alignments_bit_exact(oracle_lib, seed, n, L, W, S, w, k, mms):
+    import msspe_b200 as m
+    fa = _random_alignment(seed, n, L)
+    recs, (bases, offs) = _fasta_to_arrays(fa)
+    eng = m.Engine(k, W, S, w)
+    eng.load_genomes(bases, offs)
+    eng.build_index()
+    for d in (0, 1):
+        want, part = oracle_lib.segment_slots(fa, W, S, w, k, d)
+        assert np.array_equal(eng.segment_kmers(d), want)
+    for mode in (0, 1):
+        _check_select(eng, oracle_lib, fa, W, S, w, k, 60, mms, mode)
+    eng.close()
+
+
+def test_identical_genomes_tie_storm(oracle_lib):
+    """p = 0: every k-mer of a partition ties with every other; the tie-break decides everything."""
+    import msspe_b200 as m
+    fa = _random_alignment(7, 50, 3000, p=0.0, gaps=False)
+    recs, (bases, offs) = _fasta_to_arrays(fa)
+    eng = m.Engine(13, 500, 250, 50)
+    eng.load_genomes(bases, offs)
+    eng.build_index()
+    for mode in (0, 1):
+        _check_select(eng, oracle_lib, fa, 500, 250, 50, 13, 40, 1, mode)
+    eng.close()
+
+
+def test_empty_and_degenerate_inputs(oracle_lib):
+    import msspe_b200 as m
+    # all-gap windows and sequences shorter than the window: zero k-mers, zero segments
+    fa = b">a\n" + b"-" * 1200 + b"\n>b\n" + b"ACGT" * 20 + b"\n"
+    recs, (bases, offs) = _fasta_to_arrays(fa)
+    eng = m.Engine(13, 500, 250, 50)
+    eng.load_genomes(bases, offs)
+    eng.build_index()
+    g, maxp, s = eng.segment_info()
+    assert g == 3 and maxp == 2
+    assert np.all(eng.segment_kmers(0) == m.NO_KMER)
+    assert len(eng.select(0, 10, 1)) == 0 and len(eng.select(1, 10, 1, 1)) == 0
+    fa2 = b">only\nACGTACGT\n"
+    recs, (bases, offs) = _fasta_to_arrays(fa2)
+    eng.load_genomes(bases, offs)
+    eng.build_index()
+    assert eng.segment_info()[0] == 0
+    assert len(eng.select(0, 10, 1)) == 0
+    with pytest.raises(m.MsspeError):
+        eng.load_genomes(np.zeros(0, np.uint8), np.zeros(1, np.uint64))  # "No sequences found", main.rs:652-654
+    eng.close()
+
+
+def test_cfg1_shape_full_size(oracle_lib):
+    """BASELINE configs[0]: 50 x 10 kb, k=13, 500/250/50 -- the reference's own CPU-runnable case, full size."""
+    import msspe_b200 as m
+    from msspe_b200 import synth
+    g, k = synth.make_config("cfg1")
+    fa = synth.to_fasta(g)
+    eng = m.Engine(k, 500, 250, 50)
+    eng.load_genomes(g.reshape(-1), synth.offsets_for(g))
+    eng.build_index()
+    assert eng.segment_info()[0] == 50 * 39
+    for mode in (0, 1):
+        _check_select(eng, oracle_lib, fa, 500, 250, 50, k, 1000, 1, mode)
+    eng.close()
+
+
+def test_cfg2_full_size_properties():
+    """BASELINE configs[1] at full size (1000 x 30 kb): size-independent properties instead of the slow oracle:
+    recount and incremental modes agree exactly; frequencies never increase; every winner's postings are newly
+    marked; evals of the first iteration equal the record count."""
+    import msspe_b200 as m
+    from msspe_b200 import synth
+    g, k = synth.make_config("cfg2")
+    eng = m.Engine(k, 500, 250, 50)
+    eng.load_genomes(g.reshape(-1), synth.offsets_for(g))
+    eng.build_index()
+    G, maxp, s = eng.segment_info()
+    assert G == 1000 * 119 and maxp == 118
+    a0, b0 = eng.select_both(1000, 10, 0)
+    t0 = eng.timing()
+    a1, b1 = eng.select_both(1000, 10, 1)
+    t1 = eng.timing()
+    for x, y in ((a0, a1), (b0, b1)):
+        assert x.tobytes() == y.tobytes()
+        assert np.all(np.diff(x["freq"].astype(np.int64)) <= 0)
+        assert len(set(x["code"].tolist())) == len(x)
+    assert tuple(t0.select_evals) == tuple(t1.select_evals)
+    for d in (0, 1):
+        codes, offs, post = eng.index(d)
+        assert int(offs[-1]) == len(post)
+        assert np.all(np.diff(codes.astype(np.int64)) > 0)
+    cov, part, rec = eng.coverage(a0["code"], b0["code"])
+    assert cov.sum() > 0.5 * G and part.max() == 118 and rec.max() == 999
+    eng.close()

@@ -1,0 +1,149 @@
+"""GPU parity tests, through the C ABI, for the thermodynamic kernels (K4 oligotm, K5 thal dimer, K6 hairpin).
+Tolerance stated by the north star: 0.01 C / 0.01 kcal/mol (= 10 cal/mol); the kernels are written to be
+bit-identical to the FP64 oracle (both built without FMA contraction), which the tests also record."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_TM = 0.01      # Celsius
+TOL_DG = 10.0      # cal/mol  (0.01 kcal/mol)
+
+NTTHAL_GOLDEN = [  # delta_g.rs:197-230
+    ("AGGCCTATATCCA", "GAAGCAGTATTTT", 37.0, "-75.3988", "-25700", "-2315.07", "-35.9834"),
+    ("GCACTTGATGTGA", "GAAGCAGTATTTT", 37.0, "-65.3976", "-22500", "-2216.94", "-44.4018"),
+    ("CTGAAGCAGTATT", "GCATCTTTCCCTT", 25.0, "-101.596", "-33500", "-3209.05", "-24.1908"),
+    ("CTGAAGCAGTATT", "AATTGTGTGGATT", 25.0, "-54.2976", "-17700", "-1511.18", "-70.3113"),
+    ("AGTCCTGCGTGAT", "TGGCCTACATCAG", 25.0, "-141.872", "-45800", "-3500.74", "-11.1906"),
+]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import msspe_b200 as m
+    e = m.Engine(13, 500, 250, 50)
+    yield e
+    e.close()
+
+
+def test_ntthal_golden_blocks_on_gpu(eng):
+    import msspe_b200 as m
+    for a, b, t, ds, dh, dg, tm in NTTHAL_GOLDEN:
+        o = eng.thal_pairs([m.encode_word(a)], [m.encode_word(b)], m.THAL_ANY, m.ThalCond(50, 3, 0, 250, t, 30, 0))[0]
+        assert o["no_structure"] == 0
+        assert ("%g" % o["ds"], "%g" % o["dh"], "%g" % o["dg"], "%g" % o["tm"]) == (ds, dh, dg, tm)
+
+
+def test_primer3_kat_on_gpu(eng):
+    """primer.rs:238-250."""
+    import msspe_b200 as m
+    r = eng.primer_thermo([m.encode_word("AGCCCGTGTAAAC")])
+    assert "%.3f" % r["tm"][0] == "43.727" and "%.3f" % r["gc"][0] == "53.846"
+    assert "%.2f" % r["self_any"][0] == "0.00" and "%.2f" % r["self_end"][0] == "0.00" and "%.2f" % r["hairpin"][0] == "0.00"
+
+
+def _compare(got, want_list, what):
+    nbad = 0
+    exact = 0
+    for g, w in zip(got, want_list):
+        assert int(g["no_structure"]) == w.no_structure, what
+        if w.no_structure:
+            continue
+        assert abs(g["tm"] - w.tm) <= TOL_TM and abs(g["dg"] - w.dg) <= TOL_DG and abs(g["dh"] - w.dh) <= TOL_DG, (what, g, (w.ds, w.dh, w.dg, w.tm))
+        assert int(g["n_bp"]) == w.n_bp
+        exact += (g["tm"] == w.tm and g["dg"] == w.dg and g["ds"] == w.ds and g["dh"] == w.dh)
+        nbad += 1
+    return exact, nbad
+
+
+@pytest.mark.parametrize("k,ttype", [(13, 1), (13, 2), (15, 1), (16, 1), (20, 1), (31, 1), (32, 2), (8, 1)])
+def test_random_pairs_vs_oracle(eng, oracle_lib, k, ttype):
+    import msspe_b200 as m
+    rng = np.random.default_rng(100 + k + ttype)
+    n = 400 if k <= 16 else 150
+    a = rng.integers(0, 4, (n, k))
+    b = rng.integers(0, 4, (n, k))
+    b[: n // 4] = 3 - a[: n // 4, ::-1]            # perfect complements: long helices
+    b[n // 4: n // 2] = 3 - a[n // 4: n // 2, ::-1]
+    flip = rng.random((n // 4, k)) < 0.2          # near-complements: bulges and internal loops
+    b[n // 4: n // 2][flip] = rng.integers(0, 4, int(flip.sum()))
+    a[-8:] = rng.integers(0, 2, (8, k))           # {A,C}-only vs {A,C}-only: no structure
+    b[-8:] = rng.integers(0, 2, (8, k))
+    words_a = ["".join("ACGT"[x] for x in r) for r in a]
+    words_b = ["".join("ACGT"[x] for x in r) for r in b]
+    cond = m.ThalCond(50, 3, 0, 250, 25.0, 30, 0)
+    got = eng.thal_pairs([m.encode_word(w) for w in words_a], [m.encode_word(w) for w in words_b], ttype, cond, oligo_len=k)
+    O = oracle_lib
+    want = [O.thal(x, y, ttype, O.ThalCond(50, 3, 0, 250, 25.0, 30, 0)) for x, y in zip(words_a, words_b)]
+    exact, total = _compare(got, want, "k=%d type=%d" % (k, ttype))
+    assert exact == total, "expected bit-identical FP64 results, %d of %d were" % (exact, total)
+
+
+def test_symmetric_pairs_use_the_symmetric_concentration_term(eng, oracle_lib):
+    import msspe_b200 as m
+    pal = ["ACGTACGTACGT", "GGAATTCCGGAATTCC", "ATATATATATAT"]
+    cond = m.ThalCond(50, 1.5, 0.6, 50, 37.0, 30, 0)
+    for w in pal:
+        got = eng.thal_pairs([m.encode_word(w)], [m.encode_word(w)], m.THAL_ANY, cond, oligo_len=len(w))
+        want = oracle_lib.thal(w, w, 1, oracle_lib.ThalCond(50, 1.5, 0.6, 50, 37.0, 30, 0))
+        _compare(got, [want], w)
+        assert got[0]["tm"] == want.tm
+
+
+@pytest.mark.parametrize("k", [13, 15, 20, 24])
+def test_primer_thermo_vs_oracle(eng, oracle_lib, k):
+    import msspe_b200 as m
+    rng = np.random.default_rng(k)
+    n = 300
+    seqs = rng.integers(0, 4, (n, k))
+    # plant stem-loops so hairpins with Tm > 0 occur
+    for i in range(0, n, 3):
+        stem = rng.integers(3, 6)
+        seqs[i, k - stem:] = 3 - seqs[i, :stem][::-1]
+    words = ["".join("ACGT"[x] for x in r) for r in seqs]
+    r = eng.primer_thermo([m.encode_word(w) for w in words], oligo_len=k)
+    O = oracle_lib
+    c = O.ThalCond(50, 1.5, 0.6, 50, 37.0, 30, 0)
+    n_hp = 0
+    for i, w in enumerate(words):
+        assert abs(r["tm"][i] - O.oligotm(w)) <= 1e-9 and abs(r["gc"][i] - O.gc_percent(w)) <= 1e-12
+        for key, ttype in (("self_any", 1), ("self_end", 2), ("hairpin", 4)):
+            o = O.thal(w, w, ttype, c)
+            want = max(0.0, o.tm)
+            assert abs(r[key][i] - want) <= TOL_TM, (w, key, r[key][i], want)
+            assert r[key][i] == want, (w, key, "not bit-identical")
+            n_hp += (ttype == 4 and want > 0)
+    assert n_hp > 10  # the hairpin path was really exercised
+
+
+def test_cross_dimer_matrix_matches_pair_list_and_oracle(eng, oracle_lib):
+    """run_ntthal replacement: all ordered pairs incl. self (delta_g.rs:64-78), compaction below a limit, the
+    structure-less list; row tiling gives the same lists."""
+    import msspe_b200 as m
+    from msspe_b200 import synth
+    k, n = 13, 96
+    codes = synth.random_primers(n - 3, k, 4)
+    codes = np.concatenate([codes, [m.encode_word("AACCACACACCAA"), m.encode_word("CACACAACCACAC"), m.encode_word("CCCCCCCCCCCCC")]]).astype(np.uint64)
+    cond = m.ThalCond(50, 3, 0, 250, 25.0, 30, 0)
+    a = np.repeat(codes, n)
+    b = np.tile(codes, n)
+    full = eng.thal_pairs(a, b, m.THAL_ANY, cond)
+    limit = -1500.0
+    edges, nos = eng.cross_dimer(codes, cond, limit)
+    want_e = [(i, full["dg"][i]) for i in range(n * n) if not full["no_structure"][i] and full["dg"][i] < limit]
+    want_n = [i for i in range(n * n) if full["no_structure"][i]]
+    assert edges["pair"].tolist() == [p for p, _ in want_e] and edges["dg"].tolist() == [d for _, d in want_e]
+    assert nos.tolist() == want_n and len(want_n) >= 9 and len(want_e) > 20
+    e2, n2 = [], []
+    for rb in range(0, n, 25):
+        e, s = eng.cross_dimer(codes, cond, limit, rb, min(n, rb + 25))
+        e2.append(e)
+        n2.append(s)
+    assert np.concatenate(e2).tobytes() == edges.tobytes() and np.concatenate(n2).tolist() == nos.tolist()
+    O = oracle_lib
+    words = [m.decode_word(c, k) for c in codes]
+    for p in list(range(0, n * n, 131)) + want_n[:5]:
+        w = O.thal(words[p // n], words[p % n], 1, O.ThalCond(50, 3, 0, 250, 25.0, 30, 0))
+        assert int(full["no_structure"][p]) == w.no_structure
+        if not w.no_structure:
+            assert full["dg"][p] == w.dg and full["tm"][p] == w.tm
