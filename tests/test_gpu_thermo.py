@@ -63,10 +63,12 @@ def test_random_pairs_vs_oracle(eng, oracle_lib, k, ttype):
     n = 400 if k <= 16 else 150
     a = rng.integers(0, 4, (n, k))
     b = rng.integers(0, 4, (n, k))
-    b[: n // 4] = 3 - a[: n // 4, ::-1]            # perfect complements: long helices
-    b[n // 4: n // 2] = 3 - a[n // 4: n // 2, ::-1]
-    flip = rng.random((n // 4, k)) < 0.2          # near-complements: bulges and internal loops
-    b[n // 4: n // 2][flip] = rng.integers(0, 4, int(flip.sum()))
+    q = n // 4
+    b[:q] = 3 - a[:q, ::-1]                       # perfect complements: long helices
+    near = 3 - a[q:2 * q, ::-1]
+    flip = rng.random((q, k)) < 0.2               # near-complements: bulges and internal loops
+    near[flip] = rng.integers(0, 4, int(flip.sum()))
+    b[q:2 * q] = near
     a[-8:] = rng.integers(0, 2, (8, k))           # {A,C}-only vs {A,C}-only: no structure
     b[-8:] = rng.integers(0, 2, (8, k))
     words_a = ["".join("ACGT"[x] for x in r) for r in a]
