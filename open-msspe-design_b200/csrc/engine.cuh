@@ -55,6 +55,14 @@ struct SelectCtl {
   unsigned int pad;
   unsigned long long evals;        // sum of live records counted (reference inner-loop executions)
   unsigned long long postings_read;
+  // persistent kernel: per-iteration slots, double-buffered by iteration parity
+  unsigned int pg[2];              // max live frequency
+  unsigned int pt[2];              // number of tied k-mers
+  unsigned long long pk[2];        // best (score bits << 32 | ~code id)
+  unsigned long long t_count_ns;   // time inside the coverage-scoring phases (block 0, %globaltimer)
+  unsigned long long t_tie_ns;     // time inside the tie-break phases
+  unsigned long long t_total_ns;
+  unsigned long long t_dbg[8];     // fine-grained phase timers of block 0 (diagnostic)
 };
 
 struct msspe_ctx {

@@ -16,14 +16,17 @@
 //                  partition_coverage += 1 for each distinct partition of those postings.
 // MSSPE_SELECT_INCREMENTAL replaces count_kernel after the first iteration by decrements of freq[] through the
 // forward index for the newly covered segments (identical results, far less traffic).
+#include <cooperative_groups.h>
+
 #include "engine.cuh"
+#include "select_device.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int CNT_THREADS = MSSPE_CNT_THREADS, CNT_ITEMS = MSSPE_CNT_ITEMS, CNT_TILE = MSSPE_CNT_TILE;  // 8192 postings = 32 KB
+using namespace msspe_sel;
 constexpr int TIE_THREADS = 256, UPD_THREADS = 1024;
-
-__device__ __forceinline__ unsigned int ld_volatile(const unsigned int* p) { return *reinterpret_cast<const volatile unsigned int*>(p); }
 
 __global__ void tile_first_kernel(const uint32_t* __restrict__ post_off, uint32_t n_codes, uint32_t n_tiles,
                                   uint32_t* __restrict__ tile_first) {
@@ -43,10 +46,7 @@ count_kernel(const uint32_t* __restrict__ postings, const uint32_t* __restrict__
              unsigned long long* __restrict__ acc, SelectCtl* ctl) {
   if (ld_volatile(&ctl->done)) return;
   extern __shared__ uint32_t smask[];
-  __shared__ __align__(16) uint8_t nib[CNT_TILE / 4];
-  __shared__ uint16_t bits[CNT_THREADS];
-  __shared__ uint32_t tbase[CNT_THREADS + 1];
-  __shared__ uint32_t wsum[CNT_THREADS / 32];
+  __shared__ CountScratch scratch;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (SMEM_MASK) {
     for (uint32_t i = tid; i < mask_words; i += CNT_THREADS) smask[i] = ignored[i];
@@ -55,82 +55,16 @@ count_kernel(const uint32_t* __restrict__ postings, const uint32_t* __restrict__
   const uint32_t* mask = SMEM_MASK ? smask : ignored;
   uint32_t mymax = 0;
   unsigned long long live_total = 0;
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint32_t tile_start = tile * (uint32_t)CNT_TILE;
-    const uint32_t tile_end = min(n_post, tile_start + (uint32_t)CNT_TILE);
-    // phase 1: coalesced 128-bit loads; one live-bit nibble per uint4
-#pragma unroll
-    for (int j = 0; j < CNT_ITEMS / 4; j++) {
-      const uint32_t n = j * CNT_THREADS + tid;
-      const uint32_t pos = tile_start + 4u * n;
-      uint32_t nibble = 0;
-      if (pos + 3u < tile_end) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(postings + pos));
-        nibble = ((~mask[v.x >> 5] >> (v.x & 31u)) & 1u) | (((~mask[v.y >> 5] >> (v.y & 31u)) & 1u) << 1) |
-                 (((~mask[v.z >> 5] >> (v.z & 31u)) & 1u) << 2) | (((~mask[v.w >> 5] >> (v.w & 31u)) & 1u) << 3);
-      } else {
-        for (uint32_t e = 0; e < 4u; e++)
-          if (pos + e < tile_end) { const uint32_t s = postings[pos + e]; nibble |= ((~mask[s >> 5] >> (s & 31u)) & 1u) << e; }
-      }
-      nib[n] = (uint8_t)nibble;
-    }
-    __syncthreads();
-    // phase 2: per-thread 16-posting bit groups and their exclusive prefix over the tile
-    const uint32_t wv = *reinterpret_cast<const uint32_t*>(&nib[4 * tid]);
-    const uint32_t b16 = (wv & 0xFu) | (((wv >> 8) & 0xFu) << 4) | (((wv >> 16) & 0xFu) << 8) | (((wv >> 24) & 0xFu) << 12);
-    const uint32_t cnt = __popc(b16);
-    uint32_t inc = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t ws = lane < CNT_THREADS / 32 ? wsum[lane] : 0u, wi = ws;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
-      if (lane < CNT_THREADS / 32) wsum[lane] = wi - ws;
-      if (lane == CNT_THREADS / 32 - 1) tbase[CNT_THREADS] = wi;
-    }
-    __syncthreads();
-    bits[tid] = (uint16_t)b16;
-    tbase[tid] = wsum[warp] + inc - cnt;
-    __syncthreads();
-    if (tid == 0) live_total += tbase[CNT_THREADS];
-    // phase 3: per-k-mer sums from prefix differences
-    for (uint32_t c = tile_first[tile] + tid; c < n_codes; c += CNT_THREADS) {
-      const uint32_t a = post_off[c];
-      if (a >= tile_end) break;
-      const uint32_t b = post_off[c + 1];
-      const uint32_t lo = max(a, tile_start) - tile_start, hi = min(b, tile_end) - tile_start;
-      const uint32_t plo = tbase[lo >> 4] + __popc((uint32_t)bits[lo >> 4] & ((1u << (lo & 15u)) - 1u));
-      const uint32_t phi = hi == (uint32_t)CNT_TILE ? tbase[CNT_THREADS]
-                                                    : tbase[hi >> 4] + __popc((uint32_t)bits[hi >> 4] & ((1u << (hi & 15u)) - 1u));
-      const uint32_t sum = phi - plo;
-      if (a >= tile_start && b <= tile_end) {
-        freq[c] = sum;
-        mymax = max(mymax, sum);
-      } else {  // list spans tiles: the last arriving tile owns the total
-        const uint32_t first_tile = a / (uint32_t)CNT_TILE;
-        const uint32_t parts = (b - 1u) / (uint32_t)CNT_TILE - first_tile + 1u;
-        const unsigned long long old = atomicAdd(&acc[first_tile], (1ull << 32) | (unsigned long long)sum);
-        if ((uint32_t)(old >> 32) + 1u == parts) {
-          const uint32_t total = (uint32_t)old + sum;
-          freq[c] = total;
-          acc[first_tile] = 0ull;
-          mymax = max(mymax, total);
-        }
-      }
-    }
-    __syncthreads();
-  }
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    live_total += count_tile<SMEM_MASK>(tile, postings, post_off, tile_first, n_codes, n_post, mask, freq, acc, scratch, mymax);
   // block max -> global max
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
-  if (lane == 0) wsum[warp] = mymax;
+  if (lane == 0) scratch.wsum[warp] = mymax;
   __syncthreads();
   if (tid == 0) {
     uint32_t m = 0;
-    for (int w2 = 0; w2 < CNT_THREADS / 32; w2++) m = max(m, wsum[w2]);
+    for (int w2 = 0; w2 < CNT_THREADS / 32; w2++) m = max(m, scratch.wsum[w2]);
     if (m) atomicMax(&ctl->gmax, m);
     if (live_total) atomicAdd(&ctl->evals, live_total);
   }
@@ -151,40 +85,6 @@ freq_max_kernel(const uint32_t* __restrict__ freq, uint32_t n_codes, SelectCtl* 
     s += __shfl_xor_sync(0xffffffffu, s, o);
   }
   if ((threadIdx.x & 31) == 0) { if (m) atomicMax(&ctl->gmax, m); if (s) atomicAdd(&ctl->evals, s); }
-}
-
-// Warp-cooperative partition_tie_score (main.rs:261-283) of code c.  `seen` = this warp's partition bitmap.
-__device__ float warp_tie_score(uint32_t c, const uint32_t* __restrict__ post_off, const uint32_t* __restrict__ postings,
-                                const uint32_t* __restrict__ ignored, const uint16_t* __restrict__ seg_part,
-                                const uint32_t* __restrict__ cov, uint32_t* seen, uint32_t p_words, int lane) {
-  for (uint32_t w = lane; w < p_words; w += 32) seen[w] = 0u;
-  __syncwarp();
-  const uint32_t a = post_off[c], b = post_off[c + 1];
-  float score = 0.0f;
-  for (uint32_t base = a; base < b; base += 32) {
-    const uint32_t i = base + lane;
-    const bool valid = i < b;
-    const uint32_t seg = valid ? postings[i] : 0u;
-    const bool live = valid && !((ignored[seg >> 5] >> (seg & 31u)) & 1u);
-    const uint32_t p = live ? (uint32_t)seg_part[seg] : 0xFFFF0000u + (uint32_t)lane;
-    const unsigned peers = __match_any_sync(0xffffffffu, p);
-    const bool first = live && (lane == __ffs(peers) - 1);
-    const bool isnew = first && !((seen[p >> 5] >> (p & 31u)) & 1u);
-    const unsigned newmask = __ballot_sync(0xffffffffu, isnew);
-    float term = 0.0f;
-    if (isnew) {
-      atomicOr(&seen[p >> 5], 1u << (p & 31u));
-      term = __fdiv_rn(1.0f, __fadd_rn(__uint2float_rn(cov[p]), 1.0f));  // 1.0 / (already_covered as f32 + 1.0)
-    }
-    __syncwarp();
-    unsigned mm = newmask;
-    while (mm) {  // score += term, strictly in postings order
-      const int l = __ffs(mm) - 1;
-      mm &= mm - 1;
-      score = __fadd_rn(score, __shfl_sync(0xffffffffu, term, l));
-    }
-  }
-  return score;
 }
 
 __global__ void __launch_bounds__(TIE_THREADS)
@@ -209,7 +109,7 @@ tie_kernel(const uint32_t* __restrict__ freq, uint32_t n_codes, const uint32_t* 
       const int l = __ffs(m) - 1;
       m &= m - 1;
       const uint32_t cc = chunk * 32u + l;
-      const float score = warp_tie_score(cc, post_off, postings, ignored, seg_part, cov, seen, p_words, lane);
+      const float score = warp_tie_score<false, false>(cc, post_off, postings, ignored, seg_part, cov, seen, p_words, lane);
       if (lane == 0) {
         const unsigned long long key = ((unsigned long long)__float_as_uint(score) << 32) | (unsigned long long)(0xFFFFFFFFu - cc);
         atomicMax(&ctl->best_key, key);
@@ -266,6 +166,187 @@ update_kernel(const uint64_t* __restrict__ codes, const uint32_t* __restrict__ p
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// The whole greedy loop as ONE persistent cooperative kernel (both directions at once): the covered-segment
+// bitmask of each direction stays in shared memory for the lifetime of the kernel and every block applies the
+// winner's postings to its own copy, so an iteration costs two grid barriers and no launch:
+//   phase A  apply previous winner (smem mask; block 0 also the global mask + partition_coverage), then the
+//            coverage scoring of this block's posting tiles -> freq[], atomicMax of the best frequency
+//   barrier
+//   phase B  stop tests; scan freq[] for ties, warp-per-k-mer partition score, atomicMax of (score, ~id)
+//   barrier
+//   winner   every block reads the winner; block 0 writes the output record
+struct GreedyDir {
+  const uint32_t* postings; const uint32_t* post_off; const uint32_t* tile_first; const uint64_t* codes;
+  uint32_t n_codes, n_post, n_tiles, pad;
+  uint32_t* ignored; uint32_t* freq; unsigned long long* acc; uint32_t* cov; SelectCtl* ctl; msspe_candidate* out;
+};
+struct GreedyArgs {
+  GreedyDir d[2];
+  int ndirs; uint32_t mask_words, p_words, max_iter, mms;
+  uint32_t n_part;   // max partition_no + 1
+  uint32_t n_fp;     // entries of the block-cooperative tie-score scratch (n_part, or 0 = too many partitions)
+  const uint16_t* seg_part;
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <bool SMEM_MASK>
+__global__ void __launch_bounds__(CNT_THREADS)
+greedy_persistent_kernel(const GreedyArgs A) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char dsm[];
+  __shared__ CountScratch scratch;
+  __shared__ uint32_t s_tied[CNT_THREADS];
+  __shared__ uint32_t s_cnt, s_sc[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int WARPS = CNT_THREADS / 32;
+  // dynamic smem: [masks ndirs*mask_words] [pm p_words] [seen p_words] [fp n_fp] [lst n_fp (u64)]
+  uint32_t* smask = reinterpret_cast<uint32_t*>(dsm);
+  uint32_t* pm = smask + (SMEM_MASK ? (size_t)A.ndirs * A.mask_words : 0);
+  uint32_t* seen = pm + A.p_words;
+  uint32_t* fp = seen + A.p_words;
+  unsigned long long* lst = reinterpret_cast<unsigned long long*>(
+      dsm + (((size_t)(reinterpret_cast<unsigned char*>(fp + A.n_fp) - dsm) + 7) & ~(size_t)7));
+  if (SMEM_MASK)
+    for (uint32_t i = tid; i < (uint32_t)A.ndirs * A.mask_words; i += CNT_THREADS) smask[i] = 0u;
+  for (uint32_t i = tid; i < A.p_words; i += CNT_THREADS) pm[i] = 0u;
+  if (tid == 0) s_cnt = 0u;
+  __syncthreads();
+  // block 0 keeps the global state (bitmask, partition_coverage, output); the other blocks score tiles
+  const bool solo = gridDim.x == 1;
+  const bool worker = solo || blockIdx.x > 0;
+  const uint32_t wid = solo ? 0u : blockIdx.x - 1u, nworkers = solo ? 1u : gridDim.x - 1u;
+  bool done[2] = {false, A.ndirs < 2};
+  bool have_win[2] = {false, false};
+  uint32_t win[2] = {0, 0}, n_out[2] = {0, 0}, gsave[2] = {0, 0};
+  unsigned long long evals[2] = {0, 0};
+  const bool lead = blockIdx.x == 0 && tid == 0;
+  unsigned long long t_count = 0, t_tie = 0, t_begin = 0, dbg[4] = {0, 0, 0, 0};
+  if (lead) t_begin = globaltimer_ns();
+  for (uint32_t it = 0;; it++) {
+    const int par = it & 1;
+    unsigned long long ta = 0, tb = 0;
+    if (lead) ta = globaltimer_ns();
+    // ---------------- phase A ----------------
+    for (int d = 0; d < A.ndirs; d++) {
+      if (done[d]) continue;
+      const GreedyDir& D = A.d[d];
+      uint32_t* mask = SMEM_MASK ? smask + (size_t)d * A.mask_words : D.ignored;
+      if (have_win[d]) {  // main.rs:371-378 for the previous winner
+        const uint32_t a = D.post_off[win[d]], b = D.post_off[win[d] + 1];
+        if (SMEM_MASK)
+          for (uint32_t i = a + tid; i < b; i += CNT_THREADS) { const uint32_t sg = __ldg(D.postings + i); atomicOr(&mask[sg >> 5], 1u << (sg & 31u)); }
+        if (blockIdx.x == 0) {
+          for (uint32_t i = a + tid; i < b; i += CNT_THREADS) {
+            const uint32_t sg = __ldg(D.postings + i);
+            atomicOr(&D.ignored[sg >> 5], 1u << (sg & 31u));
+            const uint32_t p = A.seg_part[sg];
+            const uint32_t pbit = 1u << (p & 31u);
+            const uint32_t old = atomicOr(&pm[p >> 5], pbit);
+            if (!(old & pbit)) atomicAdd(&D.cov[p], 1u);
+          }
+          __syncthreads();
+          for (uint32_t i = a + tid; i < b; i += CNT_THREADS) pm[A.seg_part[__ldg(D.postings + i)] >> 5] = 0u;
+        }
+        __syncthreads();
+      }
+      if (worker) {
+        uint32_t mymax = 0;
+        unsigned long long live = 0;
+        for (uint32_t tile = wid; tile < D.n_tiles; tile += nworkers)
+          live += count_tile<SMEM_MASK>(tile, D.postings, D.post_off, D.tile_first, D.n_codes, D.n_post, mask, D.freq, D.acc, scratch, mymax);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
+        if (lane == 0) scratch.wsum[warp] = mymax;
+        __syncthreads();
+        if (tid == 0) {
+          uint32_t m = 0;
+          for (int w2 = 0; w2 < WARPS; w2++) m = max(m, scratch.wsum[w2]);
+          if (m) atomicMax(&D.ctl->pg[par], m);
+          evals[d] += live;
+        }
+        __syncthreads();
+      }
+    }
+    unsigned long long tx = 0;
+    if (lead) tx = globaltimer_ns();
+    grid.sync();
+    if (lead) { tb = globaltimer_ns(); t_count += tb - ta; dbg[0] += tx - ta; dbg[1] += tb - tx; }
+    // ---------------- phase B ----------------
+    for (int d = 0; d < A.ndirs; d++) {
+      if (done[d]) continue;
+      const GreedyDir& D = A.d[d];
+      const uint32_t g = __ldcg(&D.ctl->pg[par]);
+      gsave[d] = g;
+      if (lead) { D.ctl->pg[par ^ 1] = 0; D.ctl->pt[par ^ 1] = 0; D.ctl->pk[par ^ 1] = 0ull; }  // next iteration's slots
+      if (g <= 1u) {  // None or freq == 1: stop before the push (main.rs:353-366)
+        done[d] = true;
+        if (lead) { D.ctl->iterations = it + 1; D.ctl->n_out = n_out[d]; D.ctl->done = 1; }
+        continue;
+      }
+      const uint32_t* mask = SMEM_MASK ? smask + (size_t)d * A.mask_words : D.ignored;
+      for (uint32_t base = blockIdx.x * CNT_THREADS; base < D.n_codes; base += gridDim.x * CNT_THREADS) {
+        const uint32_t c = base + tid;
+        if (c < D.n_codes && __ldcg(D.freq + c) == g) s_tied[atomicAdd(&s_cnt, 1u)] = c;
+        __syncthreads();
+        const uint32_t nt = s_cnt;
+        for (uint32_t t = 0; t < nt; t++) {
+          const uint32_t cc = s_tied[t];
+          float score;
+          if (A.n_fp) {
+            score = block_tie_score<SMEM_MASK, true, CNT_THREADS>(cc, D.post_off, D.postings, mask, A.seg_part, D.cov, A.n_part, fp, lst, s_sc);
+          } else {  // more partitions than the shared-memory scratch holds: one warp, bitmap of seen partitions
+            if (warp == 0) {
+              const float sw = warp_tie_score<SMEM_MASK, true>(cc, D.post_off, D.postings, mask, A.seg_part, D.cov, seen, A.p_words, lane);
+              if (lane == 0) s_sc[1] = __float_as_uint(sw);
+            }
+            __syncthreads();
+            score = __uint_as_float(s_sc[1]);
+          }
+          if (tid == 0) atomicMax(&D.ctl->pk[par], ((unsigned long long)__float_as_uint(score) << 32) | (unsigned long long)(0xFFFFFFFFu - cc));
+          __syncthreads();
+        }
+        if (tid == 0) { if (nt) atomicAdd(&D.ctl->pt[par], nt); s_cnt = 0u; }
+        __syncthreads();
+      }
+    }
+    if (lead) tx = globaltimer_ns();
+    grid.sync();
+    if (lead) { const unsigned long long ty = globaltimer_ns(); t_tie += ty - tb; dbg[2] += tx - tb; dbg[3] += ty - tx; }
+    // ---------------- winner ----------------
+    bool all_done = true;
+    for (int d = 0; d < A.ndirs; d++) {
+      if (done[d]) continue;
+      const GreedyDir& D = A.d[d];
+      const unsigned long long key = __ldcg(&D.ctl->pk[par]);
+      const uint32_t c = 0xFFFFFFFFu - (uint32_t)key;
+      win[d] = c; have_win[d] = true;
+      if (lead) {
+        msspe_candidate w;
+        w.code = D.codes[c]; w.freq = gsave[d]; w.n_tied = __ldcg(&D.ctl->pt[par]); w.tie_score = __uint_as_float((uint32_t)(key >> 32)); w.reserved = 0;
+        D.out[n_out[d]] = w;
+      }
+      n_out[d]++;
+      if (gsave[d] < A.mms || n_out[d] >= A.max_iter) {  // main.rs:387-390 and the loop bound :344
+        done[d] = true;
+        if (lead) { D.ctl->iterations = it + 1; D.ctl->n_out = n_out[d]; D.ctl->done = 1; }
+      }
+      all_done = all_done && done[d];
+    }
+    if (all_done) break;
+  }
+  for (int d = 0; d < A.ndirs; d++) {
+    if (tid == 0 && evals[d]) atomicAdd(&A.d[d].ctl->evals, evals[d]);
+    if (lead) { A.d[d].ctl->t_count_ns = t_count; A.d[d].ctl->t_tie_ns = t_tie; A.d[d].ctl->t_total_ns = globaltimer_ns() - t_begin; for (int q = 0; q < 4; q++) A.d[d].ctl->t_dbg[q] = dbg[q]; }
+  }
+}
+
 struct DirRun {
   DirIndex* D; cudaStream_t st; uint32_t* tile_first; uint32_t n_tiles; bool smem_mask; uint32_t mask_words;
   unsigned count_grid; size_t count_smem; unsigned tie_grid; size_t tie_smem; uint32_t p_words;
@@ -312,12 +393,19 @@ int prepare_dir(msspe_ctx* c, int dir, uint32_t max_iter, cudaStream_t st, DirRu
   return MSSPE_OK;
 }
 
-void launch_iteration(msspe_ctx* c, DirRun& r, uint32_t max_iter, uint32_t mms, uint32_t mode, bool first) {
+void launch_iteration(msspe_ctx* c, DirRun& r, uint32_t max_iter, uint32_t mms, uint32_t mode, bool first,
+                      std::vector<cudaEvent_t>* pev) {
   DirIndex& D = *r.D;
   const uint32_t nc = (uint32_t)D.n_codes, np = (uint32_t)D.n_records;
   const bool recount = mode == MSSPE_SELECT_RECOUNT || first;
   if (recount) {
     if (r.n_tiles) {
+      if (pev) {  // profiling: bracket this launch with events on its own stream
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        pev->push_back(e0); pev->push_back(e1);
+        cudaEventRecord(e0, r.st);
+      }
       if (r.smem_mask)
         count_kernel<true><<<r.count_grid, CNT_THREADS, r.count_smem, r.st>>>(D.postings, D.post_off, r.tile_first, nc, np, r.n_tiles,
                                                                                D.ignored, r.mask_words, D.freq, D.acc, D.ctl);
@@ -325,6 +413,7 @@ void launch_iteration(msspe_ctx* c, DirRun& r, uint32_t max_iter, uint32_t mms, 
         count_kernel<false><<<r.count_grid, CNT_THREADS, 0, r.st>>>(D.postings, D.post_off, r.tile_first, nc, np, r.n_tiles,
                                                                      D.ignored, r.mask_words, D.freq, D.acc, D.ctl);
       c->timing.kernel_launches++;
+      if (pev) cudaEventRecord(pev->back(), r.st);
     }
   } else if (nc) {
     freq_max_kernel<<<min(592u, (nc + 255u) / 256u), 256, 0, r.st>>>(D.freq, nc, D.ctl);
@@ -344,11 +433,89 @@ void launch_iteration(msspe_ctx* c, DirRun& r, uint32_t max_iter, uint32_t mms, 
   c->timing.kernel_launches++;
 }
 
+int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max_iter, uint32_t mms,
+                          msspe_candidate** outs, uint32_t** n_outs) {
+  cudaStream_t st = c->stream;
+  const uint64_t G = c->n_segments;
+  GreedyArgs A{};
+  A.ndirs = ndirs; A.max_iter = max_iter; A.mms = mms; A.seg_part = c->d_seg_part;
+  A.mask_words = (uint32_t)div_up_u64(G, 32) + 1u;
+  A.p_words = (c->max_partition + 32u) / 32u;
+  MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[2], st));
+  for (int i = 0; i < ndirs; i++) {
+    DirIndex& D = c->dir[dirs[i]];
+    if (D.out_capacity < max_iter) {
+      cudaFree(D.out); D.out = nullptr;
+      MSSPE_CUDA_TRY(c, cudaMalloc(&D.out, (uint64_t)max_iter * sizeof(msspe_candidate)));
+      D.out_capacity = max_iter;
+    }
+    MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.ignored, 0, (size_t)A.mask_words * 4, st));
+    MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.cov, 0, 65536 * 4, st));
+    MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.ctl, 0, sizeof(SelectCtl), st));
+    MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.acc, 0, (uint64_t)(D.n_tiles + 1) * 8, st));
+    GreedyDir& g = A.d[i];
+    g.postings = D.postings; g.post_off = D.post_off; g.tile_first = D.tile_first; g.codes = D.codes;
+    g.n_codes = (uint32_t)D.n_codes; g.n_post = (uint32_t)D.n_records; g.n_tiles = D.n_tiles;
+    g.ignored = D.ignored; g.freq = D.freq; g.acc = D.acc; g.cov = D.cov; g.ctl = D.ctl; g.out = D.out;
+  }
+  A.n_part = c->max_partition + 1u;
+  A.n_fp = A.n_part <= 4096u ? A.n_part : 0u;
+  const size_t aux = (size_t)2 * A.p_words * 4 + (size_t)A.n_fp * 4 + (size_t)A.n_fp * 8 + 16;
+  const size_t mask_bytes = (size_t)ndirs * A.mask_words * 4;
+  const bool smem_mask = mask_bytes + aux + sizeof(CountScratch) + 1024 <= c->smem_optin;
+  const size_t smem = aux + (smem_mask ? mask_bytes : 0);
+  if (smem + sizeof(CountScratch) + 1024 > c->smem_optin) {
+    c->set_error("msspe_select: %u partitions need %zu B of shared memory (device offers %zu)", c->max_partition + 1, smem, c->smem_optin);
+    return MSSPE_ERR_CAPACITY;
+  }
+  int per_sm = 0;
+  void* fn = smem_mask ? (void*)greedy_persistent_kernel<true> : (void*)greedy_persistent_kernel<false>;
+  MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem_mask) MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_persistent_kernel<true>, CNT_THREADS, smem));
+  else MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_persistent_kernel<false>, CNT_THREADS, smem));
+  if (per_sm < 1) { c->set_error("msspe_select: persistent kernel does not fit on an SM"); return MSSPE_ERR_CAPACITY; }
+  int want = 2;
+  if (const char* e = getenv("MSSPE_PERSIST_BLOCKS_PER_SM")) want = atoi(e) > 0 ? atoi(e) : want;
+  if (per_sm > want) per_sm = want;
+  const unsigned grid = (unsigned)c->sm_count * (unsigned)per_sm;
+  void* kargs[] = {(void*)&A};
+  MSSPE_CUDA_TRY(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(CNT_THREADS), kargs, smem, st));
+  c->timing.kernel_launches++;
+  for (int i = 0; i < ndirs; i++)
+    MSSPE_CUDA_TRY(c, cudaMemcpyAsync(&c->h_ctl[i], c->dir[dirs[i]].ctl, sizeof(SelectCtl), cudaMemcpyDeviceToHost, st));
+  MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
+  MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  MSSPE_CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
+  for (int i = 0; i < ndirs; i++) {
+    const int d = dirs[i];
+    const uint32_t n = c->h_ctl[i].n_out;
+    if (n) MSSPE_CUDA_TRY(c, cudaMemcpyAsync(outs[i], c->dir[d].out, (size_t)n * sizeof(msspe_candidate), cudaMemcpyDeviceToHost, st));
+    *n_outs[i] = n;
+    c->timing.select_ms[d] = ms;
+    c->timing.select_evals[d] = c->h_ctl[i].evals;
+    c->timing.select_iterations[d] = c->h_ctl[i].iterations;
+    c->timing.select_postings_read[d] = (uint64_t)c->h_ctl[i].iterations * c->dir[d].n_records;
+    c->timing.count_kernel_launches[d] = c->h_ctl[i].iterations;
+    // phases of the two directions are interleaved inside one kernel: attribute the phase time once (to dir 0)
+    c->timing.count_kernel_ms[d] = i == 0 ? (float)(c->h_ctl[i].t_count_ns * 1e-6) : 0.f;
+    if (getenv("MSSPE_DEBUG_TIMERS") && i == 0)
+      fprintf(stderr, "[msspe] persistent greedy: total %.3f ms, iterations %u | phaseA work %.3f sync %.3f | phaseB work %.3f sync %.3f (block 0)\n",
+              c->h_ctl[i].t_total_ns * 1e-6, c->h_ctl[i].iterations, c->h_ctl[i].t_dbg[0] * 1e-6, c->h_ctl[i].t_dbg[1] * 1e-6,
+              c->h_ctl[i].t_dbg[2] * 1e-6, c->h_ctl[i].t_dbg[3] * 1e-6);
+  }
+  MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+  return MSSPE_OK;
+}
+
 int run_select(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max_iter, uint32_t mms, uint32_t mode,
                msspe_candidate** outs, uint32_t** n_outs) {
   if (!c->built) { c->set_error("msspe_select: index not built"); return MSSPE_ERR_STATE; }
+  const bool batched = (mode & MSSPE_SELECT_BATCHED) != 0;
+  mode &= ~(uint32_t)MSSPE_SELECT_BATCHED;
   if (mode > MSSPE_SELECT_INCREMENTAL) { c->set_error("msspe_select: unknown mode %u", mode); return MSSPE_ERR_INVALID; }
   MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
+  if (!batched && mode == MSSPE_SELECT_RECOUNT && max_iter > 0) return run_select_persistent(c, ndirs, dirs, max_iter, mms, outs, n_outs);
   DirRun runs[2];
   cudaStream_t streams[2] = {c->stream, c->stream2};
   cudaEvent_t ev_b[2] = {c->ev[2], c->ev[4]}, ev_e[2] = {c->ev[3], c->ev[5]};
@@ -361,6 +528,7 @@ int run_select(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max_iter, uint
     int rc = prepare_dir(c, dirs[i], max_iter, streams[i], &runs[i]);
     if (rc) return rc;
   }
+  std::vector<cudaEvent_t> pev[2];
   bool finished[2] = {max_iter == 0, max_iter == 0};
   uint32_t issued = 0;
   const uint32_t BATCH = 32;
@@ -368,7 +536,7 @@ int run_select(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max_iter, uint
     const uint32_t nb = (max_iter - issued) < BATCH ? (max_iter - issued) : BATCH;
     for (uint32_t it = 0; it < nb; it++)
       for (int i = 0; i < ndirs; i++)
-        if (!finished[i]) launch_iteration(c, runs[i], max_iter, mms, mode, issued + it == 0);
+        if (!finished[i]) launch_iteration(c, runs[i], max_iter, mms, mode, issued + it == 0, c->profiling ? &pev[i] : nullptr);
     issued += nb;
     for (int i = 0; i < ndirs; i++)
       if (!finished[i]) MSSPE_CUDA_TRY(c, cudaMemcpyAsync(&c->h_ctl[i], runs[i].D->ctl, sizeof(SelectCtl), cudaMemcpyDeviceToHost, streams[i]));
@@ -393,6 +561,13 @@ int run_select(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max_iter, uint
     const uint64_t count_launches = mode == MSSPE_SELECT_RECOUNT ? c->h_ctl[i].iterations : (c->h_ctl[i].iterations ? 1 : 0);
     c->timing.select_postings_read[d] = count_launches * runs[i].D->n_records;
     c->timing.count_kernel_launches[d] = (uint32_t)count_launches;
+    float sum_ms = 0.f;
+    for (size_t e = 0; e + 1 < pev[i].size(); e += 2) {
+      float ms = 0.f;
+      if (e / 2 < count_launches && cudaEventElapsedTime(&ms, pev[i][e], pev[i][e + 1]) == cudaSuccess) sum_ms += ms;
+      cudaEventDestroy(pev[i][e]); cudaEventDestroy(pev[i][e + 1]);
+    }
+    c->timing.count_kernel_ms[d] = sum_ms;
   }
   if (ndirs == 2) {  // join
     MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev_join, c->stream2));

@@ -40,7 +40,7 @@ int read_keyed(const std::string& path, char seqs[][8], double* vals, int cap) {
   int n = 0;
   while (n < cap && fscanf(f, "%63s %63s", s, v) == 2) {
     memset(seqs[n], 0, 8);
-    strncpy(seqs[n], s, 7);
+    memcpy(seqs[n], s, strnlen(s, 7));
     vals[n] = strcmp(v, "inf") == 0 ? (double)INFINITY : atof(v);
     n++;
   }

@@ -67,7 +67,7 @@ def test_zika_inverted_index_matches_reference_mapping(zika_engine):
             assert post[int(offs[i]):int(offs[i + 1])].tolist() == want[int(codes[i])]
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 0x100])
 def test_zika_greedy_selection_bit_exact(zika_engine, zika_fasta, oracle_lib, mode):
     eng, _ = zika_engine
     _check_select(eng, oracle_lib, zika_fasta, 500, 250, 50, 13, 1000, 2, mode)
@@ -140,7 +140,7 @@ def test_random_alignments_bit_exact(oracle_lib, seed, n, L, W, S, w, k, mms):
     for d in (0, 1):
         want, part = oracle_lib.segment_slots(fa, W, S, w, k, d)
         assert np.array_equal(eng.segment_kmers(d), want)
-    for mode in (0, 1):
+    for mode in (0, 1, 0x100):
         _check_select(eng, oracle_lib, fa, W, S, w, k, 60, mms, mode)
     eng.close()
 
@@ -153,7 +153,7 @@ def test_identical_genomes_tie_storm(oracle_lib):
     eng = m.Engine(13, 500, 250, 50)
     eng.load_genomes(bases, offs)
     eng.build_index()
-    for mode in (0, 1):
+    for mode in (0, 1, 0x100):
         _check_select(eng, oracle_lib, fa, 500, 250, 50, 13, 40, 1, mode)
     eng.close()
 
@@ -191,7 +191,7 @@ def test_cfg1_shape_full_size(oracle_lib):
     eng.load_genomes(g.reshape(-1), synth.offsets_for(g))
     eng.build_index()
     assert eng.segment_info()[0] == 50 * 39
-    for mode in (0, 1):
+    for mode in (0, 1, 0x100):
         _check_select(eng, oracle_lib, fa, 500, 250, 50, k, 1000, 1, mode)
     eng.close()
 
