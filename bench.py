@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--mode", default="recount", choices=["recount", "incremental"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-thal", action="store_true")
+    ap.add_argument("--batched", action="store_true", help="one launch per phase instead of the persistent kernel (for per-launch ncu numbers)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -173,6 +174,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     mode = m.SELECT_RECOUNT if args.mode == "recount" else m.SELECT_INCREMENTAL
+    if args.batched:
+        mode |= m.SELECT_BATCHED
     # ---- synthetic input: every rank gets its own genome set of the cfg2 shape (weak scaling) ----
     cfgd = dict(synth.CONFIGS["cfg2"])
     k = cfgd.pop("k")
@@ -337,7 +340,7 @@ def main():
             "metric": "kmer_coverage_evals_per_s", "value": total_evals / t_dev, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "select_mode": args.mode, "genomes_per_gpu": n_rec, "genome_length": L,
+            "config": {"workload": WORKLOAD, "select_mode": args.mode + ("+batched-launches" if args.batched else "+persistent-kernel" if args.mode == "recount" else ""), "genomes_per_gpu": n_rec, "genome_length": L,
                        "max_iterations": MAX_ITER, "max_mismatch_segments": mms,
                        "l2": "inputs per step (30 MB genomes + 2 x 18 MB postings) are smaller than L2; each step rebuilds the index from the genome bytes, nothing is cached across steps",
                        "iterations": [int(res_dev[0][4].select_iterations[0]), int(res_dev[0][4].select_iterations[1])],
