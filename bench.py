@@ -93,7 +93,7 @@ def clock_sampler(stop, out, gpu_index):
                 out.append(f)
         except Exception:
             pass
-        stop.wait(0.2)
+        stop.wait(0.05)
 
 
 def summarize_clocks(samples):
@@ -281,26 +281,28 @@ def main():
     # ---- secondary metric: thal dimer pairs / s, pair matrix row-tiled across ranks ----
     thal = None
     if not args.no_thal:
+        from msspe_b200 import distributed as D
         pool = synth.random_primers(THAL_POOL, 13, 4)
         cond = m.ThalCond(50, 3, 0, 250, 25.0, 30, 0)
-        rows = THAL_POOL // world
-        rb, re_ = rank * rows, (THAL_POOL if rank == world - 1 else (rank + 1) * rows)
-        eng.cross_dimer(pool, cond, -9000.0 + 1.0, rb, min(re_, rb + 64), edge_capacity=1 << 20, nostruct_capacity=1 << 16)
+        rb, re_ = D.row_block(THAL_POOL, rank, world)
+        eng.cross_dimer(pool, cond, -9000.0 + 1.0, rb, min(re_, rb + 64), edge_capacity=1 << 20, nostruct_capacity=1 << 16)  # warm-up
+        kernel_ms = []
+
+        def compute_rows(b0, b1):
+            r = eng.cross_dimer(pool, cond, -9000.0 + 1.0, b0, b1, edge_capacity=1 << 22, nostruct_capacity=1 << 20)
+            kernel_ms.append(float(eng.timing().dimer_ms))
+            return r
+
         barrier()
         t0 = time.perf_counter()
-        edges, nos = eng.cross_dimer(pool, cond, -9000.0 + 1.0, rb, re_, edge_capacity=1 << 22, nostruct_capacity=1 << 20)
+        # rows tiled across ranks, compacted edge lists merged with one NCCL all_gather (msspe_b200/distributed.py)
+        edges, nos = D.cross_dimer_sharded(compute_rows, THAL_POOL, m.EDGE_DTYPE, dist if world > 1 else None, dev)
         torch.cuda.synchronize(dev)
         t_thal = time.perf_counter() - t0
-        k_ms = float(eng.timing().dimer_ms)
-        tt = torch.tensor([t_thal, k_ms / 1e3, float(len(edges))], dtype=torch.float64, device=dev)
+        tt = torch.tensor([t_thal, sum(kernel_ms) / 1e3], dtype=torch.float64, device=dev)
         if world > 1:
-            mx = tt.clone()
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            sm = tt.clone()
-            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-            t_thal, k_s, n_edges = float(mx[0]), float(mx[1]), int(sm[2])
-        else:
-            k_s, n_edges = k_ms / 1e3, len(edges)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_thal, k_s, n_edges = float(tt[0]), float(tt[1]), int(len(edges))
         pairs = THAL_POOL * THAL_POOL
         thal = {"metric": "thal_dimer_pairs_per_s", "value": pairs / t_thal, "unit": "pairs/s", "pairs": pairs,
                 "pool": "%d uniform-random 13-mers (cfg4 shape, seed 4), mv 50 dv 3 dNTP 0 DNA 250 nM 25 C" % THAL_POOL,

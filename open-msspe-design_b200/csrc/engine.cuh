@@ -42,7 +42,8 @@ struct DirIndex {
   uint32_t n_tiles = 0;
 };
 
-constexpr int MSSPE_CNT_THREADS = 512, MSSPE_CNT_ITEMS = 16, MSSPE_CNT_TILE = MSSPE_CNT_THREADS * MSSPE_CNT_ITEMS;
+constexpr int MSSPE_CNT_THREADS = 512;  // threads per block of the K3 kernels
+constexpr int MSSPE_CNT_TILE = 512;     // postings per warp tile of the coverage scoring (32 lanes x 4 x uint4)
 
 // Device control block of the greedy loop (one per direction).
 struct SelectCtl {

@@ -46,28 +46,23 @@ count_kernel(const uint32_t* __restrict__ postings, const uint32_t* __restrict__
              unsigned long long* __restrict__ acc, SelectCtl* ctl) {
   if (ld_volatile(&ctl->done)) return;
   extern __shared__ uint32_t smask[];
-  __shared__ CountScratch scratch;
+  __shared__ uint32_t s_max;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (SMEM_MASK) {
+  constexpr int WARPS = CNT_THREADS / 32;
+  if (tid == 0) s_max = 0u;
+  if (SMEM_MASK)
     for (uint32_t i = tid; i < mask_words; i += CNT_THREADS) smask[i] = ignored[i];
-    __syncthreads();
-  }
+  __syncthreads();
   const uint32_t* mask = SMEM_MASK ? smask : ignored;
   uint32_t mymax = 0;
   unsigned long long live_total = 0;
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-    live_total += count_tile<SMEM_MASK>(tile, postings, post_off, tile_first, n_codes, n_post, mask, freq, acc, scratch, mymax);
-  // block max -> global max
+  for (uint32_t wt = blockIdx.x * WARPS + warp; wt < n_tiles; wt += gridDim.x * WARPS)
+    live_total += warp_count_tile<SMEM_MASK>(wt, postings, post_off, tile_first, n_codes, n_post, mask, freq, acc, mymax, lane);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
-  if (lane == 0) scratch.wsum[warp] = mymax;
+  if (lane == 0) { if (mymax) atomicMax(&s_max, mymax); if (live_total) atomicAdd(&ctl->evals, live_total); }
   __syncthreads();
-  if (tid == 0) {
-    uint32_t m = 0;
-    for (int w2 = 0; w2 < CNT_THREADS / 32; w2++) m = max(m, scratch.wsum[w2]);
-    if (m) atomicMax(&ctl->gmax, m);
-    if (live_total) atomicAdd(&ctl->evals, live_total);
-  }
+  if (tid == 0 && s_max) atomicMax(&ctl->gmax, s_max);
 }
 
 // max over freq[] (incremental mode: freq is maintained by decrements, so only the max is needed)
@@ -188,7 +183,22 @@ struct GreedyArgs {
   uint32_t n_part;   // max partition_no + 1
   uint32_t n_fp;     // entries of the block-cooperative tie-score scratch (n_part, or 0 = too many partitions)
   const uint16_t* seg_part;
+  unsigned int* barrier;  // grid barrier arrival counter (zeroed before the launch)
 };
+
+// Grid-wide barrier for a cooperatively launched (co-resident) grid: one arrival counter, monotonically
+// growing target.  __syncthreads + cumulative fence publish the block's writes; readers use L2-coherent loads.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (ld_volatile(counter) < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -199,11 +209,10 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 template <bool SMEM_MASK>
 __global__ void __launch_bounds__(CNT_THREADS)
 greedy_persistent_kernel(const GreedyArgs A) {
-  cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char dsm[];
-  __shared__ CountScratch scratch;
+  unsigned int bar_target = 0;
   __shared__ uint32_t s_tied[CNT_THREADS];
-  __shared__ uint32_t s_cnt, s_sc[2];
+  __shared__ uint32_t s_cnt, s_sc[2], s_max[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int WARPS = CNT_THREADS / 32;
   // dynamic smem: [masks ndirs*mask_words] [pm p_words] [seen p_words] [fp n_fp] [lst n_fp (u64)]
@@ -216,7 +225,7 @@ greedy_persistent_kernel(const GreedyArgs A) {
   if (SMEM_MASK)
     for (uint32_t i = tid; i < (uint32_t)A.ndirs * A.mask_words; i += CNT_THREADS) smask[i] = 0u;
   for (uint32_t i = tid; i < A.p_words; i += CNT_THREADS) pm[i] = 0u;
-  if (tid == 0) s_cnt = 0u;
+  if (tid == 0) { s_cnt = 0u; s_max[0] = 0u; s_max[1] = 0u; }
   __syncthreads();
   // block 0 keeps the global state (bitmask, partition_coverage, output); the other blocks score tiles
   const bool solo = gridDim.x == 1;
@@ -227,12 +236,15 @@ greedy_persistent_kernel(const GreedyArgs A) {
   uint32_t win[2] = {0, 0}, n_out[2] = {0, 0}, gsave[2] = {0, 0};
   unsigned long long evals[2] = {0, 0};
   const bool lead = blockIdx.x == 0 && tid == 0;
+  const bool wlead = blockIdx.x == (gridDim.x > 1 ? 1 : 0) && tid == 0;  // a worker block's clock (diagnostic)
+  unsigned long long wt0 = 0, wdbg[4] = {0, 0, 0, 0};
   unsigned long long t_count = 0, t_tie = 0, t_begin = 0, dbg[4] = {0, 0, 0, 0};
   if (lead) t_begin = globaltimer_ns();
   for (uint32_t it = 0;; it++) {
     const int par = it & 1;
     unsigned long long ta = 0, tb = 0;
     if (lead) ta = globaltimer_ns();
+    if (wlead) wt0 = globaltimer_ns();
     // ---------------- phase A ----------------
     for (int d = 0; d < A.ndirs; d++) {
       if (done[d]) continue;
@@ -259,24 +271,22 @@ greedy_persistent_kernel(const GreedyArgs A) {
       if (worker) {
         uint32_t mymax = 0;
         unsigned long long live = 0;
-        for (uint32_t tile = wid; tile < D.n_tiles; tile += nworkers)
-          live += count_tile<SMEM_MASK>(tile, D.postings, D.post_off, D.tile_first, D.n_codes, D.n_post, mask, D.freq, D.acc, scratch, mymax);
+        for (uint32_t wt = wid * WARPS + warp; wt < D.n_tiles; wt += nworkers * WARPS)
+          live += warp_count_tile<SMEM_MASK>(wt, D.postings, D.post_off, D.tile_first, D.n_codes, D.n_post, mask, D.freq, D.acc, mymax, lane);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
-        if (lane == 0) scratch.wsum[warp] = mymax;
-        __syncthreads();
-        if (tid == 0) {
-          uint32_t m = 0;
-          for (int w2 = 0; w2 < WARPS; w2++) m = max(m, scratch.wsum[w2]);
-          if (m) atomicMax(&D.ctl->pg[par], m);
-          evals[d] += live;
-        }
-        __syncthreads();
+        if (lane == 0) { if (mymax) atomicMax(&s_max[d], mymax); evals[d] += live; }
       }
     }
+    __syncthreads();
+    if (tid == 0 && worker)
+      for (int d = 0; d < A.ndirs; d++)
+        if (!done[d]) { if (s_max[d]) atomicMax(&A.d[d].ctl->pg[par], s_max[d]); s_max[d] = 0u; }
     unsigned long long tx = 0;
     if (lead) tx = globaltimer_ns();
-    grid.sync();
+    if (wlead) { const unsigned long long t = globaltimer_ns(); wdbg[0] += t - wt0; wt0 = t; }
+    grid_barrier(A.barrier, bar_target);
+    if (wlead) { const unsigned long long t = globaltimer_ns(); wdbg[1] += t - wt0; wt0 = t; }
     if (lead) { tb = globaltimer_ns(); t_count += tb - ta; dbg[0] += tx - ta; dbg[1] += tb - tx; }
     // ---------------- phase B ----------------
     for (int d = 0; d < A.ndirs; d++) {
@@ -317,7 +327,9 @@ greedy_persistent_kernel(const GreedyArgs A) {
       }
     }
     if (lead) tx = globaltimer_ns();
-    grid.sync();
+    if (wlead) { const unsigned long long t = globaltimer_ns(); wdbg[2] += t - wt0; wt0 = t; }
+    grid_barrier(A.barrier, bar_target);
+    if (wlead) { const unsigned long long t = globaltimer_ns(); wdbg[3] += t - wt0; wt0 = t; }
     if (lead) { const unsigned long long ty = globaltimer_ns(); t_tie += ty - tb; dbg[2] += tx - tb; dbg[3] += ty - tx; }
     // ---------------- winner ----------------
     bool all_done = true;
@@ -342,8 +354,9 @@ greedy_persistent_kernel(const GreedyArgs A) {
     if (all_done) break;
   }
   for (int d = 0; d < A.ndirs; d++) {
-    if (tid == 0 && evals[d]) atomicAdd(&A.d[d].ctl->evals, evals[d]);
+    if (lane == 0 && evals[d]) atomicAdd(&A.d[d].ctl->evals, evals[d]);
     if (lead) { A.d[d].ctl->t_count_ns = t_count; A.d[d].ctl->t_tie_ns = t_tie; A.d[d].ctl->t_total_ns = globaltimer_ns() - t_begin; for (int q = 0; q < 4; q++) A.d[d].ctl->t_dbg[q] = dbg[q]; }
+    if (wlead) for (int q = 0; q < 4; q++) A.d[d].ctl->t_dbg[4 + q] = wdbg[q];
   }
 }
 
@@ -439,6 +452,8 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
   const uint64_t G = c->n_segments;
   GreedyArgs A{};
   A.ndirs = ndirs; A.max_iter = max_iter; A.mms = mms; A.seg_part = c->d_seg_part;
+  A.barrier = c->dir[dirs[0]].pmark;  // 8 KB scratch, unused by this kernel
+  MSSPE_CUDA_TRY(c, cudaMemsetAsync(A.barrier, 0, 4, st));
   A.mask_words = (uint32_t)div_up_u64(G, 32) + 1u;
   A.p_words = (c->max_partition + 32u) / 32u;
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[2], st));
@@ -462,9 +477,9 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
   A.n_fp = A.n_part <= 4096u ? A.n_part : 0u;
   const size_t aux = (size_t)2 * A.p_words * 4 + (size_t)A.n_fp * 4 + (size_t)A.n_fp * 8 + 16;
   const size_t mask_bytes = (size_t)ndirs * A.mask_words * 4;
-  const bool smem_mask = mask_bytes + aux + sizeof(CountScratch) + 1024 <= c->smem_optin;
+  const bool smem_mask = mask_bytes + aux + (size_t)4096 + 1024 <= c->smem_optin;
   const size_t smem = aux + (smem_mask ? mask_bytes : 0);
-  if (smem + sizeof(CountScratch) + 1024 > c->smem_optin) {
+  if (smem + (size_t)4096 + 1024 > c->smem_optin) {
     c->set_error("msspe_select: %u partitions need %zu B of shared memory (device offers %zu)", c->max_partition + 1, smem, c->smem_optin);
     return MSSPE_ERR_CAPACITY;
   }
@@ -503,6 +518,9 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
       fprintf(stderr, "[msspe] persistent greedy: total %.3f ms, iterations %u | phaseA work %.3f sync %.3f | phaseB work %.3f sync %.3f (block 0)\n",
               c->h_ctl[i].t_total_ns * 1e-6, c->h_ctl[i].iterations, c->h_ctl[i].t_dbg[0] * 1e-6, c->h_ctl[i].t_dbg[1] * 1e-6,
               c->h_ctl[i].t_dbg[2] * 1e-6, c->h_ctl[i].t_dbg[3] * 1e-6);
+    if (getenv("MSSPE_DEBUG_TIMERS") && i == 0)
+      fprintf(stderr, "[msspe]   worker block 1: phaseA work %.3f sync %.3f | phaseB work %.3f sync %.3f ms\n", c->h_ctl[i].t_dbg[4] * 1e-6,
+              c->h_ctl[i].t_dbg[5] * 1e-6, c->h_ctl[i].t_dbg[6] * 1e-6, c->h_ctl[i].t_dbg[7] * 1e-6);
   }
   MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
   return MSSPE_OK;

@@ -5,104 +5,115 @@
 
 namespace msspe_sel {
 
-constexpr int CNT_THREADS = MSSPE_CNT_THREADS, CNT_ITEMS = MSSPE_CNT_ITEMS, CNT_TILE = MSSPE_CNT_TILE;  // 8192 postings = 32 KB
+constexpr int CNT_THREADS = MSSPE_CNT_THREADS, CNT_TILE = MSSPE_CNT_TILE;  // block size; postings per WARP tile
 
 __device__ __forceinline__ unsigned int ld_volatile(const unsigned int* p) { return *reinterpret_cast<const volatile unsigned int*>(p); }
-
-struct CountScratch {
-  __align__(16) uint8_t nib[CNT_TILE / 4];
-  uint16_t bits[CNT_THREADS];
-  uint32_t tbase[CNT_THREADS + 1];
-  uint32_t wsum[CNT_THREADS / 32];
-};
 
 // mask word load: shared-memory copy (plain) or the global bitmask (L2-coherent load, other blocks write it)
 template <bool SMEM_MASK>
 __device__ __forceinline__ uint32_t mask_word(const uint32_t* mask, uint32_t w) {
   return SMEM_MASK ? mask[w] : __ldcg(mask + w);
 }
-
-// One tile of the coverage scoring (main.rs:292-309): live flag per posting, per-k-mer sums through a tile
-// prefix, freq[] writes, running maximum.  Returns the number of live postings of the tile (all threads).
-// Ends with a __syncthreads() so the scratch can be reused immediately.
 template <bool SMEM_MASK>
-__device__ __forceinline__ uint32_t count_tile(uint32_t tile, const uint32_t* __restrict__ postings,
-                                               const uint32_t* __restrict__ post_off, const uint32_t* __restrict__ tile_first,
-                                               uint32_t n_codes, uint32_t n_post, const uint32_t* mask, uint32_t* freq,
-                                               unsigned long long* acc, CountScratch& s, uint32_t& mymax) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t tile_start = tile * (uint32_t)CNT_TILE;
+__device__ __forceinline__ uint32_t live_bit(const uint32_t* mask, uint32_t seg) {
+  return (~mask_word<SMEM_MASK>(mask, seg >> 5) >> (seg & 31u)) & 1u;
+}
+
+// One WARP tile (512 postings = 2 KB) of the coverage scoring (main.rs:292-309), no block-level barrier:
+//   lane l loads four coalesced uint4 (block j = postings [128j, 128j+128) of the tile, lane l owns 4 of them),
+//   gathers the covered-segment bit of each posting, keeps 4 live nibbles; one packed shuffle scan gives the
+//   exclusive live-count of every (block, lane); per-k-mer sums are differences of that prefix at the list
+//   bounds, fetched with two shuffles each.  Lists that cross a tile boundary are assembled by the last
+//   arriving tile through an arrival-counter|partial-sum word (acc[first tile of the list]).
+// Returns the live postings of the tile (uniform over the warp); mymax is per lane.
+template <bool SMEM_MASK>
+__device__ __forceinline__ uint32_t warp_count_tile(uint32_t wt, const uint32_t* __restrict__ postings,
+                                                    const uint32_t* __restrict__ post_off, const uint32_t* __restrict__ tile_first,
+                                                    uint32_t n_codes, uint32_t n_post, const uint32_t* mask, uint32_t* freq,
+                                                    unsigned long long* acc, uint32_t& mymax, int lane) {
+  const uint32_t tile_start = wt * (uint32_t)CNT_TILE;
   const uint32_t tile_end = min(n_post, tile_start + (uint32_t)CNT_TILE);
-  const uint32_t first = __ldg(tile_first + tile);  // issued first; consumed after the posting loads are in flight
-  // phase 1: coalesced 128-bit loads; one live-bit nibble per uint4
+  const uint32_t first = __ldg(tile_first + wt);
+  uint32_t nibs = 0, cnts = 0;
 #pragma unroll
-  for (int j = 0; j < CNT_ITEMS / 4; j++) {
-    const uint32_t n = j * CNT_THREADS + tid;
-    const uint32_t pos = tile_start + 4u * n;
-    uint32_t nibble = 0;
+  for (int j = 0; j < 4; j++) {
+    const uint32_t pos = tile_start + (uint32_t)(j * 32 + lane) * 4u;
+    uint32_t nib = 0;
     if (pos + 3u < tile_end) {
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(postings + pos));
-      nibble = ((~mask_word<SMEM_MASK>(mask, v.x >> 5) >> (v.x & 31u)) & 1u) |
-               (((~mask_word<SMEM_MASK>(mask, v.y >> 5) >> (v.y & 31u)) & 1u) << 1) |
-               (((~mask_word<SMEM_MASK>(mask, v.z >> 5) >> (v.z & 31u)) & 1u) << 2) |
-               (((~mask_word<SMEM_MASK>(mask, v.w >> 5) >> (v.w & 31u)) & 1u) << 3);
+      nib = live_bit<SMEM_MASK>(mask, v.x) | (live_bit<SMEM_MASK>(mask, v.y) << 1) | (live_bit<SMEM_MASK>(mask, v.z) << 2) |
+            (live_bit<SMEM_MASK>(mask, v.w) << 3);
     } else {
       for (uint32_t e = 0; e < 4u; e++)
-        if (pos + e < tile_end) { const uint32_t sg = __ldg(postings + pos + e); nibble |= ((~mask_word<SMEM_MASK>(mask, sg >> 5) >> (sg & 31u)) & 1u) << e; }
+        if (pos + e < tile_end) nib |= live_bit<SMEM_MASK>(mask, __ldg(postings + pos + e)) << e;
     }
-    s.nib[n] = (uint8_t)nibble;
+    nibs |= nib << (4 * j);
+    cnts |= (uint32_t)__popc(nib) << (8 * j);
   }
-  // first round of list bounds: in flight while the tile prefix is built
-  uint32_t c = first + tid;
-  uint32_t pa = c < n_codes ? __ldg(post_off + c) : 0xFFFFFFFFu;
-  uint32_t pb = c < n_codes ? __ldg(post_off + c + 1) : 0xFFFFFFFFu;
-  __syncthreads();
-  // phase 2: per-thread 16-posting bit groups and their exclusive prefix over the tile
-  const uint32_t wv = *reinterpret_cast<const uint32_t*>(&s.nib[4 * tid]);
-  const uint32_t b16 = (wv & 0xFu) | (((wv >> 8) & 0xFu) << 4) | (((wv >> 16) & 0xFu) << 8) | (((wv >> 24) & 0xFu) << 12);
-  const uint32_t cnt = __popc(b16);
-  uint32_t inc = cnt;
+  // list bounds of the first 128 k-mers of the tile (4 per lane): in flight during the scan
+  constexpr int CB = 4;
+  uint32_t c0 = first + lane;
+  uint32_t pa[CB], pb[CB];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-  if (lane == 31) s.wsum[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t ws = lane < CNT_THREADS / 32 ? s.wsum[lane] : 0u, wi = ws;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
-    if (lane < CNT_THREADS / 32) s.wsum[lane] = wi - ws;
-    if (lane == CNT_THREADS / 32 - 1) s.tbase[CNT_THREADS] = wi;
+  for (int r = 0; r < CB; r++) {
+    const uint32_t c = c0 + 32u * r;
+    pa[r] = c < n_codes ? __ldg(post_off + c) : 0xFFFFFFFFu;
+    pb[r] = c < n_codes ? __ldg(post_off + c + 1) : 0xFFFFFFFFu;
   }
-  __syncthreads();
-  s.bits[tid] = (uint16_t)b16;
-  s.tbase[tid] = s.wsum[warp] + inc - cnt;
-  __syncthreads();
-  const uint32_t live = s.tbase[CNT_THREADS];
-  // phase 3: per-k-mer sums from prefix differences
-  for (; c < n_codes; c += CNT_THREADS, pa = c < n_codes ? __ldg(post_off + c) : 0xFFFFFFFFu, pb = c < n_codes ? __ldg(post_off + c + 1) : 0xFFFFFFFFu) {
-    const uint32_t a = pa;
-    if (a >= tile_end) break;
-    const uint32_t b = pb;
-    const uint32_t lo = max(a, tile_start) - tile_start, hi = min(b, tile_end) - tile_start;
-    const uint32_t plo = s.tbase[lo >> 4] + __popc((uint32_t)s.bits[lo >> 4] & ((1u << (lo & 15u)) - 1u));
-    const uint32_t phi = hi == (uint32_t)CNT_TILE ? live : s.tbase[hi >> 4] + __popc((uint32_t)s.bits[hi >> 4] & ((1u << (hi & 15u)) - 1u));
-    const uint32_t sum = phi - plo;
-    if (a >= tile_start && b <= tile_end) {
-      freq[c] = sum;
-      mymax = max(mymax, sum);
-    } else {  // list spans tiles: the last arriving tile owns the total
-      const uint32_t first_tile = a / (uint32_t)CNT_TILE;
-      const uint32_t parts = (b - 1u) / (uint32_t)CNT_TILE - first_tile + 1u;
-      const unsigned long long old = atomicAdd(&acc[first_tile], (1ull << 32) | (unsigned long long)sum);
-      if ((uint32_t)(old >> 32) + 1u == parts) {
-        const uint32_t total = (uint32_t)old + sum;
-        freq[c] = total;
-        acc[first_tile] = 0ull;
-        mymax = max(mymax, total);
+  // packed inclusive scan over lanes: field j (8 bits) = live count of block j up to this lane (<= 128)
+  uint32_t inc = cnts;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+  const uint32_t excl = inc - cnts;
+  const uint32_t b1 = tot & 0xFFu, b2 = b1 + ((tot >> 8) & 0xFFu), b3 = b2 + ((tot >> 16) & 0xFFu), live = b3 + (tot >> 24);
+  const uint32_t bases = b1 | (b2 << 10) | (b3 << 20);  // base of block j = (bases >> (10*(j-1))) & 0x3FF, block 0 -> 0
+  for (;;) {
+#pragma unroll
+    for (int r = 0; r < CB; r++) {
+      if (!__any_sync(0xffffffffu, pa[r] < tile_end)) break;
+      const bool act = pa[r] < tile_end;
+      const uint32_t lo = act ? max(pa[r], tile_start) - tile_start : 0u, hi = act ? min(pb[r], tile_end) - tile_start : 0u;
+      uint32_t pre[2];  // prefix(pos), pos in [0, 512]: live postings before position pos of the tile
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const uint32_t pos = q == 0 ? lo : hi;
+        const uint32_t pp = min(pos, (uint32_t)CNT_TILE - 1u);
+        const uint32_t j = pp >> 7, l = (pp >> 2) & 31u, e = pp & 3u;
+        const uint32_t ex = __shfl_sync(0xffffffffu, excl, l), nb = __shfl_sync(0xffffffffu, nibs, l);
+        const uint32_t base = j == 0 ? 0u : (bases >> (10u * (j - 1u))) & 0x3FFu;
+        const uint32_t v = base + ((ex >> (8u * j)) & 0xFFu) + __popc((nb >> (4u * j)) & ((1u << e) - 1u));
+        pre[q] = pos >= (uint32_t)CNT_TILE ? live : v;
+      }
+      if (act) {
+        const uint32_t c = c0 + 32u * r;
+        const uint32_t sum = pre[1] - pre[0];
+        if (pa[r] >= tile_start && pb[r] <= tile_end) {
+          freq[c] = sum;
+          mymax = max(mymax, sum);
+        } else {  // list spans tiles: the last arriving tile owns the total
+          const uint32_t first_tile = pa[r] / (uint32_t)CNT_TILE;
+          const uint32_t parts = (pb[r] - 1u) / (uint32_t)CNT_TILE - first_tile + 1u;
+          const unsigned long long old = atomicAdd(&acc[first_tile], (1ull << 32) | (unsigned long long)sum);
+          if ((uint32_t)(old >> 32) + 1u == parts) {
+            const uint32_t total = (uint32_t)old + sum;
+            freq[c] = total;
+            acc[first_tile] = 0ull;
+            mymax = max(mymax, total);
+          }
+        }
       }
     }
+    // lists are ordered: if the last one fetched still starts inside the tile there may be more
+    if (!__any_sync(0xffffffffu, pa[CB - 1] < tile_end)) break;
+    c0 += 32u * CB;
+#pragma unroll
+    for (int r = 0; r < CB; r++) {
+      const uint32_t c = c0 + 32u * r;
+      pa[r] = c < n_codes ? __ldg(post_off + c) : 0xFFFFFFFFu;
+      pb[r] = c < n_codes ? __ldg(post_off + c + 1) : 0xFFFFFFFFu;
+    }
   }
-  __syncthreads();
   return live;
 }
 

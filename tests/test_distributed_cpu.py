@@ -1,0 +1,90 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: row tiling of the ordered-pair thal matrix and the
+all_gather merge.  The per-rank compute is stood in for by the oracle (tests may use it); on GPU ranks it is
+Engine.cross_dimer -- the merge logic under test is the same."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _make_compute(words, limit):
+    from oracle import oracle as O
+    import msspe_b200 as m
+    cond = O.ThalCond(50, 3, 0, 250, 25.0, 30, 0)
+    n = len(words)
+
+    def compute(rb, re_):
+        e, nos = [], []
+        for i in range(rb, re_):
+            for j in range(n):
+                o = O.thal(words[i], words[j], 1, cond)
+                if o.no_structure:
+                    nos.append(i * n + j)
+                elif o.dg < limit:
+                    e.append((i * n + j, o.dg))
+        return np.array(e, dtype=m.EDGE_DTYPE), np.array(nos, dtype=np.uint64)
+    return compute
+
+
+def _worker(rank, world, port, words, limit, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "open-msspe-design_b200"))
+    import torch.distributed as dist
+    import msspe_b200 as m
+    from msspe_b200 import distributed as D
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    e, nos = D.cross_dimer_sharded(_make_compute(words, limit), len(words), m.EDGE_DTYPE, dist, "cpu")
+    q.put((rank, e.tobytes(), nos.tobytes()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_blocks_partition_the_matrix():
+    sys.path.insert(0, os.path.join(ROOT, "open-msspe-design_b200"))
+    from msspe_b200 import distributed as D
+    for n in (0, 1, 7, 64, 20000):
+        for world in (1, 2, 3, 8):
+            blocks = [D.row_block(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.timeout(300)
+def test_sharded_cross_dimer_equals_single_process(oracle_lib):
+    sys.path.insert(0, os.path.join(ROOT, "open-msspe-design_b200"))
+    import msspe_b200 as m
+    from msspe_b200 import synth
+    k, n = 13, 21   # odd row count: ragged blocks
+    words = [m.decode_word(c, k) for c in synth.random_primers(n - 2, k, 4)] + ["AACCACACACCAA", "CACACAACCACAC"]
+    limit = -1500.0
+    want_e, want_n = _make_compute(words, limit)(0, n)
+    assert len(want_e) > 5 and len(want_n) >= 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, words, limit, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, eb, nb in got:
+        assert eb == want_e.tobytes() and nb == want_n.tobytes(), "rank %d merged result differs" % rank
