@@ -161,6 +161,10 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # libraries (NCCL) print banners on fd 1: keep fd 1 clean for the single JSON line
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import msspe_b200 as m
@@ -359,7 +363,7 @@ def main():
                          "select_fwd": float(res_dev[0][4].select_ms[0]), "select_rev": float(res_dev[0][4].select_ms[1]),
                          "thermo_last_dir": float(res_dev[0][4].thermo_ms)},
         }
-        print(json.dumps(line), flush=True)
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     eng.close()
     if world > 1:
         dist.destroy_process_group()

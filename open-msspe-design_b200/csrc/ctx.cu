@@ -62,6 +62,13 @@ extern "C" int msspe_create(const msspe_config* cfg, msspe_ctx** out) {
   if (!c) { fail_create("out of host memory"); return MSSPE_ERR_NOMEM; }
   c->cfg = *cfg;
   c->device = cfg->device;
+  {  // keep freed blocks in the stream-ordered pool instead of returning them to the driver at every sync
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   c->sm_count = prop.multiProcessorCount;
   c->smem_optin = prop.sharedMemPerBlockOptin;
   c->slots = cfg->search_windows_size >= cfg->kmer_size ? cfg->search_windows_size - cfg->kmer_size + 1 : 0;
@@ -81,10 +88,10 @@ extern "C" int msspe_create(const msspe_config* cfg, msspe_ctx** out) {
 }
 
 static void free_genomes(msspe_ctx* c) {
-  if (c->d_bases && !c->bases_borrowed) cudaFree(c->d_bases);
+  if (c->d_bases && !c->bases_borrowed) msspe_dev_free(c, c->d_bases);
   c->d_bases = nullptr; c->bases_borrowed = false;
-  if (c->d_offsets) cudaFree(c->d_offsets);
-  if (c->d_seg_base) cudaFree(c->d_seg_base);
+  if (c->d_offsets) msspe_dev_free(c, c->d_offsets);
+  if (c->d_seg_base) msspe_dev_free(c, c->d_seg_base);
   c->d_offsets = c->d_seg_base = nullptr;
   c->loaded = false;
 }
@@ -170,8 +177,8 @@ static int plan_segments(msspe_ctx* c, const uint64_t* offsets, uint32_t n) {
 
 static int upload_plan(msspe_ctx* c) {
   uint32_t n = c->n_records;
-  MSSPE_CUDA_TRY(c, cudaMalloc(&c->d_offsets, (n + 1) * sizeof(uint64_t)));
-  MSSPE_CUDA_TRY(c, cudaMalloc(&c->d_seg_base, (n + 1) * sizeof(uint64_t)));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&c->d_offsets, (n + 1) * sizeof(uint64_t), c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&c->d_seg_base, (n + 1) * sizeof(uint64_t), c->stream));
   MSSPE_CUDA_TRY(c, cudaMemcpyAsync(c->d_offsets, c->h_offsets.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
   MSSPE_CUDA_TRY(c, cudaMemcpyAsync(c->d_seg_base, c->h_seg_base.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
   return MSSPE_OK;
@@ -187,7 +194,7 @@ extern "C" int msspe_load_genomes(msspe_ctx* c, const uint8_t* bases, const uint
   int rc = plan_segments(c, offsets, n);
   if (rc) return rc;
   c->bases_bytes = offsets[n];
-  MSSPE_CUDA_TRY(c, cudaMalloc(&c->d_bases, c->bases_bytes ? c->bases_bytes : 1));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&c->d_bases, c->bases_bytes ? c->bases_bytes : 1, c->stream));
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[0], c->stream));
   if (c->bases_bytes)
     MSSPE_CUDA_TRY(c, cudaMemcpyAsync(c->d_bases, bases, c->bases_bytes, cudaMemcpyHostToDevice, c->stream));

@@ -123,3 +123,7 @@ int msspe_thal_upload_tables(msspe_ctx* ctx);
 void msspe_thal_free_tables(msspe_ctx* ctx);
 
 static inline uint64_t div_up_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// Device memory comes from the stream-ordered pool (cudaMallocAsync): no device-wide synchronisation per
+// allocation, and freed blocks are cached by the pool (release threshold = unlimited, set in msspe_create).
+static inline void msspe_dev_free(msspe_ctx* c, void* p) { if (p) cudaFreeAsync(p, c->stream); }

@@ -253,10 +253,10 @@ __global__ void build_csr_kernel(const uint64_t* __restrict__ keys, const uint32
   if (head) { codes[cid] = keys[i]; post_off[cid] = (uint32_t)i; }
 }
 
-void free_dir(DirIndex& d) {
-  cudaFree(d.codes); cudaFree(d.post_off); cudaFree(d.postings); cudaFree(d.fwd_ids); cudaFree(d.freq);
-  cudaFree(d.acc); cudaFree(d.ignored); cudaFree(d.cov); cudaFree(d.pmark); cudaFree(d.ctl); cudaFree(d.out);
-  cudaFree(d.tile_first);
+void free_dir(msspe_ctx* c, DirIndex& d) {
+  msspe_dev_free(c, d.codes); msspe_dev_free(c, d.post_off); msspe_dev_free(c, d.postings); msspe_dev_free(c, d.fwd_ids); msspe_dev_free(c, d.freq);
+  msspe_dev_free(c, d.acc); msspe_dev_free(c, d.ignored); msspe_dev_free(c, d.cov); msspe_dev_free(c, d.pmark); msspe_dev_free(c, d.ctl); msspe_dev_free(c, d.out);
+  msspe_dev_free(c, d.tile_first);
   d = DirIndex();
 }
 
@@ -317,7 +317,7 @@ int build_direction(msspe_ctx* c, int dir, float* enc_ms, float* idx_ms) {
   MSSPE_CUDA_TRY(c, cudaFreeAsync(counts, st));
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
   // ---- K2 ----
-  MSSPE_CUDA_TRY(c, cudaMalloc(&D.fwd_ids, (G * slots ? G * slots : 1) * sizeof(uint32_t)));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.fwd_ids, (G * slots ? G * slots : 1) * sizeof(uint32_t), c->stream));
   MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.fwd_ids, 0xFF, (G * slots ? G * slots : 1) * sizeof(uint32_t), st));
   uint32_t n_codes = 0;
   if (R > 0) {
@@ -348,9 +348,9 @@ int build_direction(msspe_ctx* c, int dir, float* enc_ms, float* idx_ms) {
     MSSPE_CUDA_TRY(c, cudaMemcpyAsync(&n_codes, d_total, 4, cudaMemcpyDeviceToHost, st));
     MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
     D.n_codes = n_codes;
-    MSSPE_CUDA_TRY(c, cudaMalloc(&D.codes, (uint64_t)n_codes * 8));
-    MSSPE_CUDA_TRY(c, cudaMalloc(&D.post_off, ((uint64_t)n_codes + 1) * 4));
-    MSSPE_CUDA_TRY(c, cudaMalloc(&D.postings, (uint64_t)R * 4));
+    MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.codes, (uint64_t)n_codes * 8, c->stream));
+    MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.post_off, ((uint64_t)n_codes + 1) * 4, c->stream));
+    MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.postings, (uint64_t)R * 4, c->stream));
     build_csr_kernel<<<(unsigned)div_up_u64(R, 256), 256, 0, st>>>(key_a, val_a, flags, R, slots, n_codes, D.codes,
                                                                   D.post_off, D.postings, D.fwd_ids);
     c->timing.kernel_launches++;
@@ -360,21 +360,21 @@ int build_direction(msspe_ctx* c, int dir, float* enc_ms, float* idx_ms) {
     MSSPE_CUDA_TRY(c, cudaFreeAsync(val_b, st));
   } else {
     D.n_codes = 0;
-    MSSPE_CUDA_TRY(c, cudaMalloc(&D.codes, 8));
-    MSSPE_CUDA_TRY(c, cudaMalloc(&D.post_off, 4));
+    MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.codes, 8, c->stream));
+    MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.post_off, 4, c->stream));
     MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.post_off, 0, 4, st));
-    MSSPE_CUDA_TRY(c, cudaMalloc(&D.postings, 4));
+    MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.postings, 4, c->stream));
   }
   MSSPE_CUDA_TRY(c, cudaFreeAsync(key_a, st));
   MSSPE_CUDA_TRY(c, cudaFreeAsync(val_a, st));
   MSSPE_CUDA_TRY(c, cudaFreeAsync(d_total, st));
   // greedy state
   const uint64_t Dn = n_codes ? n_codes : 1;
-  MSSPE_CUDA_TRY(c, cudaMalloc(&D.freq, Dn * 4));
-  MSSPE_CUDA_TRY(c, cudaMalloc(&D.ignored, (div_up_u64(G, 32) + 1) * 4));
-  MSSPE_CUDA_TRY(c, cudaMalloc(&D.cov, 65536 * 4));
-  MSSPE_CUDA_TRY(c, cudaMalloc(&D.pmark, 2048 * 4));
-  MSSPE_CUDA_TRY(c, cudaMalloc(&D.ctl, sizeof(SelectCtl)));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.freq, Dn * 4, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.ignored, (div_up_u64(G, 32) + 1) * 4, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.cov, 65536 * 4, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.pmark, 2048 * 4, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.ctl, sizeof(SelectCtl), c->stream));
   rc = msspe_select_prepare_static(c, dir, st);
   if (rc) return rc;
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[4], st));
@@ -389,9 +389,9 @@ int build_direction(msspe_ctx* c, int dir, float* enc_ms, float* idx_ms) {
 }  // namespace
 
 int msspe_free_index(msspe_ctx* c) {
-  free_dir(c->dir[0]); free_dir(c->dir[1]);
-  if (c->d_seg_part) cudaFree(c->d_seg_part);
-  if (c->d_seg_rec) cudaFree(c->d_seg_rec);
+  free_dir(c, c->dir[0]); free_dir(c, c->dir[1]);
+  if (c->d_seg_part) msspe_dev_free(c, c->d_seg_part);
+  if (c->d_seg_rec) msspe_dev_free(c, c->d_seg_rec);
   c->d_seg_part = nullptr; c->d_seg_rec = nullptr;
   c->built = false;
   return MSSPE_OK;
@@ -403,8 +403,8 @@ extern "C" int msspe_build_index(msspe_ctx* c) {
   MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
   msspe_free_index(c);
   const uint64_t G = c->n_segments;
-  MSSPE_CUDA_TRY(c, cudaMalloc(&c->d_seg_part, (G ? G : 1) * sizeof(uint16_t)));
-  MSSPE_CUDA_TRY(c, cudaMalloc(&c->d_seg_rec, (G ? G : 1) * sizeof(uint32_t)));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&c->d_seg_part, (G ? G : 1) * sizeof(uint16_t), c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&c->d_seg_rec, (G ? G : 1) * sizeof(uint32_t), c->stream));
   c->timing.encode_ms = c->timing.index_ms = 0.f;
   for (int d = 0; d < 2; d++) {
     int rc = build_direction(c, d, &c->timing.encode_ms, &c->timing.index_ms);
@@ -422,14 +422,14 @@ extern "C" int msspe_get_segment_kmers(msspe_ctx* c, uint8_t dir, uint64_t* code
   if (capacity < need || (need && !codes)) { c->set_error("segment k-mer table needs %llu entries", (unsigned long long)need); return MSSPE_ERR_CAPACITY; }
   if (need == 0) return MSSPE_OK;
   uint64_t* dense = nullptr;
-  MSSPE_CUDA_TRY(c, cudaMalloc(&dense, need * 8));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&dense, need * 8, c->stream));
   int rc = encode_dispatch(c, dir, ENC_DENSE, nullptr, nullptr, nullptr, nullptr, dense, c->stream);
   if (rc == MSSPE_OK) {
     cudaError_t e = cudaMemcpyAsync(codes, dense, need * 8, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) { c->set_error("copy of segment k-mers failed: %s", cudaGetErrorString(e)); rc = MSSPE_ERR_CUDA; }
   }
-  cudaFree(dense);
+  msspe_dev_free(c, dense);
   return rc;
 }
 

@@ -370,8 +370,8 @@ int prepare_dir(msspe_ctx* c, int dir, uint32_t max_iter, cudaStream_t st, DirRu
   r->D = &D; r->st = st;
   const uint64_t G = c->n_segments;
   if (D.out_capacity < max_iter) {
-    cudaFree(D.out); D.out = nullptr;
-    MSSPE_CUDA_TRY(c, cudaMalloc(&D.out, (uint64_t)(max_iter ? max_iter : 1) * sizeof(msspe_candidate)));
+    msspe_dev_free(c, D.out); D.out = nullptr;
+    MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.out, (uint64_t)(max_iter ? max_iter : 1) * sizeof(msspe_candidate), c->stream));
     D.out_capacity = max_iter;
   }
   r->mask_words = (uint32_t)div_up_u64(G, 32) + 1u;
@@ -460,8 +460,8 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
   for (int i = 0; i < ndirs; i++) {
     DirIndex& D = c->dir[dirs[i]];
     if (D.out_capacity < max_iter) {
-      cudaFree(D.out); D.out = nullptr;
-      MSSPE_CUDA_TRY(c, cudaMalloc(&D.out, (uint64_t)max_iter * sizeof(msspe_candidate)));
+      msspe_dev_free(c, D.out); D.out = nullptr;
+      MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.out, (uint64_t)max_iter * sizeof(msspe_candidate), c->stream));
       D.out_capacity = max_iter;
     }
     MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.ignored, 0, (size_t)A.mask_words * 4, st));
@@ -599,8 +599,8 @@ int run_select(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max_iter, uint
 int msspe_select_prepare_static(msspe_ctx* c, int dir, cudaStream_t st) {
   DirIndex& D = c->dir[dir];
   D.n_tiles = (uint32_t)div_up_u64(D.n_records, CNT_TILE);
-  MSSPE_CUDA_TRY(c, cudaMalloc(&D.acc, (uint64_t)(D.n_tiles + 1) * 8));
-  MSSPE_CUDA_TRY(c, cudaMalloc(&D.tile_first, (uint64_t)(D.n_tiles + 1) * 4));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.acc, (uint64_t)(D.n_tiles + 1) * 8, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.tile_first, (uint64_t)(D.n_tiles + 1) * 4, c->stream));
   if (D.n_tiles) {
     tile_first_kernel<<<(D.n_tiles + 255) / 256, 256, 0, st>>>(D.post_off, (uint32_t)D.n_codes, D.n_tiles, D.tile_first);
     c->timing.kernel_launches++;

@@ -780,9 +780,10 @@ int ensure_tables(msspe_ctx* c) {
   return msspe_thal_upload_tables(c);
 }
 
-struct DeviceBuf {
+struct DeviceBuf {  // stream-ordered scratch, returned to the pool when the call ends
   void* p = nullptr;
-  ~DeviceBuf() { if (p) cudaFree(p); }
+  cudaStream_t st = nullptr;
+  ~DeviceBuf() { if (p) cudaFreeAsync(p, st); }
 };
 
 int launch_dimer(msspe_ctx* c, DimerArgs& A, cudaStream_t st) {
@@ -825,7 +826,7 @@ int msspe_thal_upload_tables(msspe_ctx* c) {
   ThalDeviceTables* h = new ThalDeviceTables();
   msspe_thal_expand(&c->raw, h);
   if (!c->d_thal) {
-    cudaError_t e = cudaMalloc(&c->d_thal, sizeof(ThalDeviceTables));
+    cudaError_t e = cudaMallocAsync(&c->d_thal, sizeof(ThalDeviceTables), c->stream);
     if (e != cudaSuccess) { delete h; c->set_error("cudaMalloc thal tables: %s", cudaGetErrorString(e)); return MSSPE_ERR_CUDA; }
   }
   cudaError_t e = cudaMemcpy(c->d_thal, h, sizeof(ThalDeviceTables), cudaMemcpyHostToDevice);
@@ -835,7 +836,7 @@ int msspe_thal_upload_tables(msspe_ctx* c) {
 }
 
 void msspe_thal_free_tables(msspe_ctx* c) {
-  if (c->d_thal) cudaFree(c->d_thal);
+  if (c->d_thal) msspe_dev_free(c, c->d_thal);
   c->d_thal = nullptr;
 }
 
@@ -866,19 +867,19 @@ extern "C" int msspe_thal_pairs(msspe_ctx* c, const uint64_t* a, const uint64_t*
   build_dimer_consts(*hT, *cond, &K);
   delete hT;
   DeviceBuf da, db, dout, dK, dwork;
-  MSSPE_CUDA_TRY(c, cudaMalloc(&da.p, n_pairs * 8));
-  MSSPE_CUDA_TRY(c, cudaMalloc(&dout.p, n_pairs * sizeof(msspe_thal_out)));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&(da.st = c->stream, da.p), n_pairs * 8, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dout.st = c->stream, dout.p), n_pairs * sizeof(msspe_thal_out), c->stream));
   MSSPE_CUDA_TRY(c, cudaMemcpyAsync(da.p, a, n_pairs * 8, cudaMemcpyHostToDevice, st));
   if (type == MSSPE_THAL_HAIRPIN) {
-    MSSPE_CUDA_TRY(c, cudaMalloc(&dwork.p, n_pairs * sizeof(MonoWork)));
+    MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dwork.st = c->stream, dwork.p), n_pairs * sizeof(MonoWork), c->stream));
     thal_mono_kernel<<<(unsigned)div_up_u64(n_pairs, 64), 64, 0, st>>>((const uint64_t*)da.p, (uint32_t)n_pairs, (int)oligo_len, c->d_thal,
                                                                      K.saltCorr, K.t_user_K, K.maxLoop, (MonoWork*)dwork.p,
                                                                      (msspe_thal_out*)dout.p);
     c->timing.kernel_launches++;
     MSSPE_CUDA_TRY(c, cudaGetLastError());
   } else {
-    MSSPE_CUDA_TRY(c, cudaMalloc(&db.p, n_pairs * 8));
-    MSSPE_CUDA_TRY(c, cudaMalloc(&dK.p, sizeof(ThalDimerConsts)));
+    MSSPE_CUDA_TRY(c, cudaMallocAsync(&(db.st = c->stream, db.p), n_pairs * 8, c->stream));
+    MSSPE_CUDA_TRY(c, cudaMallocAsync(&dK.p, sizeof(ThalDimerConsts), c->stream));
     MSSPE_CUDA_TRY(c, cudaMemcpyAsync(db.p, b, n_pairs * 8, cudaMemcpyHostToDevice, st));
     MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dK.p, &K, sizeof K, cudaMemcpyHostToDevice, st));
     DimerArgs A{};
@@ -921,12 +922,12 @@ extern "C" int msspe_primer_thermo(msspe_ctx* c, const uint64_t* codes, uint32_t
     OK.conc_term[1] = 1.987 * log(p3.dna_conc / 1000000000.0);
   }
   DeviceBuf dcodes, dK, dtm, dgc, dout, dwork;
-  MSSPE_CUDA_TRY(c, cudaMalloc(&dcodes.p, (size_t)n * 8));
-  MSSPE_CUDA_TRY(c, cudaMalloc(&dK.p, sizeof K));
-  MSSPE_CUDA_TRY(c, cudaMalloc(&dtm.p, (size_t)n * 8));
-  MSSPE_CUDA_TRY(c, cudaMalloc(&dgc.p, (size_t)n * 8));
-  MSSPE_CUDA_TRY(c, cudaMalloc(&dout.p, (size_t)n * 3 * sizeof(msspe_thal_out)));
-  MSSPE_CUDA_TRY(c, cudaMalloc(&dwork.p, (size_t)n * sizeof(MonoWork)));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dcodes.st = c->stream, dcodes.p), (size_t)n * 8, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&dK.p, sizeof K, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dtm.st = c->stream, dtm.p), (size_t)n * 8, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dgc.st = c->stream, dgc.p), (size_t)n * 8, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dout.st = c->stream, dout.p), (size_t)n * 3 * sizeof(msspe_thal_out), c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dwork.st = c->stream, dwork.p), (size_t)n * sizeof(MonoWork), c->stream));
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[6], st));
   MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dcodes.p, codes, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dK.p, &K, sizeof K, cudaMemcpyHostToDevice, st));
@@ -982,11 +983,11 @@ extern "C" int msspe_cross_dimer(msspe_ctx* c, const uint64_t* codes, uint32_t n
   build_dimer_consts(*hT, *cond, &K);
   delete hT;
   DeviceBuf dcodes, dK, dedges, dnos, dcnt;
-  MSSPE_CUDA_TRY(c, cudaMalloc(&dcodes.p, (size_t)n * 8));
-  MSSPE_CUDA_TRY(c, cudaMalloc(&dK.p, sizeof K));
-  MSSPE_CUDA_TRY(c, cudaMalloc(&dedges.p, (size_t)(edge_capacity ? edge_capacity : 1) * sizeof(msspe_dimer_edge)));
-  MSSPE_CUDA_TRY(c, cudaMalloc(&dnos.p, (size_t)(nostruct_capacity ? nostruct_capacity : 1) * 8));
-  MSSPE_CUDA_TRY(c, cudaMalloc(&dcnt.p, 16));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dcodes.st = c->stream, dcodes.p), (size_t)n * 8, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&dK.p, sizeof K, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dedges.st = c->stream, dedges.p), (size_t)(edge_capacity ? edge_capacity : 1) * sizeof(msspe_dimer_edge), c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dnos.st = c->stream, dnos.p), (size_t)(nostruct_capacity ? nostruct_capacity : 1) * 8, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dcnt.st = c->stream, dcnt.p), 16, c->stream));
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[6], st));
   MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dcodes.p, codes, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dK.p, &K, sizeof K, cudaMemcpyHostToDevice, st));
