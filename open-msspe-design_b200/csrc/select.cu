@@ -206,15 +206,15 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-template <bool SMEM_MASK>
-__global__ void __launch_bounds__(CNT_THREADS)
+template <bool SMEM_MASK, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2)
 greedy_persistent_kernel(const GreedyArgs A) {
   extern __shared__ __align__(16) unsigned char dsm[];
   unsigned int bar_target = 0;
-  __shared__ uint32_t s_tied[CNT_THREADS];
+  __shared__ uint32_t s_tied[THREADS];
   __shared__ uint32_t s_cnt, s_sc[2], s_max[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int WARPS = CNT_THREADS / 32;
+  constexpr int WARPS = THREADS / 32;
   // dynamic smem: [masks ndirs*mask_words] [pm p_words] [seen p_words] [fp n_fp] [lst n_fp (u64)]
   uint32_t* smask = reinterpret_cast<uint32_t*>(dsm);
   uint32_t* pm = smask + (SMEM_MASK ? (size_t)A.ndirs * A.mask_words : 0);
@@ -223,8 +223,8 @@ greedy_persistent_kernel(const GreedyArgs A) {
   unsigned long long* lst = reinterpret_cast<unsigned long long*>(
       dsm + (((size_t)(reinterpret_cast<unsigned char*>(fp + A.n_fp) - dsm) + 7) & ~(size_t)7));
   if (SMEM_MASK)
-    for (uint32_t i = tid; i < (uint32_t)A.ndirs * A.mask_words; i += CNT_THREADS) smask[i] = 0u;
-  for (uint32_t i = tid; i < A.p_words; i += CNT_THREADS) pm[i] = 0u;
+    for (uint32_t i = tid; i < (uint32_t)A.ndirs * A.mask_words; i += THREADS) smask[i] = 0u;
+  for (uint32_t i = tid; i < A.p_words; i += THREADS) pm[i] = 0u;
   if (tid == 0) { s_cnt = 0u; s_max[0] = 0u; s_max[1] = 0u; }
   __syncthreads();
   // block 0 keeps the global state (bitmask, partition_coverage, output); the other blocks score tiles
@@ -253,9 +253,9 @@ greedy_persistent_kernel(const GreedyArgs A) {
       if (have_win[d]) {  // main.rs:371-378 for the previous winner
         const uint32_t a = D.post_off[win[d]], b = D.post_off[win[d] + 1];
         if (SMEM_MASK)
-          for (uint32_t i = a + tid; i < b; i += CNT_THREADS) { const uint32_t sg = __ldg(D.postings + i); atomicOr(&mask[sg >> 5], 1u << (sg & 31u)); }
+          for (uint32_t i = a + tid; i < b; i += THREADS) { const uint32_t sg = __ldg(D.postings + i); atomicOr(&mask[sg >> 5], 1u << (sg & 31u)); }
         if (blockIdx.x == 0) {
-          for (uint32_t i = a + tid; i < b; i += CNT_THREADS) {
+          for (uint32_t i = a + tid; i < b; i += THREADS) {
             const uint32_t sg = __ldg(D.postings + i);
             atomicOr(&D.ignored[sg >> 5], 1u << (sg & 31u));
             const uint32_t p = A.seg_part[sg];
@@ -264,7 +264,7 @@ greedy_persistent_kernel(const GreedyArgs A) {
             if (!(old & pbit)) atomicAdd(&D.cov[p], 1u);
           }
           __syncthreads();
-          for (uint32_t i = a + tid; i < b; i += CNT_THREADS) pm[A.seg_part[__ldg(D.postings + i)] >> 5] = 0u;
+          for (uint32_t i = a + tid; i < b; i += THREADS) pm[A.seg_part[__ldg(D.postings + i)] >> 5] = 0u;
         }
         __syncthreads();
       }
@@ -301,7 +301,7 @@ greedy_persistent_kernel(const GreedyArgs A) {
         continue;
       }
       const uint32_t* mask = SMEM_MASK ? smask + (size_t)d * A.mask_words : D.ignored;
-      for (uint32_t base = blockIdx.x * CNT_THREADS; base < D.n_codes; base += gridDim.x * CNT_THREADS) {
+      for (uint32_t base = blockIdx.x * THREADS; base < D.n_codes; base += gridDim.x * THREADS) {
         const uint32_t c = base + tid;
         if (c < D.n_codes && __ldcg(D.freq + c) == g) s_tied[atomicAdd(&s_cnt, 1u)] = c;
         __syncthreads();
@@ -310,7 +310,7 @@ greedy_persistent_kernel(const GreedyArgs A) {
           const uint32_t cc = s_tied[t];
           float score;
           if (A.n_fp) {
-            score = block_tie_score<SMEM_MASK, true, CNT_THREADS>(cc, D.post_off, D.postings, mask, A.seg_part, D.cov, A.n_part, fp, lst, s_sc);
+            score = block_tie_score<SMEM_MASK, true, THREADS>(cc, D.post_off, D.postings, mask, A.seg_part, D.cov, A.n_part, fp, lst, s_sc);
           } else {  // more partitions than the shared-memory scratch holds: one warp, bitmap of seen partitions
             if (warp == 0) {
               const float sw = warp_tie_score<SMEM_MASK, true>(cc, D.post_off, D.postings, mask, A.seg_part, D.cov, seen, A.p_words, lane);
@@ -475,7 +475,7 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
   }
   A.n_part = c->max_partition + 1u;
   A.n_fp = A.n_part <= 4096u ? A.n_part : 0u;
-  const size_t aux = (size_t)2 * A.p_words * 4 + (size_t)A.n_fp * 4 + (size_t)A.n_fp * 8 + 16;
+  const size_t aux = (size_t)2 * A.p_words * 4 + (size_t)A.n_fp * 4 + (size_t)A.n_fp * 8 + 16;  // pm, seen, fp, lst
   const size_t mask_bytes = (size_t)ndirs * A.mask_words * 4;
   const bool smem_mask = mask_bytes + aux + (size_t)4096 + 1024 <= c->smem_optin;
   const size_t smem = aux + (smem_mask ? mask_bytes : 0);
@@ -483,18 +483,24 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
     c->set_error("msspe_select: %u partitions need %zu B of shared memory (device offers %zu)", c->max_partition + 1, smem, c->smem_optin);
     return MSSPE_ERR_CAPACITY;
   }
-  int per_sm = 0;
-  void* fn = smem_mask ? (void*)greedy_persistent_kernel<true> : (void*)greedy_persistent_kernel<false>;
+  // 512-thread blocks, as many per SM as fit (<= 3); when the bitmask leaves room for one block only, 1024 threads
+  int per_sm = 0, threads = 512;
+  void* fn = smem_mask ? (void*)greedy_persistent_kernel<true, 512> : (void*)greedy_persistent_kernel<false, 512>;
   MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (smem_mask) MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_persistent_kernel<true>, CNT_THREADS, smem));
-  else MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_persistent_kernel<false>, CNT_THREADS, smem));
+  MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&per_sm, fn, 512, smem, cudaOccupancyDefault));
+  if (per_sm < 2) {
+    fn = smem_mask ? (void*)greedy_persistent_kernel<true, 1024> : (void*)greedy_persistent_kernel<false, 1024>;
+    threads = 1024;
+    MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&per_sm, fn, 1024, smem, cudaOccupancyDefault));
+  }
   if (per_sm < 1) { c->set_error("msspe_select: persistent kernel does not fit on an SM"); return MSSPE_ERR_CAPACITY; }
   int want = 2;
   if (const char* e = getenv("MSSPE_PERSIST_BLOCKS_PER_SM")) want = atoi(e) > 0 ? atoi(e) : want;
   if (per_sm > want) per_sm = want;
   const unsigned grid = (unsigned)c->sm_count * (unsigned)per_sm;
   void* kargs[] = {(void*)&A};
-  MSSPE_CUDA_TRY(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(CNT_THREADS), kargs, smem, st));
+  MSSPE_CUDA_TRY(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), kargs, smem, st));
   c->timing.kernel_launches++;
   for (int i = 0; i < ndirs; i++)
     MSSPE_CUDA_TRY(c, cudaMemcpyAsync(&c->h_ctl[i], c->dir[dirs[i]].ctl, sizeof(SelectCtl), cudaMemcpyDeviceToHost, st));
@@ -515,6 +521,8 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
     // phases of the two directions are interleaved inside one kernel: attribute the phase time once (to dir 0)
     c->timing.count_kernel_ms[d] = i == 0 ? (float)(c->h_ctl[i].t_count_ns * 1e-6) : 0.f;
     if (getenv("MSSPE_DEBUG_TIMERS") && i == 0)
+      fprintf(stderr, "[msspe] grid %u x %d, smem %zu B, smem_mask %d, ndirs %d\n", grid, threads, smem, (int)smem_mask, ndirs);
+    if (getenv("MSSPE_DEBUG_TIMERS") && i == 0)
       fprintf(stderr, "[msspe] persistent greedy: total %.3f ms, iterations %u | phaseA work %.3f sync %.3f | phaseB work %.3f sync %.3f (block 0)\n",
               c->h_ctl[i].t_total_ns * 1e-6, c->h_ctl[i].iterations, c->h_ctl[i].t_dbg[0] * 1e-6, c->h_ctl[i].t_dbg[1] * 1e-6,
               c->h_ctl[i].t_dbg[2] * 1e-6, c->h_ctl[i].t_dbg[3] * 1e-6);
@@ -533,7 +541,18 @@ int run_select(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max_iter, uint
   mode &= ~(uint32_t)MSSPE_SELECT_BATCHED;
   if (mode > MSSPE_SELECT_INCREMENTAL) { c->set_error("msspe_select: unknown mode %u", mode); return MSSPE_ERR_INVALID; }
   MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
-  if (!batched && mode == MSSPE_SELECT_RECOUNT && max_iter > 0) return run_select_persistent(c, ndirs, dirs, max_iter, mms, outs, n_outs);
+  if (!batched && mode == MSSPE_SELECT_RECOUNT && max_iter > 0) {
+    // both covered-segment bitmasks in shared memory if they fit; otherwise one direction per launch
+    const size_t one_mask = ((size_t)div_up_u64(c->n_segments, 32) + 1) * 4;
+    if (ndirs == 2 && 2 * one_mask + 16384 > c->smem_optin && one_mask + 16384 <= c->smem_optin) {
+      for (int i = 0; i < 2; i++) {
+        int rc = run_select_persistent(c, 1, &dirs[i], max_iter, mms, &outs[i], &n_outs[i]);
+        if (rc) return rc;
+      }
+      return MSSPE_OK;
+    }
+    return run_select_persistent(c, ndirs, dirs, max_iter, mms, outs, n_outs);
+  }
   DirRun runs[2];
   cudaStream_t streams[2] = {c->stream, c->stream2};
   cudaEvent_t ev_b[2] = {c->ev[2], c->ev[4]}, ev_e[2] = {c->ev[3], c->ev[5]};

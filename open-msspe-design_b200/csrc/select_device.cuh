@@ -19,12 +19,21 @@ __device__ __forceinline__ uint32_t live_bit(const uint32_t* mask, uint32_t seg)
   return (~mask_word<SMEM_MASK>(mask, seg >> 5) >> (seg & 31u)) & 1u;
 }
 
+// Live postings before position pos (0..511) of the current warp tile, from the packed per-lane scan state.
+__device__ __forceinline__ uint32_t tile_prefix(uint32_t pos, uint32_t excl, uint32_t nibs, uint32_t b1, uint32_t b2, uint32_t b3) {
+  const uint32_t j = pos >> 7, l = (pos >> 2) & 31u, e = pos & 3u;
+  const uint32_t ex = __shfl_sync(0xffffffffu, excl, l), nb = __shfl_sync(0xffffffffu, nibs, l);
+  const uint32_t base = j == 0 ? 0u : (j == 1 ? b1 : (j == 2 ? b2 : b3));
+  return base + ((ex >> (8u * j)) & 0xFFu) + __popc((nb >> (4u * j)) & ((1u << e) - 1u));
+}
+
 // One WARP tile (512 postings = 2 KB) of the coverage scoring (main.rs:292-309), no block-level barrier:
 //   lane l loads four coalesced uint4 (block j = postings [128j, 128j+128) of the tile, lane l owns 4 of them),
 //   gathers the covered-segment bit of each posting, keeps 4 live nibbles; one packed shuffle scan gives the
-//   exclusive live-count of every (block, lane); per-k-mer sums are differences of that prefix at the list
-//   bounds, fetched with two shuffles each.  Lists that cross a tile boundary are assembled by the last
-//   arriving tile through an arrival-counter|partial-sum word (acc[first tile of the list]).
+//   exclusive live-count of every (block, lane).  A k-mer's live count is prefix(next list start) - prefix(own
+//   list start): every lane evaluates the prefix at its own list start (two shuffles) and takes the upper bound
+//   from its neighbour lane.  Lists that cross a tile boundary are assembled by the last arriving tile through an
+//   arrival-counter|partial-sum word (acc[first tile of the list]).
 // Returns the live postings of the tile (uniform over the warp); mymax is per lane.
 template <bool SMEM_MASK>
 __device__ __forceinline__ uint32_t warp_count_tile(uint32_t wt, const uint32_t* __restrict__ postings,
@@ -35,31 +44,35 @@ __device__ __forceinline__ uint32_t warp_count_tile(uint32_t wt, const uint32_t*
   const uint32_t tile_end = min(n_post, tile_start + (uint32_t)CNT_TILE);
   const uint32_t first = __ldg(tile_first + wt);
   uint32_t nibs = 0, cnts = 0;
+  if (tile_start + (uint32_t)CNT_TILE <= n_post) {
+    uint4 v[4];
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const uint32_t pos = tile_start + (uint32_t)(j * 32 + lane) * 4u;
-    uint32_t nib = 0;
-    if (pos + 3u < tile_end) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(postings + pos));
-      nib = live_bit<SMEM_MASK>(mask, v.x) | (live_bit<SMEM_MASK>(mask, v.y) << 1) | (live_bit<SMEM_MASK>(mask, v.z) << 2) |
-            (live_bit<SMEM_MASK>(mask, v.w) << 3);
-    } else {
+    for (int j = 0; j < 4; j++) v[j] = __ldg(reinterpret_cast<const uint4*>(postings + tile_start + (uint32_t)(j * 32 + lane) * 4u));
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t nib = live_bit<SMEM_MASK>(mask, v[j].x) | (live_bit<SMEM_MASK>(mask, v[j].y) << 1) |
+                           (live_bit<SMEM_MASK>(mask, v[j].z) << 2) | (live_bit<SMEM_MASK>(mask, v[j].w) << 3);
+      nibs |= nib << (4 * j);
+      cnts |= (uint32_t)__popc(nib) << (8 * j);
+    }
+  } else {  // the last, partial tile
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t pos = tile_start + (uint32_t)(j * 32 + lane) * 4u;
+      uint32_t nib = 0;
       for (uint32_t e = 0; e < 4u; e++)
         if (pos + e < tile_end) nib |= live_bit<SMEM_MASK>(mask, __ldg(postings + pos + e)) << e;
+      nibs |= nib << (4 * j);
+      cnts |= (uint32_t)__popc(nib) << (8 * j);
     }
-    nibs |= nib << (4 * j);
-    cnts |= (uint32_t)__popc(nib) << (8 * j);
   }
-  // list bounds of the first 128 k-mers of the tile (4 per lane): in flight during the scan
+  // list starts of the first 32*CB k-mers of the tile (CB per lane) + the one after them; in flight during the scan
   constexpr int CB = 4;
   uint32_t c0 = first + lane;
-  uint32_t pa[CB], pb[CB];
+  uint32_t pa[CB];
 #pragma unroll
-  for (int r = 0; r < CB; r++) {
-    const uint32_t c = c0 + 32u * r;
-    pa[r] = c < n_codes ? __ldg(post_off + c) : 0xFFFFFFFFu;
-    pb[r] = c < n_codes ? __ldg(post_off + c + 1) : 0xFFFFFFFFu;
-  }
+  for (int r = 0; r < CB; r++) { const uint32_t c = c0 + 32u * r; pa[r] = c <= n_codes ? __ldg(post_off + c) : 0xFFFFFFFFu; }
+  uint32_t pnext = first + 32u * CB <= n_codes ? __ldg(post_off + first + 32u * CB) : 0xFFFFFFFFu;
   // packed inclusive scan over lanes: field j (8 bits) = live count of block j up to this lane (<= 128)
   uint32_t inc = cnts;
 #pragma unroll
@@ -67,33 +80,42 @@ __device__ __forceinline__ uint32_t warp_count_tile(uint32_t wt, const uint32_t*
   const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
   const uint32_t excl = inc - cnts;
   const uint32_t b1 = tot & 0xFFu, b2 = b1 + ((tot >> 8) & 0xFFu), b3 = b2 + ((tot >> 16) & 0xFFu), live = b3 + (tot >> 24);
-  const uint32_t bases = b1 | (b2 << 10) | (b3 << 20);  // base of block j = (bases >> (10*(j-1))) & 0x3FF, block 0 -> 0
   for (;;) {
+    // prefix at every active list start of this batch
+    uint32_t plo[CB];
+    int nr = 0;
 #pragma unroll
     for (int r = 0; r < CB; r++) {
-      if (!__any_sync(0xffffffffu, pa[r] < tile_end)) break;
-      const bool act = pa[r] < tile_end;
-      const uint32_t lo = act ? max(pa[r], tile_start) - tile_start : 0u, hi = act ? min(pb[r], tile_end) - tile_start : 0u;
-      uint32_t pre[2];  // prefix(pos), pos in [0, 512]: live postings before position pos of the tile
-#pragma unroll
-      for (int q = 0; q < 2; q++) {
-        const uint32_t pos = q == 0 ? lo : hi;
-        const uint32_t pp = min(pos, (uint32_t)CNT_TILE - 1u);
-        const uint32_t j = pp >> 7, l = (pp >> 2) & 31u, e = pp & 3u;
-        const uint32_t ex = __shfl_sync(0xffffffffu, excl, l), nb = __shfl_sync(0xffffffffu, nibs, l);
-        const uint32_t base = j == 0 ? 0u : (bases >> (10u * (j - 1u))) & 0x3FFu;
-        const uint32_t v = base + ((ex >> (8u * j)) & 0xFFu) + __popc((nb >> (4u * j)) & ((1u << e) - 1u));
-        pre[q] = pos >= (uint32_t)CNT_TILE ? live : v;
+      if (r == nr && __any_sync(0xffffffffu, pa[r] < tile_end)) {
+        const uint32_t lo = pa[r] < tile_end ? max(pa[r], tile_start) - tile_start : 0u;
+        const uint32_t v = tile_prefix(lo, excl, nibs, b1, b2, b3);
+        plo[r] = pa[r] < tile_end ? v : live;
+        nr = r + 1;
+      } else {
+        plo[r] = live;
       }
-      if (act) {
+    }
+    const bool more = nr == CB && pnext < tile_end;  // uniform: another batch of lists starts inside this tile
+    uint32_t pnext_pre = live;
+    if (more) pnext_pre = tile_prefix(pnext - tile_start, excl, nibs, b1, b2, b3);
+#pragma unroll
+    for (int r = 0; r < CB; r++) {
+      if (r >= nr) break;
+      // the next list's start and its prefix: neighbour lane, or lane 0 of the next round, or the batch successor
+      const uint32_t nxt_r = r + 1 < CB ? pa[r + 1 < CB ? r + 1 : r] : pnext;
+      const uint32_t nxt_p = r + 1 < CB ? plo[r + 1 < CB ? r + 1 : r] : pnext_pre;
+      uint32_t pb = __shfl_down_sync(0xffffffffu, pa[r], 1), phi = __shfl_down_sync(0xffffffffu, plo[r], 1);
+      const uint32_t pb31 = __shfl_sync(0xffffffffu, nxt_r, 0), phi31 = __shfl_sync(0xffffffffu, nxt_p, 0);
+      if (lane == 31) { pb = pb31; phi = phi31; }
+      if (pa[r] < tile_end) {
         const uint32_t c = c0 + 32u * r;
-        const uint32_t sum = pre[1] - pre[0];
-        if (pa[r] >= tile_start && pb[r] <= tile_end) {
+        const uint32_t sum = (pb < tile_end ? phi : live) - plo[r];
+        if (pa[r] >= tile_start && pb <= tile_end) {
           freq[c] = sum;
           mymax = max(mymax, sum);
         } else {  // list spans tiles: the last arriving tile owns the total
           const uint32_t first_tile = pa[r] / (uint32_t)CNT_TILE;
-          const uint32_t parts = (pb[r] - 1u) / (uint32_t)CNT_TILE - first_tile + 1u;
+          const uint32_t parts = (pb - 1u) / (uint32_t)CNT_TILE - first_tile + 1u;
           const unsigned long long old = atomicAdd(&acc[first_tile], (1ull << 32) | (unsigned long long)sum);
           if ((uint32_t)(old >> 32) + 1u == parts) {
             const uint32_t total = (uint32_t)old + sum;
@@ -104,15 +126,11 @@ __device__ __forceinline__ uint32_t warp_count_tile(uint32_t wt, const uint32_t*
         }
       }
     }
-    // lists are ordered: if the last one fetched still starts inside the tile there may be more
-    if (!__any_sync(0xffffffffu, pa[CB - 1] < tile_end)) break;
+    if (!more) break;
     c0 += 32u * CB;
 #pragma unroll
-    for (int r = 0; r < CB; r++) {
-      const uint32_t c = c0 + 32u * r;
-      pa[r] = c < n_codes ? __ldg(post_off + c) : 0xFFFFFFFFu;
-      pb[r] = c < n_codes ? __ldg(post_off + c + 1) : 0xFFFFFFFFu;
-    }
+    for (int r = 0; r < CB; r++) { const uint32_t c = c0 + 32u * r; pa[r] = c <= n_codes ? __ldg(post_off + c) : 0xFFFFFFFFu; }
+    pnext = c0 - lane + 32u * CB <= n_codes ? __ldg(post_off + (c0 - lane) + 32u * CB) : 0xFFFFFFFFu;
   }
   return live;
 }

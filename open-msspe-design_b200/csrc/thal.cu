@@ -116,6 +116,7 @@ struct DimerArgs {
   double dg_limit;
   msspe_dimer_edge* edges; unsigned long long edge_cap; unsigned long long* n_edges;
   uint64_t* nostruct; unsigned long long nostruct_cap; unsigned long long* n_nostruct;
+  int dbg;  // diagnostic: 1 = skip loop candidates, 2 = skip traceback, 4 = skip fill entirely
 };
 
 struct DimerShared {  // per block
@@ -135,44 +136,64 @@ struct PairView {  // per group, in shared memory
   int k;
 };
 
+// What a loop candidate needs to know about its closing pair (i,j): computed once per cell, not per candidate.
+struct Closing {
+  uint32_t a, b;             // n1[i], n2[j]
+  double atpS, atpH;         // AT penalty of the closing pair
+  double int2S, int2H;       // 1x1 mismatch term on the closing side: stackint2[n2[j]][n2[j-1]][n1[i]][n1[i-1]]
+  double tstS, tstH;         // terminal mismatch term on the closing side
+};
+
+__device__ __forceinline__ Closing make_closing(const DimerShared& sh, const PairView& pv, int i, int j) {
+  Closing c;
+  c.a = pv.n1[i]; c.b = pv.n2[j];
+  const int x = i4(pv.n2[j], pv.n2[j - 1] & 3, pv.n1[i], pv.n1[i - 1] & 3);  // i, j >= 2 where it is used
+  c.atpS = sh.atpS[c.a * 4 + c.b]; c.atpH = sh.atpH[c.a * 4 + c.b];
+  c.int2S = sh.int2S[x]; c.int2H = sh.int2H[x];
+  c.tstS = sh.tstS[x]; c.tstH = sh.tstH[x];
+  return c;
+}
+
 // (S,H) of the bulge / internal loop closed by (i,j) with inner pair (ii,jj), including the inner cell's value.
-// H = +inf marks "not possible".
-__device__ __forceinline__ void loop_candidate(const DimerShared& sh, const PairView& pv, int i, int j, int ii, int jj,
-                                               double* outS, double* outH) {
-  const uint8_t* n1 = pv.n1; const uint8_t* n2 = pv.n2;
+// H = +inf marks "not possible".  ca/cb are the 2-bit codes: n1[t] = (ca >> 2(k-t)) & 3, n2[t] = (cb >> 2(t-1)) & 3.
+__device__ __forceinline__ void loop_candidate(const DimerShared& sh, const double2* __restrict__ cell, int k, uint64_t ca, uint64_t cb,
+                                               const Closing& cl, int i, int j, int ii, int jj, double* outS, double* outH) {
   const int l1 = i - ii - 1, l2 = j - jj - 1, ls = l1 + l2 - 1;
-  const double2 inner = pv.cell[(ii - 1) * pv.k + (jj - 1)];
+  const double2 inner = cell[(ii - 1) * k + (jj - 1)];
+  const uint32_t a_in = (uint32_t)(ca >> (2 * (k - ii))) & 3u, b_in = (uint32_t)(cb >> (2 * (jj - 1))) & 3u;
   double S, H;
   if (l1 == 0 || l2 == 0) {      // bulge (l1 + l2 >= 1 guaranteed by the caller)
     if (l1 + l2 == 1) {          // size 1: the flanking pairs still stack
-      H = sh.bulgeH[ls] + sh.stackH[i4(n1[ii], n1[i], n2[jj], n2[j])];
-      S = sh.bulgeS[ls] + sh.stackS[i4(n1[ii], n1[i], n2[jj], n2[j])];
+      const int x = i4(a_in, cl.a, b_in, cl.b);
+      H = sh.bulgeH[ls] + sh.stackH[x];
+      S = sh.bulgeS[ls] + sh.stackS[x];
       if (H > 0 || S > 0) { H = INFINITY; S = -1.0; }
       H += inner.y; S += inner.x;
       if (!isfinite(H)) { H = INFINITY; S = -1.0; }
     } else {
-      H = sh.bulgeH[ls] + sh.atpH[n1[ii] * 4 + n2[jj]] + sh.atpH[n1[i] * 4 + n2[j]];
+      H = sh.bulgeH[ls] + sh.atpH[a_in * 4 + b_in] + cl.atpH;
       H += inner.y;
-      S = sh.bulgeS[ls] + sh.atpS[n1[ii] * 4 + n2[jj]] + sh.atpS[n1[i] * 4 + n2[j]];
+      S = sh.bulgeS[ls] + sh.atpS[a_in * 4 + b_in] + cl.atpS;
       S += inner.x;
       if (!isfinite(H)) { H = INFINITY; S = -1.0; }
       if (H > 0 && S > 0) { H = INFINITY; S = -1.0; }
     }
-  } else if (l1 == 1 && l2 == 1) {
-    S = sh.int2S[i4(n1[ii], n1[ii + 1], n2[jj], n2[jj + 1])] + sh.int2S[i4(n2[j], n2[j - 1], n1[i], n1[i - 1])];
-    S += inner.x;
-    H = sh.int2H[i4(n1[ii], n1[ii + 1], n2[jj], n2[jj + 1])] + sh.int2H[i4(n2[j], n2[j - 1], n1[i], n1[i - 1])];
-    H += inner.y;
-    if (!isfinite(H)) { H = INFINITY; S = -1.0; }
-    if (H > 0 && S > 0) { H = INFINITY; S = -1.0; }
   } else {
-    const int asym = l1 > l2 ? l1 - l2 : l2 - l1;
-    H = sh.interiorH[ls] + sh.tstH[i4(n1[ii], n1[ii + 1], n2[jj], n2[jj + 1])] + sh.tstH[i4(n2[j], n2[j - 1], n1[i], n1[i - 1])] +
-        (K_ILAH * asym);
-    H += inner.y;
-    S = sh.interiorS[ls] + sh.tstS[i4(n1[ii], n1[ii + 1], n2[jj], n2[jj + 1])] + sh.tstS[i4(n2[j], n2[j - 1], n1[i], n1[i - 1])] +
-        (K_ILAS * asym);
-    S += inner.x;
+    // inner-side context: n1[ii], n1[ii+1], n2[jj], n2[jj+1]  (ii+1 <= i-1 and jj+1 <= j-1 here)
+    const uint32_t a_nx = (uint32_t)(ca >> (2 * (k - ii - 1))) & 3u, b_nx = (uint32_t)(cb >> (2 * jj)) & 3u;
+    const int x = i4(a_in, a_nx, b_in, b_nx);
+    if (l1 == 1 && l2 == 1) {
+      S = sh.int2S[x] + cl.int2S;
+      S += inner.x;
+      H = sh.int2H[x] + cl.int2H;
+      H += inner.y;
+    } else {
+      const int asym = l1 > l2 ? l1 - l2 : l2 - l1;
+      H = sh.interiorH[ls] + sh.tstH[x] + cl.tstH + (K_ILAH * asym);
+      H += inner.y;
+      S = sh.interiorS[ls] + sh.tstS[x] + cl.tstS + (K_ILAS * asym);
+      S += inner.x;
+    }
     if (!isfinite(H)) { H = INFINITY; S = -1.0; }
     if (H > 0 && S > 0) { H = INFINITY; S = -1.0; }
   }
@@ -185,9 +206,10 @@ __device__ __forceinline__ uint64_t revcomp_code(uint64_t code, int k) {
   return r;
 }
 
-template <int GROUP>
+template <int SUB>
 __global__ void __launch_bounds__(DIMER_THREADS)
 thal_dimer_kernel(const DimerArgs A) {
+  constexpr int GROUP = 32;  // one warp per ordered pair
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   DimerShared& sh = *reinterpret_cast<DimerShared*>(dyn_smem);
   const int k = A.k;
@@ -252,7 +274,7 @@ thal_dimer_kernel(const DimerArgs A) {
     __syncwarp(gmask);
 
     // ---------------- fill ----------------
-    for (int i = 1; i <= k; i++) {
+    for (int i = 1; i <= ((A.dbg & 4) ? 0 : k); i++) {
       const uint32_t rm = pv.rowmask[i];
       const int a = pv.n1[i];
       for (int j = gl + 1; j <= k; j += GROUP) {
@@ -283,38 +305,50 @@ thal_dimer_kernel(const DimerArgs A) {
         pv.cell[(i - 1) * k + (j - 1)] = make_double2(S, H);
       }
       __syncwarp(gmask);
-      if (i > 1) {
-        for (uint32_t bj = rm & ~1u; bj; bj &= bj - 1u) {
-          const int j = __ffs(bj);
+      if (i > 1 && !(A.dbg & 1)) {
+        // CELLS paired cells of this row are processed at once, SUB lanes each (lane = inner row of the candidates)
+        constexpr int CELLS = 32 / SUB;
+        const int slot = lane / SUB, sl = lane % SUB;
+        for (uint32_t bj = rm & ~1u; bj;) {
+          uint32_t t = bj;
+          int j = 0;
+#pragma unroll
+          for (int q = 0; q < CELLS; q++) { const int f = t ? __ffs(t) : 0; if (q == slot) j = f; t &= t - 1u; }
+          bj = t;  // uniform: every lane strips the same CELLS lowest bits
+          const bool has = j != 0;
+          if (!has) j = 2;
           const int ri = (a * 5 + pv.n1[i + 1]) * 5 + pv.n2[j + 1];
           const double rS = rshS[ri], rH = rshH[ri];
           const double2 cur = pv.cell[(i - 1) * k + (j - 1)];
           const double Gcur = cur.y + rH - kTK * (cur.x + rS);
+          const Closing cl = make_closing(sh, pv, i, j);
           double bG = INFINITY, bS = -1.0, bH = INFINITY;
           int bkey = 0x7fffffff;
           bool clamp = false;
-          for (int l1 = gl; l1 <= i - 2; l1 += GROUP) {
-            const int ii = i - 1 - l1;
-            uint32_t cand = pv.rowmask[ii] & ((1u << (j - 1)) - 1u);
-            if (l1 == 0) cand &= ~(1u << (j - 2));
-            while (cand) {
-              const int jj = __ffs(cand);
-              cand &= cand - 1u;
-              const int l2 = j - jj - 1;
-              if (l1 + l2 > maxLoop) continue;
-              double S, H;
-              loop_candidate(sh, pv, i, j, ii, jj, &S, &H);
-              if (isfinite(H)) {
-                if (S < kMinEntropyCutoff) clamp = true;
-                const double G1 = H + rH - kTK * (S + rS);
-                const int key = (l1 + l2) * 64 + l1;
-                if (G1 < bG || (G1 == bG && key < bkey)) { bG = G1; bkey = key; bS = S; bH = H; }
+          if (has) {
+            for (int l1 = sl; l1 <= i - 2; l1 += SUB) {
+              const int ii = i - 1 - l1;
+              uint32_t cand = pv.rowmask[ii] & ((1u << (j - 1)) - 1u);
+              if (l1 == 0) cand &= ~(1u << (j - 2));
+              while (cand) {
+                const int jj = __ffs(cand);
+                cand &= cand - 1u;
+                const int l2 = j - jj - 1;
+                if (l1 + l2 > maxLoop) continue;
+                double S, H;
+                loop_candidate(sh, pv.cell, k, ca, cb, cl, i, j, ii, jj, &S, &H);
+                if (isfinite(H)) {
+                  if (S < kMinEntropyCutoff) clamp = true;
+                  const double G1 = H + rH - kTK * (S + rS);
+                  const int key = (l1 + l2) * 64 + l1;
+                  if (G1 < bG || (G1 == bG && key < bkey)) { bG = G1; bkey = key; bS = S; bH = H; }
+                }
               }
             }
           }
-          if (__any_sync(gmask, clamp)) {
-            // An entropy below the cutoff re-bases the cell mid-scan: replay the scan sequentially in one lane.
-            if (gl == 0) {
+          if (__any_sync(0xffffffffu, clamp)) {
+            // An entropy below the cutoff re-bases the cell mid-scan: replay the scan sequentially, one lane per cell.
+            if (has && sl == 0) {
               double cS = cur.x, cH = cur.y;
               for (int d = 3; d <= maxLoop + 2; d++) {
                 int ii = i - 1, jj = -ii - d + (j + i);
@@ -322,7 +356,7 @@ thal_dimer_kernel(const DimerArgs A) {
                 for (; ii > 0 && jj < j; --ii, ++jj) {
                   if (!((pv.rowmask[ii] >> (jj - 1)) & 1u)) continue;
                   double S, H;
-                  loop_candidate(sh, pv, i, j, ii, jj, &S, &H);
+                  loop_candidate(sh, pv.cell, k, ca, cb, cl, i, j, ii, jj, &S, &H);
                   const double G1 = H + rH - kTK * (S + rS), G2 = cH + rH - kTK * (cS + rS);
                   if (!(G1 < G2)) { S = -1.0; H = INFINITY; }
                   if (S < kMinEntropyCutoff) { S = kMinEntropy; H = 0.0; }
@@ -334,13 +368,11 @@ thal_dimer_kernel(const DimerArgs A) {
           } else {
             double mG = bG;
 #pragma unroll
-            for (int o = GROUP / 2; o > 0; o >>= 1) mG = fmin(mG, __shfl_xor_sync(gmask, mG, o, GROUP));
-            if (mG < Gcur) {
-              int mk = (bG == mG) ? bkey : 0x7fffffff;
+            for (int o = SUB / 2; o > 0; o >>= 1) mG = fmin(mG, __shfl_xor_sync(0xffffffffu, mG, o, SUB));
+            int mk = (bG == mG && mG < Gcur) ? bkey : 0x7fffffff;
 #pragma unroll
-              for (int o = GROUP / 2; o > 0; o >>= 1) mk = min(mk, __shfl_xor_sync(gmask, mk, o, GROUP));
-              if (bG == mG && bkey == mk) pv.cell[(i - 1) * k + (j - 1)] = make_double2(bS, bH);
-            }
+            for (int o = SUB / 2; o > 0; o >>= 1) mk = min(mk, __shfl_xor_sync(0xffffffffu, mk, o, SUB));
+            if (has && mG < Gcur && bG == mG && bkey == mk) pv.cell[(i - 1) * k + (j - 1)] = make_double2(bS, bH);
           }
         }
         __syncwarp(gmask);
@@ -386,7 +418,7 @@ thal_dimer_kernel(const DimerArgs A) {
       const double dS = bc.x + rshS[ri] + kDSi;
       // ---------------- traceback: count paired positions ----------------
       int i = bi, j = bjx, pairs = 1;
-      for (int guard = 0; guard < 2 * k + 2; guard++) {
+      for (int guard = 0; guard < ((A.dbg & 2) ? 0 : 2 * k + 2); guard++) {
         const int li = (pv.n1[i] * 5 + pv.n1[i - 1]) * 5 + pv.n2[j - 1];
         const double2 c = pv.cell[(i - 1) * k + (j - 1)];
         if (eq2(c.x, lshS[li]) && eq2(c.y, lshH[li])) break;
@@ -396,6 +428,7 @@ thal_dimer_kernel(const DimerArgs A) {
           if (eq2(c.x, sh.stackS[si] + pc.x) && eq2(c.y, sh.stackH[si] + pc.y)) { i--; j--; pairs++; continue; }
         }
         int key = 0x7fffffff;
+        const Closing cl = make_closing(sh, pv, i > 1 ? i : 2, j > 1 ? j : 2);  // only used when i, j >= 2
         for (int l1 = gl; l1 <= i - 2; l1 += GROUP) {
           const int ii = i - 1 - l1;
           uint32_t cand = j >= 2 ? (pv.rowmask[ii] & ((1u << (j - 1)) - 1u)) : 0u;
@@ -406,7 +439,7 @@ thal_dimer_kernel(const DimerArgs A) {
             const int l2 = j - jj - 1;
             if (l1 + l2 > maxLoop) continue;
             double S, H;
-            loop_candidate(sh, pv, i, j, ii, jj, &S, &H);
+            loop_candidate(sh, pv.cell, k, ca, cb, cl, i, j, ii, jj, &S, &H);
             if (eq2(c.x, S) && eq2(c.y, H)) key = min(key, (l1 + l2) * 64 + l1);
           }
         }
@@ -789,26 +822,26 @@ struct DeviceBuf {  // stream-ordered scratch, returned to the pool when the cal
 int launch_dimer(msspe_ctx* c, DimerArgs& A, cudaStream_t st) {
   if (A.n_pairs == 0) return MSSPE_OK;
   const int k = A.k;
-  const int group = k <= 16 ? 16 : 32;
-  const int groups = DIMER_THREADS / group;
+  const int sub = k <= 16 ? 8 : 16;  // lanes per cell in flight (inner rows <= 2*sub)
+  const int groups = DIMER_THREADS / 32;
   const size_t cell_bytes = (size_t)k * k * 16;
   const size_t grp_bytes = (cell_bytes + (size_t)(k + 2) * 4 + 2 * (size_t)(k + 2) + 15) & ~(size_t)15;
   const size_t smem = ((sizeof(DimerShared) + 15) & ~(size_t)15) + groups * grp_bytes;
   if (smem > c->smem_optin) { c->set_error("thal dimer: %zu B shared memory needed, device offers %zu", smem, c->smem_optin); return MSSPE_ERR_CAPACITY; }
   int per_sm = 1;
   unsigned long long blocks_needed = (A.n_pairs + groups - 1) / groups;
-  if (group == 16) {
+  if (sub == 8) {
+    MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(thal_dimer_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, thal_dimer_kernel<8>, DIMER_THREADS, smem));
+  } else {
     MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(thal_dimer_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, thal_dimer_kernel<16>, DIMER_THREADS, smem));
-  } else {
-    MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(thal_dimer_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, thal_dimer_kernel<32>, DIMER_THREADS, smem));
   }
   if (per_sm < 1) per_sm = 1;
   const unsigned long long resident = (unsigned long long)c->sm_count * per_sm;
   const unsigned grid = (unsigned)(blocks_needed < resident ? blocks_needed : resident);
-  if (group == 16) thal_dimer_kernel<16><<<grid, DIMER_THREADS, smem, st>>>(A);
-  else thal_dimer_kernel<32><<<grid, DIMER_THREADS, smem, st>>>(A);
+  if (sub == 8) thal_dimer_kernel<8><<<grid, DIMER_THREADS, smem, st>>>(A);
+  else thal_dimer_kernel<16><<<grid, DIMER_THREADS, smem, st>>>(A);
   c->timing.kernel_launches++;
   MSSPE_CUDA_TRY(c, cudaGetLastError());
   return MSSPE_OK;
@@ -997,6 +1030,7 @@ extern "C" int msspe_cross_dimer(msspe_ctx* c, const uint64_t* codes, uint32_t n
   A.k = (int)oligo_len; A.type = MSSPE_THAL_ANY; A.T = c->d_thal; A.C = (const ThalDimerConsts*)dK.p; A.out = nullptr;
   A.dg_limit = dg_limit; A.edges = (msspe_dimer_edge*)dedges.p; A.edge_cap = edge_capacity; A.n_edges = (unsigned long long*)dcnt.p;
   A.nostruct = (uint64_t*)dnos.p; A.nostruct_cap = nostruct_capacity; A.n_nostruct = (unsigned long long*)dcnt.p + 1;
+  A.dbg = getenv("MSSPE_THAL_DBG") ? atoi(getenv("MSSPE_THAL_DBG")) : 0;
   rc = launch_dimer(c, A, st);
   if (rc) return rc;
   unsigned long long cnt[2] = {0, 0};
