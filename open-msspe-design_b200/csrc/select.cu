@@ -56,8 +56,19 @@ count_kernel(const uint32_t* __restrict__ postings, const uint32_t* __restrict__
   const uint32_t* mask = SMEM_MASK ? smask : ignored;
   uint32_t mymax = 0;
   unsigned long long live_total = 0;
-  for (uint32_t wt = blockIdx.x * WARPS + warp; wt < n_tiles; wt += gridDim.x * WARPS)
-    live_total += warp_count_tile<SMEM_MASK>(wt, postings, post_off, tile_first, n_codes, n_post, mask, freq, acc, mymax, lane);
+  {
+    const uint32_t stride = gridDim.x * WARPS;
+    uint32_t wt = blockIdx.x * WARPS + warp;
+    TileLoad cur, nxt;
+    if (wt < n_tiles) tile_issue(cur, wt, postings, tile_first, n_post, lane);
+    while (wt < n_tiles) {
+      const uint32_t wn = wt + stride;
+      if (wn < n_tiles) tile_issue(nxt, wn, postings, tile_first, n_post, lane);
+      live_total += warp_count_tile<SMEM_MASK>(cur, wt, post_off, n_codes, n_post, mask, freq, acc, mymax, lane);
+      cur = nxt;
+      wt = wn;
+    }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
   if (lane == 0) { if (mymax) atomicMax(&s_max, mymax); if (live_total) atomicAdd(&ctl->evals, live_total); }
@@ -237,14 +248,15 @@ greedy_persistent_kernel(const GreedyArgs A) {
   unsigned long long evals[2] = {0, 0};
   const bool lead = blockIdx.x == 0 && tid == 0;
   const bool wlead = blockIdx.x == (gridDim.x > 1 ? 1 : 0) && tid == 0;  // a worker block's clock (diagnostic)
-  unsigned long long wt0 = 0, wdbg[4] = {0, 0, 0, 0};
-  unsigned long long t_count = 0, t_tie = 0, t_begin = 0, dbg[4] = {0, 0, 0, 0};
-  if (lead) t_begin = globaltimer_ns();
+  // phase timers live in shared memory (only one thread touches them): no registers for diagnostics
+  __shared__ unsigned long long s_tm[12];  // 0 t_begin, 1 ta, 2 tb, 3 t_count, 4 t_tie, 5 wt0, 6.. dbg
+  if (tid == 0) for (int q = 0; q < 12; q++) s_tm[q] = 0ull;
+  __syncthreads();
+  if (lead) s_tm[0] = globaltimer_ns();
   for (uint32_t it = 0;; it++) {
     const int par = it & 1;
-    unsigned long long ta = 0, tb = 0;
-    if (lead) ta = globaltimer_ns();
-    if (wlead) wt0 = globaltimer_ns();
+    if (lead) s_tm[1] = globaltimer_ns();
+    if (wlead) s_tm[5] = globaltimer_ns();
     // ---------------- phase A ----------------
     for (int d = 0; d < A.ndirs; d++) {
       if (done[d]) continue;
@@ -271,8 +283,19 @@ greedy_persistent_kernel(const GreedyArgs A) {
       if (worker) {
         uint32_t mymax = 0;
         unsigned long long live = 0;
-        for (uint32_t wt = wid * WARPS + warp; wt < D.n_tiles; wt += nworkers * WARPS)
-          live += warp_count_tile<SMEM_MASK>(wt, D.postings, D.post_off, D.tile_first, D.n_codes, D.n_post, mask, D.freq, D.acc, mymax, lane);
+        {
+          const uint32_t stride = nworkers * WARPS;
+          uint32_t wt = wid * WARPS + warp;
+          TileLoad cur, nxt;
+          if (wt < D.n_tiles) tile_issue(cur, wt, D.postings, D.tile_first, D.n_post, lane);
+          while (wt < D.n_tiles) {  // the next tile's loads are in flight while this one is scored
+            const uint32_t wn = wt + stride;
+            if (wn < D.n_tiles) tile_issue(nxt, wn, D.postings, D.tile_first, D.n_post, lane);
+            live += warp_count_tile<SMEM_MASK>(cur, wt, D.post_off, D.n_codes, D.n_post, mask, D.freq, D.acc, mymax, lane);
+            cur = nxt;
+            wt = wn;
+          }
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
         if (lane == 0) { if (mymax) atomicMax(&s_max[d], mymax); evals[d] += live; }
@@ -282,12 +305,10 @@ greedy_persistent_kernel(const GreedyArgs A) {
     if (tid == 0 && worker)
       for (int d = 0; d < A.ndirs; d++)
         if (!done[d]) { if (s_max[d]) atomicMax(&A.d[d].ctl->pg[par], s_max[d]); s_max[d] = 0u; }
-    unsigned long long tx = 0;
-    if (lead) tx = globaltimer_ns();
-    if (wlead) { const unsigned long long t = globaltimer_ns(); wdbg[0] += t - wt0; wt0 = t; }
+    if (wlead) { const unsigned long long t = globaltimer_ns(); s_tm[8] += t - s_tm[5]; s_tm[5] = t; }
     grid_barrier(A.barrier, bar_target);
-    if (wlead) { const unsigned long long t = globaltimer_ns(); wdbg[1] += t - wt0; wt0 = t; }
-    if (lead) { tb = globaltimer_ns(); t_count += tb - ta; dbg[0] += tx - ta; dbg[1] += tb - tx; }
+    if (wlead) { const unsigned long long t = globaltimer_ns(); s_tm[9] += t - s_tm[5]; s_tm[5] = t; }
+    if (lead) { s_tm[2] = globaltimer_ns(); s_tm[3] += s_tm[2] - s_tm[1]; }
     // ---------------- phase B ----------------
     for (int d = 0; d < A.ndirs; d++) {
       if (done[d]) continue;
@@ -326,11 +347,10 @@ greedy_persistent_kernel(const GreedyArgs A) {
         __syncthreads();
       }
     }
-    if (lead) tx = globaltimer_ns();
-    if (wlead) { const unsigned long long t = globaltimer_ns(); wdbg[2] += t - wt0; wt0 = t; }
+    if (wlead) { const unsigned long long t = globaltimer_ns(); s_tm[10] += t - s_tm[5]; s_tm[5] = t; }
     grid_barrier(A.barrier, bar_target);
-    if (wlead) { const unsigned long long t = globaltimer_ns(); wdbg[3] += t - wt0; wt0 = t; }
-    if (lead) { const unsigned long long ty = globaltimer_ns(); t_tie += ty - tb; dbg[2] += tx - tb; dbg[3] += ty - tx; }
+    if (wlead) { const unsigned long long t = globaltimer_ns(); s_tm[11] += t - s_tm[5]; s_tm[5] = t; }
+    if (lead) s_tm[4] += globaltimer_ns() - s_tm[2];
     // ---------------- winner ----------------
     bool all_done = true;
     for (int d = 0; d < A.ndirs; d++) {
@@ -355,8 +375,8 @@ greedy_persistent_kernel(const GreedyArgs A) {
   }
   for (int d = 0; d < A.ndirs; d++) {
     if (lane == 0 && evals[d]) atomicAdd(&A.d[d].ctl->evals, evals[d]);
-    if (lead) { A.d[d].ctl->t_count_ns = t_count; A.d[d].ctl->t_tie_ns = t_tie; A.d[d].ctl->t_total_ns = globaltimer_ns() - t_begin; for (int q = 0; q < 4; q++) A.d[d].ctl->t_dbg[q] = dbg[q]; }
-    if (wlead) for (int q = 0; q < 4; q++) A.d[d].ctl->t_dbg[4 + q] = wdbg[q];
+    if (lead) { A.d[d].ctl->t_count_ns = s_tm[3]; A.d[d].ctl->t_tie_ns = s_tm[4]; A.d[d].ctl->t_total_ns = globaltimer_ns() - s_tm[0]; }
+    if (wlead) for (int q = 0; q < 4; q++) A.d[d].ctl->t_dbg[4 + q] = s_tm[8 + q];
   }
 }
 
@@ -523,9 +543,8 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
     if (getenv("MSSPE_DEBUG_TIMERS") && i == 0)
       fprintf(stderr, "[msspe] grid %u x %d, smem %zu B, smem_mask %d, ndirs %d\n", grid, threads, smem, (int)smem_mask, ndirs);
     if (getenv("MSSPE_DEBUG_TIMERS") && i == 0)
-      fprintf(stderr, "[msspe] persistent greedy: total %.3f ms, iterations %u | phaseA work %.3f sync %.3f | phaseB work %.3f sync %.3f (block 0)\n",
-              c->h_ctl[i].t_total_ns * 1e-6, c->h_ctl[i].iterations, c->h_ctl[i].t_dbg[0] * 1e-6, c->h_ctl[i].t_dbg[1] * 1e-6,
-              c->h_ctl[i].t_dbg[2] * 1e-6, c->h_ctl[i].t_dbg[3] * 1e-6);
+      fprintf(stderr, "[msspe] persistent greedy: total %.3f ms, iterations %u | coverage-scoring phases %.3f ms, arg-max phases %.3f ms (block 0 clock, barriers included)\n",
+              c->h_ctl[i].t_total_ns * 1e-6, c->h_ctl[i].iterations, c->h_ctl[i].t_count_ns * 1e-6, c->h_ctl[i].t_tie_ns * 1e-6);
     if (getenv("MSSPE_DEBUG_TIMERS") && i == 0)
       fprintf(stderr, "[msspe]   worker block 1: phaseA work %.3f sync %.3f | phaseB work %.3f sync %.3f ms\n", c->h_ctl[i].t_dbg[4] * 1e-6,
               c->h_ctl[i].t_dbg[5] * 1e-6, c->h_ctl[i].t_dbg[6] * 1e-6, c->h_ctl[i].t_dbg[7] * 1e-6);

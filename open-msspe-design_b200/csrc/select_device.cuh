@@ -35,36 +35,51 @@ __device__ __forceinline__ uint32_t tile_prefix(uint32_t pos, uint32_t excl, uin
 //   from its neighbour lane.  Lists that cross a tile boundary are assembled by the last arriving tile through an
 //   arrival-counter|partial-sum word (acc[first tile of the list]).
 // Returns the live postings of the tile (uniform over the warp); mymax is per lane.
+// The global loads of one warp tile, issued one tile ahead of their use (register double buffering).
+struct TileLoad {
+  uint4 v[4];
+  uint32_t first;
+};
+__device__ __forceinline__ void tile_issue(TileLoad& L, uint32_t wt, const uint32_t* __restrict__ postings,
+                                           const uint32_t* __restrict__ tile_first, uint32_t n_post, int lane) {
+  const uint32_t tile_start = wt * (uint32_t)CNT_TILE;
+  L.first = __ldg(tile_first + wt);
+  if (tile_start + (uint32_t)CNT_TILE <= n_post) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) L.v[j] = __ldg(reinterpret_cast<const uint4*>(postings + tile_start + (uint32_t)(j * 32 + lane) * 4u));
+  } else {  // the last, partial tile: out-of-range slots read posting 0 and are masked out later
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t pos = tile_start + (uint32_t)(j * 32 + lane) * 4u;
+      L.v[j].x = __ldg(postings + (pos + 0u < n_post ? pos + 0u : 0u));
+      L.v[j].y = __ldg(postings + (pos + 1u < n_post ? pos + 1u : 0u));
+      L.v[j].z = __ldg(postings + (pos + 2u < n_post ? pos + 2u : 0u));
+      L.v[j].w = __ldg(postings + (pos + 3u < n_post ? pos + 3u : 0u));
+    }
+  }
+}
+
 template <bool SMEM_MASK>
-__device__ __forceinline__ uint32_t warp_count_tile(uint32_t wt, const uint32_t* __restrict__ postings,
-                                                    const uint32_t* __restrict__ post_off, const uint32_t* __restrict__ tile_first,
+__device__ __forceinline__ uint32_t warp_count_tile(const TileLoad& L, uint32_t wt,
+                                                    const uint32_t* __restrict__ post_off,
                                                     uint32_t n_codes, uint32_t n_post, const uint32_t* mask, uint32_t* freq,
                                                     unsigned long long* acc, uint32_t& mymax, int lane) {
   const uint32_t tile_start = wt * (uint32_t)CNT_TILE;
   const uint32_t tile_end = min(n_post, tile_start + (uint32_t)CNT_TILE);
-  const uint32_t first = __ldg(tile_first + wt);
+  const uint32_t first = L.first;
+  const bool partial = tile_start + (uint32_t)CNT_TILE > n_post;
   uint32_t nibs = 0, cnts = 0;
-  if (tile_start + (uint32_t)CNT_TILE <= n_post) {
-    uint4 v[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) v[j] = __ldg(reinterpret_cast<const uint4*>(postings + tile_start + (uint32_t)(j * 32 + lane) * 4u));
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const uint32_t nib = live_bit<SMEM_MASK>(mask, v[j].x) | (live_bit<SMEM_MASK>(mask, v[j].y) << 1) |
-                           (live_bit<SMEM_MASK>(mask, v[j].z) << 2) | (live_bit<SMEM_MASK>(mask, v[j].w) << 3);
-      nibs |= nib << (4 * j);
-      cnts |= (uint32_t)__popc(nib) << (8 * j);
-    }
-  } else {  // the last, partial tile
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
+  for (int j = 0; j < 4; j++) {
+    uint32_t nib = live_bit<SMEM_MASK>(mask, L.v[j].x) | (live_bit<SMEM_MASK>(mask, L.v[j].y) << 1) |
+                   (live_bit<SMEM_MASK>(mask, L.v[j].z) << 2) | (live_bit<SMEM_MASK>(mask, L.v[j].w) << 3);
+    if (partial) {
       const uint32_t pos = tile_start + (uint32_t)(j * 32 + lane) * 4u;
-      uint32_t nib = 0;
-      for (uint32_t e = 0; e < 4u; e++)
-        if (pos + e < tile_end) nib |= live_bit<SMEM_MASK>(mask, __ldg(postings + pos + e)) << e;
-      nibs |= nib << (4 * j);
-      cnts |= (uint32_t)__popc(nib) << (8 * j);
+      const uint32_t valid = pos >= tile_end ? 0u : (tile_end - pos >= 4u ? 0xFu : (1u << (tile_end - pos)) - 1u);
+      nib &= valid;
     }
+    nibs |= nib << (4 * j);
+    cnts |= (uint32_t)__popc(nib) << (8 * j);
   }
   // list starts of the first 32*CB k-mers of the tile (CB per lane) + the one after them; in flight during the scan
   constexpr int CB = 4;
