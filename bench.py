@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-thal", action="store_true")
     ap.add_argument("--batched", action="store_true", help="one launch per phase instead of the persistent kernel (for per-launch ncu numbers)")
+    ap.add_argument("--no-large", action="store_true", help="skip the cfg5/8-shard roofline probe (12,500 x 30 kb, inputs larger than L2)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -280,7 +281,35 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch, "physical_bytes_per_launch": phys_bytes_per_launch,
                 "physical_gbs": phys_bytes_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0,
                 "avg_launch_us": 1e6 * avg_launch_s, "launches": ck_n,
-                "note": "cfg2 postings (2 x 18 MB) are L2-resident after the first iteration; see DESIGN.md"}
+                "timing": "in-kernel %globaltimer of block 0 around every coverage-scoring phase of the persistent kernel (one phase = one reference recount, both directions; includes the grid barrier that ends it); with --batched: CUDA events around each count_kernel launch",
+                "note": "cfg2 postings (2 x 18 MB) are L2-resident, the loop is latency-bound at this size; roofline_large_shard shows the same kernel where it is HBM-bound; see DESIGN.md"}
+
+    # ---- the same kernel where it is HBM-bound: one GPU's shard of BASELINE configs[4] (100,000 x 30 kb over 8 GPUs) ----
+    roofline_large = None
+    if not args.no_large and rank == 0:
+        big = synth.synth_genomes(12_500, 30_000, 5, clades=256, p_clade=0.10, p_leaf=0.01)
+        e2 = m.Engine(13, 500, 250, 50, device=local_rank)
+        e2.load_genomes(big.reshape(-1), synth.offsets_for(big))
+        e2.build_index()
+        tb = e2.timing()
+        iters = 50
+        e2.select_both(iters, 10, m.SELECT_RECOUNT)      # warm-up
+        e2.select_both(iters, 10, m.SELECT_RECOUNT)
+        t2 = e2.timing()
+        ev2 = int(t2.select_evals[0] + t2.select_evals[1])
+        pr2 = int(t2.select_postings_read[0] + t2.select_postings_read[1])
+        ck2 = float(t2.count_kernel_ms[0] + t2.count_kernel_ms[1])
+        n2 = int(t2.count_kernel_launches[0] + t2.count_kernel_launches[1])
+        G2 = e2.segment_info()[0]
+        roofline_large = {"workload": "one GPU's shard of cfg5: 12,500 x 30 kb genomes (%d segments), first %d greedy iterations per direction" % (G2, iters),
+                          "bound": "hbm", "kernel": "coverage-scoring phase of greedy_persistent_kernel", "achieved": 4.0 * ev2 / ck2 / 1e6,
+                          "physical_gbs": 4.0 * pr2 / ck2 / 1e6, "peak": peak_gbs, "unit": "GB/s", "frac": 4.0 * ev2 / ck2 / 1e6 / peak_gbs,
+                          "algorithmic_bytes_per_launch": 4.0 * ev2 / max(1, n2), "avg_launch_us": 1e3 * ck2 / max(1, n2), "launches": n2,
+                          "postings_bytes_per_direction": int(4 * pr2 / max(1, n2)), "l2": "226 MB per direction per iteration: larger than the 126 MB L2",
+                          "encode_ms": float(tb.encode_ms), "index_ms": float(tb.index_ms),
+                          "timing": "in-kernel %globaltimer of block 0 around the phase (includes the grid barrier that ends it)"}
+        e2.close()
+        del big
 
     # ---- secondary metric: thal dimer pairs / s, pair matrix row-tiled across ranks ----
     thal = None
@@ -357,6 +386,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": summarize_clocks(samples),
             "roofline": roofline,
+            "roofline_large_shard": roofline_large,
             "cpu_baseline": cpu,
             "thal": thal,
             "stage_ms": {"encode": float(res_dev[0][4].encode_ms), "index": float(res_dev[0][4].index_ms),
