@@ -177,6 +177,25 @@ int msspe_coverage(msspe_ctx* ctx, const uint64_t* fwd_codes, uint32_t n_fwd, co
                    uint32_t n_rev, uint8_t* covered, uint16_t* partition_no, uint32_t* record_of_segment,
                    uint64_t capacity);
 
+/* ---- (e) genome-sharded selection: per-rank primitives ----------------------------------------------------
+ * One process per GPU holds a contiguous block of the records (hence of the global segment order).  The loop of
+ * main.rs:331-406 is then driven above the ABI (msspe_b200/distributed.py): local recount -> all-reduce(sum) of the
+ * per-k-mer counts -> identical arg-max on every rank -> tie scores from the per-rank first-seen partition
+ * positions (rank order = segment order, main.rs:268-281) -> every rank marks its own postings of the winner.
+ * These entry points are the device work of one iteration; ids are LOCAL code ids (index into msspe_get_index's
+ * codes[]), MSSPE_NO_LOCAL_ID = the k-mer does not occur on this rank. */
+#define MSSPE_NO_LOCAL_ID 0xFFFFFFFFu
+int msspe_shard_begin(msspe_ctx* ctx, uint8_t dir);
+/* device pointers (valid until the next build): ascending codes[n_codes] (u64) and freq[n_codes] (u32) */
+int msspe_shard_buffers(msspe_ctx* ctx, uint8_t dir, const uint64_t** d_codes, const uint32_t** d_freq, uint64_t* n_codes);
+/* main.rs:292-309 on this rank's segments: freq[] <- live segments per local k-mer; *live = their sum */
+int msspe_shard_count(msspe_ctx* ctx, uint8_t dir, uint64_t* live);
+/* first_pos[t * n_part + p] = offset of the first live posting of local_ids[t] in partition p, 0xFFFFFFFF if none */
+int msspe_shard_firstpos(msspe_ctx* ctx, uint8_t dir, const uint32_t* local_ids, uint32_t n, uint32_t n_part, uint32_t* first_pos);
+/* main.rs:371-378 for the winner on this rank: mark all its postings covered; part_flags[p] = 1 for every partition
+ * any of its postings lies in (n_part entries) */
+int msspe_shard_apply(msspe_ctx* ctx, uint8_t dir, uint32_t local_id, uint32_t n_part, uint8_t* part_flags);
+
 /* ---- (d) thermodynamics --------------------------------------------------------------------- */
 /* Replaces `-path <cwd>/primer3_config/` (delta_g.rs:90).  Default = tables embedded at build time. */
 int msspe_thal_params_default(msspe_thal_raw_params* out);

@@ -716,3 +716,137 @@ extern "C" int msspe_coverage(msspe_ctx* c, const uint64_t* fwd_codes, uint32_t 
   MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
   return MSSPE_OK;
 }
+
+
+// ---- genome-sharded selection: per-rank device work of one iteration (collectives live above the ABI) ----
+namespace {
+__global__ void __launch_bounds__(256)
+shard_firstpos_kernel(const uint32_t* __restrict__ ids, uint32_t n, uint32_t n_part, const uint32_t* __restrict__ post_off,
+                      const uint32_t* __restrict__ postings, const uint32_t* __restrict__ ignored,
+                      const uint16_t* __restrict__ seg_part, uint32_t* __restrict__ first_pos) {
+  const uint32_t t = blockIdx.x;
+  if (t >= n) return;
+  uint32_t* fp = first_pos + (size_t)t * n_part;
+  for (uint32_t p = threadIdx.x; p < n_part; p += blockDim.x) fp[p] = 0xFFFFFFFFu;
+  __syncthreads();
+  const uint32_t c = ids[t];
+  if (c == MSSPE_NO_LOCAL_ID) return;
+  const uint32_t a = post_off[c], b = post_off[c + 1];
+  for (uint32_t i = a + threadIdx.x; i < b; i += blockDim.x) {
+    const uint32_t seg = postings[i];
+    if (!((ignored[seg >> 5] >> (seg & 31u)) & 1u)) atomicMin(&fp[seg_part[seg]], i - a);
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+shard_apply_kernel(uint32_t c, const uint32_t* __restrict__ post_off, const uint32_t* __restrict__ postings, uint32_t* ignored,
+                   const uint16_t* __restrict__ seg_part, uint8_t* part_flags) {
+  const uint32_t a = post_off[c], b = post_off[c + 1];
+  for (uint32_t i = a + threadIdx.x; i < b; i += blockDim.x) {
+    const uint32_t seg = postings[i];
+    atomicOr(&ignored[seg >> 5], 1u << (seg & 31u));
+    part_flags[seg_part[seg]] = 1;
+  }
+}
+}  // namespace
+
+extern "C" int msspe_shard_begin(msspe_ctx* c, uint8_t dir) {
+  if (!c || dir > 1) return MSSPE_ERR_INVALID;
+  if (!c->built) { c->set_error("msspe_shard_begin: index not built"); return MSSPE_ERR_STATE; }
+  MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
+  DirIndex& D = c->dir[dir];
+  const size_t mask_words = div_up_u64(c->n_segments, 32) + 1;
+  MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.ignored, 0, mask_words * 4, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.acc, 0, (uint64_t)(D.n_tiles + 1) * 8, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.freq, 0, (D.n_codes ? D.n_codes : 1) * 4, c->stream));
+  return MSSPE_OK;
+}
+
+extern "C" int msspe_shard_buffers(msspe_ctx* c, uint8_t dir, const uint64_t** d_codes, const uint32_t** d_freq, uint64_t* n_codes) {
+  if (!c || dir > 1) return MSSPE_ERR_INVALID;
+  if (!c->built) { c->set_error("msspe_shard_buffers: index not built"); return MSSPE_ERR_STATE; }
+  if (d_codes) *d_codes = c->dir[dir].codes;
+  if (d_freq) *d_freq = c->dir[dir].freq;
+  if (n_codes) *n_codes = c->dir[dir].n_codes;
+  return MSSPE_OK;
+}
+
+extern "C" int msspe_shard_count(msspe_ctx* c, uint8_t dir, uint64_t* live) {
+  if (!c || dir > 1) return MSSPE_ERR_INVALID;
+  if (!c->built) { c->set_error("msspe_shard_count: index not built"); return MSSPE_ERR_STATE; }
+  MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
+  DirIndex& D = c->dir[dir];
+  cudaStream_t st = c->stream;
+  MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.ctl, 0, sizeof(SelectCtl), st));
+  if (D.n_tiles) {
+    const uint32_t mask_words = (uint32_t)div_up_u64(c->n_segments, 32) + 1u;
+    const size_t mask_bytes = (size_t)mask_words * 4;
+    const bool smem_mask = mask_bytes + 8192 <= c->smem_optin;
+    constexpr int WARPS = CNT_THREADS / 32;
+    const unsigned blocks = (unsigned)div_up_u64(D.n_tiles, WARPS);
+    const unsigned cap = (unsigned)c->sm_count * (smem_mask && mask_bytes > 100 * 1024 ? 1u : 2u);
+    const unsigned grid = blocks < cap ? blocks : cap;
+    if (smem_mask) {
+      MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mask_bytes));
+      count_kernel<true><<<grid, CNT_THREADS, mask_bytes, st>>>(D.postings, D.post_off, D.tile_first, (uint32_t)D.n_codes, (uint32_t)D.n_records,
+                                                                D.n_tiles, D.ignored, mask_words, D.freq, D.acc, D.ctl);
+    } else {
+      count_kernel<false><<<grid, CNT_THREADS, 0, st>>>(D.postings, D.post_off, D.tile_first, (uint32_t)D.n_codes, (uint32_t)D.n_records,
+                                                        D.n_tiles, D.ignored, mask_words, D.freq, D.acc, D.ctl);
+    }
+    c->timing.kernel_launches++;
+    MSSPE_CUDA_TRY(c, cudaGetLastError());
+  }
+  if (live) {
+    MSSPE_CUDA_TRY(c, cudaMemcpyAsync(&c->h_ctl[dir], D.ctl, sizeof(SelectCtl), cudaMemcpyDeviceToHost, st));
+    MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+    *live = c->h_ctl[dir].evals;
+  }
+  return MSSPE_OK;
+}
+
+extern "C" int msspe_shard_firstpos(msspe_ctx* c, uint8_t dir, const uint32_t* local_ids, uint32_t n, uint32_t n_part, uint32_t* first_pos) {
+  if (!c || dir > 1 || (n && (!local_ids || !first_pos))) return MSSPE_ERR_INVALID;
+  if (!c->built) { c->set_error("msspe_shard_firstpos: index not built"); return MSSPE_ERR_STATE; }
+  if (n_part <= c->max_partition && c->n_segments) { c->set_error("msspe_shard_firstpos: n_part %u <= max partition %u", n_part, c->max_partition); return MSSPE_ERR_INVALID; }
+  if (n == 0) return MSSPE_OK;
+  MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
+  DirIndex& D = c->dir[dir];
+  for (uint32_t i = 0; i < n; i++)
+    if (local_ids[i] != MSSPE_NO_LOCAL_ID && local_ids[i] >= D.n_codes) { c->set_error("msspe_shard_firstpos: id %u out of range", local_ids[i]); return MSSPE_ERR_INVALID; }
+  cudaStream_t st = c->stream;
+  uint32_t* d_ids = nullptr; uint32_t* d_fp = nullptr;
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&d_ids, (size_t)n * 4, st));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&d_fp, (size_t)n * n_part * 4, st));
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(d_ids, local_ids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  shard_firstpos_kernel<<<n, 256, 0, st>>>(d_ids, n, n_part, D.post_off, D.postings, D.ignored, c->d_seg_part, d_fp);
+  c->timing.kernel_launches++;
+  MSSPE_CUDA_TRY(c, cudaGetLastError());
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(first_pos, d_fp, (size_t)n * n_part * 4, cudaMemcpyDeviceToHost, st));
+  MSSPE_CUDA_TRY(c, cudaFreeAsync(d_ids, st));
+  MSSPE_CUDA_TRY(c, cudaFreeAsync(d_fp, st));
+  MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+  return MSSPE_OK;
+}
+
+extern "C" int msspe_shard_apply(msspe_ctx* c, uint8_t dir, uint32_t local_id, uint32_t n_part, uint8_t* part_flags) {
+  if (!c || dir > 1 || !part_flags) return MSSPE_ERR_INVALID;
+  if (!c->built) { c->set_error("msspe_shard_apply: index not built"); return MSSPE_ERR_STATE; }
+  memset(part_flags, 0, n_part);
+  if (local_id == MSSPE_NO_LOCAL_ID) return MSSPE_OK;
+  DirIndex& D = c->dir[dir];
+  if (local_id >= D.n_codes) { c->set_error("msspe_shard_apply: id %u out of range", local_id); return MSSPE_ERR_INVALID; }
+  if (n_part <= c->max_partition) { c->set_error("msspe_shard_apply: n_part %u <= max partition %u", n_part, c->max_partition); return MSSPE_ERR_INVALID; }
+  MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  uint8_t* d_flags = nullptr;
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&d_flags, n_part, st));
+  MSSPE_CUDA_TRY(c, cudaMemsetAsync(d_flags, 0, n_part, st));
+  shard_apply_kernel<<<1, 1024, 0, st>>>(local_id, D.post_off, D.postings, D.ignored, c->d_seg_part, d_flags);
+  c->timing.kernel_launches++;
+  MSSPE_CUDA_TRY(c, cudaGetLastError());
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(part_flags, d_flags, n_part, cudaMemcpyDeviceToHost, st));
+  MSSPE_CUDA_TRY(c, cudaFreeAsync(d_flags, st));
+  MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+  return MSSPE_OK;
+}

@@ -27,6 +27,7 @@ ABI_SYMBOLS = [
     "msspe_build_index", "msspe_segment_info", "msspe_get_segment_kmers", "msspe_get_index", "msspe_select",
     "msspe_select_both", "msspe_coverage", "msspe_thal_params_default", "msspe_thal_params_from_dir",
     "msspe_set_thal_params", "msspe_primer_thermo", "msspe_thal_pairs", "msspe_cross_dimer",
+    "msspe_shard_begin", "msspe_shard_buffers", "msspe_shard_count", "msspe_shard_firstpos", "msspe_shard_apply",
 ]
 
 
@@ -114,6 +115,11 @@ def load_library():
     L.msspe_cross_dimer.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(ThalCond), C.c_uint32,
                                     C.c_uint32, C.c_double, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p,
                                     C.c_uint64, C.POINTER(C.c_uint64)]
+    L.msspe_shard_begin.argtypes = [C.c_void_p, C.c_uint8]
+    L.msspe_shard_buffers.argtypes = [C.c_void_p, C.c_uint8, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.msspe_shard_count.argtypes = [C.c_void_p, C.c_uint8, C.POINTER(C.c_uint64)]
+    L.msspe_shard_firstpos.argtypes = [C.c_void_p, C.c_uint8, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.msspe_shard_apply.argtypes = [C.c_void_p, C.c_uint8, C.c_uint32, C.c_uint32, C.c_void_p]
     _lib = L
     return L
 
@@ -266,6 +272,52 @@ class Engine:
                                              row_end, dg_limit, edges.ctypes.data, ecap, C.byref(ne), nos.ctypes.data,
                                              ncap, C.byref(nn)))
         return edges[:ne.value], nos[:nn.value]
+
+    # -- genome-sharded selection: per-rank primitives (msspe_b200.distributed.select_sharded drives them) --
+    class _DevArray:
+        """Zero-copy view of a device buffer for torch.as_tensor (CUDA array interface)."""
+
+        def __init__(self, ptr, n, typestr):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+    def shard_begin(self, direction: int):
+        self._check(self.L.msspe_shard_begin(self.h, direction))
+
+    def _shard_buffers(self, direction: int):
+        pc, pf, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._check(self.L.msspe_shard_buffers(self.h, direction, C.byref(pc), C.byref(pf), C.byref(n)))
+        return pc.value, pf.value, n.value
+
+    def shard_codes(self, direction: int):
+        import torch
+        pc, _, n = self._shard_buffers(direction)
+        if n == 0:
+            return torch.zeros(0, dtype=torch.int64, device="cuda")
+        return torch.as_tensor(Engine._DevArray(pc, n, "<i8"), device="cuda")  # codes < 2^62: order-preserving as int64
+
+    def shard_count(self, direction: int):
+        import torch
+        live = C.c_uint64()
+        self._check(self.L.msspe_shard_count(self.h, direction, C.byref(live)))
+        _, pf, n = self._shard_buffers(direction)
+        f = torch.as_tensor(Engine._DevArray(pf, n, "<i4"), device="cuda") if n else torch.zeros(0, dtype=torch.int32, device="cuda")
+        return f, live.value
+
+    def shard_n_part(self) -> int:
+        g, maxp, _ = self.segment_info()
+        return (maxp + 1) if g else 0
+
+    def shard_firstpos(self, direction: int, local_ids: np.ndarray, n_part: int) -> np.ndarray:
+        ids = np.ascontiguousarray(local_ids, dtype=np.uint32)
+        out = np.full((len(ids), n_part), 0xFFFFFFFF, dtype=np.uint32)
+        if len(ids) and n_part:
+            self._check(self.L.msspe_shard_firstpos(self.h, direction, ids.ctypes.data, len(ids), n_part, out.ctypes.data))
+        return out
+
+    def shard_apply(self, direction: int, local_id: int, n_part: int) -> np.ndarray:
+        out = np.zeros(max(1, n_part), dtype=np.uint8)
+        self._check(self.L.msspe_shard_apply(self.h, direction, local_id & 0xFFFFFFFF, n_part, out.ctypes.data))
+        return out[:n_part]
 
     def set_thal_params_dir(self, path: str):
         buf = C.create_string_buffer(RAW_PARAMS_BYTES + 64)

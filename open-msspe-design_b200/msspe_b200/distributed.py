@@ -7,8 +7,10 @@ What shards:
     with one all_gather -- the only collective on this path.  Results are identical to a single-GPU run
     because the lists are keyed by the global pair index and merged in rank (= row) order.
   * independent genome sets (one design job per GPU): no collective at all (bench.py weak scaling).
-The exact genome-sharded greedy loop (k-mer owner re-shard + per-iteration 256-byte all_gather) is described in
-DESIGN.md as the next step; it is not implemented in this round.
+  * the greedy selection of ONE job whose genomes are block-partitioned over the ranks (select_sharded): every rank
+    recounts its own segments, the per-k-mer counts are merged with an all-reduce(sum) over NVLink, every rank then
+    takes the same arg-max; the order-sensitive f32 tie score is rebuilt from the per-rank positions of the first
+    live posting of each partition (rank order = global segment order).  Bit-identical to the single-GPU loop.
 """
 from __future__ import annotations
 
@@ -58,3 +60,99 @@ def cross_dimer_sharded(compute_rows, n: int, edge_dtype, dist=None, device="cpu
     all_n = np.concatenate([p.view(np.uint64) for p in parts_n]) if parts_n else np.zeros(0, dtype=np.uint64)
     # row blocks are ordered by rank and each list is sorted inside its block -> already globally sorted
     return all_e, all_n
+
+
+NO_LOCAL_ID = 0xFFFFFFFF
+
+
+def _all_reduce(t, dist, op=None):
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=op if op is not None else dist.ReduceOp.SUM)
+    return t
+
+
+def _all_gather_same(t, dist):
+    """all_gather of equally shaped tensors -> stacked [world, ...]."""
+    import torch
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return t.unsqueeze(0)
+    outs = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(outs, t.contiguous())
+    return torch.stack(outs)
+
+
+def select_sharded(se, direction: int, max_iterations: int, max_mismatch_segments: int, dist=None, device="cuda"):
+    """find_candidates_kmers (od-msspe/src/main.rs:331-406) for one direction over genome shards.
+
+    `se` is this rank's shard engine (msspe_b200.Engine after load_genomes/build_index on the rank's contiguous
+    block of records, or any object with the same shard_* methods).  Returns (candidates, evals, iterations):
+    candidates as a CANDIDATE_DTYPE array identical on every rank and identical to Engine.select on the whole input.
+    """
+    import torch
+    from . import CANDIDATE_DTYPE
+    world = dist.get_world_size() if (dist is not None and dist.is_initialized()) else 1
+    se.shard_begin(direction)
+    codes = se.shard_codes(direction).to(device)
+    n_local = int(codes.numel())
+    # ---- global k-mer dictionary: union of the per-rank sorted code lists ----
+    if world > 1:
+        sizes = _all_gather_same(torch.tensor([n_local], dtype=torch.int64, device=device), dist).flatten().tolist()
+        cap = max(max(sizes), 1)
+        padded = torch.full((cap,), -1, dtype=torch.int64, device=device)
+        padded[:n_local] = codes
+        allc = _all_gather_same(padded, dist)
+        union = torch.cat([allc[r, :sizes[r]] for r in range(world)])
+        ug = torch.unique(union, sorted=True)
+    else:
+        ug = codes.clone()
+    n_global = int(ug.numel())
+    l2g = torch.searchsorted(ug, codes) if n_local else torch.zeros(0, dtype=torch.int64, device=device)
+    g2l = torch.full((max(n_global, 1),), -1, dtype=torch.int64, device=device)
+    if n_local:
+        g2l[l2g] = torch.arange(n_local, dtype=torch.int64, device=device)
+    n_part = int(_all_reduce(torch.tensor([se.shard_n_part()], dtype=torch.int64, device=device), dist,
+                             dist.ReduceOp.MAX if world > 1 else None).item())
+    cov = np.zeros(max(n_part, 1), dtype=np.uint32)      # partition_coverage, replicated
+    out, evals, iterations = [], 0, 0
+    one = np.float32(1.0)
+    for _ in range(max_iterations):
+        freq, _live = se.shard_count(direction)
+        g = torch.zeros(max(n_global, 1), dtype=torch.int32, device=device)
+        if n_local:
+            g[l2g] = freq.to(device)
+        _all_reduce(g, dist)                               # "per-window counts merged by NCCL reduce over NVLink"
+        iterations += 1
+        evals += int(g.sum(dtype=torch.int64).item())
+        gmax = int(g.max().item()) if n_global else 0
+        if gmax <= 1:                                      # None / freq == 1: stop before the push (main.rs:353-366)
+            break
+        tied = torch.nonzero(g == gmax).flatten()          # ascending global id == ascending word
+        lids = g2l[tied]
+        lids_np = np.where(lids.cpu().numpy() < 0, NO_LOCAL_ID, lids.cpu().numpy()).astype(np.uint32)
+        fp = se.shard_firstpos(direction, lids_np, n_part)                              # [n_tied, n_part] u32
+        fpw = _all_gather_same(torch.from_numpy(fp.view(np.int32).copy()).to(device), dist).cpu().numpy().view(np.uint32)
+        has = fpw != np.uint32(0xFFFFFFFF)                                               # [world, n_tied, n_part]
+        anyp = has.any(axis=0)
+        first_rank = has.argmax(axis=0)
+        pos = np.take_along_axis(fpw, first_rank[None], axis=0)[0]
+        key = np.where(anyp, (first_rank.astype(np.uint64) << np.uint64(32)) | pos.astype(np.uint64), np.uint64(0xFFFFFFFFFFFFFFFF))
+        order = np.argsort(key, axis=1, kind="stable")
+        term = (one / (cov[:n_part].astype(np.float32) + one)).astype(np.float32)       # 1.0 / (already_covered as f32 + 1.0)
+        terms = np.where(anyp, term[None, :], np.float32(0.0)).astype(np.float32)
+        ts = np.take_along_axis(terms, order, axis=1)
+        score = np.zeros(len(tied), dtype=np.float32)
+        for t in range(int(anyp.sum(axis=1).max()) if len(tied) else 0):                 # sequential f32 adds, first-seen order
+            score = (score + ts[:, t]).astype(np.float32)
+        w = int(np.argmax(score))                                                        # first maximum = smallest word
+        gid = int(tied[w].item())
+        out.append((int(ug[gid].item()), gmax, len(tied), float(score[w]), 0))
+        lid = int(g2l[gid].item())
+        flags = se.shard_apply(direction, lid if lid >= 0 else NO_LOCAL_ID, n_part)
+        ft = _all_reduce(torch.from_numpy(flags.astype(np.int32)).to(device), dist, dist.ReduceOp.MAX if world > 1 else None)
+        cov[:n_part] += ft.cpu().numpy().astype(np.uint32)
+        if gmax < max_mismatch_segments or len(out) >= max_iterations:                    # main.rs:387-390, :344
+            break
+    res = np.zeros(len(out), dtype=CANDIDATE_DTYPE)
+    for i, (c, f, nt, sc, _) in enumerate(out):
+        res[i] = (c, f, nt, sc, 0)
+    return res, evals, iterations

@@ -224,3 +224,15 @@ def test_cfg2_full_size_properties():
     cov, part, rec = eng.coverage(a0["code"], b0["code"])
     assert cov.sum() > 0.5 * G and part.max() == 118 and rec.max() == 999
     eng.close()
+
+
+def test_sharded_selection_primitives_world1(zika_engine):
+    """msspe_shard_* primitives driven by select_sharded without a process group == the fused device loop."""
+    from msspe_b200 import distributed as D
+    eng, _ = zika_engine
+    for d in (0, 1):
+        want = eng.select(d, 1000, 2, 0)
+        want_evals = eng.timing().select_evals[d]
+        got, evals, iters = D.select_sharded(eng, d, 1000, 2, None, "cuda")
+        assert got.tobytes() == want.tobytes()
+        assert evals == want_evals and iters == eng.timing().select_iterations[d]
