@@ -41,47 +41,6 @@ MAX_ITER = 1000
 THAL_POOL = 4096
 
 
-def f32_via_text(v, fmt):
-    return np.float32(float(fmt % v))
-
-
-def host_filters(words_thermo, cfg):
-    """get_kmer_stats / filter_kmers (main.rs:408-516) on the five numbers per primer, with Primer3's text
-    round trip (%.3f / %.2f -> f32).  Host glue: <= 1000 values per direction."""
-    tm = np.array([f32_via_text(v, "%.3f") for v in words_thermo["tm"]], dtype=np.float32)
-    any_ = np.array([f32_via_text(v, "%.2f") for v in words_thermo["self_any"]], dtype=np.float32)
-    end_ = np.array([f32_via_text(v, "%.2f") for v in words_thermo["self_end"]], dtype=np.float32)
-    hp = np.array([f32_via_text(v, "%.2f") for v in words_thermo["hairpin"]], dtype=np.float32)
-    n = len(tm)
-    if n == 0:
-        return np.zeros(0, dtype=bool)
-    s = np.float32(0)
-    for v in tm:
-        s = np.float32(s + v)
-    mean = np.float32(s / np.float32(n))
-    sq = np.float32(0)
-    for v in tm:
-        d = np.float32(v - mean)
-        sq = np.float32(sq + np.float32(d * d))
-    sd = np.float32(np.sqrt(np.float32(sq / np.float32(n - 1)))) if n > 1 else np.float32("nan")
-    tm_ok = np.abs(tm - mean) <= np.float32(cfg["tm_stddev"]) * sd
-    runs = np.array([r for r in words_thermo["runs"]], dtype=bool)
-    keep = (any_ < np.float32(47.0)) & (end_ < np.float32(47.0)) & (hp < np.float32(24.0)) & (tm > np.float32(30.0)) & \
-           (tm < np.float32(60.0)) & tm_ok & ~runs
-    return keep
-
-
-def trailing_run(code, k):
-    last = code & 3
-    run = 0
-    for i in range(1, k):
-        if (code >> (2 * i)) & 3 == last:
-            run += 1
-        else:
-            break
-    return run >= 5
-
-
 def clock_sampler(stop, out, gpu_index):
     q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     while not stop.is_set():
@@ -191,7 +150,7 @@ def main():
     host_pinned = torch.from_numpy(genomes.reshape(-1)).pin_memory()
     dev_bases = host_pinned.to(dev, non_blocking=False)
     mms = min(10, max(1, -(-n_rec // 50)))  # main.rs:658-660
-    fcfg = {"tm_stddev": 2.0}
+    fcfg = m.default_filter_cfg()
 
     eng = m.Engine(k, 500, 250, 50, device=local_rank)
     stream = torch.cuda.current_stream(dev)
@@ -205,10 +164,9 @@ def main():
         eng.build_index()
         fwd, rev = eng.select_both(MAX_ITER, mms, mode)
         kept = []
-        for cand in (fwd, rev):
-            th = eng.primer_thermo(cand["code"])
-            th["runs"] = [trailing_run(int(c), k) for c in cand["code"]]
-            kept.append(cand["code"][host_filters(th, fcfg)])
+        for cand in (fwd, rev):   # get_kmer_stats + filter_kmers (main.rs:408-516) through the C ABI
+            st = eng.kmer_stats(cand["code"], fcfg)
+            kept.append(st["code"][st["keep"] != 0])
         t = eng.timing()
         return int(t.select_evals[0] + t.select_evals[1]), fwd, rev, kept, t
 
@@ -370,7 +328,7 @@ def main():
             r.close()
         fwd, rev, kept = res_dev[0][1], res_dev[0][2], res_dev[0][3]
         h2d = int(genomes.size) + 8 * (n_rec + 1)
-        d2h = int((len(fwd) + len(rev)) * (24 + 5 * 8)) + 2 * 40
+        d2h = int((len(fwd) + len(rev)) * (24 + 5 * 8 + 3 * 40)) + 2 * 128
         line = {
             "metric": "kmer_coverage_evals_per_s", "value": total_evals / t_dev, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,

@@ -206,6 +206,28 @@ int msspe_set_thal_params(msspe_ctx* ctx, const msspe_thal_raw_params* p);
  * tm = oligotm at Primer3 defaults, gc = percent, self_any/self_end/hairpin = max(0, thal Tm). */
 int msspe_primer_thermo(msspe_ctx* ctx, const uint64_t* codes, uint32_t n, uint32_t oligo_len, double* tm,
                         double* gc, double* self_any, double* self_end, double* hairpin);
+/* One row of get_kmer_stats (main.rs:408-455): the five numbers AFTER Primer3's text round trip ("%.3f" for TM and
+ * GC_PERCENT, "%.2f" for the *_TH values, each parsed back as f32 like primer.rs:67-114), the per-direction Tm mean
+ * and standard deviation (main.rs:462-467; std-dev 0.1.0 = sample deviation), tm_in_threshold (:469-471), is_run
+ * (:478-490) and the verdict of filter_kmers (:492-516). */
+typedef struct {
+  uint64_t code;
+  float tm, gc_percent, self_any_th, self_end_th, hairpin_th, mean, std;
+  uint8_t tm_ok, runs, keep, reserved;
+} msspe_kmer_stat;
+
+/* The ProgramConfig / PrimerConfig fields filter_kmers reads (config.rs:150-177). */
+typedef struct {
+  float min_tm, max_tm, max_self_dimer_any_tm, max_self_dimer_end_tm, max_hairpin_tm, tm_stddev;
+  uint8_t check_self_dimers, check_hairpin, disable_tm_stddev, disable_min_max_tm;
+} msspe_filter_cfg;
+
+/* Replaces get_kmer_stats + filter_kmers for the candidates of ONE direction, in selection order: the thermodynamics
+ * run on the device (msspe_primer_thermo), the printing/rounding, the sequential f32 mean / deviation and the strict
+ * f32 comparisons on the host exactly as the reference does them. */
+int msspe_kmer_stats(msspe_ctx* ctx, const uint64_t* codes, uint32_t n, uint32_t oligo_len, const msspe_filter_cfg* cfg,
+                     msspe_kmer_stat* out);
+
 /* Arbitrary pair list through thal (type = MSSPE_THAL_*); a[i], b[i] are 2-bit codes of length oligo_len.
  * For HAIRPIN b is ignored.  One ntthal invocation per pair in the reference (delta_g.rs:93-113). */
 int msspe_thal_pairs(msspe_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t n_pairs, uint32_t oligo_len,

@@ -1,0 +1,64 @@
+// filters.cu -- get_kmer_stats / get_tm_stat / tm_in_threshold / is_run / filter_kmers of the reference
+// (od-msspe/src/main.rs:408-516) behind the C ABI.  The five thermodynamic numbers come from the device
+// (msspe_primer_thermo); what follows is <= 1000 values per direction of strictly ordered f32 arithmetic and
+// Primer3's text formatting, which is host work by nature and must match the reference bit for bit.
+#include <cmath>
+#include <cstdlib>
+
+#include "engine.cuh"
+
+namespace {
+float via_text(double v, const char* fmt) {  // Primer3 prints, parse_primer3_output reads an f32 (primer.rs:67-114)
+  char b[64];
+  snprintf(b, sizeof b, fmt, v);
+  return strtof(b, nullptr);
+}
+}  // namespace
+
+extern "C" int msspe_kmer_stats(msspe_ctx* c, const uint64_t* codes, uint32_t n, uint32_t oligo_len, const msspe_filter_cfg* cfg,
+                                msspe_kmer_stat* out) {
+  if (!c) return MSSPE_ERR_INVALID;
+  if (!cfg || (n && (!codes || !out))) { c->set_error("msspe_kmer_stats: null argument"); return MSSPE_ERR_INVALID; }
+  if (n == 0) return MSSPE_OK;
+  std::vector<double> tm(n), gc(n), sa(n), se(n), hp(n);
+  int rc = msspe_primer_thermo(c, codes, n, oligo_len, tm.data(), gc.data(), sa.data(), se.data(), hp.data());
+  if (rc) return rc;
+  for (uint32_t i = 0; i < n; i++) {
+    msspe_kmer_stat& s = out[i];
+    s.code = codes[i];
+    s.tm = via_text(tm[i], "%.3f");
+    s.gc_percent = via_text(gc[i], "%.3f");
+    s.self_any_th = via_text(sa[i], "%.2f");
+    s.self_end_th = via_text(se[i], "%.2f");
+    s.hairpin_th = via_text(hp[i], "%.2f");
+  }
+  // get_tm_stat (main.rs:462-467): f32 sum in candidate order; std-dev 0.1.0 = sqrt(sum((x-mean)^2)/(n-1))
+  float sum = 0.0f;
+  for (uint32_t i = 0; i < n; i++) sum += out[i].tm;
+  const float mean = sum / (float)n;
+  float sq = 0.0f;
+  for (uint32_t i = 0; i < n; i++) { const float d = out[i].tm - mean; sq += d * d; }
+  const float sd = std::sqrt(sq / (float)((double)n - 1.0));
+  for (uint32_t i = 0; i < n; i++) {
+    msspe_kmer_stat& s = out[i];
+    s.mean = mean; s.std = sd;
+    s.tm_ok = std::fabs(s.tm - mean) <= (cfg->tm_stddev * sd) ? 1 : 0;      // tm_in_threshold (main.rs:469-471)
+    {  // is_run (main.rs:478-490): true iff the last six bases are equal
+      int runs = 0; uint32_t last = 0xFFu;
+      for (uint32_t t = 0; t < oligo_len; t++) {
+        const uint32_t b = (uint32_t)(codes[i] >> (2 * (oligo_len - 1 - t))) & 3u;
+        if (b == last) runs++; else runs = 0;
+        last = b;
+      }
+      s.runs = runs >= 5 ? 1 : 0;
+    }
+    const bool p_any = !cfg->check_self_dimers || (s.self_any_th < cfg->max_self_dimer_any_tm);   // filter_kmers (main.rs:492-516)
+    const bool p_end = !cfg->check_self_dimers || (s.self_end_th < cfg->max_self_dimer_end_tm);
+    const bool p_hp = !cfg->check_hairpin || (s.hairpin_th < cfg->max_hairpin_tm);
+    const bool p_mm = cfg->disable_min_max_tm || (s.tm > cfg->min_tm && s.tm < cfg->max_tm);
+    const bool p_sd = cfg->disable_tm_stddev || s.tm_ok;
+    s.keep = (p_any && p_end && p_hp && p_mm && p_sd && !s.runs) ? 1 : 0;
+    s.reserved = 0;
+  }
+  return MSSPE_OK;
+}

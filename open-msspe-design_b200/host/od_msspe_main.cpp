@@ -189,48 +189,36 @@ float via_text(double v, const char* fmt) { char b[64]; snprintf(b, sizeof b, fm
 std::string fmt2(float x) { char b[64]; snprintf(b, sizeof b, "%.2f", (double)x); return b; }  // Rust {:.2} of an f32
 std::string fmt1(float x) { if (std::isnan(x)) return "NaN"; if (std::isinf(x)) return x > 0 ? "inf" : "-inf"; char b[64]; snprintf(b, sizeof b, "%.1f", (double)x); return b; }
 
-struct KmerStat { uint64_t code; std::string word; uint8_t direction; float gc_percent, mean, std, tm; bool tm_ok; float self_any_th, self_end_th, hairpin_th; bool runs; };
+struct KmerStat { uint64_t code; std::string word; uint8_t direction; float gc_percent, mean, std, tm; bool tm_ok; float self_any_th, self_end_th, hairpin_th; bool runs; bool keep; };
 
-bool is_run(const std::string& k) { int runs = 0; char last = ' '; for (char c : k) { if (c == last) runs++; else runs = 0; last = c; } return runs >= 5; }  // main.rs:478-490
 
 #define CHECK(call) do { int rc_ = (call); if (rc_ != MSSPE_OK) { std::cerr << "od-msspe: " #call " failed (" << rc_ << "): " << msspe_last_error(ctx) << "\n"; exit(1); } } while (0)
 
-// get_kmer_stats, main.rs:408-455: Primer3 prints "%.3f" (TM, GC) and "%.2f" (*_TH); parse_primer3_output reads f32
+// get_kmer_stats + filter_kmers (main.rs:408-516) through the ABI: msspe_kmer_stats does the device thermodynamics and
+// the reference's text round trips / f32 statistics / strict comparisons.
 std::vector<KmerStat> kmer_stats(msspe_ctx* ctx, const std::vector<msspe_candidate>& cand, uint8_t dir, unsigned k, const Args& a) {
   const uint32_t n = (uint32_t)cand.size();
   std::vector<uint64_t> codes(n);
   for (uint32_t i = 0; i < n; i++) codes[i] = cand[i].code;
-  std::vector<double> tm(n), gc(n), sa(n), se(n), hp(n);
-  if (n) CHECK(msspe_primer_thermo(ctx, codes.data(), n, k, tm.data(), gc.data(), sa.data(), se.data(), hp.data()));
+  msspe_filter_cfg fc{a.min_tm, a.max_tm, a.max_self_dimer_any_tm, a.max_self_dimer_end_tm, a.max_hairpin_tm, a.tm_stddev,
+                      (uint8_t)(a.check_self_dimers == "true"), (uint8_t)(a.check_hairpin == "true"),
+                      (uint8_t)(a.disable_tm_stddev == "true"), (uint8_t)(a.disable_min_max_tm == "true")};
+  std::vector<msspe_kmer_stat> st(n ? n : 1);
+  if (n) CHECK(msspe_kmer_stats(ctx, codes.data(), n, k, &fc, st.data()));
   std::vector<KmerStat> out(n);
-  std::vector<float> tms(n);
-  for (uint32_t i = 0; i < n; i++) tms[i] = via_text(tm[i], "%.3f");
-  float sum = 0.0f; for (float v : tms) sum += v;                       // get_tm_stat, main.rs:462-467
-  const float mean = sum / (float)n;
-  float sq = 0.0f; for (float v : tms) { const float d = v - mean; sq += d * d; }
-  const float sd = std::sqrt(sq / (float)((double)n - 1.0));            // std-dev 0.1.0: sample standard deviation (n-1)
   for (uint32_t i = 0; i < n; i++) {
     KmerStat& s = out[i];
     s.code = codes[i]; s.word = decode(codes[i], k); s.direction = dir;
-    s.gc_percent = via_text(gc[i], "%.3f"); s.mean = mean; s.std = sd; s.tm = tms[i];
-    s.tm_ok = std::fabs(s.tm - mean) <= (a.tm_stddev * sd);             // tm_in_threshold, main.rs:469-471
-    s.self_any_th = via_text(sa[i], "%.2f"); s.self_end_th = via_text(se[i], "%.2f"); s.hairpin_th = via_text(hp[i], "%.2f");
-    s.runs = is_run(s.word);
+    s.gc_percent = st[i].gc_percent; s.mean = st[i].mean; s.std = st[i].std; s.tm = st[i].tm; s.tm_ok = st[i].tm_ok != 0;
+    s.self_any_th = st[i].self_any_th; s.self_end_th = st[i].self_end_th; s.hairpin_th = st[i].hairpin_th; s.runs = st[i].runs != 0;
+    s.keep = st[i].keep != 0;
   }
   return out;
 }
 
-std::vector<KmerStat> filter_kmers(const std::vector<KmerStat>& st, const Args& a) {  // main.rs:492-516
-  const bool cs = a.check_self_dimers == "true", ch = a.check_hairpin == "true", dmm = a.disable_min_max_tm == "true", dsd = a.disable_tm_stddev == "true";
+std::vector<KmerStat> filter_kmers(const std::vector<KmerStat>& st) {
   std::vector<KmerStat> out;
-  for (auto& k : st) {
-    const bool p_any = !cs || (k.self_any_th < a.max_self_dimer_any_tm);
-    const bool p_end = !cs || (k.self_end_th < a.max_self_dimer_end_tm);
-    const bool p_hp = !ch || (k.hairpin_th < a.max_hairpin_tm);
-    const bool p_mm = dmm || (k.tm > a.min_tm && k.tm < a.max_tm);
-    const bool p_sd = dsd || k.tm_ok;
-    if (p_any && p_end && p_hp && p_mm && p_sd && !k.runs) out.push_back(k);
-  }
+  for (auto& k : st) if (k.keep) out.push_back(k);
   return out;
 }
 
@@ -294,7 +282,7 @@ int main(int argc, char** argv) {
   std::vector<KmerStat> stats[2], primers_dir[2];
   for (int d = 0; d < 2; d++) {
     stats[d] = kmer_stats(ctx, cand[d], (uint8_t)d, k, a);
-    primers_dir[d] = keep_all ? stats[d] : filter_kmers(stats[d], a);
+    primers_dir[d] = keep_all ? stats[d] : filter_kmers(stats[d]);
   }
   // cross dimers (run_ntthal, main.rs:752 / delta_g.rs:61-153)
   std::vector<const KmerStat*> primers;

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "msspe_build_index", "msspe_segment_info", "msspe_get_segment_kmers", "msspe_get_index", "msspe_select",
     "msspe_select_both", "msspe_coverage", "msspe_thal_params_default", "msspe_thal_params_from_dir",
     "msspe_set_thal_params", "msspe_primer_thermo", "msspe_thal_pairs", "msspe_cross_dimer",
-    "msspe_shard_begin", "msspe_shard_buffers", "msspe_shard_count", "msspe_shard_firstpos", "msspe_shard_apply",
+    "msspe_kmer_stats", "msspe_shard_begin", "msspe_shard_buffers", "msspe_shard_count", "msspe_shard_firstpos", "msspe_shard_apply",
 ]
 
 
@@ -53,6 +53,27 @@ class ThalOut(C.Structure):
 
 class DimerEdge(C.Structure):
     _fields_ = [("pair", C.c_uint64), ("dg", C.c_double)]
+
+
+class FilterCfg(C.Structure):
+    _fields_ = [("min_tm", C.c_float), ("max_tm", C.c_float), ("max_self_dimer_any_tm", C.c_float),
+                ("max_self_dimer_end_tm", C.c_float), ("max_hairpin_tm", C.c_float), ("tm_stddev", C.c_float),
+                ("check_self_dimers", C.c_uint8), ("check_hairpin", C.c_uint8), ("disable_tm_stddev", C.c_uint8),
+                ("disable_min_max_tm", C.c_uint8)]
+
+
+def default_filter_cfg(**kw) -> "FilterCfg":
+    """constants.rs:15-20 and the config.rs defaults."""
+    f = FilterCfg(30.0, 60.0, 47.0, 47.0, 24.0, 2.0, 1, 1, 0, 0)
+    for k, v in kw.items():
+        assert hasattr(f, k), k
+        setattr(f, k, v)
+    return f
+
+
+KMER_STAT_DTYPE = np.dtype([("code", "<u8"), ("tm", "<f4"), ("gc_percent", "<f4"), ("self_any_th", "<f4"), ("self_end_th", "<f4"),
+                            ("hairpin_th", "<f4"), ("mean", "<f4"), ("std", "<f4"), ("tm_ok", "u1"), ("runs", "u1"), ("keep", "u1"),
+                            ("reserved", "u1")])
 
 
 class Timing(C.Structure):
@@ -115,6 +136,7 @@ def load_library():
     L.msspe_cross_dimer.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(ThalCond), C.c_uint32,
                                     C.c_uint32, C.c_double, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p,
                                     C.c_uint64, C.POINTER(C.c_uint64)]
+    L.msspe_kmer_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(FilterCfg), C.c_void_p]
     L.msspe_shard_begin.argtypes = [C.c_void_p, C.c_uint8]
     L.msspe_shard_buffers.argtypes = [C.c_void_p, C.c_uint8, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.msspe_shard_count.argtypes = [C.c_void_p, C.c_uint8, C.POINTER(C.c_uint64)]
@@ -247,6 +269,14 @@ class Engine:
         outs = [np.zeros(max(1, n), dtype=np.float64) for _ in range(5)]
         self._check(self.L.msspe_primer_thermo(self.h, codes.ctypes.data, n, oligo_len or self.k, *[o.ctypes.data for o in outs]))
         return dict(zip(("tm", "gc", "self_any", "self_end", "hairpin"), [o[:n] for o in outs]))
+
+    # -- get_kmer_stats + filter_kmers (main.rs:408-516) --
+    def kmer_stats(self, codes, cfg: "FilterCfg" = None, oligo_len=None) -> np.ndarray:
+        codes = np.ascontiguousarray(codes, dtype=np.uint64)
+        out = np.zeros(max(1, len(codes)), dtype=KMER_STAT_DTYPE)
+        cfg = cfg or default_filter_cfg()
+        self._check(self.L.msspe_kmer_stats(self.h, codes.ctypes.data, len(codes), oligo_len or self.k, C.byref(cfg), out.ctypes.data))
+        return out[:len(codes)]
 
     def thal_pairs(self, a, b, ttype, cond: ThalCond, oligo_len=None) -> np.ndarray:
         a = np.ascontiguousarray(a, dtype=np.uint64)

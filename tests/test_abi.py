@@ -30,14 +30,14 @@ def test_header_symbols_all_exported(lib):
 
 def test_struct_layouts_match_header(lib, tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "od_msspe_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "od_msspe_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    "sizeof(msspe_thal_raw_params),sizeof(msspe_timing),sizeof(msspe_candidate),sizeof(msspe_thal_out),"
-                   "sizeof(msspe_config),sizeof(msspe_thal_cond),sizeof(msspe_dimer_edge));}\n")
+                   "sizeof(msspe_config),sizeof(msspe_thal_cond),sizeof(msspe_dimer_edge),sizeof(msspe_kmer_stat),sizeof(msspe_filter_cfg));}\n")
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [lib.RAW_PARAMS_BYTES, C.sizeof(lib.Timing), C.sizeof(lib.Candidate), C.sizeof(lib.ThalOut), C.sizeof(lib.Config),
-            C.sizeof(lib.ThalCond), C.sizeof(lib.DimerEdge)]
+            C.sizeof(lib.ThalCond), C.sizeof(lib.DimerEdge), lib.KMER_STAT_DTYPE.itemsize, C.sizeof(lib.FilterCfg)]
     assert got == want
     assert lib.CANDIDATE_DTYPE.itemsize == got[2] and lib.THAL_OUT_DTYPE.itemsize == got[3] and lib.EDGE_DTYPE.itemsize == got[6]
 

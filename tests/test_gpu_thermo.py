@@ -149,3 +149,23 @@ def test_cross_dimer_matrix_matches_pair_list_and_oracle(eng, oracle_lib):
         assert int(full["no_structure"][p]) == w.no_structure
         if not w.no_structure:
             assert full["dg"][p] == w.dg and full["tm"][p] == w.tm
+
+
+def test_kmer_stats_and_filters_vs_oracle_pipeline(zika_fasta, oracle_lib):
+    """get_kmer_stats / filter_kmers (main.rs:408-516): text-rounded f32 values, mean, std, tm_ok, runs, verdict."""
+    import msspe_b200 as m
+    O = oracle_lib
+    want = O.run_pipeline(zika_fasta, O.default_config(check_cross_dimers=0))
+    eng = m.Engine(13, 500, 250, 50)
+    for d in (0, 1):
+        codes = [m.encode_word(w) for w, _, _, _ in want.candidates[d]]
+        st = eng.kmer_stats(codes)
+        for i, ws in enumerate(want.stats[d]):
+            for a, b in (("tm", "tm"), ("gc_percent", "gc"), ("self_any_th", "self_any"), ("self_end_th", "self_end"),
+                         ("hairpin_th", "hairpin"), ("mean", "mean"), ("std", "std")):
+                assert np.float32(st[a][i]).tobytes() == np.float32(ws[b]).tobytes(), (d, i, a)
+            assert bool(st["tm_ok"][i]) == ws["tm_ok"] and bool(st["runs"][i]) == ws["runs"]
+        kept = [m.decode_word(c, 13) for c in st["code"][st["keep"] != 0]]
+        assert kept == want.filtered[d]
+    want.close()
+    eng.close()
