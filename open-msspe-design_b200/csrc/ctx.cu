@@ -153,7 +153,7 @@ static int plan_segments(msspe_ctx* c, const uint64_t* offsets, uint32_t n) {
   if (offsets[0] != 0) { c->set_error("offsets[0] must be 0"); return MSSPE_ERR_INVALID; }
   c->h_offsets.assign(offsets, offsets + n + 1);
   c->h_seg_base.assign(n + 1, 0);
-  uint64_t g = 0, maxp = 0;
+  uint64_t g = 0, maxp = 0, minp = UINT64_MAX;
   for (uint32_t r = 0; r < n; r++) {
     if (offsets[r + 1] < offsets[r]) { c->set_error("offsets not monotone at record %u", r); return MSSPE_ERR_INVALID; }
     uint64_t L = offsets[r + 1] - offsets[r];
@@ -161,6 +161,7 @@ static int plan_segments(msspe_ctx* c, const uint64_t* offsets, uint32_t n) {
     c->h_seg_base[r] = g;
     g += P;
     if (P > maxp) maxp = P;
+    if (P < minp) minp = P;
   }
   c->h_seg_base[n] = g;
   if (g >= 0xFFFFFFFFull) { c->set_error("%llu segments exceed the u32 segment index of the reference (main.rs:250)", (unsigned long long)g); return MSSPE_ERR_CAPACITY; }
@@ -169,6 +170,7 @@ static int plan_segments(msspe_ctx* c, const uint64_t* offsets, uint32_t n) {
     return MSSPE_ERR_CAPACITY;
   }
   c->n_segments = g;
+  c->uniform_parts = (n > 0 && minp == maxp && maxp > 0 && maxp < 0xFFFFFFFFull) ? (uint32_t)maxp : 0u;
   // Segment.partition_no is `j as u16` (main.rs:227): the maximum of the wrapped values
   c->max_partition = maxp == 0 ? 0 : (maxp > 65536 ? 65535u : (uint32_t)(maxp - 1));
   c->n_records = n;

@@ -89,6 +89,7 @@ struct msspe_ctx {
   uint64_t n_segments = 0;            // G
   uint32_t slots = 0;                 // s = w - k + 1
   uint32_t max_partition = 0;
+  uint32_t uniform_parts = 0;         // > 0: every record has exactly this many partitions (equal-length alignment)
   uint16_t* d_seg_part = nullptr;     // [G]
   uint32_t* d_seg_rec = nullptr;      // [G]
   bool loaded = false, built = false;

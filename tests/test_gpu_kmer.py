@@ -236,3 +236,51 @@ def test_sharded_selection_primitives_world1(zika_engine):
         got, evals, iters = D.select_sharded(eng, d, 1000, 2, None, "cuda")
         assert got.tobytes() == want.tobytes()
         assert evals == want_evals and iters == eng.timing().select_iterations[d]
+
+
+def test_cfg3_full_size_properties():
+    """BASELINE configs[2] at full size (10,000 x 11 kb, k=15, --max-mismatch-segments=2, 1000 iterations): the three
+    loop implementations agree bit for bit; frequencies never increase; evals of iteration 0 = record count."""
+    import msspe_b200 as m
+    from msspe_b200 import synth
+    g, k = synth.make_config("cfg3")
+    eng = m.Engine(k, 500, 250, 50)
+    eng.load_genomes(g.reshape(-1), synth.offsets_for(g))
+    eng.build_index()
+    G, maxp, s = eng.segment_info()
+    assert G == 10_000 * 43 and maxp == 42 and s == 36
+    a0, b0 = eng.select_both(1000, 2, 0)
+    ev0 = tuple(eng.timing().select_evals)
+    a1, b1 = eng.select_both(1000, 2, 1)
+    ev1 = tuple(eng.timing().select_evals)
+    a2 = eng.select(0, 1000, 2, 0x100)
+    assert a0.tobytes() == a1.tobytes() == a2.tobytes() and b0.tobytes() == b1.tobytes() and ev0 == ev1
+    assert len(a0) > 100 and np.all(np.diff(a0["freq"].astype(np.int64)) <= 0)
+    first = eng.select(0, 1, 2, 0)
+    assert len(first) == 1 and eng.timing().select_evals[0] == eng.index(0)[1][-1]
+    eng.close()
+
+
+def test_ragged_record_lengths_use_the_search_path(oracle_lib):
+    """Records of different lengths (different partition counts): the per-segment record lookup is a binary search."""
+    import msspe_b200 as m
+    rng = np.random.default_rng(21)
+    anc = rng.integers(0, 4, 2600)
+    lines = []
+    for i, L in enumerate([2600, 1800, 2600, 999, 1200, 2599, 500, 499, 2600]):
+        s = anc[:L].copy()
+        mut = rng.random(L) < 0.02
+        s[mut] = rng.integers(0, 4, int(mut.sum()))
+        lines.append(">x%d\n%s\n" % (i, "".join("ACGT"[x] for x in s)))
+    fa = "".join(lines).encode()
+    recs, (bases, offs) = _fasta_to_arrays(fa)
+    eng = m.Engine(13, 500, 250, 50)
+    eng.load_genomes(bases, offs)
+    eng.build_index()
+    for d in (0, 1):
+        want, part = oracle_lib.segment_slots(fa, 500, 250, 50, 13, d)
+        assert np.array_equal(eng.segment_kmers(d), want)
+    _check_select(eng, oracle_lib, fa, 500, 250, 50, 13, 60, 1, 0)
+    cov, part2, rec = eng.coverage([], [])
+    assert part2.tolist() == part.tolist() and rec.max() == 8
+    eng.close()
