@@ -55,20 +55,11 @@ count_kernel(const uint32_t* __restrict__ postings, const uint32_t* __restrict__
   __syncthreads();
   const uint32_t* mask = SMEM_MASK ? smask : ignored;
   uint32_t mymax = 0;
-  unsigned long long live_total = 0;
-  {
-    const uint32_t stride = gridDim.x * WARPS;
-    uint32_t wt = blockIdx.x * WARPS + warp;
-    TileLoad cur, nxt;
-    if (wt < n_tiles) tile_issue(cur, wt, postings, tile_first, n_post, lane);
-    while (wt < n_tiles) {
-      const uint32_t wn = wt + stride;
-      if (wn < n_tiles) tile_issue(nxt, wn, postings, tile_first, n_post, lane);
-      live_total += warp_count_tile<SMEM_MASK>(cur, wt, post_off, n_codes, n_post, mask, freq, acc, mymax, lane);
-      cur = nxt;
-      wt = wn;
-    }
-  }
+  CountJob J;
+  J.postings = postings; J.post_off = post_off; J.n_codes = n_codes; J.n_post = n_post; J.mask = mask; J.freq = freq; J.acc = acc;
+  count_job_range(J, n_tiles, blockIdx.x * WARPS + warp, gridDim.x * WARPS);
+  J.c_first = J.t_begin < J.t_end ? __ldg(tile_first + J.t_begin) : 0u;
+  const unsigned long long live_total = warp_count_range<SMEM_MASK>(J, mymax, lane);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
   if (lane == 0) { if (mymax) atomicMax(&s_max, mymax); if (live_total) atomicAdd(&ctl->evals, live_total); }
@@ -243,9 +234,21 @@ greedy_persistent_kernel(const GreedyArgs A) {
   const bool worker = solo || blockIdx.x > 0;
   const uint32_t wid = solo ? 0u : blockIdx.x - 1u, nworkers = solo ? 1u : gridDim.x - 1u;
   bool done[2] = {false, A.ndirs < 2};
-  bool have_win[2] = {false, false};
-  uint32_t win[2] = {0, 0}, n_out[2] = {0, 0}, gsave[2] = {0, 0};
-  unsigned long long evals[2] = {0, 0};
+  // block-uniform loop state lives in shared memory (every thread writes the same value before it reads it), so
+  // that the streaming loop of phase A has the registers to itself
+  __shared__ uint32_t s_win[2], s_gsave[2];
+  __shared__ unsigned long long s_evals[2];
+  if (tid == 0) { s_evals[0] = 0ull; s_evals[1] = 0ull; }
+  __syncthreads();
+  // first k-mer of every warp's tile range: the ranges are the same in every iteration
+  __shared__ uint32_t s_cfirst[2][WARPS];
+  if (worker && lane == 0)
+    for (int d = 0; d < A.ndirs; d++) {
+      CountJob J;
+      count_job_range(J, A.d[d].n_tiles, wid * WARPS + warp, nworkers * WARPS);
+      s_cfirst[d][warp] = J.t_begin < J.t_end ? __ldg(A.d[d].tile_first + J.t_begin) : 0u;
+    }
+  __syncwarp();
   const bool lead = blockIdx.x == 0 && tid == 0;
   const bool wlead = blockIdx.x == (gridDim.x > 1 ? 1 : 0) && tid == 0;  // a worker block's clock (diagnostic)
   // phase timers live in shared memory (only one thread touches them): no registers for diagnostics
@@ -262,8 +265,8 @@ greedy_persistent_kernel(const GreedyArgs A) {
       if (done[d]) continue;
       const GreedyDir& D = A.d[d];
       uint32_t* mask = SMEM_MASK ? smask + (size_t)d * A.mask_words : D.ignored;
-      if (have_win[d]) {  // main.rs:371-378 for the previous winner
-        const uint32_t a = D.post_off[win[d]], b = D.post_off[win[d] + 1];
+      if (it > 0) {  // main.rs:371-378 for the previous winner (a direction that is not done has pushed one per iteration)
+        const uint32_t a = D.post_off[s_win[d]], b = D.post_off[s_win[d] + 1];
         if (SMEM_MASK)
           for (uint32_t i = a + tid; i < b; i += THREADS) { const uint32_t sg = __ldg(D.postings + i); atomicOr(&mask[sg >> 5], 1u << (sg & 31u)); }
         if (blockIdx.x == 0) {
@@ -282,23 +285,14 @@ greedy_persistent_kernel(const GreedyArgs A) {
       }
       if (worker) {
         uint32_t mymax = 0;
-        unsigned long long live = 0;
-        {
-          const uint32_t stride = nworkers * WARPS;
-          uint32_t wt = wid * WARPS + warp;
-          TileLoad cur, nxt;
-          if (wt < D.n_tiles) tile_issue(cur, wt, D.postings, D.tile_first, D.n_post, lane);
-          while (wt < D.n_tiles) {  // the next tile's loads are in flight while this one is scored
-            const uint32_t wn = wt + stride;
-            if (wn < D.n_tiles) tile_issue(nxt, wn, D.postings, D.tile_first, D.n_post, lane);
-            live += warp_count_tile<SMEM_MASK>(cur, wt, D.post_off, D.n_codes, D.n_post, mask, D.freq, D.acc, mymax, lane);
-            cur = nxt;
-            wt = wn;
-          }
-        }
+        CountJob J;
+        J.postings = D.postings; J.post_off = D.post_off; J.n_codes = D.n_codes; J.n_post = D.n_post; J.mask = mask; J.freq = D.freq; J.acc = D.acc;
+        count_job_range(J, D.n_tiles, wid * WARPS + warp, nworkers * WARPS);
+        J.c_first = s_cfirst[d][warp];
+        const unsigned long long live = warp_count_range<SMEM_MASK>(J, mymax, lane);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
-        if (lane == 0) { if (mymax) atomicMax(&s_max[d], mymax); evals[d] += live; }
+        if (lane == 0) { if (mymax) atomicMax(&s_max[d], mymax); if (live) atomicAdd(&s_evals[d], live); }
       }
     }
     __syncthreads();
@@ -314,19 +308,45 @@ greedy_persistent_kernel(const GreedyArgs A) {
       if (done[d]) continue;
       const GreedyDir& D = A.d[d];
       const uint32_t g = __ldcg(&D.ctl->pg[par]);
-      gsave[d] = g;
+      s_gsave[d] = g;
       if (lead) { D.ctl->pg[par ^ 1] = 0; D.ctl->pt[par ^ 1] = 0; D.ctl->pk[par ^ 1] = 0ull; }  // next iteration's slots
       if (g <= 1u) {  // None or freq == 1: stop before the push (main.rs:353-366)
         done[d] = true;
-        if (lead) { D.ctl->iterations = it + 1; D.ctl->n_out = n_out[d]; D.ctl->done = 1; }
+        if (lead) { D.ctl->iterations = it + 1; D.ctl->n_out = it; D.ctl->done = 1; }
         continue;
       }
       const uint32_t* mask = SMEM_MASK ? smask + (size_t)d * A.mask_words : D.ignored;
-      for (uint32_t base = blockIdx.x * THREADS; base < D.n_codes; base += gridDim.x * THREADS) {
-        const uint32_t c = base + tid;
-        if (c < D.n_codes && __ldcg(D.freq + c) == g) s_tied[atomicAdd(&s_cnt, 1u)] = c;
-        __syncthreads();
-        const uint32_t nt = s_cnt;
+      // collect this block's k-mers at the maximum: grid-stride scan of freq[] with four independent loads in flight
+      {
+        const uint32_t stride = gridDim.x * THREADS;
+        uint32_t c = blockIdx.x * THREADS + tid;
+        for (; c + 3u * stride < D.n_codes; c += 4u * stride) {
+          const uint32_t f0 = __ldcg(D.freq + c), f1 = __ldcg(D.freq + c + stride), f2 = __ldcg(D.freq + c + 2u * stride), f3 = __ldcg(D.freq + c + 3u * stride);
+          if (f0 == g) { const uint32_t q = atomicAdd(&s_cnt, 1u); if (q < (uint32_t)THREADS) s_tied[q] = c; }
+          if (f1 == g) { const uint32_t q = atomicAdd(&s_cnt, 1u); if (q < (uint32_t)THREADS) s_tied[q] = c + stride; }
+          if (f2 == g) { const uint32_t q = atomicAdd(&s_cnt, 1u); if (q < (uint32_t)THREADS) s_tied[q] = c + 2u * stride; }
+          if (f3 == g) { const uint32_t q = atomicAdd(&s_cnt, 1u); if (q < (uint32_t)THREADS) s_tied[q] = c + 3u * stride; }
+        }
+        for (; c < D.n_codes; c += stride)
+          if (__ldcg(D.freq + c) == g) { const uint32_t q = atomicAdd(&s_cnt, 1u); if (q < (uint32_t)THREADS) s_tied[q] = c; }
+      }
+      __syncthreads();
+      const uint32_t n_here = s_cnt;
+      __syncthreads();
+      if (tid == 0) s_cnt = 0u;
+      // the usual case: the block's ties fit the list; otherwise (tie storms) re-collect them chunk by chunk
+      const uint32_t n_chunks = n_here <= (uint32_t)THREADS ? 1u : (D.n_codes + gridDim.x * THREADS - 1u) / (gridDim.x * THREADS);
+      for (uint32_t chunk = 0; chunk < n_chunks; chunk++) {
+        uint32_t nt = n_here;
+        if (n_here > (uint32_t)THREADS) {
+          __syncthreads();
+          const uint32_t c = (chunk * gridDim.x + blockIdx.x) * THREADS + tid;
+          if (c < D.n_codes && __ldcg(D.freq + c) == g) s_tied[atomicAdd(&s_cnt, 1u)] = c;
+          __syncthreads();
+          nt = s_cnt;
+          __syncthreads();
+          if (tid == 0) s_cnt = 0u;
+        }
         for (uint32_t t = 0; t < nt; t++) {
           const uint32_t cc = s_tied[t];
           float score;
@@ -343,9 +363,9 @@ greedy_persistent_kernel(const GreedyArgs A) {
           if (tid == 0) atomicMax(&D.ctl->pk[par], ((unsigned long long)__float_as_uint(score) << 32) | (unsigned long long)(0xFFFFFFFFu - cc));
           __syncthreads();
         }
-        if (tid == 0) { if (nt) atomicAdd(&D.ctl->pt[par], nt); s_cnt = 0u; }
-        __syncthreads();
       }
+      if (tid == 0 && n_here) atomicAdd(&D.ctl->pt[par], n_here);
+      __syncthreads();
     }
     if (wlead) { const unsigned long long t = globaltimer_ns(); s_tm[10] += t - s_tm[5]; s_tm[5] = t; }
     grid_barrier(A.barrier, bar_target);
@@ -358,23 +378,23 @@ greedy_persistent_kernel(const GreedyArgs A) {
       const GreedyDir& D = A.d[d];
       const unsigned long long key = __ldcg(&D.ctl->pk[par]);
       const uint32_t c = 0xFFFFFFFFu - (uint32_t)key;
-      win[d] = c; have_win[d] = true;
+      s_win[d] = c;
+      const uint32_t g = s_gsave[d];
       if (lead) {
         msspe_candidate w;
-        w.code = D.codes[c]; w.freq = gsave[d]; w.n_tied = __ldcg(&D.ctl->pt[par]); w.tie_score = __uint_as_float((uint32_t)(key >> 32)); w.reserved = 0;
-        D.out[n_out[d]] = w;
+        w.code = D.codes[c]; w.freq = g; w.n_tied = __ldcg(&D.ctl->pt[par]); w.tie_score = __uint_as_float((uint32_t)(key >> 32)); w.reserved = 0;
+        D.out[it] = w;  // a direction that is not done has pushed one winner per iteration
       }
-      n_out[d]++;
-      if (gsave[d] < A.mms || n_out[d] >= A.max_iter) {  // main.rs:387-390 and the loop bound :344
+      if (g < A.mms || it + 1u >= A.max_iter) {  // main.rs:387-390 and the loop bound :344
         done[d] = true;
-        if (lead) { D.ctl->iterations = it + 1; D.ctl->n_out = n_out[d]; D.ctl->done = 1; }
+        if (lead) { D.ctl->iterations = it + 1; D.ctl->n_out = it + 1u; D.ctl->done = 1; }
       }
       all_done = all_done && done[d];
     }
     if (all_done) break;
   }
   for (int d = 0; d < A.ndirs; d++) {
-    if (lane == 0 && evals[d]) atomicAdd(&A.d[d].ctl->evals, evals[d]);
+    if (tid == 0 && s_evals[d]) atomicAdd(&A.d[d].ctl->evals, s_evals[d]);
     if (lead) { A.d[d].ctl->t_count_ns = s_tm[3]; A.d[d].ctl->t_tie_ns = s_tm[4]; A.d[d].ctl->t_total_ns = globaltimer_ns() - s_tm[0]; }
     if (wlead) for (int q = 0; q < 4; q++) A.d[d].ctl->t_dbg[4 + q] = s_tm[8 + q];
   }

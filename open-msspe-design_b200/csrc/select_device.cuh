@@ -19,31 +19,12 @@ __device__ __forceinline__ uint32_t live_bit(const uint32_t* mask, uint32_t seg)
   return (~mask_word<SMEM_MASK>(mask, seg >> 5) >> (seg & 31u)) & 1u;
 }
 
-// Live postings before position pos (0..511) of the current warp tile, from the packed per-lane scan state.
-__device__ __forceinline__ uint32_t tile_prefix(uint32_t pos, uint32_t excl, uint32_t nibs, uint32_t b1, uint32_t b2, uint32_t b3) {
-  const uint32_t j = pos >> 7, l = (pos >> 2) & 31u, e = pos & 3u;
-  const uint32_t ex = __shfl_sync(0xffffffffu, excl, l), nb = __shfl_sync(0xffffffffu, nibs, l);
-  const uint32_t base = j == 0 ? 0u : (j == 1 ? b1 : (j == 2 ? b2 : b3));
-  return base + ((ex >> (8u * j)) & 0xFFu) + __popc((nb >> (4u * j)) & ((1u << e) - 1u));
-}
-
-// One WARP tile (512 postings = 2 KB) of the coverage scoring (main.rs:292-309), no block-level barrier:
-//   lane l loads four coalesced uint4 (block j = postings [128j, 128j+128) of the tile, lane l owns 4 of them),
-//   gathers the covered-segment bit of each posting, keeps 4 live nibbles; one packed shuffle scan gives the
-//   exclusive live-count of every (block, lane).  A k-mer's live count is prefix(next list start) - prefix(own
-//   list start): every lane evaluates the prefix at its own list start (two shuffles) and takes the upper bound
-//   from its neighbour lane.  Lists that cross a tile boundary are assembled by the last arriving tile through an
-//   arrival-counter|partial-sum word (acc[first tile of the list]).
-// Returns the live postings of the tile (uniform over the warp); mymax is per lane.
-// The global loads of one warp tile, issued one tile ahead of their use (register double buffering).
+// The global loads of one warp tile (512 postings = 2 KB), issued one tile ahead of their use.
 struct TileLoad {
   uint4 v[4];
-  uint32_t first;
 };
-__device__ __forceinline__ void tile_issue(TileLoad& L, uint32_t wt, const uint32_t* __restrict__ postings,
-                                           const uint32_t* __restrict__ tile_first, uint32_t n_post, int lane) {
+__device__ __forceinline__ void tile_issue(TileLoad& L, uint32_t wt, const uint32_t* __restrict__ postings, uint32_t n_post, int lane) {
   const uint32_t tile_start = wt * (uint32_t)CNT_TILE;
-  L.first = __ldg(tile_first + wt);
   if (tile_start + (uint32_t)CNT_TILE <= n_post) {
 #pragma unroll
     for (int j = 0; j < 4; j++) L.v[j] = __ldg(reinterpret_cast<const uint4*>(postings + tile_start + (uint32_t)(j * 32 + lane) * 4u));
@@ -59,35 +40,70 @@ __device__ __forceinline__ void tile_issue(TileLoad& L, uint32_t wt, const uint3
   }
 }
 
+// covered bit of segment `seg` pushed into the top of the history word h (h >> 1 | bit << 31)
 template <bool SMEM_MASK>
-__device__ __forceinline__ uint32_t warp_count_tile(const TileLoad& L, uint32_t wt,
-                                                    const uint32_t* __restrict__ post_off,
-                                                    uint32_t n_codes, uint32_t n_post, const uint32_t* mask, uint32_t* freq,
-                                                    unsigned long long* acc, uint32_t& mymax, int lane) {
-  const uint32_t tile_start = wt * (uint32_t)CNT_TILE;
-  const uint32_t tile_end = min(n_post, tile_start + (uint32_t)CNT_TILE);
-  const uint32_t first = L.first;
-  const bool partial = tile_start + (uint32_t)CNT_TILE > n_post;
-  uint32_t nibs = 0, cnts = 0;
+__device__ __forceinline__ uint32_t push_covered(uint32_t h, const uint32_t* mask, uint32_t seg) {
+  return __funnelshift_r(h, mask_word<SMEM_MASK>(mask, seg >> 5) >> (seg & 31u), 1);
+}
+
+// Everything one warp needs to know about its share of a recount (one direction).
+struct CountJob {
+  const uint32_t* postings; const uint32_t* post_off;
+  uint32_t n_codes, n_post;
+  uint32_t t_begin, t_end;   // this warp's contiguous tile range
+  uint32_t tiles_per_warp;   // T: every warp of the launch owns T consecutive tiles
+  uint32_t c_first;          // k-mer whose list contains the first posting of the range (tile_first[t_begin])
+  const uint32_t* mask; uint32_t* freq; unsigned long long* acc;
+};
+
+// The sliding window of list starts: lane l holds post_off[c0 + l] (and the next two windows, already in flight).
+struct ListWindow {
+  uint32_t c0, pa, pa1, pa2;
+};
+__device__ __forceinline__ uint32_t list_start(const CountJob& J, uint32_t c) { return c <= J.n_codes ? __ldg(J.post_off + c) : 0xFFFFFFFFu; }
+
+// One WARP tile of the coverage scoring (main.rs:292-309), no block-level barrier, uniform control flow.
+//   Tile position q = 128 j + 4 l + e is held by lane l (coalesced uint4 number j, element e).  Every lane has gathered
+//   the covered bit of its 16 postings from the bitmask (tile_gather: 16 bits, bit 4j+e) and one packed shuffle scan gives
+//   the exclusive live count of every (j, l).  Lane l < 31 of the window owns k-mer c0 + l: it evaluates the live
+//   prefix at the (tile-clamped) start of its list with two shuffles and takes the prefix at the end of the list
+//   from lane l+1 (lane 31 only supplies that bound, which is why the window advances by 31).  A warp owns a
+//   contiguous range of tiles, so a list cut by a tile boundary inside the range is carried in a register
+//   (`carry` = its live postings so far); only lists that leave the range go through an arrival-counter|partial-sum
+//   word (acc[first range of the list]) and are completed by the last range to arrive.
+// Returns the live postings of the tile (uniform over the warp); mymax is per lane.
+// covered bits of the 16 postings of this lane: bit 16 + 4 j + e  <->  tile position 128 j + 4 lane + e
+template <bool SMEM_MASK>
+__device__ __forceinline__ uint32_t tile_gather(const TileLoad& L, const uint32_t* mask) {
+  uint32_t h = 0;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    uint32_t nib = live_bit<SMEM_MASK>(mask, L.v[j].x) | (live_bit<SMEM_MASK>(mask, L.v[j].y) << 1) |
-                   (live_bit<SMEM_MASK>(mask, L.v[j].z) << 2) | (live_bit<SMEM_MASK>(mask, L.v[j].w) << 3);
-    if (partial) {
-      const uint32_t pos = tile_start + (uint32_t)(j * 32 + lane) * 4u;
-      const uint32_t valid = pos >= tile_end ? 0u : (tile_end - pos >= 4u ? 0xFu : (1u << (tile_end - pos)) - 1u);
-      nib &= valid;
-    }
-    nibs |= nib << (4 * j);
-    cnts |= (uint32_t)__popc(nib) << (8 * j);
+    h = push_covered<SMEM_MASK>(h, mask, L.v[j].x);
+    h = push_covered<SMEM_MASK>(h, mask, L.v[j].y);
+    h = push_covered<SMEM_MASK>(h, mask, L.v[j].z);
+    h = push_covered<SMEM_MASK>(h, mask, L.v[j].w);
   }
-  // list starts of the first 32*CB k-mers of the tile (CB per lane) + the one after them; in flight during the scan
-  constexpr int CB = 4;
-  uint32_t c0 = first + lane;
-  uint32_t pa[CB];
+  return h;
+}
+
+__device__ __forceinline__ uint32_t warp_count_tile(uint32_t h, uint32_t wt, const CountJob& J, ListWindow& W,
+                                                    uint32_t& carry, uint32_t& mymax, int lane) {
+  const uint32_t tile_start = wt * (uint32_t)CNT_TILE;
+  const uint32_t tile_len = min(J.n_post - tile_start, (uint32_t)CNT_TILE);
+  const uint32_t tile_end = tile_start + tile_len;
+  uint32_t nibs = ~h >> 16;  // live bit of tile position 128 j + 4 lane + e at bit 4 j + e
+  if (tile_len < (uint32_t)CNT_TILE) {  // the last tile: drop the slots past the end
+    uint32_t valid = 0;
 #pragma unroll
-  for (int r = 0; r < CB; r++) { const uint32_t c = c0 + 32u * r; pa[r] = c <= n_codes ? __ldg(post_off + c) : 0xFFFFFFFFu; }
-  uint32_t pnext = first + 32u * CB <= n_codes ? __ldg(post_off + first + 32u * CB) : 0xFFFFFFFFu;
+    for (int j = 0; j < 4; j++) {
+      const uint32_t q = (uint32_t)(j * 32 + lane) * 4u;
+      const uint32_t v = q >= tile_len ? 0u : (tile_len - q >= 4u ? 0xFu : (1u << (tile_len - q)) - 1u);
+      valid |= v << (4 * j);
+    }
+    nibs &= valid;
+  }
+  const uint32_t cnts = (uint32_t)__popc(nibs & 0xFu) | ((uint32_t)__popc(nibs & 0xF0u) << 8) |
+                        ((uint32_t)__popc(nibs & 0xF00u) << 16) | ((uint32_t)__popc(nibs & 0xF000u) << 24);
   // packed inclusive scan over lanes: field j (8 bits) = live count of block j up to this lane (<= 128)
   uint32_t inc = cnts;
 #pragma unroll
@@ -95,59 +111,83 @@ __device__ __forceinline__ uint32_t warp_count_tile(const TileLoad& L, uint32_t 
   const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
   const uint32_t excl = inc - cnts;
   const uint32_t b1 = tot & 0xFFu, b2 = b1 + ((tot >> 8) & 0xFFu), b3 = b2 + ((tot >> 16) & 0xFFu), live = b3 + (tot >> 24);
+  const uint32_t b01 = b1 << 16, b23 = b2 | (b3 << 16);  // live postings before block j as 16-bit fields (block 0: none)
+  const uint32_t range_lo = J.t_begin * (uint32_t)CNT_TILE;
+  const bool last_of_range = wt + 1u == J.t_end;
+  uint32_t outsum = 0;  // live postings so far of the list that continues into the next tile of the range
   for (;;) {
-    // prefix at every active list start of this batch
-    uint32_t plo[CB];
-    int nr = 0;
-#pragma unroll
-    for (int r = 0; r < CB; r++) {
-      if (r == nr && __any_sync(0xffffffffu, pa[r] < tile_end)) {
-        const uint32_t lo = pa[r] < tile_end ? max(pa[r], tile_start) - tile_start : 0u;
-        const uint32_t v = tile_prefix(lo, excl, nibs, b1, b2, b3);
-        plo[r] = pa[r] < tile_end ? v : live;
-        nr = r + 1;
-      } else {
-        plo[r] = live;
-      }
-    }
-    const bool more = nr == CB && pnext < tile_end;  // uniform: another batch of lists starts inside this tile
-    uint32_t pnext_pre = live;
-    if (more) pnext_pre = tile_prefix(pnext - tile_start, excl, nibs, b1, b2, b3);
-#pragma unroll
-    for (int r = 0; r < CB; r++) {
-      if (r >= nr) break;
-      // the next list's start and its prefix: neighbour lane, or lane 0 of the next round, or the batch successor
-      const uint32_t nxt_r = r + 1 < CB ? pa[r + 1 < CB ? r + 1 : r] : pnext;
-      const uint32_t nxt_p = r + 1 < CB ? plo[r + 1 < CB ? r + 1 : r] : pnext_pre;
-      uint32_t pb = __shfl_down_sync(0xffffffffu, pa[r], 1), phi = __shfl_down_sync(0xffffffffu, plo[r], 1);
-      const uint32_t pb31 = __shfl_sync(0xffffffffu, nxt_r, 0), phi31 = __shfl_sync(0xffffffffu, nxt_p, 0);
-      if (lane == 31) { pb = pb31; phi = phi31; }
-      if (pa[r] < tile_end) {
-        const uint32_t c = c0 + 32u * r;
-        const uint32_t sum = (pb < tile_end ? phi : live) - plo[r];
-        if (pa[r] >= tile_start && pb <= tile_end) {
-          freq[c] = sum;
+    // live postings of the tile before the start of this lane's list (list starts clamped into the tile), branch-free:
+    // position 512 (= end of a full tile) is looked up as element 4 of the last nibble of lane 31
+    const uint32_t lo = min(max(W.pa, tile_start), tile_end) - tile_start;  // 0 .. 512
+    const uint32_t lq = min(lo, (uint32_t)CNT_TILE - 1u);
+    const uint32_t j = lq >> 7, e = lo - (lq & ~3u);
+    const uint32_t ex = __shfl_sync(0xffffffffu, excl, lq >> 2), nb = __shfl_sync(0xffffffffu, nibs, lq >> 2);
+    const uint32_t base = __byte_perm(b01, b23, 0x10u + j * 0x22u);     // 16-bit field j, zero-extended (bytes 0,1 of b01 are 0)
+    const uint32_t exj = __byte_perm(ex, 0u, 0x4440u + j);               // byte j of the packed exclusive counts
+    const uint32_t plo = base + exj + (uint32_t)__popc((nb >> (4u * j)) & ((1u << e) - 1u));
+    const uint32_t pb = __shfl_down_sync(0xffffffffu, W.pa, 1), phi = __shfl_down_sync(0xffffffffu, plo, 1);
+    if (lane < 31 && W.pa < tile_end && pb > tile_start) {  // the list overlaps this tile
+      const uint32_t total = phi - plo + (W.pa < tile_start ? carry : 0u);
+      const bool ends_here = pb <= tile_end;
+      if (ends_here && W.pa >= range_lo) {  // the whole list lies inside this warp's range
+        J.freq[W.c0 + lane] = total;
+        mymax = max(mymax, total);
+      } else if (!ends_here && !last_of_range) {
+        outsum = total;
+      } else {  // the list leaves the range: the last arriving range owns the total
+        const uint32_t first_range = (W.pa / (uint32_t)CNT_TILE) / J.tiles_per_warp;
+        const uint32_t parts = ((pb - 1u) / (uint32_t)CNT_TILE) / J.tiles_per_warp - first_range + 1u;
+        const unsigned long long old = atomicAdd(&J.acc[first_range], (1ull << 32) | (unsigned long long)total);
+        if ((uint32_t)(old >> 32) + 1u == parts) {
+          const uint32_t sum = (uint32_t)old + total;
+          J.freq[W.c0 + lane] = sum;
+          J.acc[first_range] = 0ull;
           mymax = max(mymax, sum);
-        } else {  // list spans tiles: the last arriving tile owns the total
-          const uint32_t first_tile = pa[r] / (uint32_t)CNT_TILE;
-          const uint32_t parts = (pb - 1u) / (uint32_t)CNT_TILE - first_tile + 1u;
-          const unsigned long long old = atomicAdd(&acc[first_tile], (1ull << 32) | (unsigned long long)sum);
-          if ((uint32_t)(old >> 32) + 1u == parts) {
-            const uint32_t total = (uint32_t)old + sum;
-            freq[c] = total;
-            acc[first_tile] = 0ull;
-            mymax = max(mymax, total);
-          }
         }
       }
     }
-    if (!more) break;
-    c0 += 32u * CB;
-#pragma unroll
-    for (int r = 0; r < CB; r++) { const uint32_t c = c0 + 32u * r; pa[r] = c <= n_codes ? __ldg(post_off + c) : 0xFFFFFFFFu; }
-    pnext = c0 - lane + 32u * CB <= n_codes ? __ldg(post_off + (c0 - lane) + 32u * CB) : 0xFFFFFFFFu;
+    if (__shfl_sync(0xffffffffu, W.pa, 31) >= tile_end) break;  // uniform: no further list starts inside this tile
+    W.c0 += 31u;
+    W.pa = W.pa1; W.pa1 = W.pa2;
+    W.pa2 = list_start(J, W.c0 + 62u + (uint32_t)lane);
+  }
+  carry = __reduce_add_sync(0xffffffffu, outsum);
+  return live;
+}
+
+// This warp's share of one recount: its contiguous tile range.  One register buffer: as soon as the covered bits of
+// a tile have been gathered its registers take the loads of the next tile, which are in flight while the tile is
+// scored; the lines of the tile after that are requested into L2 (no register cost).
+template <bool SMEM_MASK>
+__device__ __forceinline__ unsigned long long warp_count_range(const CountJob& J, uint32_t& mymax, int lane) {
+  unsigned long long live = 0;
+  if (J.t_begin >= J.t_end) return live;
+  TileLoad A;
+  tile_issue(A, J.t_begin, J.postings, J.n_post, lane);
+  ListWindow W;
+  W.c0 = J.c_first;
+  W.pa = list_start(J, W.c0 + (uint32_t)lane);
+  W.pa1 = list_start(J, W.c0 + 31u + (uint32_t)lane);
+  W.pa2 = list_start(J, W.c0 + 62u + (uint32_t)lane);
+  uint32_t carry = 0;
+  for (uint32_t wt = J.t_begin; wt < J.t_end; wt++) {
+    const uint32_t h = tile_gather<SMEM_MASK>(A, J.mask);
+    if (wt + 1u < J.t_end) tile_issue(A, wt + 1u, J.postings, J.n_post, lane);
+    if (wt + 2u < J.t_end && lane < 16) {
+      const uint32_t q = (wt + 2u) * (uint32_t)CNT_TILE + (uint32_t)lane * 32u;
+      if (q < J.n_post) asm volatile("prefetch.global.L2 [%0];" ::"l"(J.postings + q));
+    }
+    live += warp_count_tile(h, wt, J, W, carry, mymax, lane);
   }
   return live;
+}
+
+// Tile range of warp `gw` out of `n_warps`: T = ceil(n_tiles / n_warps) consecutive tiles per warp.
+__device__ __forceinline__ void count_job_range(CountJob& J, uint32_t n_tiles, uint32_t gw, uint32_t n_warps) {
+  const uint32_t T = (n_tiles + n_warps - 1u) / n_warps;
+  J.tiles_per_warp = T ? T : 1u;
+  J.t_begin = min(n_tiles, gw * J.tiles_per_warp);
+  J.t_end = min(n_tiles, J.t_begin + J.tiles_per_warp);
 }
 
 // Warp-cooperative partition_tie_score (main.rs:261-283) of code c.  `seen` = this warp's partition bitmap.
