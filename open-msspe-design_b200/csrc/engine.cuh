@@ -40,6 +40,15 @@ struct DirIndex {
   uint32_t out_capacity = 0;
   uint32_t* tile_first = nullptr;   // [n_tiles] first code whose postings reach into each count tile
   uint32_t n_tiles = 0;
+  // scoring stream of the persistent greedy kernel (built on first use): the lists with >= 2 postings in code order,
+  // followed by the postings of the single-posting lists.  A k-mer with one posting can never be selected (freq == 1
+  // stops the loop before the push, main.rs:354-360), so its posting only has to be counted, not reduced per list.
+  bool stream_built = false;
+  uint32_t* s_postings = nullptr;   // [R]   lists region [0, s_list_post), tail [s_list_post, R)
+  uint32_t* s_off = nullptr;        // [s_lists + 1]
+  uint32_t* s_id = nullptr;         // [s_lists] code id of each stream list
+  uint32_t* s_tile_first = nullptr; // [s_tiles]
+  uint32_t s_lists = 0, s_list_post = 0, s_tiles = 0;
 };
 
 constexpr int MSSPE_CNT_THREADS = 512;  // threads per block of the K3 kernels
@@ -120,6 +129,7 @@ int msspe_exclusive_scan_u32(msspe_ctx* ctx, const uint32_t* in, uint32_t* out, 
 // ---- stages ----
 int msspe_free_index(msspe_ctx* ctx);
 int msspe_select_prepare_static(msspe_ctx* ctx, int dir, cudaStream_t st);  // select.cu: tile tables
+int msspe_select_prepare_stream(msspe_ctx* ctx, int dir, cudaStream_t st);  // select.cu: scoring stream (lazy)
 int msspe_thal_upload_tables(msspe_ctx* ctx);
 void msspe_thal_free_tables(msspe_ctx* ctx);
 

@@ -38,6 +38,42 @@ __global__ void tile_first_kernel(const uint32_t* __restrict__ post_off, uint32_
   tile_first[t] = lo;
 }
 
+// ---- scoring stream (see DirIndex): lists with >= 2 postings in code order, single-posting lists as a tail ----
+__global__ void stream_flag_kernel(const uint32_t* __restrict__ post_off, uint32_t n_codes, uint32_t* __restrict__ multi,
+                                   uint32_t* __restrict__ mlen) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_codes) return;
+  const uint32_t len = post_off[c + 1] - post_off[c];
+  multi[c] = len >= 2u ? 1u : 0u;
+  mlen[c] = len >= 2u ? len : 0u;
+}
+
+// One warp per 32 consecutive lists; short lists are copied by their lane, long ones by the whole warp.
+__global__ void __launch_bounds__(256)
+stream_copy_kernel(const uint32_t* __restrict__ post_off, const uint32_t* __restrict__ postings, uint32_t n_codes,
+                   const uint32_t* __restrict__ rank, const uint32_t* __restrict__ moff, uint32_t n_lists, uint32_t n_list_post,
+                   uint32_t tail_begin,
+                   uint32_t* __restrict__ s_postings, uint32_t* __restrict__ s_off, uint32_t* __restrict__ s_id) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t c = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u + (uint32_t)lane;
+  uint32_t a = 0, len = 0, dst = 0;
+  if (c < n_codes) {
+    a = post_off[c]; len = post_off[c + 1] - a;
+    const uint32_t r = rank[c];
+    if (len >= 2u) { dst = moff[c]; s_off[r] = dst; s_id[r] = c; }
+    else if (len == 1u) dst = tail_begin + (c - r);  // singles before c = c - (lists with >= 2 postings before c)
+    if (len <= 8u) for (uint32_t i = 0; i < len; i++) s_postings[dst + i] = postings[a + i];
+  }
+  if (c == 0) s_off[n_lists] = n_list_post;
+  unsigned big = __ballot_sync(0xffffffffu, len > 8u);
+  while (big) {
+    const int l = __ffs(big) - 1;
+    big &= big - 1;
+    const uint32_t la = __shfl_sync(0xffffffffu, a, l), ll = __shfl_sync(0xffffffffu, len, l), ld = __shfl_sync(0xffffffffu, dst, l);
+    for (uint32_t i = lane; i < ll; i += 32) s_postings[ld + i] = postings[la + i];
+  }
+}
+
 template <bool SMEM_MASK>
 __global__ void __launch_bounds__(CNT_THREADS)
 count_kernel(const uint32_t* __restrict__ postings, const uint32_t* __restrict__ post_off,
@@ -177,6 +213,8 @@ update_kernel(const uint64_t* __restrict__ codes, const uint32_t* __restrict__ p
 struct GreedyDir {
   const uint32_t* postings; const uint32_t* post_off; const uint32_t* tile_first; const uint64_t* codes;
   uint32_t n_codes, n_post, n_tiles, pad;
+  const uint32_t* list_id;       // code id of every list of the scoring stream
+  uint32_t tail_t0, tail_t1, tail_end, pad2;  // tiles / end of the single-posting tail of the stream
   uint32_t* ignored; uint32_t* freq; unsigned long long* acc; uint32_t* cov; SelectCtl* ctl; msspe_candidate* out;
 };
 struct GreedyArgs {
@@ -289,7 +327,19 @@ greedy_persistent_kernel(const GreedyArgs A) {
         J.postings = D.postings; J.post_off = D.post_off; J.n_codes = D.n_codes; J.n_post = D.n_post; J.mask = mask; J.freq = D.freq; J.acc = D.acc;
         count_job_range(J, D.n_tiles, wid * WARPS + warp, nworkers * WARPS);
         J.c_first = s_cfirst[d][warp];
-        const unsigned long long live = warp_count_range<SMEM_MASK>(J, mymax, lane);
+        unsigned long long live = warp_count_range<SMEM_MASK>(J, mymax, lane);
+        {  // single-posting lists: their live postings are counted (evals) but never reduced per list
+          uint32_t tl = 0;
+          for (uint32_t wt = D.tail_t0 + wid * WARPS + warp; wt < D.tail_t1; wt += nworkers * WARPS) {
+            TileLoad T;
+            tile_issue(T, wt, D.postings, D.tail_end, lane);
+            uint32_t nibs = ~tile_gather<SMEM_MASK>(T, mask) >> 16;
+            const uint32_t tile_len = min(D.tail_end - wt * (uint32_t)CNT_TILE, (uint32_t)CNT_TILE);
+            if (tile_len < (uint32_t)CNT_TILE) nibs &= tile_valid_bits(tile_len, lane);
+            tl += (uint32_t)__popc(nibs);
+          }
+          live += __reduce_add_sync(0xffffffffu, tl);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
         if (lane == 0) { if (mymax) atomicMax(&s_max[d], mymax); if (live) atomicAdd(&s_evals[d], live); }
@@ -382,7 +432,7 @@ greedy_persistent_kernel(const GreedyArgs A) {
       const uint32_t g = s_gsave[d];
       if (lead) {
         msspe_candidate w;
-        w.code = D.codes[c]; w.freq = g; w.n_tied = __ldcg(&D.ctl->pt[par]); w.tie_score = __uint_as_float((uint32_t)(key >> 32)); w.reserved = 0;
+        w.code = D.codes[D.list_id[c]]; w.freq = g; w.n_tied = __ldcg(&D.ctl->pt[par]); w.tie_score = __uint_as_float((uint32_t)(key >> 32)); w.reserved = 0;
         D.out[it] = w;  // a direction that is not done has pushed one winner per iteration
       }
       if (g < A.mms || it + 1u >= A.max_iter) {  // main.rs:387-390 and the loop bound :344
@@ -508,9 +558,13 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
     MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.cov, 0, 65536 * 4, st));
     MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.ctl, 0, sizeof(SelectCtl), st));
     MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.acc, 0, (uint64_t)(D.n_tiles + 1) * 8, st));
+    int rc = msspe_select_prepare_stream(c, dirs[i], st);
+    if (rc) return rc;
     GreedyDir& g = A.d[i];
-    g.postings = D.postings; g.post_off = D.post_off; g.tile_first = D.tile_first; g.codes = D.codes;
-    g.n_codes = (uint32_t)D.n_codes; g.n_post = (uint32_t)D.n_records; g.n_tiles = D.n_tiles;
+    g.postings = D.s_postings; g.post_off = D.s_off; g.tile_first = D.s_tile_first; g.codes = D.codes; g.list_id = D.s_id;
+    g.n_codes = D.s_lists; g.n_post = D.s_list_post; g.n_tiles = D.s_tiles;
+    g.tail_t0 = D.s_tiles; g.tail_end = D.s_tiles * (uint32_t)CNT_TILE + ((uint32_t)D.n_records - D.s_list_post);
+    g.tail_t1 = (uint32_t)div_up_u64(g.tail_end, CNT_TILE);
     g.ignored = D.ignored; g.freq = D.freq; g.acc = D.acc; g.cov = D.cov; g.ctl = D.ctl; g.out = D.out;
   }
   A.n_part = c->max_partition + 1u;
@@ -556,7 +610,7 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
     c->timing.select_ms[d] = ms;
     c->timing.select_evals[d] = c->h_ctl[i].evals;
     c->timing.select_iterations[d] = c->h_ctl[i].iterations;
-    c->timing.select_postings_read[d] = (uint64_t)c->h_ctl[i].iterations * c->dir[d].n_records;
+    c->timing.select_postings_read[d] = (uint64_t)c->h_ctl[i].iterations * c->dir[d].n_records;  // lists + single-posting tail
     c->timing.count_kernel_launches[d] = c->h_ctl[i].iterations;
     // phases of the two directions are interleaved inside one kernel: attribute the phase time once (to dir 0)
     c->timing.count_kernel_ms[d] = i == 0 ? (float)(c->h_ctl[i].t_count_ns * 1e-6) : 0.f;
@@ -664,6 +718,51 @@ int msspe_select_prepare_static(msspe_ctx* c, int dir, cudaStream_t st) {
     c->timing.kernel_launches++;
     MSSPE_CUDA_TRY(c, cudaGetLastError());
   }
+  return MSSPE_OK;
+}
+
+int msspe_select_prepare_stream(msspe_ctx* c, int dir, cudaStream_t st) {
+  DirIndex& D = c->dir[dir];
+  if (D.stream_built) return MSSPE_OK;
+  const uint32_t nc = (uint32_t)D.n_codes, R = (uint32_t)D.n_records;
+  uint32_t* multi = nullptr; uint32_t* mlen = nullptr; uint32_t* d_tot = nullptr;
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&multi, ((uint64_t)nc + 1) * 4, st));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&mlen, ((uint64_t)nc + 1) * 4, st));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&d_tot, 8, st));
+  uint32_t tot[2] = {0, 0};
+  if (nc) {
+    stream_flag_kernel<<<(nc + 255u) / 256u, 256, 0, st>>>(D.post_off, nc, multi, mlen);
+    c->timing.kernel_launches++;
+    int rc = msspe_exclusive_scan_u32(c, multi, multi, nc, d_tot, st);
+    if (rc) return rc;
+    rc = msspe_exclusive_scan_u32(c, mlen, mlen, nc, d_tot + 1, st);
+    if (rc) return rc;
+    MSSPE_CUDA_TRY(c, cudaMemcpyAsync(tot, d_tot, 8, cudaMemcpyDeviceToHost, st));
+    MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+  }
+  D.s_lists = tot[0]; D.s_list_post = tot[1];
+  D.s_tiles = (uint32_t)div_up_u64(D.s_list_post, CNT_TILE);
+  const uint32_t tail_begin = D.s_tiles * (uint32_t)CNT_TILE;  // the tail starts on a tile boundary
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.s_postings, ((uint64_t)R + CNT_TILE) * 4, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.s_off, ((uint64_t)D.s_lists + 1) * 4, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.s_id, ((uint64_t)D.s_lists + 1) * 4, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.s_tile_first, ((uint64_t)D.s_tiles + 1) * 4, c->stream));
+  if (nc) {
+    stream_copy_kernel<<<(unsigned)div_up_u64(nc, 256), 256, 0, st>>>(D.post_off, D.postings, nc, multi, mlen, D.s_lists, D.s_list_post,
+                                                                      tail_begin, D.s_postings, D.s_off, D.s_id);
+    c->timing.kernel_launches++;
+  } else {
+    MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.s_off, 0, 4, st));
+  }
+  if (D.s_tiles) {
+    tile_first_kernel<<<(D.s_tiles + 255) / 256, 256, 0, st>>>(D.s_off, D.s_lists, D.s_tiles, D.s_tile_first);
+    c->timing.kernel_launches++;
+  }
+  MSSPE_CUDA_TRY(c, cudaGetLastError());
+  MSSPE_CUDA_TRY(c, cudaFreeAsync(multi, st));
+  MSSPE_CUDA_TRY(c, cudaFreeAsync(mlen, st));
+  MSSPE_CUDA_TRY(c, cudaFreeAsync(d_tot, st));
+  D.stream_built = true;
   return MSSPE_OK;
 }
 

@@ -86,22 +86,25 @@ __device__ __forceinline__ uint32_t tile_gather(const TileLoad& L, const uint32_
   return h;
 }
 
+// bits of this lane's 16 tile positions (bit 4 j + e <-> position 128 j + 4 lane + e) that lie before tile_len
+__device__ __forceinline__ uint32_t tile_valid_bits(uint32_t tile_len, int lane) {
+  uint32_t valid = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const uint32_t q = (uint32_t)(j * 32 + lane) * 4u;
+    const uint32_t v = q >= tile_len ? 0u : (tile_len - q >= 4u ? 0xFu : (1u << (tile_len - q)) - 1u);
+    valid |= v << (4 * j);
+  }
+  return valid;
+}
+
 __device__ __forceinline__ uint32_t warp_count_tile(uint32_t h, uint32_t wt, const CountJob& J, ListWindow& W,
                                                     uint32_t& carry, uint32_t& mymax, int lane) {
   const uint32_t tile_start = wt * (uint32_t)CNT_TILE;
   const uint32_t tile_len = min(J.n_post - tile_start, (uint32_t)CNT_TILE);
   const uint32_t tile_end = tile_start + tile_len;
   uint32_t nibs = ~h >> 16;  // live bit of tile position 128 j + 4 lane + e at bit 4 j + e
-  if (tile_len < (uint32_t)CNT_TILE) {  // the last tile: drop the slots past the end
-    uint32_t valid = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const uint32_t q = (uint32_t)(j * 32 + lane) * 4u;
-      const uint32_t v = q >= tile_len ? 0u : (tile_len - q >= 4u ? 0xFu : (1u << (tile_len - q)) - 1u);
-      valid |= v << (4 * j);
-    }
-    nibs &= valid;
-  }
+  if (tile_len < (uint32_t)CNT_TILE) nibs &= tile_valid_bits(tile_len, lane);  // the last tile: drop the slots past the end
   const uint32_t cnts = (uint32_t)__popc(nibs & 0xFu) | ((uint32_t)__popc(nibs & 0xF0u) << 8) |
                         ((uint32_t)__popc(nibs & 0xF00u) << 16) | ((uint32_t)__popc(nibs & 0xF000u) << 24);
   // packed inclusive scan over lanes: field j (8 bits) = live count of block j up to this lane (<= 128)
