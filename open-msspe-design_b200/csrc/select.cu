@@ -94,6 +94,7 @@ count_kernel(const uint32_t* __restrict__ postings, const uint32_t* __restrict__
   CountJob J;
   J.postings = postings; J.post_off = post_off; J.n_codes = n_codes; J.n_post = n_post; J.mask = mask; J.freq = freq; J.acc = acc;
   count_job_range(J, n_tiles, blockIdx.x * WARPS + warp, gridDim.x * WARPS);
+  J.tail_end = n_post;
   J.c_first = J.t_begin < J.t_end ? __ldg(tile_first + J.t_begin) : 0u;
   const unsigned long long live_total = warp_count_range<SMEM_MASK>(J, mymax, lane);
 #pragma unroll
@@ -246,6 +247,17 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
+// The recount job of one warp for direction d (a literal at every call site).
+template <bool SMEM_MASK>
+__device__ __forceinline__ void make_job(CountJob& J, const GreedyArgs& A, const int d, uint32_t* smask, uint32_t gw, uint32_t nw, uint32_t c_first) {
+  const GreedyDir& D = A.d[d];
+  J.postings = D.postings; J.post_off = D.post_off; J.n_codes = D.n_codes; J.n_post = D.n_post;
+  J.mask = SMEM_MASK ? smask + (size_t)d * A.mask_words : D.ignored; J.freq = D.freq; J.acc = D.acc;
+  count_job_range(J, D.n_tiles, gw, nw);
+  count_job_tail(J, D.tail_t0, D.tail_t1, D.tail_end, gw, nw);
+  J.c_first = c_first;
+}
+
 template <bool SMEM_MASK, int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2)
 greedy_persistent_kernel(const GreedyArgs A) {
@@ -278,15 +290,9 @@ greedy_persistent_kernel(const GreedyArgs A) {
   __shared__ unsigned long long s_evals[2];
   if (tid == 0) { s_evals[0] = 0ull; s_evals[1] = 0ull; }
   __syncthreads();
-  // first k-mer of every warp's tile range: the ranges are the same in every iteration
-  __shared__ uint32_t s_cfirst[2][WARPS];
-  if (worker && lane == 0)
-    for (int d = 0; d < A.ndirs; d++) {
-      CountJob J;
-      count_job_range(J, A.d[d].n_tiles, wid * WARPS + warp, nworkers * WARPS);
-      s_cfirst[d][warp] = J.t_begin < J.t_end ? __ldg(A.d[d].tile_first + J.t_begin) : 0u;
-    }
-  __syncwarp();
+  // first k-mer of this warp's tile range; recomputed only when the set of running directions changes
+  __shared__ uint32_t s_cfirst[WARPS];
+  uint32_t cfirst_sig = 0xFFFFFFFFu;
   const bool lead = blockIdx.x == 0 && tid == 0;
   const bool wlead = blockIdx.x == (gridDim.x > 1 ? 1 : 0) && tid == 0;  // a worker block's clock (diagnostic)
   // phase timers live in shared memory (only one thread touches them): no registers for diagnostics
@@ -299,11 +305,42 @@ greedy_persistent_kernel(const GreedyArgs A) {
     if (lead) s_tm[1] = globaltimer_ns();
     if (wlead) s_tm[5] = globaltimer_ns();
     // ---------------- phase A ----------------
-    for (int d = 0; d < A.ndirs; d++) {
-      if (done[d]) continue;
-      const GreedyDir& D = A.d[d];
-      uint32_t* mask = SMEM_MASK ? smask + (size_t)d * A.mask_words : D.ignored;
-      if (it > 0) {  // main.rs:371-378 for the previous winner (a direction that is not done has pushed one per iteration)
+    // The worker warps are split between the running directions in proportion to their tiles; every warp owns one
+    // contiguous tile range of one direction and issues its first loads before the bitmask update below.
+    RangeState S;
+    int myd = 0;
+    uint32_t my_gw = 0, my_nw = 1;
+    if (worker) {
+      const uint32_t W = nworkers * WARPS;
+      my_gw = wid * WARPS + warp; my_nw = W;
+      const uint32_t sig = (done[0] ? 0u : 1u) | (done[1] ? 0u : 2u);
+      if (sig == 3u) {
+        const uint32_t t0 = A.d[0].tail_t1, t1 = A.d[1].tail_t1;
+        uint32_t W0 = (uint32_t)(((unsigned long long)W * t0 + (t0 + t1) / 2u) / (unsigned long long)max(t0 + t1, 1u));
+        W0 = min(max(W0, 1u), W - 1u);
+        if (my_gw < W0) { my_nw = W0; } else { myd = 1; my_gw -= W0; my_nw = W - W0; }
+      } else {
+        myd = done[0] ? 1 : 0;
+      }
+      if (sig != cfirst_sig) {
+        cfirst_sig = sig;
+        if (lane == 0) {
+          CountJob J;
+          count_job_range(J, A.d[myd].n_tiles, my_gw, my_nw);
+          s_cfirst[warp] = J.t_begin < J.t_end ? __ldg(A.d[myd].tile_first + J.t_begin) : 0u;
+        }
+        __syncwarp();
+      }
+      // the two branches are the same code with the direction as a literal: the job's pointers then stay in the
+      // kernel-parameter constant bank instead of occupying registers across the streaming loop
+      if (myd == 0) { CountJob J; make_job<SMEM_MASK>(J, A, 0, smask, my_gw, my_nw, s_cfirst[warp]); warp_count_begin(J, S, lane); }
+      else          { CountJob J; make_job<SMEM_MASK>(J, A, 1, smask, my_gw, my_nw, s_cfirst[warp]); warp_count_begin(J, S, lane); }
+    }
+    if (it > 0) {  // main.rs:371-378 for the previous winners (a direction that is not done has pushed one per iteration)
+      for (int d = 0; d < A.ndirs; d++) {
+        if (done[d]) continue;
+        const GreedyDir& D = A.d[d];
+        uint32_t* mask = SMEM_MASK ? smask + (size_t)d * A.mask_words : D.ignored;
         const uint32_t a = D.post_off[s_win[d]], b = D.post_off[s_win[d] + 1];
         if (SMEM_MASK)
           for (uint32_t i = a + tid; i < b; i += THREADS) { const uint32_t sg = __ldg(D.postings + i); atomicOr(&mask[sg >> 5], 1u << (sg & 31u)); }
@@ -318,32 +355,19 @@ greedy_persistent_kernel(const GreedyArgs A) {
           }
           __syncthreads();
           for (uint32_t i = a + tid; i < b; i += THREADS) pm[A.seg_part[__ldg(D.postings + i)] >> 5] = 0u;
+          __syncthreads();
         }
-        __syncthreads();
       }
-      if (worker) {
-        uint32_t mymax = 0;
-        CountJob J;
-        J.postings = D.postings; J.post_off = D.post_off; J.n_codes = D.n_codes; J.n_post = D.n_post; J.mask = mask; J.freq = D.freq; J.acc = D.acc;
-        count_job_range(J, D.n_tiles, wid * WARPS + warp, nworkers * WARPS);
-        J.c_first = s_cfirst[d][warp];
-        unsigned long long live = warp_count_range<SMEM_MASK>(J, mymax, lane);
-        {  // single-posting lists: their live postings are counted (evals) but never reduced per list
-          uint32_t tl = 0;
-          for (uint32_t wt = D.tail_t0 + wid * WARPS + warp; wt < D.tail_t1; wt += nworkers * WARPS) {
-            TileLoad T;
-            tile_issue(T, wt, D.postings, D.tail_end, lane);
-            uint32_t nibs = ~tile_gather<SMEM_MASK>(T, mask) >> 16;
-            const uint32_t tile_len = min(D.tail_end - wt * (uint32_t)CNT_TILE, (uint32_t)CNT_TILE);
-            if (tile_len < (uint32_t)CNT_TILE) nibs &= tile_valid_bits(tile_len, lane);
-            tl += (uint32_t)__popc(nibs);
-          }
-          live += __reduce_add_sync(0xffffffffu, tl);
-        }
+      __syncthreads();
+    }
+    if (worker) {
+      uint32_t mymax = 0;
+      unsigned long long live;
+      if (myd == 0) { CountJob J; make_job<SMEM_MASK>(J, A, 0, smask, my_gw, my_nw, s_cfirst[warp]); live = warp_count_run<SMEM_MASK>(J, S, mymax, lane); }
+      else          { CountJob J; make_job<SMEM_MASK>(J, A, 1, smask, my_gw, my_nw, s_cfirst[warp]); live = warp_count_run<SMEM_MASK>(J, S, mymax, lane); }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
-        if (lane == 0) { if (mymax) atomicMax(&s_max[d], mymax); if (live) atomicAdd(&s_evals[d], live); }
-      }
+      for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
+      if (lane == 0) { if (mymax) atomicMax(&s_max[myd], mymax); if (live) atomicAdd(&s_evals[myd], live); }
     }
     __syncthreads();
     if (tid == 0 && worker)

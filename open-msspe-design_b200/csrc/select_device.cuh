@@ -51,6 +51,9 @@ struct CountJob {
   const uint32_t* postings; const uint32_t* post_off;
   uint32_t n_codes, n_post;
   uint32_t t_begin, t_end;   // this warp's contiguous tile range
+  uint32_t list_tiles;       // tiles [0, list_tiles) hold lists; tiles from list_tiles on hold the counted-only tail
+  uint32_t tail_end;         // end of the tail (postings); = n_post when there is no tail
+  uint32_t q_begin, q_end;   // this warp's tail tiles (processed after its list tiles)
   uint32_t tiles_per_warp;   // T: every warp of the launch owns T consecutive tiles
   uint32_t c_first;          // k-mer whose list contains the first posting of the range (tile_first[t_begin])
   const uint32_t* mask; uint32_t* freq; unsigned long long* acc;
@@ -160,29 +163,66 @@ __device__ __forceinline__ uint32_t warp_count_tile(uint32_t h, uint32_t wt, con
 
 // This warp's share of one recount: its contiguous tile range.  One register buffer: as soon as the covered bits of
 // a tile have been gathered its registers take the loads of the next tile, which are in flight while the tile is
-// scored; the lines of the tile after that are requested into L2 (no register cost).
+// scored; the lines of the tile after that are requested into L2 (no register cost).  Tiles past the lists hold the
+// counted-only tail (single-posting lists of the scoring stream): gather and popcount, no per-list reduction.
+struct RangeState {
+  TileLoad A;
+  ListWindow W;
+};
+__device__ __forceinline__ uint32_t tile_bound(const CountJob& J, uint32_t wt) { return wt < J.list_tiles ? J.n_post : J.tail_end; }
+// i-th tile of this warp: its list tiles first, then its tail tiles
+__device__ __forceinline__ uint32_t my_tile(const CountJob& J, uint32_t i) {
+  const uint32_t nl = J.t_end - J.t_begin;
+  return i < nl ? J.t_begin + i : J.q_begin + (i - nl);
+}
+
+// the first loads of the range (postings of the first tile, three windows of list starts): nothing here depends on
+// the bitmask, so the caller can issue them before the mask update of the iteration
+__device__ __forceinline__ void warp_count_begin(const CountJob& J, RangeState& S, int lane) {
+  const uint32_t n_mine = (J.t_end - J.t_begin) + (J.q_end - J.q_begin);
+  if (n_mine == 0) return;
+  const uint32_t w0 = my_tile(J, 0);
+  tile_issue(S.A, w0, J.postings, tile_bound(J, w0), lane);
+  if (J.t_begin < J.t_end) {
+    S.W.c0 = J.c_first;
+    S.W.pa = list_start(J, S.W.c0 + (uint32_t)lane);
+    S.W.pa1 = list_start(J, S.W.c0 + 31u + (uint32_t)lane);
+    S.W.pa2 = list_start(J, S.W.c0 + 62u + (uint32_t)lane);
+  }
+}
+
+template <bool SMEM_MASK>
+__device__ __forceinline__ unsigned long long warp_count_run(const CountJob& J, RangeState& S, uint32_t& mymax, int lane) {
+  unsigned long long live = 0;
+  uint32_t carry = 0, tail_live = 0;
+  const uint32_t n_mine = (J.t_end - J.t_begin) + (J.q_end - J.q_begin);
+  for (uint32_t i = 0; i < n_mine; i++) {
+    const uint32_t wt = my_tile(J, i);
+    const uint32_t h = tile_gather<SMEM_MASK>(S.A, J.mask);
+    if (i + 1u < n_mine) { const uint32_t w1 = my_tile(J, i + 1u); tile_issue(S.A, w1, J.postings, tile_bound(J, w1), lane); }
+    if (i + 2u < n_mine && lane < 16) {
+      const uint32_t w2 = my_tile(J, i + 2u);
+      const uint32_t q = w2 * (uint32_t)CNT_TILE + (uint32_t)lane * 32u;
+      if (q < tile_bound(J, w2)) asm volatile("prefetch.global.L2 [%0];" ::"l"(J.postings + q));
+    }
+    if (wt < J.list_tiles) {
+      live += warp_count_tile(h, wt, J, S.W, carry, mymax, lane);
+    } else {
+      uint32_t nibs = ~h >> 16;
+      const uint32_t tile_len = min(J.tail_end - wt * (uint32_t)CNT_TILE, (uint32_t)CNT_TILE);
+      if (tile_len < (uint32_t)CNT_TILE) nibs &= tile_valid_bits(tile_len, lane);
+      tail_live += (uint32_t)__popc(nibs);
+    }
+  }
+  if (J.q_end > J.q_begin) live += __reduce_add_sync(0xffffffffu, tail_live);
+  return live;
+}
+
 template <bool SMEM_MASK>
 __device__ __forceinline__ unsigned long long warp_count_range(const CountJob& J, uint32_t& mymax, int lane) {
-  unsigned long long live = 0;
-  if (J.t_begin >= J.t_end) return live;
-  TileLoad A;
-  tile_issue(A, J.t_begin, J.postings, J.n_post, lane);
-  ListWindow W;
-  W.c0 = J.c_first;
-  W.pa = list_start(J, W.c0 + (uint32_t)lane);
-  W.pa1 = list_start(J, W.c0 + 31u + (uint32_t)lane);
-  W.pa2 = list_start(J, W.c0 + 62u + (uint32_t)lane);
-  uint32_t carry = 0;
-  for (uint32_t wt = J.t_begin; wt < J.t_end; wt++) {
-    const uint32_t h = tile_gather<SMEM_MASK>(A, J.mask);
-    if (wt + 1u < J.t_end) tile_issue(A, wt + 1u, J.postings, J.n_post, lane);
-    if (wt + 2u < J.t_end && lane < 16) {
-      const uint32_t q = (wt + 2u) * (uint32_t)CNT_TILE + (uint32_t)lane * 32u;
-      if (q < J.n_post) asm volatile("prefetch.global.L2 [%0];" ::"l"(J.postings + q));
-    }
-    live += warp_count_tile(h, wt, J, W, carry, mymax, lane);
-  }
-  return live;
+  RangeState S;
+  warp_count_begin(J, S, lane);
+  return warp_count_run<SMEM_MASK>(J, S, mymax, lane);
 }
 
 // Tile range of warp `gw` out of `n_warps`: T = ceil(n_tiles / n_warps) consecutive tiles per warp.
@@ -191,6 +231,15 @@ __device__ __forceinline__ void count_job_range(CountJob& J, uint32_t n_tiles, u
   J.tiles_per_warp = T ? T : 1u;
   J.t_begin = min(n_tiles, gw * J.tiles_per_warp);
   J.t_end = min(n_tiles, J.t_begin + J.tiles_per_warp);
+  J.list_tiles = n_tiles; J.q_begin = J.q_end = 0u;  // no tail unless count_job_tail says otherwise
+}
+// Tail tiles [tail_t0, tail_t1) spread evenly over the warps, the last warps first (the first warps may carry one
+// list tile more than the last ones).
+__device__ __forceinline__ void count_job_tail(CountJob& J, uint32_t tail_t0, uint32_t tail_t1, uint32_t tail_end, uint32_t gw, uint32_t n_warps) {
+  const uint32_t n = tail_t1 - tail_t0, T = (n + n_warps - 1u) / n_warps, r = n_warps - 1u - gw;
+  J.tail_end = tail_end;
+  J.q_begin = min(tail_t1, tail_t0 + r * T);
+  J.q_end = min(tail_t1, J.q_begin + T);
 }
 
 // Warp-cooperative partition_tie_score (main.rs:261-283) of code c.  `seen` = this warp's partition bitmap.
