@@ -177,6 +177,24 @@ int msspe_coverage(msspe_ctx* ctx, const uint64_t* fwd_codes, uint32_t n_fwd, co
                    uint32_t n_rev, uint8_t* covered, uint16_t* partition_no, uint32_t* record_of_segment,
                    uint64_t capacity);
 
+/* print_coverage_report's aggregation (main.rs:518-574) as device reductions, so that a 12-million-segment job copies
+ * back O(records + partitions) instead of O(segments): rec_covered/rec_total[r] = covered / all segments of record r
+ * (SequenceRecord order of msspe_load_genomes), part_covered/part_total[p] likewise per Segment.partition_no,
+ * *n_covered = covered segments.  Capacities: n_records >= loaded records, n_part > max_partition. */
+int msspe_coverage_summary(msspe_ctx* ctx, const uint64_t* fwd_codes, uint32_t n_fwd, const uint64_t* rev_codes,
+                           uint32_t n_rev, uint32_t* rec_covered, uint32_t* rec_total, uint32_t n_records,
+                           uint32_t* part_covered, uint32_t* part_total, uint32_t n_part, uint64_t* n_covered);
+
+/* ---- conflict graph + greedy vertex cover ----------------------------------------------------------------------
+ * Replaces main.rs:754-798 (and graphdb.rs as its container).  codes[n] = the DISTINCT primer words (the reference
+ * keys its graph by word: a word selected in both directions is one node), edges (edge_a[e], edge_b[e]) = node
+ * indices of every conflict edge, i.e. every stored edge with dG below the threshold (a == b allowed: self
+ * conflict).  deleted[v] = 1 for the primers the loop removes: repeatedly the live primer with the most live
+ * neighbours, ties -> lexicographically greatest word.  Device: n x n adjacency bit matrix, popcount degrees, one
+ * persistent kernel for the whole loop.  n <= 65536. */
+int msspe_vertex_cover(msspe_ctx* ctx, const uint64_t* codes, uint32_t n, const uint32_t* edge_a, const uint32_t* edge_b,
+                       uint64_t n_edges, uint8_t* deleted, uint32_t* n_deleted);
+
 /* ---- (e) genome-sharded selection: per-rank primitives ----------------------------------------------------
  * One process per GPU holds a contiguous block of the records (hence of the global segment order).  The loop of
  * main.rs:331-406 is then driven above the ABI (msspe_b200/distributed.py): local recount -> all-reduce(sum) of the

@@ -606,7 +606,7 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
   void* fn = smem_mask ? (void*)greedy_persistent_kernel<true, 512> : (void*)greedy_persistent_kernel<false, 512>;
   MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&per_sm, fn, 512, smem, cudaOccupancyDefault));
-  if (per_sm < 2) {
+  if (per_sm < 2 || getenv("MSSPE_PERSIST_1024")) {
     fn = smem_mask ? (void*)greedy_persistent_kernel<true, 1024> : (void*)greedy_persistent_kernel<false, 1024>;
     threads = 1024;
     MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -313,7 +313,16 @@ int main(int argc, char** argv) {
     // parse_ntthal_output (delta_g.rs:27-59): input line t reads output line 5t.  Block u starts at line
     // 5u - 4*m(u), m(u) = structure-less pairs before u (they print ONE line).  So line 0 of block u is read iff
     // m(u) % 5 == 0, and then by input line t = u - 4*m(u)/5, whose primers get the edge.
-    std::map<std::string, std::set<std::string>> conflicts;
+    // conflict edges (main.rs:755-771) over the DISTINCT words (the reference keys its graph by word)
+    std::unordered_map<std::string, uint32_t> node_of;
+    std::vector<uint64_t> node_code; std::vector<const std::string*> node_word;
+    std::vector<uint32_t> node_of_primer(n);
+    for (uint32_t i = 0; i < n; i++) {
+      auto ins = node_of.emplace(primers[i]->word, (uint32_t)node_code.size());
+      if (ins.second) { node_code.push_back(primers[i]->code); node_word.push_back(&primers[i]->word); }
+      node_of_primer[i] = ins.first->second;
+    }
+    std::vector<uint32_t> ea, eb;
     std::set<std::string> edge_ids;
     uint64_t m = 0;
     for (uint64_t u = 0; u < lines.size(); u++) {
@@ -329,19 +338,13 @@ int main(int argc, char** argv) {
       const std::string& wa = primers[pt / n]->word; const std::string& wb = primers[pt % n]->word;
       if (!edge_ids.insert(wa + ":" + wb).second) continue;           // HashSet<Edge> keyed by id: first insert stays
       const float stored = strtof(fmt2(dg).c_str(), nullptr);         // attrs "dg" = format!("{:.2}", dg); get_dg() re-parses
-      if (stored < a.delta_g_threshold) { conflicts[wa].insert(wb); conflicts[wb].insert(wa); }   // main.rs:755-771
+      if (stored < a.delta_g_threshold) { ea.push_back(node_of_primer[pt / n]); eb.push_back(node_of_primer[pt % n]); }
     }
-    for (;;) {  // greedy vertex cover, main.rs:776-798: most active conflicts, ties -> lexicographically greatest
-      bool have = false; std::string worst; size_t wc = 0;
-      for (auto& kv : conflicts) {
-        if (deleted.count(kv.first)) continue;
-        size_t active = 0; for (auto& nb : kv.second) if (!deleted.count(nb)) active++;
-        if (active == 0) continue;
-        if (!have || active > wc || (active == wc && kv.first > worst)) { have = true; worst = kv.first; wc = active; }
-      }
-      if (!have) break;
-      deleted.insert(worst);
-    }
+    // greedy vertex cover on the device (main.rs:776-798: most active conflicts, ties -> lexicographically greatest)
+    std::vector<uint8_t> del(node_code.size(), 0);
+    uint32_t n_del = 0;
+    CHECK(msspe_vertex_cover(ctx, node_code.data(), (uint32_t)node_code.size(), ea.data(), eb.data(), ea.size(), del.data(), &n_del));
+    for (size_t v = 0; v < del.size(); v++) if (del[v]) deleted.insert(*node_word[v]);
   }
   std::vector<KmerStat> final_dir[2];
   for (int d = 0; d < 2; d++) {
@@ -354,15 +357,16 @@ int main(int argc, char** argv) {
     std::vector<uint64_t> fc, rc;
     for (auto& p : final_dir[0]) fc.push_back(p.code);
     for (auto& p : final_dir[1]) rc.push_back(p.code);
-    std::vector<uint8_t> covered(G); std::vector<uint16_t> part(G); std::vector<uint32_t> rec(G);
-    CHECK(msspe_coverage(ctx, fc.data(), (uint32_t)fc.size(), rc.data(), (uint32_t)rc.size(), covered.data(), part.data(), rec.data(), G));
-    size_t ncov = 0;
+    // per-record / per-partition (covered, total) reduced on the device: O(records + partitions) comes back
+    const uint32_t nrec = (uint32_t)records.size(), npart = maxp + 1;
+    std::vector<uint32_t> rcv(nrec), rtot(nrec), pcv(npart), ptot(npart);
+    uint64_t ncov64 = 0;
+    CHECK(msspe_coverage_summary(ctx, fc.data(), (uint32_t)fc.size(), rc.data(), (uint32_t)rc.size(), rcv.data(), rtot.data(), nrec,
+                                 pcv.data(), ptot.data(), npart, &ncov64));
+    const size_t ncov = (size_t)ncov64;
     std::unordered_map<std::string, std::pair<size_t, size_t>> seq; std::map<uint16_t, std::pair<size_t, size_t>> ps;
-    for (uint64_t g = 0; g < G; g++) {
-      auto& se = seq[records[rec[g]].name]; se.second++;
-      auto& pe = ps[part[g]]; pe.second++;
-      if (covered[g]) { se.first++; pe.first++; ncov++; }
-    }
+    for (uint32_t r = 0; r < nrec; r++) if (rtot[r]) { auto& se = seq[records[r].name]; se.first += rcv[r]; se.second += rtot[r]; }
+    for (uint32_t q = 0; q < npart; q++) if (ptot[q]) { auto& pe = ps[(uint16_t)q]; pe.first += pcv[q]; pe.second += ptot[q]; }
     float mn = INFINITY, mx = -INFINITY; size_t well = 0;
     for (auto& kv : seq) { const float c = (float)kv.second.first / (float)kv.second.second * 100.0f; mn = std::fmin(mn, c); mx = std::fmax(mx, c); if (c >= 80.0f) well++; }
     printf("\nCoverage report:\n");

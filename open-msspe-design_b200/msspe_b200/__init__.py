@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "msspe_build_index", "msspe_segment_info", "msspe_get_segment_kmers", "msspe_get_index", "msspe_select",
     "msspe_select_both", "msspe_coverage", "msspe_thal_params_default", "msspe_thal_params_from_dir",
     "msspe_set_thal_params", "msspe_primer_thermo", "msspe_thal_pairs", "msspe_cross_dimer",
-    "msspe_kmer_stats", "msspe_shard_begin", "msspe_shard_buffers", "msspe_shard_count", "msspe_shard_firstpos", "msspe_shard_apply",
+    "msspe_kmer_stats", "msspe_coverage_summary", "msspe_vertex_cover", "msspe_shard_begin", "msspe_shard_buffers", "msspe_shard_count", "msspe_shard_firstpos", "msspe_shard_apply",
 ]
 
 
@@ -125,6 +125,10 @@ def load_library():
     L.msspe_select.argtypes = [C.c_void_p, C.c_uint8, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
     L.msspe_select_both.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32),
                                     C.c_void_p, C.POINTER(C.c_uint32)]
+    L.msspe_coverage_summary.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                         C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]
+    L.msspe_vertex_cover.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                     C.POINTER(C.c_uint32)]
     L.msspe_coverage.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_uint64]
     L.msspe_thal_params_default.argtypes = [C.c_void_p]
@@ -261,6 +265,33 @@ class Engine:
         self._check(self.L.msspe_coverage(self.h, f.ctypes.data, len(f), r.ctypes.data, len(r), cov.ctypes.data,
                                           part.ctypes.data, rec.ctypes.data, g))
         return cov[:g], part[:g], rec[:g]
+
+    def coverage_summary(self, fwd_codes, rev_codes, n_records: int):
+        """print_coverage_report's aggregation (main.rs:518-574) reduced on the device: per-record and per-partition
+        (covered, total) segment counts and the number of covered segments."""
+        _, maxp, _ = self.segment_info()
+        f = np.ascontiguousarray(fwd_codes, dtype=np.uint64)
+        r = np.ascontiguousarray(rev_codes, dtype=np.uint64)
+        npart = int(maxp) + 1
+        rc = np.zeros(max(1, n_records), dtype=np.uint32); rt = np.zeros(max(1, n_records), dtype=np.uint32)
+        pc = np.zeros(npart, dtype=np.uint32); pt = np.zeros(npart, dtype=np.uint32)
+        ncov = C.c_uint64(0)
+        self._check(self.L.msspe_coverage_summary(self.h, f.ctypes.data, len(f), r.ctypes.data, len(r), rc.ctypes.data,
+                                                  rt.ctypes.data, n_records, pc.ctypes.data, pt.ctypes.data, npart, C.byref(ncov)))
+        return rc[:n_records], rt[:n_records], pc, pt, int(ncov.value)
+
+    def vertex_cover(self, codes, edge_a, edge_b) -> np.ndarray:
+        """main.rs:754-798 on the device: codes = distinct primer words, (edge_a[e], edge_b[e]) = conflict edges as
+        node indices; returns deleted[n] (uint8)."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint64)
+        ea = np.ascontiguousarray(edge_a, dtype=np.uint32); eb = np.ascontiguousarray(edge_b, dtype=np.uint32)
+        assert len(ea) == len(eb)
+        deleted = np.zeros(max(1, len(codes)), dtype=np.uint8)
+        nd = C.c_uint32(0)
+        self._check(self.L.msspe_vertex_cover(self.h, codes.ctypes.data, len(codes), ea.ctypes.data, eb.ctypes.data, len(ea),
+                                              deleted.ctypes.data, C.byref(nd)))
+        assert int(deleted[:len(codes)].sum()) == nd.value
+        return deleted[:len(codes)]
 
     # -- check_primers (primer.rs:143-166) --
     def primer_thermo(self, codes, oligo_len=None):

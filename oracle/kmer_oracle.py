@@ -256,3 +256,25 @@ def rust_fmt(x: float, prec: int) -> str:
     if d == 0 and math.copysign(1.0, x) < 0:
         s = "-" + s.lstrip("-")
     return s
+
+
+def greedy_vertex_cover(words: list[str], edges: list[tuple[str, str]]) -> set[str]:
+    """main.rs:754-798: conflicts[a] += b, conflicts[b] += a for every conflict edge (a == b is a self conflict);
+    then repeatedly delete the not-yet-deleted primer with the most not-yet-deleted neighbours (count > 0), ties ->
+    lexicographically greatest word (`c1.cmp(c2).then(p1.cmp(p2))` under max_by)."""
+    conflicts: dict[str, set[str]] = {}
+    for a, b in edges:
+        conflicts.setdefault(a, set()).add(b)
+        conflicts.setdefault(b, set()).add(a)
+    deleted: set[str] = set()
+    while True:
+        worst = None
+        for p, nbs in conflicts.items():
+            if p in deleted:
+                continue
+            active = sum(1 for n in nbs if n not in deleted)
+            if active > 0 and (worst is None or (active, p) > worst):
+                worst = (active, p)
+        if worst is None:
+            return deleted
+        deleted.add(worst[1])
