@@ -152,6 +152,19 @@ int msspe_set_profiling(msspe_ctx* ctx, int on); /* per-kernel event timing of t
 int msspe_load_genomes(msspe_ctx* ctx, const uint8_t* bases, const uint64_t* offsets, uint32_t n_records);
 /* Same, but `d_bases` is already resident in device memory on ctx's device (offsets stay host). */
 int msspe_load_genomes_device(msspe_ctx* ctx, const uint8_t* d_bases, const uint64_t* offsets, uint32_t n_records);
+/* FASTA ingest.  Replaces to_records, main.rs:108-122 (seq_io reader: id = header up to the first space, sequence
+ * lines joined, upper-cased, U -> T) with a multi-threaded parse into one pinned buffer; n_threads 0 = all cores.
+ * msspe_fasta_open only parses (no device needed); msspe_load_fasta parses AND loads: the host-to-device copy of each
+ * 32 MB chunk is issued while the worker threads normalise the next one.  A FASTA that does not start with '>' gives
+ * MSSPE_ERR_INVALID (seq_io InvalidStart), a missing file MSSPE_ERR_IO.  The handle owns names/offsets/bases. */
+typedef struct msspe_fasta msspe_fasta;
+int msspe_fasta_open(const char* path, uint32_t n_threads, msspe_fasta** out, char* err, size_t err_len);
+void msspe_fasta_close(msspe_fasta* f);
+uint32_t msspe_fasta_records(const msspe_fasta* f);
+const char* msspe_fasta_name(const msspe_fasta* f, uint32_t i);  /* SequenceRecord.name */
+const uint8_t* msspe_fasta_bases(const msspe_fasta* f);         /* SequenceRecord.sequence of all records, concatenated */
+const uint64_t* msspe_fasta_offsets(const msspe_fasta* f);      /* [records + 1] */
+int msspe_load_fasta(msspe_ctx* ctx, const char* path, uint32_t n_threads, msspe_fasta** out);
 /* K1 + K2: slice windows, encode, dedup per (segment,direction), sort, build CSR postings + forward
  * index for both directions.  Replaces main.rs:205-232 and make_kmer_segments_windows_mapping :237-255. */
 int msspe_build_index(msspe_ctx* ctx);

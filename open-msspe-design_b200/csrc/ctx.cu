@@ -186,9 +186,8 @@ static int upload_plan(msspe_ctx* c) {
   return MSSPE_OK;
 }
 
-extern "C" int msspe_load_genomes(msspe_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n) {
-  if (!c) return MSSPE_ERR_INVALID;
-  if (!offsets || (n && !bases && offsets[n] > 0)) { c->set_error("msspe_load_genomes: null argument"); return MSSPE_ERR_INVALID; }
+// Plan the segments of n records and allocate their device buffer (fasta.cu streams the bases in chunk by chunk).
+int msspe_load_begin(msspe_ctx* c, const uint64_t* offsets, uint32_t n) {
   if (n == 0) { c->set_error("No sequences found in the input file"); return MSSPE_ERR_INVALID; }  // main.rs:652-654
   MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
   msspe_free_index(c);
@@ -198,15 +197,26 @@ extern "C" int msspe_load_genomes(msspe_ctx* c, const uint8_t* bases, const uint
   c->bases_bytes = offsets[n];
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&c->d_bases, c->bases_bytes ? c->bases_bytes : 1, c->stream));
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[0], c->stream));
-  if (c->bases_bytes)
-    MSSPE_CUDA_TRY(c, cudaMemcpyAsync(c->d_bases, bases, c->bases_bytes, cudaMemcpyHostToDevice, c->stream));
-  rc = upload_plan(c);
+  return MSSPE_OK;
+}
+int msspe_load_finish(msspe_ctx* c) {
+  int rc = upload_plan(c);
   if (rc) return rc;
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[1], c->stream));
   MSSPE_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   MSSPE_CUDA_TRY(c, cudaEventElapsedTime(&c->timing.h2d_ms, c->ev[0], c->ev[1]));
   c->loaded = true;
   return MSSPE_OK;
+}
+
+extern "C" int msspe_load_genomes(msspe_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n) {
+  if (!c) return MSSPE_ERR_INVALID;
+  if (!offsets || (n && !bases && offsets[n] > 0)) { c->set_error("msspe_load_genomes: null argument"); return MSSPE_ERR_INVALID; }
+  int rc = msspe_load_begin(c, offsets, n);
+  if (rc) return rc;
+  if (c->bases_bytes)
+    MSSPE_CUDA_TRY(c, cudaMemcpyAsync(c->d_bases, bases, c->bases_bytes, cudaMemcpyHostToDevice, c->stream));
+  return msspe_load_finish(c);
 }
 
 extern "C" int msspe_load_genomes_device(msspe_ctx* c, const uint8_t* d_bases, const uint64_t* offsets, uint32_t n) {

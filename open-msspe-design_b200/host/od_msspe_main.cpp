@@ -158,30 +158,7 @@ Args parse_args(int argc, char** argv) {
   return a;
 }
 
-struct Record { std::string name, sequence; };
-
-// to_records, main.rs:108-122 (seq_io: id = header up to the first space; all sequence lines joined)
-std::vector<Record> to_records(const std::string& src) {
-  std::vector<Record> recs;
-  size_t pos = 0; bool have = false; Record cur;
-  while (pos < src.size()) {
-    size_t e = src.find('\n', pos); if (e == std::string::npos) e = src.size();
-    size_t le = e; if (le > pos && src[le - 1] == '\r') le--;
-    if (le > pos && src[pos] == '>') {
-      if (have) recs.push_back(std::move(cur));
-      cur = Record(); have = true;
-      size_t t = pos + 1; while (t < le && src[t] != ' ') t++;
-      cur.name = src.substr(pos + 1, t - pos - 1);
-    } else if (have) {
-      for (size_t i = pos; i < le; i++) { char c = (char)toupper((unsigned char)src[i]); cur.sequence.push_back(c == 'U' ? 'T' : c); }
-    } else if (le > pos) {
-      panic("called `Result::unwrap()` on an `Err` value: InvalidStart (FASTA must begin with '>')");
-    }
-    pos = e + 1;
-  }
-  if (have) recs.push_back(std::move(cur));
-  return recs;
-}
+struct Record { std::string name; };  // SequenceRecord.name; the sequences live in the msspe_fasta handle / on the device
 
 std::string decode(uint64_t code, unsigned k) { std::string s(k, 'A'); for (unsigned i = 0; i < k; i++) s[i] = "ACGT"[(code >> (2 * (k - 1 - i))) & 3]; return s; }
 uint64_t revcomp_code(uint64_t code, unsigned k) { uint64_t r = 0; for (unsigned t = 0; t < k; t++) { r = (r << 2) | (3u - (code & 3u)); code >>= 2; } return r; }
@@ -230,16 +207,12 @@ int main(int argc, char** argv) {
     std::cerr << "od-msspe (B200 engine): MAFFT alignment is out of scope of this engine; align the input first and pass --do-align=false\n";
     return 2;
   }
-  std::ifstream in(a.input, std::ios::binary);
-  if (!in) { std::cerr << "Error: Os { code: 2, kind: NotFound, message: \"No such file or directory\" }\n"; return 1; }
-  std::stringstream ss; ss << in.rdbuf();
+  {
+    std::ifstream in(a.input, std::ios::binary);
+    if (!in) { std::cerr << "Error: Os { code: 2, kind: NotFound, message: \"No such file or directory\" }\n"; return 1; }
+  }
   log_info("Aligning sequences...");
-  std::vector<Record> records = to_records(ss.str());
   log_info(".... SKIPPED.");
-  if (records.empty()) panic("No sequences found in the input file");                        // main.rs:652-654
-  const uint64_t mms = a.has_mms ? a.max_mismatch_segments
-                                 : std::min<uint64_t>(10, std::max<uint64_t>(1, (records.size() + 49) / 50));  // main.rs:658-660
-  log_info("max_mismatch_segments=" + std::to_string(mms) + " (auto-scaled from " + std::to_string(records.size()) + " sequences)");
   if (a.overlap_size < a.search_windows_size) panic("Overlap windows size must be greater or equal than search windows size");  // main.rs:201-203
   if (a.overlap_size == 0) panic("assertion failed: step != 0");                                 // step_by(0)
   if (a.window_size == 0) panic("window size must be non-zero");                                  // windows(0)
@@ -249,6 +222,19 @@ int main(int argc, char** argv) {
   msspe_config cfg{(uint32_t)a.kmer_size, (uint32_t)a.window_size, (uint32_t)a.overlap_size, (uint32_t)a.search_windows_size,
                    getenv("MSSPE_DEVICE") ? atoi(getenv("MSSPE_DEVICE")) : 0, 0};
   if (int rc = msspe_create(&cfg, &ctx)) { std::cerr << "od-msspe: cannot start the GPU engine (" << rc << "): " << msspe_last_error(nullptr) << "\n"; return 1; }
+  // 1. to_records (main.rs:108-122) + upload: multi-threaded parse into pinned memory, chunked copies overlap the parse
+  msspe_fasta* fasta = nullptr;
+  if (int rc = msspe_load_fasta(ctx, a.input.c_str(), getenv("MSSPE_THREADS") ? (uint32_t)atoi(getenv("MSSPE_THREADS")) : 0u, &fasta)) {
+    const std::string msg = msspe_last_error(ctx);
+    if (rc == MSSPE_ERR_INVALID) panic(msg);                                                      // InvalidStart, or main.rs:652-654
+    std::cerr << "od-msspe: reading " << a.input << " failed (" << rc << "): " << msg << "\n";
+    return 1;
+  }
+  std::vector<Record> records(msspe_fasta_records(fasta));
+  for (size_t i = 0; i < records.size(); i++) records[i].name = msspe_fasta_name(fasta, (uint32_t)i);  // sequences stay in the handle
+  const uint64_t mms = a.has_mms ? a.max_mismatch_segments
+                                 : std::min<uint64_t>(10, std::max<uint64_t>(1, (records.size() + 49) / 50));  // main.rs:658-660
+  log_info("max_mismatch_segments=" + std::to_string(mms) + " (auto-scaled from " + std::to_string(records.size()) + " sequences)");
   {  // `ntthal -path <cwd>/primer3_config/` (delta_g.rs:90): use that directory when present, else the embedded tables
     msspe_thal_raw_params* p = new msspe_thal_raw_params();
     char err[256] = {0};
@@ -258,11 +244,6 @@ int main(int argc, char** argv) {
   }
   // 2. segments + inverted index (get_segment_manager, main.rs:693)
   log_info("Extracting n-grams from each sequence segments...");
-  std::vector<uint64_t> offs(records.size() + 1, 0);
-  for (size_t i = 0; i < records.size(); i++) offs[i + 1] = offs[i] + records[i].sequence.size();
-  std::string bases; bases.reserve(offs.back());
-  for (auto& r : records) bases += r.sequence;
-  CHECK(msspe_load_genomes(ctx, (const uint8_t*)bases.data(), offs.data(), (uint32_t)records.size()));
   CHECK(msspe_build_index(ctx));
   uint64_t G = 0; uint32_t maxp = 0, slots = 0;
   CHECK(msspe_segment_info(ctx, &G, &maxp, &slots));
@@ -392,6 +373,7 @@ int main(int argc, char** argv) {
   }
   out.close();
   log_info("Done outputting primers");
+  msspe_fasta_close(fasta);
   msspe_destroy(ctx);
   return 0;
 }

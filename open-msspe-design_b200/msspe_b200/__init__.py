@@ -27,7 +27,8 @@ ABI_SYMBOLS = [
     "msspe_build_index", "msspe_segment_info", "msspe_get_segment_kmers", "msspe_get_index", "msspe_select",
     "msspe_select_both", "msspe_coverage", "msspe_thal_params_default", "msspe_thal_params_from_dir",
     "msspe_set_thal_params", "msspe_primer_thermo", "msspe_thal_pairs", "msspe_cross_dimer",
-    "msspe_kmer_stats", "msspe_coverage_summary", "msspe_vertex_cover", "msspe_shard_begin", "msspe_shard_buffers", "msspe_shard_count", "msspe_shard_firstpos", "msspe_shard_apply",
+    "msspe_fasta_open", "msspe_fasta_close", "msspe_fasta_records", "msspe_fasta_name", "msspe_fasta_bases",
+    "msspe_fasta_offsets", "msspe_load_fasta", "msspe_kmer_stats", "msspe_coverage_summary", "msspe_vertex_cover", "msspe_shard_begin", "msspe_shard_buffers", "msspe_shard_count", "msspe_shard_firstpos", "msspe_shard_apply",
 ]
 
 
@@ -125,6 +126,18 @@ def load_library():
     L.msspe_select.argtypes = [C.c_void_p, C.c_uint8, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
     L.msspe_select_both.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32),
                                     C.c_void_p, C.POINTER(C.c_uint32)]
+    L.msspe_fasta_open.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+    L.msspe_fasta_close.argtypes = [C.c_void_p]
+    L.msspe_fasta_close.restype = None
+    L.msspe_fasta_records.argtypes = [C.c_void_p]
+    L.msspe_fasta_records.restype = C.c_uint32
+    L.msspe_fasta_name.argtypes = [C.c_void_p, C.c_uint32]
+    L.msspe_fasta_name.restype = C.c_char_p
+    L.msspe_fasta_bases.argtypes = [C.c_void_p]
+    L.msspe_fasta_bases.restype = C.c_void_p
+    L.msspe_fasta_offsets.argtypes = [C.c_void_p]
+    L.msspe_fasta_offsets.restype = C.c_void_p
+    L.msspe_load_fasta.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_void_p)]
     L.msspe_coverage_summary.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                          C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]
     L.msspe_vertex_cover.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
@@ -172,6 +185,44 @@ def pack_records(seqs) -> tuple[np.ndarray, np.ndarray]:
     return bases, offs
 
 
+class Fasta:
+    """A parsed FASTA file (to_records, main.rs:108-122): names, offsets[n+1] and the normalised bases."""
+
+    def __init__(self, L, handle):
+        self.L, self.h = L, handle
+        n = L.msspe_fasta_records(handle)
+        self.names = [L.msspe_fasta_name(handle, i).decode() for i in range(n)]
+        self.offsets = np.ctypeslib.as_array(C.cast(L.msspe_fasta_offsets(handle), C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
+        nb = int(self.offsets[-1])
+        self.bases = (np.ctypeslib.as_array(C.cast(L.msspe_fasta_bases(handle), C.POINTER(C.c_uint8)), shape=(nb,)).copy()
+                      if nb else np.zeros(0, np.uint8))
+
+    def sequences(self):
+        return [self.bases[int(self.offsets[i]):int(self.offsets[i + 1])].tobytes().decode("latin-1") for i in range(len(self.names))]
+
+    def close(self):
+        if self.h:
+            self.L.msspe_fasta_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def fasta_open(path: str, n_threads: int = 0) -> Fasta:
+    """Parse only (host; no device needed)."""
+    L = load_library()
+    h = C.c_void_p()
+    err = C.create_string_buffer(256)
+    rc = L.msspe_fasta_open(os.fsencode(path), n_threads, C.byref(h), err, 256)
+    if rc != OK:
+        raise MsspeError(rc, err.value.decode())
+    return Fasta(L, h)
+
+
 class Engine:
     """One msspe_ctx.  Method names follow the reference functions they replace."""
 
@@ -206,6 +257,12 @@ class Engine:
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         self._check(self.L.msspe_load_genomes(self.h, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1))
+
+    def load_fasta(self, path: str, n_threads: int = 0) -> Fasta:
+        """Parse and load in one call (chunked host-to-device copies overlap the parse)."""
+        h = C.c_void_p()
+        self._check(self.L.msspe_load_fasta(self.h, os.fsencode(path), n_threads, C.byref(h)))
+        return Fasta(self.L, h)
 
     def load_genomes_device(self, device_ptr: int, offsets: np.ndarray, keepalive=None):
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
