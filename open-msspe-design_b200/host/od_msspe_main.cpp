@@ -207,9 +207,18 @@ int main(int argc, char** argv) {
     std::cerr << "od-msspe (B200 engine): MAFFT alignment is out of scope of this engine; align the input first and pass --do-align=false\n";
     return 2;
   }
-  {
+  {  // the two input errors the reference raises before anything else, from the first non-empty line alone
     std::ifstream in(a.input, std::ios::binary);
     if (!in) { std::cerr << "Error: Os { code: 2, kind: NotFound, message: \"No such file or directory\" }\n"; return 1; }
+    std::string line; bool any = false;
+    while (std::getline(in, line)) {
+      if (!line.empty() && line.back() == '\r') line.pop_back();
+      if (line.empty()) continue;
+      any = true;
+      if (line[0] != '>') panic("called `Result::unwrap()` on an `Err` value: InvalidStart (FASTA must begin with '>')");
+      break;
+    }
+    if (!any) panic("No sequences found in the input file");                                    // main.rs:652-654
   }
   log_info("Aligning sequences...");
   log_info(".... SKIPPED.");
