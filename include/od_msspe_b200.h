@@ -263,6 +263,12 @@ int msspe_kmer_stats(msspe_ctx* ctx, const uint64_t* codes, uint32_t n, uint32_t
  * For HAIRPIN b is ignored.  One ntthal invocation per pair in the reference (delta_g.rs:93-113). */
 int msspe_thal_pairs(msspe_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t n_pairs, uint32_t oligo_len,
                      int32_t type, const msspe_thal_cond* cond, msspe_thal_out* out);
+/* msspe_thal_pairs for the dimer types (ANY, END1) plus the base pairs of every structure, which is what ntthal's
+ * SEQ/STR drawing (the four lines the parser of delta_g.rs:55 skips) is made from:
+ * pairing[p * MSSPE_MAX_OLIGO + i] = 1-based position, in the REVERSED second oligo (3'->5', as ntthal draws it),
+ * of the base that base i (0-based) of the first oligo pairs with; 0 = unpaired. */
+int msspe_thal_pairs_aligned(msspe_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t n_pairs, uint32_t oligo_len,
+                             int32_t type, const msspe_thal_cond* cond, msspe_thal_out* out, uint8_t* pairing);
 /* Replaces run_ntthal, delta_g.rs:83-153, for rows [row_begin,row_end) of the n x n ordered-pair matrix
  * (all pairs incl. self, a-major, delta_g.rs:64-78).  Emits every pair with dG < dg_limit (caller passes
  * threshold + margin and finishes the "%g"/f32 comparison, delta_g.rs:33-36) and every pair without a

@@ -117,6 +117,7 @@ struct DimerArgs {
   msspe_dimer_edge* edges; unsigned long long edge_cap; unsigned long long* n_edges;
   uint64_t* nostruct; unsigned long long nostruct_cap; unsigned long long* n_nostruct;
   int dbg;  // diagnostic: 1 = skip loop candidates, 2 = skip traceback, 4 = skip fill entirely
+  uint8_t* pairing;  // optional [n_pairs][MSSPE_MAX_OLIGO], zeroed: partner (1-based, in the reversed second oligo) of base i
 };
 
 struct DimerShared {  // per block
@@ -418,6 +419,7 @@ thal_dimer_kernel(const DimerArgs A) {
       const double dS = bc.x + rshS[ri] + kDSi;
       // ---------------- traceback: count paired positions ----------------
       int i = bi, j = bjx, pairs = 1;
+      if (A.pairing && gl == 0) A.pairing[p * MSSPE_MAX_OLIGO + (i - 1)] = (uint8_t)j;
       for (int guard = 0; guard < ((A.dbg & 2) ? 0 : 2 * k + 2); guard++) {
         const int li = (pv.n1[i] * 5 + pv.n1[i - 1]) * 5 + pv.n2[j - 1];
         const double2 c = pv.cell[(i - 1) * k + (j - 1)];
@@ -425,7 +427,11 @@ thal_dimer_kernel(const DimerArgs A) {
         if (i > 1 && j > 1 && ((pv.rowmask[i - 1] >> (j - 2)) & 1u)) {
           const int si = i4(pv.n1[i - 1], pv.n1[i], pv.n2[j - 1], pv.n2[j]);
           const double2 pc = pv.cell[(i - 2) * k + (j - 2)];
-          if (eq2(c.x, sh.stackS[si] + pc.x) && eq2(c.y, sh.stackH[si] + pc.y)) { i--; j--; pairs++; continue; }
+          if (eq2(c.x, sh.stackS[si] + pc.x) && eq2(c.y, sh.stackH[si] + pc.y)) {
+            i--; j--; pairs++;
+            if (A.pairing && gl == 0) A.pairing[p * MSSPE_MAX_OLIGO + (i - 1)] = (uint8_t)j;
+            continue;
+          }
         }
         int key = 0x7fffffff;
         const Closing cl = make_closing(sh, pv, i > 1 ? i : 2, j > 1 ? j : 2);  // only used when i, j >= 2
@@ -448,6 +454,7 @@ thal_dimer_kernel(const DimerArgs A) {
         if (key == 0x7fffffff) break;
         const int l1 = key & 63, l2 = (key >> 6) - l1;
         i = i - 1 - l1; j = j - 1 - l2; pairs++;
+        if (A.pairing && gl == 0) A.pairing[p * MSSPE_MAX_OLIGO + (i - 1)] = (uint8_t)j;
       }
       const int N = pairs - 1;  // (#paired bases in both strands)/2 - 1
       const double t = (dH / (dS + (N * saltCorr) + RC)) - kAbsZero;
@@ -881,8 +888,8 @@ extern "C" int msspe_set_thal_params(msspe_ctx* c, const msspe_thal_raw_params* 
   return msspe_thal_upload_tables(c);
 }
 
-extern "C" int msspe_thal_pairs(msspe_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t n_pairs, uint32_t oligo_len,
-                                int32_t type, const msspe_thal_cond* cond, msspe_thal_out* out) {
+static int thal_pairs_impl(msspe_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t n_pairs, uint32_t oligo_len,
+                           int32_t type, const msspe_thal_cond* cond, msspe_thal_out* out, uint8_t* pairing) {
   if (!c) return MSSPE_ERR_INVALID;
   if (!cond || (n_pairs && (!a || !out))) { c->set_error("msspe_thal_pairs: null argument"); return MSSPE_ERR_INVALID; }
   if (type != MSSPE_THAL_ANY && type != MSSPE_THAL_END1 && type != MSSPE_THAL_HAIRPIN) { c->set_error("msspe_thal_pairs: unsupported type %d", type); return MSSPE_ERR_INVALID; }
@@ -899,9 +906,14 @@ extern "C" int msspe_thal_pairs(msspe_ctx* c, const uint64_t* a, const uint64_t*
   ThalDimerConsts K;
   build_dimer_consts(*hT, *cond, &K);
   delete hT;
-  DeviceBuf da, db, dout, dK, dwork;
+  DeviceBuf da, db, dout, dK, dwork, dpair;
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&(da.st = c->stream, da.p), n_pairs * 8, c->stream));
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dout.st = c->stream, dout.p), n_pairs * sizeof(msspe_thal_out), c->stream));
+  if (pairing) {
+    if (type == MSSPE_THAL_HAIRPIN) { c->set_error("msspe_thal_pairs_aligned: dimer types only"); return MSSPE_ERR_INVALID; }
+    MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dpair.st = c->stream, dpair.p), n_pairs * MSSPE_MAX_OLIGO, c->stream));
+    MSSPE_CUDA_TRY(c, cudaMemsetAsync(dpair.p, 0, n_pairs * MSSPE_MAX_OLIGO, st));
+  }
   MSSPE_CUDA_TRY(c, cudaMemcpyAsync(da.p, a, n_pairs * 8, cudaMemcpyHostToDevice, st));
   if (type == MSSPE_THAL_HAIRPIN) {
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dwork.st = c->stream, dwork.p), n_pairs * sizeof(MonoWork), c->stream));
@@ -917,13 +929,25 @@ extern "C" int msspe_thal_pairs(msspe_ctx* c, const uint64_t* a, const uint64_t*
     MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dK.p, &K, sizeof K, cudaMemcpyHostToDevice, st));
     DimerArgs A{};
     A.a = (const uint64_t*)da.p; A.b = (const uint64_t*)db.p; A.n_pairs = n_pairs; A.matrix = 0; A.k = (int)oligo_len; A.type = type;
-    A.T = c->d_thal; A.C = (const ThalDimerConsts*)dK.p; A.out = (msspe_thal_out*)dout.p;
+    A.T = c->d_thal; A.C = (const ThalDimerConsts*)dK.p; A.out = (msspe_thal_out*)dout.p; A.pairing = (uint8_t*)dpair.p;
     rc = launch_dimer(c, A, st);
     if (rc) return rc;
   }
   MSSPE_CUDA_TRY(c, cudaMemcpyAsync(out, dout.p, n_pairs * sizeof(msspe_thal_out), cudaMemcpyDeviceToHost, st));
+  if (pairing) MSSPE_CUDA_TRY(c, cudaMemcpyAsync(pairing, dpair.p, n_pairs * MSSPE_MAX_OLIGO, cudaMemcpyDeviceToHost, st));
   MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
   return MSSPE_OK;
+}
+
+extern "C" int msspe_thal_pairs(msspe_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t n_pairs, uint32_t oligo_len,
+                                int32_t type, const msspe_thal_cond* cond, msspe_thal_out* out) {
+  return thal_pairs_impl(c, a, b, n_pairs, oligo_len, type, cond, out, nullptr);
+}
+
+extern "C" int msspe_thal_pairs_aligned(msspe_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t n_pairs, uint32_t oligo_len,
+                                        int32_t type, const msspe_thal_cond* cond, msspe_thal_out* out, uint8_t* pairing) {
+  if (c && !pairing) { c->set_error("msspe_thal_pairs_aligned: null argument"); return MSSPE_ERR_INVALID; }
+  return thal_pairs_impl(c, a, b, n_pairs, oligo_len, type, cond, out, pairing);
 }
 
 extern "C" int msspe_primer_thermo(msspe_ctx* c, const uint64_t* codes, uint32_t n, uint32_t oligo_len, double* tm, double* gc,

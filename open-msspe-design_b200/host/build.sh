@@ -6,4 +6,10 @@ PKG="$(dirname "$HERE")"
 mkdir -p "$PKG/bin"
 g++ -O2 -std=c++17 -Wall -ffp-contract=off -o "$PKG/bin/od-msspe" "$HERE/od_msspe_main.cpp" \
   -L"$PKG" -lodmsspe_b200 -Wl,-rpath,'$ORIGIN/..' -Wl,-rpath,/usr/local/cuda/lib64
-echo "built $PKG/bin/od-msspe"
+# the protocol shims for the reference's --ntthal / --primer3 seam (seam #1)
+mkdir -p "$PKG/bin/shims"
+g++ -O2 -std=c++17 -Wall -ffp-contract=off -o "$PKG/bin/shims/ntthal" "$HERE/ntthal_shim.cpp" \
+  -L"$PKG" -lodmsspe_b200 -Wl,-rpath,'$ORIGIN/../..' -Wl,-rpath,/usr/local/cuda/lib64
+g++ -O2 -std=c++17 -Wall -ffp-contract=off -o "$PKG/bin/shims/primer3_core" "$HERE/primer3_core_shim.cpp" \
+  -L"$PKG" -lodmsspe_b200 -Wl,-rpath,'$ORIGIN/../..' -Wl,-rpath,/usr/local/cuda/lib64
+echo "built $PKG/bin/od-msspe, $PKG/bin/shims/ntthal, $PKG/bin/shims/primer3_core"

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "msspe_get_timing", "msspe_reset_timing", "msspe_set_profiling", "msspe_load_genomes", "msspe_load_genomes_device",
     "msspe_build_index", "msspe_segment_info", "msspe_get_segment_kmers", "msspe_get_index", "msspe_select",
     "msspe_select_both", "msspe_coverage", "msspe_thal_params_default", "msspe_thal_params_from_dir",
-    "msspe_set_thal_params", "msspe_primer_thermo", "msspe_thal_pairs", "msspe_cross_dimer",
+    "msspe_set_thal_params", "msspe_primer_thermo", "msspe_thal_pairs", "msspe_thal_pairs_aligned", "msspe_cross_dimer",
     "msspe_fasta_open", "msspe_fasta_close", "msspe_fasta_records", "msspe_fasta_name", "msspe_fasta_bases",
     "msspe_fasta_offsets", "msspe_load_fasta", "msspe_kmer_stats", "msspe_coverage_summary", "msspe_vertex_cover", "msspe_shard_begin", "msspe_shard_buffers", "msspe_shard_count", "msspe_shard_firstpos", "msspe_shard_apply",
 ]
