@@ -42,6 +42,24 @@ THAL_POOL = 4096
 
 
 def clock_sampler(stop, out, gpu_index):
+    """SM clock and throttle reasons DURING the timed region.  In-process NVML (a query costs microseconds); spawning
+    nvidia-smi every few milliseconds takes a driver lock often enough to perturb the host-side calls being timed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[gpu_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not stop.is_set():
+            r = get_reasons(h)
+            flag = lambda bit: "Active" if r & bit else "Not Active"  # noqa: E731
+            out.append([str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(mx), flag(0x8), flag(0x40), flag(0x20), flag(0x4)])
+            stop.wait(0.01)
+        return
+    except Exception:
+        pass
     q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     while not stop.is_set():
         try:
