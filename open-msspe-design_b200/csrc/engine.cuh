@@ -69,6 +69,9 @@ struct SelectCtl {
   unsigned int pg[2];              // max live frequency
   unsigned int pt[2];              // number of tied k-mers
   unsigned long long pk[2];        // best (score bits << 32 | ~code id)
+  unsigned int plive[2];           // live postings counted in this iteration (all blocks)
+  unsigned int resume_it;          // persistent kernel left for a stream compaction: iteration to resume at
+  unsigned int exit_compact;       // 1 = it left because less than half of the streamed postings were still live
   unsigned long long t_count_ns;   // time inside the coverage-scoring phases (block 0, %globaltimer)
   unsigned long long t_tie_ns;     // time inside the tie-break phases
   unsigned long long t_total_ns;

@@ -74,6 +74,84 @@ stream_copy_kernel(const uint32_t* __restrict__ post_off, const uint32_t* __rest
   }
 }
 
+// ---- dead-posting compaction of the scoring stream (between launches of the persistent kernel) ----
+// live postings of every list of the current stream under the covered-segment bitmask; one warp per 32 lists
+__global__ void __launch_bounds__(256)
+stream_live_kernel(const uint32_t* __restrict__ s_off, const uint32_t* __restrict__ s_postings, uint32_t n_lists,
+                   const uint32_t* __restrict__ ignored, uint32_t* __restrict__ cnt, uint32_t* __restrict__ multi,
+                   uint32_t* __restrict__ mlen, uint32_t* __restrict__ single) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t c = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u + (uint32_t)lane;
+  uint32_t a = 0, len = 0, live = 0;
+  if (c < n_lists) {
+    a = s_off[c]; len = s_off[c + 1] - a;
+    if (len <= 8u) for (uint32_t i = 0; i < len; i++) { const uint32_t g = s_postings[a + i]; live += (~ignored[g >> 5] >> (g & 31u)) & 1u; }
+  }
+  unsigned big = __ballot_sync(0xffffffffu, len > 8u);
+  while (big) {
+    const int l = __ffs(big) - 1;
+    big &= big - 1;
+    const uint32_t la = __shfl_sync(0xffffffffu, a, l), ll = __shfl_sync(0xffffffffu, len, l);
+    uint32_t n = 0;
+    for (uint32_t i = lane; i < ll; i += 32) { const uint32_t g = s_postings[la + i]; n += (~ignored[g >> 5] >> (g & 31u)) & 1u; }
+    n = __reduce_add_sync(0xffffffffu, n);
+    if (lane == l) live = n;
+  }
+  if (c < n_lists) { cnt[c] = live; multi[c] = live >= 2u ? 1u : 0u; mlen[c] = live >= 2u ? live : 0u; single[c] = live == 1u ? 1u : 0u; }
+}
+
+// order-preserving move of the live postings: lists that still have >= 2 of them keep a list (new rank = number of
+// such lists before), a list left with one contributes it to the counted-only tail, dead lists vanish
+__global__ void __launch_bounds__(256)
+stream_compact_kernel(const uint32_t* __restrict__ s_off, const uint32_t* __restrict__ s_postings, const uint32_t* __restrict__ s_id,
+                      uint32_t n_lists, const uint32_t* __restrict__ ignored, const uint32_t* __restrict__ cnt,
+                      const uint32_t* __restrict__ rank, const uint32_t* __restrict__ moff, const uint32_t* __restrict__ srank,
+                      uint32_t new_lists, uint32_t new_list_post, uint32_t new_tail_begin, uint32_t* __restrict__ n_postings,
+                      uint32_t* __restrict__ n_off, uint32_t* __restrict__ n_id) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t c = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u + (uint32_t)lane;
+  uint32_t a = 0, len = 0, dst = 0, n = 0;
+  if (c < n_lists) {
+    a = s_off[c]; len = s_off[c + 1] - a; n = cnt[c];
+    if (n >= 2u) { dst = moff[c]; n_off[rank[c]] = dst; n_id[rank[c]] = s_id[c]; }
+    else if (n == 1u) dst = new_tail_begin + srank[c];
+    if (n && len <= 8u)
+      for (uint32_t i = 0; i < len; i++) { const uint32_t g = s_postings[a + i]; if ((~ignored[g >> 5] >> (g & 31u)) & 1u) n_postings[dst++] = g; }
+  }
+  if (c == 0) n_off[new_lists] = new_list_post;
+  unsigned big = __ballot_sync(0xffffffffu, n && len > 8u);
+  while (big) {
+    const int l = __ffs(big) - 1;
+    big &= big - 1;
+    const uint32_t la = __shfl_sync(0xffffffffu, a, l), ll = __shfl_sync(0xffffffffu, len, l);
+    uint32_t ld = __shfl_sync(0xffffffffu, dst, l);
+    for (uint32_t base = 0; base < ll; base += 32) {
+      const uint32_t i = base + lane;
+      const uint32_t g = i < ll ? s_postings[la + i] : 0u;
+      const bool live = i < ll && ((~ignored[g >> 5] >> (g & 31u)) & 1u);
+      const unsigned m = __ballot_sync(0xffffffffu, live);
+      if (live) n_postings[ld + __popc(m & ((1u << lane) - 1u))] = g;
+      ld += __popc(m);
+    }
+  }
+}
+
+// live postings of the old tail, appended to the new tail in any order (the tail is only counted)
+__global__ void stream_tail_compact_kernel(const uint32_t* __restrict__ s_postings, uint32_t tail_begin, uint32_t tail_end,
+                                           const uint32_t* __restrict__ ignored, uint32_t* __restrict__ n_postings, uint32_t dst_begin,
+                                           uint32_t* counter) {
+  const uint32_t i = tail_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t g = i < tail_end ? s_postings[i] : 0u;
+  const bool live = i < tail_end && ((~ignored[g >> 5] >> (g & 31u)) & 1u);
+  const unsigned m = __ballot_sync(0xffffffffu, live);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31;
+  uint32_t base = 0;
+  if (lane == __ffs(m) - 1) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (live) n_postings[dst_begin + base + __popc(m & ((1u << lane) - 1u))] = g;
+}
+
 template <bool SMEM_MASK>
 __global__ void __launch_bounds__(CNT_THREADS)
 count_kernel(const uint32_t* __restrict__ postings, const uint32_t* __restrict__ post_off,
@@ -215,12 +293,16 @@ struct GreedyDir {
   const uint32_t* postings; const uint32_t* post_off; const uint32_t* tile_first; const uint64_t* codes;
   uint32_t n_codes, n_post, n_tiles, pad;
   const uint32_t* list_id;       // code id of every list of the scoring stream
-  uint32_t tail_t0, tail_t1, tail_end, pad2;  // tiles / end of the single-posting tail of the stream
+  uint32_t tail_t0, tail_t1, tail_end, stream_total;  // tiles / end of the counted-only tail; postings streamed per recount
+  const uint32_t* full_off; const uint32_t* full_postings;  // the complete CSR: main.rs:371-378 walks ALL postings of a winner
+  uint32_t done0, pad2;          // resumed launch: this direction had already finished
   uint32_t* ignored; uint32_t* freq; unsigned long long* acc; uint32_t* cov; SelectCtl* ctl; msspe_candidate* out;
 };
 struct GreedyArgs {
   GreedyDir d[2];
   int ndirs; uint32_t mask_words, p_words, max_iter, mms;
+  uint32_t it0;       // first iteration of this launch (> 0: resumed after a stream compaction)
+  uint32_t compact_min;  // leave for a compaction when < half of a stream of at least this many postings is live (0 = never)
   uint32_t n_part;   // max partition_no + 1
   uint32_t n_fp;     // entries of the block-cooperative tie-score scratch (n_part, or 0 = too many partitions)
   const uint16_t* seg_part;
@@ -245,6 +327,26 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+}
+
+// Block 0's share of main.rs:371-378: EVERY posting of the winner (also the already covered ones, which the
+// compacted stream no longer holds, hence the complete CSR) is marked in the global bitmask, and every distinct
+// partition among them gets partition_coverage += 1.  pm = shared-memory partition bitmap, left zeroed.
+template <int THREADS>
+__device__ __forceinline__ void apply_winner_global(const GreedyDir& D, const uint16_t* __restrict__ seg_part, uint32_t code_id, uint32_t* pm) {
+  const int tid = threadIdx.x;
+  const uint32_t a = D.full_off[code_id], b = D.full_off[code_id + 1];
+  for (uint32_t i = a + tid; i < b; i += THREADS) {
+    const uint32_t sg = __ldg(D.full_postings + i);
+    atomicOr(&D.ignored[sg >> 5], 1u << (sg & 31u));
+    const uint32_t p = seg_part[sg];
+    const uint32_t pbit = 1u << (p & 31u);
+    const uint32_t old = atomicOr(&pm[p >> 5], pbit);
+    if (!(old & pbit)) atomicAdd(&D.cov[p], 1u);
+  }
+  __syncthreads();
+  for (uint32_t i = a + tid; i < b; i += THREADS) pm[seg_part[__ldg(D.full_postings + i)] >> 5] = 0u;
+  __syncthreads();
 }
 
 // The recount job of one warp for direction d (a literal at every call site).
@@ -274,8 +376,9 @@ greedy_persistent_kernel(const GreedyArgs A) {
   uint32_t* fp = seen + A.p_words;
   unsigned long long* lst = reinterpret_cast<unsigned long long*>(
       dsm + (((size_t)(reinterpret_cast<unsigned char*>(fp + A.n_fp) - dsm) + 7) & ~(size_t)7));
-  if (SMEM_MASK)
-    for (uint32_t i = tid; i < (uint32_t)A.ndirs * A.mask_words; i += THREADS) smask[i] = 0u;
+  if (SMEM_MASK)  // the global bitmask is all zero at the first launch and current at a resumed one
+    for (int d = 0; d < A.ndirs; d++)
+      for (uint32_t i = tid; i < A.mask_words; i += THREADS) smask[(size_t)d * A.mask_words + i] = __ldcg(A.d[d].ignored + i);
   for (uint32_t i = tid; i < A.p_words; i += THREADS) pm[i] = 0u;
   if (tid == 0) { s_cnt = 0u; s_max[0] = 0u; s_max[1] = 0u; }
   __syncthreads();
@@ -283,12 +386,13 @@ greedy_persistent_kernel(const GreedyArgs A) {
   const bool solo = gridDim.x == 1;
   const bool worker = solo || blockIdx.x > 0;
   const uint32_t wid = solo ? 0u : blockIdx.x - 1u, nworkers = solo ? 1u : gridDim.x - 1u;
-  bool done[2] = {false, A.ndirs < 2};
+  bool done[2] = {A.d[0].done0 != 0u, A.ndirs < 2 || A.d[1].done0 != 0u};
   // block-uniform loop state lives in shared memory (every thread writes the same value before it reads it), so
   // that the streaming loop of phase A has the registers to itself
   __shared__ uint32_t s_win[2], s_gsave[2];
   __shared__ unsigned long long s_evals[2];
-  if (tid == 0) { s_evals[0] = 0ull; s_evals[1] = 0ull; }
+  __shared__ uint32_t s_live[2];  // this block's live postings of the current iteration
+  if (tid == 0) { s_evals[0] = 0ull; s_evals[1] = 0ull; s_live[0] = 0u; s_live[1] = 0u; }
   __syncthreads();
   // first k-mer of this warp's tile range; recomputed only when the set of running directions changes
   __shared__ uint32_t s_cfirst[WARPS];
@@ -300,7 +404,7 @@ greedy_persistent_kernel(const GreedyArgs A) {
   if (tid == 0) for (int q = 0; q < 12; q++) s_tm[q] = 0ull;
   __syncthreads();
   if (lead) s_tm[0] = globaltimer_ns();
-  for (uint32_t it = 0;; it++) {
+  for (uint32_t it = A.it0;; it++) {
     const int par = it & 1;
     if (lead) s_tm[1] = globaltimer_ns();
     if (wlead) s_tm[5] = globaltimer_ns();
@@ -336,29 +440,18 @@ greedy_persistent_kernel(const GreedyArgs A) {
       if (myd == 0) { CountJob J; make_job<SMEM_MASK>(J, A, 0, smask, my_gw, my_nw, s_cfirst[warp]); warp_count_begin(J, S, lane); }
       else          { CountJob J; make_job<SMEM_MASK>(J, A, 1, smask, my_gw, my_nw, s_cfirst[warp]); warp_count_begin(J, S, lane); }
     }
-    if (it > 0) {  // main.rs:371-378 for the previous winners (a direction that is not done has pushed one per iteration)
+    if (it > A.it0) {  // main.rs:371-378 for the previous winners (a direction that is not done has pushed one per iteration)
       for (int d = 0; d < A.ndirs; d++) {
         if (done[d]) continue;
         const GreedyDir& D = A.d[d];
         uint32_t* mask = SMEM_MASK ? smask + (size_t)d * A.mask_words : D.ignored;
-        const uint32_t a = D.post_off[s_win[d]], b = D.post_off[s_win[d] + 1];
+        const uint32_t a = D.post_off[s_win[d]], b = D.post_off[s_win[d] + 1];  // live part is enough for the bitmask
         if (SMEM_MASK)
           for (uint32_t i = a + tid; i < b; i += THREADS) { const uint32_t sg = __ldg(D.postings + i); atomicOr(&mask[sg >> 5], 1u << (sg & 31u)); }
-        if (blockIdx.x == 0) {
-          for (uint32_t i = a + tid; i < b; i += THREADS) {
-            const uint32_t sg = __ldg(D.postings + i);
-            atomicOr(&D.ignored[sg >> 5], 1u << (sg & 31u));
-            const uint32_t p = A.seg_part[sg];
-            const uint32_t pbit = 1u << (p & 31u);
-            const uint32_t old = atomicOr(&pm[p >> 5], pbit);
-            if (!(old & pbit)) atomicAdd(&D.cov[p], 1u);
-          }
-          __syncthreads();
-          for (uint32_t i = a + tid; i < b; i += THREADS) pm[A.seg_part[__ldg(D.postings + i)] >> 5] = 0u;
-          __syncthreads();
-        }
+        if (blockIdx.x == 0) apply_winner_global<THREADS>(D, A.seg_part, D.list_id[s_win[d]], pm);
       }
       __syncthreads();
+      if (!SMEM_MASK) grid_barrier(A.barrier, bar_target);  // the workers read the global bitmask block 0 has just updated
     }
     if (worker) {
       uint32_t mymax = 0;
@@ -367,12 +460,16 @@ greedy_persistent_kernel(const GreedyArgs A) {
       else          { CountJob J; make_job<SMEM_MASK>(J, A, 1, smask, my_gw, my_nw, s_cfirst[warp]); live = warp_count_run<SMEM_MASK>(J, S, mymax, lane); }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
-      if (lane == 0) { if (mymax) atomicMax(&s_max[myd], mymax); if (live) atomicAdd(&s_evals[myd], live); }
+      if (lane == 0) { if (mymax) atomicMax(&s_max[myd], mymax); if (live) atomicAdd(&s_live[myd], (uint32_t)live); }
     }
     __syncthreads();
     if (tid == 0 && worker)
       for (int d = 0; d < A.ndirs; d++)
-        if (!done[d]) { if (s_max[d]) atomicMax(&A.d[d].ctl->pg[par], s_max[d]); s_max[d] = 0u; }
+        if (!done[d]) {
+          if (s_max[d]) atomicMax(&A.d[d].ctl->pg[par], s_max[d]);
+          if (s_live[d]) atomicAdd(&A.d[d].ctl->plive[par], s_live[d]);
+          s_evals[d] += s_live[d]; s_max[d] = 0u; s_live[d] = 0u;
+        }
     if (wlead) { const unsigned long long t = globaltimer_ns(); s_tm[8] += t - s_tm[5]; s_tm[5] = t; }
     grid_barrier(A.barrier, bar_target);
     if (wlead) { const unsigned long long t = globaltimer_ns(); s_tm[9] += t - s_tm[5]; s_tm[5] = t; }
@@ -383,7 +480,7 @@ greedy_persistent_kernel(const GreedyArgs A) {
       const GreedyDir& D = A.d[d];
       const uint32_t g = __ldcg(&D.ctl->pg[par]);
       s_gsave[d] = g;
-      if (lead) { D.ctl->pg[par ^ 1] = 0; D.ctl->pt[par ^ 1] = 0; D.ctl->pk[par ^ 1] = 0ull; }  // next iteration's slots
+      if (lead) { D.ctl->pg[par ^ 1] = 0; D.ctl->pt[par ^ 1] = 0; D.ctl->pk[par ^ 1] = 0ull; D.ctl->plive[par ^ 1] = 0; D.ctl->postings_read += D.stream_total; }  // next iteration's slots
       if (g <= 1u) {  // None or freq == 1: stop before the push (main.rs:353-366)
         done[d] = true;
         if (lead) { D.ctl->iterations = it + 1; D.ctl->n_out = it; D.ctl->done = 1; }
@@ -466,11 +563,24 @@ greedy_persistent_kernel(const GreedyArgs A) {
       all_done = all_done && done[d];
     }
     if (all_done) break;
+    if (A.compact_min) {  // less than half of what a running direction streams is still live: leave for a compaction
+      bool leave = false;
+      for (int d = 0; d < A.ndirs; d++)
+        if (!done[d] && A.d[d].stream_total >= A.compact_min && 2u * __ldcg(&A.d[d].ctl->plive[par]) < A.d[d].stream_total) leave = true;
+      if (leave) {
+        for (int d = 0; d < A.ndirs; d++) {
+          if (done[d]) continue;
+          if (blockIdx.x == 0) apply_winner_global<THREADS>(A.d[d], A.seg_part, A.d[d].list_id[s_win[d]], pm);  // nothing stays pending
+          if (lead) { A.d[d].ctl->resume_it = it + 1u; A.d[d].ctl->exit_compact = 1u; }
+        }
+        break;
+      }
+    }
   }
   for (int d = 0; d < A.ndirs; d++) {
     if (tid == 0 && s_evals[d]) atomicAdd(&A.d[d].ctl->evals, s_evals[d]);
-    if (lead) { A.d[d].ctl->t_count_ns = s_tm[3]; A.d[d].ctl->t_tie_ns = s_tm[4]; A.d[d].ctl->t_total_ns = globaltimer_ns() - s_tm[0]; }
-    if (wlead) for (int q = 0; q < 4; q++) A.d[d].ctl->t_dbg[4 + q] = s_tm[8 + q];
+    if (lead) { A.d[d].ctl->t_count_ns += s_tm[3]; A.d[d].ctl->t_tie_ns += s_tm[4]; A.d[d].ctl->t_total_ns += globaltimer_ns() - s_tm[0]; }
+    if (wlead) for (int q = 0; q < 4; q++) A.d[d].ctl->t_dbg[4 + q] += s_tm[8 + q];
   }
 }
 
@@ -560,6 +670,74 @@ void launch_iteration(msspe_ctx* c, DirRun& r, uint32_t max_iter, uint32_t mms, 
   c->timing.kernel_launches++;
 }
 
+// The stream a direction currently scores: the pristine one of the index, or a compacted working copy.
+struct ScoreStream {
+  uint32_t* postings; uint32_t* off; uint32_t* id; uint32_t* tile_first;
+  uint32_t lists, list_post, tiles, tail_end;
+  bool owned;
+};
+
+void free_stream(msspe_ctx* c, ScoreStream& S) {
+  if (!S.owned) return;
+  msspe_dev_free(c, S.postings); msspe_dev_free(c, S.off); msspe_dev_free(c, S.id); msspe_dev_free(c, S.tile_first);
+  S.owned = false;
+}
+
+// Drop the dead postings of a stream (order-preserving), given the current global bitmask of the direction.
+int compact_stream(msspe_ctx* c, DirIndex& D, ScoreStream& S, cudaStream_t st) {
+  const uint32_t nl = S.lists, tail_begin = S.tiles * (uint32_t)CNT_TILE;
+  uint32_t *cnt = nullptr, *multi = nullptr, *mlen = nullptr, *single = nullptr, *d_tot = nullptr;
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&cnt, ((uint64_t)nl + 1) * 4, st));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&multi, ((uint64_t)nl + 1) * 4, st));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&mlen, ((uint64_t)nl + 1) * 4, st));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&single, ((uint64_t)nl + 1) * 4, st));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&d_tot, 16, st));
+  MSSPE_CUDA_TRY(c, cudaMemsetAsync(d_tot, 0, 16, st));
+  uint32_t tot[4] = {0, 0, 0, 0};  // lists kept, their postings, lists left with one posting, live postings of the old tail
+  if (nl) {
+    stream_live_kernel<<<(unsigned)div_up_u64(nl, 256), 256, 0, st>>>(S.off, S.postings, nl, D.ignored, cnt, multi, mlen, single);
+    c->timing.kernel_launches++;
+    int rc = msspe_exclusive_scan_u32(c, multi, multi, nl, d_tot, st);
+    if (!rc) rc = msspe_exclusive_scan_u32(c, mlen, mlen, nl, d_tot + 1, st);
+    if (!rc) rc = msspe_exclusive_scan_u32(c, single, single, nl, d_tot + 2, st);
+    if (rc) return rc;
+  }
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(tot, d_tot, 12, cudaMemcpyDeviceToHost, st));
+  MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+  ScoreStream N{};
+  N.lists = tot[0]; N.list_post = tot[1]; N.tiles = (uint32_t)div_up_u64(N.list_post, CNT_TILE); N.owned = true;
+  const uint32_t n_tail_begin = N.tiles * (uint32_t)CNT_TILE;
+  const uint64_t cap = (uint64_t)n_tail_begin + tot[2] + (S.tail_end - tail_begin) + CNT_TILE;
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&N.postings, cap * 4, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&N.off, ((uint64_t)N.lists + 1) * 4, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&N.id, ((uint64_t)N.lists + 1) * 4, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&N.tile_first, ((uint64_t)N.tiles + 1) * 4, c->stream));
+  if (nl) {
+    stream_compact_kernel<<<(unsigned)div_up_u64(nl, 256), 256, 0, st>>>(S.off, S.postings, S.id, nl, D.ignored, cnt, multi, mlen, single, N.lists,
+                                                                         N.list_post, n_tail_begin, N.postings, N.off, N.id);
+    c->timing.kernel_launches++;
+  } else {
+    MSSPE_CUDA_TRY(c, cudaMemsetAsync(N.off, 0, 4, st));
+  }
+  if (S.tail_end > tail_begin) {
+    stream_tail_compact_kernel<<<(unsigned)div_up_u64(S.tail_end - tail_begin, 256), 256, 0, st>>>(S.postings, tail_begin, S.tail_end, D.ignored, N.postings,
+                                                                                               n_tail_begin + tot[2], d_tot + 3);
+    c->timing.kernel_launches++;
+  }
+  if (N.tiles) {
+    tile_first_kernel<<<(N.tiles + 255) / 256, 256, 0, st>>>(N.off, N.lists, N.tiles, N.tile_first);
+    c->timing.kernel_launches++;
+  }
+  MSSPE_CUDA_TRY(c, cudaGetLastError());
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(&tot[3], d_tot + 3, 4, cudaMemcpyDeviceToHost, st));
+  for (uint32_t* p : {cnt, multi, mlen, single, d_tot}) MSSPE_CUDA_TRY(c, cudaFreeAsync(p, st));
+  MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+  N.tail_end = n_tail_begin + tot[2] + tot[3];
+  free_stream(c, S);
+  S = N;
+  return MSSPE_OK;
+}
+
 int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max_iter, uint32_t mms,
                           msspe_candidate** outs, uint32_t** n_outs) {
   cudaStream_t st = c->stream;
@@ -567,10 +745,12 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
   GreedyArgs A{};
   A.ndirs = ndirs; A.max_iter = max_iter; A.mms = mms; A.seg_part = c->d_seg_part;
   A.barrier = c->dir[dirs[0]].pmark;  // 8 KB scratch, unused by this kernel
-  MSSPE_CUDA_TRY(c, cudaMemsetAsync(A.barrier, 0, 4, st));
   A.mask_words = (uint32_t)div_up_u64(G, 32) + 1u;
   A.p_words = (c->max_partition + 32u) / 32u;
+  A.compact_min = 1u << 20;  // compaction passes cost ~0.3 ms of launches and syncs: not worth it for small streams
+  if (const char* e = getenv("MSSPE_COMPACT_MIN")) A.compact_min = (uint32_t)strtoul(e, nullptr, 10);
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[2], st));
+  ScoreStream cur[2] = {};
   for (int i = 0; i < ndirs; i++) {
     DirIndex& D = c->dir[dirs[i]];
     if (D.out_capacity < max_iter) {
@@ -584,12 +764,9 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
     MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.acc, 0, (uint64_t)(D.n_tiles + 1) * 8, st));
     int rc = msspe_select_prepare_stream(c, dirs[i], st);
     if (rc) return rc;
-    GreedyDir& g = A.d[i];
-    g.postings = D.s_postings; g.post_off = D.s_off; g.tile_first = D.s_tile_first; g.codes = D.codes; g.list_id = D.s_id;
-    g.n_codes = D.s_lists; g.n_post = D.s_list_post; g.n_tiles = D.s_tiles;
-    g.tail_t0 = D.s_tiles; g.tail_end = D.s_tiles * (uint32_t)CNT_TILE + ((uint32_t)D.n_records - D.s_list_post);
-    g.tail_t1 = (uint32_t)div_up_u64(g.tail_end, CNT_TILE);
-    g.ignored = D.ignored; g.freq = D.freq; g.acc = D.acc; g.cov = D.cov; g.ctl = D.ctl; g.out = D.out;
+    cur[i] = ScoreStream{D.s_postings, D.s_off, D.s_id, D.s_tile_first, D.s_lists, D.s_list_post, D.s_tiles,
+                         D.s_tiles * (uint32_t)CNT_TILE + ((uint32_t)D.n_records - D.s_list_post), false};
+    memset(&c->h_ctl[i], 0, sizeof(SelectCtl));
   }
   A.n_part = c->max_partition + 1u;
   A.n_fp = A.n_part <= 4096u ? A.n_part : 0u;
@@ -617,11 +794,46 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
   if (const char* e = getenv("MSSPE_PERSIST_BLOCKS_PER_SM")) want = atoi(e) > 0 ? atoi(e) : want;
   if (per_sm > want) per_sm = want;
   const unsigned grid = (unsigned)c->sm_count * (unsigned)per_sm;
-  void* kargs[] = {(void*)&A};
-  MSSPE_CUDA_TRY(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), kargs, smem, st));
-  c->timing.kernel_launches++;
-  for (int i = 0; i < ndirs; i++)
-    MSSPE_CUDA_TRY(c, cudaMemcpyAsync(&c->h_ctl[i], c->dir[dirs[i]].ctl, sizeof(SelectCtl), cudaMemcpyDeviceToHost, st));
+  uint32_t launches = 0, compactions = 0;
+  for (;;) {  // one launch per stretch between stream compactions
+    for (int i = 0; i < ndirs; i++) {
+      DirIndex& D = c->dir[dirs[i]];
+      GreedyDir& g = A.d[i];
+      const ScoreStream& S = cur[i];
+      g.postings = S.postings; g.post_off = S.off; g.tile_first = S.tile_first; g.codes = D.codes; g.list_id = S.id;
+      g.n_codes = S.lists; g.n_post = S.list_post; g.n_tiles = S.tiles;
+      g.tail_t0 = S.tiles; g.tail_end = S.tail_end; g.tail_t1 = (uint32_t)div_up_u64(S.tail_end, CNT_TILE);
+      g.stream_total = S.list_post + (S.tail_end - S.tiles * (uint32_t)CNT_TILE);
+      g.full_off = D.post_off; g.full_postings = D.postings;
+      g.done0 = c->h_ctl[i].done;
+      g.ignored = D.ignored; g.freq = D.freq; g.acc = D.acc; g.cov = D.cov; g.ctl = D.ctl; g.out = D.out;
+    }
+    MSSPE_CUDA_TRY(c, cudaMemsetAsync(A.barrier, 0, 4, st));
+    void* kargs[] = {(void*)&A};
+    MSSPE_CUDA_TRY(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), kargs, smem, st));
+    c->timing.kernel_launches++;
+    launches++;
+    for (int i = 0; i < ndirs; i++)
+      MSSPE_CUDA_TRY(c, cudaMemcpyAsync(&c->h_ctl[i], c->dir[dirs[i]].ctl, sizeof(SelectCtl), cudaMemcpyDeviceToHost, st));
+    MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+    bool resume = false;
+    uint32_t it0 = 0;
+    for (int i = 0; i < ndirs; i++)
+      if (!c->h_ctl[i].done && c->h_ctl[i].exit_compact) { resume = true; it0 = c->h_ctl[i].resume_it; }
+    if (!resume) break;
+    for (int i = 0; i < ndirs; i++) {
+      DirIndex& D = c->dir[dirs[i]];
+      if (c->h_ctl[i].done) continue;
+      int rc = compact_stream(c, D, cur[i], st);
+      if (rc) return rc;
+      // the per-iteration slots of the control block restart clean; everything cumulative stays
+      SelectCtl& h = c->h_ctl[i];
+      h.pg[0] = h.pg[1] = h.pt[0] = h.pt[1] = h.plive[0] = h.plive[1] = 0; h.pk[0] = h.pk[1] = 0ull; h.exit_compact = 0;
+      MSSPE_CUDA_TRY(c, cudaMemcpyAsync(D.ctl, &h, sizeof(SelectCtl), cudaMemcpyHostToDevice, st));
+    }
+    A.it0 = it0;
+    compactions++;
+  }
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
   MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
   float ms = 0.f;
@@ -634,18 +846,19 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
     c->timing.select_ms[d] = ms;
     c->timing.select_evals[d] = c->h_ctl[i].evals;
     c->timing.select_iterations[d] = c->h_ctl[i].iterations;
-    c->timing.select_postings_read[d] = (uint64_t)c->h_ctl[i].iterations * c->dir[d].n_records;  // lists + single-posting tail
+    c->timing.select_postings_read[d] = c->h_ctl[i].postings_read;  // lists + counted-only tail of the stream of each iteration
     c->timing.count_kernel_launches[d] = c->h_ctl[i].iterations;
     // phases of the two directions are interleaved inside one kernel: attribute the phase time once (to dir 0)
     c->timing.count_kernel_ms[d] = i == 0 ? (float)(c->h_ctl[i].t_count_ns * 1e-6) : 0.f;
     if (getenv("MSSPE_DEBUG_TIMERS") && i == 0)
-      fprintf(stderr, "[msspe] grid %u x %d, smem %zu B, smem_mask %d, ndirs %d\n", grid, threads, smem, (int)smem_mask, ndirs);
+      fprintf(stderr, "[msspe] grid %u x %d, smem %zu B, smem_mask %d, ndirs %d, launches %u (stream compactions %u)\n", grid, threads, smem, (int)smem_mask, ndirs, launches, compactions);
     if (getenv("MSSPE_DEBUG_TIMERS") && i == 0)
-      fprintf(stderr, "[msspe] persistent greedy: total %.3f ms, iterations %u | coverage-scoring phases %.3f ms, arg-max phases %.3f ms (block 0 clock, barriers included)\n",
-              c->h_ctl[i].t_total_ns * 1e-6, c->h_ctl[i].iterations, c->h_ctl[i].t_count_ns * 1e-6, c->h_ctl[i].t_tie_ns * 1e-6);
+      fprintf(stderr, "[msspe] persistent greedy: total %.3f ms (wall %.3f), iterations %u | coverage-scoring phases %.3f ms, arg-max phases %.3f ms (block 0 clock, barriers included)\n",
+              c->h_ctl[i].t_total_ns * 1e-6, ms, c->h_ctl[i].iterations, c->h_ctl[i].t_count_ns * 1e-6, c->h_ctl[i].t_tie_ns * 1e-6);
     if (getenv("MSSPE_DEBUG_TIMERS") && i == 0)
       fprintf(stderr, "[msspe]   worker block 1: phaseA work %.3f sync %.3f | phaseB work %.3f sync %.3f ms\n", c->h_ctl[i].t_dbg[4] * 1e-6,
               c->h_ctl[i].t_dbg[5] * 1e-6, c->h_ctl[i].t_dbg[6] * 1e-6, c->h_ctl[i].t_dbg[7] * 1e-6);
+    free_stream(c, cur[i]);
   }
   MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
   return MSSPE_OK;
