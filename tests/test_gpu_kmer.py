@@ -284,3 +284,24 @@ def test_ragged_record_lengths_use_the_search_path(oracle_lib):
     cov, part2, rec = eng.coverage([], [])
     assert part2.tolist() == part.tolist() and rec.max() == 8
     eng.close()
+
+
+@pytest.mark.parametrize("compact_min", ["1", "4096"])
+def test_stream_compaction_on_small_inputs(zika_fasta, oracle_lib, compact_min, monkeypatch):
+    """The persistent kernel leaves for a dead-posting compaction of its scoring stream when less than half of what it
+    streams is live.  By default only streams of >= 2^20 postings do (cfg2, cfg3); MSSPE_COMPACT_MIN=1 forces many
+    compactions on the small fixtures: the Zika alignment (incl. the partition_coverage of already covered postings,
+    main.rs:371-378, which the compacted stream no longer holds), random alignments with massive ties, a tie storm."""
+    import msspe_b200 as m
+    monkeypatch.setenv("MSSPE_COMPACT_MIN", compact_min)
+    cases = [(zika_fasta, 500, 250, 50, 13, 1000, 2), (_random_alignment(3, 64, 1000), 128, 64, 64, 5, 60, 2),
+             (_random_alignment(1, 40, 2000), 200, 100, 60, 9, 200, 1), (_random_alignment(7, 50, 3000, p=0.0, gaps=False), 500, 250, 50, 13, 40, 1)]
+    for fa, W, S, w, k, it, mms in cases:
+        recs, (bases, offs) = _fasta_to_arrays(fa)
+        eng = m.Engine(k, W, S, w)
+        eng.load_genomes(bases, offs)
+        eng.build_index()
+        _check_select(eng, oracle_lib, fa, W, S, w, k, it, mms, 0)
+        a, b = eng.select_both(it, mms, 0)          # both directions in one launch sequence; a second run on the same index
+        assert a.tobytes() == eng.select(0, it, mms, 0).tobytes() and b.tobytes() == eng.select(1, it, mms, 0).tobytes()
+        eng.close()
