@@ -48,6 +48,7 @@ struct DirIndex {
   uint32_t* s_off = nullptr;        // [s_lists + 1]
   uint32_t* s_id = nullptr;         // [s_lists] code id of each stream list
   uint32_t* s_tile_first = nullptr; // [s_tiles]
+  uint32_t* s_cost = nullptr;       // [tiles + 2] exclusive prefix of the tile costs (range balancing)
   uint32_t s_lists = 0, s_list_post = 0, s_tiles = 0;
 };
 

@@ -38,6 +38,19 @@ __global__ void tile_first_kernel(const uint32_t* __restrict__ post_off, uint32_
   tile_first[t] = lo;
 }
 
+// Cost of every tile of a scoring stream for the range balancing of the persistent kernel, in units of ~3 warp
+// instructions: a list tile costs a fixed part (gather, scan, first round of list lanes) plus a share per list that
+// starts in it (every 31 of them is another round); a tile of the counted-only tail is a gather and a popcount.
+__global__ void tile_cost_kernel(const uint32_t* __restrict__ tile_first, uint32_t list_tiles, uint32_t n_lists, uint32_t all_tiles,
+                                 uint32_t* __restrict__ cost) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > all_tiles) return;
+  uint32_t c = 0u;  // cost[all_tiles] = 0: the exclusive scan then ends with the total
+  if (t < list_tiles) c = 72u + ((t + 1u < list_tiles ? tile_first[t + 1u] : n_lists) - tile_first[t]);
+  else if (t < all_tiles) c = 60u;
+  cost[t] = c;
+}
+
 // ---- scoring stream (see DirIndex): lists with >= 2 postings in code order, single-posting lists as a tail ----
 __global__ void stream_flag_kernel(const uint32_t* __restrict__ post_off, uint32_t n_codes, uint32_t* __restrict__ multi,
                                    uint32_t* __restrict__ mlen) {
@@ -296,6 +309,7 @@ struct GreedyDir {
   uint32_t tail_t0, tail_t1, tail_end, stream_total;  // tiles / end of the counted-only tail; postings streamed per recount
   const uint32_t* full_off; const uint32_t* full_postings;  // the complete CSR: main.rs:371-378 walks ALL postings of a winner
   uint32_t done0, pad2;          // resumed launch: this direction had already finished
+  const uint32_t* cost_prefix;   // [tail_t1 + 1] exclusive prefix of the tile costs, cost_prefix[tail_t1] = total
   uint32_t* ignored; uint32_t* freq; unsigned long long* acc; uint32_t* cov; SelectCtl* ctl; msspe_candidate* out;
 };
 struct GreedyArgs {
@@ -351,13 +365,22 @@ __device__ __forceinline__ void apply_winner_global(const GreedyDir& D, const ui
 
 // The recount job of one warp for direction d (a literal at every call site).
 template <bool SMEM_MASK>
-__device__ __forceinline__ void make_job(CountJob& J, const GreedyArgs& A, const int d, uint32_t* smask, uint32_t gw, uint32_t nw, uint32_t c_first) {
+__device__ __forceinline__ void make_job(CountJob& J, const GreedyArgs& A, const int d, uint32_t* smask, uint32_t t_begin, uint32_t t_end, uint32_t c_first) {
   const GreedyDir& D = A.d[d];
   J.postings = D.postings; J.post_off = D.post_off; J.n_codes = D.n_codes; J.n_post = D.n_post;
   J.mask = SMEM_MASK ? smask + (size_t)d * A.mask_words : D.ignored; J.freq = D.freq; J.acc = D.acc;
-  count_job_range(J, D.n_tiles, gw, nw);
-  count_job_tail(J, D.tail_t0, D.tail_t1, D.tail_end, gw, nw);
+  J.t_begin = t_begin; J.t_end = t_end; J.list_tiles = D.n_tiles; J.tail_end = D.tail_end;
   J.c_first = c_first;
+}
+
+// First tile of warp gw's range when the tiles [0, n) are split over nw warps by cost: the first t whose prefix
+// reaches ceil(total * gw / nw).  Ranges of consecutive warps tile [0, n) without gaps; a range may be empty.
+__device__ __forceinline__ uint32_t balanced_begin(const uint32_t* __restrict__ P, uint32_t n, uint32_t gw, uint32_t nw) {
+  const unsigned long long total = P[n];
+  const uint32_t target = (uint32_t)((total * gw + nw - 1u) / nw);
+  uint32_t lo = 0, hi = n;  // answer in [lo, hi]; P[n] = total >= target
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(P + mid) >= target) hi = mid; else lo = mid + 1u; }
+  return lo;
 }
 
 template <bool SMEM_MASK, int THREADS>
@@ -395,7 +418,7 @@ greedy_persistent_kernel(const GreedyArgs A) {
   if (tid == 0) { s_evals[0] = 0ull; s_evals[1] = 0ull; s_live[0] = 0u; s_live[1] = 0u; }
   __syncthreads();
   // first k-mer of this warp's tile range; recomputed only when the set of running directions changes
-  __shared__ uint32_t s_cfirst[WARPS];
+  __shared__ uint32_t s_cfirst[WARPS], s_tb[WARPS], s_te[WARPS];  // this warp's cost-balanced tile range
   uint32_t cfirst_sig = 0xFFFFFFFFu;
   const bool lead = blockIdx.x == 0 && tid == 0;
   const bool wlead = blockIdx.x == (gridDim.x > 1 ? 1 : 0) && tid == 0;  // a worker block's clock (diagnostic)
@@ -426,19 +449,21 @@ greedy_persistent_kernel(const GreedyArgs A) {
       } else {
         myd = done[0] ? 1 : 0;
       }
-      if (sig != cfirst_sig) {
+      if (sig != cfirst_sig) {  // the ranges only change when a direction finishes
         cfirst_sig = sig;
         if (lane == 0) {
-          CountJob J;
-          count_job_range(J, A.d[myd].n_tiles, my_gw, my_nw);
-          s_cfirst[warp] = J.t_begin < J.t_end ? __ldg(A.d[myd].tile_first + J.t_begin) : 0u;
+          const GreedyDir& D = A.d[myd];
+          const uint32_t tb = balanced_begin(D.cost_prefix, D.tail_t1, my_gw, my_nw);
+          const uint32_t te = my_gw + 1u == my_nw ? D.tail_t1 : balanced_begin(D.cost_prefix, D.tail_t1, my_gw + 1u, my_nw);
+          s_tb[warp] = tb; s_te[warp] = te;
+          s_cfirst[warp] = tb < min(te, D.n_tiles) ? __ldg(D.tile_first + tb) : 0u;
         }
         __syncwarp();
       }
       // the two branches are the same code with the direction as a literal: the job's pointers then stay in the
       // kernel-parameter constant bank instead of occupying registers across the streaming loop
-      if (myd == 0) { CountJob J; make_job<SMEM_MASK>(J, A, 0, smask, my_gw, my_nw, s_cfirst[warp]); warp_count_begin(J, S, lane); }
-      else          { CountJob J; make_job<SMEM_MASK>(J, A, 1, smask, my_gw, my_nw, s_cfirst[warp]); warp_count_begin(J, S, lane); }
+      if (myd == 0) { CountJob J; make_job<SMEM_MASK>(J, A, 0, smask, s_tb[warp], s_te[warp], s_cfirst[warp]); warp_count_begin(J, S, lane); }
+      else          { CountJob J; make_job<SMEM_MASK>(J, A, 1, smask, s_tb[warp], s_te[warp], s_cfirst[warp]); warp_count_begin(J, S, lane); }
     }
     if (it > A.it0) {  // main.rs:371-378 for the previous winners (a direction that is not done has pushed one per iteration)
       for (int d = 0; d < A.ndirs; d++) {
@@ -456,8 +481,8 @@ greedy_persistent_kernel(const GreedyArgs A) {
     if (worker) {
       uint32_t mymax = 0;
       unsigned long long live;
-      if (myd == 0) { CountJob J; make_job<SMEM_MASK>(J, A, 0, smask, my_gw, my_nw, s_cfirst[warp]); live = warp_count_run<SMEM_MASK>(J, S, mymax, lane); }
-      else          { CountJob J; make_job<SMEM_MASK>(J, A, 1, smask, my_gw, my_nw, s_cfirst[warp]); live = warp_count_run<SMEM_MASK>(J, S, mymax, lane); }
+      if (myd == 0) { CountJob J; make_job<SMEM_MASK>(J, A, 0, smask, s_tb[warp], s_te[warp], s_cfirst[warp]); live = warp_count_run<SMEM_MASK>(J, S, mymax, lane); }
+      else          { CountJob J; make_job<SMEM_MASK>(J, A, 1, smask, s_tb[warp], s_te[warp], s_cfirst[warp]); live = warp_count_run<SMEM_MASK>(J, S, mymax, lane); }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
       if (lane == 0) { if (mymax) atomicMax(&s_max[myd], mymax); if (live) atomicAdd(&s_live[myd], (uint32_t)live); }
@@ -672,15 +697,24 @@ void launch_iteration(msspe_ctx* c, DirRun& r, uint32_t max_iter, uint32_t mms, 
 
 // The stream a direction currently scores: the pristine one of the index, or a compacted working copy.
 struct ScoreStream {
-  uint32_t* postings; uint32_t* off; uint32_t* id; uint32_t* tile_first;
+  uint32_t* postings; uint32_t* off; uint32_t* id; uint32_t* tile_first; uint32_t* cost;
   uint32_t lists, list_post, tiles, tail_end;
   bool owned;
 };
 
 void free_stream(msspe_ctx* c, ScoreStream& S) {
   if (!S.owned) return;
-  msspe_dev_free(c, S.postings); msspe_dev_free(c, S.off); msspe_dev_free(c, S.id); msspe_dev_free(c, S.tile_first);
+  msspe_dev_free(c, S.postings); msspe_dev_free(c, S.off); msspe_dev_free(c, S.id); msspe_dev_free(c, S.tile_first); msspe_dev_free(c, S.cost);
   S.owned = false;
+}
+
+// Exclusive prefix of the tile costs of a stream (list tiles, then tail tiles); entry [all_tiles] = total.
+int build_cost_prefix(msspe_ctx* c, const uint32_t* tile_first, uint32_t list_tiles, uint32_t n_lists, uint32_t tail_end, uint32_t** out, cudaStream_t st) {
+  const uint32_t all_tiles = (uint32_t)div_up_u64(tail_end, CNT_TILE) > list_tiles ? (uint32_t)div_up_u64(tail_end, CNT_TILE) : list_tiles;
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(out, ((uint64_t)all_tiles + 2) * 4, c->stream));
+  tile_cost_kernel<<<(all_tiles + 256u) / 256u, 256, 0, st>>>(tile_first, list_tiles, n_lists, all_tiles, *out);
+  c->timing.kernel_launches++;
+  return msspe_exclusive_scan_u32(c, *out, *out, (uint64_t)all_tiles + 1, nullptr, st);
 }
 
 // Drop the dead postings of a stream (order-preserving), given the current global bitmask of the direction.
@@ -733,6 +767,8 @@ int compact_stream(msspe_ctx* c, DirIndex& D, ScoreStream& S, cudaStream_t st) {
   for (uint32_t* p : {cnt, multi, mlen, single, d_tot}) MSSPE_CUDA_TRY(c, cudaFreeAsync(p, st));
   MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
   N.tail_end = n_tail_begin + tot[2] + tot[3];
+  int rc2 = build_cost_prefix(c, N.tile_first, N.tiles, N.lists, N.tail_end, &N.cost, st);
+  if (rc2) return rc2;
   free_stream(c, S);
   S = N;
   return MSSPE_OK;
@@ -764,7 +800,7 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
     MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.acc, 0, (uint64_t)(D.n_tiles + 1) * 8, st));
     int rc = msspe_select_prepare_stream(c, dirs[i], st);
     if (rc) return rc;
-    cur[i] = ScoreStream{D.s_postings, D.s_off, D.s_id, D.s_tile_first, D.s_lists, D.s_list_post, D.s_tiles,
+    cur[i] = ScoreStream{D.s_postings, D.s_off, D.s_id, D.s_tile_first, D.s_cost, D.s_lists, D.s_list_post, D.s_tiles,
                          D.s_tiles * (uint32_t)CNT_TILE + ((uint32_t)D.n_records - D.s_list_post), false};
     memset(&c->h_ctl[i], 0, sizeof(SelectCtl));
   }
@@ -804,7 +840,7 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
       g.n_codes = S.lists; g.n_post = S.list_post; g.n_tiles = S.tiles;
       g.tail_t0 = S.tiles; g.tail_end = S.tail_end; g.tail_t1 = (uint32_t)div_up_u64(S.tail_end, CNT_TILE);
       g.stream_total = S.list_post + (S.tail_end - S.tiles * (uint32_t)CNT_TILE);
-      g.full_off = D.post_off; g.full_postings = D.postings;
+      g.full_off = D.post_off; g.full_postings = D.postings; g.cost_prefix = S.cost;
       g.done0 = c->h_ctl[i].done;
       g.ignored = D.ignored; g.freq = D.freq; g.acc = D.acc; g.cov = D.cov; g.ctl = D.ctl; g.out = D.out;
     }
@@ -996,6 +1032,11 @@ int msspe_select_prepare_stream(msspe_ctx* c, int dir, cudaStream_t st) {
     c->timing.kernel_launches++;
   }
   MSSPE_CUDA_TRY(c, cudaGetLastError());
+  {
+    const uint32_t tail_end = D.s_tiles * (uint32_t)CNT_TILE + (R - D.s_list_post);
+    int rc = build_cost_prefix(c, D.s_tile_first, D.s_tiles, D.s_lists, tail_end, &D.s_cost, st);
+    if (rc) return rc;
+  }
   MSSPE_CUDA_TRY(c, cudaFreeAsync(multi, st));
   MSSPE_CUDA_TRY(c, cudaFreeAsync(mlen, st));
   MSSPE_CUDA_TRY(c, cudaFreeAsync(d_tot, st));

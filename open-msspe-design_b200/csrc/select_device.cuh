@@ -53,8 +53,6 @@ struct CountJob {
   uint32_t t_begin, t_end;   // this warp's contiguous tile range
   uint32_t list_tiles;       // tiles [0, list_tiles) hold lists; tiles from list_tiles on hold the counted-only tail
   uint32_t tail_end;         // end of the tail (postings); = n_post when there is no tail
-  uint32_t q_begin, q_end;   // this warp's tail tiles (processed after its list tiles)
-  uint32_t tiles_per_warp;   // T: every warp of the launch owns T consecutive tiles
   uint32_t c_first;          // k-mer whose list contains the first posting of the range (tile_first[t_begin])
   const uint32_t* mask; uint32_t* freq; unsigned long long* acc;
 };
@@ -72,8 +70,8 @@ __device__ __forceinline__ uint32_t list_start(const CountJob& J, uint32_t c) { 
 //   prefix at the (tile-clamped) start of its list with two shuffles and takes the prefix at the end of the list
 //   from lane l+1 (lane 31 only supplies that bound, which is why the window advances by 31).  A warp owns a
 //   contiguous range of tiles, so a list cut by a tile boundary inside the range is carried in a register
-//   (`carry` = its live postings so far); only lists that leave the range go through an arrival-counter|partial-sum
-//   word (acc[first range of the list]) and are completed by the last range to arrive.
+//   (`carry` = its live postings so far); only lists that leave the range go through a tiles-covered|partial-sum word
+//   (acc[first tile of the list]) and are completed by the range whose arrival covers the last missing tile.
 // Returns the live postings of the tile (uniform over the warp); mymax is per lane.
 // covered bits of the 16 postings of this lane: bit 16 + 4 j + e  <->  tile position 128 j + 4 lane + e
 template <bool SMEM_MASK>
@@ -119,7 +117,7 @@ __device__ __forceinline__ uint32_t warp_count_tile(uint32_t h, uint32_t wt, con
   const uint32_t b1 = tot & 0xFFu, b2 = b1 + ((tot >> 8) & 0xFFu), b3 = b2 + ((tot >> 16) & 0xFFu), live = b3 + (tot >> 24);
   const uint32_t b01 = b1 << 16, b23 = b2 | (b3 << 16);  // live postings before block j as 16-bit fields (block 0: none)
   const uint32_t range_lo = J.t_begin * (uint32_t)CNT_TILE;
-  const bool last_of_range = wt + 1u == J.t_end;
+  const bool last_of_range = wt + 1u == min(J.t_end, J.list_tiles);  // the last LIST tile of the range
   uint32_t outsum = 0;  // live postings so far of the list that continues into the next tile of the range
   for (;;) {
     // live postings of the tile before the start of this lane's list (list starts clamped into the tile), branch-free:
@@ -141,13 +139,14 @@ __device__ __forceinline__ uint32_t warp_count_tile(uint32_t h, uint32_t wt, con
       } else if (!ends_here && !last_of_range) {
         outsum = total;
       } else {  // the list leaves the range: the last arriving range owns the total
-        const uint32_t first_range = (W.pa / (uint32_t)CNT_TILE) / J.tiles_per_warp;
-        const uint32_t parts = ((pb - 1u) / (uint32_t)CNT_TILE) / J.tiles_per_warp - first_range + 1u;
-        const unsigned long long old = atomicAdd(&J.acc[first_range], (1ull << 32) | (unsigned long long)total);
-        if ((uint32_t)(old >> 32) + 1u == parts) {
+        // arrivals are counted in TILES of the list covered by the arriving range, so ranges of any shape work
+        const uint32_t t_a = W.pa / (uint32_t)CNT_TILE, t_b = (pb - 1u) / (uint32_t)CNT_TILE;
+        const uint32_t covered = min(t_b, J.t_end - 1u) - max(t_a, J.t_begin) + 1u;
+        const unsigned long long old = atomicAdd(&J.acc[t_a], ((unsigned long long)covered << 32) | (unsigned long long)total);
+        if ((uint32_t)(old >> 32) + covered == t_b - t_a + 1u) {
           const uint32_t sum = (uint32_t)old + total;
           J.freq[W.c0 + lane] = sum;
-          J.acc[first_range] = 0ull;
+          J.acc[t_a] = 0ull;
           mymax = max(mymax, sum);
         }
       }
@@ -170,20 +169,12 @@ struct RangeState {
   ListWindow W;
 };
 __device__ __forceinline__ uint32_t tile_bound(const CountJob& J, uint32_t wt) { return wt < J.list_tiles ? J.n_post : J.tail_end; }
-// i-th tile of this warp: its list tiles first, then its tail tiles
-__device__ __forceinline__ uint32_t my_tile(const CountJob& J, uint32_t i) {
-  const uint32_t nl = J.t_end - J.t_begin;
-  return i < nl ? J.t_begin + i : J.q_begin + (i - nl);
-}
-
 // the first loads of the range (postings of the first tile, three windows of list starts): nothing here depends on
 // the bitmask, so the caller can issue them before the mask update of the iteration
 __device__ __forceinline__ void warp_count_begin(const CountJob& J, RangeState& S, int lane) {
-  const uint32_t n_mine = (J.t_end - J.t_begin) + (J.q_end - J.q_begin);
-  if (n_mine == 0) return;
-  const uint32_t w0 = my_tile(J, 0);
-  tile_issue(S.A, w0, J.postings, tile_bound(J, w0), lane);
-  if (J.t_begin < J.t_end) {
+  if (J.t_begin >= J.t_end) return;
+  tile_issue(S.A, J.t_begin, J.postings, tile_bound(J, J.t_begin), lane);
+  if (J.t_begin < J.list_tiles) {
     S.W.c0 = J.c_first;
     S.W.pa = list_start(J, S.W.c0 + (uint32_t)lane);
     S.W.pa1 = list_start(J, S.W.c0 + 31u + (uint32_t)lane);
@@ -195,15 +186,12 @@ template <bool SMEM_MASK>
 __device__ __forceinline__ unsigned long long warp_count_run(const CountJob& J, RangeState& S, uint32_t& mymax, int lane) {
   unsigned long long live = 0;
   uint32_t carry = 0, tail_live = 0;
-  const uint32_t n_mine = (J.t_end - J.t_begin) + (J.q_end - J.q_begin);
-  for (uint32_t i = 0; i < n_mine; i++) {
-    const uint32_t wt = my_tile(J, i);
+  for (uint32_t wt = J.t_begin; wt < J.t_end; wt++) {
     const uint32_t h = tile_gather<SMEM_MASK>(S.A, J.mask);
-    if (i + 1u < n_mine) { const uint32_t w1 = my_tile(J, i + 1u); tile_issue(S.A, w1, J.postings, tile_bound(J, w1), lane); }
-    if (i + 2u < n_mine && lane < 16) {
-      const uint32_t w2 = my_tile(J, i + 2u);
-      const uint32_t q = w2 * (uint32_t)CNT_TILE + (uint32_t)lane * 32u;
-      if (q < tile_bound(J, w2)) asm volatile("prefetch.global.L2 [%0];" ::"l"(J.postings + q));
+    if (wt + 1u < J.t_end) tile_issue(S.A, wt + 1u, J.postings, tile_bound(J, wt + 1u), lane);
+    if (wt + 2u < J.t_end && lane < 16) {
+      const uint32_t q = (wt + 2u) * (uint32_t)CNT_TILE + (uint32_t)lane * 32u;
+      if (q < tile_bound(J, wt + 2u)) asm volatile("prefetch.global.L2 [%0];" ::"l"(J.postings + q));
     }
     if (wt < J.list_tiles) {
       live += warp_count_tile(h, wt, J, S.W, carry, mymax, lane);
@@ -214,7 +202,7 @@ __device__ __forceinline__ unsigned long long warp_count_run(const CountJob& J, 
       tail_live += (uint32_t)__popc(nibs);
     }
   }
-  if (J.q_end > J.q_begin) live += __reduce_add_sync(0xffffffffu, tail_live);
+  if (J.t_end > J.list_tiles) live += __reduce_add_sync(0xffffffffu, tail_live);
   return live;
 }
 
@@ -225,21 +213,13 @@ __device__ __forceinline__ unsigned long long warp_count_range(const CountJob& J
   return warp_count_run<SMEM_MASK>(J, S, mymax, lane);
 }
 
-// Tile range of warp `gw` out of `n_warps`: T = ceil(n_tiles / n_warps) consecutive tiles per warp.
+// Tile range of warp `gw` out of `n_warps`, equal tile counts: T = ceil(n_tiles / n_warps) consecutive tiles per warp
+// (stand-alone count kernel; the persistent kernel balances its ranges by cost, select.cu).
 __device__ __forceinline__ void count_job_range(CountJob& J, uint32_t n_tiles, uint32_t gw, uint32_t n_warps) {
-  const uint32_t T = (n_tiles + n_warps - 1u) / n_warps;
-  J.tiles_per_warp = T ? T : 1u;
-  J.t_begin = min(n_tiles, gw * J.tiles_per_warp);
-  J.t_end = min(n_tiles, J.t_begin + J.tiles_per_warp);
-  J.list_tiles = n_tiles; J.q_begin = J.q_end = 0u;  // no tail unless count_job_tail says otherwise
-}
-// Tail tiles [tail_t0, tail_t1) spread evenly over the warps, the last warps first (the first warps may carry one
-// list tile more than the last ones).
-__device__ __forceinline__ void count_job_tail(CountJob& J, uint32_t tail_t0, uint32_t tail_t1, uint32_t tail_end, uint32_t gw, uint32_t n_warps) {
-  const uint32_t n = tail_t1 - tail_t0, T = (n + n_warps - 1u) / n_warps, r = n_warps - 1u - gw;
-  J.tail_end = tail_end;
-  J.q_begin = min(tail_t1, tail_t0 + r * T);
-  J.q_end = min(tail_t1, J.q_begin + T);
+  const uint32_t T = max((n_tiles + n_warps - 1u) / n_warps, 1u);
+  J.t_begin = min(n_tiles, gw * T);
+  J.t_end = min(n_tiles, J.t_begin + T);
+  J.list_tiles = n_tiles;
 }
 
 // Warp-cooperative partition_tie_score (main.rs:261-283) of code c.  `seen` = this warp's partition bitmap.
