@@ -6,6 +6,7 @@
 // 5-line ntthal parser's bookkeeping (delta_g.rs:27-59), the conflict-graph vertex cover (main.rs:754-815).
 // There is no CPU fallback: without a usable CUDA device the program exits with an error.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -48,7 +49,12 @@ struct Args {  // config.rs:11-148 with constants.rs defaults
   exit(101);
 }
 bool log_enabled() { static int v = -1; if (v < 0) v = (getenv("RUST_LOG") || getenv("MSSPE_LOG")) ? 1 : 0; return v == 1; }
-void log_info(const std::string& m) { if (log_enabled()) std::cerr << "[INFO  od_msspe] " << m << "\n"; }
+double elapsed_s() { static const auto t0 = std::chrono::steady_clock::now(); return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+void log_info(const std::string& m) {  // env_logger prints a wall-clock stamp here; the elapsed time is more useful for a pipeline
+  if (!log_enabled()) return;
+  char b[32]; snprintf(b, sizeof b, "%8.3fs", elapsed_s());
+  std::cerr << "[" << b << " INFO  od_msspe] " << m << "\n";
+}
 
 struct Opt { const char* flag; const char* env; int kind; void* dst; };  // kind: 0 u64, 1 f32, 2 bool-string, 3 string, 4 optional u64
 
@@ -202,6 +208,7 @@ std::vector<KmerStat> filter_kmers(const std::vector<KmerStat>& st) {
 }  // namespace
 
 int main(int argc, char** argv) {
+  elapsed_s();
   Args a = parse_args(argc, argv);
   if (a.do_align == "true") {
     std::cerr << "od-msspe (B200 engine): MAFFT alignment is out of scope of this engine; align the input first and pass --do-align=false\n";
@@ -231,6 +238,7 @@ int main(int argc, char** argv) {
   msspe_config cfg{(uint32_t)a.kmer_size, (uint32_t)a.window_size, (uint32_t)a.overlap_size, (uint32_t)a.search_windows_size,
                    getenv("MSSPE_DEVICE") ? atoi(getenv("MSSPE_DEVICE")) : 0, 0};
   if (int rc = msspe_create(&cfg, &ctx)) { std::cerr << "od-msspe: cannot start the GPU engine (" << rc << "): " << msspe_last_error(nullptr) << "\n"; return 1; }
+  log_info("GPU engine ready");
   // 1. to_records (main.rs:108-122) + upload: multi-threaded parse into pinned memory, chunked copies overlap the parse
   msspe_fasta* fasta = nullptr;
   if (int rc = msspe_load_fasta(ctx, a.input.c_str(), getenv("MSSPE_THREADS") ? (uint32_t)atoi(getenv("MSSPE_THREADS")) : 0u, &fasta)) {
@@ -252,7 +260,7 @@ int main(int argc, char** argv) {
     delete p;
   }
   // 2. segments + inverted index (get_segment_manager, main.rs:693)
-  log_info("Extracting n-grams from each sequence segments...");
+  log_info("Read " + std::to_string(records.size()) + " sequences; extracting n-grams from each sequence segments...");
   CHECK(msspe_build_index(ctx));
   uint64_t G = 0; uint32_t maxp = 0, slots = 0;
   CHECK(msspe_segment_info(ctx, &G, &maxp, &slots));
@@ -367,7 +375,7 @@ int main(int argc, char** argv) {
     if (!any) printf("  All partitions have primer coverage\n"); else printf("  Uncovered partitions: [%s]\n", unc.c_str());
   }
   // 6. CSV (main.rs:836-857)
-  log_info("Outputting primers...");
+  log_info("Coverage report done; outputting primers...");
   std::ofstream out(a.output, std::ios::binary);
   if (!out) { std::cerr << "Error: cannot create " << a.output << "\n"; return 1; }
   out << "direction,name,primers,gc,avg,std,tm\n";
