@@ -320,6 +320,7 @@ struct GreedyArgs {
   uint32_t n_part;   // max partition_no + 1
   uint32_t n_fp;     // entries of the block-cooperative tie-score scratch (n_part, or 0 = too many partitions)
   const uint16_t* seg_part;
+  uint32_t uniform_parts;  // > 0: every record has this many partitions, partition_no = segment % uniform_parts (no table lookup)
   unsigned int* barrier;  // grid barrier arrival counter (zeroed before the launch)
 };
 
@@ -347,19 +348,19 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // compacted stream no longer holds, hence the complete CSR) is marked in the global bitmask, and every distinct
 // partition among them gets partition_coverage += 1.  pm = shared-memory partition bitmap, left zeroed.
 template <int THREADS>
-__device__ __forceinline__ void apply_winner_global(const GreedyDir& D, const uint16_t* __restrict__ seg_part, uint32_t code_id, uint32_t* pm) {
+__device__ __forceinline__ void apply_winner_global(const GreedyDir& D, const uint16_t* __restrict__ seg_part, uint32_t uniform_parts, uint32_t code_id, uint32_t* pm) {
   const int tid = threadIdx.x;
   const uint32_t a = D.full_off[code_id], b = D.full_off[code_id + 1];
   for (uint32_t i = a + tid; i < b; i += THREADS) {
     const uint32_t sg = __ldg(D.full_postings + i);
     atomicOr(&D.ignored[sg >> 5], 1u << (sg & 31u));
-    const uint32_t p = seg_part[sg];
+    const uint32_t p = partition_of(seg_part, uniform_parts, sg);
     const uint32_t pbit = 1u << (p & 31u);
     const uint32_t old = atomicOr(&pm[p >> 5], pbit);
     if (!(old & pbit)) atomicAdd(&D.cov[p], 1u);
   }
   __syncthreads();
-  for (uint32_t i = a + tid; i < b; i += THREADS) pm[seg_part[__ldg(D.full_postings + i)] >> 5] = 0u;
+  for (uint32_t i = a + tid; i < b; i += THREADS) pm[partition_of(seg_part, uniform_parts, __ldg(D.full_postings + i)) >> 5] = 0u;
   __syncthreads();
 }
 
@@ -388,22 +389,23 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2)
 greedy_persistent_kernel(const GreedyArgs A) {
   extern __shared__ __align__(16) unsigned char dsm[];
   unsigned int bar_target = 0;
-  __shared__ uint32_t s_tied[THREADS];
-  __shared__ uint32_t s_cnt, s_sc[2], s_max[2];
+  __shared__ uint32_t s_tied[2 * THREADS];
+  __shared__ uint32_t s_cnt2[2], s_sc[2], s_max[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int WARPS = THREADS / 32;
-  // dynamic smem: [masks ndirs*mask_words] [pm p_words] [seen p_words] [fp n_fp] [lst n_fp (u64)]
+  // dynamic smem: [masks ndirs*mask_words] [pm p_words] [seen p_words] [fp n_fp] [lst n_fp (u64)] [cov 2*n_fp]
   uint32_t* smask = reinterpret_cast<uint32_t*>(dsm);
   uint32_t* pm = smask + (SMEM_MASK ? (size_t)A.ndirs * A.mask_words : 0);
   uint32_t* seen = pm + A.p_words;
   uint32_t* fp = seen + A.p_words;
   unsigned long long* lst = reinterpret_cast<unsigned long long*>(
       dsm + (((size_t)(reinterpret_cast<unsigned char*>(fp + A.n_fp) - dsm) + 7) & ~(size_t)7));
+  uint32_t* s_cov = reinterpret_cast<uint32_t*>(lst + A.n_fp);  // [2][n_fp] this iteration's partition_coverage
   if (SMEM_MASK)  // the global bitmask is all zero at the first launch and current at a resumed one
     for (int d = 0; d < A.ndirs; d++)
       for (uint32_t i = tid; i < A.mask_words; i += THREADS) smask[(size_t)d * A.mask_words + i] = __ldcg(A.d[d].ignored + i);
   for (uint32_t i = tid; i < A.p_words; i += THREADS) pm[i] = 0u;
-  if (tid == 0) { s_cnt = 0u; s_max[0] = 0u; s_max[1] = 0u; }
+  if (tid == 0) { s_cnt2[0] = 0u; s_cnt2[1] = 0u; s_max[0] = 0u; s_max[1] = 0u; }
   __syncthreads();
   // block 0 keeps the global state (bitmask, partition_coverage, output); the other blocks score tiles
   const bool solo = gridDim.x == 1;
@@ -473,7 +475,7 @@ greedy_persistent_kernel(const GreedyArgs A) {
         const uint32_t a = D.post_off[s_win[d]], b = D.post_off[s_win[d] + 1];  // live part is enough for the bitmask
         if (SMEM_MASK)
           for (uint32_t i = a + tid; i < b; i += THREADS) { const uint32_t sg = __ldg(D.postings + i); atomicOr(&mask[sg >> 5], 1u << (sg & 31u)); }
-        if (blockIdx.x == 0) apply_winner_global<THREADS>(D, A.seg_part, D.list_id[s_win[d]], pm);
+        if (blockIdx.x == 0) apply_winner_global<THREADS>(D, A.seg_part, A.uniform_parts, D.list_id[s_win[d]], pm);
       }
       __syncthreads();
       if (!SMEM_MASK) grid_barrier(A.barrier, bar_target);  // the workers read the global bitmask block 0 has just updated
@@ -500,10 +502,29 @@ greedy_persistent_kernel(const GreedyArgs A) {
     if (wlead) { const unsigned long long t = globaltimer_ns(); s_tm[9] += t - s_tm[5]; s_tm[5] = t; }
     if (lead) { s_tm[2] = globaltimer_ns(); s_tm[3] += s_tm[2] - s_tm[1]; }
     // ---------------- phase B ----------------
+    // Both directions at once: the maxima, this block's slice of both freq[] arrays and both partition_coverage
+    // tables are requested before anything is waited for (one L2 round trip instead of one per direction and step).
+    uint32_t gd[2] = {0u, 0u};
+    for (int d = 0; d < A.ndirs; d++)
+      if (!done[d]) gd[d] = __ldcg(&A.d[d].ctl->pg[par]);
+    if (A.n_fp)  // partition_coverage of this iteration (block 0 finished updating it before the barrier)
+      for (int d = 0; d < A.ndirs; d++)
+        if (!done[d]) for (uint32_t q = tid; q < A.n_part; q += THREADS) s_cov[(size_t)d * A.n_fp + q] = __ldcg(A.d[d].cov + q);
+    uint32_t f_first[2][2];
+    {
+      const uint32_t stride = gridDim.x * THREADS, c = blockIdx.x * THREADS + tid;
+#pragma unroll
+      for (int d = 0; d < 2; d++)
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          const uint32_t cc = c + (uint32_t)q * stride;
+          f_first[d][q] = (d < A.ndirs && !done[d] && cc < A.d[d].n_codes) ? __ldcg(A.d[d].freq + cc) : 0u;  // a maximum is >= 2
+        }
+    }
     for (int d = 0; d < A.ndirs; d++) {
       if (done[d]) continue;
       const GreedyDir& D = A.d[d];
-      const uint32_t g = __ldcg(&D.ctl->pg[par]);
+      const uint32_t g = gd[d];
       s_gsave[d] = g;
       if (lead) { D.ctl->pg[par ^ 1] = 0; D.ctl->pt[par ^ 1] = 0; D.ctl->pk[par ^ 1] = 0ull; D.ctl->plive[par ^ 1] = 0; D.ctl->postings_read += D.stream_total; }  // next iteration's slots
       if (g <= 1u) {  // None or freq == 1: stop before the push (main.rs:353-366)
@@ -511,25 +532,28 @@ greedy_persistent_kernel(const GreedyArgs A) {
         if (lead) { D.ctl->iterations = it + 1; D.ctl->n_out = it; D.ctl->done = 1; }
         continue;
       }
-      const uint32_t* mask = SMEM_MASK ? smask + (size_t)d * A.mask_words : D.ignored;
-      // collect this block's k-mers at the maximum: grid-stride scan of freq[] with four independent loads in flight
+      // collect this block's k-mers at the maximum (grid-stride over freq[]; the first two strides are already here)
+      uint32_t* tied = s_tied + d * THREADS;
       {
         const uint32_t stride = gridDim.x * THREADS;
         uint32_t c = blockIdx.x * THREADS + tid;
-        for (; c + 3u * stride < D.n_codes; c += 4u * stride) {
-          const uint32_t f0 = __ldcg(D.freq + c), f1 = __ldcg(D.freq + c + stride), f2 = __ldcg(D.freq + c + 2u * stride), f3 = __ldcg(D.freq + c + 3u * stride);
-          if (f0 == g) { const uint32_t q = atomicAdd(&s_cnt, 1u); if (q < (uint32_t)THREADS) s_tied[q] = c; }
-          if (f1 == g) { const uint32_t q = atomicAdd(&s_cnt, 1u); if (q < (uint32_t)THREADS) s_tied[q] = c + stride; }
-          if (f2 == g) { const uint32_t q = atomicAdd(&s_cnt, 1u); if (q < (uint32_t)THREADS) s_tied[q] = c + 2u * stride; }
-          if (f3 == g) { const uint32_t q = atomicAdd(&s_cnt, 1u); if (q < (uint32_t)THREADS) s_tied[q] = c + 3u * stride; }
-        }
-        for (; c < D.n_codes; c += stride)
-          if (__ldcg(D.freq + c) == g) { const uint32_t q = atomicAdd(&s_cnt, 1u); if (q < (uint32_t)THREADS) s_tied[q] = c; }
+        if (f_first[d][0] == g) { const uint32_t q = atomicAdd(&s_cnt2[d], 1u); if (q < (uint32_t)THREADS) tied[q] = c; }
+        if (f_first[d][1] == g) { const uint32_t q = atomicAdd(&s_cnt2[d], 1u); if (q < (uint32_t)THREADS) tied[q] = c + stride; }
+        for (c += 2u * stride; c < D.n_codes; c += stride)
+          if (__ldcg(D.freq + c) == g) { const uint32_t q = atomicAdd(&s_cnt2[d], 1u); if (q < (uint32_t)THREADS) tied[q] = c; }
       }
+    }
+    __syncthreads();
+    for (int d = 0; d < A.ndirs; d++) {
+      if (done[d]) continue;
+      const GreedyDir& D = A.d[d];
+      const uint32_t g = gd[d];
+      const uint32_t* mask = SMEM_MASK ? smask + (size_t)d * A.mask_words : D.ignored;
+      const uint32_t* covp = A.n_fp ? s_cov + (size_t)d * A.n_fp : D.cov;
+      uint32_t* tied = s_tied + d * THREADS;
+      const uint32_t n_here = s_cnt2[d];
       __syncthreads();
-      const uint32_t n_here = s_cnt;
-      __syncthreads();
-      if (tid == 0) s_cnt = 0u;
+      if (tid == 0) s_cnt2[d] = 0u;
       // the usual case: the block's ties fit the list; otherwise (tie storms) re-collect them chunk by chunk
       const uint32_t n_chunks = n_here <= (uint32_t)THREADS ? 1u : (D.n_codes + gridDim.x * THREADS - 1u) / (gridDim.x * THREADS);
       for (uint32_t chunk = 0; chunk < n_chunks; chunk++) {
@@ -537,17 +561,17 @@ greedy_persistent_kernel(const GreedyArgs A) {
         if (n_here > (uint32_t)THREADS) {
           __syncthreads();
           const uint32_t c = (chunk * gridDim.x + blockIdx.x) * THREADS + tid;
-          if (c < D.n_codes && __ldcg(D.freq + c) == g) s_tied[atomicAdd(&s_cnt, 1u)] = c;
+          if (c < D.n_codes && __ldcg(D.freq + c) == g) tied[atomicAdd(&s_cnt2[d], 1u)] = c;
           __syncthreads();
-          nt = s_cnt;
+          nt = s_cnt2[d];
           __syncthreads();
-          if (tid == 0) s_cnt = 0u;
+          if (tid == 0) s_cnt2[d] = 0u;
         }
         for (uint32_t t = 0; t < nt; t++) {
-          const uint32_t cc = s_tied[t];
+          const uint32_t cc = tied[t];
           float score;
           if (A.n_fp) {
-            score = block_tie_score<SMEM_MASK, true, THREADS>(cc, D.post_off, D.postings, mask, A.seg_part, D.cov, A.n_part, fp, lst, s_sc);
+            score = block_tie_score<SMEM_MASK, false, THREADS>(cc, D.post_off, D.postings, mask, A.seg_part, A.uniform_parts, covp, A.n_part, fp, lst, s_sc);
           } else {  // more partitions than the shared-memory scratch holds: one warp, bitmap of seen partitions
             if (warp == 0) {
               const float sw = warp_tie_score<SMEM_MASK, true>(cc, D.post_off, D.postings, mask, A.seg_part, D.cov, seen, A.p_words, lane);
@@ -595,7 +619,7 @@ greedy_persistent_kernel(const GreedyArgs A) {
       if (leave) {
         for (int d = 0; d < A.ndirs; d++) {
           if (done[d]) continue;
-          if (blockIdx.x == 0) apply_winner_global<THREADS>(A.d[d], A.seg_part, A.d[d].list_id[s_win[d]], pm);  // nothing stays pending
+          if (blockIdx.x == 0) apply_winner_global<THREADS>(A.d[d], A.seg_part, A.uniform_parts, A.d[d].list_id[s_win[d]], pm);  // nothing stays pending
           if (lead) { A.d[d].ctl->resume_it = it + 1u; A.d[d].ctl->exit_compact = 1u; }
         }
         break;
@@ -780,6 +804,7 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
   const uint64_t G = c->n_segments;
   GreedyArgs A{};
   A.ndirs = ndirs; A.max_iter = max_iter; A.mms = mms; A.seg_part = c->d_seg_part;
+  A.uniform_parts = (c->uniform_parts && c->uniform_parts <= 65536u) ? c->uniform_parts : 0u;
   A.barrier = c->dir[dirs[0]].pmark;  // 8 KB scratch, unused by this kernel
   A.mask_words = (uint32_t)div_up_u64(G, 32) + 1u;
   A.p_words = (c->max_partition + 32u) / 32u;
@@ -806,7 +831,7 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
   }
   A.n_part = c->max_partition + 1u;
   A.n_fp = A.n_part <= 4096u ? A.n_part : 0u;
-  const size_t aux = (size_t)2 * A.p_words * 4 + (size_t)A.n_fp * 4 + (size_t)A.n_fp * 8 + 16;  // pm, seen, fp, lst
+  const size_t aux = (size_t)2 * A.p_words * 4 + (size_t)A.n_fp * 4 + (size_t)A.n_fp * 8 + (size_t)2 * A.n_fp * 4 + 16;  // pm, seen, fp, lst, cov
   const size_t mask_bytes = (size_t)ndirs * A.mask_words * 4;
   const bool smem_mask = mask_bytes + aux + (size_t)4096 + 1024 <= c->smem_optin;
   const size_t smem = aux + (smem_mask ? mask_bytes : 0);

@@ -265,10 +265,17 @@ __device__ __forceinline__ float warp_tie_score(uint32_t c, const uint32_t* __re
 // thread looks at its share of the postings at once and records, per partition, the position of the first live
 // posting (atomicMin); the distinct partitions are then ordered by that position and the f32 terms are added
 // sequentially in that order -- the same order, hence the same rounding, as the scan of main.rs:268-281.
-// fp[n_part] u32 and lst[n_part] u64 are shared-memory scratch; sc = {count, score bits}.
+// fp[n_part] u32 and lst[n_part] u64 are shared-memory scratch; sc = {count, score bits}.  COHERENT: cov is the global
+// table (written by block 0 inside this launch) rather than the block's shared-memory copy of this iteration.
+// Segment.partition_no (main.rs:227) of segment `seg`: its index inside its record when all records have equally
+// many partitions (pre-aligned, equal-length genomes: no table lookup), else from the table.
+__device__ __forceinline__ uint32_t partition_of(const uint16_t* __restrict__ seg_part, uint32_t uniform_parts, uint32_t seg) {
+  return uniform_parts ? seg % uniform_parts : (uint32_t)seg_part[seg];
+}
+
 template <bool SMEM_MASK, bool COHERENT, int THREADS>
 __device__ __forceinline__ float block_tie_score(uint32_t c, const uint32_t* __restrict__ post_off, const uint32_t* __restrict__ postings,
-                                                 const uint32_t* mask, const uint16_t* __restrict__ seg_part, const uint32_t* cov,
+                                                 const uint32_t* mask, const uint16_t* __restrict__ seg_part, uint32_t uniform_parts, const uint32_t* cov,
                                                  uint32_t n_part, uint32_t* fp, unsigned long long* lst, uint32_t* sc) {
   const int tid = threadIdx.x;
   for (uint32_t p = tid; p < n_part; p += THREADS) fp[p] = 0xFFFFFFFFu;
@@ -277,8 +284,8 @@ __device__ __forceinline__ float block_tie_score(uint32_t c, const uint32_t* __r
   const uint32_t a = post_off[c], b = post_off[c + 1];
   for (uint32_t i = a + tid; i < b; i += THREADS) {
     const uint32_t seg = __ldg(postings + i);
-    const uint32_t mw = SMEM_MASK ? mask[seg >> 5] : (COHERENT ? __ldcg(mask + (seg >> 5)) : mask[seg >> 5]);
-    if (!((mw >> (seg & 31u)) & 1u)) atomicMin(&fp[seg_part[seg]], i);
+    const uint32_t mw = SMEM_MASK ? mask[seg >> 5] : __ldcg(mask + (seg >> 5));  // the global bitmask is written inside this launch
+    if (!((mw >> (seg & 31u)) & 1u)) atomicMin(&fp[partition_of(seg_part, uniform_parts, seg)], i);
   }
   __syncthreads();
   for (uint32_t p = tid; p < n_part; p += THREADS) {
