@@ -181,10 +181,8 @@ def main():
             eng.load_genomes(host_pinned.numpy(), offs)
         eng.build_index()
         fwd, rev = eng.select_both(MAX_ITER, mms, mode)
-        kept = []
-        for cand in (fwd, rev):   # get_kmer_stats + filter_kmers (main.rs:408-516) through the C ABI
-            st = eng.kmer_stats(cand["code"], fcfg)
-            kept.append(st["code"][st["keep"] != 0])
+        # get_kmer_stats + filter_kmers for both directions (main.rs:723-732, 408-516) through the C ABI, one device batch
+        kept = [st["code"][st["keep"] != 0] for st in eng.kmer_stats_both(fwd["code"], rev["code"], fcfg)]
         t = eng.timing()
         return int(t.select_evals[0] + t.select_evals[1]), fwd, rev, kept, t
 

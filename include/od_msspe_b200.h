@@ -259,6 +259,11 @@ typedef struct {
 int msspe_kmer_stats(msspe_ctx* ctx, const uint64_t* codes, uint32_t n, uint32_t oligo_len, const msspe_filter_cfg* cfg,
                      msspe_kmer_stat* out);
 
+/* The two get_kmer_stats calls of main.rs:723-724 at once: one device batch for the candidates of both directions,
+ * per-direction statistics and verdicts identical to two msspe_kmer_stats calls. */
+int msspe_kmer_stats_both(msspe_ctx* ctx, const uint64_t* fwd_codes, uint32_t n_fwd, const uint64_t* rev_codes, uint32_t n_rev,
+                          uint32_t oligo_len, const msspe_filter_cfg* cfg, msspe_kmer_stat* out_fwd, msspe_kmer_stat* out_rev);
+
 /* Arbitrary pair list through thal (type = MSSPE_THAL_*); a[i], b[i] are 2-bit codes of length oligo_len.
  * For HAIRPIN b is ignored.  One ntthal invocation per pair in the reference (delta_g.rs:93-113). */
 int msspe_thal_pairs(msspe_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t n_pairs, uint32_t oligo_len,

@@ -15,14 +15,11 @@ float via_text(double v, const char* fmt) {  // Primer3 prints, parse_primer3_ou
 }
 }  // namespace
 
-extern "C" int msspe_kmer_stats(msspe_ctx* c, const uint64_t* codes, uint32_t n, uint32_t oligo_len, const msspe_filter_cfg* cfg,
-                                msspe_kmer_stat* out) {
-  if (!c) return MSSPE_ERR_INVALID;
-  if (!cfg || (n && (!codes || !out))) { c->set_error("msspe_kmer_stats: null argument"); return MSSPE_ERR_INVALID; }
-  if (n == 0) return MSSPE_OK;
-  std::vector<double> tm(n), gc(n), sa(n), se(n), hp(n);
-  int rc = msspe_primer_thermo(c, codes, n, oligo_len, tm.data(), gc.data(), sa.data(), se.data(), hp.data());
-  if (rc) return rc;
+namespace {
+// Everything after the device numbers, for the candidates of ONE direction (statistics are per direction).
+void stats_of_direction(const uint64_t* codes, uint32_t n, uint32_t oligo_len, const msspe_filter_cfg* cfg, const double* tm, const double* gc,
+                        const double* sa, const double* se, const double* hp, msspe_kmer_stat* out) {
+  if (n == 0) return;
   for (uint32_t i = 0; i < n; i++) {
     msspe_kmer_stat& s = out[i];
     s.code = codes[i];
@@ -60,5 +57,36 @@ extern "C" int msspe_kmer_stats(msspe_ctx* c, const uint64_t* codes, uint32_t n,
     s.keep = (p_any && p_end && p_hp && p_mm && p_sd && !s.runs) ? 1 : 0;
     s.reserved = 0;
   }
+}
+}  // namespace
+
+extern "C" int msspe_kmer_stats(msspe_ctx* c, const uint64_t* codes, uint32_t n, uint32_t oligo_len, const msspe_filter_cfg* cfg,
+                                msspe_kmer_stat* out) {
+  if (!c) return MSSPE_ERR_INVALID;
+  if (!cfg || (n && (!codes || !out))) { c->set_error("msspe_kmer_stats: null argument"); return MSSPE_ERR_INVALID; }
+  if (n == 0) return MSSPE_OK;
+  std::vector<double> tm(n), gc(n), sa(n), se(n), hp(n);
+  int rc = msspe_primer_thermo(c, codes, n, oligo_len, tm.data(), gc.data(), sa.data(), se.data(), hp.data());
+  if (rc) return rc;
+  stats_of_direction(codes, n, oligo_len, cfg, tm.data(), gc.data(), sa.data(), se.data(), hp.data(), out);
+  return MSSPE_OK;
+}
+
+// Both directions (main.rs:723-724 calls get_kmer_stats twice): ONE device batch for all candidates, then the
+// per-direction statistics and verdicts exactly as two msspe_kmer_stats calls would give them.
+extern "C" int msspe_kmer_stats_both(msspe_ctx* c, const uint64_t* fwd_codes, uint32_t n_fwd, const uint64_t* rev_codes, uint32_t n_rev,
+                                     uint32_t oligo_len, const msspe_filter_cfg* cfg, msspe_kmer_stat* out_fwd, msspe_kmer_stat* out_rev) {
+  if (!c) return MSSPE_ERR_INVALID;
+  if (!cfg || (n_fwd && (!fwd_codes || !out_fwd)) || (n_rev && (!rev_codes || !out_rev))) { c->set_error("msspe_kmer_stats_both: null argument"); return MSSPE_ERR_INVALID; }
+  const uint32_t n = n_fwd + n_rev;
+  if (n == 0) return MSSPE_OK;
+  std::vector<uint64_t> codes(n);
+  for (uint32_t i = 0; i < n_fwd; i++) codes[i] = fwd_codes[i];
+  for (uint32_t i = 0; i < n_rev; i++) codes[n_fwd + i] = rev_codes[i];
+  std::vector<double> tm(n), gc(n), sa(n), se(n), hp(n);
+  int rc = msspe_primer_thermo(c, codes.data(), n, oligo_len, tm.data(), gc.data(), sa.data(), se.data(), hp.data());
+  if (rc) return rc;
+  stats_of_direction(fwd_codes, n_fwd, oligo_len, cfg, tm.data(), gc.data(), sa.data(), se.data(), hp.data(), out_fwd);
+  stats_of_direction(rev_codes, n_rev, oligo_len, cfg, tm.data() + n_fwd, gc.data() + n_fwd, sa.data() + n_fwd, se.data() + n_fwd, hp.data() + n_fwd, out_rev);
   return MSSPE_OK;
 }

@@ -177,26 +177,31 @@ struct KmerStat { uint64_t code; std::string word; uint8_t direction; float gc_p
 
 #define CHECK(call) do { int rc_ = (call); if (rc_ != MSSPE_OK) { std::cerr << "od-msspe: " #call " failed (" << rc_ << "): " << msspe_last_error(ctx) << "\n"; exit(1); } } while (0)
 
-// get_kmer_stats + filter_kmers (main.rs:408-516) through the ABI: msspe_kmer_stats does the device thermodynamics and
-// the reference's text round trips / f32 statistics / strict comparisons.
-std::vector<KmerStat> kmer_stats(msspe_ctx* ctx, const std::vector<msspe_candidate>& cand, uint8_t dir, unsigned k, const Args& a) {
-  const uint32_t n = (uint32_t)cand.size();
-  std::vector<uint64_t> codes(n);
-  for (uint32_t i = 0; i < n; i++) codes[i] = cand[i].code;
+// get_kmer_stats + filter_kmers (main.rs:408-516) for both directions through the ABI: msspe_kmer_stats_both does the
+// device thermodynamics in one batch and the reference's text round trips / f32 statistics / strict comparisons.
+void kmer_stats_both(msspe_ctx* ctx, const std::vector<msspe_candidate> cand[2], unsigned k, const Args& a, std::vector<KmerStat> out[2]) {
+  std::vector<uint64_t> codes[2];
+  std::vector<msspe_kmer_stat> st[2];
+  for (int d = 0; d < 2; d++) {
+    codes[d].resize(cand[d].size());
+    for (size_t i = 0; i < cand[d].size(); i++) codes[d][i] = cand[d][i].code;
+    st[d].resize(cand[d].size() ? cand[d].size() : 1);
+  }
   msspe_filter_cfg fc{a.min_tm, a.max_tm, a.max_self_dimer_any_tm, a.max_self_dimer_end_tm, a.max_hairpin_tm, a.tm_stddev,
                       (uint8_t)(a.check_self_dimers == "true"), (uint8_t)(a.check_hairpin == "true"),
                       (uint8_t)(a.disable_tm_stddev == "true"), (uint8_t)(a.disable_min_max_tm == "true")};
-  std::vector<msspe_kmer_stat> st(n ? n : 1);
-  if (n) CHECK(msspe_kmer_stats(ctx, codes.data(), n, k, &fc, st.data()));
-  std::vector<KmerStat> out(n);
-  for (uint32_t i = 0; i < n; i++) {
-    KmerStat& s = out[i];
-    s.code = codes[i]; s.word = decode(codes[i], k); s.direction = dir;
-    s.gc_percent = st[i].gc_percent; s.mean = st[i].mean; s.std = st[i].std; s.tm = st[i].tm; s.tm_ok = st[i].tm_ok != 0;
-    s.self_any_th = st[i].self_any_th; s.self_end_th = st[i].self_end_th; s.hairpin_th = st[i].hairpin_th; s.runs = st[i].runs != 0;
-    s.keep = st[i].keep != 0;
+  CHECK(msspe_kmer_stats_both(ctx, codes[0].data(), (uint32_t)codes[0].size(), codes[1].data(), (uint32_t)codes[1].size(), k, &fc, st[0].data(), st[1].data()));
+  for (int d = 0; d < 2; d++) {
+    out[d].resize(codes[d].size());
+    for (size_t i = 0; i < codes[d].size(); i++) {
+      KmerStat& s = out[d][i];
+      const msspe_kmer_stat& t = st[d][i];
+      s.code = codes[d][i]; s.word = decode(codes[d][i], k); s.direction = (uint8_t)d;
+      s.gc_percent = t.gc_percent; s.mean = t.mean; s.std = t.std; s.tm = t.tm; s.tm_ok = t.tm_ok != 0;
+      s.self_any_th = t.self_any_th; s.self_end_th = t.self_end_th; s.hairpin_th = t.hairpin_th; s.runs = t.runs != 0;
+      s.keep = t.keep != 0;
+    }
   }
-  return out;
 }
 
 std::vector<KmerStat> filter_kmers(const std::vector<KmerStat>& st) {
@@ -278,10 +283,8 @@ int main(int argc, char** argv) {
   // 4. thermodynamic filters (main.rs:723-732)
   const bool keep_all = a.keep_all == "true";
   std::vector<KmerStat> stats[2], primers_dir[2];
-  for (int d = 0; d < 2; d++) {
-    stats[d] = kmer_stats(ctx, cand[d], (uint8_t)d, k, a);
-    primers_dir[d] = keep_all ? stats[d] : filter_kmers(stats[d]);
-  }
+  kmer_stats_both(ctx, cand, k, a, stats);
+  for (int d = 0; d < 2; d++) primers_dir[d] = keep_all ? stats[d] : filter_kmers(stats[d]);
   // cross dimers (run_ntthal, main.rs:752 / delta_g.rs:61-153)
   std::vector<const KmerStat*> primers;
   for (int d = 0; d < 2; d++) for (auto& s : primers_dir[d]) primers.push_back(&s);

@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "msspe_select_both", "msspe_coverage", "msspe_thal_params_default", "msspe_thal_params_from_dir",
     "msspe_set_thal_params", "msspe_primer_thermo", "msspe_thal_pairs", "msspe_thal_pairs_aligned", "msspe_cross_dimer",
     "msspe_fasta_open", "msspe_fasta_close", "msspe_fasta_records", "msspe_fasta_name", "msspe_fasta_bases",
-    "msspe_fasta_offsets", "msspe_load_fasta", "msspe_kmer_stats", "msspe_coverage_summary", "msspe_vertex_cover", "msspe_shard_begin", "msspe_shard_buffers", "msspe_shard_count", "msspe_shard_firstpos", "msspe_shard_apply",
+    "msspe_fasta_offsets", "msspe_load_fasta", "msspe_kmer_stats", "msspe_kmer_stats_both", "msspe_coverage_summary", "msspe_vertex_cover", "msspe_shard_begin", "msspe_shard_buffers", "msspe_shard_count", "msspe_shard_firstpos", "msspe_shard_apply",
 ]
 
 
@@ -154,6 +154,7 @@ def load_library():
                                     C.c_uint32, C.c_double, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p,
                                     C.c_uint64, C.POINTER(C.c_uint64)]
     L.msspe_kmer_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(FilterCfg), C.c_void_p]
+    L.msspe_kmer_stats_both.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(FilterCfg), C.c_void_p, C.c_void_p]
     L.msspe_shard_begin.argtypes = [C.c_void_p, C.c_uint8]
     L.msspe_shard_buffers.argtypes = [C.c_void_p, C.c_uint8, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.msspe_shard_count.argtypes = [C.c_void_p, C.c_uint8, C.POINTER(C.c_uint64)]
@@ -365,6 +366,15 @@ class Engine:
         cfg = cfg or default_filter_cfg()
         self._check(self.L.msspe_kmer_stats(self.h, codes.ctypes.data, len(codes), oligo_len or self.k, C.byref(cfg), out.ctypes.data))
         return out[:len(codes)]
+
+    def kmer_stats_both(self, fwd_codes, rev_codes, cfg: "FilterCfg" = None, oligo_len=None):
+        """get_kmer_stats + filter_kmers for both directions with one device batch (main.rs:723-724)."""
+        f = np.ascontiguousarray(fwd_codes, dtype=np.uint64); r = np.ascontiguousarray(rev_codes, dtype=np.uint64)
+        of = np.zeros(max(1, len(f)), dtype=KMER_STAT_DTYPE); orv = np.zeros(max(1, len(r)), dtype=KMER_STAT_DTYPE)
+        cfg = cfg or default_filter_cfg()
+        self._check(self.L.msspe_kmer_stats_both(self.h, f.ctypes.data, len(f), r.ctypes.data, len(r), oligo_len or self.k, C.byref(cfg),
+                                                 of.ctypes.data, orv.ctypes.data))
+        return of[:len(f)], orv[:len(r)]
 
     def thal_pairs(self, a, b, ttype, cond: ThalCond, oligo_len=None) -> np.ndarray:
         a = np.ascontiguousarray(a, dtype=np.uint64)

@@ -169,3 +169,18 @@ def test_kmer_stats_and_filters_vs_oracle_pipeline(zika_fasta, oracle_lib):
         assert kept == want.filtered[d]
     want.close()
     eng.close()
+
+
+def test_kmer_stats_both_equals_two_calls():
+    """One device batch for both directions (main.rs:723-724) gives byte-identical rows to two msspe_kmer_stats calls,
+    including the per-direction mean / standard deviation."""
+    import msspe_b200 as m
+    from msspe_b200 import synth
+    eng = m.Engine(13, 500, 250, 50)
+    f = synth.random_primers(301, 13, 21); r = synth.random_primers(97, 13, 22)
+    cfg = m.default_filter_cfg()
+    a, b = eng.kmer_stats_both(f, r, cfg)
+    assert a.tobytes() == eng.kmer_stats(f, cfg).tobytes() and b.tobytes() == eng.kmer_stats(r, cfg).tobytes()
+    a, b = eng.kmer_stats_both(f[:0], r, cfg)
+    assert len(a) == 0 and b.tobytes() == eng.kmer_stats(r, cfg).tobytes()
+    eng.close()
