@@ -3,8 +3,9 @@ import csv, subprocess, sys, io
 rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hi = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')
-hdr = rows[hi]; ix = {h: i for i, h in enumerate(hdr)}; data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+his = [i for i, r in enumerate(rows) if r and r[0] == 'Address']  # one source table per profiled kernel: take the longest-running (last) one
+hi = his[-1]
+hdr = rows[hi]; ix = {h: i for i, h in enumerate(hdr)}; data = [r for r in rows[hi + 1:] if len(r) == len(hdr) and r[0] != 'Address']
 tot = sum(int(r[ix['# Samples']]) for r in data)
 print('samples', tot, 'warp instr', sum(int(r[ix['Instructions Executed']]) for r in data))
 stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
