@@ -305,3 +305,28 @@ def test_stream_compaction_on_small_inputs(zika_fasta, oracle_lib, compact_min, 
         a, b = eng.select_both(it, mms, 0)          # both directions in one launch sequence; a second run on the same index
         assert a.tobytes() == eng.select(0, it, mms, 0).tobytes() and b.tobytes() == eng.select(1, it, mms, 0).tobytes()
         eng.close()
+
+
+def test_global_bitmask_variant_many_segments():
+    """More segments than a shared-memory bitmask can hold (2,000 genomes x 1,000 partitions = 2.0 M segments > 1.8 M
+    bits): the persistent kernel reads the global bitmask, which block 0 updates inside the launch (grid barrier
+    after the update).  No oracle at this size: the persistent loop, the launch-per-phase loop and the incremental
+    loop -- three different code paths -- must agree bit for bit, and the evals of iteration 0 = record count."""
+    import msspe_b200 as m
+    from msspe_b200 import synth
+    g = synth.synth_genomes(2000, 30_000, 11, clades=16, p_clade=0.08, p_leaf=0.01)
+    eng = m.Engine(13, 30, 30, 20)
+    eng.load_genomes(g.reshape(-1), synth.offsets_for(g))
+    eng.build_index()
+    G, maxp, s = eng.segment_info()
+    assert G == 2000 * 1000 and maxp == 999 and s == 8
+    a0, b0 = eng.select_both(60, 10, 0)
+    ev0 = tuple(eng.timing().select_evals)
+    a1, b1 = eng.select_both(60, 10, 1)
+    ev1 = tuple(eng.timing().select_evals)
+    a2 = eng.select(0, 60, 10, 0x100)
+    assert a0.tobytes() == a1.tobytes() == a2.tobytes() and b0.tobytes() == b1.tobytes() and ev0 == ev1
+    assert len(a0) == 60 and np.all(np.diff(a0["freq"].astype(np.int64)) <= 0)
+    first = eng.select(0, 1, 10, 0)
+    assert len(first) == 1 and eng.timing().select_evals[0] == eng.index(0)[1][-1]
+    eng.close()
