@@ -159,40 +159,45 @@ __device__ __forceinline__ Closing make_closing(const DimerShared& sh, const Pai
 // H = +inf marks "not possible".  ca/cb are the 2-bit codes: n1[t] = (ca >> 2(k-t)) & 3, n2[t] = (cb >> 2(t-1)) & 3.
 __device__ __forceinline__ void loop_candidate(const DimerShared& sh, const double2* __restrict__ cell, int k, uint64_t ca, uint64_t cb,
                                                const Closing& cl, int i, int j, int ii, int jj, double* outS, double* outH) {
-  // Branch-free over the four loop kinds (the lanes of a warp hold all of them at once, so branches would serialise):
-  //   kind                 A              B                C           D
-  //   bulge of size 1      bulge[ls]      stack[xb]        -           -         rejected BEFORE the inner cell is added if H > 0 || S > 0
-  //   longer bulge         bulge[ls]      atp[inner pair]  closing atp -
-  //   1x1 internal         int2[x]        closing int2     -           -
-  //   other internal       interior[ls]   tstack[x]        closing tst ILAS*|l1-l2|
-  // value = ((A + B) + C) + D, then += inner cell -- the association order of the scalar code; an absent term is +0.0,
-  // which leaves every sum bit-identical.
   const int l1 = i - ii - 1, l2 = j - jj - 1, ls = l1 + l2 - 1;
   const double2 inner = cell[(ii - 1) * k + (jj - 1)];
   const uint32_t a_in = (uint32_t)(ca >> (2 * (k - ii))) & 3u, b_in = (uint32_t)(cb >> (2 * (jj - 1))) & 3u;
-  const uint32_t a_nx = (uint32_t)(ca >> (2 * (k - ii - 1))) & 3u, b_nx = (uint32_t)(cb >> (2 * jj)) & 3u;  // n1[ii+1], n2[jj+1]
-  const bool bulge = l1 == 0 || l2 == 0;
-  const bool b1 = bulge && ls == 0, i11 = !bulge && ls == 1, inter = !bulge && ls != 1, bn = bulge && ls != 0;
-  const int x_in = i4(a_in, a_nx, b_in, b_nx), x_b = i4(a_in, cl.a, b_in, cl.b);
-  // A
-  const double* tAS = bulge ? sh.bulgeS : (i11 ? sh.int2S : sh.interiorS);
-  const double* tAH = bulge ? sh.bulgeH : (i11 ? sh.int2H : sh.interiorH);
-  const int iA = i11 ? x_in : ls;
-  // B (a table term except for the 1x1 loop)
-  const double* tBS = b1 ? sh.stackS : (bn ? sh.atpS : sh.tstS);
-  const double* tBH = b1 ? sh.stackH : (bn ? sh.atpH : sh.tstH);
-  const int iB = b1 ? x_b : (bn ? (int)(a_in * 4u + b_in) : x_in);
-  const double vBS = tBS[iB], vBH = tBH[iB];
-  const double BS = i11 ? cl.int2S : vBS, BH = i11 ? cl.int2H : vBH;
-  const double CS = bn ? cl.atpS : (inter ? cl.tstS : 0.0), CH = bn ? cl.atpH : (inter ? cl.tstH : 0.0);
-  const int asym = l1 > l2 ? l1 - l2 : l2 - l1;
-  const double DS = inter ? (K_ILAS * asym) : 0.0, DH = inter ? (K_ILAH * asym) : 0.0;
-  double S = tAS[iA] + BS + CS + DS;
-  double H = tAH[iA] + BH + CH + DH;
-  if (b1 && (H > 0 || S > 0)) { H = INFINITY; S = -1.0; }
-  H += inner.y; S += inner.x;
-  if (!isfinite(H)) { H = INFINITY; S = -1.0; }
-  if (!b1 && H > 0 && S > 0) { H = INFINITY; S = -1.0; }
+  double S, H;
+  if (l1 == 0 || l2 == 0) {      // bulge (l1 + l2 >= 1 guaranteed by the caller)
+    if (l1 + l2 == 1) {          // size 1: the flanking pairs still stack
+      const int x = i4(a_in, cl.a, b_in, cl.b);
+      H = sh.bulgeH[ls] + sh.stackH[x];
+      S = sh.bulgeS[ls] + sh.stackS[x];
+      if (H > 0 || S > 0) { H = INFINITY; S = -1.0; }
+      H += inner.y; S += inner.x;
+      if (!isfinite(H)) { H = INFINITY; S = -1.0; }
+    } else {
+      H = sh.bulgeH[ls] + sh.atpH[a_in * 4 + b_in] + cl.atpH;
+      H += inner.y;
+      S = sh.bulgeS[ls] + sh.atpS[a_in * 4 + b_in] + cl.atpS;
+      S += inner.x;
+      if (!isfinite(H)) { H = INFINITY; S = -1.0; }
+      if (H > 0 && S > 0) { H = INFINITY; S = -1.0; }
+    }
+  } else {
+    // inner-side context: n1[ii], n1[ii+1], n2[jj], n2[jj+1]  (ii+1 <= i-1 and jj+1 <= j-1 here)
+    const uint32_t a_nx = (uint32_t)(ca >> (2 * (k - ii - 1))) & 3u, b_nx = (uint32_t)(cb >> (2 * jj)) & 3u;
+    const int x = i4(a_in, a_nx, b_in, b_nx);
+    if (l1 == 1 && l2 == 1) {
+      S = sh.int2S[x] + cl.int2S;
+      S += inner.x;
+      H = sh.int2H[x] + cl.int2H;
+      H += inner.y;
+    } else {
+      const int asym = l1 > l2 ? l1 - l2 : l2 - l1;
+      H = sh.interiorH[ls] + sh.tstH[x] + cl.tstH + (K_ILAH * asym);
+      H += inner.y;
+      S = sh.interiorS[ls] + sh.tstS[x] + cl.tstS + (K_ILAS * asym);
+      S += inner.x;
+    }
+    if (!isfinite(H)) { H = INFINITY; S = -1.0; }
+    if (H > 0 && S > 0) { H = INFINITY; S = -1.0; }
+  }
   *outS = S; *outH = H;
 }
 

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_PKG), "libodmsspe_b200.so")
+LIB_PATH = os.environ.get("MSSPE_LIB") or os.path.join(os.path.dirname(_PKG), "libodmsspe_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_IO, ERR_CAPACITY = 0, -1, -2, -3, -4, -5, -6
 DIR_FWD, DIR_REV = 0, 1
