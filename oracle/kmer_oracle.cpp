@@ -18,6 +18,7 @@
 #include <cstring>
 #include <ctime>
 #include <cctype>
+#include <unistd.h>
 #include <map>
 #include <set>
 #include <string>
@@ -207,10 +208,53 @@ struct Config {
   int keep_all, check_cross_dimers, check_self_dimers, check_hairpin, disable_tm_stddev, disable_min_max_tm;
 };
 
+// ---- external-tool mode (tests/test_shims.py): like the reference, spawn the executables named by ORACLE_PRIMER3 /
+// ORACLE_NTTHAL (the reference's --primer3 / --ntthal, config.rs:142-147), feed them the reference's input text and
+// read their output with restatements of the reference's parsers.  Unset = the in-process oracle arithmetic.
+std::string run_tool(const std::string& cmd, const std::string& input) {
+  char in_path[] = "/tmp/oracle_tool_in_XXXXXX", out_path[] = "/tmp/oracle_tool_out_XXXXXX";
+  int fi = mkstemp(in_path), fo = mkstemp(out_path);
+  if (fi < 0 || fo < 0) return "";
+  FILE* f = fdopen(fi, "wb"); fwrite(input.data(), 1, input.size(), f); fclose(f);
+  close(fo);
+  const std::string full = cmd + " < " + in_path + " > " + out_path;
+  const int rc = system(full.c_str());
+  std::string out;
+  if (rc == 0) { FILE* g = fopen(out_path, "rb"); if (g) { char b[65536]; size_t n; while ((n = fread(b, 1, sizeof b, g)) > 0) out.append(b, n); fclose(g); } }
+  remove(in_path); remove(out_path);
+  return out;
+}
+
 // primer3_core check_primers emulation: primer.rs:125-166 (+ Primer3 defaults: mv 50, dv 1.5, dNTP 0.6,
 // DNA 50 nM, thal at 37 C, maxLoop 30; "%.3f" for TM/GC, "%.2f" for *_TH, then parse::<f32>).
-std::vector<PrimerInfo> check_primers(const std::vector<std::string>& primers) {
+std::vector<PrimerInfo> check_primers(const std::vector<std::string>& primers, float min_tm, float max_tm) {
   std::vector<PrimerInfo> out;
+  if (const char* exe = getenv("ORACLE_PRIMER3")) {
+    std::string in;  // format_primer3_input, primer.rs:125-140
+    char b[128];
+    for (auto& p : primers) {
+      in += "SEQUENCE_ID=" + p + "\nSEQUENCE_PRIMER=" + p + "\nPRIMER_TASK=check_primers\nPRIMER_MIN_SIZE=13\n";
+      snprintf(b, sizeof b, "PRIMER_MIN_TM=%.2f\nPRIMER_MAX_TM=%.2f\nPRIMER_OPT_TM=%.2f\n", (double)min_tm, (double)max_tm, (double)max_tm);
+      in += b; in += "PRIMER_PICK_ANYWAY=1\n=\n";
+    }
+    const std::string text = run_tool(exe, in);
+    PrimerInfo cur{"", 0, 0, 0, 0, 0};  // parse_primer3_output, primer.rs:67-114
+    size_t pos = 0;
+    while (pos < text.size()) {
+      size_t e = text.find('\n', pos); if (e == std::string::npos) e = text.size();
+      const std::string line = text.substr(pos, e - pos); pos = e + 1;
+      if (line == "=") { if (cur.id.empty()) break; out.push_back(cur); cur = PrimerInfo{"", 0, 0, 0, 0, 0}; continue; }
+      const size_t q = line.find('='); if (q == std::string::npos) continue;
+      const std::string k = line.substr(0, q); std::string v = line.substr(q + 1); { const size_t q2 = v.find('='); if (q2 != std::string::npos) v = v.substr(0, q2); }
+      if (k == "SEQUENCE_ID") cur.id = v;
+      else if (k == "PRIMER_LEFT_0_TM") cur.tm = parse_f32(v.c_str());
+      else if (k == "PRIMER_LEFT_0_GC_PERCENT") cur.gc = parse_f32(v.c_str());
+      else if (k == "PRIMER_LEFT_0_SELF_ANY_TH") cur.self_any_th = parse_f32(v.c_str());
+      else if (k == "PRIMER_LEFT_0_SELF_END_TH") cur.self_end_th = parse_f32(v.c_str());
+      else if (k == "PRIMER_LEFT_0_HAIRPIN_TH") cur.hairpin_th = parse_f32(v.c_str());
+    }
+    return out;
+  }
   msspe_thal_cond c{50.0, 1.5, 0.6, 50.0, 37.0, 30, 0};
   for (auto& p : primers) {
     PrimerInfo pi; pi.id = p;
@@ -247,7 +291,7 @@ bool is_run(const std::string& k) {                                           //
 
 std::vector<KmerStat> get_kmer_stats(const std::vector<Cand>& recs, uint8_t dir, const Config& cfg) {  // main.rs:408-455
   std::vector<std::string> primers; for (auto& r : recs) primers.push_back(r.word);
-  auto infos = check_primers(primers);
+  auto infos = check_primers(primers, cfg.min_tm, cfg.max_tm);
   std::unordered_map<std::string, const PrimerInfo*> mp;
   for (auto& i : infos) mp.emplace(i.id, &i);
   float mean = NAN, sd = NAN;
@@ -302,6 +346,13 @@ std::string run_ntthal_text(const std::string& input, const Config& c, uint64_t*
   auto r2 = [](float v) { char b[64]; snprintf(b, sizeof b, "%.2f", (double)v); return atof(b); };  // {:.2} argv
   msspe_thal_cond cond{r2(c.mv_conc), r2(c.dv_conc), r2(c.dntp_conc), r2(c.dna_conc), r2(c.annealing_temp), 30, 0};
   std::string out;
+  if (const char* exe = getenv("ORACLE_NTTHAL")) {  // argv of delta_g.rs:93-110 (-path only when ./primer3_config/ exists)
+    char b[512];
+    snprintf(b, sizeof b, "%s -a ANY -mv %.2f -dv %.2f -n %.2f -d %.2f -t %.2f %s-i", exe, (double)c.mv_conc, (double)c.dv_conc, (double)c.dntp_conc,
+             (double)c.dna_conc, (double)c.annealing_temp, access("primer3_config", R_OK) == 0 ? "-path primer3_config/ " : "");
+    for (auto& l : lines_of(input)) { (void)l; (*n_pairs)++; }
+    return run_tool(b, input + "\n");
+  }
   for (auto& l : lines_of(input)) {
     size_t comma = l.find(',');
     std::string a = l.substr(0, comma), b = l.substr(comma + 1);

@@ -183,3 +183,20 @@ def test_primer3_core_shim_reference_vector_and_engine_parity():
     eng.close()
     bad = subprocess.run([exe], input="SEQUENCE_ID=x\nSEQUENCE_PRIMER=ACGT\nPRIMER_TASK=generic\n=\n", capture_output=True, text=True)
     assert "PRIMER_ERROR=" in bad.stdout and bad.stdout.endswith("=\n")
+
+
+@pytest.mark.parametrize("okw", [dict(), dict(delta_g_threshold=-3000.0, max_hairpin_tm=40.0, tm_stddev=1.0, max_mismatch_segments=5),
+                                 dict(check_self_dimers=0), dict(kmer_size=15, max_iterations=40, disable_tm_stddev=1, disable_min_max_tm=1)],
+                         ids=["defaults", "thresholds", "no_self", "k15"])
+def test_reference_host_logic_over_the_shims_equals_the_full_pipeline(zika_fasta, oracle_lib, monkeypatch, okw):
+    """The seam end to end: the restated reference pipeline (the oracle's port of main.rs: FASTA, k-mer engine, filters,
+    5-line parser, vertex cover, report, CSV) SPAWNS the two shims exactly as the Rust binary spawns `--primer3` /
+    `--ntthal` (its input text, its argv, its parsers) instead of doing its own thermodynamics.  CSV and report must
+    be byte-identical to the same pipeline with the in-process FP64 oracle arithmetic."""
+    want = oracle_lib.run_pipeline(zika_fasta, oracle_lib.default_config(**okw))
+    monkeypatch.setenv("ORACLE_PRIMER3", os.path.join(SHIMS, "primer3_core"))
+    monkeypatch.setenv("ORACLE_NTTHAL", os.path.join(SHIMS, "ntthal"))
+    got = oracle_lib.run_pipeline(zika_fasta, oracle_lib.default_config(**okw))
+    assert got.csv == want.csv and got.report == want.report
+    assert len(got.csv.split("\n")) > 20
+    got.close(); want.close()
