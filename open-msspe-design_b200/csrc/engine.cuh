@@ -130,6 +130,9 @@ struct msspe_ctx {
 int msspe_exclusive_scan_u32(msspe_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* d_total,
                              cudaStream_t st);
 
+int msspe_radix_sort_pairs(msspe_ctx* ctx, uint64_t** key_a, uint32_t** val_a, uint64_t** key_b, uint32_t** val_b, uint64_t n,
+                           uint32_t key_bits, cudaStream_t st);
+
 // ---- stages ----
 int msspe_free_index(msspe_ctx* ctx);
 int msspe_select_prepare_static(msspe_ctx* ctx, int dir, cudaStream_t st);  // select.cu: tile tables

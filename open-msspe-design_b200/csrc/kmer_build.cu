@@ -257,6 +257,33 @@ __global__ void build_csr_kernel(const uint64_t* __restrict__ keys, const uint32
   if (head) { codes[cid] = keys[i]; post_off[cid] = (uint32_t)i; }
 }
 
+}  // namespace
+
+// Stable LSD radix sort of (u64 key, u32 payload) pairs by the low `key_bits` bits; ping-pongs between the a and b
+// buffers and leaves the result in *key_a / *val_a (the pointers are swapped as needed).
+int msspe_radix_sort_pairs(msspe_ctx* c, uint64_t** key_a, uint32_t** val_a, uint64_t** key_b, uint32_t** val_b, uint64_t n, uint32_t key_bits,
+                           cudaStream_t st) {
+  if (n == 0) return MSSPE_OK;
+  const uint32_t nb = (uint32_t)div_up_u64(n, RS_TILE);
+  uint32_t* hist = nullptr;
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&hist, (uint64_t)256 * nb * sizeof(uint32_t), st));
+  const int passes = (int)((key_bits + 7) / 8);
+  for (int p = 0; p < passes; p++) {
+    radix_hist_kernel<<<nb, RS_THREADS, 0, st>>>(*key_a, n, 8 * p, hist, nb);
+    c->timing.kernel_launches++;
+    int rc = msspe_exclusive_scan_u32(c, hist, hist, (uint64_t)256 * nb, nullptr, st);
+    if (rc) return rc;
+    radix_scatter_kernel<<<nb, RS_THREADS, 0, st>>>(*key_a, *val_a, n, 8 * p, hist, nb, *key_b, *val_b);
+    c->timing.kernel_launches++;
+    std::swap(*key_a, *key_b); std::swap(*val_a, *val_b);
+  }
+  MSSPE_CUDA_TRY(c, cudaGetLastError());
+  MSSPE_CUDA_TRY(c, cudaFreeAsync(hist, st));
+  return MSSPE_OK;
+}
+
+namespace {
+
 void free_dir(msspe_ctx* c, DirIndex& d) {
   msspe_dev_free(c, d.codes); msspe_dev_free(c, d.post_off); msspe_dev_free(c, d.postings); msspe_dev_free(c, d.fwd_ids); msspe_dev_free(c, d.freq);
   msspe_dev_free(c, d.acc); msspe_dev_free(c, d.ignored); msspe_dev_free(c, d.cov); msspe_dev_free(c, d.pmark); msspe_dev_free(c, d.ctl); msspe_dev_free(c, d.out);
@@ -328,21 +355,8 @@ int build_direction(msspe_ctx* c, int dir, float* enc_ms, float* idx_ms) {
   if (R > 0) {
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&key_b, Ra * 8, st));
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&val_b, Ra * 4, st));
-    const uint32_t nb = (uint32_t)div_up_u64(R, RS_TILE);
-    uint32_t* hist = nullptr;
-    MSSPE_CUDA_TRY(c, cudaMallocAsync(&hist, (uint64_t)256 * nb * sizeof(uint32_t), st));
-    const int passes = (int)((2 * c->cfg.kmer_size + 7) / 8);
-    for (int p = 0; p < passes; p++) {
-      radix_hist_kernel<<<nb, RS_THREADS, 0, st>>>(key_a, R, 8 * p, hist, nb);
-      c->timing.kernel_launches++;
-      rc = msspe_exclusive_scan_u32(c, hist, hist, (uint64_t)256 * nb, nullptr, st);
-      if (rc) return rc;
-      radix_scatter_kernel<<<nb, RS_THREADS, 0, st>>>(key_a, val_a, R, 8 * p, hist, nb, key_b, val_b);
-      c->timing.kernel_launches++;
-      std::swap(key_a, key_b); std::swap(val_a, val_b);
-    }
-    MSSPE_CUDA_TRY(c, cudaGetLastError());
-    MSSPE_CUDA_TRY(c, cudaFreeAsync(hist, st));
+    rc = msspe_radix_sort_pairs(c, &key_a, &val_a, &key_b, &val_b, R, 2 * c->cfg.kmer_size, st);
+    if (rc) return rc;
     // sorted records are in key_a / val_a
     uint32_t* flags = nullptr;
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&flags, (uint64_t)R * 4, st));

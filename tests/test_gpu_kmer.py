@@ -140,7 +140,7 @@ def test_random_alignments_bit_exact(oracle_lib, seed, n, L, W, S, w, k, mms):
     for d in (0, 1):
         want, part = oracle_lib.segment_slots(fa, W, S, w, k, d)
         assert np.array_equal(eng.segment_kmers(d), want)
-    for mode in (0, 1, 0x100):
+    for mode in (0, 1, 0x100, 0x101):   # persistent recount / persistent incremental / launch-per-phase recount / incremental
         _check_select(eng, oracle_lib, fa, W, S, w, k, 60, mms, mode)
     eng.close()
 
@@ -153,7 +153,7 @@ def test_identical_genomes_tie_storm(oracle_lib):
     eng = m.Engine(13, 500, 250, 50)
     eng.load_genomes(bases, offs)
     eng.build_index()
-    for mode in (0, 1, 0x100):
+    for mode in (0, 1, 0x100, 0x101):
         _check_select(eng, oracle_lib, fa, 500, 250, 50, 13, 40, 1, mode)
     eng.close()
 
@@ -320,12 +320,17 @@ def test_global_bitmask_variant_many_segments():
     eng.build_index()
     G, maxp, s = eng.segment_info()
     assert G == 2000 * 1000 and maxp == 999 and s == 8
-    a0, b0 = eng.select_both(60, 10, 0)
-    ev0 = tuple(eng.timing().select_evals)
+    os.environ["MSSPE_FORCE_RECOUNT"] = "1"     # without it a recount request of this size is served by the incremental kernel
+    try:
+        a0, b0 = eng.select_both(60, 10, 0)
+        ev0 = tuple(eng.timing().select_evals)
+    finally:
+        del os.environ["MSSPE_FORCE_RECOUNT"]
     a1, b1 = eng.select_both(60, 10, 1)
     ev1 = tuple(eng.timing().select_evals)
     a2 = eng.select(0, 60, 10, 0x100)
-    assert a0.tobytes() == a1.tobytes() == a2.tobytes() and b0.tobytes() == b1.tobytes() and ev0 == ev1
+    a3, b3 = eng.select_both(60, 10, 0)         # the automatic fallback
+    assert a0.tobytes() == a1.tobytes() == a2.tobytes() == a3.tobytes() and b0.tobytes() == b1.tobytes() == b3.tobytes() and ev0 == ev1
     assert len(a0) == 60 and np.all(np.diff(a0["freq"].astype(np.int64)) <= 0)
     first = eng.select(0, 1, 10, 0)
     assert len(first) == 1 and eng.timing().select_evals[0] == eng.index(0)[1][-1]
