@@ -18,6 +18,8 @@
 // forward index for the newly covered segments (identical results, far less traffic).
 #include <cooperative_groups.h>
 
+#include <algorithm>
+
 #include "engine.cuh"
 #include "select_device.cuh"
 
@@ -1276,7 +1278,12 @@ int run_select(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max_iter, uint
   if (!c->built) { c->set_error("msspe_select: index not built"); return MSSPE_ERR_STATE; }
   const bool batched = (mode & MSSPE_SELECT_BATCHED) != 0;
   mode &= ~(uint32_t)MSSPE_SELECT_BATCHED;
-  if (mode > MSSPE_SELECT_INCREMENTAL) { c->set_error("msspe_select: unknown mode %u", mode); return MSSPE_ERR_INVALID; }
+  if (mode > MSSPE_SELECT_AUTO) { c->set_error("msspe_select: unknown mode %u", mode); return MSSPE_ERR_INVALID; }
+  if (mode == MSSPE_SELECT_AUTO) {  // measured on B200: on par up to cfg3 (15 M postings per direction), incremental ahead beyond
+    uint64_t most = 0;
+    for (int i = 0; i < ndirs; i++) most = std::max<uint64_t>(most, c->dir[dirs[i]].n_records);
+    mode = most >= (1ull << 24) ? MSSPE_SELECT_INCREMENTAL : MSSPE_SELECT_RECOUNT;
+  }
   MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
   if (!batched && mode == MSSPE_SELECT_INCREMENTAL && max_iter > 0) return run_select_incremental(c, ndirs, dirs, max_iter, mms, outs, n_outs);
   if (!batched && mode == MSSPE_SELECT_RECOUNT && max_iter > 0) {

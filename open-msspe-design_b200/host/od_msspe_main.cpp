@@ -276,7 +276,7 @@ int main(int argc, char** argv) {
   std::vector<msspe_candidate> cand[2];
   cand[0].resize(a.max_iterations ? a.max_iterations : 1); cand[1].resize(a.max_iterations ? a.max_iterations : 1);
   uint32_t nf = 0, nr = 0;
-  CHECK(msspe_select_both(ctx, (uint32_t)a.max_iterations, (uint32_t)std::min<uint64_t>(mms, 0xFFFFFFFFull), MSSPE_SELECT_RECOUNT,
+  CHECK(msspe_select_both(ctx, (uint32_t)a.max_iterations, (uint32_t)std::min<uint64_t>(mms, 0xFFFFFFFFull), MSSPE_SELECT_AUTO,
                           cand[0].data(), &nf, cand[1].data(), &nr));
   cand[0].resize(nf); cand[1].resize(nr);
   log_info("Done calculating, Total candidate k-mers: fwd: " + std::to_string(nf) + ", rev: " + std::to_string(nr));

@@ -67,7 +67,7 @@ def test_zika_inverted_index_matches_reference_mapping(zika_engine):
             assert post[int(offs[i]):int(offs[i + 1])].tolist() == want[int(codes[i])]
 
 
-@pytest.mark.parametrize("mode", [0, 1, 0x100])
+@pytest.mark.parametrize("mode", [0, 1, 2, 0x100, 0x101])
 def test_zika_greedy_selection_bit_exact(zika_engine, zika_fasta, oracle_lib, mode):
     eng, _ = zika_engine
     _check_select(eng, oracle_lib, zika_fasta, 500, 250, 50, 13, 1000, 2, mode)
