@@ -339,6 +339,10 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   }
   __syncthreads();
 }
+// cooperative_groups' own grid barrier: 1.21 us against 1.45 us for the counter above in isolation (296 x 512,
+// tools/microbench/grid_barrier.cu).  Inside the kernels the difference is within noise: the incremental kernel runs
+// 4 % faster with it, the recount kernel 3 % slower -- each keeps the one it measured better with.
+__device__ __forceinline__ void grid_barrier_cg() { cg::this_grid().sync(); }
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -1077,7 +1081,7 @@ greedy_incremental_kernel(const IncArgs A) {
       }
     }
     INC_STAMP(2)
-    grid_barrier(A.barrier, bar_target);
+    grid_barrier_cg();
     INC_STAMP(3)
     // ---------------- phase 2 ----------------
     bool all_done = true;
@@ -1147,7 +1151,7 @@ greedy_incremental_kernel(const IncArgs A) {
     }
     INC_STAMP(4)
     if (all_done) break;
-    grid_barrier(A.barrier, bar_target);
+    grid_barrier_cg();
     INC_STAMP(5)
     for (int d = 0; d < A.ndirs; d++)
       if (!done[d]) live[d] -= (unsigned long long)__ldcg(&A.d[d].ctl->plive[par]);
