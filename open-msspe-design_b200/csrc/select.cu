@@ -979,7 +979,8 @@ greedy_incremental_kernel(const IncArgs A) {
   uint32_t* fp = seen + A.p_words;
   unsigned long long* lst = reinterpret_cast<unsigned long long*>(dsm + (((size_t)(reinterpret_cast<unsigned char*>(fp + A.n_fp) - dsm) + 7) & ~(size_t)7));
   __shared__ uint32_t s_tied[2 * THREADS];
-  __shared__ uint32_t s_cnt2[2], s_sc[2], s_g[2], s_nt[2], s_dec, s_red[THREADS / 32];
+  __shared__ uint32_t s_cnt2[2], s_sc[2], s_g[2], s_nt[2], s_can[2], s_dec, s_red[2 * (THREADS / 32)];
+  uint32_t* s_cov = reinterpret_cast<uint32_t*>(lst + A.n_fp);  // [2][n_fp] this iteration's partition_coverage
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned int bar_target = 0;
   bool done[2] = {false, A.ndirs < 2};
@@ -996,28 +997,48 @@ greedy_incremental_kernel(const IncArgs A) {
   for (uint32_t it = 0;; it++) {
     const int par = it & 1;
     // ---------------- phase 1 ----------------
-    // the maximum never grows: walk down the histogram from the previous one, THREADS bins per step (early on the
-    // occupied bins are far apart, a serial walk would be hundreds of dependent L2 loads)
-    for (int d = 0; d < A.ndirs; d++) {
-      if (done[d]) continue;
-      uint32_t g = s_g[d];
+    // The maximum never grows: walk down the histogram from the previous one, THREADS bins per step, both directions
+    // in the same pass (early on the occupied bins are far apart: a serial walk would be hundreds of dependent L2 loads).
+    // The thread that finds the maximum already holds hist[max] (the tie count) and has asked for cnt_ge[max] too.
+    // In the same round trip: this iteration's partition_coverage tables into shared memory.
+    if (A.n_fp)
+      for (int d = 0; d < A.ndirs; d++)
+        if (!done[d]) for (uint32_t q = tid; q < A.n_part; q += THREADS) s_cov[(size_t)d * A.n_fp + q] = __ldcg(A.d[d].cov + q);
+    {
+      uint32_t g[2] = {s_g[0], s_g[1]};
+      bool open[2] = {!done[0], A.ndirs > 1 && !done[1]};
       __syncthreads();
-      for (;;) {
-        const uint32_t mine = g >= (uint32_t)tid ? g - (uint32_t)tid : 0u;          // bins g, g-1, ..., g-THREADS+1
-        const uint32_t cand = (g >= (uint32_t)tid && mine > 0u && __ldcg(A.d[d].hist + mine) != 0u) ? mine : 0u;
-        const uint32_t wmax = __reduce_max_sync(0xffffffffu, cand);
-        if (lane == 0) s_red[warp] = wmax;
-        __syncthreads();
-        uint32_t best = 0u;
+      while (open[0] || open[1]) {
+        uint32_t hv[2] = {0u, 0u}, cg_[2] = {0u, 0u}, mine[2] = {0u, 0u};
 #pragma unroll
-        for (int w2 = 0; w2 < WARPS; w2++) best = max(best, s_red[w2]);
+        for (int d = 0; d < 2; d++)
+          if (open[d] && g[d] >= (uint32_t)tid && g[d] - (uint32_t)tid > 0u) {
+            mine[d] = g[d] - (uint32_t)tid;                       // bins g, g-1, ..., g-THREADS+1
+            hv[d] = __ldcg(A.d[d].hist + mine[d]);
+            cg_[d] = __ldg(A.d[d].cnt_ge + mine[d]);
+          }
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+          const uint32_t wmax = __reduce_max_sync(0xffffffffu, hv[d] ? mine[d] : 0u);
+          if (lane == 0) s_red[d * WARPS + warp] = wmax;
+        }
         __syncthreads();
-        if (best || g < (uint32_t)THREADS) { g = best; break; }
-        g -= (uint32_t)THREADS;
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+          if (!open[d]) continue;
+          uint32_t best = 0u;
+#pragma unroll
+          for (int w2 = 0; w2 < WARPS; w2++) best = max(best, s_red[d * WARPS + w2]);
+          if (best || g[d] < (uint32_t)THREADS) {
+            if (best ? (mine[d] == best && hv[d]) : tid == 0) { s_g[d] = best; s_nt[d] = best ? hv[d] : 0u; s_can[d] = best ? cg_[d] : 0u; }
+            open[d] = false;
+          } else {
+            g[d] -= (uint32_t)THREADS;
+          }
+        }
+        __syncthreads();
       }
-      if (tid == 0) { s_g[d] = g; s_nt[d] = g ? __ldcg(A.d[d].hist + g) : 0u; }
     }
-    __syncthreads();
     INC_STAMP(1)
     for (int d = 0; d < A.ndirs; d++) {
       if (done[d]) continue;
@@ -1032,7 +1053,7 @@ greedy_incremental_kernel(const IncArgs A) {
       // counts only fall: a k-mer can be at g only if its initial count was >= g, i.e. it sits in the first cnt_ge[g]
       // entries of the order by descending initial count -- a few thousand entries while g is large
       uint32_t* tied = s_tied + d * THREADS;
-      const uint32_t stride = gridDim.x * THREADS, n_can = __ldg(D.cnt_ge + g);
+      const uint32_t stride = gridDim.x * THREADS, n_can = s_can[d];
       // entry x goes to block x % gridDim.x: k-mers of equal initial count are neighbours in this order, and so are
       // the tied ones -- dealt out round-robin every block scores about the same number of them
       for (uint32_t x = blockIdx.x + gridDim.x * (uint32_t)tid; x < n_can; x += stride) {
@@ -1056,7 +1077,7 @@ greedy_incremental_kernel(const IncArgs A) {
           __syncthreads();
           const uint32_t x = chunk * gridDim.x * THREADS + blockIdx.x + gridDim.x * (uint32_t)tid;
           const uint32_t c = x < D.n_codes ? __ldg(D.by_freq + x) : 0u;
-          if (x < __ldg(D.cnt_ge + g) && __ldcg(D.freq + c) == g) tied[atomicAdd(&s_cnt2[d], 1u)] = c;
+          if (x < s_can[d] && __ldcg(D.freq + c) == g) tied[atomicAdd(&s_cnt2[d], 1u)] = c;
           __syncthreads();
           nt = s_cnt2[d];
           __syncthreads();
@@ -1066,7 +1087,7 @@ greedy_incremental_kernel(const IncArgs A) {
           const uint32_t cc = tied[t];
           float score;
           if (A.n_fp) {
-            score = block_tie_score<false, true, THREADS>(cc, D.post_off, D.postings, D.ignored, A.seg_part, A.uniform_parts, D.cov, A.n_part, fp, lst, s_sc);
+            score = block_tie_score<false, false, THREADS>(cc, D.post_off, D.postings, D.ignored, A.seg_part, A.uniform_parts, s_cov + (size_t)d * A.n_fp, A.n_part, fp, lst, s_sc);
           } else {
             if (warp == 0) {
               const float sw = warp_tie_score<false, true>(cc, D.post_off, D.postings, D.ignored, A.seg_part, D.cov, seen, A.p_words, lane);
@@ -1237,7 +1258,7 @@ int run_select_incremental(msspe_ctx* c, int ndirs, const int* dirs, uint32_t ma
     g.n_codes = (uint32_t)D.n_codes; g.n_post = (uint32_t)D.n_records; g.gmax0 = gmax0;
     g.by_freq = d_byfreq[i]; g.cnt_ge = d_cntge[i];
   }
-  const size_t smem = (size_t)A.p_words * 4 + (size_t)A.n_fp * 4 + (size_t)A.n_fp * 8 + 32;
+  const size_t smem = (size_t)A.p_words * 4 + (size_t)A.n_fp * 4 + (size_t)A.n_fp * 8 + (size_t)2 * A.n_fp * 4 + 32;
   void* fn = (void*)greedy_incremental_kernel<512>;
   MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
