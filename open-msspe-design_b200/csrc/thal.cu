@@ -772,9 +772,13 @@ __device__ void mono_run(const ThalDeviceTables* T, MonoWork& w, double saltCorr
 __global__ void __launch_bounds__(64)
 thal_mono_kernel(const uint64_t* __restrict__ codes, uint32_t n, int k, const ThalDeviceTables* T, double saltCorr, double temp_K,
                  int maxLoop, MonoWork* work, msspe_thal_out* out) {
+  // One thread per oligo (<= 2000 per run: latency, not throughput).  The DP matrices of the thread live in SHARED
+  // memory when the launch provides it (MONO_SMEM_THREADS threads per block, one MonoWork each): the scalar recursion
+  // is a chain of dependent matrix reads, ~30 cycles each from shared memory against ~600 from a per-thread global scratch.
+  extern __shared__ __align__(16) unsigned char mono_smem[];
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  MonoWork& w = work[t];
+  MonoWork& w = work ? work[t] : reinterpret_cast<MonoWork*>(mono_smem)[threadIdx.x];
   const uint64_t c = codes[t];
   w.len = k; w.maxLoop = maxLoop;
   for (int x = 0; x < k; x++) w.n1[x + 1] = (int)((c >> (2 * (k - 1 - x))) & 3u);
@@ -854,6 +858,24 @@ int launch_dimer(msspe_ctx* c, DimerArgs& A, cudaStream_t st) {
   return MSSPE_OK;
 }
 
+// Hairpin launch: the per-thread DP scratch in shared memory (as many threads per block as fit) when that keeps the
+// whole batch in one wave of blocks, else the global scratch `work` with 64-thread blocks.
+int launch_mono(msspe_ctx* c, const uint64_t* d_codes, uint32_t n, int k, const ThalDimerConsts& K, MonoWork* work, msspe_thal_out* out,
+                cudaStream_t st) {
+  const int per_block = (int)((c->smem_optin - 1024) / sizeof(MonoWork));
+  const bool smem_ok = per_block >= 1 && !getenv("MSSPE_MONO_GLOBAL") && (uint64_t)n <= (uint64_t)per_block * (uint64_t)c->sm_count;  // one wave (measured: 0.49 vs 0.65 ms at 600, slower beyond one wave)
+  if (smem_ok) {
+    const size_t smem = (size_t)per_block * sizeof(MonoWork);
+    MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(thal_mono_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    thal_mono_kernel<<<(n + per_block - 1) / per_block, per_block, smem, st>>>(d_codes, n, k, c->d_thal, K.saltCorr, K.t_user_K, K.maxLoop, nullptr, out);
+  } else {
+    thal_mono_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_codes, n, k, c->d_thal, K.saltCorr, K.t_user_K, K.maxLoop, work, out);
+  }
+  c->timing.kernel_launches++;
+  MSSPE_CUDA_TRY(c, cudaGetLastError());
+  return MSSPE_OK;
+}
+
 int check_thal_args(msspe_ctx* c, uint32_t oligo_len, const msspe_thal_cond* cond) {
   if (oligo_len < 1 || oligo_len > MSSPE_MAX_OLIGO) { c->set_error("oligo length %u outside 1..%d", oligo_len, MSSPE_MAX_OLIGO); return MSSPE_ERR_INVALID; }
   if (cond && (cond->max_loop < 0 || cond->max_loop > 30)) { c->set_error("max_loop %d outside 0..30", cond->max_loop); return MSSPE_ERR_INVALID; }
@@ -917,11 +939,8 @@ static int thal_pairs_impl(msspe_ctx* c, const uint64_t* a, const uint64_t* b, u
   MSSPE_CUDA_TRY(c, cudaMemcpyAsync(da.p, a, n_pairs * 8, cudaMemcpyHostToDevice, st));
   if (type == MSSPE_THAL_HAIRPIN) {
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dwork.st = c->stream, dwork.p), n_pairs * sizeof(MonoWork), c->stream));
-    thal_mono_kernel<<<(unsigned)div_up_u64(n_pairs, 64), 64, 0, st>>>((const uint64_t*)da.p, (uint32_t)n_pairs, (int)oligo_len, c->d_thal,
-                                                                     K.saltCorr, K.t_user_K, K.maxLoop, (MonoWork*)dwork.p,
-                                                                     (msspe_thal_out*)dout.p);
-    c->timing.kernel_launches++;
-    MSSPE_CUDA_TRY(c, cudaGetLastError());
+    rc = launch_mono(c, (const uint64_t*)da.p, (uint32_t)n_pairs, (int)oligo_len, K, (MonoWork*)dwork.p, (msspe_thal_out*)dout.p, st);
+    if (rc) return rc;
   } else {
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&(db.st = c->stream, db.p), n_pairs * 8, c->stream));
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&dK.p, sizeof(ThalDimerConsts), c->stream));
@@ -999,9 +1018,8 @@ extern "C" int msspe_primer_thermo(msspe_ctx* c, const uint64_t* codes, uint32_t
     rc = launch_dimer(c, A, st);
     if (rc) return rc;
   }
-  thal_mono_kernel<<<(n + 63) / 64, 64, 0, st>>>((const uint64_t*)dcodes.p, n, (int)oligo_len, c->d_thal, K.saltCorr, K.t_user_K, K.maxLoop,
-                                                (MonoWork*)dwork.p, o3 + (size_t)2 * n);
-  c->timing.kernel_launches++;
+  rc = launch_mono(c, (const uint64_t*)dcodes.p, n, (int)oligo_len, K, (MonoWork*)dwork.p, o3 + (size_t)2 * n, st);
+  if (rc) return rc;
   MSSPE_CUDA_TRY(c, cudaGetLastError());
   std::vector<msspe_thal_out> h((size_t)n * 3);
   MSSPE_CUDA_TRY(c, cudaMemcpyAsync(tm, dtm.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
