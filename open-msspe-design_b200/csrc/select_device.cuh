@@ -162,7 +162,8 @@ __device__ __forceinline__ uint32_t warp_count_tile(uint32_t h, uint32_t wt, con
 
 // This warp's share of one recount: its contiguous tile range.  One register buffer: as soon as the covered bits of
 // a tile have been gathered its registers take the loads of the next tile, which are in flight while the tile is
-// scored; the lines of the tile after that are requested into L2 (no register cost).  Tiles past the lists hold the
+// scored.  (An additional prefetch.global.L2 of the tile after that was measured: 4.37 TB/s with it at distance 2,
+// 4.22 at distance 4, 4.66 without -- 32 warps x 2 KB in flight per SM already cover the latency.)  Tiles past the lists hold the
 // counted-only tail (single-posting lists of the scoring stream): gather and popcount, no per-list reduction.
 struct RangeState {
   TileLoad A;
@@ -189,10 +190,6 @@ __device__ __forceinline__ unsigned long long warp_count_run(const CountJob& J, 
   for (uint32_t wt = J.t_begin; wt < J.t_end; wt++) {
     const uint32_t h = tile_gather<SMEM_MASK>(S.A, J.mask);
     if (wt + 1u < J.t_end) tile_issue(S.A, wt + 1u, J.postings, tile_bound(J, wt + 1u), lane);
-    if (wt + 2u < J.t_end && lane < 16) {
-      const uint32_t q = (wt + 2u) * (uint32_t)CNT_TILE + (uint32_t)lane * 32u;
-      if (q < tile_bound(J, wt + 2u)) asm volatile("prefetch.global.L2 [%0];" ::"l"(J.postings + q));
-    }
     if (wt < J.list_tiles) {
       live += warp_count_tile(h, wt, J, S.W, carry, mymax, lane);
     } else {
