@@ -1,21 +1,19 @@
 // select.cu -- K3: the device-resident greedy set-cover loop.  Replaces find_candidates_kmers
 // (od-msspe/src/main.rs:331-406), find_most_freq_kmer (:285-329) and partition_tie_score (:261-283).
 //
-// Per iteration (one find_most_freq_kmer call of the reference) three kernels run back to back on one stream,
-// with no host round trip; a device-side `done` flag turns the remaining launches of a batch into no-ops:
-//   count_kernel   streams the CSR postings once (4 B per (segment,k-mer) record, 128-bit coalesced loads),
-//                  gathers the covered-segment bit of every posting from a shared-memory copy of the bitmask,
-//                  reduces per k-mer (segmented sum via a tile prefix), writes freq[], and atomically maxes the
-//                  best frequency.  This is the reference's recount, main.rs:292-309: one "coverage eval" per
-//                  live record.  HBM/L2-bound: algorithmic traffic 4 B per record.
-//   tie_kernel     scans freq[] for k-mers at the maximum and computes the partition-diversity score of each
-//                  with one warp per tied k-mer: sequential f32 adds in postings order over first-seen live
-//                  partitions, exactly main.rs:268-281; atomicMax on (score bits, ~code id) implements
-//                  `s1.partial_cmp(s2).then(k2.word.cmp(&k1.word))` under max_by (main.rs:320-324).
-//   update_kernel  applies main.rs:353-390: stop tests, push, mark every posting of the winner covered,
-//                  partition_coverage += 1 for each distinct partition of those postings.
-// MSSPE_SELECT_INCREMENTAL replaces count_kernel after the first iteration by decrements of freq[] through the
-// forward index for the newly covered segments (identical results, far less traffic).
+// Four implementations of the same loop live here; all return identical winners, frequencies, tie counts, f32 scores
+// and reference-equivalent evals (every parity test runs several of them):
+//   greedy_persistent_kernel    MSSPE_SELECT_RECOUNT: the reference's algorithm -- every live (segment, k-mer) record is
+//                               examined in every iteration (main.rs:292-309) -- as ONE cooperative launch for both
+//                               directions: phase A recount of a "scoring stream" against a shared-memory bitmask,
+//                               phase B arg-max with the partition-diversity tie score, two grid barriers per iteration;
+//                               the host compacts the stream between launches when less than half of it is live.
+//   greedy_incremental_kernel   MSSPE_SELECT_INCREMENTAL: counts kept exact through the forward index, histogram of
+//                               counts for the maximum; no shared-memory bitmask, any number of segments.
+//   count_kernel / tie_kernel / update_kernel (+ freq_max_kernel)   MSSPE_SELECT_BATCHED: the same phases as one launch
+//                               each per iteration (per-launch profiling; count_kernel also serves msspe_shard_count).
+// The building blocks of the recount and of the tie score are in select_device.cuh.  Also here: the scoring-stream
+// build and compaction, msspe_coverage, and the per-rank primitives of the genome-sharded loop (msspe_shard_*).
 #include <cooperative_groups.h>
 
 #include <algorithm>

@@ -1,5 +1,5 @@
-// select_device.cuh -- device building blocks of K3 shared by the launch-per-phase path (select.cu) and the
-// persistent cooperative kernel (select_persistent.cu).
+// select_device.cuh -- device building blocks of K3 shared by the kernels of select.cu: the warp-tile recount
+// (gather, packed scan, list windows, range carry) and the partition_tie_score variants.
 #pragma once
 #include "engine.cuh"
 
