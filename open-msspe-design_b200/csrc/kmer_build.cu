@@ -201,19 +201,29 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restri
   const uint64_t wbase = (uint64_t)blockIdx.x * RS_TILE + (uint64_t)warp * RS_WARP_TILE;
   uint64_t key[RS_ITEMS];
   uint32_t val[RS_ITEMS], rank[RS_ITEMS];
+  unsigned peers[RS_ITEMS];
 #pragma unroll
-  for (int i = 0; i < RS_ITEMS; i++) {
+  for (int i = 0; i < RS_ITEMS; i++) {  // all loads and all digit matches first: independent, their latencies overlap
     const uint64_t p = wbase + (uint64_t)i * 32 + lane;
     const bool in = p < n;
     key[i] = in ? keys[p] : 0ull;
     val[i] = in ? vals[p] : 0u;
+  }
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; i++) {
+    const bool in = wbase + (uint64_t)i * 32 + lane < n;
     const uint32_t d = in ? (uint32_t)((key[i] >> shift) & 0xFFu) : 0x100u;  // 0x100: out-of-range lanes group apart
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    const int leader = __ffs(peers) - 1;
+    peers[i] = __match_any_sync(0xffffffffu, d);
+  }
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; i++) {  // the counters advance in record order (stability): this part stays sequential
+    const bool in = wbase + (uint64_t)i * 32 + lane < n;
+    const uint32_t d = (uint32_t)((key[i] >> shift) & 0xFFu);
+    const int leader = __ffs(peers[i]) - 1;
     uint32_t old = 0;
-    if (in && lane == leader) { old = cnt[warp][d]; cnt[warp][d] = old + __popc(peers); }
+    if (in && lane == leader) { old = cnt[warp][d]; cnt[warp][d] = old + __popc(peers[i]); }
     old = __shfl_sync(0xffffffffu, old, leader);
-    rank[i] = old + __popc(peers & ((1u << lane) - 1u));
+    rank[i] = old + __popc(peers[i] & ((1u << lane) - 1u));
     __syncwarp();
   }
   __syncthreads();
