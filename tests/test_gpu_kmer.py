@@ -335,3 +335,23 @@ def test_global_bitmask_variant_many_segments():
     first = eng.select(0, 1, 10, 0)
     assert len(first) == 1 and eng.timing().select_evals[0] == eng.index(0)[1][-1]
     eng.close()
+
+
+def test_cfg5_shard_loop_variants_agree():
+    """One GPU's shard of BASELINE configs[4] (12,500 x 30 kb, 1.49 M segments, 2 x 56.5 M postings, larger than L2):
+    the recount kernel (with its stream compaction) and the incremental kernel return byte-identical winners, tie
+    counts, f32 scores and reference-equivalent evals over 300 iterations per direction; AUTO picks one of them."""
+    import msspe_b200 as m
+    from msspe_b200 import synth
+    g = synth.synth_genomes(12_500, 30_000, 5, clades=256, p_clade=0.10, p_leaf=0.01)
+    eng = m.Engine(13, 500, 250, 50)
+    eng.load_genomes(g.reshape(-1), synth.offsets_for(g))
+    eng.build_index()
+    assert eng.segment_info() == (12_500 * 119, 118, 38)
+    out = {}
+    for mode in (m.SELECT_RECOUNT, m.SELECT_INCREMENTAL, m.SELECT_AUTO):
+        a, b = eng.select_both(300, 10, mode)
+        out[mode] = (a.tobytes(), b.tobytes(), tuple(eng.timing().select_evals))
+        assert len(a) == 300 and len(b) == 300
+    assert out[m.SELECT_RECOUNT] == out[m.SELECT_INCREMENTAL] == out[m.SELECT_AUTO]
+    eng.close()
