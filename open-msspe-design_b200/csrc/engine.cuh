@@ -29,6 +29,7 @@ struct DirIndex {
   uint32_t* post_off = nullptr;  // [D+1] CSR offsets into postings
   uint32_t* postings = nullptr;  // [R] segment ids, ascending inside each list
   uint32_t* fwd_ids = nullptr;   // [G*s] code id per (segment, slot), 0xFFFFFFFF if none (forward index)
+  uint32_t* list_part = nullptr; // [D] partition_no shared by ALL postings of the list, or >= 2^31 when they span several
   // greedy state
   uint32_t* freq = nullptr;      // [D] live count per code
   unsigned long long* acc = nullptr;  // [D] arrival-counter|partial-sum for lists that span count tiles

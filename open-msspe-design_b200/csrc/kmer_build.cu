@@ -252,19 +252,32 @@ __global__ void mark_heads_kernel(const uint64_t* __restrict__ keys, uint64_t n,
 }
 
 // flags_scan[i] = exclusive scan of head flags; head(i) <=> (i == 0 || keys differ)
+// Also list_part[cid] (zeroed by the caller): the partition_no (main.rs:227) of the list's postings if they all share
+// one -- the rule in a pre-aligned alignment, where a word sits in the same column of every genome -- else bit 31 set.
+// partition_tie_score (main.rs:261-283) of such a list is 1/(partition_coverage[p] + 1) whichever postings are live.
 __global__ void build_csr_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ idx,
                                  const uint32_t* __restrict__ escan, uint64_t n, uint32_t slots, uint32_t n_codes,
                                  uint64_t* __restrict__ codes, uint32_t* __restrict__ post_off,
-                                 uint32_t* __restrict__ postings, uint32_t* __restrict__ fwd_ids) {
+                                 uint32_t* __restrict__ postings, uint32_t* __restrict__ fwd_ids,
+                                 const uint16_t* __restrict__ seg_part, uint32_t uniform_parts, uint32_t* __restrict__ list_part) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) post_off[n_codes] = (uint32_t)n;
   if (i >= n) return;
   const bool head = (i == 0 || keys[i] != keys[i - 1]);
   const uint32_t cid = escan[i] + (head ? 1u : 0u) - 1u;
   const uint32_t rec = idx[i];
-  postings[i] = rec / slots;
+  const uint32_t seg = rec / slots;
+  postings[i] = seg;
   fwd_ids[rec] = cid;
-  if (head) { codes[cid] = keys[i]; post_off[cid] = (uint32_t)i; }
+  const uint32_t part = uniform_parts ? seg % uniform_parts : (uint32_t)seg_part[seg];
+  if (head) {
+    codes[cid] = keys[i]; post_off[cid] = (uint32_t)i;
+    atomicOr(&list_part[cid], part);
+  } else {
+    const uint32_t pseg = idx[i - 1] / slots;
+    const uint32_t ppart = uniform_parts ? pseg % uniform_parts : (uint32_t)seg_part[pseg];
+    if (ppart != part) atomicOr(&list_part[cid], 0x80000000u);
+  }
 }
 
 }  // namespace
@@ -295,7 +308,7 @@ int msspe_radix_sort_pairs(msspe_ctx* c, uint64_t** key_a, uint32_t** val_a, uin
 namespace {
 
 void free_dir(msspe_ctx* c, DirIndex& d) {
-  msspe_dev_free(c, d.codes); msspe_dev_free(c, d.post_off); msspe_dev_free(c, d.postings); msspe_dev_free(c, d.fwd_ids); msspe_dev_free(c, d.freq);
+  msspe_dev_free(c, d.codes); msspe_dev_free(c, d.post_off); msspe_dev_free(c, d.postings); msspe_dev_free(c, d.fwd_ids); msspe_dev_free(c, d.list_part); msspe_dev_free(c, d.freq);
   msspe_dev_free(c, d.acc); msspe_dev_free(c, d.ignored); msspe_dev_free(c, d.cov); msspe_dev_free(c, d.pmark); msspe_dev_free(c, d.ctl); msspe_dev_free(c, d.out);
   msspe_dev_free(c, d.tile_first);
   msspe_dev_free(c, d.s_postings); msspe_dev_free(c, d.s_off); msspe_dev_free(c, d.s_id); msspe_dev_free(c, d.s_tile_first); msspe_dev_free(c, d.s_cost);
@@ -380,8 +393,11 @@ int build_direction(msspe_ctx* c, int dir, float* enc_ms, float* idx_ms) {
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.codes, (uint64_t)n_codes * 8, c->stream));
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.post_off, ((uint64_t)n_codes + 1) * 4, c->stream));
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.postings, (uint64_t)R * 4, c->stream));
+    MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.list_part, (uint64_t)(n_codes ? n_codes : 1) * 4, c->stream));
+    MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.list_part, 0, (uint64_t)(n_codes ? n_codes : 1) * 4, st));
     build_csr_kernel<<<(unsigned)div_up_u64(R, 256), 256, 0, st>>>(key_a, val_a, flags, R, slots, n_codes, D.codes,
-                                                                  D.post_off, D.postings, D.fwd_ids);
+                                                                  D.post_off, D.postings, D.fwd_ids, c->d_seg_part,
+                                                                  (c->uniform_parts && c->uniform_parts <= 65536u) ? c->uniform_parts : 0u, D.list_part);
     c->timing.kernel_launches++;
     MSSPE_CUDA_TRY(c, cudaGetLastError());
     MSSPE_CUDA_TRY(c, cudaFreeAsync(flags, st));
@@ -393,6 +409,7 @@ int build_direction(msspe_ctx* c, int dir, float* enc_ms, float* idx_ms) {
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.post_off, 4, c->stream));
     MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.post_off, 0, 4, st));
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.postings, 4, c->stream));
+    MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.list_part, 4, c->stream));
   }
   MSSPE_CUDA_TRY(c, cudaFreeAsync(key_a, st));
   MSSPE_CUDA_TRY(c, cudaFreeAsync(val_a, st));

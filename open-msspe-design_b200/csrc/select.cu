@@ -306,6 +306,7 @@ struct GreedyDir {
   const uint32_t* postings; const uint32_t* post_off; const uint32_t* tile_first; const uint64_t* codes;
   uint32_t n_codes, n_post, n_tiles, pad;
   const uint32_t* list_id;       // code id of every list of the scoring stream
+  const uint32_t* list_part;     // [D] by code id: the partition all postings of the list lie in, or >= 2^31 (several)
   uint32_t tail_t0, tail_t1, tail_end, stream_total;  // tiles / end of the counted-only tail; postings streamed per recount
   const uint32_t* full_off; const uint32_t* full_postings;  // the complete CSR: main.rs:371-378 walks ALL postings of a winner
   uint32_t done0, pad2;          // resumed launch: this direction had already finished
@@ -368,6 +369,22 @@ __device__ __forceinline__ void apply_winner_global(const GreedyDir& D, const ui
   __syncthreads();
 }
 
+// The same for one direction by HALF a block (threads [lt0, lt0 + THREADS/2)), without the block barriers: block 0
+// applies the winners of both directions side by side (two chains of four dependent L2 round trips in parallel
+// instead of one after the other).  The caller synchronises and calls clear_partition_marks afterwards.
+template <int THREADS>
+__device__ __forceinline__ void apply_winner_half(const GreedyDir& D, const uint16_t* __restrict__ seg_part, uint32_t uniform_parts, uint32_t code_id, uint32_t* pm, int lt) {
+  const uint32_t a = D.full_off[code_id], b = D.full_off[code_id + 1];
+  for (uint32_t i = a + lt; i < b; i += THREADS / 2) {
+    const uint32_t sg = __ldg(D.full_postings + i);
+    atomicOr(&D.ignored[sg >> 5], 1u << (sg & 31u));
+    const uint32_t p = partition_of(seg_part, uniform_parts, sg);
+    const uint32_t pbit = 1u << (p & 31u);
+    const uint32_t old = atomicOr(&pm[p >> 5], pbit);
+    if (!(old & pbit)) atomicAdd(&D.cov[p], 1u);
+  }
+}
+
 // The recount job of one warp for direction d (a literal at every call site).
 template <bool SMEM_MASK>
 __device__ __forceinline__ void make_job(CountJob& J, const GreedyArgs& A, const int d, uint32_t* smask, uint32_t t_begin, uint32_t t_end, uint32_t c_first) {
@@ -397,10 +414,10 @@ greedy_persistent_kernel(const GreedyArgs A) {
   __shared__ uint32_t s_cnt2[2], s_sc[2], s_max[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int WARPS = THREADS / 32;
-  // dynamic smem: [masks ndirs*mask_words] [pm p_words] [seen p_words] [fp n_fp] [lst n_fp (u64)] [cov 2*n_fp]
+  // dynamic smem: [masks ndirs*mask_words] [pm 2*p_words] [seen p_words] [fp n_fp] [lst n_fp (u64)] [cov 2*n_fp]
   uint32_t* smask = reinterpret_cast<uint32_t*>(dsm);
   uint32_t* pm = smask + (SMEM_MASK ? (size_t)A.ndirs * A.mask_words : 0);
-  uint32_t* seen = pm + A.p_words;
+  uint32_t* seen = pm + 2u * A.p_words;
   uint32_t* fp = seen + A.p_words;
   unsigned long long* lst = reinterpret_cast<unsigned long long*>(
       dsm + (((size_t)(reinterpret_cast<unsigned char*>(fp + A.n_fp) - dsm) + 7) & ~(size_t)7));
@@ -408,7 +425,7 @@ greedy_persistent_kernel(const GreedyArgs A) {
   if (SMEM_MASK)  // the global bitmask is all zero at the first launch and current at a resumed one
     for (int d = 0; d < A.ndirs; d++)
       for (uint32_t i = tid; i < A.mask_words; i += THREADS) smask[(size_t)d * A.mask_words + i] = __ldcg(A.d[d].ignored + i);
-  for (uint32_t i = tid; i < A.p_words; i += THREADS) pm[i] = 0u;
+  for (uint32_t i = tid; i < 2u * A.p_words; i += THREADS) pm[i] = 0u;
   if (tid == 0) { s_cnt2[0] = 0u; s_cnt2[1] = 0u; s_max[0] = 0u; s_max[1] = 0u; }
   __syncthreads();
   // block 0 keeps the global state (bitmask, partition_coverage, output); the other blocks score tiles
@@ -418,7 +435,8 @@ greedy_persistent_kernel(const GreedyArgs A) {
   bool done[2] = {A.d[0].done0 != 0u, A.ndirs < 2 || A.d[1].done0 != 0u};
   // block-uniform loop state lives in shared memory (every thread writes the same value before it reads it), so
   // that the streaming loop of phase A has the registers to itself
-  __shared__ uint32_t s_win[2], s_gsave[2];
+  __shared__ uint32_t s_win[2], s_gsave[2], s_gd[2], s_pl[2];
+  __shared__ unsigned long long s_key[2];
   __shared__ unsigned long long s_evals[2];
   __shared__ uint32_t s_live[2];  // this block's live postings of the current iteration
   if (tid == 0) { s_evals[0] = 0ull; s_evals[1] = 0ull; s_live[0] = 0u; s_live[1] = 0u; }
@@ -472,6 +490,7 @@ greedy_persistent_kernel(const GreedyArgs A) {
       else          { CountJob J; make_job<SMEM_MASK>(J, A, 1, smask, s_tb[warp], s_te[warp], s_cfirst[warp]); warp_count_begin(J, S, lane); }
     }
     if (it > A.it0) {  // main.rs:371-378 for the previous winners (a direction that is not done has pushed one per iteration)
+      const bool both = A.ndirs == 2 && !done[0] && !done[1];
       for (int d = 0; d < A.ndirs; d++) {
         if (done[d]) continue;
         const GreedyDir& D = A.d[d];
@@ -479,7 +498,13 @@ greedy_persistent_kernel(const GreedyArgs A) {
         const uint32_t a = D.post_off[s_win[d]], b = D.post_off[s_win[d] + 1];  // live part is enough for the bitmask
         if (SMEM_MASK)
           for (uint32_t i = a + tid; i < b; i += THREADS) { const uint32_t sg = __ldg(D.postings + i); atomicOr(&mask[sg >> 5], 1u << (sg & 31u)); }
-        if (blockIdx.x == 0) apply_winner_global<THREADS>(D, A.seg_part, A.uniform_parts, D.list_id[s_win[d]], pm);
+        if (blockIdx.x == 0 && !both) apply_winner_global<THREADS>(D, A.seg_part, A.uniform_parts, D.list_id[s_win[d]], pm);
+      }
+      if (blockIdx.x == 0 && both) {  // half a block per direction (the direction is a literal in each branch)
+        if (tid < THREADS / 2) apply_winner_half<THREADS>(A.d[0], A.seg_part, A.uniform_parts, A.d[0].list_id[s_win[0]], pm, tid);
+        else                   apply_winner_half<THREADS>(A.d[1], A.seg_part, A.uniform_parts, A.d[1].list_id[s_win[1]], pm + A.p_words, tid - THREADS / 2);
+        __syncthreads();
+        for (uint32_t i = tid; i < 2u * A.p_words; i += THREADS) pm[i] = 0u;
       }
       __syncthreads();
       if (!SMEM_MASK) grid_barrier(A.barrier, bar_target);  // the workers read the global bitmask block 0 has just updated
@@ -508,9 +533,9 @@ greedy_persistent_kernel(const GreedyArgs A) {
     // ---------------- phase B ----------------
     // Both directions at once: the maxima, this block's slice of both freq[] arrays and both partition_coverage
     // tables are requested before anything is waited for (one L2 round trip instead of one per direction and step).
-    uint32_t gd[2] = {0u, 0u};
-    for (int d = 0; d < A.ndirs; d++)
-      if (!done[d]) gd[d] = __ldcg(&A.d[d].ctl->pg[par]);
+    // One thread per direction fetches the maximum and shares it: the same word requested by every warp of the
+    // grid (4736 x 2 L2 requests for one line) is a hot spot in its L2 slice.
+    if (tid < 2 && tid < A.ndirs && !(tid == 0 ? done[0] : done[1])) s_gd[tid] = __ldcg(&A.d[tid].ctl->pg[par]);
     if (A.n_fp)  // partition_coverage of this iteration (block 0 finished updating it before the barrier)
       for (int d = 0; d < A.ndirs; d++)
         if (!done[d]) for (uint32_t q = tid; q < A.n_part; q += THREADS) s_cov[(size_t)d * A.n_fp + q] = __ldcg(A.d[d].cov + q);
@@ -525,6 +550,8 @@ greedy_persistent_kernel(const GreedyArgs A) {
           f_first[d][q] = (d < A.ndirs && !done[d] && cc < A.d[d].n_codes) ? __ldcg(A.d[d].freq + cc) : 0u;  // a maximum is >= 2
         }
     }
+    __syncthreads();
+    const uint32_t gd[2] = {done[0] ? 0u : s_gd[0], done[1] ? 0u : s_gd[1]};
     for (int d = 0; d < A.ndirs; d++) {
       if (done[d]) continue;
       const GreedyDir& D = A.d[d];
@@ -571,8 +598,22 @@ greedy_persistent_kernel(const GreedyArgs A) {
           __syncthreads();
           if (tid == 0) s_cnt2[d] = 0u;
         }
+        // A k-mer whose postings all lie in ONE partition p (list_part, fixed at index build; the rule in a pre-aligned
+        // alignment) scores 0.0 + 1/(partition_coverage[p] + 1) whichever of them are live: one thread each, no list scan.
+        if ((uint32_t)tid < nt) {
+          const uint32_t cc = tied[tid];
+          const uint32_t lp = __ldg(D.list_part + __ldg(D.list_id + cc));
+          if (!(lp >> 31)) {
+            const uint32_t cv = A.n_fp ? covp[lp] : __ldcg(D.cov + lp);
+            const float sc1 = __fdiv_rn(1.0f, __fadd_rn(__uint2float_rn(cv), 1.0f));
+            atomicMax(&D.ctl->pk[par], ((unsigned long long)__float_as_uint(sc1) << 32) | (unsigned long long)(0xFFFFFFFFu - cc));
+            tied[tid] = cc | 0x80000000u;  // scored
+          }
+        }
+        __syncthreads();
         for (uint32_t t = 0; t < nt; t++) {
           const uint32_t cc = tied[t];
+          if (cc >> 31) continue;  // block-uniform: scored above
           float score;
           if (A.n_fp) {
             score = block_tie_score<SMEM_MASK, false, THREADS>(cc, D.post_off, D.postings, mask, A.seg_part, A.uniform_parts, covp, A.n_part, fp, lst, s_sc);
@@ -597,10 +638,15 @@ greedy_persistent_kernel(const GreedyArgs A) {
     if (lead) s_tm[4] += globaltimer_ns() - s_tm[2];
     // ---------------- winner ----------------
     bool all_done = true;
+    if (tid < 2 && tid < A.ndirs && !(tid == 0 ? done[0] : done[1])) {  // again one thread per direction asks L2
+      s_key[tid] = __ldcg(&A.d[tid].ctl->pk[par]);
+      if (A.compact_min) s_pl[tid] = __ldcg(&A.d[tid].ctl->plive[par]);
+    }
+    __syncthreads();
     for (int d = 0; d < A.ndirs; d++) {
       if (done[d]) continue;
       const GreedyDir& D = A.d[d];
-      const unsigned long long key = __ldcg(&D.ctl->pk[par]);
+      const unsigned long long key = s_key[d];
       const uint32_t c = 0xFFFFFFFFu - (uint32_t)key;
       s_win[d] = c;
       const uint32_t g = s_gsave[d];
@@ -619,7 +665,7 @@ greedy_persistent_kernel(const GreedyArgs A) {
     if (A.compact_min) {  // less than half of what a running direction streams is still live: leave for a compaction
       bool leave = false;
       for (int d = 0; d < A.ndirs; d++)
-        if (!done[d] && A.d[d].stream_total >= A.compact_min && 2u * __ldcg(&A.d[d].ctl->plive[par]) < A.d[d].stream_total) leave = true;
+        if (!done[d] && A.d[d].stream_total >= A.compact_min && 2u * s_pl[d] < A.d[d].stream_total) leave = true;
       if (leave) {
         for (int d = 0; d < A.ndirs; d++) {
           if (done[d]) continue;
@@ -835,7 +881,9 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
   }
   A.n_part = c->max_partition + 1u;
   A.n_fp = A.n_part <= 4096u ? A.n_part : 0u;
-  const size_t aux = (size_t)2 * A.p_words * 4 + (size_t)A.n_fp * 4 + (size_t)A.n_fp * 8 + (size_t)2 * A.n_fp * 4 + 16;  // pm, seen, fp, lst, cov
+  // tied k-mers with short lists are scored by one warp each (a partition bitmap per warp); needs the shared-memory
+  // partition_coverage copy (n_fp) and small bitmaps
+  const size_t aux = (size_t)3 * A.p_words * 4 + (size_t)A.n_fp * 4 + (size_t)A.n_fp * 8 + (size_t)2 * A.n_fp * 4 + 16;  // pm (x2), seen, fp, lst, cov
   const size_t mask_bytes = (size_t)ndirs * A.mask_words * 4;
   const bool smem_mask = mask_bytes + aux + (size_t)4096 + 1024 <= c->smem_optin;
   const size_t smem = aux + (smem_mask ? mask_bytes : 0);
@@ -865,7 +913,7 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
       DirIndex& D = c->dir[dirs[i]];
       GreedyDir& g = A.d[i];
       const ScoreStream& S = cur[i];
-      g.postings = S.postings; g.post_off = S.off; g.tile_first = S.tile_first; g.codes = D.codes; g.list_id = S.id;
+      g.postings = S.postings; g.post_off = S.off; g.tile_first = S.tile_first; g.codes = D.codes; g.list_id = S.id; g.list_part = D.list_part;
       g.n_codes = S.lists; g.n_post = S.list_post; g.n_tiles = S.tiles;
       g.tail_t0 = S.tiles; g.tail_end = S.tail_end; g.tail_t1 = (uint32_t)div_up_u64(S.tail_end, CNT_TILE);
       g.stream_total = S.list_post + (S.tail_end - S.tiles * (uint32_t)CNT_TILE);
@@ -949,6 +997,7 @@ struct IncDir {
   SelectCtl* ctl; msspe_candidate* out;
   uint32_t n_codes, n_post, gmax0, pad;
   const uint32_t* by_freq;   // code ids by descending initial count (ties: ascending id)
+  const uint32_t* list_part; // [D] the partition all postings of the list lie in, or >= 2^31 (several)
   const uint32_t* cnt_ge;    // [gmax0 + 2] cnt_ge[f] = k-mers whose INITIAL count is >= f: only they can ever be at f
 };
 struct IncArgs {
@@ -987,6 +1036,7 @@ greedy_incremental_kernel(const IncArgs A) {
   __syncthreads();
   const bool lead = blockIdx.x == 0 && tid == 0;
   const bool tlead = blockIdx.x == (gridDim.x > 1 ? 1 : 0) && tid == 0;  // diagnostic clock of one block
+  __shared__ unsigned long long s_key[2];
   __shared__ unsigned long long s_t[6];  // 0 last stamp, 1 walk, 2 collect+score, 3 barrier 1, 4 apply, 5 barrier 2
   if (tid == 0) for (int q = 0; q < 6; q++) s_t[q] = 0ull;
   __syncthreads();
@@ -1081,8 +1131,21 @@ greedy_incremental_kernel(const IncArgs A) {
           __syncthreads();
           if (tid == 0) s_cnt2[d] = 0u;
         }
+        // single-partition lists (list_part): 0.0 + 1/(partition_coverage[p] + 1), one thread each, no list scan
+        if ((uint32_t)tid < nt) {
+          const uint32_t cc = tied[tid];
+          const uint32_t lp = __ldg(D.list_part + cc);
+          if (!(lp >> 31)) {
+            const uint32_t cv = A.n_fp ? s_cov[(size_t)d * A.n_fp + lp] : __ldcg(D.cov + lp);
+            const float sc1 = __fdiv_rn(1.0f, __fadd_rn(__uint2float_rn(cv), 1.0f));
+            atomicMax(&D.ctl->pk[par], ((unsigned long long)__float_as_uint(sc1) << 32) | (unsigned long long)(0xFFFFFFFFu - cc));
+            tied[tid] = cc | 0x80000000u;  // scored
+          }
+        }
+        __syncthreads();
         for (uint32_t t = 0; t < nt; t++) {
           const uint32_t cc = tied[t];
+          if (cc >> 31) continue;  // block-uniform: scored above
           float score;
           if (A.n_fp) {
             score = block_tie_score<false, false, THREADS>(cc, D.post_off, D.postings, D.ignored, A.seg_part, A.uniform_parts, s_cov + (size_t)d * A.n_fp, A.n_part, fp, lst, s_sc);
@@ -1104,11 +1167,14 @@ greedy_incremental_kernel(const IncArgs A) {
     INC_STAMP(3)
     // ---------------- phase 2 ----------------
     bool all_done = true;
+    // one thread per direction fetches the winner's key (every warp of the grid asking for the same word is an L2 hot spot)
+    if (tid < 2 && tid < A.ndirs && !(tid == 0 ? done[0] : done[1])) s_key[tid] = __ldcg(&A.d[tid].ctl->pk[par]);
+    __syncthreads();
     for (int d = 0; d < A.ndirs; d++) {
       if (done[d]) continue;
       const IncDir& D = A.d[d];
       const uint32_t g = s_g[d];
-      const unsigned long long key = __ldcg(&D.ctl->pk[par]);
+      const unsigned long long key = s_key[d];
       const uint32_t c = 0xFFFFFFFFu - (uint32_t)key;
       if (lead) {
         msspe_candidate w;
@@ -1149,8 +1215,18 @@ greedy_incremental_kernel(const IncArgs A) {
           uint32_t f0 = 0u, f1 = 0u;
           if (id0 != 0xFFFFFFFFu) f0 = atomicSub(&D.freq[id0], 1u);
           if (id1 != 0xFFFFFFFFu) f1 = atomicSub(&D.freq[id1], 1u);
-          if (id0 != 0xFFFFFFFFu) { atomicSub(&D.hist[f0], 1u); atomicAdd(&D.hist[f0 - 1u], 1u); dec++; }
-          if (id1 != 0xFFFFFFFFu) { atomicSub(&D.hist[f1], 1u); atomicAdd(&D.hist[f1 - 1u], 1u); dec++; }
+          // neighbouring k-mers of a window mostly have the same count: one histogram update per distinct count
+          // of the warp instead of one per k-mer (late in a run all counts fall into a handful of bins)
+          {
+            const bool on0 = id0 != 0xFFFFFFFFu, on1 = id1 != 0xFFFFFFFFu;
+            const unsigned g0 = __match_any_sync(0xffffffffu, on0 ? f0 : 0xFFFFFF00u + (uint32_t)lane);
+            if (on0 && lane == __ffs(g0) - 1) { const uint32_t n = (uint32_t)__popc(g0); atomicSub(&D.hist[f0], n); atomicAdd(&D.hist[f0 - 1u], n); }
+            if (A.slots > 32u) {
+              const unsigned g1 = __match_any_sync(0xffffffffu, on1 ? f1 : 0xFFFFFF00u + (uint32_t)lane);
+              if (on1 && lane == __ffs(g1) - 1) { const uint32_t n = (uint32_t)__popc(g1); atomicSub(&D.hist[f1], n); atomicAdd(&D.hist[f1 - 1u], n); }
+            }
+            dec += (on0 ? 1u : 0u) + (on1 ? 1u : 0u);
+          }
           for (uint32_t q = lane + 64u; q < A.slots; q += 32) {
             const uint32_t id = __ldg(fw + q);
             if (id != 0xFFFFFFFFu) {
@@ -1172,8 +1248,9 @@ greedy_incremental_kernel(const IncArgs A) {
     if (all_done) break;
     grid_barrier_cg();
     INC_STAMP(5)
-    for (int d = 0; d < A.ndirs; d++)
-      if (!done[d]) live[d] -= (unsigned long long)__ldcg(&A.d[d].ctl->plive[par]);
+    if (lead)  // only the lead thread reports evals
+      for (int d = 0; d < A.ndirs; d++)
+        if (!done[d]) live[d] -= (unsigned long long)__ldcg(&A.d[d].ctl->plive[par]);
   }
 #undef INC_STAMP
   if (tlead) for (int q = 0; q < 5; q++) A.d[0].ctl->t_dbg[q] = s_t[q + 1];
@@ -1254,7 +1331,7 @@ int run_select_incremental(msspe_ctx* c, int ndirs, const int* dirs, uint32_t ma
     g.post_off = D.post_off; g.postings = D.postings; g.codes = D.codes; g.fwd_ids = D.fwd_ids; g.freq = D.freq; g.hist = d_hist[i];
     g.ignored = D.ignored; g.cov = D.cov; g.pmark = d_pmark[i]; g.ctl = D.ctl; g.out = D.out;
     g.n_codes = (uint32_t)D.n_codes; g.n_post = (uint32_t)D.n_records; g.gmax0 = gmax0;
-    g.by_freq = d_byfreq[i]; g.cnt_ge = d_cntge[i];
+    g.by_freq = d_byfreq[i]; g.cnt_ge = d_cntge[i]; g.list_part = D.list_part;
   }
   const size_t smem = (size_t)A.p_words * 4 + (size_t)A.n_fp * 4 + (size_t)A.n_fp * 8 + (size_t)2 * A.n_fp * 4 + 32;
   void* fn = (void*)greedy_incremental_kernel<512>;
