@@ -47,7 +47,7 @@ struct DirIndex {
   bool stream_built = false;
   uint32_t* s_postings = nullptr;   // [R]   lists region [0, s_list_post), tail [s_list_post, R)
   uint32_t* s_off = nullptr;        // [s_lists + 1]
-  uint32_t* s_id = nullptr;         // [s_lists] code id of each stream list
+  uint4* s_id = nullptr;            // [s_lists] per stream list: code id, list_part, its range in the complete CSR
   uint32_t* s_tile_first = nullptr; // [s_tiles]
   uint32_t* s_cost = nullptr;       // [tiles + 2] exclusive prefix of the tile costs (range balancing)
   uint32_t s_lists = 0, s_list_post = 0, s_tiles = 0;
@@ -78,6 +78,7 @@ struct SelectCtl {
   unsigned long long t_tie_ns;     // time inside the tie-break phases
   unsigned long long t_total_ns;
   unsigned long long t_dbg[8];     // fine-grained phase timers of block 0 (diagnostic)
+  unsigned long long t_fine[24];   // per-step clocks, only written by a -DMSSPE_FINE_TIMERS build (diagnostic)
 };
 
 struct msspe_ctx {

@@ -65,15 +65,15 @@ __global__ void stream_flag_kernel(const uint32_t* __restrict__ post_off, uint32
 __global__ void __launch_bounds__(256)
 stream_copy_kernel(const uint32_t* __restrict__ post_off, const uint32_t* __restrict__ postings, uint32_t n_codes,
                    const uint32_t* __restrict__ rank, const uint32_t* __restrict__ moff, uint32_t n_lists, uint32_t n_list_post,
-                   uint32_t tail_begin,
-                   uint32_t* __restrict__ s_postings, uint32_t* __restrict__ s_off, uint32_t* __restrict__ s_id) {
+                   uint32_t tail_begin, const uint32_t* __restrict__ list_part,
+                   uint32_t* __restrict__ s_postings, uint32_t* __restrict__ s_off, uint4* __restrict__ s_id) {
   const int lane = threadIdx.x & 31;
   const uint32_t c = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u + (uint32_t)lane;
   uint32_t a = 0, len = 0, dst = 0;
   if (c < n_codes) {
     a = post_off[c]; len = post_off[c + 1] - a;
     const uint32_t r = rank[c];
-    if (len >= 2u) { dst = moff[c]; s_off[r] = dst; s_id[r] = c; }
+    if (len >= 2u) { dst = moff[c]; s_off[r] = dst; s_id[r] = make_uint4(c, list_part[c], a, a + len); }
     else if (len == 1u) dst = tail_begin + (c - r);  // singles before c = c - (lists with >= 2 postings before c)
     if (len <= 8u) for (uint32_t i = 0; i < len; i++) s_postings[dst + i] = postings[a + i];
   }
@@ -116,11 +116,11 @@ stream_live_kernel(const uint32_t* __restrict__ s_off, const uint32_t* __restric
 // order-preserving move of the live postings: lists that still have >= 2 of them keep a list (new rank = number of
 // such lists before), a list left with one contributes it to the counted-only tail, dead lists vanish
 __global__ void __launch_bounds__(256)
-stream_compact_kernel(const uint32_t* __restrict__ s_off, const uint32_t* __restrict__ s_postings, const uint32_t* __restrict__ s_id,
+stream_compact_kernel(const uint32_t* __restrict__ s_off, const uint32_t* __restrict__ s_postings, const uint4* __restrict__ s_id,
                       uint32_t n_lists, const uint32_t* __restrict__ ignored, const uint32_t* __restrict__ cnt,
                       const uint32_t* __restrict__ rank, const uint32_t* __restrict__ moff, const uint32_t* __restrict__ srank,
                       uint32_t new_lists, uint32_t new_list_post, uint32_t new_tail_begin, uint32_t* __restrict__ n_postings,
-                      uint32_t* __restrict__ n_off, uint32_t* __restrict__ n_id) {
+                      uint32_t* __restrict__ n_off, uint4* __restrict__ n_id) {
   const int lane = threadIdx.x & 31;
   const uint32_t c = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u + (uint32_t)lane;
   uint32_t a = 0, len = 0, dst = 0, n = 0;
@@ -305,8 +305,8 @@ update_kernel(const uint64_t* __restrict__ codes, const uint32_t* __restrict__ p
 struct GreedyDir {
   const uint32_t* postings; const uint32_t* post_off; const uint32_t* tile_first; const uint64_t* codes;
   uint32_t n_codes, n_post, n_tiles, pad;
-  const uint32_t* list_id;       // code id of every list of the scoring stream
-  const uint32_t* list_part;     // [D] by code id: the partition all postings of the list lie in, or >= 2^31 (several)
+  const uint4* list_id;          // per list of the scoring stream: .x code id, .y the partition ALL its postings lie in or >= 2^31 (several),
+                                 // .z/.w its range in the complete CSR (full_postings)
   uint32_t tail_t0, tail_t1, tail_end, stream_total;  // tiles / end of the counted-only tail; postings streamed per recount
   const uint32_t* full_off; const uint32_t* full_postings;  // the complete CSR: main.rs:371-378 walks ALL postings of a winner
   uint32_t done0, pad2;          // resumed launch: this direction had already finished
@@ -353,9 +353,10 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // compacted stream no longer holds, hence the complete CSR) is marked in the global bitmask, and every distinct
 // partition among them gets partition_coverage += 1.  pm = shared-memory partition bitmap, left zeroed.
 template <int THREADS>
-__device__ __forceinline__ void apply_winner_global(const GreedyDir& D, const uint16_t* __restrict__ seg_part, uint32_t uniform_parts, uint32_t code_id, uint32_t* pm) {
+__device__ __forceinline__ void apply_winner_global(const GreedyDir& D, const uint16_t* __restrict__ seg_part, uint32_t uniform_parts, uint32_t list, uint32_t* pm) {
   const int tid = threadIdx.x;
-  const uint32_t a = D.full_off[code_id], b = D.full_off[code_id + 1];
+  const uint4 e = __ldg(D.list_id + list);  // .z/.w: the list's range in the complete CSR
+  const uint32_t a = e.z, b = e.w;
   for (uint32_t i = a + tid; i < b; i += THREADS) {
     const uint32_t sg = __ldg(D.full_postings + i);
     atomicOr(&D.ignored[sg >> 5], 1u << (sg & 31u));
@@ -373,8 +374,9 @@ __device__ __forceinline__ void apply_winner_global(const GreedyDir& D, const ui
 // applies the winners of both directions side by side (two chains of four dependent L2 round trips in parallel
 // instead of one after the other).  The caller synchronises and calls clear_partition_marks afterwards.
 template <int THREADS>
-__device__ __forceinline__ void apply_winner_half(const GreedyDir& D, const uint16_t* __restrict__ seg_part, uint32_t uniform_parts, uint32_t code_id, uint32_t* pm, int lt) {
-  const uint32_t a = D.full_off[code_id], b = D.full_off[code_id + 1];
+__device__ __forceinline__ void apply_winner_half(const GreedyDir& D, const uint16_t* __restrict__ seg_part, uint32_t uniform_parts, uint32_t list, uint32_t* pm, int lt) {
+  const uint4 e = __ldg(D.list_id + list);
+  const uint32_t a = e.z, b = e.w;
   for (uint32_t i = a + lt; i < b; i += THREADS / 2) {
     const uint32_t sg = __ldg(D.full_postings + i);
     atomicOr(&D.ignored[sg >> 5], 1u << (sg & 31u));
@@ -383,6 +385,19 @@ __device__ __forceinline__ void apply_winner_half(const GreedyDir& D, const uint
     const uint32_t old = atomicOr(&pm[p >> 5], pbit);
     if (!(old & pbit)) atomicAdd(&D.cov[p], 1u);
   }
+}
+
+// Tied k-mers whose postings all lie in one partition (list_id[].y < 2^31): score = 0.0 + 1/(partition_coverage + 1),
+// one thread each; scored entries of tied[] are flagged with bit 31.  (Tie-storm chunks; the usual case is inlined.)
+__device__ __forceinline__ void single_partition_ties(const GreedyDir& D, uint32_t* tied, uint32_t nt, const uint32_t* covp, bool cov_shared, int par, int tid) {
+  if ((uint32_t)tid >= nt) return;
+  const uint32_t cc = tied[tid];
+  const uint4 e = __ldg(D.list_id + cc);
+  if (e.y >> 31) return;
+  const uint32_t cv = cov_shared ? covp[e.y] : __ldcg(D.cov + e.y);
+  const float sc1 = __fdiv_rn(1.0f, __fadd_rn(__uint2float_rn(cv), 1.0f));
+  atomicMax(&D.ctl->pk[par], ((unsigned long long)__float_as_uint(sc1) << 32) | (unsigned long long)(0xFFFFFFFFu - cc));
+  tied[tid] = cc | 0x80000000u;
 }
 
 // The recount job of one warp for direction d (a literal at every call site).
@@ -426,7 +441,15 @@ greedy_persistent_kernel(const GreedyArgs A) {
     for (int d = 0; d < A.ndirs; d++)
       for (uint32_t i = tid; i < A.mask_words; i += THREADS) smask[(size_t)d * A.mask_words + i] = __ldcg(A.d[d].ignored + i);
   for (uint32_t i = tid; i < 2u * A.p_words; i += THREADS) pm[i] = 0u;
-  if (tid == 0) { s_cnt2[0] = 0u; s_cnt2[1] = 0u; s_max[0] = 0u; s_max[1] = 0u; }
+  // Every block keeps its own copy of both partition_coverage tables in shared memory: loaded here (zero at the
+  // first launch, current at a resumed one), then kept up to date from the winners (a winner whose postings lie in one
+  // partition raises exactly that entry; the rare multi-partition winner makes the block reload the table).  296 blocks
+  // fetching the same few lines every iteration was a 1 us hot spot in L2.
+  __shared__ uint32_t s_reload[2];
+  if (A.n_fp)
+    for (int d = 0; d < A.ndirs; d++)
+      for (uint32_t q = tid; q < A.n_part; q += THREADS) s_cov[(size_t)d * A.n_fp + q] = __ldcg(A.d[d].cov + q);
+  if (tid == 0) { s_cnt2[0] = 0u; s_cnt2[1] = 0u; s_max[0] = 0u; s_max[1] = 0u; s_reload[0] = 0u; s_reload[1] = 0u; }
   __syncthreads();
   // block 0 keeps the global state (bitmask, partition_coverage, output); the other blocks score tiles
   const bool solo = gridDim.x == 1;
@@ -435,11 +458,11 @@ greedy_persistent_kernel(const GreedyArgs A) {
   bool done[2] = {A.d[0].done0 != 0u, A.ndirs < 2 || A.d[1].done0 != 0u};
   // block-uniform loop state lives in shared memory (every thread writes the same value before it reads it), so
   // that the streaming loop of phase A has the registers to itself
-  __shared__ uint32_t s_win[2], s_gsave[2], s_gd[2], s_pl[2];
-  __shared__ unsigned long long s_key[2];
+  __shared__ uint32_t s_win[2], s_gsave[2], s_gd[2], s_pl[2], s_pt[2], s_npush[2];
+  __shared__ unsigned long long s_key[2], s_pread[2];
   __shared__ unsigned long long s_evals[2];
   __shared__ uint32_t s_live[2];  // this block's live postings of the current iteration
-  if (tid == 0) { s_evals[0] = 0ull; s_evals[1] = 0ull; s_live[0] = 0u; s_live[1] = 0u; }
+  if (tid == 0) { s_evals[0] = 0ull; s_evals[1] = 0ull; s_live[0] = 0u; s_live[1] = 0u; s_pread[0] = 0ull; s_pread[1] = 0ull; s_npush[0] = A.it0; s_npush[1] = A.it0; }
   __syncthreads();
   // first k-mer of this warp's tile range; recomputed only when the set of running directions changes
   __shared__ uint32_t s_cfirst[WARPS], s_tb[WARPS], s_te[WARPS];  // this warp's cost-balanced tile range
@@ -451,6 +474,13 @@ greedy_persistent_kernel(const GreedyArgs A) {
   if (tid == 0) for (int q = 0; q < 12; q++) s_tm[q] = 0ull;
   __syncthreads();
   if (lead) s_tm[0] = globaltimer_ns();
+#ifdef MSSPE_FINE_TIMERS  // build-time diagnostic: per-step clocks of worker block 1 (slots 0..11) and block 0 (12..23)
+  __shared__ unsigned long long s_ft[12], s_flast;
+  if (tid == 0) { for (int q = 0; q < 12; q++) s_ft[q] = 0ull; s_flast = globaltimer_ns(); }
+#define FSTAMP(k) if ((wlead || lead) && tid == 0) { const unsigned long long t_ = globaltimer_ns(); s_ft[k] += t_ - s_flast; s_flast = t_; }
+#else
+#define FSTAMP(k)
+#endif
   for (uint32_t it = A.it0;; it++) {
     const int par = it & 1;
     if (lead) s_tm[1] = globaltimer_ns();
@@ -491,6 +521,11 @@ greedy_persistent_kernel(const GreedyArgs A) {
     }
     if (it > A.it0) {  // main.rs:371-378 for the previous winners (a direction that is not done has pushed one per iteration)
       const bool both = A.ndirs == 2 && !done[0] && !done[1];
+      uint4 we = make_uint4(0u, 0xFFFFFFFFu, 0u, 0u);  // thread d: the winner's list entry, for the block's partition_coverage copy
+      if (A.n_fp) {
+        if (tid == 0 && !done[0]) we = __ldg(A.d[0].list_id + s_win[0]);
+        else if (tid == 1 && A.ndirs > 1 && !done[1]) we = __ldg(A.d[1].list_id + s_win[1]);
+      }
       for (int d = 0; d < A.ndirs; d++) {
         if (done[d]) continue;
         const GreedyDir& D = A.d[d];
@@ -498,17 +533,22 @@ greedy_persistent_kernel(const GreedyArgs A) {
         const uint32_t a = D.post_off[s_win[d]], b = D.post_off[s_win[d] + 1];  // live part is enough for the bitmask
         if (SMEM_MASK)
           for (uint32_t i = a + tid; i < b; i += THREADS) { const uint32_t sg = __ldg(D.postings + i); atomicOr(&mask[sg >> 5], 1u << (sg & 31u)); }
-        if (blockIdx.x == 0 && !both) apply_winner_global<THREADS>(D, A.seg_part, A.uniform_parts, D.list_id[s_win[d]], pm);
+        if (blockIdx.x == 0 && !both) apply_winner_global<THREADS>(D, A.seg_part, A.uniform_parts, s_win[d], pm);
       }
       if (blockIdx.x == 0 && both) {  // half a block per direction (the direction is a literal in each branch)
-        if (tid < THREADS / 2) apply_winner_half<THREADS>(A.d[0], A.seg_part, A.uniform_parts, A.d[0].list_id[s_win[0]], pm, tid);
-        else                   apply_winner_half<THREADS>(A.d[1], A.seg_part, A.uniform_parts, A.d[1].list_id[s_win[1]], pm + A.p_words, tid - THREADS / 2);
+        if (tid < THREADS / 2) apply_winner_half<THREADS>(A.d[0], A.seg_part, A.uniform_parts, s_win[0], pm, tid);
+        else                   apply_winner_half<THREADS>(A.d[1], A.seg_part, A.uniform_parts, s_win[1], pm + A.p_words, tid - THREADS / 2);
         __syncthreads();
         for (uint32_t i = tid; i < 2u * A.p_words; i += THREADS) pm[i] = 0u;
+      }
+      if (we.y != 0xFFFFFFFFu) {  // threads 0 / 1 of a direction that pushed a winner
+        if (!(we.y >> 31)) s_cov[(size_t)tid * A.n_fp + we.y] += 1u;
+        else s_reload[tid] = 1u;
       }
       __syncthreads();
       if (!SMEM_MASK) grid_barrier(A.barrier, bar_target);  // the workers read the global bitmask block 0 has just updated
     }
+    FSTAMP(0)
     if (worker) {
       uint32_t mymax = 0;
       unsigned long long live;
@@ -518,6 +558,7 @@ greedy_persistent_kernel(const GreedyArgs A) {
       for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
       if (lane == 0) { if (mymax) atomicMax(&s_max[myd], mymax); if (live) atomicAdd(&s_live[myd], (uint32_t)live); }
     }
+    FSTAMP(1)
     __syncthreads();
     if (tid == 0 && worker)
       for (int d = 0; d < A.ndirs; d++)
@@ -527,7 +568,9 @@ greedy_persistent_kernel(const GreedyArgs A) {
           s_evals[d] += s_live[d]; s_max[d] = 0u; s_live[d] = 0u;
         }
     if (wlead) { const unsigned long long t = globaltimer_ns(); s_tm[8] += t - s_tm[5]; s_tm[5] = t; }
+    FSTAMP(2)
     grid_barrier(A.barrier, bar_target);
+    FSTAMP(3)
     if (wlead) { const unsigned long long t = globaltimer_ns(); s_tm[9] += t - s_tm[5]; s_tm[5] = t; }
     if (lead) { s_tm[2] = globaltimer_ns(); s_tm[3] += s_tm[2] - s_tm[1]; }
     // ---------------- phase B ----------------
@@ -536,9 +579,9 @@ greedy_persistent_kernel(const GreedyArgs A) {
     // One thread per direction fetches the maximum and shares it: the same word requested by every warp of the
     // grid (4736 x 2 L2 requests for one line) is a hot spot in its L2 slice.
     if (tid < 2 && tid < A.ndirs && !(tid == 0 ? done[0] : done[1])) s_gd[tid] = __ldcg(&A.d[tid].ctl->pg[par]);
-    if (A.n_fp)  // partition_coverage of this iteration (block 0 finished updating it before the barrier)
+    if (A.n_fp)  // a multi-partition winner: re-read the table (block 0 finished updating it before the barrier)
       for (int d = 0; d < A.ndirs; d++)
-        if (!done[d]) for (uint32_t q = tid; q < A.n_part; q += THREADS) s_cov[(size_t)d * A.n_fp + q] = __ldcg(A.d[d].cov + q);
+        if (!done[d] && s_reload[d]) for (uint32_t q = tid; q < A.n_part; q += THREADS) s_cov[(size_t)d * A.n_fp + q] = __ldcg(A.d[d].cov + q);
     uint32_t f_first[2][2];
     {
       const uint32_t stride = gridDim.x * THREADS, c = blockIdx.x * THREADS + tid;
@@ -551,13 +594,16 @@ greedy_persistent_kernel(const GreedyArgs A) {
         }
     }
     __syncthreads();
+    FSTAMP(4)
+    if (tid == 0) { s_reload[0] = 0u; s_reload[1] = 0u; }
     const uint32_t gd[2] = {done[0] ? 0u : s_gd[0], done[1] ? 0u : s_gd[1]};
     for (int d = 0; d < A.ndirs; d++) {
       if (done[d]) continue;
       const GreedyDir& D = A.d[d];
       const uint32_t g = gd[d];
       s_gsave[d] = g;
-      if (lead) { D.ctl->pg[par ^ 1] = 0; D.ctl->pt[par ^ 1] = 0; D.ctl->pk[par ^ 1] = 0ull; D.ctl->plive[par ^ 1] = 0; D.ctl->postings_read += D.stream_total; }  // next iteration's slots
+      // next iteration's slots: plain stores only -- block 0 is on the critical path of every barrier, its lead thread must not wait for L2
+      if (lead) { D.ctl->pg[par ^ 1] = 0; D.ctl->pt[par ^ 1] = 0; D.ctl->pk[par ^ 1] = 0ull; D.ctl->plive[par ^ 1] = 0; s_pread[d] += D.stream_total; }
       if (g <= 1u) {  // None or freq == 1: stop before the push (main.rs:353-366)
         done[d] = true;
         if (lead) { D.ctl->iterations = it + 1; D.ctl->n_out = it; D.ctl->done = 1; }
@@ -575,6 +621,43 @@ greedy_persistent_kernel(const GreedyArgs A) {
       }
     }
     __syncthreads();
+    FSTAMP(5)
+    // A k-mer whose postings all lie in ONE partition p (list_id[].y, fixed at index build; the rule in a pre-aligned
+    // alignment) scores 0.0 + 1/(partition_coverage[p] + 1) whichever of them are live: one thread each, no list scan,
+    // both directions in the same round trip.  What is scored here is flagged (bit 31) in the tied list.
+    {
+      const bool on0 = !done[0] && s_cnt2[0] <= (uint32_t)THREADS, on1 = A.ndirs > 1 && !done[1] && s_cnt2[1] <= (uint32_t)THREADS;
+      uint4 e0 = make_uint4(0u, 0x80000000u, 0u, 0u), e1 = e0;
+      const uint32_t c0 = on0 && (uint32_t)tid < s_cnt2[0] ? s_tied[tid] : 0xFFFFFFFFu;
+      const uint32_t c1 = on1 && (uint32_t)tid < s_cnt2[1] ? s_tied[THREADS + tid] : 0xFFFFFFFFu;
+      if (c0 != 0xFFFFFFFFu) e0 = __ldg(A.d[0].list_id + c0);
+      if (c1 != 0xFFFFFFFFu) e1 = __ldg(A.d[1].list_id + c1);
+      if (!(e0.y >> 31)) {
+        const uint32_t cv = A.n_fp ? s_cov[e0.y] : __ldcg(A.d[0].cov + e0.y);
+        const float sc1 = __fdiv_rn(1.0f, __fadd_rn(__uint2float_rn(cv), 1.0f));
+        atomicMax(&A.d[0].ctl->pk[par], ((unsigned long long)__float_as_uint(sc1) << 32) | (unsigned long long)(0xFFFFFFFFu - c0));
+        s_tied[tid] = c0 | 0x80000000u;
+      }
+      if (!(e1.y >> 31)) {
+        const uint32_t cv = A.n_fp ? s_cov[(size_t)A.n_fp + e1.y] : __ldcg(A.d[1].cov + e1.y);
+        const float sc1 = __fdiv_rn(1.0f, __fadd_rn(__uint2float_rn(cv), 1.0f));
+        atomicMax(&A.d[1].ctl->pk[par], ((unsigned long long)__float_as_uint(sc1) << 32) | (unsigned long long)(0xFFFFFFFFu - c1));
+        s_tied[THREADS + tid] = c1 | 0x80000000u;
+      }
+    }
+    // the usual case ends here: everything tied in this block was scored above (one barrier, which also tells)
+    const uint32_t nh0 = done[0] ? 0u : s_cnt2[0], nh1 = (A.ndirs < 2 || done[1]) ? 0u : s_cnt2[1];
+    const bool mine_left = ((uint32_t)tid < min(nh0, (uint32_t)THREADS) && !(s_tied[tid] >> 31)) ||
+                           ((uint32_t)tid < min(nh1, (uint32_t)THREADS) && !(s_tied[THREADS + tid] >> 31)) ||
+                           nh0 > (uint32_t)THREADS || nh1 > (uint32_t)THREADS;
+    const bool slow = __syncthreads_or(mine_left ? 1 : 0) != 0;
+    FSTAMP(6)
+    if (!slow && tid == 0) {
+      if (nh0) atomicAdd(&A.d[0].ctl->pt[par], nh0);
+      if (nh1) atomicAdd(&A.d[1].ctl->pt[par], nh1);
+      s_cnt2[0] = 0u; s_cnt2[1] = 0u;
+    }
+    if (slow)
     for (int d = 0; d < A.ndirs; d++) {
       if (done[d]) continue;
       const GreedyDir& D = A.d[d];
@@ -598,19 +681,10 @@ greedy_persistent_kernel(const GreedyArgs A) {
           __syncthreads();
           if (tid == 0) s_cnt2[d] = 0u;
         }
-        // A k-mer whose postings all lie in ONE partition p (list_part, fixed at index build; the rule in a pre-aligned
-        // alignment) scores 0.0 + 1/(partition_coverage[p] + 1) whichever of them are live: one thread each, no list scan.
-        if ((uint32_t)tid < nt) {
-          const uint32_t cc = tied[tid];
-          const uint32_t lp = __ldg(D.list_part + __ldg(D.list_id + cc));
-          if (!(lp >> 31)) {
-            const uint32_t cv = A.n_fp ? covp[lp] : __ldcg(D.cov + lp);
-            const float sc1 = __fdiv_rn(1.0f, __fadd_rn(__uint2float_rn(cv), 1.0f));
-            atomicMax(&D.ctl->pk[par], ((unsigned long long)__float_as_uint(sc1) << 32) | (unsigned long long)(0xFFFFFFFFu - cc));
-            tied[tid] = cc | 0x80000000u;  // scored
-          }
+        if (n_here > (uint32_t)THREADS) {  // (the usual case was scored before this loop, both directions at once)
+          single_partition_ties(D, tied, nt, covp, A.n_fp != 0u, par, tid);
+          __syncthreads();
         }
-        __syncthreads();
         for (uint32_t t = 0; t < nt; t++) {
           const uint32_t cc = tied[t];
           if (cc >> 31) continue;  // block-uniform: scored above
@@ -633,16 +707,20 @@ greedy_persistent_kernel(const GreedyArgs A) {
       __syncthreads();
     }
     if (wlead) { const unsigned long long t = globaltimer_ns(); s_tm[10] += t - s_tm[5]; s_tm[5] = t; }
+    FSTAMP(7)
     grid_barrier(A.barrier, bar_target);
+    FSTAMP(8)
     if (wlead) { const unsigned long long t = globaltimer_ns(); s_tm[11] += t - s_tm[5]; s_tm[5] = t; }
     if (lead) s_tm[4] += globaltimer_ns() - s_tm[2];
     // ---------------- winner ----------------
     bool all_done = true;
     if (tid < 2 && tid < A.ndirs && !(tid == 0 ? done[0] : done[1])) {  // again one thread per direction asks L2
       s_key[tid] = __ldcg(&A.d[tid].ctl->pk[par]);
+      if (blockIdx.x == 0) s_pt[tid] = __ldcg(&A.d[tid].ctl->pt[par]);
       if (A.compact_min) s_pl[tid] = __ldcg(&A.d[tid].ctl->plive[par]);
     }
     __syncthreads();
+    FSTAMP(9)
     for (int d = 0; d < A.ndirs; d++) {
       if (done[d]) continue;
       const GreedyDir& D = A.d[d];
@@ -652,8 +730,10 @@ greedy_persistent_kernel(const GreedyArgs A) {
       const uint32_t g = s_gsave[d];
       if (lead) {
         msspe_candidate w;
-        w.code = D.codes[D.list_id[c]]; w.freq = g; w.n_tied = __ldcg(&D.ctl->pt[par]); w.tie_score = __uint_as_float((uint32_t)(key >> 32)); w.reserved = 0;
+        // .code holds the stream list for now; the words are filled in when the launch ends (no dependent loads here)
+        w.code = c; w.freq = g; w.n_tied = s_pt[d]; w.tie_score = __uint_as_float((uint32_t)(key >> 32)); w.reserved = 0;
         D.out[it] = w;  // a direction that is not done has pushed one winner per iteration
+        s_npush[d] = it + 1u;
       }
       if (g < A.mms || it + 1u >= A.max_iter) {  // main.rs:387-390 and the loop bound :344
         done[d] = true;
@@ -661,6 +741,7 @@ greedy_persistent_kernel(const GreedyArgs A) {
       }
       all_done = all_done && done[d];
     }
+    FSTAMP(10)
     if (all_done) break;
     if (A.compact_min) {  // less than half of what a running direction streams is still live: leave for a compaction
       bool leave = false;
@@ -669,17 +750,27 @@ greedy_persistent_kernel(const GreedyArgs A) {
       if (leave) {
         for (int d = 0; d < A.ndirs; d++) {
           if (done[d]) continue;
-          if (blockIdx.x == 0) apply_winner_global<THREADS>(A.d[d], A.seg_part, A.uniform_parts, A.d[d].list_id[s_win[d]], pm);  // nothing stays pending
+          if (blockIdx.x == 0) apply_winner_global<THREADS>(A.d[d], A.seg_part, A.uniform_parts, s_win[d], pm);  // nothing stays pending
           if (lead) { A.d[d].ctl->resume_it = it + 1u; A.d[d].ctl->exit_compact = 1u; }
         }
         break;
       }
     }
   }
+  if (blockIdx.x == 0) {  // the winners of this launch: stream list -> word
+    __syncthreads();
+    for (int d = 0; d < A.ndirs; d++)
+      for (uint32_t i = A.it0 + tid; i < s_npush[d]; i += THREADS)
+        A.d[d].out[i].code = A.d[d].codes[__ldg(A.d[d].list_id + (uint32_t)A.d[d].out[i].code).x];
+  }
   for (int d = 0; d < A.ndirs; d++) {
+    if (lead) A.d[d].ctl->postings_read += s_pread[d];
     if (tid == 0 && s_evals[d]) atomicAdd(&A.d[d].ctl->evals, s_evals[d]);
     if (lead) { A.d[d].ctl->t_count_ns += s_tm[3]; A.d[d].ctl->t_tie_ns += s_tm[4]; A.d[d].ctl->t_total_ns += globaltimer_ns() - s_tm[0]; }
     if (wlead) for (int q = 0; q < 4; q++) A.d[d].ctl->t_dbg[4 + q] += s_tm[8 + q];
+#ifdef MSSPE_FINE_TIMERS
+    if (d == 0 && (wlead || lead)) for (int q = 0; q < 12; q++) A.d[0].ctl->t_fine[(lead ? 12 : 0) + q] += s_ft[q];
+#endif
   }
 }
 
@@ -771,7 +862,7 @@ void launch_iteration(msspe_ctx* c, DirRun& r, uint32_t max_iter, uint32_t mms, 
 
 // The stream a direction currently scores: the pristine one of the index, or a compacted working copy.
 struct ScoreStream {
-  uint32_t* postings; uint32_t* off; uint32_t* id; uint32_t* tile_first; uint32_t* cost;
+  uint32_t* postings; uint32_t* off; uint4* id; uint32_t* tile_first; uint32_t* cost;
   uint32_t lists, list_post, tiles, tail_end;
   bool owned;
 };
@@ -818,7 +909,7 @@ int compact_stream(msspe_ctx* c, DirIndex& D, ScoreStream& S, cudaStream_t st) {
   const uint64_t cap = (uint64_t)n_tail_begin + tot[2] + (S.tail_end - tail_begin) + CNT_TILE;
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&N.postings, cap * 4, c->stream));
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&N.off, ((uint64_t)N.lists + 1) * 4, c->stream));
-  MSSPE_CUDA_TRY(c, cudaMallocAsync(&N.id, ((uint64_t)N.lists + 1) * 4, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&N.id, ((uint64_t)N.lists + 1) * 16, c->stream));
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&N.tile_first, ((uint64_t)N.tiles + 1) * 4, c->stream));
   if (nl) {
     stream_compact_kernel<<<(unsigned)div_up_u64(nl, 256), 256, 0, st>>>(S.off, S.postings, S.id, nl, D.ignored, cnt, multi, mlen, single, N.lists,
@@ -913,7 +1004,7 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
       DirIndex& D = c->dir[dirs[i]];
       GreedyDir& g = A.d[i];
       const ScoreStream& S = cur[i];
-      g.postings = S.postings; g.post_off = S.off; g.tile_first = S.tile_first; g.codes = D.codes; g.list_id = S.id; g.list_part = D.list_part;
+      g.postings = S.postings; g.post_off = S.off; g.tile_first = S.tile_first; g.codes = D.codes; g.list_id = S.id;
       g.n_codes = S.lists; g.n_post = S.list_post; g.n_tiles = S.tiles;
       g.tail_t0 = S.tiles; g.tail_end = S.tail_end; g.tail_t1 = (uint32_t)div_up_u64(S.tail_end, CNT_TILE);
       g.stream_total = S.list_post + (S.tail_end - S.tiles * (uint32_t)CNT_TILE);
@@ -968,6 +1059,14 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
     if (getenv("MSSPE_DEBUG_TIMERS") && i == 0)
       fprintf(stderr, "[msspe] persistent greedy: total %.3f ms (wall %.3f), iterations %u | coverage-scoring phases %.3f ms, arg-max phases %.3f ms (block 0 clock, barriers included)\n",
               c->h_ctl[i].t_total_ns * 1e-6, ms, c->h_ctl[i].iterations, c->h_ctl[i].t_count_ns * 1e-6, c->h_ctl[i].t_tie_ns * 1e-6);
+    if (getenv("MSSPE_DEBUG_TIMERS") && i == 0 && c->h_ctl[i].t_fine[3]) {
+      fprintf(stderr, "[msspe]   fine (us/iteration) 0 update+sync | 1 count | 2 sync+atomics | 3 barrier1 | 4 max | 5 collect | 6 single-partition ties | 7 other ties | 8 barrier2 | 9 key | 10 winner\n");
+      for (int b = 0; b < 2; b++) {
+        fprintf(stderr, "[msspe]   %s:", b ? "block 0" : "block 1");
+        for (int q = 0; q < 11; q++) fprintf(stderr, " %.2f", c->h_ctl[i].t_fine[12 * b + q] * 1e-3 / (c->h_ctl[i].iterations ? c->h_ctl[i].iterations : 1));
+        fprintf(stderr, "\n");
+      }
+    }
     if (getenv("MSSPE_DEBUG_TIMERS") && i == 0)
       fprintf(stderr, "[msspe]   worker block 1: phaseA work %.3f sync %.3f | phaseB work %.3f sync %.3f ms\n", c->h_ctl[i].t_dbg[4] * 1e-6,
               c->h_ctl[i].t_dbg[5] * 1e-6, c->h_ctl[i].t_dbg[6] * 1e-6, c->h_ctl[i].t_dbg[7] * 1e-6);
@@ -1037,8 +1136,10 @@ greedy_incremental_kernel(const IncArgs A) {
   const bool lead = blockIdx.x == 0 && tid == 0;
   const bool tlead = blockIdx.x == (gridDim.x > 1 ? 1 : 0) && tid == 0;  // diagnostic clock of one block
   __shared__ unsigned long long s_key[2];
+  __shared__ uint32_t s_npush[2];  // winners pushed (lead thread)
+  __shared__ uint32_t s_reload[2]; // the last winner's postings span several partitions: re-read partition_coverage
   __shared__ unsigned long long s_t[6];  // 0 last stamp, 1 walk, 2 collect+score, 3 barrier 1, 4 apply, 5 barrier 2
-  if (tid == 0) for (int q = 0; q < 6; q++) s_t[q] = 0ull;
+  if (tid == 0) { for (int q = 0; q < 6; q++) s_t[q] = 0ull; s_npush[0] = 0u; s_npush[1] = 0u; s_reload[0] = 0u; s_reload[1] = 0u; }
   __syncthreads();
   if (tlead) s_t[0] = globaltimer_ns();
 #define INC_STAMP(slot) if (tlead) { const unsigned long long t_ = globaltimer_ns(); s_t[slot] += t_ - s_t[0]; s_t[0] = t_; }
@@ -1049,13 +1150,16 @@ greedy_incremental_kernel(const IncArgs A) {
     // in the same pass (early on the occupied bins are far apart: a serial walk would be hundreds of dependent L2 loads).
     // The thread that finds the maximum already holds hist[max] (the tie count) and has asked for cnt_ge[max] too.
     // In the same round trip: this iteration's partition_coverage tables into shared memory.
+    // (the block's copy of partition_coverage is kept up to date from the winners; a multi-partition winner -- rare --
+    // makes it re-read the table here)
     if (A.n_fp)
       for (int d = 0; d < A.ndirs; d++)
-        if (!done[d]) for (uint32_t q = tid; q < A.n_part; q += THREADS) s_cov[(size_t)d * A.n_fp + q] = __ldcg(A.d[d].cov + q);
+        if (!done[d] && (it == 0 || s_reload[d])) for (uint32_t q = tid; q < A.n_part; q += THREADS) s_cov[(size_t)d * A.n_fp + q] = __ldcg(A.d[d].cov + q);
     {
       uint32_t g[2] = {s_g[0], s_g[1]};
       bool open[2] = {!done[0], A.ndirs > 1 && !done[1]};
       __syncthreads();
+      if (tid == 0) { s_reload[0] = 0u; s_reload[1] = 0u; }
       while (open[0] || open[1]) {
         uint32_t hv[2] = {0u, 0u}, cg_[2] = {0u, 0u}, mine[2] = {0u, 0u};
 #pragma unroll
@@ -1110,6 +1214,34 @@ greedy_incremental_kernel(const IncArgs A) {
       }
     }
     __syncthreads();
+    // The usual case: the block's ties fit the lists and all of them lie in one partition each (list_part): score =
+    // 0.0 + 1/(partition_coverage[p] + 1), one thread per tied k-mer, both directions in one round trip, one barrier.
+    bool slow;
+    {
+      const uint32_t nh0 = done[0] ? 0u : s_cnt2[0], nh1 = (A.ndirs < 2 || done[1]) ? 0u : s_cnt2[1];
+      const bool fit = nh0 <= (uint32_t)THREADS && nh1 <= (uint32_t)THREADS;
+      const uint32_t c0 = fit && (uint32_t)tid < nh0 ? s_tied[tid] : 0xFFFFFFFFu;
+      const uint32_t c1 = fit && (uint32_t)tid < nh1 ? s_tied[THREADS + tid] : 0xFFFFFFFFu;
+      uint32_t lp0 = 0x80000000u, lp1 = 0x80000000u;
+      if (c0 != 0xFFFFFFFFu) lp0 = __ldg(A.d[0].list_part + c0);
+      if (c1 != 0xFFFFFFFFu) lp1 = __ldg(A.d[1].list_part + c1);
+      if (!(lp0 >> 31)) {
+        const uint32_t cv = A.n_fp ? s_cov[lp0] : __ldcg(A.d[0].cov + lp0);
+        const float sc1 = __fdiv_rn(1.0f, __fadd_rn(__uint2float_rn(cv), 1.0f));
+        atomicMax(&A.d[0].ctl->pk[par], ((unsigned long long)__float_as_uint(sc1) << 32) | (unsigned long long)(0xFFFFFFFFu - c0));
+        s_tied[tid] = c0 | 0x80000000u;
+      }
+      if (!(lp1 >> 31)) {
+        const uint32_t cv = A.n_fp ? s_cov[(size_t)A.n_fp + lp1] : __ldcg(A.d[1].cov + lp1);
+        const float sc1 = __fdiv_rn(1.0f, __fadd_rn(__uint2float_rn(cv), 1.0f));
+        atomicMax(&A.d[1].ctl->pk[par], ((unsigned long long)__float_as_uint(sc1) << 32) | (unsigned long long)(0xFFFFFFFFu - c1));
+        s_tied[THREADS + tid] = c1 | 0x80000000u;
+      }
+      const bool mine_left = !fit || (c0 != 0xFFFFFFFFu && (lp0 >> 31)) || (c1 != 0xFFFFFFFFu && (lp1 >> 31));
+      slow = __syncthreads_or(mine_left ? 1 : 0) != 0;
+      if (!slow && tid == 0) { s_cnt2[0] = 0u; s_cnt2[1] = 0u; }
+    }
+    if (slow)
     for (int d = 0; d < A.ndirs; d++) {
       if (done[d]) continue;
       const IncDir& D = A.d[d];
@@ -1131,8 +1263,8 @@ greedy_incremental_kernel(const IncArgs A) {
           __syncthreads();
           if (tid == 0) s_cnt2[d] = 0u;
         }
-        // single-partition lists (list_part): 0.0 + 1/(partition_coverage[p] + 1), one thread each, no list scan
-        if ((uint32_t)tid < nt) {
+        // tie-storm chunks: single-partition lists as above (the usual case was scored and flagged before this loop)
+        if (n_here > (uint32_t)THREADS && (uint32_t)tid < nt) {
           const uint32_t cc = tied[tid];
           const uint32_t lp = __ldg(D.list_part + cc);
           if (!(lp >> 31)) {
@@ -1178,7 +1310,8 @@ greedy_incremental_kernel(const IncArgs A) {
       const uint32_t c = 0xFFFFFFFFu - (uint32_t)key;
       if (lead) {
         msspe_candidate w;
-        w.code = D.codes[c]; w.freq = g; w.n_tied = s_nt[d]; w.tie_score = __uint_as_float((uint32_t)(key >> 32)); w.reserved = 0;
+        w.code = c; w.freq = g; w.n_tied = s_nt[d];  // the word is filled in after the loop (no dependent load here)
+        s_npush[d] = it + 1u; w.tie_score = __uint_as_float((uint32_t)(key >> 32)); w.reserved = 0;
         D.out[it] = w;
         D.ctl->pk[par ^ 1] = 0ull; D.ctl->plive[par ^ 1] = 0u;  // next iteration's slots (nobody reads them in this phase)
       }
@@ -1188,6 +1321,10 @@ greedy_incremental_kernel(const IncArgs A) {
         continue;
       }
       all_done = false;
+      if (A.n_fp && tid == 32 * d) {  // this block's partition_coverage copy
+        const uint32_t lp = __ldg(D.list_part + c);
+        if (!(lp >> 31)) s_cov[(size_t)d * A.n_fp + lp] += 1u; else s_reload[d] = 1u;
+      }
       // main.rs:371-378 over the whole grid, then the decrements of the newly covered segments
       uint32_t* pmark = D.pmark + (size_t)par * 2048u;
       if (blockIdx.x == 0) for (uint32_t q = tid; q < 2048u; q += THREADS) D.pmark[(size_t)(par ^ 1) * 2048u + q] = 0u;
@@ -1253,6 +1390,13 @@ greedy_incremental_kernel(const IncArgs A) {
         if (!done[d]) live[d] -= (unsigned long long)__ldcg(&A.d[d].ctl->plive[par]);
   }
 #undef INC_STAMP
+  if (blockIdx.x == 0) {  // winners: code id -> word
+    __syncthreads();
+    for (int d = 0; d < A.ndirs; d++) {
+      const uint32_t n = s_npush[d];
+      for (uint32_t i = tid; i < n; i += THREADS) A.d[d].out[i].code = A.d[d].codes[(uint32_t)A.d[d].out[i].code];
+    }
+  }
   if (tlead) for (int q = 0; q < 5; q++) A.d[0].ctl->t_dbg[q] = s_t[q + 1];
 }
 
@@ -1500,11 +1644,11 @@ int msspe_select_prepare_stream(msspe_ctx* c, int dir, cudaStream_t st) {
   const uint32_t tail_begin = D.s_tiles * (uint32_t)CNT_TILE;  // the tail starts on a tile boundary
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.s_postings, ((uint64_t)R + CNT_TILE) * 4, c->stream));
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.s_off, ((uint64_t)D.s_lists + 1) * 4, c->stream));
-  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.s_id, ((uint64_t)D.s_lists + 1) * 4, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.s_id, ((uint64_t)D.s_lists + 1) * 16, c->stream));
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.s_tile_first, ((uint64_t)D.s_tiles + 1) * 4, c->stream));
   if (nc) {
     stream_copy_kernel<<<(unsigned)div_up_u64(nc, 256), 256, 0, st>>>(D.post_off, D.postings, nc, multi, mlen, D.s_lists, D.s_list_post,
-                                                                      tail_begin, D.s_postings, D.s_off, D.s_id);
+                                                                      tail_begin, D.list_part, D.s_postings, D.s_off, D.s_id);
     c->timing.kernel_launches++;
   } else {
     MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.s_off, 0, 4, st));
