@@ -1129,8 +1129,12 @@ greedy_incremental_kernel(const IncArgs A) {
   uint32_t* s_cov = reinterpret_cast<uint32_t*>(lst + A.n_fp);  // [2][n_fp] this iteration's partition_coverage
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned int bar_target = 0;
-  bool done[2] = {false, A.ndirs < 2};
-  unsigned long long live[2] = {A.d[0].n_post, A.ndirs > 1 ? A.d[1].n_post : 0ull}, evals[2] = {0ull, 0ull};
+  // bit d = direction d is finished.  A register: a bool[2] indexed by a loop variable lives in LOCAL memory, and the
+  // fence of every grid barrier invalidates L1, so each `if (DONE(d))` after a barrier was a round trip to L2.
+  uint32_t donem = A.ndirs < 2 ? 2u : 0u;
+#define DONE(d) ((donem >> (d)) & 1u)
+  __shared__ unsigned long long live[2], evals[2];  // the lead thread's bookkeeping of reference-equivalent evals
+  if (tid == 0) { live[0] = A.d[0].n_post; live[1] = A.ndirs > 1 ? A.d[1].n_post : 0ull; evals[0] = 0ull; evals[1] = 0ull; }
   if (tid == 0) { s_cnt2[0] = s_cnt2[1] = 0u; s_g[0] = A.d[0].gmax0; s_g[1] = A.ndirs > 1 ? A.d[1].gmax0 : 0u; s_dec = 0u; }
   __syncthreads();
   const bool lead = blockIdx.x == 0 && tid == 0;
@@ -1154,10 +1158,10 @@ greedy_incremental_kernel(const IncArgs A) {
     // makes it re-read the table here)
     if (A.n_fp)
       for (int d = 0; d < A.ndirs; d++)
-        if (!done[d] && (it == 0 || s_reload[d])) for (uint32_t q = tid; q < A.n_part; q += THREADS) s_cov[(size_t)d * A.n_fp + q] = __ldcg(A.d[d].cov + q);
+        if (!DONE(d) && (it == 0 || s_reload[d])) for (uint32_t q = tid; q < A.n_part; q += THREADS) s_cov[(size_t)d * A.n_fp + q] = __ldcg(A.d[d].cov + q);
     {
       uint32_t g[2] = {s_g[0], s_g[1]};
-      bool open[2] = {!done[0], A.ndirs > 1 && !done[1]};
+      bool open[2] = {!DONE(0), A.ndirs > 1 && !DONE(1)};
       __syncthreads();
       if (tid == 0) { s_reload[0] = 0u; s_reload[1] = 0u; }
       while (open[0] || open[1]) {
@@ -1193,12 +1197,12 @@ greedy_incremental_kernel(const IncArgs A) {
     }
     INC_STAMP(1)
     for (int d = 0; d < A.ndirs; d++) {
-      if (done[d]) continue;
+      if (DONE(d)) continue;
       const IncDir& D = A.d[d];
       const uint32_t g = s_g[d];
-      evals[d] += live[d];                                     // what the recount of this call would have examined
+      if (lead) evals[d] += live[d];                           // what the recount of this call would have examined
       if (g <= 1u) {  // None or freq == 1: stop before the push (main.rs:353-366)
-        done[d] = true;
+        donem |= 1u << (d);
         if (lead) { D.ctl->iterations = it + 1; D.ctl->n_out = it; D.ctl->done = 1; D.ctl->evals = evals[d]; }
         continue;
       }
@@ -1218,7 +1222,7 @@ greedy_incremental_kernel(const IncArgs A) {
     // 0.0 + 1/(partition_coverage[p] + 1), one thread per tied k-mer, both directions in one round trip, one barrier.
     bool slow;
     {
-      const uint32_t nh0 = done[0] ? 0u : s_cnt2[0], nh1 = (A.ndirs < 2 || done[1]) ? 0u : s_cnt2[1];
+      const uint32_t nh0 = DONE(0) ? 0u : s_cnt2[0], nh1 = (A.ndirs < 2 || DONE(1)) ? 0u : s_cnt2[1];
       const bool fit = nh0 <= (uint32_t)THREADS && nh1 <= (uint32_t)THREADS;
       const uint32_t c0 = fit && (uint32_t)tid < nh0 ? s_tied[tid] : 0xFFFFFFFFu;
       const uint32_t c1 = fit && (uint32_t)tid < nh1 ? s_tied[THREADS + tid] : 0xFFFFFFFFu;
@@ -1243,7 +1247,7 @@ greedy_incremental_kernel(const IncArgs A) {
     }
     if (slow)
     for (int d = 0; d < A.ndirs; d++) {
-      if (done[d]) continue;
+      if (DONE(d)) continue;
       const IncDir& D = A.d[d];
       const uint32_t g = s_g[d];
       uint32_t* tied = s_tied + d * THREADS;
@@ -1300,10 +1304,10 @@ greedy_incremental_kernel(const IncArgs A) {
     // ---------------- phase 2 ----------------
     bool all_done = true;
     // one thread per direction fetches the winner's key (every warp of the grid asking for the same word is an L2 hot spot)
-    if (tid < 2 && tid < A.ndirs && !(tid == 0 ? done[0] : done[1])) s_key[tid] = __ldcg(&A.d[tid].ctl->pk[par]);
+    if (tid < 2 && tid < A.ndirs && !DONE(tid)) s_key[tid] = __ldcg(&A.d[tid].ctl->pk[par]);
     __syncthreads();
     for (int d = 0; d < A.ndirs; d++) {
-      if (done[d]) continue;
+      if (DONE(d)) continue;
       const IncDir& D = A.d[d];
       const uint32_t g = s_g[d];
       const unsigned long long key = s_key[d];
@@ -1316,7 +1320,7 @@ greedy_incremental_kernel(const IncArgs A) {
         D.ctl->pk[par ^ 1] = 0ull; D.ctl->plive[par ^ 1] = 0u;  // next iteration's slots (nobody reads them in this phase)
       }
       if (g < A.mms || it + 1u >= A.max_iter) {  // main.rs:387-390 and the loop bound :344
-        done[d] = true;
+        donem |= 1u << (d);
         if (lead) { D.ctl->iterations = it + 1; D.ctl->n_out = it + 1u; D.ctl->done = 1; D.ctl->evals = evals[d]; }
         continue;
       }
@@ -1387,7 +1391,7 @@ greedy_incremental_kernel(const IncArgs A) {
     INC_STAMP(5)
     if (lead)  // only the lead thread reports evals
       for (int d = 0; d < A.ndirs; d++)
-        if (!done[d]) live[d] -= (unsigned long long)__ldcg(&A.d[d].ctl->plive[par]);
+        if (!DONE(d)) live[d] -= (unsigned long long)__ldcg(&A.d[d].ctl->plive[par]);
   }
 #undef INC_STAMP
   if (blockIdx.x == 0) {  // winners: code id -> word
@@ -1399,6 +1403,7 @@ greedy_incremental_kernel(const IncArgs A) {
   }
   if (tlead) for (int q = 0; q < 5; q++) A.d[0].ctl->t_dbg[q] = s_t[q + 1];
 }
+#undef DONE
 
 int run_select_incremental(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max_iter, uint32_t mms,
                            msspe_candidate** outs, uint32_t** n_outs) {
