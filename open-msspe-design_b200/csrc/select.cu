@@ -578,7 +578,9 @@ greedy_persistent_kernel(const GreedyArgs A) {
     // tables are requested before anything is waited for (one L2 round trip instead of one per direction and step).
     // One thread per direction fetches the maximum and shares it: the same word requested by every warp of the
     // grid (4736 x 2 L2 requests for one line) is a hot spot in its L2 slice.
-    if (tid < 2 && tid < A.ndirs && !(tid == 0 ? done[0] : done[1])) s_gd[tid] = __ldcg(&A.d[tid].ctl->pg[par]);
+    // (unconditionally: done[] is indexed by loop variables and lives in local memory, whose L1 lines the barrier's fence
+    // has just invalidated -- testing it first would put a second L2 round trip in front of this load)
+    if (tid < 2 && tid < A.ndirs) s_gd[tid] = __ldcg(&A.d[tid].ctl->pg[par]);
     if (A.n_fp)  // a multi-partition winner: re-read the table (block 0 finished updating it before the barrier)
       for (int d = 0; d < A.ndirs; d++)
         if (!done[d] && s_reload[d]) for (uint32_t q = tid; q < A.n_part; q += THREADS) s_cov[(size_t)d * A.n_fp + q] = __ldcg(A.d[d].cov + q);
@@ -590,7 +592,7 @@ greedy_persistent_kernel(const GreedyArgs A) {
 #pragma unroll
         for (int q = 0; q < 2; q++) {
           const uint32_t cc = c + (uint32_t)q * stride;
-          f_first[d][q] = (d < A.ndirs && !done[d] && cc < A.d[d].n_codes) ? __ldcg(A.d[d].freq + cc) : 0u;  // a maximum is >= 2
+          f_first[d][q] = (d < A.ndirs && cc < A.d[d].n_codes) ? __ldcg(A.d[d].freq + cc) : 0u;  // a maximum is >= 2; a finished direction is skipped below
         }
     }
     __syncthreads();
