@@ -67,7 +67,7 @@ typedef struct {
 /* How the device-resident greedy loop recomputes frequencies each iteration. Results are identical. */
 #define MSSPE_SELECT_RECOUNT 0     /* re-stream every posting each iteration = main.rs:292-309 */
 #define MSSPE_SELECT_INCREMENTAL 1 /* decrement counts of k-mers in newly covered segments */
-#define MSSPE_SELECT_AUTO 2        /* whichever is faster for the input: incremental from 2^24 postings per direction on */
+#define MSSPE_SELECT_AUTO 2        /* whichever is faster for the input: incremental from 2^21 postings per direction on */
 #define MSSPE_SELECT_BATCHED 0x100 /* OR-able: one launch per phase instead of the persistent cooperative kernel */
 
 /* NtthalOptions, delta_g.rs:18-25 (without the threshold), and Primer3's thal_args. */

@@ -1144,6 +1144,7 @@ greedy_incremental_kernel(const IncArgs A) {
   __shared__ unsigned long long s_key[2];
   __shared__ uint32_t s_npush[2];  // winners pushed (lead thread)
   __shared__ uint32_t s_reload[2]; // the last winner's postings span several partitions: re-read partition_coverage
+  __shared__ uint32_t s_wa[2], s_wb[2], s_wp[2];  // the winner's posting range and list_part (fetched by one thread per direction)
   __shared__ unsigned long long s_t[6];  // 0 last stamp, 1 walk, 2 collect+score, 3 barrier 1, 4 apply, 5 barrier 2
   if (tid == 0) { for (int q = 0; q < 6; q++) s_t[q] = 0ull; s_npush[0] = 0u; s_npush[1] = 0u; s_reload[0] = 0u; s_reload[1] = 0u; }
   __syncthreads();
@@ -1306,7 +1307,15 @@ greedy_incremental_kernel(const IncArgs A) {
     // ---------------- phase 2 ----------------
     bool all_done = true;
     // one thread per direction fetches the winner's key (every warp of the grid asking for the same word is an L2 hot spot)
-    if (tid < 2 && tid < A.ndirs && !DONE(tid)) s_key[tid] = __ldcg(&A.d[tid].ctl->pk[par]);
+    // ... and the winner's posting range and list_part, so that 296 requests instead of 4736 go to those lines
+    if (tid < 2 && tid < A.ndirs && !DONE(tid)) {
+      const unsigned long long key = __ldcg(&A.d[tid].ctl->pk[par]);
+      const uint32_t c = 0xFFFFFFFFu - (uint32_t)key;
+      s_key[tid] = key;
+      if (c < A.d[tid].n_codes) {
+        s_wa[tid] = __ldg(A.d[tid].post_off + c); s_wb[tid] = __ldg(A.d[tid].post_off + c + 1u); s_wp[tid] = __ldg(A.d[tid].list_part + c);
+      }
+    }
     __syncthreads();
     for (int d = 0; d < A.ndirs; d++) {
       if (DONE(d)) continue;
@@ -1328,13 +1337,13 @@ greedy_incremental_kernel(const IncArgs A) {
       }
       all_done = false;
       if (A.n_fp && tid == 32 * d) {  // this block's partition_coverage copy
-        const uint32_t lp = __ldg(D.list_part + c);
+        const uint32_t lp = s_wp[d];
         if (!(lp >> 31)) s_cov[(size_t)d * A.n_fp + lp] += 1u; else s_reload[d] = 1u;
       }
       // main.rs:371-378 over the whole grid, then the decrements of the newly covered segments
       uint32_t* pmark = D.pmark + (size_t)par * 2048u;
       if (blockIdx.x == 0) for (uint32_t q = tid; q < 2048u; q += THREADS) D.pmark[(size_t)(par ^ 1) * 2048u + q] = 0u;
-      const uint32_t a = D.post_off[c], b = D.post_off[c + 1];
+      const uint32_t a = s_wa[d], b = s_wb[d];
       uint32_t dec = 0;
       // one warp per posting, dealt out over the whole grid: lane 0 marks the segment (bitmask, partition_coverage); if it
       // was not covered before, the 32 lanes take its k-mers (forward index): each loses one live segment
@@ -1530,10 +1539,11 @@ int run_select(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max_iter, uint
   const bool batched = (mode & MSSPE_SELECT_BATCHED) != 0;
   mode &= ~(uint32_t)MSSPE_SELECT_BATCHED;
   if (mode > MSSPE_SELECT_AUTO) { c->set_error("msspe_select: unknown mode %u", mode); return MSSPE_ERR_INVALID; }
-  if (mode == MSSPE_SELECT_AUTO) {  // measured on B200: on par up to cfg3 (15 M postings per direction), incremental ahead beyond
+  if (mode == MSSPE_SELECT_AUTO) {  // measured on B200: incremental ahead at cfg2 (4.5 M postings per direction: 8.6 vs 9.4 ms), cfg3 (16.8 vs
+                                    // 23.4 ms) and beyond; below that its set-up (order by initial count, histogram) is what counts
     uint64_t most = 0;
     for (int i = 0; i < ndirs; i++) most = std::max<uint64_t>(most, c->dir[dirs[i]].n_records);
-    mode = most >= (1ull << 24) ? MSSPE_SELECT_INCREMENTAL : MSSPE_SELECT_RECOUNT;
+    mode = most >= (1ull << 21) ? MSSPE_SELECT_INCREMENTAL : MSSPE_SELECT_RECOUNT;
   }
   MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
   if (!batched && mode == MSSPE_SELECT_INCREMENTAL && max_iter > 0) return run_select_incremental(c, ndirs, dirs, max_iter, mms, outs, n_outs);
