@@ -14,6 +14,7 @@
 #include <thread>
 
 #include "engine.cuh"
+#include <chrono>
 
 struct msspe_fasta {
   std::vector<std::string> names;
@@ -87,6 +88,14 @@ int parse_fasta(const char* path, uint32_t threads, msspe_fasta* F, const std::f
   }
   const uint8_t* s = M.p;
   const uint64_t n = M.n;
+  const bool dbg = getenv("MSSPE_DEBUG_TIMERS") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!dbg) return;
+    const auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[msspe] fasta: %s %.3f s\n", what, std::chrono::duration<double>(t - t_last).count());
+    t_last = t;
+  };
   // 1. record starts: '>' at the start of a line
   std::vector<uint64_t> starts;
   {
@@ -112,6 +121,7 @@ int parse_fasta(const char* path, uint32_t threads, msspe_fasta* F, const std::f
     for_lines(s, 0, lim, [&](uint64_t b, uint64_t e) { if (e > b) bad = true; });
     if (bad) { set_err(err, err_len, "called `Result::unwrap()` on an `Err` value: InvalidStart (FASTA must begin with '>')"); return MSSPE_ERR_INVALID; }
   }
+  lap("record starts");
   const uint64_t nrec = starts.size();
   if (nrec >= 0xFFFFFFFFull) { set_err(err, err_len, "too many records"); return MSSPE_ERR_CAPACITY; }
   F->names.assign(nrec, std::string());
@@ -136,7 +146,9 @@ int parse_fasta(const char* path, uint32_t threads, msspe_fasta* F, const std::f
   });
   for (uint64_t i = 0; i < nrec; i++) F->offsets[i + 1] += F->offsets[i];
   F->n_bytes = F->offsets[nrec];
+  lap("names and lengths");
   uint8_t* dst = on_sized(F->n_bytes);
+  lap("allocation");
   if (!dst && F->n_bytes) { set_err(err, err_len, "out of host memory"); return MSSPE_ERR_NOMEM; }
   // 3. normalise, in chunks of ~32 MB of output; a finished chunk is handed on while the next one is being written
   const uint64_t chunk_bytes = 32ull << 20;
@@ -157,14 +169,20 @@ int parse_fasta(const char* path, uint32_t threads, msspe_fasta* F, const std::f
     r0 = r1;
   }
   if (copier.joinable()) copier.join();
+  lap("normalise + copy");
   return MSSPE_OK;
 }
 
+// Pinning costs about as much per byte as parsing does (page-locking 3 GB: ~1 s), so only small inputs get a pinned
+// buffer; a large one is pageable and its chunks go to the device through the driver's own staging buffers while the
+// worker threads normalise the next chunk.  MSSPE_FASTA_PINNED=0/1 forces either.
 uint8_t* host_alloc(msspe_fasta* F, uint64_t bytes) {
   const uint64_t a = bytes ? bytes : 1;
   void* p = nullptr;
-  if (cudaMallocHost(&p, a) == cudaSuccess) { F->pinned = true; }
-  else { (void)cudaGetLastError(); p = malloc(a); F->pinned = false; }  // no CUDA context (tests of the parser): pageable
+  bool want_pinned = a <= (256ull << 20);
+  if (const char* e = getenv("MSSPE_FASTA_PINNED")) want_pinned = atoi(e) != 0;
+  if (want_pinned && cudaMallocHost(&p, a) == cudaSuccess) { F->pinned = true; }
+  else { if (want_pinned) (void)cudaGetLastError(); p = malloc(a); F->pinned = false; }  // also: no CUDA context (tests of the parser)
   F->bases = (uint8_t*)p;
   return F->bases;
 }
