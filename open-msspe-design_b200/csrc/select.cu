@@ -339,8 +339,9 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 // cooperative_groups' own grid barrier: 1.21 us against 1.45 us for the counter above in isolation (296 x 512,
-// tools/microbench/grid_barrier.cu).  Inside the kernels the difference is within noise: the incremental kernel runs
-// 4 % faster with it, the recount kernel 3 % slower -- each keeps the one it measured better with.
+// tools/microbench/grid_barrier.cu).  Both persistent kernels use it for their two barriers per iteration (recount kernel,
+// same-box A/B after the tie-score work: cfg2 7.90 vs 8.20 ms, cfg5/8 shard within 2 %); the counter above remains for
+// the extra barrier of the global-bitmask variant.
 __device__ __forceinline__ void grid_barrier_cg() { cg::this_grid().sync(); }
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -569,7 +570,7 @@ greedy_persistent_kernel(const GreedyArgs A) {
         }
     if (wlead) { const unsigned long long t = globaltimer_ns(); s_tm[8] += t - s_tm[5]; s_tm[5] = t; }
     FSTAMP(2)
-    grid_barrier(A.barrier, bar_target);
+    grid_barrier_cg();
     FSTAMP(3)
     if (wlead) { const unsigned long long t = globaltimer_ns(); s_tm[9] += t - s_tm[5]; s_tm[5] = t; }
     if (lead) { s_tm[2] = globaltimer_ns(); s_tm[3] += s_tm[2] - s_tm[1]; }
@@ -710,7 +711,7 @@ greedy_persistent_kernel(const GreedyArgs A) {
     }
     if (wlead) { const unsigned long long t = globaltimer_ns(); s_tm[10] += t - s_tm[5]; s_tm[5] = t; }
     FSTAMP(7)
-    grid_barrier(A.barrier, bar_target);
+    grid_barrier_cg();
     FSTAMP(8)
     if (wlead) { const unsigned long long t = globaltimer_ns(); s_tm[11] += t - s_tm[5]; s_tm[5] = t; }
     if (lead) s_tm[4] += globaltimer_ns() - s_tm[2];
