@@ -12,6 +12,9 @@ pytestmark = pytest.mark.gpu
 from oracle import kmer_oracle as ko  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+# every loop variant: persistent recount, persistent incremental, AUTO, per-partition greedy sequences + merge, and the
+# launch-per-phase forms of the first two
+ALL_MODES = (0, 1, 2, 3, 0x100, 0x101)
 
 
 def _fasta_to_arrays(fa: bytes):
@@ -30,6 +33,35 @@ def _check_select(eng, O, fa, W, S, w, k, max_iter, mms, mode):
         assert got["tie_score"].astype(np.float32).tobytes() == want["scores"].tobytes()
         t = eng.timing()
         assert t.select_evals[d] == want["evals"], "coverage evals differ from the reference-equivalent count"
+
+
+def _load_golden(name):
+    """tests/golden/<name>_candidates.json: written offline by tools/gen_size_goldens.py from the CPU oracle
+    (oracle_select = main.rs:285-406 with a full recount per iteration) on the same synthetic input."""
+    with open(os.path.join(GOLDEN, "%s_candidates.json" % name)) as f:
+        return json.load(f)
+
+
+def _check_golden(eng, gold, mode, both=True):
+    """Every loop variant is compared with the ORACLE's winners / frequencies / tie counts / f32 tie scores (bit
+    patterns) / reference-equivalent evals at this size -- not with another variant of the CUDA path."""
+    it, mms = gold["max_iterations"], gold["max_mismatch_segments"]
+    if both:
+        res = eng.select_both(it, mms, mode)
+        evals = tuple(eng.timing().select_evals)
+    else:
+        res, evals = [], []
+        for d in (0, 1):
+            res.append(eng.select(d, it, mms, mode))
+            evals.append(eng.timing().select_evals[d])
+    for d in (0, 1):
+        want, got = gold["dirs"][d], res[d]
+        assert got["code"].tolist() == want["codes"], "mode %#x direction %d: winners differ from the oracle golden" % (mode, d)
+        assert got["freq"].tolist() == want["freqs"]
+        assert got["n_tied"].tolist() == want["n_tied"]
+        assert got["tie_score"].astype(np.float32).view(np.uint32).tolist() == want["score_bits"]
+        assert int(evals[d]) == want["evals"], "mode %#x direction %d: coverage evals differ from the oracle" % (mode, d)
+    return res
 
 
 @pytest.fixture(scope="module")
@@ -196,27 +228,29 @@ def test_cfg1_shape_full_size(oracle_lib):
     eng.close()
 
 
-def test_cfg2_full_size_properties():
-    """BASELINE configs[1] at full size (1000 x 30 kb): size-independent properties instead of the slow oracle:
-    recount and incremental modes agree exactly; frequencies never increase; every winner's postings are newly
-    marked; evals of the first iteration equal the record count."""
+def test_cfg2_full_size_vs_oracle_golden(monkeypatch):
+    """BASELINE configs[1] at full size (1000 x 30 kb, 2 x ~605 iterations, 1.1e9 reference-equivalent evals): every loop
+    variant against tests/golden/cfg2_candidates.json (the CPU oracle run offline, tools/gen_size_goldens.py), incl. the
+    variants that only exist at scale: default-threshold stream compaction, the 148 x 1024 block shape
+    (MSSPE_PERSIST_1024), the AUTO switch, launch-per-phase."""
     import msspe_b200 as m
     from msspe_b200 import synth
+    gold = _load_golden("cfg2")
     g, k = synth.make_config("cfg2")
+    assert g.shape == (gold["genomes"], gold["length"]) and k == gold["kmer_size"]
     eng = m.Engine(k, 500, 250, 50)
     eng.load_genomes(g.reshape(-1), synth.offsets_for(g))
     eng.build_index()
     G, maxp, s = eng.segment_info()
     assert G == 1000 * 119 and maxp == 118
-    a0, b0 = eng.select_both(1000, 10, 0)
-    t0 = eng.timing()
-    a1, b1 = eng.select_both(1000, 10, 1)
-    t1 = eng.timing()
-    for x, y in ((a0, a1), (b0, b1)):
-        assert x.tobytes() == y.tobytes()
-        assert np.all(np.diff(x["freq"].astype(np.int64)) <= 0)
-        assert len(set(x["code"].tolist())) == len(x)
-    assert tuple(t0.select_evals) == tuple(t1.select_evals)
+    for mode in ALL_MODES:
+        a0, b0 = _check_golden(eng, gold, mode)
+    _check_golden(eng, gold, m.SELECT_RECOUNT, both=False)
+    monkeypatch.setenv("MSSPE_PERSIST_1024", "1")
+    _check_golden(eng, gold, m.SELECT_RECOUNT)
+    monkeypatch.delenv("MSSPE_PERSIST_1024")
+    for x in (a0, b0):
+        assert np.all(np.diff(x["freq"].astype(np.int64)) <= 0) and len(set(x["code"].tolist())) == len(x)
     for d in (0, 1):
         codes, offs, post = eng.index(d)
         assert int(offs[-1]) == len(post)
@@ -238,24 +272,26 @@ def test_sharded_selection_primitives_world1(zika_engine):
         assert evals == want_evals and iters == eng.timing().select_iterations[d]
 
 
-def test_cfg3_full_size_properties():
-    """BASELINE configs[2] at full size (10,000 x 11 kb, k=15, --max-mismatch-segments=2, 1000 iterations): the three
-    loop implementations agree bit for bit; frequencies never increase; evals of iteration 0 = record count."""
+def test_cfg3_full_size_vs_oracle_golden(monkeypatch):
+    """BASELINE configs[2] at full size (10,000 x 11 kb, k=15, --max-mismatch-segments=2, 2 x 1000 iterations, 6.4e9
+    reference-equivalent evals) -- the bench.py headline workload: every loop variant against
+    tests/golden/cfg3_candidates.json (CPU oracle, offline)."""
     import msspe_b200 as m
     from msspe_b200 import synth
+    gold = _load_golden("cfg3")
     g, k = synth.make_config("cfg3")
+    assert g.shape == (gold["genomes"], gold["length"]) and k == gold["kmer_size"]
     eng = m.Engine(k, 500, 250, 50)
     eng.load_genomes(g.reshape(-1), synth.offsets_for(g))
     eng.build_index()
     G, maxp, s = eng.segment_info()
     assert G == 10_000 * 43 and maxp == 42 and s == 36
-    a0, b0 = eng.select_both(1000, 2, 0)
-    ev0 = tuple(eng.timing().select_evals)
-    a1, b1 = eng.select_both(1000, 2, 1)
-    ev1 = tuple(eng.timing().select_evals)
-    a2 = eng.select(0, 1000, 2, 0x100)
-    assert a0.tobytes() == a1.tobytes() == a2.tobytes() and b0.tobytes() == b1.tobytes() and ev0 == ev1
-    assert len(a0) > 100 and np.all(np.diff(a0["freq"].astype(np.int64)) <= 0)
+    for mode in ALL_MODES:
+        a0, b0 = _check_golden(eng, gold, mode)
+    monkeypatch.setenv("MSSPE_PERSIST_1024", "1")
+    _check_golden(eng, gold, m.SELECT_RECOUNT)
+    monkeypatch.delenv("MSSPE_PERSIST_1024")
+    assert len(a0) == 1000 and np.all(np.diff(a0["freq"].astype(np.int64)) <= 0)
     first = eng.select(0, 1, 2, 0)
     assert len(first) == 1 and eng.timing().select_evals[0] == eng.index(0)[1][-1]
     eng.close()
@@ -310,10 +346,10 @@ def test_stream_compaction_on_small_inputs(zika_fasta, oracle_lib, compact_min, 
 def test_global_bitmask_variant_many_segments():
     """More segments than a shared-memory bitmask can hold (2,000 genomes x 1,000 partitions = 2.0 M segments > 1.8 M
     bits): the persistent kernel reads the global bitmask, which block 0 updates inside the launch (grid barrier
-    after the update).  No oracle at this size: the persistent loop, the launch-per-phase loop and the incremental
-    loop -- three different code paths -- must agree bit for bit, and the evals of iteration 0 = record count."""
+    after the update).  Every loop variant against tests/golden/bitmask2m_candidates.json (CPU oracle, offline)."""
     import msspe_b200 as m
     from msspe_b200 import synth
+    gold = _load_golden("bitmask2m")
     g = synth.synth_genomes(2000, 30_000, 11, clades=16, p_clade=0.08, p_leaf=0.01)
     eng = m.Engine(13, 30, 30, 20)
     eng.load_genomes(g.reshape(-1), synth.offsets_for(g))
@@ -322,36 +358,43 @@ def test_global_bitmask_variant_many_segments():
     assert G == 2000 * 1000 and maxp == 999 and s == 8
     os.environ["MSSPE_FORCE_RECOUNT"] = "1"     # without it a recount request of this size is served by the incremental kernel
     try:
-        a0, b0 = eng.select_both(60, 10, 0)
-        ev0 = tuple(eng.timing().select_evals)
+        _check_golden(eng, gold, m.SELECT_RECOUNT)
     finally:
         del os.environ["MSSPE_FORCE_RECOUNT"]
-    a1, b1 = eng.select_both(60, 10, 1)
-    ev1 = tuple(eng.timing().select_evals)
-    a2 = eng.select(0, 60, 10, 0x100)
-    a3, b3 = eng.select_both(60, 10, 0)         # the automatic fallback
-    assert a0.tobytes() == a1.tobytes() == a2.tobytes() == a3.tobytes() and b0.tobytes() == b1.tobytes() == b3.tobytes() and ev0 == ev1
+    for mode in ALL_MODES:                      # mode 0 now = the automatic fallback to the incremental kernel
+        a0, b0 = _check_golden(eng, gold, mode)
     assert len(a0) == 60 and np.all(np.diff(a0["freq"].astype(np.int64)) <= 0)
     first = eng.select(0, 1, 10, 0)
     assert len(first) == 1 and eng.timing().select_evals[0] == eng.index(0)[1][-1]
     eng.close()
 
 
-def test_cfg5_shard_loop_variants_agree():
-    """One GPU's shard of BASELINE configs[4] (12,500 x 30 kb, 1.49 M segments, 2 x 56.5 M postings, larger than L2):
-    the recount kernel (with its stream compaction) and the incremental kernel return byte-identical winners, tie
-    counts, f32 scores and reference-equivalent evals over 300 iterations per direction; AUTO picks one of them."""
+def test_cfg5_shard_vs_oracle_golden(monkeypatch):
+    """One GPU's eighth of BASELINE configs[4] (12,500 x 30 kb, 1.49 M segments, 2 x 56.5 M postings, larger than L2):
+    the first 100 iterations per direction of every loop variant against tests/golden/cfg5shard_candidates.json (CPU
+    oracle, offline, 1.1e10 evals), incl. the u32 posting offsets at 5.6e7 postings and the 148 x 1024 block shape;
+    then 300 iterations: the variants agree with each other beyond the golden's horizon and with its prefix."""
     import msspe_b200 as m
     from msspe_b200 import synth
+    gold = _load_golden("cfg5shard")
     g = synth.synth_genomes(12_500, 30_000, 5, clades=256, p_clade=0.10, p_leaf=0.01)
+    assert g.shape == (gold["genomes"], gold["length"])
     eng = m.Engine(13, 500, 250, 50)
     eng.load_genomes(g.reshape(-1), synth.offsets_for(g))
     eng.build_index()
     assert eng.segment_info() == (12_500 * 119, 118, 38)
+    for mode in ALL_MODES:
+        if mode & m.SELECT_BATCHED and (mode & 0xFF) == m.SELECT_RECOUNT:
+            continue    # 2 x 100 stand-alone recounts of 226 MB: covered by cfg2/cfg3, skipped here for GPU time
+        _check_golden(eng, gold, mode)
+    monkeypatch.setenv("MSSPE_PERSIST_1024", "1")
+    _check_golden(eng, gold, m.SELECT_RECOUNT)
+    monkeypatch.delenv("MSSPE_PERSIST_1024")
     out = {}
-    for mode in (m.SELECT_RECOUNT, m.SELECT_INCREMENTAL, m.SELECT_AUTO):
+    for mode in (m.SELECT_RECOUNT, m.SELECT_INCREMENTAL, m.SELECT_AUTO, m.SELECT_PARTITIONED):
         a, b = eng.select_both(300, 10, mode)
         out[mode] = (a.tobytes(), b.tobytes(), tuple(eng.timing().select_evals))
         assert len(a) == 300 and len(b) == 300
-    assert out[m.SELECT_RECOUNT] == out[m.SELECT_INCREMENTAL] == out[m.SELECT_AUTO]
+        assert a["code"][:100].tolist() == gold["dirs"][0]["codes"] and b["code"][:100].tolist() == gold["dirs"][1]["codes"]
+    assert out[m.SELECT_RECOUNT] == out[m.SELECT_INCREMENTAL] == out[m.SELECT_AUTO] == out[m.SELECT_PARTITIONED]
     eng.close()
