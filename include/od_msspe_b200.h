@@ -67,7 +67,12 @@ typedef struct {
 /* How the device-resident greedy loop recomputes frequencies each iteration. Results are identical. */
 #define MSSPE_SELECT_RECOUNT 0     /* re-stream every posting each iteration = main.rs:292-309 */
 #define MSSPE_SELECT_INCREMENTAL 1 /* decrement counts of k-mers in newly covered segments */
-#define MSSPE_SELECT_AUTO 2        /* whichever is faster for the input: incremental from 2^21 postings per direction on */
+#define MSSPE_SELECT_AUTO 2        /* whichever is faster for the input: partitioned when few lists span several partitions,
+                                      else incremental from 2^21 postings per direction on, else recount */
+#define MSSPE_SELECT_PARTITIONED 3 /* every partition runs its own greedy sequence (a k-mer whose postings lie in one partition only
+                                      changes counts inside it); the reference's global order is their merge by (frequency,
+                                      partition_coverage, word); lists spanning several partitions are checked against the merged
+                                      order and, where one would have won, inserted with a roll-back of the partitions it touches */
 #define MSSPE_SELECT_BATCHED 0x100 /* OR-able: one launch per phase instead of the persistent cooperative kernel */
 
 /* NtthalOptions, delta_g.rs:18-25 (without the threshold), and Primer3's thal_args. */

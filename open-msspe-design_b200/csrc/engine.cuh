@@ -51,6 +51,16 @@ struct DirIndex {
   uint32_t* s_tile_first = nullptr; // [s_tiles]
   uint32_t* s_cost = nullptr;       // [tiles + 2] exclusive prefix of the tile costs (range balancing)
   uint32_t s_lists = 0, s_list_post = 0, s_tiles = 0;
+  // partition view of the index for MSSPE_SELECT_PARTITIONED (select_part.cu; built on first use): the codes grouped by
+  // the partition all their postings share ("units"), lists that span several partitions kept apart
+  bool pv_built = false;
+  uint32_t pv_units = 0, pv_single = 0, pv_multi_n = 0;
+  uint64_t pv_multi_postings = 0;
+  uint32_t* pv_ucode_off = nullptr;  // [U+1] CSR over pv_ucodes
+  uint32_t* pv_ucodes = nullptr;     // [D] code ids: single-partition lists grouped by unit (ascending inside), then the multi-partition lists
+  uint32_t* pv_fwdl = nullptr;       // [G*s] forward index renumbered: position in pv_ucodes | 0x80000000 for multi lists, 0xFFFFFFFF none
+  uint32_t* pv_useg_off = nullptr;   // [U+1] CSR over pv_usegs
+  uint32_t* pv_usegs = nullptr;      // [G] segment ids grouped by partition (ascending inside)
 };
 
 constexpr int MSSPE_CNT_THREADS = 512;  // threads per block of the K3 kernels
@@ -139,6 +149,11 @@ int msspe_radix_sort_pairs(msspe_ctx* ctx, uint64_t** key_a, uint32_t** val_a, u
 int msspe_free_index(msspe_ctx* ctx);
 int msspe_select_prepare_static(msspe_ctx* ctx, int dir, cudaStream_t st);  // select.cu: tile tables
 int msspe_select_prepare_stream(msspe_ctx* ctx, int dir, cudaStream_t st);  // select.cu: scoring stream (lazy)
+// select_part.cu: per-partition greedy sequences + merge (MSSPE_SELECT_PARTITIONED)
+int msspe_select_partitioned(msspe_ctx* ctx, int ndirs, const int* dirs, uint32_t max_iter, uint32_t mms, msspe_candidate** outs,
+                             uint32_t** n_outs);
+int msspe_partition_view(msspe_ctx* ctx, int dir, cudaStream_t st);   // builds DirIndex::pv_* (lazy)
+bool msspe_partitioned_applicable(msspe_ctx* ctx, int ndirs, const int* dirs, uint32_t max_iter);
 int msspe_thal_upload_tables(msspe_ctx* ctx);
 void msspe_thal_free_tables(msspe_ctx* ctx);
 

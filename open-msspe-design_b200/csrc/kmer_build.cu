@@ -311,6 +311,7 @@ void free_dir(msspe_ctx* c, DirIndex& d) {
   msspe_dev_free(c, d.codes); msspe_dev_free(c, d.post_off); msspe_dev_free(c, d.postings); msspe_dev_free(c, d.fwd_ids); msspe_dev_free(c, d.list_part); msspe_dev_free(c, d.freq);
   msspe_dev_free(c, d.acc); msspe_dev_free(c, d.ignored); msspe_dev_free(c, d.cov); msspe_dev_free(c, d.pmark); msspe_dev_free(c, d.ctl); msspe_dev_free(c, d.out);
   msspe_dev_free(c, d.tile_first);
+  msspe_dev_free(c, d.pv_ucode_off); msspe_dev_free(c, d.pv_ucodes); msspe_dev_free(c, d.pv_fwdl); msspe_dev_free(c, d.pv_useg_off); msspe_dev_free(c, d.pv_usegs);
   msspe_dev_free(c, d.s_postings); msspe_dev_free(c, d.s_off); msspe_dev_free(c, d.s_id); msspe_dev_free(c, d.s_tile_first); msspe_dev_free(c, d.s_cost);
   d = DirIndex();
 }

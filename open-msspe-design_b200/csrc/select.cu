@@ -1539,7 +1539,13 @@ int run_select(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max_iter, uint
   if (!c->built) { c->set_error("msspe_select: index not built"); return MSSPE_ERR_STATE; }
   const bool batched = (mode & MSSPE_SELECT_BATCHED) != 0;
   mode &= ~(uint32_t)MSSPE_SELECT_BATCHED;
-  if (mode > MSSPE_SELECT_AUTO) { c->set_error("msspe_select: unknown mode %u", mode); return MSSPE_ERR_INVALID; }
+  if (mode > MSSPE_SELECT_PARTITIONED) { c->set_error("msspe_select: unknown mode %u", mode); return MSSPE_ERR_INVALID; }
+  MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
+  // AUTO: the per-partition decomposition wherever (almost) every list lies in one partition (any pre-aligned input);
+  // measured on B200 against the two whole-index loops in DESIGN.md
+  if (mode == MSSPE_SELECT_AUTO && !batched && !getenv("MSSPE_AUTO_NO_PARTITIONED") && msspe_partitioned_applicable(c, ndirs, dirs, max_iter))
+    mode = MSSPE_SELECT_PARTITIONED;
+  if (mode == MSSPE_SELECT_PARTITIONED) return msspe_select_partitioned(c, ndirs, dirs, max_iter, mms, outs, n_outs);
   if (mode == MSSPE_SELECT_AUTO) {  // measured on B200: incremental ahead at cfg2 (4.5 M postings per direction: 8.6 vs 9.4 ms), cfg3 (16.8 vs
                                     // 23.4 ms) and beyond; below that its set-up (order by initial count, histogram) is what counts
     uint64_t most = 0;

@@ -1,0 +1,860 @@
+// select_part.cu -- MSSPE_SELECT_PARTITIONED: the greedy loop of find_candidates_kmers (od-msspe/src/main.rs:331-406)
+// decomposed by partition.  No grid barrier, no per-iteration recount of the whole index.
+//
+// Why it is exact.  A k-mer whose postings all lie in ONE partition p (Segment.partition_no, main.rs:227) -- the rule in
+// a pre-aligned alignment, where a word sits in the same columns of every genome -- only ever changes the live counts
+// of k-mers of partition-p segments when it is chosen, and its partition_tie_score (main.rs:261-283) is
+// 0.0 + 1/(partition_coverage[p] + 1) whichever of its postings are live.  So each partition ("unit") runs its OWN
+// greedy sequence, key (frequency, smaller word), independently of every other one, and the loop's global selection
+// order is the merge of those sequences by (frequency desc, partition_coverage asc, word asc) -- partition_coverage[p]
+// being the number of winners p has already supplied -- cut by the stop rules of main.rs:353-390.  Lists that span
+// several partitions couple units.  They are never candidates inside a unit; after every merge each of them is checked
+// against the merged order: its live count at iteration t follows from the cover times of its postings, its score is
+// the reference's sequential f32 sum over first-seen live partitions.  The earliest iteration t* at which one of them
+// beats the merged winner is an EXTERNAL winner: everything before t* is final, the units it touches are rolled back
+// to their state at t* and re-run, the rest is re-merged.  tests/_partitioned_model.py is this algorithm in Python,
+// checked on the CPU against the restated reference loop (tests/test_partitioned_model.py); the GPU tests compare this
+// file with reference-loop goldens at BASELINE sizes.
+//
+// Rounds of seven launches, enqueued in batches without host round trips (every kernel returns at once when its
+// direction is done):
+//   part_extend_kernel   one block per unit: (re)count after a roll-back, then up to `nsteps` greedy steps on exact
+//                        incremental counts (the unit's forward index), cover token per segment = the entry that covered it
+//   part_gather_kernel   list of not-yet-final entries
+//   part_merge_kernel    one warp per entry: its global position = entries of all units with a better key (binary
+//                        search per unit); also the tie count and the live records (coverage evals) of that iteration
+//   part_plan_kernel     horizon (first position an unfinished unit could still change), stop rules, window to verify
+//   part_stage_kernel    multi-partition lists whose upper bound reaches the smallest winning frequency of the window
+//   part_verify_kernel   one block per staged list: cover-time histogram -> live count per iteration, exact tie scores
+//   part_finalize_kernel winners before the horizon / before t* become final; external winner applied, units flagged
+#include "engine.cuh"
+
+#include <algorithm>
+
+namespace {
+
+constexpr uint32_t TK_LIVE = 0xFFFFFFFFu;                  // segment not covered
+constexpr uint32_t LID_NONE = 0xFFFFFFFFu, LID_MULTI = 0x80000000u;
+constexpr uint32_t ST_FINISHED = 1u, ST_RECOUNT = 2u, ST_EXTEND = 4u;
+constexpr uint32_t T_INF = 0xFFFFFFFFu;
+constexpr int EXT_T = 512;        // threads of the unit kernel
+constexpr int NEWCAP = 2048;      // newly covered segments handled per batch of the apply phase
+constexpr int VER_T = 256;        // threads of the verify kernel
+constexpr int TP_SLOTS = 64;      // distinct partitions of a multi-partition list handled by the parallel score path
+
+struct PEntry { uint32_t freq, cid, tied, pad; unsigned long long live_before; };
+
+struct PartCtl {
+  uint32_t t_final, done, n_out, iterations;
+  unsigned long long evals;
+  unsigned long long live_all;     // live records of all units (evals of the iteration that finds nothing)
+  uint32_t E, H, cutbound, V, terminal, do_terminal, fmin, t_hi;
+  uint32_t n_stage, n_viol, vmin, n_ext;
+  uint32_t rounds, rollbacks, staged_total, pad;
+};
+
+struct PartDir {
+  const uint64_t* codes; const uint32_t* post_off; const uint32_t* postings;
+  const uint32_t* ucode_off; const uint32_t* ucodes; const uint32_t* fwdl; const uint32_t* useg_off; const uint32_t* usegs;
+  uint32_t n_single, n_multi;
+  uint32_t* pfreq; uint32_t* token; unsigned long long* ulive; PEntry* entries; uint32_t* pos; uint32_t* rfin; uint32_t* ulen;
+  uint32_t* status; uint32_t* ext_cov; uint32_t* elist; uint32_t* order; uint32_t* tied; unsigned long long* tot_live; uint32_t* mt;
+  uint32_t* ub; uint32_t* stage; uint4* viol; uint32_t* touch;
+  PartCtl* ctl; msspe_candidate* out;
+};
+
+struct PartArgs {
+  PartDir d[2];
+  int ndirs;
+  uint32_t U, CAP, slots, max_iter, mms, uniform_parts, nsteps;
+  const uint16_t* seg_part;
+};
+
+__device__ __forceinline__ uint32_t part_of(const PartArgs& A, uint32_t seg) {
+  return A.uniform_parts ? seg % A.uniform_parts : (uint32_t)A.seg_part[seg];
+}
+
+template <int T>
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < T / 32 ? sh[lane] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[32] = v;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+template <int T>
+__device__ __forceinline__ uint32_t block_min_u32(uint32_t v, unsigned long long* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_down_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < T / 32 ? (uint32_t)sh[lane] : 0xFFFFFFFFu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_down_sync(0xffffffffu, v, o));
+    if (lane == 0) sh[32] = v;
+  }
+  __syncthreads();
+  return (uint32_t)sh[32];
+}
+
+// ---- unit kernel ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EXT_T) part_extend_kernel(PartArgs A) {
+  const PartDir& D = A.d[blockIdx.y];
+  if (D.ctl->done) return;
+  const uint32_t u = blockIdx.x;
+  const uint32_t st = D.status[u];
+  if (!(st & (ST_RECOUNT | ST_EXTEND))) return;
+  __shared__ unsigned long long sh[34];
+  __shared__ unsigned long long s_key[EXT_T / 32];
+  __shared__ uint32_t s_cnt[EXT_T / 32];
+  __shared__ uint32_t s_new[NEWCAP];
+  __shared__ uint32_t s_n;
+  __shared__ unsigned long long s_bkey;
+  __shared__ uint32_t s_bcnt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t o0 = D.ucode_off[u], o1 = D.ucode_off[u + 1];
+  const uint32_t g0 = D.useg_off[u], g1 = D.useg_off[u + 1];
+  const uint32_t slot0 = u * A.CAP, slots = A.slots;
+  uint32_t len = D.ulen[u];
+  unsigned long long live = D.ulive[u];
+  bool finished = (st & ST_FINISHED) != 0;
+  if (st & ST_RECOUNT) {  // state of the unit = its final entries + external winners: restore, then count from the forward index
+    const uint32_t keep = D.rfin[u];
+    len = keep;
+    finished = false;
+    for (uint32_t i = g0 + tid; i < g1; i += EXT_T) {
+      const uint32_t g = D.usegs[i];
+      const uint32_t tk = __ldcg(D.token + g);
+      if (tk >= slot0 + keep && tk < slot0 + A.CAP) D.token[g] = TK_LIVE;
+    }
+    for (uint32_t j = o0 + tid; j < o1; j += EXT_T) D.pfreq[j] = 0u;
+    __syncthreads();
+    const unsigned long long n = (unsigned long long)(g1 - g0) * slots;
+    unsigned long long cnt = 0;
+    for (unsigned long long x = tid; x < n; x += EXT_T) {
+      const uint32_t si = (uint32_t)(x / slots), q = (uint32_t)(x - (unsigned long long)si * slots);
+      const uint32_t g = D.usegs[g0 + si];
+      if (__ldcg(D.token + g) == TK_LIVE) {
+        const uint32_t l = __ldg(D.fwdl + (unsigned long long)g * slots + q);
+        if (l != LID_NONE) { cnt++; if (!(l & LID_MULTI)) atomicAdd(D.pfreq + l, 1u); }
+      }
+    }
+    live = block_sum_u64<EXT_T>(cnt, sh);
+  }
+  for (uint32_t step = 0; step < A.nsteps && !finished; step++) {
+    if (len >= A.CAP) { finished = true; break; }  // entry number CAP = max_iterations can never be among the first max_iterations
+    // arg-max over the unit's k-mers: (live count, then smaller word = smaller index), and how many share the count
+    unsigned long long bk = 0ull; uint32_t bc = 0u;
+    for (uint32_t j = o0 + tid; j < o1; j += EXT_T) {
+      const uint32_t f = __ldcg(D.pfreq + j);
+      const unsigned long long key = ((unsigned long long)f << 32) | (unsigned long long)(0xFFFFFFFFu - (j - o0));
+      const uint32_t bf = (uint32_t)(bk >> 32);
+      if (f > bf || bc == 0u) { bk = key; bc = 1u; }
+      else if (f == bf) { bc++; if (key > bk) bk = key; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long ok = __shfl_down_sync(0xffffffffu, bk, o);
+      const uint32_t oc = __shfl_down_sync(0xffffffffu, bc, o);
+      if (oc) {
+        const uint32_t f = (uint32_t)(ok >> 32), bf = (uint32_t)(bk >> 32);
+        if (bc == 0u || f > bf) { bk = ok; bc = oc; }
+        else if (f == bf) { bc += oc; if (ok > bk) bk = ok; }
+      }
+    }
+    if (lane == 0) { s_key[warp] = bk; s_cnt[warp] = bc; }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long k2 = 0ull; uint32_t c2 = 0u;
+      for (int w2 = 0; w2 < EXT_T / 32; w2++) {
+        const unsigned long long ok = s_key[w2]; const uint32_t oc = s_cnt[w2];
+        if (!oc) continue;
+        const uint32_t f = (uint32_t)(ok >> 32), bf = (uint32_t)(k2 >> 32);
+        if (c2 == 0u || f > bf) { k2 = ok; c2 = oc; }
+        else if (f == bf) { c2 += oc; if (ok > k2) k2 = ok; }
+      }
+      s_bkey = k2; s_bcnt = c2;
+    }
+    __syncthreads();
+    const uint32_t fmax = s_bcnt ? (uint32_t)(s_bkey >> 32) : 0u;
+    if (fmax < 2u) { finished = true; break; }      // freq == 1 stops before the push (main.rs:354-360); 0 = None
+    const uint32_t jwin = o0 + (0xFFFFFFFFu - (uint32_t)s_bkey);
+    const uint32_t cid = D.ucodes[jwin];
+    const uint32_t slot = slot0 + len;
+    if (tid == 0) { PEntry e; e.freq = fmax; e.cid = cid; e.tied = s_bcnt; e.pad = 0u; e.live_before = live; D.entries[slot] = e; }
+    const uint32_t pb = D.post_off[cid], pe = D.post_off[cid + 1];
+    unsigned long long dec = 0;
+    for (uint32_t b = pb; b < pe; b += NEWCAP) {     // main.rs:371-378 for this unit: cover the winner's live segments ...
+      if (tid == 0) s_n = 0u;
+      __syncthreads();
+      const uint32_t be = min(pe, b + (uint32_t)NEWCAP);
+      for (uint32_t i = b + tid; i < be; i += EXT_T) {
+        const uint32_t g = __ldg(D.postings + i);
+        if (__ldcg(D.token + g) == TK_LIVE) { D.token[g] = slot; s_new[atomicAdd(&s_n, 1u)] = g; }
+      }
+      __syncthreads();
+      const uint32_t n = s_n * slots;              // ... and take their k-mers out of the live counts
+      for (uint32_t x = tid; x < n; x += EXT_T) {
+        const uint32_t si = x / slots, q = x - si * slots;
+        const uint32_t l = __ldg(D.fwdl + (unsigned long long)s_new[si] * slots + q);
+        if (l != LID_NONE) { dec++; if (!(l & LID_MULTI)) atomicSub(D.pfreq + l, 1u); }
+      }
+      __syncthreads();
+    }
+    live -= block_sum_u64<EXT_T>(dec, sh);
+    len++;
+    if (fmax < A.mms) { finished = true; break; }   // pushed, then break (main.rs:387-390)
+  }
+  if (tid == 0) { D.ulen[u] = len; D.ulive[u] = live; D.status[u] = finished ? ST_FINISHED : 0u; }
+}
+
+// ---- list of non-final entries ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) part_gather_kernel(PartArgs A) {
+  const PartDir& D = A.d[blockIdx.x];
+  PartCtl* C = D.ctl;
+  if (C->done) return;
+  __shared__ unsigned long long sh[34];
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = 0u;
+  unsigned long long live = 0;
+  __syncthreads();
+  for (uint32_t u0 = 0; u0 < A.U; u0 += 1024) {
+    const uint32_t u = u0 + tid;
+    uint32_t n = 0, rf = 0;
+    if (u < A.U) { rf = D.rfin[u]; n = D.ulen[u] - rf; live += D.ulive[u]; }
+    uint32_t inc = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = s_w[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+      s_w[lane] = wi - w;
+      if (lane == 31) sh[33] = wi;
+    }
+    __syncthreads();
+    const uint32_t off = s_base + s_w[warp] + inc - n;
+    for (uint32_t r = 0; r < n; r++) D.elist[off + r] = u * A.CAP + rf + r;
+    __syncthreads();
+    if (tid == 0) s_base += (uint32_t)sh[33];
+    __syncthreads();
+  }
+  const unsigned long long la = block_sum_u64<1024>(live, sh);
+  for (uint32_t i = tid; i <= A.max_iter; i += 1024) D.mt[i] = 0u;
+  if (tid == 0) { C->E = s_base; C->live_all = la; C->n_stage = 0u; C->n_viol = 0u; C->vmin = T_INF; C->rounds++; }
+}
+
+// key order of the merge: higher frequency, then lower partition_coverage (= higher 1/(cov+1), main.rs:320-324), then smaller word
+__device__ __forceinline__ bool better(uint32_t fa, uint32_t ca, uint32_t ia, uint32_t fb, uint32_t cb, uint32_t ib) {
+  return fa > fb || (fa == fb && (ca < cb || (ca == cb && ia < ib)));
+}
+
+__global__ void __launch_bounds__(256) part_merge_kernel(PartArgs A) {
+  const PartDir& D = A.d[blockIdx.y];
+  const PartCtl* C = D.ctl;
+  if (C->done) return;
+  const uint32_t E = C->E, t_final = C->t_final;
+  const int lane = threadIdx.x & 31;
+  const uint32_t wpb = blockDim.x >> 5;
+  for (uint32_t xi = blockIdx.x * wpb + (threadIdx.x >> 5); xi < E; xi += gridDim.x * wpb) {
+    const uint32_t slot = D.elist[xi];
+    const uint32_t ux = slot / A.CAP, rx = slot - ux * A.CAP;
+    const PEntry ex = D.entries[slot];
+    const uint32_t covx = rx + D.ext_cov[ux];
+    uint32_t cnt = 0, tied = 0; unsigned long long live = 0;
+    for (uint32_t q = lane; q < A.U; q += 32) {
+      const uint32_t rf = D.rfin[q], ln = D.ulen[q];
+      uint32_t idx;                                  // the entry of unit q that is its head at the time x is chosen
+      if (q == ux) idx = rx;
+      else {
+        const uint32_t ec = D.ext_cov[q];
+        uint32_t lo = rf, n = ln - rf;
+        while (n > 0) {
+          const uint32_t half = n >> 1, mid = lo + half;
+          const PEntry* e = D.entries + (unsigned long long)q * A.CAP + mid;
+          if (better(e->freq, mid + ec, e->cid, ex.freq, covx, ex.cid)) { lo = mid + 1; n -= half + 1; } else n = half;
+        }
+        idx = lo;
+      }
+      cnt += idx - rf;
+      if (idx < ln) {
+        const PEntry* e = D.entries + (unsigned long long)q * A.CAP + idx;
+        live += e->live_before;
+        if (e->freq == ex.freq) tied += e->tied;
+      } else live += D.ulive[q];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      cnt += __shfl_down_sync(0xffffffffu, cnt, o); tied += __shfl_down_sync(0xffffffffu, tied, o); live += __shfl_down_sync(0xffffffffu, live, o);
+    }
+    if (lane == 0) {
+      D.pos[slot] = t_final + cnt;
+      if (t_final + cnt <= A.max_iter) { D.order[cnt] = slot; D.tied[cnt] = tied; D.tot_live[cnt] = live; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) part_plan_kernel(PartArgs A) {
+  const PartDir& D = A.d[blockIdx.x];
+  PartCtl* C = D.ctl;
+  if (C->done) return;
+  __shared__ unsigned long long sh[34];
+  const int tid = threadIdx.x;
+  const uint32_t E = C->E, t_final = C->t_final;
+  uint32_t h = T_INF;
+  for (uint32_t u = tid; u < A.U; u += 1024) {
+    if (!(D.status[u] & ST_FINISHED)) {
+      const uint32_t rf = D.rfin[u], ln = D.ulen[u];
+      h = min(h, ln > rf ? D.pos[u * A.CAP + ln - 1] + 1u : t_final);
+    }
+  }
+  const uint32_t H = block_min_u32<1024>(h, sh);
+  const uint32_t room = A.max_iter - t_final;           // positions still open
+  uint32_t first = T_INF;
+  for (uint32_t i = tid; i < E && i < room; i += 1024)
+    if (D.entries[D.order[i]].freq < A.mms) first = min(first, i);
+  first = block_min_u32<1024>(first, sh);
+  if (tid == 0) {
+    uint32_t cutbound = A.max_iter, terminal = 0u;
+    if (first != T_INF) cutbound = min(cutbound, t_final + first + 1u);
+    else if (E < room) { cutbound = t_final + E; terminal = 1u; }
+    const uint32_t V = min(H, cutbound);
+    const uint32_t do_term = (terminal && H == T_INF) ? 1u : 0u;
+    uint32_t fmin = T_INF;
+    if (do_term) fmin = 2u;
+    else if (V > t_final) fmin = D.entries[D.order[V - 1u - t_final]].freq;
+    C->H = H; C->cutbound = cutbound; C->V = V; C->terminal = terminal; C->do_terminal = do_term; C->fmin = fmin; C->t_hi = V + do_term;
+  }
+}
+
+__global__ void __launch_bounds__(256) part_stage_kernel(PartArgs A) {
+  const PartDir& D = A.d[blockIdx.y];
+  PartCtl* C = D.ctl;
+  if (C->done) return;
+  const uint32_t fmin = C->fmin;
+  const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < D.n_multi && D.ub[m] >= fmin) D.stage[atomicAdd(&C->n_stage, 1u)] = m;
+}
+
+// cover time of a segment: the global position of the entry (or external winner) that covered it
+__device__ __forceinline__ uint32_t time_of(const PartDir& D, uint32_t g) {
+  const uint32_t tk = __ldcg(D.token + g);
+  return tk == TK_LIVE ? T_INF : __ldcg(D.pos + tk);
+}
+
+// partition_coverage[p] at iteration t: winners unit p supplied before t + external winners that touched it (all final)
+__device__ uint32_t cov_at(const PartArgs& A, const PartDir& D, uint32_t p, uint32_t t) {
+  uint32_t lo = 0, n = D.ulen[p];
+  const uint32_t* ps = D.pos + (unsigned long long)p * A.CAP;
+  while (n > 0) { const uint32_t half = n >> 1; if (__ldcg(ps + lo + half) < t) { lo += half + 1; n -= half + 1; } else n = half; }
+  return D.ext_cov[p] + lo;
+}
+
+// partition_tie_score (main.rs:261-283) of a multi-partition list at iteration t: f32 terms added sequentially in the
+// order in which the partitions are first seen among the LIVE postings (ascending segment index).
+__device__ float multi_score(const PartArgs& A, const PartDir& D, uint32_t a, uint32_t b, uint32_t t, uint32_t* tp, uint32_t* tfirst,
+                             uint32_t* s_flag, uint32_t* seen, float* s_score) {
+  const int tid = threadIdx.x;
+  for (int k = tid; k < TP_SLOTS; k += VER_T) { tp[k] = 0xFFFFFFFFu; tfirst[k] = 0xFFFFFFFFu; }
+  if (tid == 0) *s_flag = 0u;
+  __syncthreads();
+  for (uint32_t i = a + tid; i < b; i += VER_T) {
+    const uint32_t g = __ldg(D.postings + i);
+    if (time_of(D, g) < t) continue;
+    const uint32_t p = part_of(A, g);
+    int k = 0;
+    for (; k < TP_SLOTS; k++) {
+      const uint32_t old = atomicCAS(&tp[k], 0xFFFFFFFFu, p);
+      if (old == 0xFFFFFFFFu || old == p) { atomicMin(&tfirst[k], i); break; }
+    }
+    if (k == TP_SLOTS) *s_flag = 1u;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float score = 0.0f;
+    if (*s_flag) {   // more distinct partitions than slots (degenerate inputs): the reference's loop as it stands
+      const uint32_t words = (A.U + 31u) / 32u;
+      for (uint32_t w2 = 0; w2 < words; w2++) seen[w2] = 0u;
+      for (uint32_t i = a; i < b; i++) {
+        const uint32_t g = __ldg(D.postings + i);
+        if (time_of(D, g) < t) continue;
+        const uint32_t p = part_of(A, g);
+        if (!((seen[p >> 5] >> (p & 31u)) & 1u)) {
+          seen[p >> 5] |= 1u << (p & 31u);
+          score = __fadd_rn(score, __fdiv_rn(1.0f, __fadd_rn((float)cov_at(A, D, p, t), 1.0f)));
+        }
+      }
+    } else {
+      int n = 0;
+      for (int k = 0; k < TP_SLOTS; k++) if (tp[k] != 0xFFFFFFFFu) { tp[n] = tp[k]; tfirst[n] = tfirst[k]; n++; }
+      for (int i = 1; i < n; i++) {
+        const uint32_t kp = tp[i], kf = tfirst[i]; int j = i - 1;
+        while (j >= 0 && tfirst[j] > kf) { tp[j + 1] = tp[j]; tfirst[j + 1] = tfirst[j]; j--; }
+        tp[j + 1] = kp; tfirst[j + 1] = kf;
+      }
+      for (int i = 0; i < n; i++) score = __fadd_rn(score, __fdiv_rn(1.0f, __fadd_rn((float)cov_at(A, D, tp[i], t), 1.0f)));
+    }
+    *s_score = score;
+  }
+  __syncthreads();
+  return *s_score;
+}
+
+// dynamic shared memory: h[max_iter + 2] (cover-time histogram -> exclusive prefix), wf[max_iter + 2], seen[(U + 31) / 32]
+__global__ void __launch_bounds__(VER_T) part_verify_kernel(PartArgs A) {
+  const PartDir& D = A.d[blockIdx.y];
+  PartCtl* C = D.ctl;
+  if (C->done) return;
+  extern __shared__ uint32_t dsm[];
+  uint32_t* h = dsm;
+  uint32_t* wf = dsm + (A.max_iter + 2u);             // winning frequency of every iteration of the window
+  uint32_t* seen = wf + (A.max_iter + 2u);
+  __shared__ unsigned long long sh[34];
+  __shared__ uint32_t tp[TP_SLOTS], tfirst[TP_SLOTS];
+  __shared__ uint32_t s_flag, s_carry;
+  __shared__ float s_score;
+  const int tid = threadIdx.x;
+  const uint32_t n_stage = C->n_stage, t_final = C->t_final, V = C->V, t_hi = C->t_hi, fmin = C->fmin;
+  const uint32_t W = t_hi - t_final;
+  if (blockIdx.x >= n_stage) return;
+  for (uint32_t i = tid; i < V - t_final; i += VER_T) wf[i] = D.entries[D.order[i]].freq;
+  __syncthreads();
+  for (uint32_t si = blockIdx.x; si < n_stage; si += gridDim.x) {
+    const uint32_t m = D.stage[si];
+    const uint32_t c = D.ucodes[D.n_single + m];
+    const uint32_t a = D.post_off[c], b = D.post_off[c + 1];
+    for (uint32_t i = tid; i < W; i += VER_T) h[i] = 0u;
+    if (tid == 0) s_carry = 0u;
+    __syncthreads();
+    unsigned long long l0 = 0;
+    for (uint32_t i = a + tid; i < b; i += VER_T) {
+      const uint32_t tm = time_of(D, __ldg(D.postings + i));
+      if (tm >= t_final) { l0++; if (tm < t_hi) atomicAdd(&h[tm - t_final], 1u); }
+    }
+    const uint32_t L0 = (uint32_t)block_sum_u64<VER_T>(l0, sh);
+    if (tid == 0) D.ub[m] = L0;                      // live count at t_final: an upper bound for every later iteration
+    if (L0 < fmin) continue;
+    // h[i] -> postings covered before iteration t_final + i (exclusive prefix); live count there = L0 - h[i]
+    for (uint32_t i0 = 0; i0 < W; i0 += VER_T) {
+      const uint32_t i = i0 + tid;
+      const uint32_t v = i < W ? h[i] : 0u;
+      uint32_t inc = v;
+      const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      __syncthreads();
+      if (lane == 31) sh[warp] = inc;
+      __syncthreads();
+      uint32_t wbase = 0;
+      for (int w2 = 0; w2 < warp; w2++) wbase += (uint32_t)sh[w2];
+      const uint32_t carry = s_carry;
+      if (i < W) h[i] = carry + wbase + inc - v;
+      __syncthreads();
+      if (tid == VER_T - 1) s_carry = carry + wbase + inc;
+      __syncthreads();
+    }
+    // first iteration with a strictly larger live count than the merged winner (terminal iteration: any count >= 2)
+    uint32_t fs = T_INF;
+    for (uint32_t i = tid; i < W; i += VER_T) {
+      const uint32_t t = t_final + i, cnt = L0 - h[i];
+      const bool strict = t < V ? cnt > wf[i] : cnt >= 2u;
+      if (strict) { fs = i; break; }
+    }
+    fs = block_min_u32<VER_T>(fs, sh);
+    // equal counts before that: the tie-break decides, in ascending iteration order, until one wins
+    const uint32_t lim = min(fs, V - t_final);
+    uint32_t tv = T_INF, tv_cnt = 0; float tv_score = 0.0f;
+    for (uint32_t cur = 0; cur < lim;) {
+      uint32_t nx = T_INF;
+      for (uint32_t i = cur + tid; i < lim; i += VER_T) if (L0 - h[i] == wf[i]) { nx = i; break; }
+      nx = block_min_u32<VER_T>(nx, sh);
+      if (nx == T_INF) break;
+      const uint32_t i = nx, t = t_final + nx;
+      if (tid == 0) atomicAdd(D.mt + i, 1u);
+      const float sc = multi_score(A, D, a, b, t, tp, tfirst, &s_flag, seen, &s_score);
+      const uint32_t slot = D.order[i];
+      const uint32_t ux = slot / A.CAP, rx = slot - ux * A.CAP;
+      const float wsc = __fdiv_rn(1.0f, __fadd_rn((float)(rx + D.ext_cov[ux]), 1.0f));
+      if (sc > wsc || (sc == wsc && c < D.entries[slot].cid)) { tv = t; tv_cnt = wf[i]; tv_score = sc; break; }
+      cur = nx + 1u;
+    }
+    if (tv == T_INF && fs != T_INF) {
+      tv = t_final + fs; tv_cnt = L0 - h[fs];
+      tv_score = multi_score(A, D, a, b, tv, tp, tfirst, &s_flag, seen, &s_score);
+    }
+    if (tv != T_INF && tid == 0) {
+      const uint32_t k = atomicAdd(&C->n_viol, 1u);
+      D.viol[k] = make_uint4(tv, tv_cnt, __float_as_uint(tv_score), c);
+      atomicMin(&C->vmin, tv);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(1024) part_finalize_kernel(PartArgs A) {
+  const PartDir& D = A.d[blockIdx.x];
+  PartCtl* C = D.ctl;
+  if (C->done) return;
+  __shared__ unsigned long long sh[34];
+  __shared__ unsigned long long s_best;
+  __shared__ uint32_t s_bestc, s_same;
+  const int tid = threadIdx.x;
+  const uint32_t t_final = C->t_final, V = C->V, vmin = C->vmin, n_viol = C->n_viol;
+  const bool viol = vmin != T_INF;
+  const uint32_t t_new = viol ? vmin : V;
+  // winners before t_new are final
+  unsigned long long ev = 0;
+  for (uint32_t i = tid; i < t_new - t_final; i += 1024) {
+    const uint32_t slot = D.order[i];
+    const PEntry e = D.entries[slot];
+    const uint32_t ux = slot / A.CAP, rx = slot - ux * A.CAP;
+    msspe_candidate o;
+    o.code = D.codes[e.cid]; o.freq = e.freq; o.n_tied = D.tied[i] + D.mt[i];
+    o.tie_score = __fdiv_rn(1.0f, __fadd_rn((float)(rx + D.ext_cov[ux]), 1.0f)); o.reserved = 0u;
+    D.out[t_final + i] = o;
+    ev += D.tot_live[i];
+  }
+  ev = block_sum_u64<1024>(ev, sh);
+  for (uint32_t u = tid; u < A.U; u += 1024) {
+    uint32_t lo = D.rfin[u], n = D.ulen[u] - lo;
+    const uint32_t* ps = D.pos + (unsigned long long)u * A.CAP;
+    while (n > 0) { const uint32_t half = n >> 1; if (ps[lo + half] < t_new) { lo += half + 1; n -= half + 1; } else n = half; }
+    D.rfin[u] = lo;
+  }
+  if (tid == 0) { s_best = 0ull; s_bestc = 0u; s_same = 0u; }
+  __syncthreads();
+  if (viol) {
+    // the external winner: best (count, score, smaller word) among the lists that win at t_new
+    for (uint32_t k = tid; k < n_viol; k += 1024) {
+      const uint4 v = D.viol[k];
+      if (v.x == t_new) atomicMax(&s_best, ((unsigned long long)v.y << 32) | (unsigned long long)v.z);  // scores are >= 0: bit order = value order
+    }
+    __syncthreads();
+    for (uint32_t k = tid; k < n_viol; k += 1024) {
+      const uint4 v = D.viol[k];
+      if (v.x == t_new && ((((unsigned long long)v.y << 32) | (unsigned long long)v.z) == s_best)) atomicMax(&s_bestc, 0xFFFFFFFFu - v.w);
+      if (v.x == t_new && v.y == (uint32_t)(s_best >> 32)) atomicAdd(&s_same, 1u);
+    }
+    __syncthreads();
+    const uint32_t c = 0xFFFFFFFFu - s_bestc, cnt = (uint32_t)(s_best >> 32);
+    const uint32_t iw = t_new - t_final;
+    const bool has_entry = t_new < V;                // a merged winner stood at t_new (not the terminal iteration)
+    const uint32_t j = C->n_ext;
+    const uint32_t a = D.post_off[c], b = D.post_off[c + 1];
+    if (tid == 0) {
+      msspe_candidate o;
+      o.code = D.codes[c]; o.freq = cnt; o.tie_score = __uint_as_float((uint32_t)s_best); o.reserved = 0u;
+      const bool tie_case = has_entry && D.entries[D.order[iw]].freq == cnt;
+      o.n_tied = tie_case ? D.tied[iw] + D.mt[iw] : s_same;
+      D.out[t_new] = o;
+      D.pos[A.U * A.CAP + j] = t_new;
+      C->evals += ev + (has_entry ? D.tot_live[iw] : C->live_all);
+      C->iterations += iw + 1u;
+    }
+    __syncthreads();
+    for (uint32_t i = a + tid; i < b; i += 1024) {   // main.rs:371-378: cover its live postings, partition_coverage for ALL its partitions
+      const uint32_t g = D.postings[i];
+      const uint32_t p = part_of(A, g);
+      if (atomicExch(D.touch + p, 1u) == 0u) atomicAdd(D.ext_cov + p, 1u);
+      if (time_of(D, g) >= t_new) { D.token[g] = A.U * A.CAP + j; D.status[p] = ST_RECOUNT | ST_EXTEND; }
+    }
+    __syncthreads();
+    for (uint32_t i = a + tid; i < b; i += 1024) D.touch[part_of(A, D.postings[i])] = 0u;
+    if (tid == 0) {
+      C->n_ext = j + 1u; C->rollbacks++;
+      C->t_final = t_new + 1u;
+      if (cnt < A.mms || t_new + 1u >= A.max_iter) { C->done = 1u; C->n_out = t_new + 1u; }
+    }
+    return;
+  }
+  const uint32_t cutbound = C->cutbound, H = C->H, terminal = C->terminal;
+  const bool done = V == cutbound && (!terminal || H == T_INF);
+  if (!done) {
+    const uint32_t bound = terminal ? A.max_iter : cutbound;
+    for (uint32_t u = tid; u < A.U; u += 1024) {
+      const uint32_t st = D.status[u];
+      if (st & ST_FINISHED) continue;
+      const uint32_t rf = D.rfin[u], ln = D.ulen[u];
+      const uint32_t last = ln > rf ? D.pos[u * A.CAP + ln - 1] + 1u : t_new;
+      if (last < bound) D.status[u] = st | ST_EXTEND;
+    }
+  }
+  if (tid == 0) {
+    C->evals += ev; C->iterations += t_new - t_final;
+    C->t_final = t_new;
+    if (done) {
+      if (C->do_terminal) { C->evals += C->live_all; C->iterations += 1u; }  // the call that found freq == 1 / nothing still counted
+      C->done = 1u; C->n_out = t_new;
+    }
+  }
+}
+
+// ---- partition view of the index -------------------------------------------------------------------------------------
+__global__ void pv_key_kernel(const uint32_t* __restrict__ list_part, uint32_t n, uint32_t U, uint64_t* __restrict__ key, uint32_t* __restrict__ val) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const uint32_t lp = list_part[c];
+  key[c] = (lp & 0x80000000u) ? (uint64_t)U : (uint64_t)lp;
+  val[c] = c;
+}
+__global__ void pv_bounds_kernel(const uint64_t* __restrict__ key, uint32_t n, uint32_t U, uint32_t* __restrict__ off) {
+  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u > U) return;
+  uint32_t lo = 0, len = n;
+  while (len > 0) { const uint32_t half = len >> 1; if (key[lo + half] < (uint64_t)u) { lo += half + 1; len -= half + 1; } else len = half; }
+  off[u] = lo;
+}
+__global__ void pv_lid_kernel(const uint32_t* __restrict__ ucodes, uint32_t n, uint32_t n_single, uint32_t* __restrict__ lid) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  lid[ucodes[i]] = i < n_single ? i : (LID_MULTI | (i - n_single));
+}
+__global__ void pv_fwdl_kernel(const uint32_t* __restrict__ fwd_ids, uint64_t n, const uint32_t* __restrict__ lid, uint32_t* __restrict__ fwdl) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t c = fwd_ids[i];
+  fwdl[i] = c == 0xFFFFFFFFu ? LID_NONE : __ldg(lid + c);
+}
+__global__ void pv_segkey_kernel(const uint16_t* __restrict__ seg_part, uint32_t uniform_parts, uint64_t G, uint64_t* __restrict__ key, uint32_t* __restrict__ val) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  key[g] = uniform_parts ? g % uniform_parts : (uint64_t)seg_part[g];
+  val[g] = (uint32_t)g;
+}
+__global__ void pv_mlen_kernel(const uint32_t* __restrict__ ucodes, uint32_t n_single, uint32_t n_multi, const uint32_t* __restrict__ post_off,
+                               uint32_t* __restrict__ ub, unsigned long long* total) {
+  const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_multi) return;
+  const uint32_t c = ucodes[n_single + m];
+  const uint32_t len = post_off[c + 1] - post_off[c];
+  if (ub) ub[m] = len;
+  if (total) atomicAdd(total, (unsigned long long)len);
+}
+__global__ void pv_status_kernel(uint32_t* status, uint32_t U) {
+  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < U) status[u] = ST_RECOUNT | ST_EXTEND;
+}
+
+uint32_t bits_for(uint32_t v) { uint32_t b = 1; while ((v >> b) != 0u && b < 32) b++; return b; }
+
+}  // namespace
+
+int msspe_partition_view(msspe_ctx* c, int dir, cudaStream_t st) {
+  DirIndex& D = c->dir[dir];
+  if (D.pv_built) return MSSPE_OK;
+  const uint32_t U = c->n_segments ? c->max_partition + 1u : 0u;
+  const uint32_t nc = (uint32_t)D.n_codes;
+  const uint64_t G = c->n_segments, GS = G * c->slots;
+  const uint32_t uni = (c->uniform_parts && c->uniform_parts <= 65536u) ? c->uniform_parts : 0u;
+  D.pv_units = U;
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.pv_ucode_off, ((uint64_t)U + 2) * 4, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.pv_useg_off, ((uint64_t)U + 2) * 4, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.pv_ucodes, ((uint64_t)nc + 1) * 4, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.pv_usegs, (G + 1) * 4, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.pv_fwdl, (GS + 1) * 4, c->stream));
+  uint64_t *ka = nullptr, *kb = nullptr; uint32_t *va = nullptr, *vb = nullptr; uint32_t* lid = nullptr; unsigned long long* d_tot = nullptr;
+  const uint64_t nmax = std::max<uint64_t>(std::max<uint64_t>(nc, G), 1);
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&ka, nmax * 8, st)); MSSPE_CUDA_TRY(c, cudaMallocAsync(&kb, nmax * 8, st));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&va, nmax * 4, st)); MSSPE_CUDA_TRY(c, cudaMallocAsync(&vb, nmax * 4, st));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&lid, ((uint64_t)nc + 1) * 4, st));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&d_tot, 8, st));
+  MSSPE_CUDA_TRY(c, cudaMemsetAsync(d_tot, 0, 8, st));
+  uint32_t h_off[2] = {0, 0};
+  if (nc) {  // codes by unit (stable: ascending code id = ascending word inside a unit), multi-partition lists last
+    pv_key_kernel<<<(nc + 255u) / 256u, 256, 0, st>>>(D.list_part, nc, U, ka, va);
+    c->timing.kernel_launches++;
+    int rc = msspe_radix_sort_pairs(c, &ka, &va, &kb, &vb, nc, bits_for(U), st);
+    if (rc) return rc;
+    MSSPE_CUDA_TRY(c, cudaMemcpyAsync(D.pv_ucodes, va, (uint64_t)nc * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  pv_bounds_kernel<<<(U + 1 + 255u) / 256u, 256, 0, st>>>(ka, nc, U, D.pv_ucode_off);
+  c->timing.kernel_launches++;
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(&h_off[0], D.pv_ucode_off + U, 4, cudaMemcpyDeviceToHost, st));
+  MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+  D.pv_single = h_off[0]; D.pv_multi_n = nc - h_off[0];
+  if (nc) {
+    pv_lid_kernel<<<(nc + 255u) / 256u, 256, 0, st>>>(D.pv_ucodes, nc, D.pv_single, lid);
+    c->timing.kernel_launches++;
+  }
+  if (GS) {
+    pv_fwdl_kernel<<<(unsigned)div_up_u64(GS, 256), 256, 0, st>>>(D.fwd_ids, GS, lid, D.pv_fwdl);
+    c->timing.kernel_launches++;
+  }
+  if (D.pv_multi_n) {
+    pv_mlen_kernel<<<(D.pv_multi_n + 255u) / 256u, 256, 0, st>>>(D.pv_ucodes, D.pv_single, D.pv_multi_n, D.post_off, nullptr, d_tot);
+    c->timing.kernel_launches++;
+  }
+  if (G) {   // segments by partition (stable: ascending segment index inside a partition)
+    pv_segkey_kernel<<<(unsigned)div_up_u64(G, 256), 256, 0, st>>>(c->d_seg_part, uni, G, ka, va);
+    c->timing.kernel_launches++;
+    int rc = msspe_radix_sort_pairs(c, &ka, &va, &kb, &vb, G, bits_for(U), st);
+    if (rc) return rc;
+    MSSPE_CUDA_TRY(c, cudaMemcpyAsync(D.pv_usegs, va, G * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  pv_bounds_kernel<<<(U + 1 + 255u) / 256u, 256, 0, st>>>(ka, (uint32_t)G, U, D.pv_useg_off);
+  c->timing.kernel_launches++;
+  unsigned long long tot = 0;
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(&tot, d_tot, 8, cudaMemcpyDeviceToHost, st));
+  MSSPE_CUDA_TRY(c, cudaGetLastError());
+  MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+  D.pv_multi_postings = tot;
+  MSSPE_CUDA_TRY(c, cudaFreeAsync(ka, st)); MSSPE_CUDA_TRY(c, cudaFreeAsync(kb, st));
+  MSSPE_CUDA_TRY(c, cudaFreeAsync(va, st)); MSSPE_CUDA_TRY(c, cudaFreeAsync(vb, st));
+  MSSPE_CUDA_TRY(c, cudaFreeAsync(lid, st)); MSSPE_CUDA_TRY(c, cudaFreeAsync(d_tot, st));
+  D.pv_built = true;
+  return MSSPE_OK;
+}
+
+// AUTO's test: the decomposition pays when (almost) every list lies in one partition; entries are U x max_iterations.
+bool msspe_partitioned_applicable(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max_iter) {
+  if (!c->n_segments || !max_iter) return false;
+  const uint64_t U = (uint64_t)c->max_partition + 1u;
+  if (U > 4096u || U * max_iter > (1ull << 24)) return false;
+  for (int i = 0; i < ndirs; i++) {
+    if (msspe_partition_view(c, dirs[i], c->stream) != MSSPE_OK) return false;
+    const DirIndex& D = c->dir[dirs[i]];
+    if (D.pv_multi_postings * 8u > D.n_records) return false;   // more than 1/8 of the postings in multi-partition lists
+  }
+  return true;
+}
+
+int msspe_select_partitioned(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max_iter, uint32_t mms, msspe_candidate** outs,
+                             uint32_t** n_outs) {
+  cudaStream_t st = c->stream;
+  const uint64_t G = c->n_segments;
+  const uint32_t U = G ? c->max_partition + 1u : 0u;
+  for (int i = 0; i < ndirs; i++) { *n_outs[i] = 0; c->timing.select_evals[dirs[i]] = 0; c->timing.select_iterations[dirs[i]] = 0; c->timing.select_ms[dirs[i]] = 0.f;
+                                    c->timing.select_postings_read[dirs[i]] = 0; c->timing.count_kernel_launches[dirs[i]] = 0; c->timing.count_kernel_ms[dirs[i]] = 0.f; }
+  if (max_iter == 0) return MSSPE_OK;
+  if (U == 0) { for (int i = 0; i < ndirs; i++) c->timing.select_iterations[dirs[i]] = 1; return MSSPE_OK; }
+  const uint64_t CAP = max_iter;
+  if ((uint64_t)U * CAP + max_iter >= 0xFFFFFFF0ull) { c->set_error("msspe_select: %u partitions x %u iterations exceed the entry table of the partitioned loop", U, max_iter); return MSSPE_ERR_CAPACITY; }
+  MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[2], st));
+  PartArgs A{};
+  A.ndirs = ndirs; A.U = U; A.CAP = (uint32_t)CAP; A.slots = c->slots; A.max_iter = max_iter; A.mms = mms;
+  A.uniform_parts = (c->uniform_parts && c->uniform_parts <= 65536u) ? c->uniform_parts : 0u;
+  A.seg_part = c->d_seg_part;
+  std::vector<void*> scratch;
+  auto alloc = [&](void** p, uint64_t bytes, int fill) -> int {
+    MSSPE_CUDA_TRY(c, cudaMallocAsync(p, bytes ? bytes : 4, st));
+    if (fill >= 0) MSSPE_CUDA_TRY(c, cudaMemsetAsync(*p, fill, bytes ? bytes : 4, st));
+    scratch.push_back(*p);
+    return MSSPE_OK;
+  };
+  uint32_t max_multi = 0;
+  for (int i = 0; i < ndirs; i++) {
+    int rc = msspe_partition_view(c, dirs[i], st);
+    if (rc) return rc;
+    DirIndex& X = c->dir[dirs[i]];
+    if (X.out_capacity < max_iter) {
+      msspe_dev_free(c, X.out); X.out = nullptr;
+      MSSPE_CUDA_TRY(c, cudaMallocAsync(&X.out, (uint64_t)max_iter * sizeof(msspe_candidate), c->stream));
+      X.out_capacity = max_iter;
+    }
+    PartDir& P = A.d[i];
+    P.codes = X.codes; P.post_off = X.post_off; P.postings = X.postings; P.ucode_off = X.pv_ucode_off; P.ucodes = X.pv_ucodes;
+    P.fwdl = X.pv_fwdl; P.useg_off = X.pv_useg_off; P.usegs = X.pv_usegs; P.n_single = X.pv_single; P.n_multi = X.pv_multi_n;
+    P.out = X.out;
+    max_multi = std::max(max_multi, P.n_multi);
+    const uint64_t ne = (uint64_t)U * CAP;
+#define PV_ALLOC(field, bytes, fill) { int rc2 = alloc((void**)&P.field, (bytes), (fill)); if (rc2) return rc2; }
+    PV_ALLOC(pfreq, ((uint64_t)X.n_codes + 1) * 4, 0);
+    PV_ALLOC(token, (G + 1) * 4, 0xFF);
+    PV_ALLOC(ulive, (uint64_t)U * 8, 0);
+    PV_ALLOC(entries, ne * sizeof(PEntry), -1);
+    PV_ALLOC(pos, (ne + max_iter + 1) * 4, 0xFF);
+    PV_ALLOC(rfin, (uint64_t)U * 4, 0);
+    PV_ALLOC(ulen, (uint64_t)U * 4, 0);
+    PV_ALLOC(status, (uint64_t)U * 4, -1);
+    PV_ALLOC(ext_cov, (uint64_t)U * 4, 0);
+    PV_ALLOC(elist, ne * 4, -1);
+    PV_ALLOC(order, ((uint64_t)max_iter + 2) * 4, 0);
+    PV_ALLOC(tied, ((uint64_t)max_iter + 2) * 4, 0);
+    PV_ALLOC(tot_live, ((uint64_t)max_iter + 2) * 8, 0);
+    PV_ALLOC(mt, ((uint64_t)max_iter + 2) * 4, 0);
+    PV_ALLOC(ub, ((uint64_t)P.n_multi + 1) * 4, 0);
+    PV_ALLOC(stage, ((uint64_t)P.n_multi + 1) * 4, -1);
+    PV_ALLOC(viol, ((uint64_t)P.n_multi + 1) * 16, -1);
+    PV_ALLOC(touch, (uint64_t)U * 4, 0);
+    PV_ALLOC(ctl, sizeof(PartCtl), 0);
+#undef PV_ALLOC
+    pv_status_kernel<<<(U + 255u) / 256u, 256, 0, st>>>(P.status, U);
+    c->timing.kernel_launches++;
+    if (P.n_multi) {
+      pv_mlen_kernel<<<(P.n_multi + 255u) / 256u, 256, 0, st>>>(P.ucodes, P.n_single, P.n_multi, P.post_off, P.ub, nullptr);
+      c->timing.kernel_launches++;
+    }
+  }
+  const size_t ver_smem = (2 * ((size_t)max_iter + 2) + (U + 31u) / 32u) * 4;
+  if (ver_smem > c->smem_optin) { c->set_error("msspe_select: max_iterations %u too large for the verify kernel's histogram", max_iter); return MSSPE_ERR_CAPACITY; }
+  MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(part_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ver_smem));
+  uint32_t chunk0 = (uint32_t)std::max<uint64_t>(4, (3ull * max_iter + 2ull * U - 1) / (2ull * U));
+  uint32_t chunk = 8;
+  if (const char* e = getenv("MSSPE_PART_CHUNK0")) chunk0 = (uint32_t)std::max(1, atoi(e));
+  if (const char* e = getenv("MSSPE_PART_CHUNK")) chunk = (uint32_t)std::max(1, atoi(e));
+  const unsigned merge_grid = (unsigned)c->sm_count * 4u, ver_grid = (unsigned)c->sm_count * 2u;
+  PartCtl* h = reinterpret_cast<PartCtl*>(c->h_ctl);   // pinned staging: 2 x SelectCtl is larger than 2 x PartCtl
+  static_assert(2 * sizeof(PartCtl) <= 2 * sizeof(SelectCtl), "pinned staging too small");
+  uint32_t round = 0;
+  const uint32_t BATCH = 4;
+  for (;;) {
+    for (uint32_t b = 0; b < BATCH; b++, round++) {
+      A.nsteps = round == 0 ? chunk0 : chunk;
+      part_extend_kernel<<<dim3(U, ndirs), EXT_T, 0, st>>>(A);
+      part_gather_kernel<<<ndirs, 1024, 0, st>>>(A);
+      part_merge_kernel<<<dim3(merge_grid, ndirs), 256, 0, st>>>(A);
+      part_plan_kernel<<<ndirs, 1024, 0, st>>>(A);
+      if (max_multi) {
+        part_stage_kernel<<<dim3((max_multi + 255u) / 256u, ndirs), 256, 0, st>>>(A);
+        part_verify_kernel<<<dim3(ver_grid, ndirs), VER_T, ver_smem, st>>>(A);
+        c->timing.kernel_launches += 2;
+      }
+      part_finalize_kernel<<<ndirs, 1024, 0, st>>>(A);
+      c->timing.kernel_launches += 5;
+    }
+    MSSPE_CUDA_TRY(c, cudaGetLastError());
+    for (int i = 0; i < ndirs; i++) MSSPE_CUDA_TRY(c, cudaMemcpyAsync(&h[i], A.d[i].ctl, sizeof(PartCtl), cudaMemcpyDeviceToHost, st));
+    MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+    bool all = true;
+    for (int i = 0; i < ndirs; i++) all = all && h[i].done;
+    if (all) break;
+    if (round > 4u * max_iter + 64u) { c->set_error("msspe_select: partitioned loop did not converge"); return MSSPE_ERR_STATE; }
+  }
+  MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
+  for (int i = 0; i < ndirs; i++) {
+    const int d = dirs[i];
+    const uint32_t n = h[i].n_out;
+    if (n) MSSPE_CUDA_TRY(c, cudaMemcpyAsync(outs[i], c->dir[d].out, (size_t)n * sizeof(msspe_candidate), cudaMemcpyDeviceToHost, st));
+    *n_outs[i] = n;
+    c->timing.select_evals[d] = h[i].evals;
+    c->timing.select_iterations[d] = h[i].iterations;
+    c->timing.select_postings_read[d] = c->dir[d].n_records;   // the forward index is read about once (counts) + once (decrements)
+  }
+  for (void* p : scratch) MSSPE_CUDA_TRY(c, cudaFreeAsync(p, st));
+  MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  MSSPE_CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
+  for (int i = 0; i < ndirs; i++) c->timing.select_ms[dirs[i]] = ms;
+  if (getenv("MSSPE_DEBUG_TIMERS"))
+    for (int i = 0; i < ndirs; i++)
+      fprintf(stderr, "[msspe] partitioned greedy dir %d: %u winners, %u iterations, %u rounds, %u external winners, %u multi-partition lists (%llu postings), %.3f ms\n",
+              dirs[i], h[i].n_out, h[i].iterations, h[i].rounds, h[i].rollbacks, A.d[i].n_multi, (unsigned long long)c->dir[dirs[i]].pv_multi_postings, ms);
+  return MSSPE_OK;
+}

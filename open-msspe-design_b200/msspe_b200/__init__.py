@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("MSSPE_LIB") or os.path.join(os.path.dirname(_PKG), "l
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_IO, ERR_CAPACITY = 0, -1, -2, -3, -4, -5, -6
 DIR_FWD, DIR_REV = 0, 1
 NO_KMER = np.uint64(0xFFFFFFFFFFFFFFFF)
-SELECT_RECOUNT, SELECT_INCREMENTAL, SELECT_AUTO, SELECT_BATCHED = 0, 1, 2, 0x100
+SELECT_RECOUNT, SELECT_INCREMENTAL, SELECT_AUTO, SELECT_PARTITIONED, SELECT_BATCHED = 0, 1, 2, 3, 0x100
 THAL_ANY, THAL_END1, THAL_HAIRPIN = 1, 2, 4
 
 # every symbol include/od_msspe_b200.h declares

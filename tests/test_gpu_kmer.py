@@ -99,7 +99,7 @@ def test_zika_inverted_index_matches_reference_mapping(zika_engine):
             assert post[int(offs[i]):int(offs[i + 1])].tolist() == want[int(codes[i])]
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 0x100, 0x101])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 0x100, 0x101])
 def test_zika_greedy_selection_bit_exact(zika_engine, zika_fasta, oracle_lib, mode):
     eng, _ = zika_engine
     _check_select(eng, oracle_lib, zika_fasta, 500, 250, 50, 13, 1000, 2, mode)
@@ -113,9 +113,11 @@ def test_zika_greedy_selection_bit_exact(zika_engine, zika_fasta, oracle_lib, mo
 def test_zika_stop_rules(zika_engine, zika_fasta, oracle_lib):
     """max_iterations bound (main.rs:344) and the frequency threshold break after the push (main.rs:387-390)."""
     eng, _ = zika_engine
-    _check_select(eng, oracle_lib, zika_fasta, 500, 250, 50, 13, 7, 2, 0)
-    _check_select(eng, oracle_lib, zika_fasta, 500, 250, 50, 13, 1000, 94, 0)
-    _check_select(eng, oracle_lib, zika_fasta, 500, 250, 50, 13, 0, 2, 0)
+    for mode in (0, 3):
+        _check_select(eng, oracle_lib, zika_fasta, 500, 250, 50, 13, 7, 2, mode)
+        _check_select(eng, oracle_lib, zika_fasta, 500, 250, 50, 13, 1000, 94, mode)
+        _check_select(eng, oracle_lib, zika_fasta, 500, 250, 50, 13, 0, 2, mode)
+        _check_select(eng, oracle_lib, zika_fasta, 500, 250, 50, 13, 1, 2, mode)
 
 
 def test_reference_unit_vectors_through_the_engine(oracle_lib):
@@ -133,6 +135,7 @@ def test_reference_unit_vectors_through_the_engine(oracle_lib):
     assert [ko.decode(int(c), 3) for c in f[0] if c != m.NO_KMER] == ["AAC", "ACC", "CCT"]
     assert len([c for c in r[1] if c != m.NO_KMER]) == 3
     _check_select(eng, oracle_lib, fa, 10, 5, 5, 3, 10, 1, 0)
+    _check_select(eng, oracle_lib, fa, 10, 5, 5, 3, 10, 1, 3)
     eng.close()
 
 
@@ -161,6 +164,7 @@ def _random_alignment(seed, n, L, p=0.03, gaps=True):
     (3, 64, 1000, 128, 64, 64, 5, 2),       # tiny k: heavy within-window duplicates, massive ties
     (4, 20, 1200, 300, 150, 100, 31, 1),    # maximum k
     (5, 25, 900, 90, 45, 45, 17, 1),        # k > 16: 64-bit codes
+    (6, 30, 1200, 100, 50, 30, 6, 3),       # single- and multi-partition lists mixed: many external winners in the partitioned loop
 ])
 def test_random_alignments_bit_exact(oracle_lib, seed, n, L, W, S, w, k, mms):
     import msspe_b200 as m
@@ -172,7 +176,7 @@ def test_random_alignments_bit_exact(oracle_lib, seed, n, L, W, S, w, k, mms):
     for d in (0, 1):
         want, part = oracle_lib.segment_slots(fa, W, S, w, k, d)
         assert np.array_equal(eng.segment_kmers(d), want)
-    for mode in (0, 1, 0x100, 0x101):   # persistent recount / persistent incremental / launch-per-phase recount / incremental
+    for mode in (0, 1, 2, 3, 0x100, 0x101):   # persistent recount / incremental / AUTO / partitioned / launch-per-phase recount / incremental
         _check_select(eng, oracle_lib, fa, W, S, w, k, 60, mms, mode)
     eng.close()
 
@@ -185,7 +189,7 @@ def test_identical_genomes_tie_storm(oracle_lib):
     eng = m.Engine(13, 500, 250, 50)
     eng.load_genomes(bases, offs)
     eng.build_index()
-    for mode in (0, 1, 0x100, 0x101):
+    for mode in (0, 1, 3, 0x100, 0x101):
         _check_select(eng, oracle_lib, fa, 500, 250, 50, 13, 40, 1, mode)
     eng.close()
 
@@ -201,13 +205,13 @@ def test_empty_and_degenerate_inputs(oracle_lib):
     g, maxp, s = eng.segment_info()
     assert g == 3 and maxp == 2
     assert np.all(eng.segment_kmers(0) == m.NO_KMER)
-    assert len(eng.select(0, 10, 1)) == 0 and len(eng.select(1, 10, 1, 1)) == 0
+    assert len(eng.select(0, 10, 1)) == 0 and len(eng.select(1, 10, 1, 1)) == 0 and len(eng.select(0, 10, 1, 3)) == 0
     fa2 = b">only\nACGTACGT\n"
     recs, (bases, offs) = _fasta_to_arrays(fa2)
     eng.load_genomes(bases, offs)
     eng.build_index()
     assert eng.segment_info()[0] == 0
-    assert len(eng.select(0, 10, 1)) == 0
+    assert len(eng.select(0, 10, 1)) == 0 and len(eng.select(0, 10, 1, 3)) == 0 and len(eng.select(1, 10, 1, 2)) == 0
     with pytest.raises(m.MsspeError):
         eng.load_genomes(np.zeros(0, np.uint8), np.zeros(1, np.uint64))  # "No sequences found", main.rs:652-654
     eng.close()
@@ -223,7 +227,7 @@ def test_cfg1_shape_full_size(oracle_lib):
     eng.load_genomes(g.reshape(-1), synth.offsets_for(g))
     eng.build_index()
     assert eng.segment_info()[0] == 50 * 39
-    for mode in (0, 1, 0x100):
+    for mode in (0, 1, 2, 3, 0x100):
         _check_select(eng, oracle_lib, fa, 500, 250, 50, k, 1000, 1, mode)
     eng.close()
 
@@ -317,6 +321,7 @@ def test_ragged_record_lengths_use_the_search_path(oracle_lib):
         want, part = oracle_lib.segment_slots(fa, 500, 250, 50, 13, d)
         assert np.array_equal(eng.segment_kmers(d), want)
     _check_select(eng, oracle_lib, fa, 500, 250, 50, 13, 60, 1, 0)
+    _check_select(eng, oracle_lib, fa, 500, 250, 50, 13, 60, 1, 3)
     cov, part2, rec = eng.coverage([], [])
     assert part2.tolist() == part.tolist() and rec.max() == 8
     eng.close()
@@ -398,3 +403,34 @@ def test_cfg5_shard_vs_oracle_golden(monkeypatch):
         assert a["code"][:100].tolist() == gold["dirs"][0]["codes"] and b["code"][:100].tolist() == gold["dirs"][1]["codes"]
     assert out[m.SELECT_RECOUNT] == out[m.SELECT_INCREMENTAL] == out[m.SELECT_AUTO] == out[m.SELECT_PARTITIONED]
     eng.close()
+
+
+@pytest.mark.parametrize("chunks", [None, ("1", "1"), ("3", "2")])
+def test_partitioned_loop_with_repeats_and_small_chunks(oracle_lib, zika_fasta, chunks, monkeypatch):
+    """MSSPE_SELECT_PARTITIONED where its hard cases live: a genome family with a repeated block (the strongest lists span
+    two partitions and win early: external winners, roll-backs, partition_coverage of already covered postings), with the
+    look-ahead chunk sizes forced down so that extension rounds, horizon limits and roll-backs interleave."""
+    import msspe_b200 as m
+    if chunks:
+        monkeypatch.setenv("MSSPE_PART_CHUNK0", chunks[0])
+        monkeypatch.setenv("MSSPE_PART_CHUNK", chunks[1])
+    rng = np.random.default_rng(5)
+    anc = rng.integers(0, 4, 3000)
+    anc[2000:2300] = anc[500:800]
+    out = []
+    for i in range(40):
+        s = anc.copy()
+        mut = rng.random(3000) < 0.03
+        s[mut] = rng.integers(0, 4, int(mut.sum()))
+        out.append(">r%d\n%s\n" % (i, "".join("ACGT"[x] for x in s)))
+    cases = [("".join(out).encode(), 500, 250, 50, 13, 200, 1), ("".join(out).encode(), 500, 250, 50, 13, 200, 3),
+             (zika_fasta, 500, 250, 50, 13, 1000, 2), (_random_alignment(6, 30, 1200), 100, 50, 30, 6, 60, 3)]
+    for fa, W, S, w, k, it, mms in cases:
+        recs, (bases, offs) = _fasta_to_arrays(fa)
+        eng = m.Engine(k, W, S, w)
+        eng.load_genomes(bases, offs)
+        eng.build_index()
+        _check_select(eng, oracle_lib, fa, W, S, w, k, it, mms, m.SELECT_PARTITIONED)
+        a, b = eng.select_both(it, mms, m.SELECT_PARTITIONED)
+        assert a.tobytes() == eng.select(0, it, mms, 0).tobytes() and b.tobytes() == eng.select(1, it, mms, 0).tobytes()
+        eng.close()
