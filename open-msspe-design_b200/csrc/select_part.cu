@@ -18,8 +18,9 @@
 //
 // Rounds of seven launches, enqueued in batches without host round trips (every kernel returns at once when its
 // direction is done):
-//   part_extend_kernel   one block per unit: (re)count after a roll-back, then up to `nsteps` greedy steps on exact
-//                        incremental counts (the unit's forward index), cover token per segment = the entry that covered it
+//   part_extend_kernel   one thread-block cluster per unit: roll-back of what changed since the external winner, then up to
+//                        `nsteps` greedy steps on exact incremental counts (the unit's forward index); cover token per
+//                        segment = the entry that covered it; partial arg-max / counts exchanged through DSMEM
 //   part_gather_kernel   list of not-yet-final entries
 //   part_merge_kernel    one warp per entry: its global position = entries of all units with a better key (binary
 //                        search per unit); also the tie count and the live records (coverage evals) of that iteration
@@ -27,15 +28,19 @@
 //   part_stage_kernel    multi-partition lists whose upper bound reaches the smallest winning frequency of the window
 //   part_verify_kernel   one block per staged list: cover-time histogram -> live count per iteration, exact tie scores
 //   part_finalize_kernel winners before the horizon / before t* become final; external winner applied, units flagged
-#include "engine.cuh"
+#include <cooperative_groups.h>
 
 #include <algorithm>
+
+#include "engine.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
 constexpr uint32_t TK_LIVE = 0xFFFFFFFFu;                  // segment not covered
 constexpr uint32_t LID_NONE = 0xFFFFFFFFu, LID_MULTI = 0x80000000u;
-constexpr uint32_t ST_FINISHED = 1u, ST_RECOUNT = 2u, ST_EXTEND = 4u;
+constexpr uint32_t ST_FINISHED = 1u, ST_ROLLBACK = 2u, ST_EXTEND = 4u;
 constexpr uint32_t T_INF = 0xFFFFFFFFu;
 constexpr int EXT_T = 512;        // threads of the unit kernel
 constexpr int NEWCAP = 2048;      // newly covered segments handled per batch of the apply phase
@@ -111,54 +116,102 @@ __device__ __forceinline__ uint32_t block_min_u32(uint32_t v, unsigned long long
 }
 
 // ---- unit kernel ---------------------------------------------------------------------------------------------------
+// One thread-block CLUSTER of C CTAs per unit (C = 1, 2, 4 or 8 by unit size): the CTAs split the unit's k-mers for the
+// arg-max, the winner's postings for the cover step and the unit's segments for a roll-back, and exchange their partial
+// results through distributed shared memory (every CTA pushes its part into the others' buffers, one hardware cluster
+// barrier, every CTA combines the same C parts) -- two cluster barriers per greedy step, no global-memory round trip.
+struct ExPart { unsigned long long key; long long delta; uint32_t cnt; uint32_t pad; };
+
+template <int C>
+__device__ __forceinline__ void cluster_sync_all() {
+  if (C == 1) __syncthreads();
+  else { __threadfence(); cg::this_cluster().sync(); }
+}
+
+// s_ex[par][r] of every CTA <- this CTA's part; after the barrier every CTA holds all C parts
+template <int C>
+__device__ __forceinline__ void exchange(ExPart (*s_ex)[8], int par, uint32_t rank, unsigned long long key, uint32_t cnt, long long delta) {
+  if (threadIdx.x == 0) {
+    ExPart e; e.key = key; e.delta = delta; e.cnt = cnt; e.pad = 0u;
+    if (C == 1) s_ex[par][0] = e;
+    else {
+      cg::cluster_group cl = cg::this_cluster();
+#pragma unroll
+      for (int rr = 0; rr < C; rr++) { ExPart* dst = cl.map_shared_rank(&s_ex[par][rank], rr); *dst = e; }
+    }
+  }
+  cluster_sync_all<C>();
+}
+
+// +1 / -1 on the live counts of the k-mers of `n` segments held in s_list (bit 31 of an entry = "revive": +1)
+__device__ __forceinline__ long long apply_list(const PartDir& D, const uint32_t* s_list, uint32_t n, uint32_t slots) {
+  long long d = 0;
+  const uint32_t items = n * slots;
+  for (uint32_t x = threadIdx.x; x < items; x += EXT_T) {
+    const uint32_t si = x / slots, q = x - si * slots;
+    const uint32_t e = s_list[si];
+    const uint32_t l = __ldg(D.fwdl + (unsigned long long)(e & 0x7FFFFFFFu) * slots + q);
+    if (l != LID_NONE) {
+      if (e & 0x80000000u) { d--; if (!(l & LID_MULTI)) atomicAdd(D.pfreq + l, 1u); }
+      else { d++; if (!(l & LID_MULTI)) atomicSub(D.pfreq + l, 1u); }
+    }
+  }
+  return d;
+}
+
+template <int C>
 __global__ void __launch_bounds__(EXT_T) part_extend_kernel(PartArgs A) {
   const PartDir& D = A.d[blockIdx.y];
   if (D.ctl->done) return;
-  const uint32_t u = blockIdx.x;
+  const uint32_t u = blockIdx.x / C, rank = blockIdx.x % C;   // cluster = C consecutive blocks of the x dimension
   const uint32_t st = D.status[u];
-  if (!(st & (ST_RECOUNT | ST_EXTEND))) return;
+  if (!(st & (ST_ROLLBACK | ST_EXTEND))) return;              // the whole cluster leaves together
   __shared__ unsigned long long sh[34];
   __shared__ unsigned long long s_key[EXT_T / 32];
   __shared__ uint32_t s_cnt[EXT_T / 32];
   __shared__ uint32_t s_new[NEWCAP];
   __shared__ uint32_t s_n;
-  __shared__ unsigned long long s_bkey;
-  __shared__ uint32_t s_bcnt;
+  __shared__ ExPart s_ex[2][8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t o0 = D.ucode_off[u], o1 = D.ucode_off[u + 1];
   const uint32_t g0 = D.useg_off[u], g1 = D.useg_off[u + 1];
   const uint32_t slot0 = u * A.CAP, slots = A.slots;
   uint32_t len = D.ulen[u];
-  unsigned long long live = D.ulive[u];
+  long long live = (long long)D.ulive[u];
   bool finished = (st & ST_FINISHED) != 0;
-  if (st & ST_RECOUNT) {  // state of the unit = its final entries + external winners: restore, then count from the forward index
+  int par = 0;
+  long long delta = 0;                                        // records this CTA took out of the live count, not yet exchanged
+  if (C > 1) cg::this_cluster().sync();                       // nobody pushes into a CTA that has not started yet
+  if (st & ST_ROLLBACK) {
+    // back to the unit's state at the external winner's iteration: segments covered by the truncated entries live again,
+    // segments the external winner newly covered leave the counts.  Cost ~ changed segments, not the unit.
     const uint32_t keep = D.rfin[u];
-    len = keep;
-    finished = false;
-    for (uint32_t i = g0 + tid; i < g1; i += EXT_T) {
-      const uint32_t g = D.usegs[i];
-      const uint32_t tk = __ldcg(D.token + g);
-      if (tk >= slot0 + keep && tk < slot0 + A.CAP) D.token[g] = TK_LIVE;
-    }
-    for (uint32_t j = o0 + tid; j < o1; j += EXT_T) D.pfreq[j] = 0u;
-    __syncthreads();
-    const unsigned long long n = (unsigned long long)(g1 - g0) * slots;
-    unsigned long long cnt = 0;
-    for (unsigned long long x = tid; x < n; x += EXT_T) {
-      const uint32_t si = (uint32_t)(x / slots), q = (uint32_t)(x - (unsigned long long)si * slots);
-      const uint32_t g = D.usegs[g0 + si];
-      if (__ldcg(D.token + g) == TK_LIVE) {
-        const uint32_t l = __ldg(D.fwdl + (unsigned long long)g * slots + q);
-        if (l != LID_NONE) { cnt++; if (!(l & LID_MULTI)) atomicAdd(D.pfreq + l, 1u); }
+    const uint32_t ext_live = A.U * A.CAP + 2u * (D.ctl->n_ext - 1u);   // token of "was live, now covered by the newest external winner"
+    len = keep; finished = false;
+    for (uint32_t b = g0 + rank * NEWCAP; b < g1; b += C * NEWCAP) {
+      if (tid == 0) s_n = 0u;
+      __syncthreads();
+      const uint32_t be = min(g1, b + (uint32_t)NEWCAP);
+      for (uint32_t i = b + tid; i < be; i += EXT_T) {
+        const uint32_t g = D.usegs[i];
+        const uint32_t tk = __ldcg(D.token + g);
+        if (tk >= slot0 + keep && tk < slot0 + A.CAP) { D.token[g] = TK_LIVE; s_new[atomicAdd(&s_n, 1u)] = g | 0x80000000u; }
+        else if (tk == ext_live) s_new[atomicAdd(&s_n, 1u)] = g;
       }
+      __syncthreads();
+      delta += apply_list(D, s_new, s_n, slots);
+      __syncthreads();
     }
-    live = block_sum_u64<EXT_T>(cnt, sh);
+    delta = (long long)block_sum_u64<EXT_T>((unsigned long long)delta, sh);
+    exchange<C>(s_ex, par, rank, 0ull, 0u, delta);
+    for (int rr = 0; rr < C; rr++) live -= s_ex[par][rr].delta;
+    par ^= 1; delta = 0;
   }
   for (uint32_t step = 0; step < A.nsteps && !finished; step++) {
     if (len >= A.CAP) { finished = true; break; }  // entry number CAP = max_iterations can never be among the first max_iterations
     // arg-max over the unit's k-mers: (live count, then smaller word = smaller index), and how many share the count
     unsigned long long bk = 0ull; uint32_t bc = 0u;
-    for (uint32_t j = o0 + tid; j < o1; j += EXT_T) {
+    for (uint32_t j = o0 + rank * EXT_T + tid; j < o1; j += C * EXT_T) {
       const uint32_t f = __ldcg(D.pfreq + j);
       const unsigned long long key = ((unsigned long long)f << 32) | (unsigned long long)(0xFFFFFFFFu - (j - o0));
       const uint32_t bf = (uint32_t)(bk >> 32);
@@ -178,26 +231,34 @@ __global__ void __launch_bounds__(EXT_T) part_extend_kernel(PartArgs A) {
     if (lane == 0) { s_key[warp] = bk; s_cnt[warp] = bc; }
     __syncthreads();
     if (tid == 0) {
-      unsigned long long k2 = 0ull; uint32_t c2 = 0u;
+      bk = 0ull; bc = 0u;
       for (int w2 = 0; w2 < EXT_T / 32; w2++) {
         const unsigned long long ok = s_key[w2]; const uint32_t oc = s_cnt[w2];
         if (!oc) continue;
-        const uint32_t f = (uint32_t)(ok >> 32), bf = (uint32_t)(k2 >> 32);
-        if (c2 == 0u || f > bf) { k2 = ok; c2 = oc; }
-        else if (f == bf) { c2 += oc; if (ok > k2) k2 = ok; }
+        const uint32_t f = (uint32_t)(ok >> 32), bf = (uint32_t)(bk >> 32);
+        if (bc == 0u || f > bf) { bk = ok; bc = oc; }
+        else if (f == bf) { bc += oc; if (ok > bk) bk = ok; }
       }
-      s_bkey = k2; s_bcnt = c2;
     }
-    __syncthreads();
-    const uint32_t fmax = s_bcnt ? (uint32_t)(s_bkey >> 32) : 0u;
+    exchange<C>(s_ex, par, rank, bk, bc, delta);      // + what the previous step took out of the live records
+    unsigned long long wk = 0ull; uint32_t wc = 0u;
+    for (int rr = 0; rr < C; rr++) {
+      const ExPart e = s_ex[par][rr];
+      live -= e.delta;
+      if (!e.cnt) continue;
+      const uint32_t f = (uint32_t)(e.key >> 32), bf = (uint32_t)(wk >> 32);
+      if (wc == 0u || f > bf) { wk = e.key; wc = e.cnt; }
+      else if (f == bf) { wc += e.cnt; if (e.key > wk) wk = e.key; }
+    }
+    par ^= 1; delta = 0;
+    const uint32_t fmax = wc ? (uint32_t)(wk >> 32) : 0u;
     if (fmax < 2u) { finished = true; break; }      // freq == 1 stops before the push (main.rs:354-360); 0 = None
-    const uint32_t jwin = o0 + (0xFFFFFFFFu - (uint32_t)s_bkey);
+    const uint32_t jwin = o0 + (0xFFFFFFFFu - (uint32_t)wk);
     const uint32_t cid = D.ucodes[jwin];
     const uint32_t slot = slot0 + len;
-    if (tid == 0) { PEntry e; e.freq = fmax; e.cid = cid; e.tied = s_bcnt; e.pad = 0u; e.live_before = live; D.entries[slot] = e; }
+    if (rank == 0 && tid == 0) { PEntry e; e.freq = fmax; e.cid = cid; e.tied = wc; e.pad = 0u; e.live_before = (unsigned long long)live; D.entries[slot] = e; }
     const uint32_t pb = D.post_off[cid], pe = D.post_off[cid + 1];
-    unsigned long long dec = 0;
-    for (uint32_t b = pb; b < pe; b += NEWCAP) {     // main.rs:371-378 for this unit: cover the winner's live segments ...
+    for (uint32_t b = pb + rank * NEWCAP; b < pe; b += C * NEWCAP) {   // main.rs:371-378 for this unit: cover the winner's live segments ...
       if (tid == 0) s_n = 0u;
       __syncthreads();
       const uint32_t be = min(pe, b + (uint32_t)NEWCAP);
@@ -206,19 +267,36 @@ __global__ void __launch_bounds__(EXT_T) part_extend_kernel(PartArgs A) {
         if (__ldcg(D.token + g) == TK_LIVE) { D.token[g] = slot; s_new[atomicAdd(&s_n, 1u)] = g; }
       }
       __syncthreads();
-      const uint32_t n = s_n * slots;              // ... and take their k-mers out of the live counts
-      for (uint32_t x = tid; x < n; x += EXT_T) {
-        const uint32_t si = x / slots, q = x - si * slots;
-        const uint32_t l = __ldg(D.fwdl + (unsigned long long)s_new[si] * slots + q);
-        if (l != LID_NONE) { dec++; if (!(l & LID_MULTI)) atomicSub(D.pfreq + l, 1u); }
-      }
+      delta += apply_list(D, s_new, s_n, slots);      // ... and take their k-mers out of the live counts
       __syncthreads();
     }
-    live -= block_sum_u64<EXT_T>(dec, sh);
+    delta = (long long)block_sum_u64<EXT_T>((unsigned long long)delta, sh);
+    cluster_sync_all<C>();                           // every CTA's decrements are in before anybody scans again
     len++;
     if (fmax < A.mms) { finished = true; break; }   // pushed, then break (main.rs:387-390)
   }
-  if (tid == 0) { D.ulen[u] = len; D.ulive[u] = live; D.status[u] = finished ? ST_FINISHED : 0u; }
+  exchange<C>(s_ex, par, rank, 0ull, 0u, delta);      // the last step's share of the live records
+  for (int rr = 0; rr < C; rr++) live -= s_ex[par][rr].delta;
+  if (rank == 0 && tid == 0) { D.ulen[u] = len; D.ulive[u] = (unsigned long long)live; D.status[u] = finished ? ST_FINISHED : 0u; }
+  if (C > 1) cg::this_cluster().sync();               // no CTA exits while a peer may still push into its shared memory
+}
+
+// initial state: live count of a single-partition list = its length; live records per unit
+__global__ void part_init_freq_kernel(PartArgs A) {
+  const PartDir& D = A.d[blockIdx.y];
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= D.n_single) return;
+  const uint32_t c = D.ucodes[j];
+  D.pfreq[j] = D.post_off[c + 1] - D.post_off[c];
+}
+__global__ void part_init_live_kernel(PartArgs A, unsigned long long G) {
+  const PartDir& D = A.d[blockIdx.y];
+  const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  uint32_t n = 0;
+  const uint32_t* f = D.fwdl + g * A.slots;
+  for (uint32_t q = 0; q < A.slots; q++) n += __ldg(f + q) != LID_NONE;
+  if (n) atomicAdd(D.ulive + part_of(A, (uint32_t)g), (unsigned long long)n);
 }
 
 // ---- list of non-final entries ------------------------------------------------------------------------------------------
@@ -564,7 +642,7 @@ __global__ void __launch_bounds__(1024) part_finalize_kernel(PartArgs A) {
       const bool tie_case = has_entry && D.entries[D.order[iw]].freq == cnt;
       o.n_tied = tie_case ? D.tied[iw] + D.mt[iw] : s_same;
       D.out[t_new] = o;
-      D.pos[A.U * A.CAP + j] = t_new;
+      D.pos[A.U * A.CAP + 2u * j] = t_new; D.pos[A.U * A.CAP + 2u * j + 1u] = t_new;
       C->evals += ev + (has_entry ? D.tot_live[iw] : C->live_all);
       C->iterations += iw + 1u;
     }
@@ -573,7 +651,8 @@ __global__ void __launch_bounds__(1024) part_finalize_kernel(PartArgs A) {
       const uint32_t g = D.postings[i];
       const uint32_t p = part_of(A, g);
       if (atomicExch(D.touch + p, 1u) == 0u) atomicAdd(D.ext_cov + p, 1u);
-      if (time_of(D, g) >= t_new) { D.token[g] = A.U * A.CAP + j; D.status[p] = ST_RECOUNT | ST_EXTEND; }
+      const uint32_t tk = __ldcg(D.token + g);    // two codes: "was live" (leaves the counts at the roll-back) / "was covered by a truncated entry"
+      if (tk == TK_LIVE || __ldcg(D.pos + tk) >= t_new) { D.token[g] = A.U * A.CAP + 2u * j + (tk != TK_LIVE ? 1u : 0u); D.status[p] = ST_ROLLBACK | ST_EXTEND; }
     }
     __syncthreads();
     for (uint32_t i = a + tid; i < b; i += 1024) D.touch[part_of(A, D.postings[i])] = 0u;
@@ -649,7 +728,28 @@ __global__ void pv_mlen_kernel(const uint32_t* __restrict__ ucodes, uint32_t n_s
 }
 __global__ void pv_status_kernel(uint32_t* status, uint32_t U) {
   const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u < U) status[u] = ST_RECOUNT | ST_EXTEND;
+  if (u < U) status[u] = ST_EXTEND;
+}
+
+template <int C>
+int launch_extend_c(msspe_ctx* c, const PartArgs& A, cudaStream_t st) {
+  if (C == 1) { part_extend_kernel<1><<<dim3(A.U, A.ndirs), EXT_T, 0, st>>>(A); return MSSPE_OK; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(A.U * C, A.ndirs); cfg.blockDim = dim3(EXT_T); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  MSSPE_CUDA_TRY(c, cudaLaunchKernelEx(&cfg, part_extend_kernel<C>, A));
+  return MSSPE_OK;
+}
+int launch_extend(msspe_ctx* c, const PartArgs& A, int csize, cudaStream_t st) {
+  switch (csize) {
+    case 8: return launch_extend_c<8>(c, A, st);
+    case 4: return launch_extend_c<4>(c, A, st);
+    case 2: return launch_extend_c<2>(c, A, st);
+    default: return launch_extend_c<1>(c, A, st);
+  }
 }
 
 uint32_t bits_for(uint32_t v) { uint32_t b = 1; while ((v >> b) != 0u && b < 32) b++; return b; }
@@ -745,7 +845,8 @@ int msspe_select_partitioned(msspe_ctx* c, int ndirs, const int* dirs, uint32_t 
   if (max_iter == 0) return MSSPE_OK;
   if (U == 0) { for (int i = 0; i < ndirs; i++) c->timing.select_iterations[dirs[i]] = 1; return MSSPE_OK; }
   const uint64_t CAP = max_iter;
-  if ((uint64_t)U * CAP + max_iter >= 0xFFFFFFF0ull) { c->set_error("msspe_select: %u partitions x %u iterations exceed the entry table of the partitioned loop", U, max_iter); return MSSPE_ERR_CAPACITY; }
+  if (G >= 0x80000000ull) { c->set_error("msspe_select: the partitioned loop holds at most 2^31 segments"); return MSSPE_ERR_CAPACITY; }
+  if ((uint64_t)U * CAP + 2ull * max_iter >= 0x7FFFFFF0ull) { c->set_error("msspe_select: %u partitions x %u iterations exceed the entry table of the partitioned loop", U, max_iter); return MSSPE_ERR_CAPACITY; }
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[2], st));
   PartArgs A{};
   A.ndirs = ndirs; A.U = U; A.CAP = (uint32_t)CAP; A.slots = c->slots; A.max_iter = max_iter; A.mms = mms;
@@ -775,11 +876,11 @@ int msspe_select_partitioned(msspe_ctx* c, int ndirs, const int* dirs, uint32_t 
     max_multi = std::max(max_multi, P.n_multi);
     const uint64_t ne = (uint64_t)U * CAP;
 #define PV_ALLOC(field, bytes, fill) { int rc2 = alloc((void**)&P.field, (bytes), (fill)); if (rc2) return rc2; }
-    PV_ALLOC(pfreq, ((uint64_t)X.n_codes + 1) * 4, 0);
+    PV_ALLOC(pfreq, ((uint64_t)X.n_codes + 1) * 4, -1);
     PV_ALLOC(token, (G + 1) * 4, 0xFF);
     PV_ALLOC(ulive, (uint64_t)U * 8, 0);
     PV_ALLOC(entries, ne * sizeof(PEntry), -1);
-    PV_ALLOC(pos, (ne + max_iter + 1) * 4, 0xFF);
+    PV_ALLOC(pos, (ne + 2ull * max_iter + 2) * 4, 0xFF);
     PV_ALLOC(rfin, (uint64_t)U * 4, 0);
     PV_ALLOC(ulen, (uint64_t)U * 4, 0);
     PV_ALLOC(status, (uint64_t)U * 4, -1);
@@ -810,6 +911,17 @@ int msspe_select_partitioned(msspe_ctx* c, int ndirs, const int* dirs, uint32_t 
   if (const char* e = getenv("MSSPE_PART_CHUNK0")) chunk0 = (uint32_t)std::max(1, atoi(e));
   if (const char* e = getenv("MSSPE_PART_CHUNK")) chunk = (uint32_t)std::max(1, atoi(e));
   const unsigned merge_grid = (unsigned)c->sm_count * 4u, ver_grid = (unsigned)c->sm_count * 2u;
+  // CTAs per unit (one thread-block cluster): by the forward-index entries of a unit, i.e. the work of covering all of it
+  const uint64_t unit_items = G / U * c->slots;
+  int csize = unit_items >= (1u << 20) ? 8 : unit_items >= (1u << 18) ? 4 : unit_items >= (1u << 16) ? 2 : 1;
+  if (const char* e = getenv("MSSPE_PART_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) csize = v; }
+  {
+    unsigned mx = 1;
+    for (int i = 0; i < ndirs; i++) mx = std::max<unsigned>(mx, A.d[i].n_single);
+    part_init_freq_kernel<<<dim3((mx + 255u) / 256u, ndirs), 256, 0, st>>>(A);
+    part_init_live_kernel<<<dim3((unsigned)div_up_u64(G, 256), ndirs), 256, 0, st>>>(A, G);
+    c->timing.kernel_launches += 2;
+  }
   PartCtl* h = reinterpret_cast<PartCtl*>(c->h_ctl);   // pinned staging: 2 x SelectCtl is larger than 2 x PartCtl
   static_assert(2 * sizeof(PartCtl) <= 2 * sizeof(SelectCtl), "pinned staging too small");
   uint32_t round = 0;
@@ -817,7 +929,10 @@ int msspe_select_partitioned(msspe_ctx* c, int ndirs, const int* dirs, uint32_t 
   for (;;) {
     for (uint32_t b = 0; b < BATCH; b++, round++) {
       A.nsteps = round == 0 ? chunk0 : chunk;
-      part_extend_kernel<<<dim3(U, ndirs), EXT_T, 0, st>>>(A);
+      {
+        int rc2 = launch_extend(c, A, csize, st);
+        if (rc2) return rc2;
+      }
       part_gather_kernel<<<ndirs, 1024, 0, st>>>(A);
       part_merge_kernel<<<dim3(merge_grid, ndirs), 256, 0, st>>>(A);
       part_plan_kernel<<<ndirs, 1024, 0, st>>>(A);
