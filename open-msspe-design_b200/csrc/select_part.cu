@@ -55,7 +55,8 @@ struct PartCtl {
   unsigned long long live_all;     // live records of all units (evals of the iteration that finds nothing)
   uint32_t E, H, cutbound, V, terminal, do_terminal, fmin, t_hi;
   uint32_t n_stage, n_viol, vmin, n_ext;
-  uint32_t rounds, rollbacks, staged_total, pad;
+  uint32_t rounds, rollbacks, wmax, last_viol;
+  uint32_t clipped, pad0, pad1, pad2;
 };
 
 struct PartDir {
@@ -143,17 +144,30 @@ __device__ __forceinline__ void exchange(ExPart (*s_ex)[8], int par, uint32_t ra
   cluster_sync_all<C>();
 }
 
-// +1 / -1 on the live counts of the k-mers of `n` segments held in s_list (bit 31 of an entry = "revive": +1)
+// +1 / -1 on the live counts of the k-mers of `n` segments held in s_list (bit 31 of an entry = "revive": +1).
+// Flattened over (segment, slot): consecutive lanes read consecutive forward-index entries (coalesced); four independent
+// loads are in flight per thread before the first atomic -- the loop is bound by L2 latency, not by bandwidth.
 __device__ __forceinline__ long long apply_list(const PartDir& D, const uint32_t* s_list, uint32_t n, uint32_t slots) {
   long long d = 0;
   const uint32_t items = n * slots;
-  for (uint32_t x = threadIdx.x; x < items; x += EXT_T) {
-    const uint32_t si = x / slots, q = x - si * slots;
-    const uint32_t e = s_list[si];
-    const uint32_t l = __ldg(D.fwdl + (unsigned long long)(e & 0x7FFFFFFFu) * slots + q);
-    if (l != LID_NONE) {
-      if (e & 0x80000000u) { d--; if (!(l & LID_MULTI)) atomicAdd(D.pfreq + l, 1u); }
-      else { d++; if (!(l & LID_MULTI)) atomicSub(D.pfreq + l, 1u); }
+  for (uint32_t x0 = threadIdx.x; x0 < items; x0 += 4 * EXT_T) {
+    uint32_t l[4], sg[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t x = x0 + k * EXT_T;
+      l[k] = LID_NONE; sg[k] = 0u;
+      if (x < items) {
+        const uint32_t si = x / slots, q = x - si * slots;
+        const uint32_t e = s_list[si];
+        sg[k] = e & 0x80000000u;
+        l[k] = __ldg(D.fwdl + (unsigned long long)(e & 0x7FFFFFFFu) * slots + q);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (l[k] == LID_NONE) continue;
+      if (sg[k]) { d--; if (!(l[k] & LID_MULTI)) atomicAdd(D.pfreq + l[k], 1u); }
+      else { d++; if (!(l[k] & LID_MULTI)) atomicSub(D.pfreq + l[k], 1u); }
     }
   }
   return d;
@@ -188,10 +202,12 @@ __global__ void __launch_bounds__(EXT_T) part_extend_kernel(PartArgs A) {
     const uint32_t keep = D.rfin[u];
     const uint32_t ext_live = A.U * A.CAP + 2u * (D.ctl->n_ext - 1u);   // token of "was live, now covered by the newest external winner"
     len = keep; finished = false;
-    for (uint32_t b = g0 + rank * NEWCAP; b < g1; b += C * NEWCAP) {
+    const uint32_t gshare = (g1 - g0 + C - 1) / C;
+    const uint32_t gb = min(g1, g0 + rank * gshare), ge = min(g1, gb + gshare);
+    for (uint32_t b = gb; b < ge; b += NEWCAP) {
       if (tid == 0) s_n = 0u;
       __syncthreads();
-      const uint32_t be = min(g1, b + (uint32_t)NEWCAP);
+      const uint32_t be = min(ge, b + (uint32_t)NEWCAP);
       for (uint32_t i = b + tid; i < be; i += EXT_T) {
         const uint32_t g = D.usegs[i];
         const uint32_t tk = __ldcg(D.token + g);
@@ -211,12 +227,19 @@ __global__ void __launch_bounds__(EXT_T) part_extend_kernel(PartArgs A) {
     if (len >= A.CAP) { finished = true; break; }  // entry number CAP = max_iterations can never be among the first max_iterations
     // arg-max over the unit's k-mers: (live count, then smaller word = smaller index), and how many share the count
     unsigned long long bk = 0ull; uint32_t bc = 0u;
-    for (uint32_t j = o0 + rank * EXT_T + tid; j < o1; j += C * EXT_T) {
-      const uint32_t f = __ldcg(D.pfreq + j);
-      const unsigned long long key = ((unsigned long long)f << 32) | (unsigned long long)(0xFFFFFFFFu - (j - o0));
-      const uint32_t bf = (uint32_t)(bk >> 32);
-      if (f > bf || bc == 0u) { bk = key; bc = 1u; }
-      else if (f == bf) { bc++; if (key > bk) bk = key; }
+    for (uint32_t j0 = o0 + rank * EXT_T + tid; j0 < o1; j0 += 4 * C * EXT_T) {   // four loads in flight per thread
+      uint32_t fv[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) { const uint32_t j = j0 + k * C * EXT_T; fv[k] = j < o1 ? __ldcg(D.pfreq + j) : 0xFFFFFFFFu; }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t f = fv[k], j = j0 + k * C * EXT_T;
+        if (j >= o1) continue;
+        const unsigned long long key = ((unsigned long long)f << 32) | (unsigned long long)(0xFFFFFFFFu - (j - o0));
+        const uint32_t bf = (uint32_t)(bk >> 32);
+        if (f > bf || bc == 0u) { bk = key; bc = 1u; }
+        else if (f == bf) { bc++; if (key > bk) bk = key; }
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -258,10 +281,12 @@ __global__ void __launch_bounds__(EXT_T) part_extend_kernel(PartArgs A) {
     const uint32_t slot = slot0 + len;
     if (rank == 0 && tid == 0) { PEntry e; e.freq = fmax; e.cid = cid; e.tied = wc; e.pad = 0u; e.live_before = (unsigned long long)live; D.entries[slot] = e; }
     const uint32_t pb = D.post_off[cid], pe = D.post_off[cid + 1];
-    for (uint32_t b = pb + rank * NEWCAP; b < pe; b += C * NEWCAP) {   // main.rs:371-378 for this unit: cover the winner's live segments ...
+    const uint32_t share = (pe - pb + C - 1) / C;      // an equal share of the winner's postings for every CTA of the cluster
+    const uint32_t mb = min(pe, pb + rank * share), me = min(pe, mb + share);
+    for (uint32_t b = mb; b < me; b += NEWCAP) {       // main.rs:371-378 for this unit: cover the winner's live segments ...
       if (tid == 0) s_n = 0u;
       __syncthreads();
-      const uint32_t be = min(pe, b + (uint32_t)NEWCAP);
+      const uint32_t be = min(me, b + (uint32_t)NEWCAP);
       for (uint32_t i = b + tid; i < be; i += EXT_T) {
         const uint32_t g = __ldg(D.postings + i);
         if (__ldcg(D.token + g) == TK_LIVE) { D.token[g] = slot; s_new[atomicAdd(&s_n, 1u)] = g; }
@@ -413,11 +438,16 @@ __global__ void __launch_bounds__(1024) part_plan_kernel(PartArgs A) {
     uint32_t cutbound = A.max_iter, terminal = 0u;
     if (first != T_INF) cutbound = min(cutbound, t_final + first + 1u);
     else if (E < room) { cutbound = t_final + E; terminal = 1u; }
-    const uint32_t V = min(H, cutbound);
-    const uint32_t do_term = (terminal && H == T_INF) ? 1u : 0u;
+    // verify at most wmax iterations ahead: the earliest external winner is all that counts, and it is usually near
+    uint32_t V = min(H, cutbound);
+    const uint32_t wmax = C->wmax ? C->wmax : A.max_iter;
+    bool clipped = false;
+    if (V - t_final > wmax) { V = t_final + wmax; clipped = true; }
+    const uint32_t do_term = (terminal && H == T_INF && !clipped) ? 1u : 0u;
     uint32_t fmin = T_INF;
     if (do_term) fmin = 2u;
     else if (V > t_final) fmin = D.entries[D.order[V - 1u - t_final]].freq;
+    C->clipped = clipped ? 1u : 0u;
     C->H = H; C->cutbound = cutbound; C->V = V; C->terminal = terminal; C->do_terminal = do_term; C->fmin = fmin; C->t_hi = V + do_term;
   }
 }
@@ -658,6 +688,8 @@ __global__ void __launch_bounds__(1024) part_finalize_kernel(PartArgs A) {
     for (uint32_t i = a + tid; i < b; i += 1024) D.touch[part_of(A, D.postings[i])] = 0u;
     if (tid == 0) {
       C->n_ext = j + 1u; C->rollbacks++;
+      const uint32_t gap = t_new - C->last_viol;     // window of the next rounds: twice the distance to the previous external winner
+      C->last_viol = t_new; C->wmax = min(A.max_iter, max(32u, 2u * gap));
       C->t_final = t_new + 1u;
       if (cnt < A.mms || t_new + 1u >= A.max_iter) { C->done = 1u; C->n_out = t_new + 1u; }
     }
@@ -665,7 +697,7 @@ __global__ void __launch_bounds__(1024) part_finalize_kernel(PartArgs A) {
   }
   const uint32_t cutbound = C->cutbound, H = C->H, terminal = C->terminal;
   const bool done = V == cutbound && (!terminal || H == T_INF);
-  if (!done) {
+  if (!done && !C->clipped) {                            // a clipped window was not limited by the horizon: nobody has to extend
     const uint32_t bound = terminal ? A.max_iter : cutbound;
     for (uint32_t u = tid; u < A.U; u += 1024) {
       const uint32_t st = D.status[u];
@@ -678,6 +710,7 @@ __global__ void __launch_bounds__(1024) part_finalize_kernel(PartArgs A) {
   if (tid == 0) {
     C->evals += ev; C->iterations += t_new - t_final;
     C->t_final = t_new;
+    if (C->wmax) C->wmax = min(A.max_iter, 2u * C->wmax);   // a clean window: look twice as far next time
     if (done) {
       if (C->do_terminal) { C->evals += C->live_all; C->iterations += 1u; }  // the call that found freq == 1 / nothing still counted
       C->done = 1u; C->n_out = t_new;
