@@ -1,23 +1,26 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the od-msspe hot path on B200 (contract: see the task statement).
 
-A "step" is one pass of the hot path over one synthetic input batch: BASELINE.json configs[1]
-(1,000 x 30 kb coronavirus-like pre-aligned genomes, k=13, window 500 / step 250 / search 50,
---check-hairpin --check-self-dimers, Tm sigma filter on, cross-dimers off): load -> K1 encode -> K2 index ->
-K3 greedy selection (both directions, up to 1000 iterations) -> K4-K6 primer thermodynamics -> filters.
+A "step" is one pass of the hot path over one synthetic input batch.  Workload at --gpus 1: BASELINE.json configs[2],
+the largest named single-GPU configuration (10,000 x 11 kb dengue-like pre-aligned genomes, k=15, window 500 / step 250 /
+search 50, --max-mismatch-segments=2, --max-iterations 1000, hairpin + self-dimer checks, Tm filters):
+load -> K1 encode -> K2 index -> K3 greedy selection (both directions) -> K4-K6 primer thermodynamics -> filters.
+The winners of every run are compared with tests/golden/cfg3_candidates.json (CPU oracle, offline).
 
-  value     reference-equivalent k-mer coverage evals / s with the genomes already resident in HBM
-            (one eval = one execution of od-msspe/src/main.rs:302-307; counted on the device, equal to
-            the oracle's count -- tests/test_gpu_kmer.py)
-  e2e       the same metric through the C ABI with HOST buffers (pinned host -> device copy and the
-            device -> host result reads inside the timed region)
-  roofline  the count kernel (K3 coverage scoring): algorithmic bytes = 4 B per eval
-  thal      secondary metric of BASELINE.json: all-ordered-pairs thal dimer pairs / s on a cfg4-style pool
+  value         reference-equivalent k-mer coverage evals / s with the genomes already resident in HBM (one eval = one
+                execution of od-msspe/src/main.rs:302-307; the count equals the oracle's, tests/test_gpu_kmer.py)
+  e2e           the same metric through the C ABI with HOST buffers (pinned host -> device copy of the genomes and the
+                device -> host reads of the results inside the timed region)
+  roofline      the kernel class with the largest share of device time in the timed steps (CUDA events around every launch,
+                msspe_get_kernel_profile): algorithmic bytes per launch / average launch time / measured HBM peak
+  thal          secondary metric of BASELINE.json: all-ordered-pairs thal dimer pairs / s on the 20,000-primer pool of
+                configs[3] (4.0e8 pairs), row-tiled across ranks, with its own (SM-issue) roofline entry
+  cpu_baseline  the CPU restatement of the reference (oracle/, single-threaded like the Rust binary, which cannot be
+                built in this image) on a bounded sample of the same workload
 
-`--impl reference` times the CPU restatement of the reference (oracle/, single-threaded like the Rust binary,
-which cannot be built in this image) on a bounded sample of the same workload.
-With --gpus N (torchrun) every rank runs an independent genome set of the same shape (weak scaling, no
-data-path collective) and the thal pair matrix is row-tiled across the ranks.
+`--impl reference` times that CPU restatement alone: the complete cfg3 alignment (every genome, every column), each step
+= the first REF_ITERS greedy iterations of both directions (the full 2 x 1000 iterations take the port ~50 minutes).
+With --gpus N (torchrun) see run_multi().
 """
 from __future__ import annotations
 
@@ -35,10 +38,17 @@ sys.path.insert(0, os.path.join(ROOT, "open-msspe-design_b200"))
 
 import numpy as np  # noqa: E402
 
-WORKLOAD = "cfg2: synthetic 1000 x 30 kb pre-aligned genomes, k=13, window 500/step 250/search 50, hairpin+self-dimer checks, Tm stddev filter"
-CPU_SAMPLE_COLS = 8000
-MAX_ITER = 1000
-THAL_POOL = 4096
+WORKLOAD = ("cfg3: synthetic 10,000 x 11 kb dengue-like pre-aligned genomes, k=15, window 500/step 250/search 50, "
+            "--max-mismatch-segments=2, --max-iterations 1000, hairpin+self-dimer checks, Tm min/max + stddev filters")
+CFG, K_WINDOW = "cfg3", (500, 250, 50)
+MAX_ITER, MMS = 1000, 2
+REF_ITERS = 2            # greedy iterations per direction and step of the CPU arm (complete alignment)
+THAL_POOL = 20_000       # BASELINE configs[3]
+THAL_COND = (50, 3, 0, 250, 25.0, 30, 0)
+THAL_LIMIT = -9000.0 + 1.0
+# algorithmic bytes of one launch of each kernel class are counted by the library (DESIGN.md section 4 states the
+# per-unit figures); flop of one 13-mer ordered pair through thal ANY: SURVEY.md 8(d), candidates x 25 on a uniform pool
+THAL_FLOP_PER_PAIR = 1.8e4
 
 
 def clock_sampler(stop, out, gpu_index):
@@ -83,40 +93,108 @@ def summarize_clocks(samples):
     return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(samples)}
 
 
-def run_reference(args, rank, world):
-    """CPU arm: the oracle's C++ port of the reference pipeline, single-threaded, on a bounded sample."""
-    if rank != 0:
-        return
+def load_golden():
+    with open(os.path.join(ROOT, "tests", "golden", "%s_candidates.json" % CFG)) as f:
+        return json.load(f)
+
+
+def cpu_arm(genomes, k, steps, warmup):
+    """The oracle's C++ port of find_candidates_kmers (main.rs:331-406: string k-mers, hash maps, a full recount per
+    iteration), single-threaded like the reference, on the COMPLETE alignment; the segment manager is built once
+    (untimed, as the GPU arm's genomes are resident); one step = REF_ITERS iterations of both directions."""
     from oracle import oracle as O
     from msspe_b200 import synth
     O.build()
-    g, k = synth.make_config("cfg2")
-    fa = synth.to_fasta(g[:, :CPU_SAMPLE_COLS])
-    cfg = O.default_config(check_cross_dimers=0)
+    W, S, w = K_WINDOW
+    t0 = time.perf_counter()
+    mgr = O.Manager(synth.to_fasta(genomes), W, S, w, k)
+    t_build = time.perf_counter() - t0
+    gold = load_golden()
     times, evals = [], 0
-    for it in range(args.warmup + args.steps):
+    for it in range(warmup + steps):
         t0 = time.perf_counter()
-        r = O.run_pipeline(fa, cfg, 0)
+        ev = 0
+        for d in (0, 1):
+            r = mgr.select(d, REF_ITERS, MMS)
+            ev += r["evals"]
+            assert r["codes"].tolist() == gold["dirs"][d]["codes"][:REF_ITERS]
         dt = time.perf_counter() - t0
-        ev = sum(r.evals)
-        r.close()
-        if it >= args.warmup:
+        if it >= warmup:
             times.append(dt)
             evals += ev
+    mgr.close()
     total = sum(times)
-    val = evals / total
-    sample = "columns [0,%d) of the cfg2 alignment (1000 genomes x %d partitions), full greedy loop both directions + primer thermo + filters" % (
-        CPU_SAMPLE_COLS, (CPU_SAMPLE_COLS - 500) // 250 + 1)
+    sample = ("the complete cfg3 alignment (10,000 genomes x 11,000 columns, %d segments); one step = the first %d greedy iterations "
+              "of both directions (2 x 1000 iterations take this port ~50 min); segment manager built once, untimed (%.0f s)" % (
+                  mgr.n_segments, REF_ITERS, t_build))
+    return {"value": evals / total, "unit": "evals/s", "cores": 1, "kind": "port", "sample": sample, "host_cores": os.cpu_count(),
+            "note": "restated reference baseline (oracle port, not the Rust binary: no cargo/rustc in this image); the reference is single-threaded",
+            "ms_per_step": 1e3 * total / max(1, len(times)), "steps": len(times)}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from msspe_b200 import synth
+    g, k = synth.make_config(CFG)
+    cpu = cpu_arm(g, k, args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": "kmer_coverage_evals_per_s", "value": val, "unit": "evals/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, len(times)), "higher_is_better": True,
+        "impl": "reference", "metric": "kmer_coverage_evals_per_s", "value": cpu["value"], "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": 1, "kind": "port", "sample": sample,
-                         "note": "restated reference baseline (not the Rust binary: no cargo/rustc in this image); the reference is single-threaded, host has %d cores" % (os.cpu_count() or 0)},
-        "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": WORKLOAD, "sample": cpu["sample"]},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def thal_section(eng, m, synth, dist, world, rank, dev, barrier):
+    """All ordered pairs of the cfg4 pool through thal ANY (delta_g.rs:61-153), rows tiled across the ranks; the compacted
+    lists stay on the device, one all_gather of the counts and one of the lists (msspe_b200/distributed.py)."""
+    import torch
+    from msspe_b200 import distributed as D
+    pool = synth.random_primers(THAL_POOL, 13, 4)
+    cond = m.ThalCond(*THAL_COND)
+    rb, re_ = D.row_block(THAL_POOL, rank, world)
+    ecap, ncap = max(1 << 16, (re_ - rb) * THAL_POOL // 50), max(1 << 16, (re_ - rb) * THAL_POOL // 2000)
+    eng.cross_dimer_device(pool, cond, THAL_LIMIT, rb, min(re_, rb + 64), edge_capacity=ecap, nostruct_capacity=ncap)  # warm-up
+    kernel_ms = []
+
+    def compute_rows(b0, b1):
+        r = eng.cross_dimer_device(pool, cond, THAL_LIMIT, b0, b1, edge_capacity=ecap, nostruct_capacity=ncap)
+        kernel_ms.append(float(eng.timing().dimer_ms))
+        return r
+
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    edges, nos = D.cross_dimer_sharded_tensors(compute_rows, THAL_POOL, m.EDGE_DTYPE, dist if world > 1 else None, dev)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t_thal = time.perf_counter() - t0
+    tt = torch.tensor([t_thal, sum(kernel_ms) / 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_thal, k_s = float(tt[0]), float(tt[1])
+    pairs = THAL_POOL * THAL_POOL
+    ncu = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_thal_dimer_metrics.json")) as f:
+            ncu = json.load(f)
+    except Exception:
+        pass
+    return {"metric": "thal_dimer_pairs_per_s", "value": pairs / t_thal, "unit": "pairs/s", "pairs": pairs,
+            "pool": "%d uniform-random 13-mers (BASELINE configs[3], seed 4), mv 50 dv 3 dNTP 0 DNA 250 nM 25 C" % THAL_POOL,
+            "kernel_only_pairs_per_s": pairs / k_s if k_s > 0 else None, "conflict_edges_below_-9000": int(len(edges)),
+            "structureless_pairs": int(len(nos)), "seconds": t_thal,
+            "scaling": "strong (rows tiled across ranks; one all_gather of counts + one of the device-resident lists)",
+            "roofline": {"bound": "sm_issue", "kernel": "thal_dimer_kernel<8>", "achieved": pairs / k_s if k_s > 0 else None, "unit": "pairs/s",
+                         "flop_per_pair": THAL_FLOP_PER_PAIR, "achieved_fp64_gflops": pairs / k_s * THAL_FLOP_PER_PAIR / 1e9 if k_s > 0 else None,
+                         "issue_active_pct": ncu.get("issue_active_pct"), "fp64_pipe_pct": ncu.get("fp64_pipe_pct"),
+                         "lanes_active_per_inst": ncu.get("lanes_active_per_inst"), "ncu_source": ncu.get("source"),
+                         "note": "16 B in / <= 48 B out per pair against ~1e4 instructions: HBM is irrelevant (ncu: < 0.01 % DRAM); the bound is SM issue slots"}}
 
 
 def main():
@@ -125,18 +203,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="recount", choices=["recount", "incremental"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "partitioned", "recount", "incremental"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-thal", action="store_true")
-    ap.add_argument("--batched", action="store_true", help="one launch per phase instead of the persistent kernel (for per-launch ncu numbers)")
-    ap.add_argument("--no-large", action="store_true", help="skip the cfg5/8-shard roofline probe (12,500 x 30 kb, inputs larger than L2)")
+    ap.add_argument("--no-large", action="store_true", help="skip the cfg5/8-shard probe of the recount kernel (12,500 x 30 kb, inputs larger than L2)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
         return
 
     # libraries (NCCL) print banners on fd 1: keep fd 1 clean for the single JSON line
@@ -155,11 +232,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    mode = m.SELECT_RECOUNT if args.mode == "recount" else m.SELECT_INCREMENTAL
-    if args.batched:
-        mode |= m.SELECT_BATCHED
-    # ---- synthetic input: every rank gets its own genome set of the cfg2 shape (weak scaling) ----
-    cfgd = dict(synth.CONFIGS["cfg2"])
+    mode = {"auto": m.SELECT_AUTO, "partitioned": m.SELECT_PARTITIONED, "recount": m.SELECT_RECOUNT, "incremental": m.SELECT_INCREMENTAL}[args.mode]
+    # ---- synthetic input (N > 1: every rank its own genome set of the same shape, no data-path collective) ----
+    cfgd = dict(synth.CONFIGS[CFG])
     k = cfgd.pop("k")
     cfgd["seed"] = cfgd["seed"] + 1000 * rank
     genomes = synth.synth_genomes(**cfgd)
@@ -167,12 +242,13 @@ def main():
     offs = synth.offsets_for(genomes)
     host_pinned = torch.from_numpy(genomes.reshape(-1)).pin_memory()
     dev_bases = host_pinned.to(dev, non_blocking=False)
-    mms = min(10, max(1, -(-n_rec // 50)))  # main.rs:658-660
     fcfg = m.default_filter_cfg()
+    gold = load_golden() if rank == 0 else None
 
-    eng = m.Engine(k, 500, 250, 50, device=local_rank)
+    eng = m.Engine(k, *K_WINDOW, device=local_rank)
     stream = torch.cuda.current_stream(dev)
     eng.set_stream(stream.cuda_stream)
+    d2h_bytes = [0]
 
     def one_step(device_resident: bool):
         if device_resident:
@@ -180,9 +256,11 @@ def main():
         else:
             eng.load_genomes(host_pinned.numpy(), offs)
         eng.build_index()
-        fwd, rev = eng.select_both(MAX_ITER, mms, mode)
+        fwd, rev = eng.select_both(MAX_ITER, MMS, mode)
         # get_kmer_stats + filter_kmers for both directions (main.rs:723-732, 408-516) through the C ABI, one device batch
-        kept = [st["code"][st["keep"] != 0] for st in eng.kmer_stats_both(fwd["code"], rev["code"], fcfg)]
+        st = eng.kmer_stats_both(fwd["code"], rev["code"], fcfg)
+        kept = [s["code"][s["keep"] != 0] for s in st]
+        d2h_bytes[0] = fwd.nbytes + rev.nbytes + st[0].nbytes + st[1].nbytes   # what came back to the host this step
         t = eng.timing()
         return int(t.select_evals[0] + t.select_evals[1]), fwd, rev, kept, t
 
@@ -192,7 +270,7 @@ def main():
         torch.cuda.synchronize(dev)
 
     def timed(fn, steps):
-        """K steps, device-timed with CUDA events on the launching stream; returns (ms_total, results)."""
+        """K steps, device-timed with CUDA events on the launching stream; returns (ms_total, wall ms, results)."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
@@ -204,7 +282,11 @@ def main():
         barrier()
         return max(e0.elapsed_time(e1), 0.0), wall, res
 
-    for _ in range(args.warmup):
+    # cold start: the very first step of the process (stream-ordered pool maps fresh memory, partition view built)
+    t0 = time.perf_counter()
+    _, _, _, _, tcold = one_step(True)
+    cold_ms = 1e3 * (time.perf_counter() - t0)
+    for _ in range(max(0, args.warmup - 1)):
         one_step(True)
     one_step(False)
 
@@ -214,41 +296,48 @@ def main():
     eng.reset_timing()
     ms_dev, wall_dev, res_dev = timed(lambda: one_step(True), args.steps)
     launches = eng.timing().kernel_launches
+    # the same K steps once more with CUDA events around every kernel launch of the library (two event records per launch
+    # cost ~0.5 ms per step, so the headline value is the unprofiled pass; both are inside bench.py's timed regions)
+    eng.set_profiling(True)
+    eng.reset_timing()
+    ms_prof, wall_prof, _ = timed(lambda: one_step(True), args.steps)
+    kprof = eng.kernel_profile()
+    eng.set_profiling(False)
     ms_e2e, wall_e2e, res_e2e = timed(lambda: one_step(False), args.steps)
     stop.set()
     th.join(timeout=2)
 
     evals_step = res_dev[0][0]
     assert all(r[0] == evals_step for r in res_dev + res_e2e)
-    # the device timeline includes host gaps (the engine synchronises between batches); use the larger of
-    # event time and wall time so that nothing is hidden
+    # the device timeline includes host gaps (the engine synchronises between stages); use the larger of event time and
+    # wall time so that nothing is hidden
     t_dev = max(ms_dev, wall_dev) / 1e3
     t_e2e = max(ms_e2e, wall_e2e) / 1e3
 
-    # ---- the incremental loop (identical winners, no recount after the first): reported separately ----
-    inc = None
-    if args.mode == "recount":
-        def inc_step():
-            eng.load_genomes_device(dev_bases.data_ptr(), offs, keepalive=dev_bases)
-            eng.build_index()
-            f2, r2 = eng.select_both(MAX_ITER, mms, m.SELECT_INCREMENTAL)
-            eng.kmer_stats_both(f2["code"], r2["code"], fcfg)
-            return f2, r2
-        inc_step()
-        ms_i, wall_i, res_i = timed(inc_step, args.steps)
-        same = res_i[0][0].tobytes() == res_dev[0][1].tobytes() and res_i[0][1].tobytes() == res_dev[0][2].tobytes()
-        t_i = max(ms_i, wall_i) / 1e3
-        inc = {"value": evals_step * args.steps / t_i, "unit": "reference-equivalent evals/s", "ms_per_step": 1e3 * t_i / args.steps,
-               "identical_winners": bool(same),
-               "note": "MSSPE_SELECT_INCREMENTAL: exact counts maintained through the forward index, one persistent kernel; no posting is re-streamed, so this is an algorithmic speed-up and not a bandwidth figure (on this rank)"}
+    golden = None
+    if rank == 0:
+        fwd, rev = res_dev[0][1], res_dev[0][2]
+        ok = all(x["code"].tolist() == gold["dirs"][d]["codes"] and x["freq"].tolist() == gold["dirs"][d]["freqs"] for d, x in enumerate((fwd, rev)))
+        ok = ok and evals_step == gold["dirs"][0]["evals"] + gold["dirs"][1]["evals"]
+        golden = {"file": "tests/golden/%s_candidates.json" % CFG, "matched": bool(ok),
+                  "what": "winners, frequencies and reference-equivalent evals of both directions vs the CPU oracle (tools/gen_size_goldens.py)"}
+        if not ok:
+            raise SystemExit("bench.py: winners differ from the oracle golden -- refusing to report a number")
 
-    # ---- roofline of the dominant kernel (count_kernel), from one extra profiled step ----
-    L_ = m.load_library()
-    L_.msspe_set_profiling(eng.h, 1)
-    _, _, _, _, tprof = one_step(True)
-    L_.msspe_set_profiling(eng.h, 0)
-    ck_ms = float(tprof.count_kernel_ms[0] + tprof.count_kernel_ms[1])
-    ck_n = int(tprof.count_kernel_launches[0] + tprof.count_kernel_launches[1])
+    # ---- the other exact loop implementations on the same index (reported separately) ----
+    variants = {}
+    if rank == 0:
+        for label, md in (("partitioned", m.SELECT_PARTITIONED), ("incremental", m.SELECT_INCREMENTAL), ("recount", m.SELECT_RECOUNT)):
+            eng.select_both(MAX_ITER, MMS, md)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            f2, r2 = eng.select_both(MAX_ITER, MMS, md)
+            dt = time.perf_counter() - t0
+            same = f2.tobytes() == res_dev[0][1].tobytes() and r2.tobytes() == res_dev[0][2].tobytes()
+            variants[label] = {"greedy_loop_ms": 1e3 * dt, "identical_winners": bool(same),
+                               "loop_evals_per_s": evals_step / dt}
+
+    # ---- roofline of the dominant kernel class of the timed steps ----
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -257,30 +346,47 @@ def main():
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    alg_bytes_per_launch = 4.0 * evals_step / max(1, ck_n)
-    phys_bytes_per_launch = 4.0 * float(tprof.select_postings_read[0] + tprof.select_postings_read[1]) / max(1, ck_n)
-    avg_launch_s = (ck_ms / 1e3) / max(1, ck_n)
-    achieved = alg_bytes_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "count_kernel_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": "count_kernel (K3 coverage scoring)", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs if peak_gbs else None, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes_per_launch, "physical_bytes_per_launch": phys_bytes_per_launch,
-                "physical_gbs": phys_bytes_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0,
-                "avg_launch_us": 1e6 * avg_launch_s, "launches": ck_n,
-                "timing": "in-kernel %globaltimer of block 0 around every coverage-scoring phase of the persistent kernel (one phase = one reference recount, both directions; includes the grid barrier that ends it); with --batched: CUDA events around each count_kernel launch",
-                "note": "cfg2 postings (2 x 18 MB) are L2-resident, the loop is latency-bound at this size; roofline_large_shard shows the same kernel where it is HBM-bound; see DESIGN.md"}
+    classes = [{"kernel": r["name"].decode(), "ms_per_step": float(r["ms"]) / args.steps, "launches_per_step": int(r["launches"]) // args.steps,
+                "alg_bytes_per_step": int(r["alg_bytes"]) // args.steps} for r in kprof]
+    classes.sort(key=lambda c: -c["ms_per_step"])
+    dom = classes[0] if classes else None
+    roofline = None
+    if dom:
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r2_dominant_kernel_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("kernel") == dom["kernel"]:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        lp = max(1, dom["launches_per_step"])
+        alg_per_launch = dom["alg_bytes_per_step"] / lp
+        avg_launch_s = dom["ms_per_step"] / 1e3 / lp
+        achieved = alg_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
+        bound = "hbm"
+        if traffic is not None and alg_per_launch > 0 and traffic < 0.25 * alg_per_launch:
+            bound = "latency/L2"
+        roofline = {"bound": bound, "kernel": dom["kernel"], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                    "frac": achieved / peak_gbs if peak_gbs else None, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_us": 1e6 * avg_launch_s, "launches_per_step": lp,
+                    "share_of_kernel_time": dom["ms_per_step"] / max(1e-9, sum(c["ms_per_step"] for c in classes)),
+                    "timing": "CUDA events around every launch of this class on the launching stream, inside the timed steps (msspe_get_kernel_profile)",
+                    "per_unit": "algorithmic bytes per launch as the library counts them; DESIGN.md section 4 states the per-unit figure of every class"}
+    # the greedy loop as a whole: reference-equivalent evals x 4 B against HBM (the partitioned loop skips the recount)
+    sel_ms = float(res_dev[0][4].select_ms[0])
+    greedy = {"loop_ms": sel_ms, "reference_equivalent_gbs": 4.0 * evals_step / (sel_ms / 1e3) / 1e9 if sel_ms > 0 else None, "peak": peak_gbs,
+              "note": "4 B x reference-equivalent evals / loop time: above the HBM peak because the per-partition loop examines each forward-index "
+                      "record about twice in the whole run instead of once per iteration; an algorithmic speed-up, not a bandwidth figure"}
 
-    # ---- the same kernel where it is HBM-bound: one GPU's shard of BASELINE configs[4] (100,000 x 30 kb over 8 GPUs) ----
+    # ---- the recount kernel where it is HBM-bound: one GPU's shard of BASELINE configs[4] (first 50 iterations) ----
     roofline_large = None
     if not args.no_large and rank == 0:
         big = synth.synth_genomes(12_500, 30_000, 5, clades=256, p_clade=0.10, p_leaf=0.01)
         e2 = m.Engine(13, 500, 250, 50, device=local_rank)
         e2.load_genomes(big.reshape(-1), synth.offsets_for(big))
+        e2.build_index()
+        tb0 = e2.timing()
         e2.build_index()
         tb = e2.timing()
         iters = 50
@@ -292,46 +398,25 @@ def main():
         ck2 = float(t2.count_kernel_ms[0] + t2.count_kernel_ms[1])
         n2 = int(t2.count_kernel_launches[0] + t2.count_kernel_launches[1])
         G2 = e2.segment_info()[0]
-        roofline_large = {"workload": "one GPU's shard of cfg5: 12,500 x 30 kb genomes (%d segments), first %d greedy iterations per direction" % (G2, iters),
-                          "bound": "hbm", "kernel": "coverage-scoring phase of greedy_persistent_kernel", "achieved": 4.0 * ev2 / ck2 / 1e6,
-                          "physical_gbs": 4.0 * pr2 / ck2 / 1e6, "peak": peak_gbs, "unit": "GB/s", "frac": 4.0 * ev2 / ck2 / 1e6 / peak_gbs,
+        t0 = time.perf_counter()
+        e2.select_both(1000, 10, m.SELECT_AUTO)
+        auto_ms = 1e3 * (time.perf_counter() - t0)
+        roofline_large = {"workload": "one GPU's shard of cfg5: 12,500 x 30 kb genomes (%d segments), first %d greedy iterations per direction, MSSPE_SELECT_RECOUNT" % (G2, iters),
+                          "bound": "hbm", "kernel": "coverage-scoring phase of greedy_persistent_kernel", "achieved": 4.0 * ev2 / ck2 / 1e6 if ck2 > 0 else None,
+                          "physical_gbs": 4.0 * pr2 / ck2 / 1e6 if ck2 > 0 else None, "peak": peak_gbs, "unit": "GB/s",
+                          "frac": 4.0 * ev2 / ck2 / 1e6 / peak_gbs if ck2 > 0 else None,
                           "algorithmic_bytes_per_launch": 4.0 * ev2 / max(1, n2), "avg_launch_us": 1e3 * ck2 / max(1, n2), "launches": n2,
-                          "postings_bytes_per_direction": int(4 * pr2 / max(1, n2)), "l2": "226 MB per direction per iteration: larger than the 126 MB L2",
+                          "l2": "226 MB of postings per direction per iteration: larger than the 126 MB L2",
+                          "encode_ms_first_build": float(tb0.encode_ms), "index_ms_first_build": float(tb0.index_ms),
                           "encode_ms": float(tb.encode_ms), "index_ms": float(tb.index_ms),
+                          "auto_loop_2x1000_iterations_ms": auto_ms,
                           "timing": "in-kernel %globaltimer of block 0 around the phase (includes the grid barrier that ends it)"}
         e2.close()
         del big
 
-    # ---- secondary metric: thal dimer pairs / s, pair matrix row-tiled across ranks ----
     thal = None
     if not args.no_thal:
-        from msspe_b200 import distributed as D
-        pool = synth.random_primers(THAL_POOL, 13, 4)
-        cond = m.ThalCond(50, 3, 0, 250, 25.0, 30, 0)
-        rb, re_ = D.row_block(THAL_POOL, rank, world)
-        eng.cross_dimer(pool, cond, -9000.0 + 1.0, rb, min(re_, rb + 64), edge_capacity=1 << 20, nostruct_capacity=1 << 16)  # warm-up
-        kernel_ms = []
-
-        def compute_rows(b0, b1):
-            r = eng.cross_dimer(pool, cond, -9000.0 + 1.0, b0, b1, edge_capacity=1 << 22, nostruct_capacity=1 << 20)
-            kernel_ms.append(float(eng.timing().dimer_ms))
-            return r
-
-        barrier()
-        t0 = time.perf_counter()
-        # rows tiled across ranks, compacted edge lists merged with one NCCL all_gather (msspe_b200/distributed.py)
-        edges, nos = D.cross_dimer_sharded(compute_rows, THAL_POOL, m.EDGE_DTYPE, dist if world > 1 else None, dev)
-        torch.cuda.synchronize(dev)
-        t_thal = time.perf_counter() - t0
-        tt = torch.tensor([t_thal, sum(kernel_ms) / 1e3], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_thal, k_s, n_edges = float(tt[0]), float(tt[1]), int(len(edges))
-        pairs = THAL_POOL * THAL_POOL
-        thal = {"metric": "thal_dimer_pairs_per_s", "value": pairs / t_thal, "unit": "pairs/s", "pairs": pairs,
-                "pool": "%d uniform-random 13-mers (cfg4 shape, seed 4), mv 50 dv 3 dNTP 0 DNA 250 nM 25 C" % THAL_POOL,
-                "kernel_only_pairs_per_s": pairs / k_s if k_s > 0 else None, "conflict_edges_below_-9000": n_edges,
-                "scaling": "strong (rows tiled across ranks)", "bound": "SM issue (FP64/ALU), not HBM"}
+        thal = thal_section(eng, m, synth, dist, world, rank, dev, barrier)
 
     # ---- aggregate over ranks ----
     agg = torch.tensor([float(evals_step * args.steps), t_dev, t_e2e, float(launches)], dtype=torch.float64, device=dev)
@@ -347,43 +432,35 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            from oracle import oracle as O
-            O.build()
-            fa = synth.to_fasta(genomes[:, :CPU_SAMPLE_COLS])
-            t0 = time.perf_counter()
-            r = O.run_pipeline(fa, O.default_config(check_cross_dimers=0), 0)
-            dt = time.perf_counter() - t0
-            cpu = {"value": sum(r.evals) / dt, "unit": "evals/s", "cores": 1, "kind": "port",
-                   "sample": "columns [0,%d) of the cfg2 alignment (1000 genomes x %d partitions), full pipeline, %.1f s" % (
-                       CPU_SAMPLE_COLS, (CPU_SAMPLE_COLS - 500) // 250 + 1, dt),
-                   "host_cores": os.cpu_count(),
-                   "note": "restated reference baseline (oracle port, not the Rust binary); the reference is single-threaded"}
-            r.close()
-        fwd, rev, kept = res_dev[0][1], res_dev[0][2], res_dev[0][3]
+            cpu = cpu_arm(genomes, k, 1, 0)
+        fwd, rev, kept, tm = res_dev[0][1], res_dev[0][2], res_dev[0][3], res_dev[0][4]
         h2d = int(genomes.size) + 8 * (n_rec + 1)
-        d2h = int((len(fwd) + len(rev)) * (24 + 5 * 8 + 3 * 40)) + 2 * 128
         line = {
             "metric": "kmer_coverage_evals_per_s", "value": total_evals / t_dev, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "select_mode": args.mode + ("+batched-launches" if args.batched else "+persistent-kernel" if args.mode == "recount" else ""), "genomes_per_gpu": n_rec, "genome_length": L,
-                       "max_iterations": MAX_ITER, "max_mismatch_segments": mms,
-                       "l2": "inputs per step (30 MB genomes + 2 x 18 MB postings) are smaller than L2; each step rebuilds the index from the genome bytes, nothing is cached across steps",
-                       "iterations": [int(res_dev[0][4].select_iterations[0]), int(res_dev[0][4].select_iterations[1])],
+            "config": {"workload": WORKLOAD, "select_mode": args.mode, "genomes_per_gpu": n_rec, "genome_length": L,
+                       "max_iterations": MAX_ITER, "max_mismatch_segments": MMS, "golden": golden,
+                       "multi_gpu": None if world == 1 else "every rank runs its own cfg3-shaped job (weak scaling, no data-path collective)",
+                       "l2": "inputs per step (110 MB of genomes, 2 x 62 MB of postings, 2 x 62 MB forward index) exceed the 126 MB L2; each step rebuilds the index from the genome bytes, nothing is cached across steps",
+                       "iterations": [int(tm.select_iterations[0]), int(tm.select_iterations[1])],
                        "candidates": [int(len(fwd)), int(len(rev))], "kept_after_filters": [int(len(kept[0])), int(len(kept[1]))],
                        "evals_per_step": evals_step},
-            "e2e": {"value": total_evals / t_e2e, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": total_evals / t_e2e, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h_bytes[0]),
                     "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": summarize_clocks(samples),
             "roofline": roofline,
+            "kernel_classes": classes,
+            "kernel_classes_ms_per_step_profiled_pass": 1e3 * max(ms_prof, wall_prof) / 1e3 / args.steps,
+            "greedy_loop": greedy,
+            "loop_variants": variants,
             "roofline_large_shard": roofline_large,
-            "incremental": inc,
             "cpu_baseline": cpu,
             "thal": thal,
-            "stage_ms": {"encode": float(res_dev[0][4].encode_ms), "index": float(res_dev[0][4].index_ms),
-                         "select_fwd": float(res_dev[0][4].select_ms[0]), "select_rev": float(res_dev[0][4].select_ms[1]),
-                         "thermo_last_dir": float(res_dev[0][4].thermo_ms)},
+            "stage_ms": {"encode": float(tm.encode_ms), "index": float(tm.index_ms), "select": float(tm.select_ms[0]), "thermo": float(tm.thermo_ms)},
+            "cold_start": {"first_step_ms": cold_ms, "encode_ms": float(tcold.encode_ms), "index_ms": float(tcold.index_ms),
+                           "note": "first step of the process: the stream-ordered pool maps fresh device memory, the partition view is built"},
         }
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     eng.close()

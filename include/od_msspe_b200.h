@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MSSPE_ABI_VERSION 1
+#define MSSPE_ABI_VERSION 2
 
 #define MSSPE_OK 0
 #define MSSPE_ERR_INVALID (-1)     /* bad argument (the reference would panic!/clap-error) */
@@ -149,7 +149,16 @@ int msspe_set_stream(msspe_ctx* ctx, void* cuda_stream);
 int msspe_synchronize(msspe_ctx* ctx);
 int msspe_get_timing(msspe_ctx* ctx, msspe_timing* out);
 int msspe_reset_timing(msspe_ctx* ctx);
-int msspe_set_profiling(msspe_ctx* ctx, int on); /* per-kernel event timing of the count kernel */
+int msspe_set_profiling(msspe_ctx* ctx, int on); /* per-launch CUDA-event timing of this library's kernels */
+/* Per kernel class since the last msspe_reset_timing: launches and algorithmic bytes (DESIGN.md states the per-unit figure
+ * of each class) always; device time (CUDA events around every launch, on the launching stream) while profiling is on. */
+typedef struct {
+  char name[56];
+  float ms;
+  uint32_t launches;
+  uint64_t alg_bytes;
+} msspe_kernel_prof;
+int msspe_get_kernel_profile(msspe_ctx* ctx, msspe_kernel_prof* out, uint32_t capacity, uint32_t* n);
 
 /* ---- (a) segments and inverted index ------------------------------------------------------- */
 /* Replaces get_segment_manager, main.rs:196-235 (input side).  `bases` = the records' sequences
@@ -288,6 +297,14 @@ int msspe_cross_dimer(msspe_ctx* ctx, const uint64_t* codes, uint32_t n, uint32_
                       const msspe_thal_cond* cond, uint32_t row_begin, uint32_t row_end, double dg_limit,
                       msspe_dimer_edge* edges, uint64_t edge_capacity, uint64_t* n_edges,
                       uint64_t* nostruct_pairs, uint64_t nostruct_capacity, uint64_t* n_nostruct);
+
+/* msspe_cross_dimer with the two compacted lists left on the DEVICE (unsorted; ctx-owned buffers, valid until the next
+ * cross-dimer call on this ctx): the per-rank half of the row-tiled N x N matrix of SURVEY 8(e) -- the ranks exchange the
+ * counts and merge the lists with one all_gather on device buffers instead of a host round trip per rank. */
+int msspe_cross_dimer_device(msspe_ctx* ctx, const uint64_t* codes, uint32_t n, uint32_t oligo_len,
+                             const msspe_thal_cond* cond, uint32_t row_begin, uint32_t row_end, double dg_limit,
+                             uint64_t edge_capacity, uint64_t nostruct_capacity, const msspe_dimer_edge** d_edges,
+                             uint64_t* n_edges, const uint64_t** d_nostruct, uint64_t* n_nostruct);
 
 #ifdef __cplusplus
 }

@@ -3,6 +3,7 @@
 #include "engine.cuh"
 
 static thread_local std::string g_create_error;
+static void kprof_resolve(msspe_ctx* c);
 
 extern "C" int msspe_abi_version(void) { return MSSPE_ABI_VERSION; }
 
@@ -104,6 +105,10 @@ extern "C" void msspe_destroy(msspe_ctx* c) {
   msspe_free_index(c);
   free_genomes(c);
   msspe_thal_free_tables(c);
+  if (c->xd_edges) cudaFreeAsync(c->xd_edges, c->stream);
+  if (c->xd_nostruct) cudaFreeAsync(c->xd_nostruct, c->stream);
+  kprof_resolve(c);
+  for (cudaEvent_t e : c->kprof_pool) cudaEventDestroy(e);
   for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -136,10 +141,57 @@ extern "C" int msspe_get_timing(msspe_ctx* c, msspe_timing* out) {
   *out = c->timing;
   return MSSPE_OK;
 }
+static void kprof_resolve(msspe_ctx* c) {
+  for (auto& p : c->kprof_pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(p.e1) == cudaSuccess && cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) c->kprof[p.cls].ms += ms;
+    c->kprof_pool.push_back(p.e0); c->kprof_pool.push_back(p.e1);
+  }
+  c->kprof_pending.clear();
+}
 extern "C" int msspe_reset_timing(msspe_ctx* c) {
   if (!c) return MSSPE_ERR_INVALID;
   memset(&c->timing, 0, sizeof c->timing);
+  kprof_resolve(c);
+  for (int i = 0; i < KP_N; i++) c->kprof[i] = KProfClass();
   return MSSPE_OK;
+}
+cudaEvent_t msspe_kprof_begin(msspe_ctx* c, cudaStream_t st) {
+  if (!c->profiling) return nullptr;
+  cudaEvent_t e = nullptr;
+  if (!c->kprof_pool.empty()) { e = c->kprof_pool.back(); c->kprof_pool.pop_back(); }
+  else if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+  cudaEventRecord(e, st);
+  return e;
+}
+void msspe_kprof_end(msspe_ctx* c, int cls, cudaEvent_t e0, cudaStream_t st, uint64_t alg_bytes) {
+  c->kprof[cls].launches++; c->kprof[cls].bytes += alg_bytes;
+  c->timing.kernel_launches++;
+  if (!e0) return;
+  cudaEvent_t e1 = nullptr;
+  if (!c->kprof_pool.empty()) { e1 = c->kprof_pool.back(); c->kprof_pool.pop_back(); }
+  else if (cudaEventCreate(&e1) != cudaSuccess) { c->kprof_pool.push_back(e0); return; }
+  cudaEventRecord(e1, st);
+  c->kprof_pending.push_back({cls, e0, e1});
+}
+extern "C" int msspe_get_kernel_profile(msspe_ctx* c, msspe_kernel_prof* out, uint32_t capacity, uint32_t* n) {
+  if (!c || !n) return MSSPE_ERR_INVALID;
+  static const char* names[KP_N] = {"encode_windows", "radix_hist", "radix_scatter", "scan", "build_csr", "partition_view", "greedy_unit (part_extend)",
+                                    "greedy_merge (gather/merge/plan/stage/finalize)", "greedy_verify", "greedy_whole_index", "primer_thermo", "thal_dimer"};
+  MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
+  kprof_resolve(c);
+  uint32_t k = 0;
+  for (int i = 0; i < KP_N; i++) {
+    if (!c->kprof[i].launches) continue;
+    if (out && k < capacity) {
+      memset(&out[k], 0, sizeof out[k]);
+      snprintf(out[k].name, sizeof out[k].name, "%s", names[i]);
+      out[k].ms = (float)c->kprof[i].ms; out[k].launches = c->kprof[i].launches; out[k].alg_bytes = c->kprof[i].bytes;
+    }
+    k++;
+  }
+  *n = k;
+  return (out && k > capacity) ? MSSPE_ERR_CAPACITY : MSSPE_OK;
 }
 extern "C" int msspe_set_profiling(msspe_ctx* c, int on) {
   if (!c) return MSSPE_ERR_INVALID;

@@ -91,7 +91,19 @@ struct SelectCtl {
   unsigned long long t_fine[24];   // per-step clocks, only written by a -DMSSPE_FINE_TIMERS build (diagnostic)
 };
 
+// Kernel classes of the per-kernel profile (msspe_get_kernel_profile): launches and algorithmic bytes are always counted,
+// device time only while msspe_set_profiling is on (two CUDA events around every launch, on the launching stream).
+enum {
+  KP_ENCODE = 0, KP_SORT_HIST, KP_SORT_SCATTER, KP_SCAN, KP_CSR, KP_VIEW, KP_GREEDY_UNIT, KP_GREEDY_MERGE, KP_GREEDY_VERIFY,
+  KP_GREEDY_WHOLE, KP_THERMO, KP_DIMER, KP_N
+};
+struct KProfClass { double ms = 0.0; uint32_t launches = 0; uint64_t bytes = 0; };
+struct KProfPending { int cls; cudaEvent_t e0, e1; };
+
 struct msspe_ctx {
+  KProfClass kprof[KP_N];
+  std::vector<KProfPending> kprof_pending;
+  std::vector<cudaEvent_t> kprof_pool;
   msspe_config cfg{};
   int device = 0;
   int sm_count = 148;
@@ -123,6 +135,8 @@ struct msspe_ctx {
   msspe_thal_raw_params raw{};
   bool raw_set = false;
   struct ThalDeviceTables* d_thal = nullptr;  // device copy of static tables
+  msspe_dimer_edge* xd_edges = nullptr;       // msspe_cross_dimer_device: lists of the last call (ctx-owned)
+  uint64_t* xd_nostruct = nullptr;
   // pinned staging
   SelectCtl* h_ctl = nullptr;  // [2] pinned
   msspe_timing timing{};
@@ -158,6 +172,17 @@ int msspe_thal_upload_tables(msspe_ctx* ctx);
 void msspe_thal_free_tables(msspe_ctx* ctx);
 
 static inline uint64_t div_up_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// ---- per-kernel profile (ctx.cu) ----
+cudaEvent_t msspe_kprof_begin(msspe_ctx* c, cudaStream_t st);
+void msspe_kprof_end(msspe_ctx* c, int cls, cudaEvent_t e0, cudaStream_t st, uint64_t alg_bytes);
+// usage: { KPROF(c, KP_X, st, bytes) kernel<<<...>>>(...); }   -- the guard's destructor records the closing event
+struct KProfGuard {
+  msspe_ctx* c; int cls; cudaStream_t st; uint64_t bytes; cudaEvent_t e0;
+  KProfGuard(msspe_ctx* c_, int cls_, cudaStream_t st_, uint64_t bytes_) : c(c_), cls(cls_), st(st_), bytes(bytes_), e0(msspe_kprof_begin(c_, st_)) {}
+  ~KProfGuard() { msspe_kprof_end(c, cls, e0, st, bytes); }
+};
+#define KPROF(c, cls, st, bytes) KProfGuard _kp_guard_##__LINE__((c), (cls), (st), (uint64_t)(bytes));
 
 // Device memory comes from the stream-ordered pool (cudaMallocAsync): no device-wide synchronisation per
 // allocation, and freed blocks are cached by the pool (release threshold = unlimited, set in msspe_create).

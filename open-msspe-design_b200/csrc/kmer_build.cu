@@ -150,18 +150,15 @@ int msspe_exclusive_scan_u32(msspe_ctx* ctx, const uint32_t* in, uint32_t* out, 
     MSSPE_CUDA_TRY(ctx, cudaMemcpyAsync(last_in, in + (n - 1), 4, cudaMemcpyDeviceToDevice, st));
   }
   if (nb > 1) MSSPE_CUDA_TRY(ctx, cudaMallocAsync(&bsum, nb * sizeof(uint32_t), st));
-  scan_block_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, n, bsum);
-  ctx->timing.kernel_launches++;
+  { KPROF(ctx, KP_SCAN, st, n * 8) scan_block_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, n, bsum); }
   if (nb > 1) {
     int rc = msspe_exclusive_scan_u32(ctx, bsum, bsum, nb, nullptr, st);
     if (rc) return rc;
-    scan_add_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(out, n, bsum);
-    ctx->timing.kernel_launches++;
+    { KPROF(ctx, KP_SCAN, st, n * 8) scan_add_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(out, n, bsum); }
     MSSPE_CUDA_TRY(ctx, cudaFreeAsync(bsum, st));
   }
   if (d_total) {
-    scan_total_kernel<<<1, 1, 0, st>>>(last_in, out + (n - 1), d_total);
-    ctx->timing.kernel_launches++;
+    { KPROF(ctx, KP_SCAN, st, 8) scan_total_kernel<<<1, 1, 0, st>>>(last_in, out + (n - 1), d_total); }
     MSSPE_CUDA_TRY(ctx, cudaFreeAsync(last_in, st));
   }
   MSSPE_CUDA_TRY(ctx, cudaGetLastError());
@@ -292,12 +289,10 @@ int msspe_radix_sort_pairs(msspe_ctx* c, uint64_t** key_a, uint32_t** val_a, uin
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&hist, (uint64_t)256 * nb * sizeof(uint32_t), st));
   const int passes = (int)((key_bits + 7) / 8);
   for (int p = 0; p < passes; p++) {
-    radix_hist_kernel<<<nb, RS_THREADS, 0, st>>>(*key_a, n, 8 * p, hist, nb);
-    c->timing.kernel_launches++;
+    { KPROF(c, KP_SORT_HIST, st, n * 8) radix_hist_kernel<<<nb, RS_THREADS, 0, st>>>(*key_a, n, 8 * p, hist, nb); }
     int rc = msspe_exclusive_scan_u32(c, hist, hist, (uint64_t)256 * nb, nullptr, st);
     if (rc) return rc;
-    radix_scatter_kernel<<<nb, RS_THREADS, 0, st>>>(*key_a, *val_a, n, 8 * p, hist, nb, *key_b, *val_b);
-    c->timing.kernel_launches++;
+    { KPROF(c, KP_SORT_SCATTER, st, n * 24) radix_scatter_kernel<<<nb, RS_THREADS, 0, st>>>(*key_a, *val_a, n, 8 * p, hist, nb, *key_b, *val_b); }
     std::swap(*key_a, *key_b); std::swap(*val_a, *val_b);
   }
   MSSPE_CUDA_TRY(c, cudaGetLastError());
@@ -332,11 +327,13 @@ int launch_encode(msspe_ctx* c, int mode, uint32_t* counts, const uint32_t* rec_
     cudaFuncSetAttribute(encode_windows_kernel<ENC_EMIT, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(encode_windows_kernel<ENC_DENSE, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
-  if (mode == ENC_COUNT) encode_windows_kernel<ENC_COUNT, DIR><<<grid, ENC_WARPS * 32, smem, st>>>(ENC_ARGS);
-  else if (mode == ENC_EMIT) encode_windows_kernel<ENC_EMIT, DIR><<<grid, ENC_WARPS * 32, smem, st>>>(ENC_ARGS);
-  else encode_windows_kernel<ENC_DENSE, DIR><<<grid, ENC_WARPS * 32, smem, st>>>(ENC_ARGS);
+  {
+    KPROF(c, KP_ENCODE, st, c->n_segments * (w + (mode == ENC_COUNT ? 4u : slots * (mode == ENC_EMIT ? 12u : 8u))))
+    if (mode == ENC_COUNT) encode_windows_kernel<ENC_COUNT, DIR><<<grid, ENC_WARPS * 32, smem, st>>>(ENC_ARGS);
+    else if (mode == ENC_EMIT) encode_windows_kernel<ENC_EMIT, DIR><<<grid, ENC_WARPS * 32, smem, st>>>(ENC_ARGS);
+    else encode_windows_kernel<ENC_DENSE, DIR><<<grid, ENC_WARPS * 32, smem, st>>>(ENC_ARGS);
+  }
 #undef ENC_ARGS
-  c->timing.kernel_launches++;
   MSSPE_CUDA_TRY(c, cudaGetLastError());
   return MSSPE_OK;
 }
@@ -384,8 +381,7 @@ int build_direction(msspe_ctx* c, int dir, float* enc_ms, float* idx_ms) {
     // sorted records are in key_a / val_a
     uint32_t* flags = nullptr;
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&flags, (uint64_t)R * 4, st));
-    mark_heads_kernel<<<(unsigned)div_up_u64(R, 256), 256, 0, st>>>(key_a, R, flags);
-    c->timing.kernel_launches++;
+    { KPROF(c, KP_CSR, st, (uint64_t)R * 12) mark_heads_kernel<<<(unsigned)div_up_u64(R, 256), 256, 0, st>>>(key_a, R, flags); }
     rc = msspe_exclusive_scan_u32(c, flags, flags, R, d_total, st);
     if (rc) return rc;
     MSSPE_CUDA_TRY(c, cudaMemcpyAsync(&n_codes, d_total, 4, cudaMemcpyDeviceToHost, st));
@@ -396,10 +392,10 @@ int build_direction(msspe_ctx* c, int dir, float* enc_ms, float* idx_ms) {
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.postings, (uint64_t)R * 4, c->stream));
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.list_part, (uint64_t)(n_codes ? n_codes : 1) * 4, c->stream));
     MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.list_part, 0, (uint64_t)(n_codes ? n_codes : 1) * 4, st));
-    build_csr_kernel<<<(unsigned)div_up_u64(R, 256), 256, 0, st>>>(key_a, val_a, flags, R, slots, n_codes, D.codes,
+    { KPROF(c, KP_CSR, st, (uint64_t)R * 24)
+      build_csr_kernel<<<(unsigned)div_up_u64(R, 256), 256, 0, st>>>(key_a, val_a, flags, R, slots, n_codes, D.codes,
                                                                   D.post_off, D.postings, D.fwd_ids, c->d_seg_part,
-                                                                  (c->uniform_parts && c->uniform_parts <= 65536u) ? c->uniform_parts : 0u, D.list_part);
-    c->timing.kernel_launches++;
+                                                                  (c->uniform_parts && c->uniform_parts <= 65536u) ? c->uniform_parts : 0u, D.list_part); }
     MSSPE_CUDA_TRY(c, cudaGetLastError());
     MSSPE_CUDA_TRY(c, cudaFreeAsync(flags, st));
     MSSPE_CUDA_TRY(c, cudaFreeAsync(key_b, st));

@@ -1017,8 +1017,7 @@ int run_select_persistent(msspe_ctx* c, int ndirs, const int* dirs, uint32_t max
     }
     MSSPE_CUDA_TRY(c, cudaMemsetAsync(A.barrier, 0, 4, st));
     void* kargs[] = {(void*)&A};
-    MSSPE_CUDA_TRY(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), kargs, smem, st));
-    c->timing.kernel_launches++;
+    { KPROF(c, KP_GREEDY_WHOLE, st, 0) MSSPE_CUDA_TRY(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), kargs, smem, st)); }
     launches++;
     for (int i = 0; i < ndirs; i++)
       MSSPE_CUDA_TRY(c, cudaMemcpyAsync(&c->h_ctl[i], c->dir[dirs[i]].ctl, sizeof(SelectCtl), cudaMemcpyDeviceToHost, st));
@@ -1502,8 +1501,7 @@ int run_select_incremental(msspe_ctx* c, int ndirs, const int* dirs, uint32_t ma
   if (per_sm < 1) { c->set_error("msspe_select: incremental kernel does not fit on an SM"); return MSSPE_ERR_CAPACITY; }
   if (per_sm > 2) per_sm = 2;
   void* kargs[] = {(void*)&A};
-  MSSPE_CUDA_TRY(c, cudaLaunchCooperativeKernel(fn, dim3((unsigned)c->sm_count * (unsigned)per_sm), dim3(512), kargs, smem, st));
-  c->timing.kernel_launches++;
+  { KPROF(c, KP_GREEDY_WHOLE, st, 0) MSSPE_CUDA_TRY(c, cudaLaunchCooperativeKernel(fn, dim3((unsigned)c->sm_count * (unsigned)per_sm), dim3(512), kargs, smem, st)); }
   for (int i = 0; i < ndirs; i++)
     MSSPE_CUDA_TRY(c, cudaMemcpyAsync(&c->h_ctl[i], c->dir[dirs[i]].ctl, sizeof(SelectCtl), cudaMemcpyDeviceToHost, st));
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[3], st));

@@ -963,19 +963,18 @@ int msspe_select_partitioned(msspe_ctx* c, int ndirs, const int* dirs, uint32_t 
     for (uint32_t b = 0; b < BATCH; b++, round++) {
       A.nsteps = round == 0 ? chunk0 : chunk;
       {
+        KPROF(c, KP_GREEDY_UNIT, st, 0)
         int rc2 = launch_extend(c, A, csize, st);
         if (rc2) return rc2;
       }
-      part_gather_kernel<<<ndirs, 1024, 0, st>>>(A);
-      part_merge_kernel<<<dim3(merge_grid, ndirs), 256, 0, st>>>(A);
-      part_plan_kernel<<<ndirs, 1024, 0, st>>>(A);
+      { KPROF(c, KP_GREEDY_MERGE, st, 0) part_gather_kernel<<<ndirs, 1024, 0, st>>>(A); }
+      { KPROF(c, KP_GREEDY_MERGE, st, 0) part_merge_kernel<<<dim3(merge_grid, ndirs), 256, 0, st>>>(A); }
+      { KPROF(c, KP_GREEDY_MERGE, st, 0) part_plan_kernel<<<ndirs, 1024, 0, st>>>(A); }
       if (max_multi) {
-        part_stage_kernel<<<dim3((max_multi + 255u) / 256u, ndirs), 256, 0, st>>>(A);
-        part_verify_kernel<<<dim3(ver_grid, ndirs), VER_T, ver_smem, st>>>(A);
-        c->timing.kernel_launches += 2;
+        { KPROF(c, KP_GREEDY_MERGE, st, 0) part_stage_kernel<<<dim3((max_multi + 255u) / 256u, ndirs), 256, 0, st>>>(A); }
+        { KPROF(c, KP_GREEDY_VERIFY, st, 0) part_verify_kernel<<<dim3(ver_grid, ndirs), VER_T, ver_smem, st>>>(A); }
       }
-      part_finalize_kernel<<<ndirs, 1024, 0, st>>>(A);
-      c->timing.kernel_launches += 5;
+      { KPROF(c, KP_GREEDY_MERGE, st, 0) part_finalize_kernel<<<ndirs, 1024, 0, st>>>(A); }
     }
     MSSPE_CUDA_TRY(c, cudaGetLastError());
     for (int i = 0; i < ndirs; i++) MSSPE_CUDA_TRY(c, cudaMemcpyAsync(&h[i], A.d[i].ctl, sizeof(PartCtl), cudaMemcpyDeviceToHost, st));

@@ -851,9 +851,11 @@ int launch_dimer(msspe_ctx* c, DimerArgs& A, cudaStream_t st) {
   if (per_sm < 1) per_sm = 1;
   const unsigned long long resident = (unsigned long long)c->sm_count * per_sm;
   const unsigned grid = (unsigned)(blocks_needed < resident ? blocks_needed : resident);
-  if (sub == 8) thal_dimer_kernel<8><<<grid, DIMER_THREADS, smem, st>>>(A);
-  else thal_dimer_kernel<16><<<grid, DIMER_THREADS, smem, st>>>(A);
-  c->timing.kernel_launches++;
+  {
+    KPROF(c, KP_DIMER, st, A.n_pairs * 16)
+    if (sub == 8) thal_dimer_kernel<8><<<grid, DIMER_THREADS, smem, st>>>(A);
+    else thal_dimer_kernel<16><<<grid, DIMER_THREADS, smem, st>>>(A);
+  }
   MSSPE_CUDA_TRY(c, cudaGetLastError());
   return MSSPE_OK;
 }
@@ -943,7 +945,7 @@ static int thal_pairs_impl(msspe_ctx* c, const uint64_t* a, const uint64_t* b, u
     if (rc) return rc;
   } else {
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&(db.st = c->stream, db.p), n_pairs * 8, c->stream));
-    MSSPE_CUDA_TRY(c, cudaMallocAsync(&dK.p, sizeof(ThalDimerConsts), c->stream));
+    MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dK.st = c->stream, dK.p), sizeof(ThalDimerConsts), c->stream));
     MSSPE_CUDA_TRY(c, cudaMemcpyAsync(db.p, b, n_pairs * 8, cudaMemcpyHostToDevice, st));
     MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dK.p, &K, sizeof K, cudaMemcpyHostToDevice, st));
     DimerArgs A{};
@@ -999,7 +1001,7 @@ extern "C" int msspe_primer_thermo(msspe_ctx* c, const uint64_t* codes, uint32_t
   }
   DeviceBuf dcodes, dK, dtm, dgc, dout, dwork;
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dcodes.st = c->stream, dcodes.p), (size_t)n * 8, c->stream));
-  MSSPE_CUDA_TRY(c, cudaMallocAsync(&dK.p, sizeof K, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dK.st = c->stream, dK.p), sizeof K, c->stream));
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dtm.st = c->stream, dtm.p), (size_t)n * 8, c->stream));
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dgc.st = c->stream, dgc.p), (size_t)n * 8, c->stream));
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dout.st = c->stream, dout.p), (size_t)n * 3 * sizeof(msspe_thal_out), c->stream));
@@ -1037,6 +1039,62 @@ extern "C" int msspe_primer_thermo(msspe_ctx* c, const uint64_t* codes, uint32_t
   return MSSPE_OK;
 }
 
+// The compacted lists of a cross-dimer call stay on the device (ctx-owned, valid until the next such call): what a rank
+// of the row-tiled matrix hands to ONE all_gather on device buffers (msspe_b200/distributed.py) instead of a host round trip.
+extern "C" int msspe_cross_dimer_device(msspe_ctx* c, const uint64_t* codes, uint32_t n, uint32_t oligo_len, const msspe_thal_cond* cond,
+                                        uint32_t row_begin, uint32_t row_end, double dg_limit, uint64_t edge_capacity, uint64_t nostruct_capacity,
+                                        const msspe_dimer_edge** d_edges, uint64_t* n_edges, const uint64_t** d_nostruct, uint64_t* n_nostruct) {
+  if (!c) return MSSPE_ERR_INVALID;
+  if (!cond || !n_edges || !n_nostruct || !d_edges || !d_nostruct || (n && !codes) || row_begin > row_end || row_end > n) { c->set_error("msspe_cross_dimer_device: bad argument"); return MSSPE_ERR_INVALID; }
+  int rc = check_thal_args(c, oligo_len, cond);
+  if (rc) return rc;
+  *n_edges = 0; *n_nostruct = 0; *d_edges = nullptr; *d_nostruct = nullptr;
+  MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  if (c->xd_edges) { cudaFreeAsync(c->xd_edges, st); c->xd_edges = nullptr; }
+  if (c->xd_nostruct) { cudaFreeAsync(c->xd_nostruct, st); c->xd_nostruct = nullptr; }
+  const unsigned long long n_pairs = (unsigned long long)(row_end - row_begin) * n;
+  if (n_pairs == 0) return MSSPE_OK;
+  rc = ensure_tables(c);
+  if (rc) return rc;
+  ThalDeviceTables* hT = new ThalDeviceTables();
+  msspe_thal_expand(&c->raw, hT);
+  ThalDimerConsts K;
+  build_dimer_consts(*hT, *cond, &K);
+  delete hT;
+  DeviceBuf dcodes, dK, dcnt;
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dcodes.st = st, dcodes.p), (size_t)n * 8, st));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dK.st = st, dK.p), sizeof K, st));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dcnt.st = st, dcnt.p), 16, st));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&c->xd_edges, (size_t)(edge_capacity ? edge_capacity : 1) * sizeof(msspe_dimer_edge), st));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&c->xd_nostruct, (size_t)(nostruct_capacity ? nostruct_capacity : 1) * 8, st));
+  MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[6], st));
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dcodes.p, codes, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dK.p, &K, sizeof K, cudaMemcpyHostToDevice, st));
+  MSSPE_CUDA_TRY(c, cudaMemsetAsync(dcnt.p, 0, 16, st));
+  DimerArgs A{};
+  A.a = (const uint64_t*)dcodes.p; A.b = (const uint64_t*)dcodes.p; A.n_pairs = n_pairs; A.n = n; A.row_begin = row_begin; A.matrix = 1;
+  A.k = (int)oligo_len; A.type = MSSPE_THAL_ANY; A.T = c->d_thal; A.C = (const ThalDimerConsts*)dK.p; A.out = nullptr;
+  A.dg_limit = dg_limit; A.edges = c->xd_edges; A.edge_cap = edge_capacity; A.n_edges = (unsigned long long*)dcnt.p;
+  A.nostruct = c->xd_nostruct; A.nostruct_cap = nostruct_capacity; A.n_nostruct = (unsigned long long*)dcnt.p + 1;
+  A.dbg = 0;
+  rc = launch_dimer(c, A, st);
+  if (rc) return rc;
+  unsigned long long cnt[2] = {0, 0};
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(cnt, dcnt.p, 16, cudaMemcpyDeviceToHost, st));
+  MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[7], st));
+  MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+  MSSPE_CUDA_TRY(c, cudaEventElapsedTime(&c->timing.dimer_ms, c->ev[6], c->ev[7]));
+  *n_edges = cnt[0]; *n_nostruct = cnt[1];
+  if (cnt[0] > edge_capacity || cnt[1] > nostruct_capacity) {
+    c->set_error("msspe_cross_dimer_device: %llu edges / %llu structure-less pairs exceed the capacity (%llu / %llu)", cnt[0], cnt[1],
+                 (unsigned long long)edge_capacity, (unsigned long long)nostruct_capacity);
+    return MSSPE_ERR_CAPACITY;
+  }
+  *d_edges = c->xd_edges; *d_nostruct = c->xd_nostruct;
+  return MSSPE_OK;
+}
+
 extern "C" int msspe_cross_dimer(msspe_ctx* c, const uint64_t* codes, uint32_t n, uint32_t oligo_len, const msspe_thal_cond* cond,
                                  uint32_t row_begin, uint32_t row_end, double dg_limit, msspe_dimer_edge* edges,
                                  uint64_t edge_capacity, uint64_t* n_edges, uint64_t* nostruct_pairs, uint64_t nostruct_capacity,
@@ -1059,7 +1117,7 @@ extern "C" int msspe_cross_dimer(msspe_ctx* c, const uint64_t* codes, uint32_t n
   delete hT;
   DeviceBuf dcodes, dK, dedges, dnos, dcnt;
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dcodes.st = c->stream, dcodes.p), (size_t)n * 8, c->stream));
-  MSSPE_CUDA_TRY(c, cudaMallocAsync(&dK.p, sizeof K, c->stream));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dK.st = c->stream, dK.p), sizeof K, c->stream));
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dedges.st = c->stream, dedges.p), (size_t)(edge_capacity ? edge_capacity : 1) * sizeof(msspe_dimer_edge), c->stream));
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dnos.st = c->stream, dnos.p), (size_t)(nostruct_capacity ? nostruct_capacity : 1) * 8, c->stream));
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dcnt.st = c->stream, dcnt.p), 16, c->stream));

@@ -29,6 +29,7 @@ ABI_SYMBOLS = [
     "msspe_set_thal_params", "msspe_primer_thermo", "msspe_thal_pairs", "msspe_thal_pairs_aligned", "msspe_cross_dimer",
     "msspe_fasta_open", "msspe_fasta_close", "msspe_fasta_records", "msspe_fasta_name", "msspe_fasta_bases",
     "msspe_fasta_offsets", "msspe_load_fasta", "msspe_kmer_stats", "msspe_kmer_stats_both", "msspe_coverage_summary", "msspe_vertex_cover", "msspe_shard_begin", "msspe_shard_buffers", "msspe_shard_count", "msspe_shard_firstpos", "msspe_shard_apply",
+    "msspe_get_kernel_profile", "msspe_cross_dimer_device",
 ]
 
 
@@ -85,6 +86,7 @@ class Timing(C.Structure):
                 ("count_kernel_launches", C.c_uint32 * 2)]
 
 
+KERNEL_PROF_DTYPE = np.dtype([("name", "S56"), ("ms", "<f4"), ("launches", "<u4"), ("alg_bytes", "<u8")])
 CANDIDATE_DTYPE = np.dtype([("code", "<u8"), ("freq", "<u4"), ("n_tied", "<u4"), ("tie_score", "<f4"), ("reserved", "<u4")])
 THAL_OUT_DTYPE = np.dtype([("ds", "<f8"), ("dh", "<f8"), ("dg", "<f8"), ("tm", "<f8"), ("no_structure", "<i4"), ("n_bp", "<i4")])
 EDGE_DTYPE = np.dtype([("pair", "<u8"), ("dg", "<f8")])
@@ -153,6 +155,10 @@ def load_library():
     L.msspe_cross_dimer.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(ThalCond), C.c_uint32,
                                     C.c_uint32, C.c_double, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p,
                                     C.c_uint64, C.POINTER(C.c_uint64)]
+    L.msspe_cross_dimer_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(ThalCond), C.c_uint32, C.c_uint32,
+                                           C.c_double, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.msspe_get_kernel_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     L.msspe_kmer_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(FilterCfg), C.c_void_p]
     L.msspe_kmer_stats_both.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(FilterCfg), C.c_void_p, C.c_void_p]
     L.msspe_shard_begin.argtypes = [C.c_void_p, C.c_uint8]
@@ -400,6 +406,36 @@ class Engine:
                                              row_end, dg_limit, edges.ctypes.data, ecap, C.byref(ne), nos.ctypes.data,
                                              ncap, C.byref(nn)))
         return edges[:ne.value], nos[:nn.value]
+
+    def cross_dimer_device(self, codes, cond: ThalCond, dg_limit: float, row_begin=0, row_end=None, oligo_len=None,
+                           edge_capacity=None, nostruct_capacity=None):
+        """msspe_cross_dimer with the compacted lists left on the device: returns (edges, nostruct) as torch tensors viewing
+        ctx-owned buffers (int64 [n, 2] = (pair, dG bits) and int64 [m]); valid until the next cross-dimer call."""
+        import torch
+        codes = np.ascontiguousarray(codes, dtype=np.uint64)
+        n = len(codes)
+        row_end = n if row_end is None else row_end
+        rows = row_end - row_begin
+        ecap = edge_capacity if edge_capacity is not None else max(1024, rows * n)
+        ncap = nostruct_capacity if nostruct_capacity is not None else max(1024, rows * n)
+        pe, pn, ne, nn = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self._check(self.L.msspe_cross_dimer_device(self.h, codes.ctypes.data, n, oligo_len or self.k, C.byref(cond), row_begin, row_end,
+                                                    dg_limit, ecap, ncap, C.byref(pe), C.byref(ne), C.byref(pn), C.byref(nn)))
+        e = (torch.as_tensor(Engine._DevArray(pe.value, 2 * ne.value, "<i8"), device="cuda").view(-1, 2) if ne.value
+             else torch.zeros((0, 2), dtype=torch.int64, device="cuda"))
+        s = (torch.as_tensor(Engine._DevArray(pn.value, nn.value, "<i8"), device="cuda") if nn.value
+             else torch.zeros(0, dtype=torch.int64, device="cuda"))
+        return e, s
+
+    def kernel_profile(self) -> np.ndarray:
+        """Per kernel class since the last reset_timing: launches, algorithmic bytes, device ms (while profiling is on)."""
+        out = np.zeros(16, dtype=KERNEL_PROF_DTYPE)
+        n = C.c_uint32()
+        self._check(self.L.msspe_get_kernel_profile(self.h, out.ctypes.data, 16, C.byref(n)))
+        return out[:n.value]
+
+    def set_profiling(self, on: bool):
+        self._check(self.L.msspe_set_profiling(self.h, 1 if on else 0))
 
     # -- genome-sharded selection: per-rank primitives (msspe_b200.distributed.select_sharded drives them) --
     class _DevArray:

@@ -62,6 +62,40 @@ def cross_dimer_sharded(compute_rows, n: int, edge_dtype, dist=None, device="cpu
     return all_e, all_n
 
 
+def cross_dimer_sharded_tensors(compute_rows_t, n: int, edge_dtype, dist=None, device="cuda"):
+    """Row-tiled all-pairs dimer evaluation with the per-rank lists kept on the device (delta_g.rs:83-153).
+
+    compute_rows_t(row_begin, row_end) -> (edges int64 [m, 2] = (pair, dG bit pattern), nostruct int64 [q]) as tensors on
+    `device`, unsorted (on a GPU rank: Engine.cross_dimer_device, which leaves them in ctx-owned device buffers).
+    Collectives: ONE all_gather_into_tensor of the two counts (the only host read before the end) and ONE
+    all_gather_into_tensor of the packed lists; the merged lists are sorted by pair index on the device and come back
+    with one device-to-host copy each.  Result identical on every rank and to a single-rank run."""
+    import torch
+    world = dist.get_world_size() if (dist is not None and dist.is_initialized()) else 1
+    rank = dist.get_rank() if world > 1 else 0
+    rb, re_ = row_block(n, rank, world)
+    e, q = compute_rows_t(rb, re_)
+    if world > 1:
+        sz = torch.tensor([e.shape[0], q.shape[0]], dtype=torch.int64, device=device)
+        all_sz = torch.empty(2 * world, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(all_sz, sz)
+        all_sz = all_sz.cpu().view(world, 2)
+        cap_e, cap_q = max(1, int(all_sz[:, 0].max())), max(1, int(all_sz[:, 1].max()))
+        buf = torch.empty(2 * cap_e + cap_q, dtype=torch.int64, device=device)
+        buf[:2 * e.shape[0]] = e.reshape(-1)
+        buf[2 * cap_e:2 * cap_e + q.shape[0]] = q
+        out = torch.empty(world * buf.numel(), dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(out, buf)
+        out = out.view(world, -1)
+        e = torch.cat([out[r, :2 * int(all_sz[r, 0])].view(-1, 2) for r in range(world)])
+        q = torch.cat([out[r, 2 * cap_e:2 * cap_e + int(all_sz[r, 1])] for r in range(world)])
+    if e.shape[0]:
+        e = e[torch.argsort(e[:, 0])]
+    q = torch.sort(q).values
+    edges = e.contiguous().cpu().numpy().view(edge_dtype).reshape(-1)
+    return edges, q.cpu().numpy().view(np.uint64)
+
+
 NO_LOCAL_ID = 0xFFFFFFFF
 
 

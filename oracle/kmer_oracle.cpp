@@ -168,8 +168,10 @@ Winner find_most_freq_kmer(const std::vector<Segment>& segs, uint8_t dir, const 
 
 struct Cand { std::string word; size_t freq; size_t n_tied; float score; };
 
-std::vector<Cand> find_candidates_kmers(const Manager& m, uint8_t dir, size_t max_iter, size_t mms, uint64_t* evals) {
-  std::vector<Cand> out; Mapping mp = make_mapping(m.segments);             // main.rs:331-406
+std::vector<Cand> find_candidates_kmers(const Manager& m, uint8_t dir, size_t max_iter, size_t mms, uint64_t* evals,
+                                        const Mapping* prebuilt = nullptr) {
+  std::vector<Cand> out; Mapping own; if (!prebuilt) own = make_mapping(m.segments);   // main.rs:331-406 (:337 builds the mapping)
+  const Mapping& mp = prebuilt ? *prebuilt : own;
   std::unordered_set<uint32_t> ignored; std::unordered_map<uint16_t, size_t> cov;
   for (size_t it = 0; it < max_iter; it++) {
     Winner w = find_most_freq_kmer(m.segments, dir, ignored, mp, cov, evals);
@@ -177,7 +179,7 @@ std::vector<Cand> find_candidates_kmers(const Manager& m, uint8_t dir, size_t ma
     if (w.freq == 1) break;
     out.push_back({w.word, w.freq, w.n_tied, w.score});
     std::unordered_set<uint16_t> newly;
-    for (uint32_t idx : mp[{w.word, dir}]) { ignored.insert(idx); newly.insert(m.segments[idx].partition_no); }
+    for (uint32_t idx : mp.at({w.word, dir})) { ignored.insert(idx); newly.insert(m.segments[idx].partition_no); }
     for (uint16_t p : newly) cov[p] += 1;
     if (w.freq < mms) break;
   }
@@ -579,5 +581,31 @@ uint64_t oracle_select(const char* fasta, uint64_t len, uint64_t W, uint64_t S, 
   }
   return c.size();
 }
+
+// A segment manager kept across calls (bench.py's CPU arm: build once, untimed -- the GPU arm's genomes are resident too --
+// then time find_candidates_kmers alone on the complete alignment for a bounded number of iterations).
+struct KeptManager { Manager m; Mapping mp; };
+void* oracle_manager_create(const char* fasta, uint64_t len, uint64_t W, uint64_t S, uint64_t w, uint64_t k) {
+  KeptManager* km = new KeptManager();
+  km->m.records = to_records(fasta, len);
+  get_segment_manager(km->m, W, S, w, k);
+  km->mp = make_mapping(km->m.segments);      // main.rs:337, once for all later calls (both directions share the map, as in the reference)
+  return km;
+}
+uint64_t oracle_manager_segments(void* h) { return ((KeptManager*)h)->m.segments.size(); }
+uint64_t oracle_manager_select(void* h, int dir, uint64_t max_iter, uint64_t mms, uint64_t* codes, uint32_t* freqs, uint64_t capacity,
+                               uint64_t* evals, double* seconds) {
+  KeptManager& km = *(KeptManager*)h;
+  uint64_t ev = 0; double t0 = now_s();
+  auto c = find_candidates_kmers(km.m, (uint8_t)dir, max_iter, mms, &ev, &km.mp);
+  if (seconds) *seconds = now_s() - t0;
+  if (evals) *evals = ev;
+  for (size_t i = 0; i < c.size() && i < capacity; i++) {
+    uint64_t v = 0; for (char ch : c[i].word) v = (v << 2) | (uint64_t)(strchr("ACGT", ch) - "ACGT");
+    codes[i] = v; freqs[i] = (uint32_t)c[i].freq;
+  }
+  return c.size();
+}
+void oracle_manager_free(void* h) { delete (KeptManager*)h; }
 
 }  // extern "C"

@@ -86,6 +86,14 @@ def lib():
                                                                               C.c_void_p, C.c_uint64,
                                                                               C.POINTER(C.c_uint64),
                                                                               C.POINTER(C.c_double)]
+        L.oracle_manager_create.restype = C.c_void_p
+        L.oracle_manager_create.argtypes = [C.c_char_p, C.c_uint64] + [C.c_uint64] * 4
+        L.oracle_manager_segments.restype = C.c_uint64
+        L.oracle_manager_segments.argtypes = [C.c_void_p]
+        L.oracle_manager_select.restype = C.c_uint64
+        L.oracle_manager_select.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
+                                            C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+        L.oracle_manager_free.argtypes = [C.c_void_p]
         L.oracle_thal_load_embedded()
         _LIB = L
     return _LIB
@@ -181,3 +189,25 @@ def select(fasta: bytes, W, S, w, k, direction, max_iter, mms):
     n = L.oracle_select(fasta, len(fasta), W, S, w, k, direction, max_iter, mms, codes.ctypes.data, freqs.ctypes.data,
                         tied.ctypes.data, scores.ctypes.data, max_iter, C.byref(ev), C.byref(sec))
     return dict(codes=codes[:n], freqs=freqs[:n], n_tied=tied[:n], scores=scores[:n], evals=ev.value, seconds=sec.value)
+
+
+class Manager:
+    """get_segment_manager (main.rs:196-235) built once and kept: repeated find_candidates_kmers calls on the same input."""
+
+    def __init__(self, fasta: bytes, W, S, w, k):
+        self._h = lib().oracle_manager_create(fasta, len(fasta), W, S, w, k)
+        self.n_segments = lib().oracle_manager_segments(self._h)
+
+    def select(self, direction, max_iter, mms):
+        import numpy as np
+        codes = np.zeros(max(1, max_iter), dtype=np.uint64)
+        freqs = np.zeros(max(1, max_iter), dtype=np.uint32)
+        ev, sec = C.c_uint64(), C.c_double()
+        n = lib().oracle_manager_select(self._h, direction, max_iter, mms, codes.ctypes.data, freqs.ctypes.data, max_iter,
+                                        C.byref(ev), C.byref(sec))
+        return dict(codes=codes[:n], freqs=freqs[:n], evals=ev.value, seconds=sec.value)
+
+    def close(self):
+        if self._h:
+            lib().oracle_manager_free(self._h)
+            self._h = None

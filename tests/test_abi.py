@@ -25,7 +25,7 @@ def test_header_symbols_all_exported(lib):
     L = lib.load_library()
     for s in declared:
         assert hasattr(L, s), s
-    assert L.msspe_abi_version() == 1
+    assert L.msspe_abi_version() == 2
 
 
 def test_struct_layouts_match_header(lib, tmp_path):

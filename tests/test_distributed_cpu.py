@@ -49,6 +49,17 @@ def _worker(rank, world, port, words, limit, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     e, nos = D.cross_dimer_sharded(_make_compute(words, limit), len(words), m.EDGE_DTYPE, dist, "cpu")
+    # the device-list path (Engine.cross_dimer_device on a GPU rank): unsorted (pair, dG bits) tensors, one all_gather of the
+    # counts, one of the packed lists, sorted after the merge
+    import torch
+
+    def compute_t(rb, re_):
+        ee, nn = _make_compute(words, limit)(rb, re_)
+        perm = np.random.default_rng(rank).permutation(len(ee))
+        t = torch.from_numpy(np.ascontiguousarray(ee[perm]).view(np.int64).reshape(-1, 2).copy())
+        return t, torch.from_numpy(nn[::-1].copy().view(np.int64))
+    e2, nos2 = D.cross_dimer_sharded_tensors(compute_t, len(words), m.EDGE_DTYPE, dist, "cpu")
+    assert e2.tobytes() == e.tobytes() and nos2.tobytes() == nos.tobytes()
     q.put((rank, e.tobytes(), nos.tobytes()))
     dist.barrier()
     dist.destroy_process_group()

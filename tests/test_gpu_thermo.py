@@ -184,3 +184,87 @@ def test_kmer_stats_both_equals_two_calls():
     a, b = eng.kmer_stats_both(f[:0], r, cfg)
     assert len(a) == 0 and b.tobytes() == eng.kmer_stats(r, cfg).tobytes()
     eng.close()
+
+
+def _vertex_cover_by_degrees(pool, ea, eb):
+    """main.rs:776-798 on integer degrees (the oracle's string version, ko.greedy_vertex_cover, is quadratic in Python and
+    is what this is checked against in tests/test_graph.py): repeatedly the live node with the most live neighbours (a
+    self conflict counts the node itself), ties -> the greatest word; until no live node has a live neighbour."""
+    n = len(pool)
+    nbr = [set() for _ in range(n)]
+    for a, b in zip(ea.tolist(), eb.tolist()):
+        nbr[a].add(b)
+        nbr[b].add(a)
+    alive = np.ones(n, bool)
+    deg = np.array([len(x) for x in nbr], dtype=np.int64)
+    want = np.zeros(n, np.uint8)
+    while True:
+        cand = np.where(alive & (deg > 0))[0]
+        if len(cand) == 0:
+            break
+        mx = deg[cand].max()
+        v = max((int(pool[c]), int(c)) for c in cand[deg[cand] == mx])[1]
+        alive[v] = False
+        want[v] = 1
+        for u in nbr[v]:
+            if alive[u]:
+                deg[u] -= 1
+        deg[v] = 0
+    return want
+
+
+def test_cfg4_pool_20000_primers_vs_oracle(eng, oracle_lib):
+    """BASELINE configs[3] at its stated size: all 4.0e8 ordered pairs of the 20,000-primer pool (delta_g.rs:61-81 builds
+    all N^2 pairs incl. self) through the matrix entry points, lists kept on the device and row-tiled as the multi-GPU path
+    does.  Checked against the CPU oracle's thal on >= 10^4 sampled pairs (edge or not: dG below / above the limit, bit
+    for bit) and on EVERY pair the engine reports as structure-less; the edge list through the host entry point for one
+    row block equals the device lists; then the conflict graph + vertex cover at this size (main.rs:754-798) against the
+    oracle's restatement of the loop on the same edges."""
+    import msspe_b200 as m
+    from msspe_b200 import synth, distributed as D
+    O = oracle_lib
+    n, k = 20_000, 13
+    pool = synth.random_primers(n, k, 4)
+    cond = m.ThalCond(50, 3, 0, 250, 25.0, 30, 0)
+    limit = -9000.0 + 1.0
+    parts_e, parts_n = [], []
+    for r in range(4):          # four row blocks, as four ranks would
+        rb, re_ = D.row_block(n, r, 4)
+        e, s = eng.cross_dimer_device(pool, cond, limit, rb, re_, edge_capacity=(re_ - rb) * n // 50, nostruct_capacity=1 << 16)
+        parts_e.append(e.cpu().numpy().copy())
+        parts_n.append(s.cpu().numpy().copy())
+    e = np.concatenate(parts_e)
+    e = e[np.argsort(e[:, 0], kind="stable")]
+    edges = np.ascontiguousarray(e).view(m.EDGE_DTYPE).reshape(-1)
+    nos = np.sort(np.concatenate(parts_n)).view(np.uint64)
+    assert 0.002 * n * n < len(edges) < 0.02 * n * n and len(np.unique(edges["pair"])) == len(edges)
+    # the host entry point on one row block returns the same (sorted) lists
+    rb, re_ = D.row_block(n, 1, 4)
+    e1, s1 = eng.cross_dimer(pool, cond, limit, rb, rb + 500, edge_capacity=1 << 20, nostruct_capacity=1 << 16)
+    sel = (edges["pair"] >= rb * n) & (edges["pair"] < (rb + 500) * n)
+    assert e1.tobytes() == edges[sel].tobytes()
+    assert s1.tolist() == nos[(nos >= rb * n) & (nos < (rb + 500) * n)].tolist()
+    # oracle on sampled pairs + on every reported edge of a sample + every structure-less pair
+    words = [m.decode_word(c, k) for c in pool]
+    oc = O.ThalCond(50, 3, 0, 250, 25.0, 30, 0)
+    rng = np.random.default_rng(44)
+    edge_dg = dict(zip(edges["pair"].tolist(), edges["dg"].tolist()))
+    nos_set = set(nos.tolist())
+    sample = set(rng.integers(0, n * n, 10_000).tolist()) | set(rng.choice(edges["pair"], 2_000, replace=False).tolist()) | {i * n + i for i in range(0, n, 37)}
+    for p in sample:
+        w = O.thal(words[p // n], words[p % n], 1, oc)
+        if w.no_structure:
+            assert p in nos_set
+        elif w.dg < limit:
+            assert edge_dg.get(p) == w.dg, (p, edge_dg.get(p), w.dg)
+        else:
+            assert p not in edge_dg and p not in nos_set
+    for p in nos.tolist():
+        assert O.thal(words[p // n], words[p % n], 1, oc).no_structure == 1
+    # conflict graph + vertex cover (main.rs:754-798) on these 20,000 nodes: edges with %g -> f32 dG < threshold
+    dg32 = np.array([np.float32(float("%g" % d)) for d in edges["dg"]], dtype=np.float32)
+    conf = edges["pair"][dg32 < np.float32(-9000.0)]
+    ea, eb = (conf // n).astype(np.uint32), (conf % n).astype(np.uint32)
+    deleted = eng.vertex_cover(pool, ea, eb)
+    want = _vertex_cover_by_degrees(pool, ea, eb)
+    assert deleted.tolist() == want.tolist() and want.sum() > 100

@@ -22,6 +22,24 @@ def test_vertex_cover_oracle_hand_cases():
     assert ko.greedy_vertex_cover(list("ab"), []) == set()
 
 
+def test_degree_restatement_used_at_cfg4_size_equals_the_oracle():
+    """tests/test_gpu_thermo.py checks the 20,000-node vertex cover against an integer-degree restatement (the oracle's
+    string version is quadratic in Python); here that restatement is pinned to the oracle on random graphs."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "open-msspe-design_b200"))
+    import msspe_b200 as m
+    from test_gpu_thermo import _vertex_cover_by_degrees
+    for seed, (n, pe, ps) in enumerate([(1, 0.0, 1.0), (2, 1.0, 0.0), (40, 0.05, 0.1), (120, 0.02, 0.05), (33, 0.5, 0.5), (200, 0.004, 0.0)]):
+        rng = np.random.default_rng(seed)
+        codes, ea, eb = _random_graph(rng, n, 13, pe, ps)
+        words = [m.decode_word(int(c), 13) for c in codes]
+        want = ko.greedy_vertex_cover(words, [(words[x], words[y]) for x, y in zip(ea.tolist(), eb.tolist())])
+        got = _vertex_cover_by_degrees(codes, ea, eb)
+        assert {words[i] for i in np.nonzero(got)[0]} == want
+
+
 # ---------------------------------------------------------------- device (GPU)
 def _random_graph(rng, n, k, p_edge, p_self):
     from msspe_b200 import synth
