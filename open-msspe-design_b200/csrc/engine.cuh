@@ -160,6 +160,8 @@ int msspe_radix_sort_pairs(msspe_ctx* ctx, uint64_t** key_a, uint32_t** val_a, u
                            uint32_t key_bits, cudaStream_t st);
 
 // ---- stages ----
+bool msspe_build_fast_applicable(const msspe_ctx* ctx);   // kmer_build_fast.cu
+int msspe_build_fast(msspe_ctx* ctx);
 int msspe_free_index(msspe_ctx* ctx);
 int msspe_select_prepare_static(msspe_ctx* ctx, int dir, cudaStream_t st);  // select.cu: tile tables
 int msspe_select_prepare_stream(msspe_ctx* ctx, int dir, cudaStream_t st);  // select.cu: scoring stream (lazy)

@@ -449,6 +449,12 @@ extern "C" int msspe_build_index(msspe_ctx* c) {
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&c->d_seg_part, (G ? G : 1) * sizeof(uint16_t), c->stream));
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&c->d_seg_rec, (G ? G : 1) * sizeof(uint32_t), c->stream));
   c->timing.encode_ms = c->timing.index_ms = 0.f;
+  if (msspe_build_fast_applicable(c)) {   // words of <= 16 bases: code + record index in one u64 (kmer_build_fast.cu)
+    int rc = msspe_build_fast(c);
+    if (rc) { msspe_free_index(c); return rc; }
+    c->built = true;
+    return MSSPE_OK;
+  }
   for (int d = 0; d < 2; d++) {
     int rc = build_direction(c, d, &c->timing.encode_ms, &c->timing.index_ms);
     if (rc) { msspe_free_index(c); return rc; }
