@@ -210,6 +210,10 @@ static int plan_segments(msspe_ctx* c, const uint64_t* offsets, uint32_t n) {
     if (offsets[r + 1] < offsets[r]) { c->set_error("offsets not monotone at record %u", r); return MSSPE_ERR_INVALID; }
     uint64_t L = offsets[r + 1] - offsets[r];
     uint64_t P = L >= W ? (L - W) / S + 1 : 0;
+    if (P > 65536) {  // Segment.partition_no is `j as u16` (main.rs:227): beyond 65,536 windows the reference wraps silently
+      c->set_error("record %u has %llu partitions; partition_no is u16 in the reference (main.rs:84,227) and would wrap: use a larger --overlap-size", r, (unsigned long long)P);
+      return MSSPE_ERR_INVALID;
+    }
     c->h_seg_base[r] = g;
     g += P;
     if (P > maxp) maxp = P;

@@ -134,7 +134,9 @@ struct msspe_ctx {
   // thermodynamic tables
   msspe_thal_raw_params raw{};
   bool raw_set = false;
-  struct ThalDeviceTables* d_thal = nullptr;  // device copy of static tables
+  struct ThalDeviceTables* d_thal = nullptr;  // device copy of static tables (ntthal stand-ins: msspe_set_thal_params applies)
+  struct ThalDeviceTables* d_thal_p3 = nullptr;  // Primer3's compiled-in tables (primer3_core stand-ins), never overridden
+  msspe_thal_raw_params* raw_p3 = nullptr;
   msspe_dimer_edge* xd_edges = nullptr;       // msspe_cross_dimer_device: lists of the last call (ctx-owned)
   uint64_t* xd_nostruct = nullptr;
   // pinned staging

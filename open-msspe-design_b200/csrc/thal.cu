@@ -824,6 +824,21 @@ int ensure_tables(msspe_ctx* c) {
   return msspe_thal_upload_tables(c);
 }
 
+// primer3_core is started without any parameter path (primer.rs:125-140, 151-160): its thal tables and oligotm's
+// SantaLucia table are the ones compiled into Primer3.  So the primer3_core stand-ins (msspe_primer_thermo, msspe_kmer_stats*)
+// always use the embedded tables; msspe_set_thal_params / `-path` (delta_g.rs:90) reaches only the ntthal stand-ins.
+int ensure_p3_tables(msspe_ctx* c) {
+  if (c->d_thal_p3) return MSSPE_OK;
+  if (!c->raw_p3) { c->raw_p3 = new msspe_thal_raw_params(); msspe_thal_params_default(c->raw_p3); }
+  ThalDeviceTables* h = new ThalDeviceTables();
+  msspe_thal_expand(c->raw_p3, h);
+  cudaError_t e = cudaMallocAsync(&c->d_thal_p3, sizeof(ThalDeviceTables), c->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(c->d_thal_p3, h, sizeof(ThalDeviceTables), cudaMemcpyHostToDevice);
+  delete h;
+  if (e != cudaSuccess) { c->set_error("upload Primer3 default tables: %s", cudaGetErrorString(e)); return MSSPE_ERR_CUDA; }
+  return MSSPE_OK;
+}
+
 struct DeviceBuf {  // stream-ordered scratch, returned to the pool when the call ends
   void* p = nullptr;
   cudaStream_t st = nullptr;
@@ -863,15 +878,15 @@ int launch_dimer(msspe_ctx* c, DimerArgs& A, cudaStream_t st) {
 // Hairpin launch: the per-thread DP scratch in shared memory (as many threads per block as fit) when that keeps the
 // whole batch in one wave of blocks, else the global scratch `work` with 64-thread blocks.
 int launch_mono(msspe_ctx* c, const uint64_t* d_codes, uint32_t n, int k, const ThalDimerConsts& K, MonoWork* work, msspe_thal_out* out,
-                cudaStream_t st) {
+                cudaStream_t st, const ThalDeviceTables* T) {
   const int per_block = (int)((c->smem_optin - 1024) / sizeof(MonoWork));
   const bool smem_ok = per_block >= 1 && !getenv("MSSPE_MONO_GLOBAL") && (uint64_t)n <= (uint64_t)per_block * (uint64_t)c->sm_count;  // one wave (measured: 0.49 vs 0.65 ms at 600, slower beyond one wave)
   if (smem_ok) {
     const size_t smem = (size_t)per_block * sizeof(MonoWork);
     MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(thal_mono_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    thal_mono_kernel<<<(n + per_block - 1) / per_block, per_block, smem, st>>>(d_codes, n, k, c->d_thal, K.saltCorr, K.t_user_K, K.maxLoop, nullptr, out);
+    thal_mono_kernel<<<(n + per_block - 1) / per_block, per_block, smem, st>>>(d_codes, n, k, T, K.saltCorr, K.t_user_K, K.maxLoop, nullptr, out);
   } else {
-    thal_mono_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_codes, n, k, c->d_thal, K.saltCorr, K.t_user_K, K.maxLoop, work, out);
+    thal_mono_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_codes, n, k, T, K.saltCorr, K.t_user_K, K.maxLoop, work, out);
   }
   c->timing.kernel_launches++;
   MSSPE_CUDA_TRY(c, cudaGetLastError());
@@ -902,6 +917,9 @@ int msspe_thal_upload_tables(msspe_ctx* c) {
 void msspe_thal_free_tables(msspe_ctx* c) {
   if (c->d_thal) msspe_dev_free(c, c->d_thal);
   c->d_thal = nullptr;
+  if (c->d_thal_p3) msspe_dev_free(c, c->d_thal_p3);
+  c->d_thal_p3 = nullptr;
+  delete c->raw_p3; c->raw_p3 = nullptr;
 }
 
 extern "C" int msspe_set_thal_params(msspe_ctx* c, const msspe_thal_raw_params* p) {
@@ -941,7 +959,7 @@ static int thal_pairs_impl(msspe_ctx* c, const uint64_t* a, const uint64_t* b, u
   MSSPE_CUDA_TRY(c, cudaMemcpyAsync(da.p, a, n_pairs * 8, cudaMemcpyHostToDevice, st));
   if (type == MSSPE_THAL_HAIRPIN) {
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dwork.st = c->stream, dwork.p), n_pairs * sizeof(MonoWork), c->stream));
-    rc = launch_mono(c, (const uint64_t*)da.p, (uint32_t)n_pairs, (int)oligo_len, K, (MonoWork*)dwork.p, (msspe_thal_out*)dout.p, st);
+    rc = launch_mono(c, (const uint64_t*)da.p, (uint32_t)n_pairs, (int)oligo_len, K, (MonoWork*)dwork.p, (msspe_thal_out*)dout.p, st, c->d_thal);
     if (rc) return rc;
   } else {
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&(db.st = c->stream, db.p), n_pairs * 8, c->stream));
@@ -979,13 +997,13 @@ extern "C" int msspe_primer_thermo(msspe_ctx* c, const uint64_t* codes, uint32_t
   if (rc) return rc;
   if (n == 0) return MSSPE_OK;
   MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
-  rc = ensure_tables(c);
+  rc = ensure_p3_tables(c);
   if (rc) return rc;
   cudaStream_t st = c->stream;
   // Primer3 defaults (primer.rs:125-140 sends no salt tags): mv 50, dv 1.5, dNTP 0.6, DNA 50 nM; thal at 37 C, maxLoop 30
   const msspe_thal_cond p3{50.0, 1.5, 0.6, 50.0, 37.0, 30, 0};
   ThalDeviceTables* hT = new ThalDeviceTables();
-  msspe_thal_expand(&c->raw, hT);
+  msspe_thal_expand(c->raw_p3, hT);
   ThalDimerConsts K;
   build_dimer_consts(*hT, p3, &K);
   delete hT;
@@ -1009,18 +1027,18 @@ extern "C" int msspe_primer_thermo(msspe_ctx* c, const uint64_t* codes, uint32_t
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[6], st));
   MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dcodes.p, codes, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dK.p, &K, sizeof K, cudaMemcpyHostToDevice, st));
-  oligotm_kernel<<<(n + 127) / 128, 128, 0, st>>>((const uint64_t*)dcodes.p, n, (int)oligo_len, c->d_thal, OK, (double*)dtm.p, (double*)dgc.p);
+  oligotm_kernel<<<(n + 127) / 128, 128, 0, st>>>((const uint64_t*)dcodes.p, n, (int)oligo_len, c->d_thal_p3, OK, (double*)dtm.p, (double*)dgc.p);
   c->timing.kernel_launches++;
   msspe_thal_out* o3 = (msspe_thal_out*)dout.p;
   for (int pass = 0; pass < 2; pass++) {  // SELF_ANY_TH, SELF_END_TH: thal(s, s)
     DimerArgs A{};
     A.a = (const uint64_t*)dcodes.p; A.b = (const uint64_t*)dcodes.p; A.n_pairs = n; A.matrix = 0; A.k = (int)oligo_len;
     A.type = pass == 0 ? MSSPE_THAL_ANY : MSSPE_THAL_END1;
-    A.T = c->d_thal; A.C = (const ThalDimerConsts*)dK.p; A.out = o3 + (size_t)pass * n;
+    A.T = c->d_thal_p3; A.C = (const ThalDimerConsts*)dK.p; A.out = o3 + (size_t)pass * n;
     rc = launch_dimer(c, A, st);
     if (rc) return rc;
   }
-  rc = launch_mono(c, (const uint64_t*)dcodes.p, n, (int)oligo_len, K, (MonoWork*)dwork.p, o3 + (size_t)2 * n, st);
+  rc = launch_mono(c, (const uint64_t*)dcodes.p, n, (int)oligo_len, K, (MonoWork*)dwork.p, o3 + (size_t)2 * n, st, c->d_thal_p3);
   if (rc) return rc;
   MSSPE_CUDA_TRY(c, cudaGetLastError());
   std::vector<msspe_thal_out> h((size_t)n * 3);

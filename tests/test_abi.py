@@ -71,8 +71,9 @@ def test_product_never_references_the_oracle():
                 assert "oracle" not in txt.lower() or fn == "thal.cu" and "oracle" not in txt, (dp, fn)
 
 
-def test_embedded_params_equal_a_directory_load(lib, tmp_path):
-    """msspe_thal_params_from_dir on files regenerated from the embedded tables must round-trip."""
+def write_param_dir(lib, path, stack_ds_shift=0.0):
+    """The embedded tables written out as a primer3_config directory (stack.ds optionally shifted: a directory that
+    differs from Primer3's compiled-in tables).  Returns the raw embedded block."""
     L = lib.load_library()
     a = C.create_string_buffer(lib.RAW_PARAMS_BYTES)
     assert L.msspe_thal_params_default(a) == 0
@@ -83,10 +84,13 @@ def test_embedded_params_equal_a_directory_load(lib, tmp_path):
              ("tstack2.ds", 256), ("tstack2.dh", 256)]
     pos = 0
     fmt = lambda v: "inf" if np.isinf(v) else repr(float(v))
+    os.makedirs(str(path), exist_ok=True)
     for fn, n in names:
-        vals = d[pos:pos + n]
+        vals = d[pos:pos + n].copy()
         pos += n
-        with open(tmp_path / fn, "w") as f:
+        if fn == "stack.ds" and stack_ds_shift:
+            vals[np.isfinite(vals)] += stack_ds_shift
+        with open(os.path.join(str(path), fn), "w") as f:
             if fn.startswith("loops"):
                 for r in range(30):
                     f.write("%d\t%s\n" % (r + 1, "\t".join(fmt(v) for v in vals[3 * r:3 * r + 3])))
@@ -99,10 +103,17 @@ def test_embedded_params_equal_a_directory_load(lib, tmp_path):
             n = int.from_bytes(raw[off:off + 4], "little")
             seqs = raw[off + 4: off + 4 + cap * 8]
             vals = np.frombuffer(raw[off + 8 + cap * 8: off + 8 + cap * 16], dtype=np.float64)
-            with open(tmp_path / ("%s.%s" % (base, ext)), "w") as f:
+            with open(os.path.join(str(path), "%s.%s" % (base, ext)), "w") as f:
                 for i in range(n):
                     f.write("%s\t%s\n" % (seqs[8 * i:8 * i + ln].decode(), fmt(vals[i])))
             off += 8 + cap * 16
+    return a
+
+
+def test_embedded_params_equal_a_directory_load(lib, tmp_path):
+    """msspe_thal_params_from_dir on files regenerated from the embedded tables must round-trip."""
+    L = lib.load_library()
+    a = write_param_dir(lib, tmp_path)
     b = C.create_string_buffer(lib.RAW_PARAMS_BYTES)
     err = C.create_string_buffer(256)
     assert L.msspe_thal_params_from_dir(str(tmp_path).encode(), b, err, 256) == 0, err.value

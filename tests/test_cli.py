@@ -1,6 +1,7 @@
 """The drop-in process boundary: `od-msspe` flags / env (config.rs:11-148), FASTA in, CSV + stdout report out.
 CPU tests cover the argument surface; GPU tests compare the produced bytes with the oracle pipeline."""
 import os
+import sys
 import subprocess
 
 import pytest
@@ -102,14 +103,49 @@ def test_cli_env_fallbacks_and_param_dir(exe, zika_fasta, oracle_lib, tmp_path):
 
 
 @pytest.mark.gpu
+def test_cli_param_dir_reaches_ntthal_only(exe, zika_fasta, oracle_lib, tmp_path):
+    """delta_g.rs:90-108 gives `-path <cwd>/primer3_config/` to ntthal only; primer3_core is started without a parameter
+    path (primer.rs:125-160) and uses Primer3's compiled-in tables.  So a ./primer3_config/ that DIFFERS from the built-in
+    tables must not move Tm / GC / SELF_*_TH / HAIRPIN_TH, the filter verdicts or (with cross-dimers off) a byte of the
+    CSV; with cross-dimers on it does change the dG edges."""
+    import msspe_b200 as m
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_abi import write_param_dir
+    fa = tmp_path / "in.fa"
+    fa.write_bytes(zika_fasta)
+    write_param_dir(m, tmp_path / "primer3_config", stack_ds_shift=-3.0)
+    out = tmp_path / "o.csv"
+    r = run(exe, "-i", str(fa), "-o", str(out), "--do-align=false", "--check-cross-dimers=false", cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    want = oracle_lib.run_pipeline(zika_fasta, oracle_lib.default_config(check_cross_dimers=0))   # embedded (= Primer3 built-in) tables
+    assert out.read_text() == want.csv and r.stdout == want.report
+    want.close()
+    # the library call behind it: primer thermodynamics are unchanged by msspe_set_thal_params, pair dG is not
+    eng = m.Engine(13, 500, 250, 50)
+    codes = [m.encode_word(w) for w in ("AGCCCGTGTAAAC", "GCGCGCGCATATA", "ACGTACGTACGTA", "GGGGCCCCAAATT")]
+    cond = m.ThalCond(50, 3, 0, 250, 25.0, 30, 0)
+    t0 = eng.primer_thermo(codes)
+    p0 = eng.thal_pairs(codes, codes[::-1], m.THAL_ANY, cond)
+    eng.set_thal_params_dir(str(tmp_path / "primer3_config"))
+    t1 = eng.primer_thermo(codes)
+    p1 = eng.thal_pairs(codes, codes[::-1], m.THAL_ANY, cond)
+    for key in ("tm", "gc", "self_any", "self_end", "hairpin"):
+        assert t0[key].tobytes() == t1[key].tobytes(), key
+    assert p0["dg"].tobytes() != p1["dg"].tobytes()
+    eng.close()
+
+
+@pytest.mark.gpu
 def test_cli_golden_files(exe, zika_fasta, tmp_path):
+    """tests/golden/snapshot_*: SNAPSHOTS written by this repo's own oracle pipeline (not reference output -- the Rust
+    binary and its Mach-O Primer3 cannot run here); they catch unintended drift of either side, nothing more."""
     fa = tmp_path / "in.fa"
     fa.write_bytes(zika_fasta)
     out = tmp_path / "o.csv"
     r = run(exe, "-i", str(fa), "-o", str(out), "--do-align=false")
     g = os.path.join(ROOT, "tests", "golden")
-    assert out.read_text() == open(os.path.join(g, "zika96_default.csv")).read()
-    assert r.stdout == open(os.path.join(g, "zika96_default.report.txt")).read()
+    assert out.read_text() == open(os.path.join(g, "snapshot_zika96_default.csv")).read()
+    assert r.stdout == open(os.path.join(g, "snapshot_zika96_default.report.txt")).read()
 
 
 @pytest.mark.gpu

@@ -100,3 +100,41 @@ def test_load_fasta_equals_load_genomes(tmp_path, zika_fasta):
     with pytest.raises(m.MsspeError):
         e2.load_fasta(str(tmp_path / "nope.fa"))
     e1.close(); e2.close(); f.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pinned", ["0", "1"])
+def test_load_fasta_pageable_and_pinned_paths(tmp_path, pinned, monkeypatch):
+    """Inputs above 256 MB are parsed into a PAGEABLE buffer whose 32 MB chunks go to the device while the next chunk is
+    normalised (fasta.cu host_alloc); MSSPE_FASTA_PINNED forces either path at any size.  A 100 MB multi-chunk file with
+    lower case, U, CR/LF and ragged line lengths through both paths: names, offsets, device-side k-mers and the greedy
+    winners must equal the oracle's to_records + msspe_load_genomes."""
+    import msspe_b200 as m
+    monkeypatch.setenv("MSSPE_FASTA_PINNED", pinned)
+    rng = np.random.default_rng(8)
+    anc = rng.integers(0, 4, 50_000)
+    lines = []
+    for i in range(2000):
+        s = anc.copy()
+        mut = rng.random(len(s)) < 0.01
+        s[mut] = rng.integers(0, 4, int(mut.sum()))
+        seq = "".join(np.array(list("ACGU" if i % 3 == 0 else "acgt" if i % 3 == 1 else "ACGT"))[s])
+        wrap = 60 + (i % 7) * 13
+        body = ("\r\n" if i % 5 == 0 else "\n").join(seq[j:j + wrap] for j in range(0, len(seq), wrap))
+        lines.append(">rec%d some description\n%s\n" % (i, body))
+    data = "".join(lines).encode()
+    assert len(data) > 100 << 20
+    p = tmp_path / "big.fa"
+    p.write_bytes(data)
+    recs = ko.to_records(data)
+    bases, offs = m.pack_records([r.sequence.encode() for r in recs])
+    e1 = m.Engine(13, 500, 250, 50); e1.load_genomes(bases, offs); e1.build_index()
+    e2 = m.Engine(13, 500, 250, 50); f = e2.load_fasta(str(p), 0); e2.build_index()
+    assert f.names == [r.name for r in recs] and np.array_equal(f.offsets, offs) and np.array_equal(f.bases, bases)
+    assert e1.segment_info() == e2.segment_info()
+    for d in (0, 1):
+        c1, o1, p1 = e1.index(d)
+        c2, o2, p2 = e2.index(d)
+        assert np.array_equal(c1, c2) and np.array_equal(o1, o2) and np.array_equal(p1, p2)
+        assert e1.select(d, 30, 10, m.SELECT_AUTO).tobytes() == e2.select(d, 30, 10, m.SELECT_AUTO).tobytes()
+    e1.close(); e2.close(); f.close()

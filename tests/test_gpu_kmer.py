@@ -103,7 +103,7 @@ def test_zika_inverted_index_matches_reference_mapping(zika_engine):
 def test_zika_greedy_selection_bit_exact(zika_engine, zika_fasta, oracle_lib, mode):
     eng, _ = zika_engine
     _check_select(eng, oracle_lib, zika_fasta, 500, 250, 50, 13, 1000, 2, mode)
-    with open(os.path.join(GOLDEN, "zika96_candidates.json")) as f:
+    with open(os.path.join(GOLDEN, "snapshot_zika96_candidates.json")) as f:
         gold = json.load(f)
     fwd, rev = eng.select_both(1000, 2, mode)
     assert [[ko.decode(int(c), 13), int(f)] for c, f in zip(fwd["code"], fwd["freq"])] == gold["fwd"]
@@ -215,6 +215,14 @@ def test_empty_and_degenerate_inputs(oracle_lib):
     with pytest.raises(m.MsspeError):
         eng.load_genomes(np.zeros(0, np.uint8), np.zeros(1, np.uint64))  # "No sequences found", main.rs:652-654
     eng.close()
+    # Segment.partition_no is `j as u16` (main.rs:84,227): more than 65,536 windows per record would wrap in the reference;
+    # the engine refuses instead of mixing wrapped (K1) and unwrapped (tie score) partition numbers
+    e2 = m.Engine(1, 2, 1, 1)
+    with pytest.raises(m.MsspeError) as ei:
+        e2.load_genomes(np.full(70_000, ord("A"), np.uint8), np.array([0, 70_000], np.uint64))
+    assert ei.value.code == m.ERR_INVALID
+    e2.load_genomes(np.full(65_537, ord("A"), np.uint8), np.array([0, 65_537], np.uint64))   # exactly 65,536 windows: accepted
+    e2.close()
 
 
 def test_cfg1_shape_full_size(oracle_lib):

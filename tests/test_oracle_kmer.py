@@ -92,7 +92,7 @@ def test_zika_greedy_matches_survey_golden(zika_fasta):
                        ("AGAGAGATCATAC", 93)]
     assert rev[:5] == [("CCACCGCCATCTG", 94), ("ACTGCTGTTGTCA", 93), ("AATGGCATCCCTT", 92), ("ATTGTGTCAATGT", 92),
                        ("CCACCTCCATACA", 92)]
-    with open(os.path.join(GOLDEN, "zika96_candidates.json")) as f:
+    with open(os.path.join(GOLDEN, "snapshot_zika96_candidates.json")) as f:
         gold = json.load(f)
     assert [list(x) for x in fwd] == gold["fwd"] and [list(x) for x in rev] == gold["rev"]
 
@@ -148,8 +148,8 @@ def test_format_and_parse_ntthal_text_semantics(oracle_lib, zika_fasta):
     """Whole-pipeline regression on the Zika fixture (oracle-derived golden, NOT a reference output)."""
     O = oracle_lib
     r = O.run_pipeline(zika_fasta, O.default_config())
-    with open(os.path.join(GOLDEN, "zika96_default.csv")) as f:
+    with open(os.path.join(GOLDEN, "snapshot_zika96_default.csv")) as f:
         assert r.csv == f.read()
-    with open(os.path.join(GOLDEN, "zika96_default.report.txt")) as f:
+    with open(os.path.join(GOLDEN, "snapshot_zika96_default.report.txt")) as f:
         assert r.report == f.read()
     r.close()
