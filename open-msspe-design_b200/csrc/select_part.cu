@@ -47,7 +47,7 @@ constexpr int NEWCAP = 2048;      // newly covered segments handled per batch of
 constexpr int VER_T = 256;        // threads of the verify kernel
 constexpr int TP_SLOTS = 64;      // distinct partitions of a multi-partition list handled by the parallel score path
 
-struct PEntry { uint32_t freq, cid, tied, pad; unsigned long long live_before; };
+struct PEntry { uint32_t freq, cid, tied, pad; unsigned long long live_before; unsigned long long code; };   // code = the word: rank-independent tie-break
 
 struct PartCtl {
   uint32_t t_final, done, n_out, iterations;
@@ -66,6 +66,7 @@ struct PartDir {
   uint32_t* pfreq; uint32_t* token; unsigned long long* ulive; PEntry* entries; uint32_t* pos; uint32_t* rfin; uint32_t* ulen;
   uint32_t* status; uint32_t* ext_cov; uint32_t* elist; uint32_t* order; uint32_t* tied; unsigned long long* tot_live; uint32_t* mt;
   uint32_t* ub; uint32_t* stage; uint4* viol; uint32_t* touch;
+  uint32_t* win_freq; uint32_t* win_cov; unsigned long long* win_code;   // the merged winner of every window position (plan kernel)
   PartCtl* ctl; msspe_candidate* out;
 };
 
@@ -73,6 +74,7 @@ struct PartArgs {
   PartDir d[2];
   int ndirs;
   uint32_t U, CAP, slots, max_iter, mms, uniform_parts, nsteps;
+  uint32_t max_ahead;   // a unit keeps at most this many not-yet-final entries (the multi-GPU exchange has fixed-size records)
   const uint16_t* seg_part;
 };
 
@@ -223,7 +225,8 @@ __global__ void __launch_bounds__(EXT_T) part_extend_kernel(PartArgs A) {
     for (int rr = 0; rr < C; rr++) live -= s_ex[par][rr].delta;
     par ^= 1; delta = 0;
   }
-  for (uint32_t step = 0; step < A.nsteps && !finished; step++) {
+  const uint32_t rf0 = D.rfin[u];
+  for (uint32_t step = 0; step < A.nsteps && !finished && len - rf0 < A.max_ahead; step++) {
     if (len >= A.CAP) { finished = true; break; }  // entry number CAP = max_iterations can never be among the first max_iterations
     // arg-max over the unit's k-mers: (live count, then smaller word = smaller index), and how many share the count
     unsigned long long bk = 0ull; uint32_t bc = 0u;
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(EXT_T) part_extend_kernel(PartArgs A) {
     const uint32_t jwin = o0 + (0xFFFFFFFFu - (uint32_t)wk);
     const uint32_t cid = D.ucodes[jwin];
     const uint32_t slot = slot0 + len;
-    if (rank == 0 && tid == 0) { PEntry e; e.freq = fmax; e.cid = cid; e.tied = wc; e.pad = 0u; e.live_before = (unsigned long long)live; D.entries[slot] = e; }
+    if (rank == 0 && tid == 0) { PEntry e; e.freq = fmax; e.cid = cid; e.tied = wc; e.pad = 0u; e.live_before = (unsigned long long)live; e.code = D.codes[cid]; D.entries[slot] = e; }
     const uint32_t pb = D.post_off[cid], pe = D.post_off[cid + 1];
     const uint32_t share = (pe - pb + C - 1) / C;      // an equal share of the winner's postings for every CTA of the cluster
     const uint32_t mb = min(pe, pb + rank * share), me = min(pe, mb + share);
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(1024) part_gather_kernel(PartArgs A) {
 }
 
 // key order of the merge: higher frequency, then lower partition_coverage (= higher 1/(cov+1), main.rs:320-324), then smaller word
-__device__ __forceinline__ bool better(uint32_t fa, uint32_t ca, uint32_t ia, uint32_t fb, uint32_t cb, uint32_t ib) {
+__device__ __forceinline__ bool better(uint32_t fa, uint32_t ca, unsigned long long ia, uint32_t fb, uint32_t cb, unsigned long long ib) {
   return fa > fb || (fa == fb && (ca < cb || (ca == cb && ia < ib)));
 }
 
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(256) part_merge_kernel(PartArgs A) {
         while (n > 0) {
           const uint32_t half = n >> 1, mid = lo + half;
           const PEntry* e = D.entries + (unsigned long long)q * A.CAP + mid;
-          if (better(e->freq, mid + ec, e->cid, ex.freq, covx, ex.cid)) { lo = mid + 1; n -= half + 1; } else n = half;
+          if (better(e->freq, mid + ec, e->code, ex.freq, covx, ex.code)) { lo = mid + 1; n -= half + 1; } else n = half;
         }
         idx = lo;
       }
@@ -434,6 +437,7 @@ __global__ void __launch_bounds__(1024) part_plan_kernel(PartArgs A) {
   for (uint32_t i = tid; i < E && i < room; i += 1024)
     if (D.entries[D.order[i]].freq < A.mms) first = min(first, i);
   first = block_min_u32<1024>(first, sh);
+  __shared__ uint32_t s_V;
   if (tid == 0) {
     uint32_t cutbound = A.max_iter, terminal = 0u;
     if (first != T_INF) cutbound = min(cutbound, t_final + first + 1u);
@@ -448,7 +452,15 @@ __global__ void __launch_bounds__(1024) part_plan_kernel(PartArgs A) {
     if (do_term) fmin = 2u;
     else if (V > t_final) fmin = D.entries[D.order[V - 1u - t_final]].freq;
     C->clipped = clipped ? 1u : 0u;
+    s_V = V;
     C->H = H; C->cutbound = cutbound; C->V = V; C->terminal = terminal; C->do_terminal = do_term; C->fmin = fmin; C->t_hi = V + do_term;
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < s_V - t_final; i += 1024) {   // what the verify kernels compare the multi-partition lists with
+    const uint32_t slot = D.order[i];
+    const uint32_t ux = slot / A.CAP, rx = slot - ux * A.CAP;
+    const PEntry* e = D.entries + slot;
+    D.win_freq[i] = e->freq; D.win_cov[i] = rx + D.ext_cov[ux]; D.win_code[i] = e->code;
   }
 }
 
@@ -542,7 +554,7 @@ __global__ void __launch_bounds__(VER_T) part_verify_kernel(PartArgs A) {
   const uint32_t n_stage = C->n_stage, t_final = C->t_final, V = C->V, t_hi = C->t_hi, fmin = C->fmin;
   const uint32_t W = t_hi - t_final;
   if (blockIdx.x >= n_stage) return;
-  for (uint32_t i = tid; i < V - t_final; i += VER_T) wf[i] = D.entries[D.order[i]].freq;
+  for (uint32_t i = tid; i < V - t_final; i += VER_T) wf[i] = D.win_freq[i];
   __syncthreads();
   for (uint32_t si = blockIdx.x; si < n_stage; si += gridDim.x) {
     const uint32_t m = D.stage[si];
@@ -597,10 +609,8 @@ __global__ void __launch_bounds__(VER_T) part_verify_kernel(PartArgs A) {
       const uint32_t i = nx, t = t_final + nx;
       if (tid == 0) atomicAdd(D.mt + i, 1u);
       const float sc = multi_score(A, D, a, b, t, tp, tfirst, &s_flag, seen, &s_score);
-      const uint32_t slot = D.order[i];
-      const uint32_t ux = slot / A.CAP, rx = slot - ux * A.CAP;
-      const float wsc = __fdiv_rn(1.0f, __fadd_rn((float)(rx + D.ext_cov[ux]), 1.0f));
-      if (sc > wsc || (sc == wsc && c < D.entries[slot].cid)) { tv = t; tv_cnt = wf[i]; tv_score = sc; break; }
+      const float wsc = __fdiv_rn(1.0f, __fadd_rn((float)D.win_cov[i], 1.0f));
+      if (sc > wsc || (sc == wsc && D.codes[c] < D.win_code[i])) { tv = t; tv_cnt = wf[i]; tv_score = sc; break; }
       cur = nx + 1u;
     }
     if (tv == T_INF && fs != T_INF) {
@@ -634,7 +644,7 @@ __global__ void __launch_bounds__(1024) part_finalize_kernel(PartArgs A) {
     const PEntry e = D.entries[slot];
     const uint32_t ux = slot / A.CAP, rx = slot - ux * A.CAP;
     msspe_candidate o;
-    o.code = D.codes[e.cid]; o.freq = e.freq; o.n_tied = D.tied[i] + D.mt[i];
+    o.code = e.code; o.freq = e.freq; o.n_tied = D.tied[i] + D.mt[i];
     o.tie_score = __fdiv_rn(1.0f, __fadd_rn((float)(rx + D.ext_cov[ux]), 1.0f)); o.reserved = 0u;
     D.out[t_final + i] = o;
     ev += D.tot_live[i];
@@ -884,7 +894,7 @@ int msspe_select_partitioned(msspe_ctx* c, int ndirs, const int* dirs, uint32_t 
   PartArgs A{};
   A.ndirs = ndirs; A.U = U; A.CAP = (uint32_t)CAP; A.slots = c->slots; A.max_iter = max_iter; A.mms = mms;
   A.uniform_parts = (c->uniform_parts && c->uniform_parts <= 65536u) ? c->uniform_parts : 0u;
-  A.seg_part = c->d_seg_part;
+  A.seg_part = c->d_seg_part; A.max_ahead = 0xFFFFFFFFu;
   std::vector<void*> scratch;
   auto alloc = [&](void** p, uint64_t bytes, int fill) -> int {
     MSSPE_CUDA_TRY(c, cudaMallocAsync(p, bytes ? bytes : 4, st));
@@ -927,6 +937,9 @@ int msspe_select_partitioned(msspe_ctx* c, int ndirs, const int* dirs, uint32_t 
     PV_ALLOC(stage, ((uint64_t)P.n_multi + 1) * 4, -1);
     PV_ALLOC(viol, ((uint64_t)P.n_multi + 1) * 16, -1);
     PV_ALLOC(touch, (uint64_t)U * 4, 0);
+    PV_ALLOC(win_freq, ((uint64_t)max_iter + 2) * 4, 0);
+    PV_ALLOC(win_cov, ((uint64_t)max_iter + 2) * 4, 0);
+    PV_ALLOC(win_code, ((uint64_t)max_iter + 2) * 8, 0);
     PV_ALLOC(ctl, sizeof(PartCtl), 0);
 #undef PV_ALLOC
     pv_status_kernel<<<(U + 255u) / 256u, 256, 0, st>>>(P.status, U);
