@@ -306,6 +306,21 @@ int msspe_cross_dimer_device(msspe_ctx* ctx, const uint64_t* codes, uint32_t n, 
                              uint64_t edge_capacity, uint64_t nostruct_capacity, const msspe_dimer_edge** d_edges,
                              uint64_t* n_edges, const uint64_t** d_nostruct, uint64_t* n_nostruct);
 
+/* ---- (e) ONE design job over several GPUs: partitions (alignment columns) sharded over the ranks -------------------------
+ * One process per GPU.  Every rank's ctx is loaded with the columns of a contiguous range of partitions of EVERY genome
+ * (partition p of a genome = columns [p * overlap_size, p * overlap_size + window_size), main.rs:173-181; rank ranges in
+ * rank order, together all partitions) and builds its own index (no communication).  msspe_select_both_dist then
+ * replaces find_candidates_kmers (main.rs:331-406, both directions) for the WHOLE input: collective over the ranks,
+ * every rank receives the complete candidate lists, bit-identical to msspe_select_both on one GPU holding all
+ * columns.  Communication: NCCL (bound with dlopen from the host process), an all-gather of the ranks' not-yet-final
+ * per-partition winners and one all-reduce per round of the greedy loop's rounds -- nothing per iteration.
+ * msspe_dist_unique_id (rank 0; broadcast the 128 bytes with any out-of-band channel) + msspe_dist_init (all ranks,
+ * collective) create the communicator.  MSSPE_ERR_CAPACITY for the documented limits of this path. */
+int msspe_dist_unique_id(uint8_t* out128);
+int msspe_dist_init(msspe_ctx* ctx, const uint8_t* id128, int rank, int world);
+int msspe_select_both_dist(msspe_ctx* ctx, uint32_t max_iterations, uint32_t max_mismatch_segments,
+                           msspe_candidate* out_fwd, uint32_t* n_fwd, msspe_candidate* out_rev, uint32_t* n_rev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,6 +105,7 @@ extern "C" void msspe_destroy(msspe_ctx* c) {
   msspe_free_index(c);
   free_genomes(c);
   msspe_thal_free_tables(c);
+  msspe_dist_free(c);
   if (c->xd_edges) cudaFreeAsync(c->xd_edges, c->stream);
   if (c->xd_nostruct) cudaFreeAsync(c->xd_nostruct, c->stream);
   kprof_resolve(c);

@@ -53,7 +53,7 @@ struct DirIndex {
   uint32_t s_lists = 0, s_list_post = 0, s_tiles = 0;
   // partition view of the index for MSSPE_SELECT_PARTITIONED (select_part.cu; built on first use): the codes grouped by
   // the partition all their postings share ("units"), lists that span several partitions kept apart
-  bool pv_built = false;
+  bool pv_built = false, pv_dist = false;   // pv_dist: built for the multi-GPU loop (words of other ranks count as multi-partition)
   uint32_t pv_units = 0, pv_single = 0, pv_multi_n = 0;
   uint64_t pv_multi_postings = 0;
   uint32_t* pv_ucode_off = nullptr;  // [U+1] CSR over pv_ucodes
@@ -137,6 +137,7 @@ struct msspe_ctx {
   struct ThalDeviceTables* d_thal = nullptr;  // device copy of static tables (ntthal stand-ins: msspe_set_thal_params applies)
   struct ThalDeviceTables* d_thal_p3 = nullptr;  // Primer3's compiled-in tables (primer3_core stand-ins), never overridden
   msspe_thal_raw_params* raw_p3 = nullptr;
+  void* dist = nullptr;                        // select_dist.cu: NCCL communicator of the multi-GPU loop
   msspe_dimer_edge* xd_edges = nullptr;       // msspe_cross_dimer_device: lists of the last call (ctx-owned)
   uint64_t* xd_nostruct = nullptr;
   // pinned staging
@@ -172,6 +173,7 @@ int msspe_select_partitioned(msspe_ctx* ctx, int ndirs, const int* dirs, uint32_
                              uint32_t** n_outs);
 int msspe_partition_view(msspe_ctx* ctx, int dir, cudaStream_t st);   // builds DirIndex::pv_* (lazy)
 bool msspe_partitioned_applicable(msspe_ctx* ctx, int ndirs, const int* dirs, uint32_t max_iter);
+void msspe_dist_free(msspe_ctx* ctx);                                  // select_dist.cu
 int msspe_thal_upload_tables(msspe_ctx* ctx);
 void msspe_thal_free_tables(msspe_ctx* ctx);
 

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "msspe_set_thal_params", "msspe_primer_thermo", "msspe_thal_pairs", "msspe_thal_pairs_aligned", "msspe_cross_dimer",
     "msspe_fasta_open", "msspe_fasta_close", "msspe_fasta_records", "msspe_fasta_name", "msspe_fasta_bases",
     "msspe_fasta_offsets", "msspe_load_fasta", "msspe_kmer_stats", "msspe_kmer_stats_both", "msspe_coverage_summary", "msspe_vertex_cover", "msspe_shard_begin", "msspe_shard_buffers", "msspe_shard_count", "msspe_shard_firstpos", "msspe_shard_apply",
-    "msspe_get_kernel_profile", "msspe_cross_dimer_device",
+    "msspe_get_kernel_profile", "msspe_cross_dimer_device", "msspe_dist_unique_id", "msspe_dist_init", "msspe_select_both_dist",
 ]
 
 
@@ -158,6 +158,9 @@ def load_library():
     L.msspe_cross_dimer_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(ThalCond), C.c_uint32, C.c_uint32,
                                            C.c_double, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.msspe_dist_unique_id.argtypes = [C.c_void_p]
+    L.msspe_dist_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.msspe_select_both_dist.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.POINTER(C.c_uint32)]
     L.msspe_get_kernel_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     L.msspe_kmer_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(FilterCfg), C.c_void_p]
     L.msspe_kmer_stats_both.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(FilterCfg), C.c_void_p, C.c_void_p]
@@ -426,6 +429,30 @@ class Engine:
         s = (torch.as_tensor(Engine._DevArray(pn.value, nn.value, "<i8"), device="cuda") if nn.value
              else torch.zeros(0, dtype=torch.int64, device="cuda"))
         return e, s
+
+    def dist_init(self, dist, device):
+        """Communicator of the multi-GPU loop: rank 0 draws the NCCL id, torch.distributed carries its 128 bytes."""
+        import torch
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if dist.get_rank() == 0:
+            buf = C.create_string_buffer(128)
+            rc = self.L.msspe_dist_unique_id(buf)
+            if rc != OK:
+                raise MsspeError(rc, "msspe_dist_unique_id failed (libnccl.so.2 not loadable?)")
+            idt = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        idt = idt.to(device)
+        dist.broadcast(idt, 0)
+        raw = bytes(idt.cpu().numpy().tobytes())
+        self._check(self.L.msspe_dist_init(self.h, raw, dist.get_rank(), dist.get_world_size()))
+
+    def select_both_dist(self, max_iterations: int, max_mismatch_segments: int):
+        """find_candidates_kmers of the WHOLE job (both directions) from this rank's column shard; collective."""
+        a = np.zeros(max(1, max_iterations), dtype=CANDIDATE_DTYPE)
+        b = np.zeros(max(1, max_iterations), dtype=CANDIDATE_DTYPE)
+        na, nb = C.c_uint32(), C.c_uint32()
+        self._check(self.L.msspe_select_both_dist(self.h, max_iterations, max_mismatch_segments, a.ctypes.data, C.byref(na),
+                                                  b.ctypes.data, C.byref(nb)))
+        return a[:na.value], b[:nb.value]
 
     def kernel_profile(self) -> np.ndarray:
         """Per kernel class since the last reset_timing: launches, algorithmic bytes, device ms (while profiling is on)."""

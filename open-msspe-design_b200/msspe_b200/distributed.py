@@ -96,6 +96,23 @@ def cross_dimer_sharded_tensors(compute_rows_t, n: int, edge_dtype, dist=None, d
     return edges, q.cpu().numpy().view(np.uint64)
 
 
+def partition_range(n_part: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous partitions [begin, end) of rank `rank` (the column shard of the multi-GPU loop)."""
+    return row_block(n_part, rank, world)
+
+
+def column_shard(genomes: np.ndarray, window: int, step: int, rank: int, world: int) -> np.ndarray:
+    """The columns of this rank's partitions for EVERY genome of an equal-length alignment (n x L uint8): partition p =
+    columns [p * step, p * step + window) (main.rs:173-181), so a contiguous partition range is a contiguous column
+    range and the rank's windows are exactly the global windows of its partitions."""
+    n, L = genomes.shape
+    n_part = (L - window) // step + 1 if L >= window else 0
+    p0, p1 = partition_range(n_part, rank, world)
+    if p1 <= p0:
+        return np.zeros((n, 0), dtype=np.uint8)
+    return np.ascontiguousarray(genomes[:, p0 * step:(p1 - 1) * step + window])
+
+
 NO_LOCAL_ID = 0xFFFFFFFF
 
 
