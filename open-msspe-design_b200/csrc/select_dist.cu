@@ -13,10 +13,11 @@
 // round, enqueued on the ctx stream; rounds are batched without host round trips exactly as on one GPU.  NCCL is bound
 // with dlopen (the library the host process already uses, e.g. torch's), no link-time dependency.
 //
+// The f32 tie score of a cross list (main.rs:268-281) is a sum in first-seen partition order.  With one or two live
+// partitions the sum is commutative; from three on the order matters, so the iteration is "asked": the loop finalises
+// up to it, and the next round's buffer carries the first live genome of every partition at that iteration.
 // Limits of this path (MSSPE_ERR_CAPACITY, never a wrong answer): more than DIST_XCAP cross lists staged in one round;
-// a cross list with live postings in more than two partitions of one rank, or a frequency tie of a cross list whose
-// live postings span more than two partitions (the f32 tie score is order-sensitive from three terms on, main.rs:268-281,
-// and the first-seen order is not exchanged); with two terms the sum is commutative and exact.
+// a cross list with postings in more than DIST_SL partitions of one rank (or 24 live partitions in total).
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -28,6 +29,8 @@ constexpr uint32_t DIST_KMAX = 32;      // not-yet-final entries a unit may hold
 constexpr uint32_t DIST_WMAX = 62;      // iterations verified ahead per round
 constexpr uint32_t DIST_XW = DIST_WMAX + 4;   // words per cross-list row: [0] live count at t_final, [1 + i] cover-time histogram
 constexpr uint32_t DIST_XCAP = 4096;    // cross lists staged per round
+constexpr uint32_t DIST_SL = 3;         // partitions of one cross list a rank can report per round
+constexpr uint32_t DIST_PW = 3;         // words per reported partition: unit + 1, last cover time, first live genome at the queried iteration
 constexpr uint32_t VR_WORDS = 8;        // local best record: tv, cnt, score bits, code lo, code hi, n_same, has, pad (+ touched-unit mask)
 
 struct NcclApi {
@@ -204,10 +207,10 @@ __global__ void __launch_bounds__(128) dist_xhist_kernel(PartArgs A, DistArgs X)
   const PartCtl* C = D.ctl;
   if (C->done) return;
   __shared__ uint32_t h[DIST_XW];
-  __shared__ uint32_t tp[8], tmx[8];
+  __shared__ uint32_t tp[8], tmx[8], tnf[8];
   __shared__ unsigned long long sh[34];
   const int tid = threadIdx.x;
-  const uint32_t ns = min(*Q.n_xstage, DIST_XCAP), t_final = C->t_final, t_hi = C->t_hi;
+  const uint32_t ns = min(*Q.n_xstage, DIST_XCAP), t_final = C->t_final, t_hi = C->t_hi, tq = C->tq;
   for (uint32_t s = blockIdx.x; s < ns; s += gridDim.x) {
     const uint32_t xid = Q.xstage[s];
     const uint32_t m = Q.x_local[xid];
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(128) dist_xhist_kernel(PartArgs A, DistArgs X)
     const uint32_t c = D.ucodes[D.n_single + m];
     const uint32_t a = D.post_off[c], b = D.post_off[c + 1];
     for (uint32_t i = tid; i < DIST_XW; i += 128) h[i] = 0u;
-    if (tid < 8) { tp[tid] = 0xFFFFFFFFu; tmx[tid] = 0u; }
+    if (tid < 8) { tp[tid] = 0xFFFFFFFFu; tmx[tid] = 0u; tnf[tid] = 0xFFFFFFFFu; }
     __syncthreads();
     unsigned long long l0 = 0;
     for (uint32_t i = a + tid; i < b; i += 128) {
@@ -224,7 +227,14 @@ __global__ void __launch_bounds__(128) dist_xhist_kernel(PartArgs A, DistArgs X)
       if (tm >= t_final) { l0++; if (tm < t_hi) atomicAdd(&h[1u + tm - t_final], 1u); }
       const uint32_t p = part_of(A, g);
       int k = 0;
-      for (; k < 8; k++) { const uint32_t old = atomicCAS(&tp[k], 0xFFFFFFFFu, p); if (old == 0xFFFFFFFFu || old == p) { atomicMax(&tmx[k], tm); break; } }
+      for (; k < 8; k++) {
+        const uint32_t old = atomicCAS(&tp[k], 0xFFFFFFFFu, p);
+        if (old == 0xFFFFFFFFu || old == p) {
+          atomicMax(&tmx[k], tm);
+          if (tq != T_INF && tm >= tq) atomicMin(&tnf[k], g / A.uniform_parts);   // genome of the first posting still live at the queried iteration
+          break;
+        }
+      }
       if (k == 8) atomicOr(Q.err, 2u);
     }
     const uint32_t L0 = (uint32_t)block_sum_u64<128>(l0, sh);
@@ -232,10 +242,13 @@ __global__ void __launch_bounds__(128) dist_xhist_kernel(PartArgs A, DistArgs X)
     for (uint32_t i = 1 + tid; i < DIST_XW; i += 128) row[i] = h[i];
     if (tid == 0) {
       row[0] = L0;
-      uint32_t* pb = Q.xbuf + X.xb_off_pb + ((size_t)s * X.world + X.rank) * 4;   // two (unit + 1, last cover time) pairs per rank
-      int n = 0;
-      for (int k = 0; k < 8; k++) if (tp[k] != 0xFFFFFFFFu) { if (n < 2) { pb[2 * n] = gu_of(X, tp[k]) + 1u; pb[2 * n + 1] = tmx[k]; } n++; }
-      if (n > 2) atomicOr(Q.err, 2u);
+      uint32_t* pb = Q.xbuf + X.xb_off_pb + ((size_t)s * X.world + X.rank) * (DIST_SL * DIST_PW);
+      uint32_t n = 0;
+      for (int k = 0; k < 8; k++) if (tp[k] != 0xFFFFFFFFu) {
+        if (n < DIST_SL) { pb[DIST_PW * n] = gu_of(X, tp[k]) + 1u; pb[DIST_PW * n + 1] = tmx[k]; pb[DIST_PW * n + 2] = tnf[k]; }
+        n++;
+      }
+      if (n > DIST_SL) atomicOr(Q.err, 2u);
     }
     __syncthreads();
   }
@@ -272,23 +285,35 @@ __global__ void dist_decide_kernel(PartArgs AV, DistArgs X) {
     const bool term = t >= Vend;
     const uint32_t F = term ? 1u : V.win_freq[i];
     if (cnt < F || (term && cnt < 2u)) continue;
-    // the reference's f32 tie score over the partitions with a live posting at t: at most two terms (commutative)
-    float score = 0.0f; int live = 0;
+    // partitions with a live posting at t (a partition is live as long as its last cover time is >= t)
+    uint32_t lg[24], ln[24]; int live = 0; bool over = false;
     for (int r = 0; r < X.world; r++) {
-      const uint32_t* pb = Q.xbuf + X.xb_off_pb + ((size_t)s * X.world + r) * 4;
-      for (int k = 0; k < 2; k++) {
-        if (pb[2 * k] && pb[2 * k + 1] >= t) { score = __fadd_rn(score, __fdiv_rn(1.0f, __fadd_rn((float)cov_view(AV, V, pb[2 * k] - 1u, t), 1.0f))); live++; }
+      const uint32_t* pb = Q.xbuf + X.xb_off_pb + ((size_t)s * X.world + r) * (DIST_SL * DIST_PW);
+      for (uint32_t k = 0; k < DIST_SL; k++)
+        if (pb[DIST_PW * k] && pb[DIST_PW * k + 1] >= t) { if (live < 24) { lg[live] = pb[DIST_PW * k] - 1u; ln[live] = pb[DIST_PW * k + 2]; live++; } else over = true; }
+    }
+    if (over) { atomicOr(Q.err, 2u); return; }
+    const bool strict = term || cnt > F;
+    if (!strict) atomicAdd(V.mt + i, 1u);
+    // the reference's f32 tie score (main.rs:268-281): terms in the order the partitions are first seen among the live
+    // postings.  One or two terms: the sum is commutative.  Three or more: the order matters, and only the queried
+    // iteration carries it (first live genome per partition) -- otherwise ask for it and stop here.
+    if (live > 2) {
+      if (t != C->tq) { atomicMin(&C->tq_next, t); return; }
+      for (int a2 = 1; a2 < live; a2++) {   // order by (first live genome, partition): global segment order
+        const uint32_t kg = lg[a2], kn = ln[a2]; int b2 = a2 - 1;
+        while (b2 >= 0 && (ln[b2] > kn || (ln[b2] == kn && lg[b2] > kg))) { lg[b2 + 1] = lg[b2]; ln[b2 + 1] = ln[b2]; b2--; }
+        lg[b2 + 1] = kg; ln[b2 + 1] = kn;
       }
     }
-    bool wins = term || cnt > F;
+    float score = 0.0f;
+    for (int a2 = 0; a2 < live; a2++) score = __fadd_rn(score, __fdiv_rn(1.0f, __fadd_rn((float)cov_view(AV, V, lg[a2], t), 1.0f)));
+    bool wins = strict;
     if (!wins) {
-      atomicAdd(V.mt + i, 1u);
-      if (live > 2) { atomicOr(Q.err, 4u); return; }
       const float wsc = __fdiv_rn(1.0f, __fadd_rn((float)V.win_cov[i], 1.0f));
       wins = score > wsc || (score == wsc && code < V.win_code[i]);
     }
     if (wins) {
-      if (live > 2) { atomicOr(Q.err, 4u); return; }
       Q.cviol[s] = make_uint4(t, cnt, __float_as_uint(score), xid);
       atomicMin(&C->vmin, t);
       return;
@@ -316,9 +341,12 @@ __global__ void __launch_bounds__(1024) dist_finalize_kernel(PartArgs A, PartArg
   for (uint32_t r = tid; r < (uint32_t)X.world; r += 1024) { const uint32_t* vr = Q.xbuf + X.xb_off_vr + (size_t)r * X.vr_words; if (vr[6]) atomicMin(&s_tv, vr[0]); }
   for (uint32_t s = tid; s < ns; s += 1024) atomicMin(&s_tv, Q.cviol[s].x);
   __syncthreads();
-  const uint32_t tv = s_tv;
+  // an iteration whose tie needs the first-seen order of >= 3 partitions comes first: finalise up to it and ask (tq)
+  const uint32_t tqn = C->tq_next;
+  const bool ask = tqn != T_INF && tqn <= s_tv;
+  const uint32_t tv = ask ? T_INF : s_tv;
   const bool viol = tv != T_INF;
-  const uint32_t t_new = viol ? tv : Vend;
+  const uint32_t t_new = ask ? tqn : (viol ? tv : Vend);
   if (viol) {   // best (count, score, smaller word) among everything that wins at tv; words are unique, so the key decides
     for (uint32_t r = tid; r < (uint32_t)X.world; r += 1024) { const uint32_t* vr = Q.xbuf + X.xb_off_vr + (size_t)r * X.vr_words; if (vr[6] && vr[0] == tv) atomicMax(&s_best, ((unsigned long long)vr[1] << 32) | vr[2]); }
     for (uint32_t s = tid; s < ns; s += 1024) { const uint4 v = Q.cviol[s]; if (v.x == tv) atomicMax(&s_best, ((unsigned long long)v.y << 32) | v.z); }
@@ -399,13 +427,13 @@ __global__ void __launch_bounds__(1024) dist_finalize_kernel(PartArgs A, PartArg
       C->n_ext = j + 1u; C->rollbacks++;
       const uint32_t gap = t_new - C->last_viol;
       C->last_viol = t_new; C->wmax = min(DIST_WMAX, max(32u, 2u * gap));
-      C->t_final = t_new + 1u;
+      C->t_final = t_new + 1u; C->tq = T_INF;
       if (cnt < A.mms || t_new + 1u >= A.max_iter) { C->done = 1u; C->n_out = t_new + 1u; }
     }
     return;
   }
   const uint32_t cutbound = C->cutbound, H = C->H, terminal = C->terminal;
-  const bool done = Vend == cutbound && (!terminal || H == T_INF);
+  const bool done = !ask && Vend == cutbound && (!terminal || H == T_INF);
   if (!done && !C->clipped) {
     const uint32_t bound = terminal ? A.max_iter : cutbound;
     for (uint32_t u = tid; u < X.U_loc; u += 1024) {
@@ -419,7 +447,8 @@ __global__ void __launch_bounds__(1024) dist_finalize_kernel(PartArgs A, PartArg
   if (tid == 0) {
     C->evals += ev; C->iterations += t_new - t_final;
     C->t_final = t_new;
-    if (C->wmax) C->wmax = min(DIST_WMAX, 2u * C->wmax);
+    C->tq = ask ? tqn : T_INF;
+    if (C->wmax && !ask) C->wmax = min(DIST_WMAX, 2u * C->wmax);
     if (done) {
       if (C->do_terminal) { C->evals += C->live_all; C->iterations += 1u; }
       C->done = 1u; C->n_out = t_new;
@@ -540,6 +569,7 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
   if (max_iter == 0) return MSSPE_OK;
   const uint64_t G = c->n_segments;
   const uint32_t U_loc = G ? c->max_partition + 1u : 0u;
+  if (G && !(c->uniform_parts && c->uniform_parts <= 65536u)) { c->set_error("msspe_select_both_dist: a column shard has records of equal length (every genome, the same columns)"); return MSSPE_ERR_INVALID; }
   if (G >= 0x80000000ull) { c->set_error("msspe_select_both_dist: at most 2^31 segments per rank"); return MSSPE_ERR_CAPACITY; }
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[2], st));
   std::vector<void*> scratch;
@@ -578,7 +608,7 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
   X.vr_words = VR_WORDS + UW;
   X.xb_off_mt = DIST_XCAP * DIST_XW;
   X.xb_off_pb = X.xb_off_mt + DIST_XW;
-  X.xb_off_vr = X.xb_off_pb + DIST_XCAP * (uint32_t)world * 4u;
+  X.xb_off_vr = X.xb_off_pb + DIST_XCAP * (uint32_t)world * (DIST_SL * DIST_PW);
   X.xb_off_err = X.xb_off_vr + (uint32_t)world * X.vr_words;
   X.xb_words = X.xb_off_err + 1u;
   const size_t block_bytes = (size_t)UM * DIST_KMAX * sizeof(PEntry) + (size_t)UM * sizeof(uint4) + (size_t)UM * 8;
@@ -699,7 +729,7 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
       MSSPE_NCCL_TRY(c, ds, N->AllReduce(Q.xparts, Q.xparts, (size_t)n_x * UW, ncclUint32, ncclSum, ds->comm, st));   // disjoint bits per rank: sum = or
     }
     // PartCtl: verify windows are bounded by the exchange record
-    PartCtl h0; memset(&h0, 0, sizeof h0); h0.wmax = DIST_WMAX;
+    PartCtl h0; memset(&h0, 0, sizeof h0); h0.wmax = DIST_WMAX; h0.tq = T_INF; h0.tq_next = T_INF;
     MSSPE_CUDA_TRY(c, cudaMemcpyAsync(P.ctl, &h0, sizeof h0, cudaMemcpyHostToDevice, st));
     MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
   }
@@ -762,7 +792,7 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
     MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
     if ((h_err[0] | h_err[1]) & (1u | 4u | 8u)) {   // bits every rank sees in the same round (2 = local: it arrives as 8 one round later)
       c->set_error("msspe_select_both_dist: limit of the multi-GPU loop reached (flags %u/%u: 1 = more than %u cross-rank lists staged in a round, "
-                   "2 = a cross-rank list in more than two partitions of a rank, 4 = frequency tie of a cross-rank list over more than two partitions)",
+                   "2 = a cross-rank list in more than 3 partitions of one rank or 24 in total)",
                    h_err[0], h_err[1], DIST_XCAP);
       return MSSPE_ERR_CAPACITY;
     }

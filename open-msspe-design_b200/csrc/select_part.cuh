@@ -29,7 +29,7 @@ struct PartCtl {
   uint32_t E, H, cutbound, V, terminal, do_terminal, fmin, t_hi;
   uint32_t n_stage, n_viol, vmin, n_ext;
   uint32_t rounds, rollbacks, wmax, last_viol;
-  uint32_t clipped, pad0, pad1, pad2;
+  uint32_t clipped, tq, tq_next, pad2;   // multi-GPU loop: iteration whose tie scores need the first-seen order of the partitions (pending / next)
 };
 
 struct PartDir {
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(1024) part_gather_kernel(PartArgs A) {
   }
   const unsigned long long la = block_sum_u64<1024>(live, sh);
   for (uint32_t i = tid; i <= A.max_iter; i += 1024) D.mt[i] = 0u;
-  if (tid == 0) { C->E = s_base; C->live_all = la; C->n_stage = 0u; C->n_viol = 0u; C->vmin = T_INF; C->rounds++; }
+  if (tid == 0) { C->E = s_base; C->live_all = la; C->n_stage = 0u; C->n_viol = 0u; C->vmin = T_INF; C->tq_next = T_INF; C->rounds++; }
 }
 
 // key order of the merge: higher frequency, then lower partition_coverage (= higher 1/(cov+1), main.rs:320-324), then smaller word
