@@ -90,6 +90,7 @@ struct DistArgs {
   DistDir x[2];
   int rank, world;
   uint32_t UM, U_pad, U_loc, UW;        // units per rank (max), padded total, local units, mask words
+  uint32_t xcap;                        // cross lists that can be staged per round: min(DIST_XCAP, cross lists of the job)
   uint32_t xb_off_mt, xb_off_pb, xb_off_vr, xb_off_err, xb_words, vr_words;
 };
 
@@ -113,12 +114,12 @@ __global__ void dist_pack_kernel(PartArgs A, DistArgs X) {
 }
 
 // recvbuf = world blocks of {entries[UM*KMAX], hdr[UM], live[UM]} -> the view V (contiguous over the padded units)
-__global__ void dist_unpack_kernel(PartArgs AV, DistArgs X, size_t block_bytes) {
+__global__ void dist_unpack_kernel(PartArgs AV, DistArgs X, size_t rank_stride) {
   const PartDir& V = AV.d[blockIdx.y];
   const DistDir& Q = X.x[blockIdx.y];
   const uint32_t gu = blockIdx.x;       // < U_pad
   const uint32_t r = gu / X.UM, u = gu - r * X.UM;
-  const unsigned char* blk = Q.recvbuf + (size_t)r * block_bytes;
+  const unsigned char* blk = Q.recvbuf + (size_t)r * rank_stride;   // both directions of a rank travel in one block
   const PEntry* e = reinterpret_cast<const PEntry*>(blk) + (size_t)u * DIST_KMAX;
   const uint4* h = reinterpret_cast<const uint4*>(blk + (size_t)X.UM * DIST_KMAX * sizeof(PEntry));
   const unsigned long long* l = reinterpret_cast<const unsigned long long*>(blk + (size_t)X.UM * DIST_KMAX * sizeof(PEntry) + (size_t)X.UM * sizeof(uint4));
@@ -195,8 +196,8 @@ __global__ void dist_xscatter_kernel(PartArgs A, DistArgs X, int d, const uint32
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Q.n_x) return;
   const bool f = (!A.d[d].ctl->done && Q.ub_x[i] >= A.d[d].ctl->fmin);
-  if (f) { const uint32_t s = scan[i]; if (s < DIST_XCAP) Q.xstage[s] = i; }
-  if (i == Q.n_x - 1) { const uint32_t n = scan[i] + (f ? 1u : 0u); *Q.n_xstage = n; if (n > DIST_XCAP) atomicOr(Q.err, 1u); }
+  if (f) { const uint32_t s = scan[i]; if (s < X.xcap) Q.xstage[s] = i; }
+  if (i == Q.n_x - 1) { const uint32_t n = scan[i] + (f ? 1u : 0u); *Q.n_xstage = n; if (n > X.xcap) atomicOr(Q.err, 1u); }
 }
 
 // one block per staged cross list: this rank's cover-time histogram of the window, its live count at t_final, and the
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(128) dist_xhist_kernel(PartArgs A, DistArgs X)
   __shared__ uint32_t tp[8], tmx[8], tnf[8];
   __shared__ unsigned long long sh[34];
   const int tid = threadIdx.x;
-  const uint32_t ns = min(*Q.n_xstage, DIST_XCAP), t_final = C->t_final, t_hi = C->t_hi, tq = C->tq;
+  const uint32_t ns = min(*Q.n_xstage, X.xcap), t_final = C->t_final, t_hi = C->t_hi, tq = C->tq;
   for (uint32_t s = blockIdx.x; s < ns; s += gridDim.x) {
     const uint32_t xid = Q.xstage[s];
     const uint32_t m = Q.x_local[xid];
@@ -269,7 +270,7 @@ __global__ void dist_decide_kernel(PartArgs AV, DistArgs X) {
   PartCtl* C = V.ctl;
   if (C->done) return;
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t ns = min(*Q.n_xstage, DIST_XCAP);
+  const uint32_t ns = min(*Q.n_xstage, X.xcap);
   if (s >= ns) return;
   const uint32_t xid = Q.xstage[s];
   const uint32_t* row = Q.xbuf + (size_t)s * DIST_XW;
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(1024) dist_finalize_kernel(PartArgs A, PartArg
   __shared__ uint32_t s_tv, s_same, s_src;
   const int tid = threadIdx.x;
   const uint32_t t_final = C->t_final, Vend = C->V;
-  const uint32_t ns = min(*Q.n_xstage, DIST_XCAP);
+  const uint32_t ns = min(*Q.n_xstage, X.xcap);
   if (tid == 0 && Q.xbuf[X.xb_off_err]) atomicOr(Q.err, 8u);
   // earliest external winner over the ranks' local candidates and the cross lists
   if (tid == 0) { s_tv = T_INF; s_best = 0ull; s_code = ~0ull; s_same = 0u; s_src = 0xFFFFFFFFu; }
@@ -606,14 +607,12 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
   DistArgs X{};
   X.rank = rank; X.world = world; X.UM = UM; X.U_pad = U_pad; X.U_loc = U_loc; X.UW = UW;
   X.vr_words = VR_WORDS + UW;
-  X.xb_off_mt = DIST_XCAP * DIST_XW;
-  X.xb_off_pb = X.xb_off_mt + DIST_XW;
-  X.xb_off_vr = X.xb_off_pb + DIST_XCAP * (uint32_t)world * (DIST_SL * DIST_PW);
-  X.xb_off_err = X.xb_off_vr + (uint32_t)world * X.vr_words;
-  X.xb_words = X.xb_off_err + 1u;
-  const size_t block_bytes = (size_t)UM * DIST_KMAX * sizeof(PEntry) + (size_t)UM * sizeof(uint4) + (size_t)UM * 8;
+  const size_t block_bytes = ((size_t)UM * DIST_KMAX * sizeof(PEntry) + (size_t)UM * sizeof(uint4) + (size_t)UM * 8 + 15) & ~(size_t)15;
   uint32_t max_nx = 0, max_multi = 0;
   uint32_t* xscan[2] = {nullptr, nullptr};
+  // both directions share one all-gather and one all-reduce per round
+  unsigned char* send_all = nullptr; unsigned char* recv_all = nullptr; uint32_t* xbuf_all = nullptr;
+  DA(send_all, 2 * block_bytes, 0); DA(recv_all, 2 * block_bytes * world, 0);
 
   for (int d = 0; d < 2; d++) {
     DirIndex& I = c->dir[d];
@@ -708,14 +707,14 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
     DA(Vw.tot_live, ((uint64_t)max_iter + 2) * 8, 0);
     DA(Vw.mt, ((uint64_t)max_iter + 2) * 4, 0);      // ties of cross lists (the same on every rank)
     // the window arrays and the control block are shared by the local and the view side
-    DA(Q.sendbuf, block_bytes, 0); DA(Q.recvbuf, block_bytes * world, 0);
+    Q.sendbuf = send_all + (size_t)d * block_bytes; Q.recvbuf = recv_all + (size_t)d * block_bytes;
     Q.send_e = reinterpret_cast<PEntry*>(Q.sendbuf);
     Q.send_h = reinterpret_cast<uint4*>(Q.sendbuf + (size_t)UM * DIST_KMAX * sizeof(PEntry));
     Q.send_l = reinterpret_cast<unsigned long long*>(Q.sendbuf + (size_t)UM * DIST_KMAX * sizeof(PEntry) + (size_t)UM * sizeof(uint4));
     DA(Q.g_extcov, (uint64_t)U_pad * 4, 0); DA(Q.g_rfin, (uint64_t)U_pad * 4, 0);
     DA(Q.ub_x, ((uint64_t)n_x + 1) * 4, 0); DA(Q.x_local, ((uint64_t)n_x + 1) * 4, 0xFF); DA(Q.xparts, ((uint64_t)n_x + 1) * UW * 4, 0);
     DA(Q.xflags, ((uint64_t)n_x + 1) * 4, 0); DA(Q.xstage, (uint64_t)DIST_XCAP * 4, 0); DA(Q.n_xstage, 4, 0);
-    DA(Q.xbuf, (uint64_t)X.xb_words * 4, 0); DA(Q.cviol, (uint64_t)DIST_XCAP * 16, 0xFF); DA(Q.err, 4, 0);
+    DA(Q.cviol, (uint64_t)DIST_XCAP * 16, 0xFF); DA(Q.err, 4, 0);
     DA(xscan[d], ((uint64_t)n_x + 1) * 4, 0);
     uint32_t* m_xid = nullptr; uint32_t* xlen_local = nullptr;
     DA(m_xid, ((uint64_t)P.n_multi + 1) * 4, 0xFF); DA(xlen_local, ((uint64_t)n_x + 1) * 4, 0);
@@ -733,6 +732,15 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
     MSSPE_CUDA_TRY(c, cudaMemcpyAsync(P.ctl, &h0, sizeof h0, cudaMemcpyHostToDevice, st));
     MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
   }
+  // the all-reduced buffer: rows of the staged cross lists | ties of local lists | reported partitions | local best records | limit flag
+  X.xcap = std::min<uint32_t>(DIST_XCAP, std::max<uint32_t>(128u, (max_nx + 127u) & ~127u));
+  X.xb_off_mt = X.xcap * DIST_XW;
+  X.xb_off_pb = X.xb_off_mt + DIST_XW;
+  X.xb_off_vr = X.xb_off_pb + X.xcap * (uint32_t)world * (DIST_SL * DIST_PW);
+  X.xb_off_err = X.xb_off_vr + (uint32_t)world * X.vr_words;
+  X.xb_words = X.xb_off_err + 1u;
+  DA(xbuf_all, 2ull * X.xb_words * 4, 0);
+  for (int d = 0; d < 2; d++) X.x[d].xbuf = xbuf_all + (size_t)d * X.xb_words;
   if (U_loc) {
     dist_status_kernel<<<dim3((U_loc + 255u) / 256u, 2), 256, 0, st>>>(A);
     unsigned mx = 1;
@@ -758,13 +766,13 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
       A.nsteps = round == 0 ? chunk0 : chunk;
       if (U_loc) { KPROF(c, KP_GREEDY_UNIT, st, 0) int rc2 = launch_extend(c, A, csize, st); if (rc2) return rc2; }
       { KPROF(c, KP_GREEDY_MERGE, st, 0) dist_pack_kernel<<<dim3(UM, 2), 64, 0, st>>>(A, X); }
-      for (int d = 0; d < 2; d++) MSSPE_NCCL_TRY(c, ds, N->AllGather(X.x[d].sendbuf, X.x[d].recvbuf, block_bytes, ncclUint8, ds->comm, st));
-      { KPROF(c, KP_GREEDY_MERGE, st, 0) dist_unpack_kernel<<<dim3(U_pad, 2), 32, 0, st>>>(AV, X, block_bytes); }
+      MSSPE_NCCL_TRY(c, ds, N->AllGather(send_all, recv_all, 2 * block_bytes, ncclUint8, ds->comm, st));
+      { KPROF(c, KP_GREEDY_MERGE, st, 0) dist_unpack_kernel<<<dim3(U_pad, 2), 32, 0, st>>>(AV, X, 2 * block_bytes); }
       { KPROF(c, KP_GREEDY_MERGE, st, 0) part_gather_kernel<<<2, 1024, 0, st>>>(AV); }
       { KPROF(c, KP_GREEDY_MERGE, st, 0) part_merge_kernel<<<dim3(merge_grid, 2), 256, 0, st>>>(AV); }
       { KPROF(c, KP_GREEDY_MERGE, st, 0) part_plan_kernel<<<2, 1024, 0, st>>>(AV); }
       if (U_loc) { KPROF(c, KP_GREEDY_MERGE, st, 0) dist_posback_kernel<<<dim3(U_loc, 2), 32, 0, st>>>(A, AV, X); }
-      for (int d = 0; d < 2; d++) MSSPE_CUDA_TRY(c, cudaMemsetAsync(X.x[d].xbuf, 0, (size_t)X.xb_words * 4, st));
+      MSSPE_CUDA_TRY(c, cudaMemsetAsync(xbuf_all, 0, 2 * (size_t)X.xb_words * 4, st));
       if (max_multi) {
         { KPROF(c, KP_GREEDY_MERGE, st, 0) part_stage_kernel<<<dim3((max_multi + 255u) / 256u, 2), 256, 0, st>>>(A); }
         { KPROF(c, KP_GREEDY_VERIFY, st, 0) part_verify_kernel<<<dim3(ver_grid, 2), VER_T, ver_smem, st>>>(A); }
@@ -780,8 +788,8 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
         }
         { KPROF(c, KP_GREEDY_VERIFY, st, 0) dist_xhist_kernel<<<dim3(ver_grid, 2), 128, 0, st>>>(A, X); }
       }
-      for (int d = 0; d < 2; d++) MSSPE_NCCL_TRY(c, ds, N->AllReduce(X.x[d].xbuf, X.x[d].xbuf, X.xb_words, ncclUint32, ncclSum, ds->comm, st));
-      if (max_nx) { KPROF(c, KP_GREEDY_VERIFY, st, 0) dist_decide_kernel<<<dim3(DIST_XCAP / 128, 2), 128, 0, st>>>(AV, X); }
+      MSSPE_NCCL_TRY(c, ds, N->AllReduce(xbuf_all, xbuf_all, 2 * (size_t)X.xb_words, ncclUint32, ncclSum, ds->comm, st));
+      if (max_nx) { KPROF(c, KP_GREEDY_VERIFY, st, 0) dist_decide_kernel<<<dim3(X.xcap / 128, 2), 128, 0, st>>>(AV, X); }
       { KPROF(c, KP_GREEDY_MERGE, st, 0) dist_finalize_kernel<<<2, 1024, 0, st>>>(A, AV, X); }
     }
     MSSPE_CUDA_TRY(c, cudaGetLastError());
