@@ -25,9 +25,8 @@
 
 namespace {
 
-constexpr uint32_t DIST_KMAX = 32;      // not-yet-final entries a unit may hold (fixed-size exchange record)
-constexpr uint32_t DIST_WMAX = 62;      // iterations verified ahead per round
-constexpr uint32_t DIST_XW = DIST_WMAX + 4;   // words per cross-list row: [0] live count at t_final, [1 + i] cover-time histogram
+// per call (DistArgs): kmax = not-yet-final entries a unit may hold (fixed-size exchange record), wmax = iterations verified
+// ahead per round, xw = wmax + 4 words per cross-list row ([0] live count at t_final, [1 + i] cover-time histogram)
 constexpr uint32_t DIST_XCAP = 4096;    // cross lists staged per round
 constexpr uint32_t DIST_SL = 3;         // partitions of one cross list a rank can report per round
 constexpr uint32_t DIST_PW = 3;         // words per reported partition: unit + 1, last cover time, first live genome at the queried iteration
@@ -91,6 +90,7 @@ struct DistArgs {
   int rank, world;
   uint32_t UM, U_pad, U_loc, UW;        // units per rank (max), padded total, local units, mask words
   uint32_t xcap;                        // cross lists that can be staged per round: min(DIST_XCAP, cross lists of the job)
+  uint32_t kmax, xw, wmax;              // not-yet-final entries per unit in the exchange record; words per cross-list row; window cap
   uint32_t xb_off_mt, xb_off_pb, xb_off_vr, xb_off_err, xb_words, vr_words;
 };
 
@@ -104,13 +104,13 @@ __global__ void dist_pack_kernel(PartArgs A, DistArgs X) {
   const int tid = threadIdx.x;
   uint32_t nnf = 0, st = ST_FINISHED, rf = 0; unsigned long long ul = 0;
   if (u < X.U_loc) { rf = D.rfin[u]; nnf = D.ulen[u] - rf; st = D.status[u]; ul = D.ulive[u]; }
-  for (uint32_t i = tid; i < DIST_KMAX; i += blockDim.x) {
+  for (uint32_t i = tid; i < X.kmax; i += blockDim.x) {
     PEntry e; e.freq = 0; e.cid = 0; e.tied = 0; e.pad = 0; e.live_before = 0; e.code = 0;
     if (i < nnf) e = D.entries[(unsigned long long)u * A.CAP + rf + i];
-    Q.send_e[(unsigned long long)u * DIST_KMAX + i] = e;
+    Q.send_e[(unsigned long long)u * X.kmax + i] = e;
   }
   if (tid == 0) { Q.send_h[u] = make_uint4(nnf, st, rf, 0u); Q.send_l[u] = ul; }
-  if (u == 0) for (uint32_t i = tid; i < DIST_XW; i += blockDim.x) D.mt[i] = 0u;   // ties of this rank's local lists (part_verify adds to it)
+  if (u == 0) for (uint32_t i = tid; i < X.xw && i < A.max_iter + 2u; i += blockDim.x) D.mt[i] = 0u;   // ties of this rank's local lists (part_verify adds to it)
 }
 
 // recvbuf = world blocks of {entries[UM*KMAX], hdr[UM], live[UM]} -> the view V (contiguous over the padded units)
@@ -120,10 +120,10 @@ __global__ void dist_unpack_kernel(PartArgs AV, DistArgs X, size_t rank_stride) 
   const uint32_t gu = blockIdx.x;       // < U_pad
   const uint32_t r = gu / X.UM, u = gu - r * X.UM;
   const unsigned char* blk = Q.recvbuf + (size_t)r * rank_stride;   // both directions of a rank travel in one block
-  const PEntry* e = reinterpret_cast<const PEntry*>(blk) + (size_t)u * DIST_KMAX;
-  const uint4* h = reinterpret_cast<const uint4*>(blk + (size_t)X.UM * DIST_KMAX * sizeof(PEntry));
-  const unsigned long long* l = reinterpret_cast<const unsigned long long*>(blk + (size_t)X.UM * DIST_KMAX * sizeof(PEntry) + (size_t)X.UM * sizeof(uint4));
-  for (uint32_t i = threadIdx.x; i < DIST_KMAX; i += blockDim.x) V.entries[(unsigned long long)gu * DIST_KMAX + i] = e[i];
+  const PEntry* e = reinterpret_cast<const PEntry*>(blk) + (size_t)u * X.kmax;
+  const uint4* h = reinterpret_cast<const uint4*>(blk + (size_t)X.UM * X.kmax * sizeof(PEntry));
+  const unsigned long long* l = reinterpret_cast<const unsigned long long*>(blk + (size_t)X.UM * X.kmax * sizeof(PEntry) + (size_t)X.UM * sizeof(uint4));
+  for (uint32_t i = threadIdx.x; i < X.kmax; i += blockDim.x) V.entries[(unsigned long long)gu * X.kmax + i] = e[i];
   if (threadIdx.x == 0) {
     const uint4 hh = h[u];
     V.ulen[gu] = hh.x; V.rfin[gu] = 0u; V.status[gu] = hh.y; V.ulive[gu] = l[u];
@@ -141,7 +141,7 @@ __global__ void dist_posback_kernel(PartArgs A, PartArgs AV, DistArgs X) {
   if (u >= X.U_loc) return;
   const uint32_t gu = gu_of(X, u);
   const uint32_t rf = D.rfin[u], nnf = D.ulen[u] - rf;
-  for (uint32_t i = threadIdx.x; i < nnf; i += blockDim.x) D.pos[(unsigned long long)u * A.CAP + rf + i] = V.pos[(unsigned long long)gu * DIST_KMAX + i];
+  for (uint32_t i = threadIdx.x; i < nnf; i += blockDim.x) D.pos[(unsigned long long)u * A.CAP + rf + i] = V.pos[(unsigned long long)gu * X.kmax + i];
 }
 
 // ---- local multi-partition lists: best external-winner candidate of this rank -----------------------------------------
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) dist_localbest_kernel(PartArgs A, DistArg
   for (uint32_t i = tid; i < X.vr_words; i += 256) vr[i] = 0u;
   // ties of the local lists (counted by part_verify into D.mt) travel in the summed buffer
   const uint32_t W = C->t_hi - C->t_final;
-  for (uint32_t i = tid; i < W && i < DIST_XW; i += 256) Q.xbuf[X.xb_off_mt + i] = D.mt[i];
+  for (uint32_t i = tid; i < W && i < X.xw && i < A.max_iter + 2u; i += 256) Q.xbuf[X.xb_off_mt + i] = D.mt[i];
   if (tid == 0) { s_best = 0ull; s_bestc = 0u; s_same = 0u; Q.xbuf[X.xb_off_err] = *Q.err ? 1u : 0u; }   // a limit hit on any rank stops all of them
   __syncthreads();
   if (vmin == T_INF) return;
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(128) dist_xhist_kernel(PartArgs A, DistArgs X)
   const DistDir& Q = X.x[blockIdx.y];
   const PartCtl* C = D.ctl;
   if (C->done) return;
-  __shared__ uint32_t h[DIST_XW];
+  extern __shared__ uint32_t h[];
   __shared__ uint32_t tp[8], tmx[8], tnf[8];
   __shared__ unsigned long long sh[34];
   const int tid = threadIdx.x;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(128) dist_xhist_kernel(PartArgs A, DistArgs X)
     if (m == 0xFFFFFFFFu) continue;                  // not on this rank: its row stays zero
     const uint32_t c = D.ucodes[D.n_single + m];
     const uint32_t a = D.post_off[c], b = D.post_off[c + 1];
-    for (uint32_t i = tid; i < DIST_XW; i += 128) h[i] = 0u;
+    for (uint32_t i = tid; i < X.xw; i += 128) h[i] = 0u;
     if (tid < 8) { tp[tid] = 0xFFFFFFFFu; tmx[tid] = 0u; tnf[tid] = 0xFFFFFFFFu; }
     __syncthreads();
     unsigned long long l0 = 0;
@@ -239,8 +239,8 @@ __global__ void __launch_bounds__(128) dist_xhist_kernel(PartArgs A, DistArgs X)
       if (k == 8) atomicOr(Q.err, 2u);
     }
     const uint32_t L0 = (uint32_t)block_sum_u64<128>(l0, sh);
-    uint32_t* row = Q.xbuf + (size_t)s * DIST_XW;
-    for (uint32_t i = 1 + tid; i < DIST_XW; i += 128) row[i] = h[i];
+    uint32_t* row = Q.xbuf + (size_t)s * X.xw;
+    for (uint32_t i = 1 + tid; i < X.xw; i += 128) row[i] = h[i];
     if (tid == 0) {
       row[0] = L0;
       uint32_t* pb = Q.xbuf + X.xb_off_pb + ((size_t)s * X.world + X.rank) * (DIST_SL * DIST_PW);
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(128) dist_xhist_kernel(PartArgs A, DistArgs X)
 // partition_coverage of padded unit gu at iteration t from the replicated view
 __device__ uint32_t cov_view(const PartArgs& AV, const PartDir& V, uint32_t gu, uint32_t t) {
   uint32_t lo = 0, n = V.ulen[gu];
-  const uint32_t* ps = V.pos + (unsigned long long)gu * DIST_KMAX;
+  const uint32_t* ps = V.pos + (unsigned long long)gu * AV.CAP;
   while (n > 0) { const uint32_t half = n >> 1; if (ps[lo + half] < t) { lo += half + 1; n -= half + 1; } else n = half; }
   return V.ext_cov[gu] + lo;            // ext_cov of the view already holds the unit's final entries
 }
@@ -273,7 +273,7 @@ __global__ void dist_decide_kernel(PartArgs AV, DistArgs X) {
   const uint32_t ns = min(*Q.n_xstage, X.xcap);
   if (s >= ns) return;
   const uint32_t xid = Q.xstage[s];
-  const uint32_t* row = Q.xbuf + (size_t)s * DIST_XW;
+  const uint32_t* row = Q.xbuf + (size_t)s * X.xw;
   const uint32_t L0 = row[0], t_final = C->t_final, Vend = C->V, t_hi = C->t_hi, fmin = C->fmin;
   Q.ub_x[xid] = L0;
   Q.cviol[s] = make_uint4(T_INF, 0u, 0u, xid);
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(1024) dist_finalize_kernel(PartArgs A, PartArg
     if (tid == 0) {
       C->n_ext = j + 1u; C->rollbacks++;
       const uint32_t gap = t_new - C->last_viol;
-      C->last_viol = t_new; C->wmax = min(DIST_WMAX, max(32u, 2u * gap));
+      C->last_viol = t_new; C->wmax = min(X.wmax, max(32u, 2u * gap));
       C->t_final = t_new + 1u; C->tq = T_INF;
       if (cnt < A.mms || t_new + 1u >= A.max_iter) { C->done = 1u; C->n_out = t_new + 1u; }
     }
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(1024) dist_finalize_kernel(PartArgs A, PartArg
     C->evals += ev; C->iterations += t_new - t_final;
     C->t_final = t_new;
     C->tq = ask ? tqn : T_INF;
-    if (C->wmax && !ask) C->wmax = min(DIST_WMAX, 2u * C->wmax);
+    if (C->wmax && !ask) C->wmax = min(X.wmax, 2u * C->wmax);
     if (done) {
       if (C->do_terminal) { C->evals += C->live_all; C->iterations += 1u; }
       C->done = 1u; C->n_out = t_new;
@@ -602,12 +602,15 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
   PartArgs A{}, AV{};
   A.ndirs = 2; A.U = U_loc; A.CAP = (uint32_t)CAP; A.slots = c->slots; A.max_iter = max_iter; A.mms = mms;
   A.uniform_parts = (c->uniform_parts && c->uniform_parts <= 65536u) ? c->uniform_parts : 0u;
-  A.seg_part = c->d_seg_part; A.max_ahead = DIST_KMAX;
-  AV = A; AV.U = U_pad; AV.CAP = DIST_KMAX; AV.max_ahead = DIST_KMAX;
+  // not-yet-final entries a unit may hold = size of its exchange record: about three times the average share of the winners
+  uint32_t kmax = 32;
+  while (kmax < 256 && (uint64_t)kmax * U_pad < 3ull * max_iter) kmax <<= 1;
+  A.seg_part = c->d_seg_part; A.max_ahead = kmax;
+  AV = A; AV.U = U_pad; AV.CAP = kmax; AV.max_ahead = kmax;
   DistArgs X{};
   X.rank = rank; X.world = world; X.UM = UM; X.U_pad = U_pad; X.U_loc = U_loc; X.UW = UW;
-  X.vr_words = VR_WORDS + UW;
-  const size_t block_bytes = ((size_t)UM * DIST_KMAX * sizeof(PEntry) + (size_t)UM * sizeof(uint4) + (size_t)UM * 8 + 15) & ~(size_t)15;
+  X.vr_words = VR_WORDS + UW; X.kmax = kmax;
+  const size_t block_bytes = ((size_t)UM * kmax * sizeof(PEntry) + (size_t)UM * sizeof(uint4) + (size_t)UM * 8 + 15) & ~(size_t)15;
   uint32_t max_nx = 0, max_multi = 0;
   uint32_t* xscan[2] = {nullptr, nullptr};
   // both directions share one all-gather and one all-reduce per round
@@ -693,7 +696,7 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
     P.elist = nullptr; P.order = nullptr; P.tied = nullptr; P.tot_live = nullptr;
     PartDir& Vw = AV.d[d];
     Vw = P;
-    const uint64_t nv = (uint64_t)U_pad * DIST_KMAX;
+    const uint64_t nv = (uint64_t)U_pad * kmax;
     DA(Vw.entries, nv * sizeof(PEntry), 0);
     DA(Vw.pos, (nv + 2) * 4, 0xFF);
     DA(Vw.rfin, (uint64_t)U_pad * 4, 0);
@@ -709,8 +712,8 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
     // the window arrays and the control block are shared by the local and the view side
     Q.sendbuf = send_all + (size_t)d * block_bytes; Q.recvbuf = recv_all + (size_t)d * block_bytes;
     Q.send_e = reinterpret_cast<PEntry*>(Q.sendbuf);
-    Q.send_h = reinterpret_cast<uint4*>(Q.sendbuf + (size_t)UM * DIST_KMAX * sizeof(PEntry));
-    Q.send_l = reinterpret_cast<unsigned long long*>(Q.sendbuf + (size_t)UM * DIST_KMAX * sizeof(PEntry) + (size_t)UM * sizeof(uint4));
+    Q.send_h = reinterpret_cast<uint4*>(Q.sendbuf + (size_t)UM * kmax * sizeof(PEntry));
+    Q.send_l = reinterpret_cast<unsigned long long*>(Q.sendbuf + (size_t)UM * kmax * sizeof(PEntry) + (size_t)UM * sizeof(uint4));
     DA(Q.g_extcov, (uint64_t)U_pad * 4, 0); DA(Q.g_rfin, (uint64_t)U_pad * 4, 0);
     DA(Q.ub_x, ((uint64_t)n_x + 1) * 4, 0); DA(Q.x_local, ((uint64_t)n_x + 1) * 4, 0xFF); DA(Q.xparts, ((uint64_t)n_x + 1) * UW * 4, 0);
     DA(Q.xflags, ((uint64_t)n_x + 1) * 4, 0); DA(Q.xstage, (uint64_t)DIST_XCAP * 4, 0); DA(Q.n_xstage, 4, 0);
@@ -728,14 +731,20 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
       MSSPE_NCCL_TRY(c, ds, N->AllReduce(Q.xparts, Q.xparts, (size_t)n_x * UW, ncclUint32, ncclSum, ds->comm, st));   // disjoint bits per rank: sum = or
     }
     // PartCtl: verify windows are bounded by the exchange record
-    PartCtl h0; memset(&h0, 0, sizeof h0); h0.wmax = DIST_WMAX; h0.tq = T_INF; h0.tq_next = T_INF;
-    MSSPE_CUDA_TRY(c, cudaMemcpyAsync(P.ctl, &h0, sizeof h0, cudaMemcpyHostToDevice, st));
     MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
   }
   // the all-reduced buffer: rows of the staged cross lists | ties of local lists | reported partitions | local best records | limit flag
   X.xcap = std::min<uint32_t>(DIST_XCAP, std::max<uint32_t>(128u, (max_nx + 127u) & ~127u));
-  X.xb_off_mt = X.xcap * DIST_XW;
-  X.xb_off_pb = X.xb_off_mt + DIST_XW;
+  // iterations verified ahead per round: as many as a 1 MB buffer of histogram rows allows (62 ... 1020)
+  X.wmax = std::min<uint32_t>(std::min<uint32_t>(1020u, std::max<uint32_t>(62u, 262144u / X.xcap - 4u)), std::max<uint32_t>(max_iter, 1u));
+  X.xw = X.wmax + 4u;
+  {
+    PartCtl h0; memset(&h0, 0, sizeof h0); h0.wmax = X.wmax; h0.tq = T_INF; h0.tq_next = T_INF;
+    for (int d = 0; d < 2; d++) MSSPE_CUDA_TRY(c, cudaMemcpyAsync(A.d[d].ctl, &h0, sizeof h0, cudaMemcpyHostToDevice, st));
+    MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+  }
+  X.xb_off_mt = X.xcap * X.xw;
+  X.xb_off_pb = X.xb_off_mt + X.xw;
   X.xb_off_vr = X.xb_off_pb + X.xcap * (uint32_t)world * (DIST_SL * DIST_PW);
   X.xb_off_err = X.xb_off_vr + (uint32_t)world * X.vr_words;
   X.xb_words = X.xb_off_err + 1u;
@@ -754,7 +763,7 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
   const uint64_t unit_items = U_loc ? G / U_loc * c->slots : 0;
   int csize = unit_items >= (1u << 20) ? 8 : unit_items >= (1u << 18) ? 4 : unit_items >= (1u << 16) ? 2 : 1;
   if (const char* e = getenv("MSSPE_PART_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) csize = v; }
-  const uint32_t chunk0 = std::min<uint32_t>(DIST_KMAX, (uint32_t)std::max<uint64_t>(4, (3ull * max_iter + 2ull * U_pad - 1) / (2ull * U_pad)));
+  const uint32_t chunk0 = std::min<uint32_t>(kmax, (uint32_t)std::max<uint64_t>(4, (3ull * max_iter + 2ull * U_pad - 1) / (2ull * U_pad)));
   const uint32_t chunk = 8;
   const unsigned merge_grid = (unsigned)c->sm_count * 2u, ver_grid = (unsigned)c->sm_count * 2u;
   PartCtl* h = reinterpret_cast<PartCtl*>(c->h_ctl);
@@ -786,7 +795,7 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
           if (rc2) return rc2;
           dist_xscatter_kernel<<<(X.x[d].n_x + 255u) / 256u, 256, 0, st>>>(A, X, d, xscan[d]);
         }
-        { KPROF(c, KP_GREEDY_VERIFY, st, 0) dist_xhist_kernel<<<dim3(ver_grid, 2), 128, 0, st>>>(A, X); }
+        { KPROF(c, KP_GREEDY_VERIFY, st, 0) dist_xhist_kernel<<<dim3(ver_grid, 2), 128, (size_t)X.xw * 4, st>>>(A, X); }
       }
       MSSPE_NCCL_TRY(c, ds, N->AllReduce(xbuf_all, xbuf_all, 2 * (size_t)X.xb_words, ncclUint32, ncclSum, ds->comm, st));
       if (max_nx) { KPROF(c, KP_GREEDY_VERIFY, st, 0) dist_decide_kernel<<<dim3(X.xcap / 128, 2), 128, 0, st>>>(AV, X); }
