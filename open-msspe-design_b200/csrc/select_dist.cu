@@ -20,6 +20,7 @@
 // a cross list with postings in more than DIST_SL partitions of one rank (or 24 live partitions in total).
 #include <dlfcn.h>
 #include <nccl.h>
+#include <time.h>
 
 #include "select_part.cuh"
 
@@ -573,6 +574,10 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
   if (G && !(c->uniform_parts && c->uniform_parts <= 65536u)) { c->set_error("msspe_select_both_dist: a column shard has records of equal length (every genome, the same columns)"); return MSSPE_ERR_INVALID; }
   if (G >= 0x80000000ull) { c->set_error("msspe_select_both_dist: at most 2^31 segments per rank"); return MSSPE_ERR_CAPACITY; }
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[2], st));
+  const bool dbg = getenv("MSSPE_DEBUG_TIMERS") != nullptr;
+  auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return 1e3 * ts.tv_sec + 1e-6 * ts.tv_nsec; };
+  const double t_begin = now_ms();
+  double t_setup = 0.0;
   std::vector<void*> scratch;
   auto alloc = [&](void** p, uint64_t bytes, int fill) -> int {
     MSSPE_CUDA_TRY(c, cudaMallocAsync(p, bytes ? bytes : 4, st));
@@ -770,6 +775,7 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
   uint32_t h_err[2] = {0, 0};
   uint32_t round = 0;
   const uint32_t BATCH = 4;
+  if (dbg) { cudaStreamSynchronize(st); t_setup = now_ms() - t_begin; }
   for (;;) {
     for (uint32_t b = 0; b < BATCH; b++, round++) {
       A.nsteps = round == 0 ? chunk0 : chunk;
@@ -841,8 +847,8 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
   c->timing.select_ms[0] = c->timing.select_ms[1] = ms;
   if (getenv("MSSPE_DEBUG_TIMERS"))
     for (int d = 0; d < 2; d++)
-      fprintf(stderr, "[msspe] rank %d/%d partitioned greedy dir %d: %u winners, %u rounds, %u external winners, %u local multi lists, %u cross-rank lists, %.3f ms\n",
-              rank, world, d, h[d].n_out, h[d].rounds, h[d].rollbacks, A.d[d].n_multi, X.x[d].n_x, ms);
+      fprintf(stderr, "[msspe] rank %d/%d partitioned greedy dir %d: %u winners, %u rounds, %u external winners, %u local multi lists, %u cross-rank lists, %.3f ms (set-up %.3f ms, wall %.3f ms; kmax %u, window %u, staged cap %u, buffer %u KB)\n",
+              rank, world, d, h[d].n_out, h[d].rounds, h[d].rollbacks, A.d[d].n_multi, X.x[d].n_x, ms, t_setup, now_ms() - t_begin, X.kmax, X.wmax, X.xcap, 2 * X.xb_words / 256);
 #undef DA
   return MSSPE_OK;
 }

@@ -283,3 +283,298 @@ def select(slots, part, max_iter, mms, **kw):
     return dict(codes=[o[0] for o in m.out], freqs=[o[1] for o in m.out], n_tied=[o[2] for o in m.out],
                 score_bits=[f32_bits(o[3]) for o in m.out], evals=m.evals, iterations=m.iterations, rounds=m.rounds,
                 rollbacks=m.rollbacks)
+
+
+# ---- the multi-GPU loop (csrc/select_dist.cu) -----------------------------------------------------------------------------
+class DistributedPartitionedSelect:
+    """One rank of the column-sharded loop.  `comm.all_gather(obj)` returns the list of every rank's obj (rank order); all
+    decisions are taken on gathered data, identically on every rank -- the protocol of select_dist.cu: (1) all-gather of
+    the units' not-yet-final entries, replicated merge; (2) per round one exchange carrying each rank's best local
+    external winner, the cover-time histograms of the cross-rank lists and, per partition of such a list, its last cover
+    time (+ the first live genome at a queried iteration: the f32 tie score is order-sensitive from three partitions on)."""
+
+    def __init__(self, slots, part, n_part_local, comm, rank, world, max_iter, mms, kmax=8, wmax=16, chunk0=4, chunk=2):
+        self.L = PartitionedSelect(slots, part, max_iter, mms)
+        self.comm, self.rank, self.world, self.max_iter, self.mms = comm, rank, world, max_iter, mms
+        self.kmax, self.wmax_cap, self.wmax, self.chunk0, self.chunk = kmax, wmax, wmax, chunk0, chunk
+        L = self.L
+        self.n_part_local = n_part_local
+        self.P = L.U                                            # partitions (uniform alignment: genome = segment // P)
+        sizes = comm.all_gather(L.U)
+        self.UM = max(max(sizes), 1)
+        self.U_pad = self.UM * world
+        # words that occur on several ranks leave the units' candidate lists
+        all_codes = comm.all_gather([int(c) for c in L.codes])
+        seen = {}
+        for r, cs in enumerate(all_codes):
+            for c in cs:
+                seen[c] = seen.get(c, 0) + 1
+        self.cross = sorted(c for c, n in seen.items() if n >= 2)
+        self.xlocal = {}
+        code_to_cid = {int(c): i for i, c in enumerate(L.codes)}
+        for code in self.cross:
+            if code in code_to_cid:
+                cid = code_to_cid[code]
+                self.xlocal[code] = cid
+                if L.list_part[cid] >= 0:
+                    L.unit_codes[L.list_part[cid]].remove(cid)
+                    L.list_part[cid] = -1
+                    L.multi.append(cid)
+        self.local_multi = [c for c in L.multi if int(L.codes[c]) not in self.xlocal]
+        self.xparts = {}
+        for code in self.cross:
+            mine = {self.gu(L.part[g]) for g in L.post[L.off[self.xlocal[code]]:L.off[self.xlocal[code] + 1]]} if code in self.xlocal else set()
+            self.xparts[code] = set().union(*comm.all_gather(mine))
+        self.ext_cov = [0] * self.U_pad                        # replicated
+        self.t_final, self.tq = 0, None
+        self.out, self.evals, self.iterations, self.rounds, self.rollbacks, self.asks = [], 0, 0, 0, 0, 0
+
+    def gu(self, u_local):
+        return self.rank * self.UM + u_local
+
+    def cov_view(self, gu, t):
+        e = self.table[gu]
+        return self.ext_cov[gu] + e["rfin"] + sum(1 for p in e["pos"] if p < t)
+
+    def round(self):
+        L = self.L
+        self.rounds += 1
+        for u in range(L.U):
+            if (L.want_extend[u] and not L.finished[u]) or L.need_recount[u]:
+                n = self.chunk0 if self.rounds == 1 else self.chunk
+                room = self.kmax - (len(L.entries[u]) - L.rfin[u]) if not L.need_recount[u] else self.kmax
+                L.extend(u, max(0, min(n, room)))
+            L.want_extend[u] = False
+        # (1) the units' not-yet-final entries -> replicated table
+        pack = []
+        for u in range(self.UM):
+            if u < L.U:
+                ents = [(e["freq"], int(L.codes[e["cid"]]), e["tied"], e["live_before"]) for e in L.entries[u][L.rfin[u]:]]
+                pack.append(dict(rfin=L.rfin[u], ents=ents, finished=L.finished[u], ulive=L.ulive[u], pos=[]))
+            else:
+                pack.append(dict(rfin=0, ents=[], finished=True, ulive=0, pos=[]))
+        self.table = [e for blk in self.comm.all_gather(pack) for e in blk]
+        nonfinal = [(gu, i) for gu in range(self.U_pad) for i in range(len(self.table[gu]["ents"]))]
+        key = lambda x: (-self.table[x[0]]["ents"][x[1]][0], self.table[x[0]]["rfin"] + x[1] + self.ext_cov[x[0]], self.table[x[0]]["ents"][x[1]][1])  # noqa: E731
+        nonfinal.sort(key=key)
+        for gu in range(self.U_pad):
+            self.table[gu]["pos"] = [None] * len(self.table[gu]["ents"])
+        for i, (gu, idx) in enumerate(nonfinal):
+            self.table[gu]["pos"][idx] = self.t_final + i
+        for u in range(L.U):                                    # positions back into this rank's entries (cover tokens refer to them)
+            for idx, p in enumerate(self.table[self.gu(u)]["pos"]):
+                L.entries[u][L.rfin[u] + idx]["pos"] = p
+        H = INF
+        for gu in range(self.U_pad):
+            e = self.table[gu]
+            if not e["finished"]:
+                H = min(H, e["pos"][-1] + 1 if e["pos"] else self.t_final)
+        cutbound, terminal = self.max_iter, False
+        for i, (gu, idx) in enumerate(nonfinal):
+            if self.table[gu]["ents"][idx][0] < self.mms:
+                cutbound = min(cutbound, self.t_final + i + 1)
+                break
+        else:
+            if self.t_final + len(nonfinal) < self.max_iter:
+                cutbound, terminal = self.t_final + len(nonfinal), True
+        V = min(H, cutbound)
+        clipped = V - self.t_final > self.wmax
+        if clipped:
+            V = self.t_final + self.wmax
+        do_terminal = terminal and H == INF and not clipped
+        t_hi = V + (1 if do_terminal else 0)
+        win = {}
+        for i in range(V - self.t_final):
+            gu, idx = nonfinal[i]
+            f, code, tied, lb = self.table[gu]["ents"][idx]
+            win[self.t_final + i] = (f, self.table[gu]["rfin"] + idx + self.ext_cov[gu], code)
+
+        def heads_at(t):
+            tot, tied_by_f = 0, {}
+            for gu in range(self.U_pad):
+                e = self.table[gu]
+                for idx, p in enumerate(e["pos"]):
+                    if p >= t:
+                        tot += e["ents"][idx][3]
+                        tied_by_f[e["ents"][idx][0]] = tied_by_f.get(e["ents"][idx][0], 0) + e["ents"][idx][2]
+                        break
+                else:
+                    tot += e["ulive"]
+            return tot, tied_by_f
+
+        # (2a) this rank's lists that lie inside it: exactly the one-GPU check
+        L.t_final = self.t_final
+        local_best, mt_local, local_viol = None, {}, []
+        for c in self.local_multi:
+            times = [L.time_of(g) for g in L.post[L.off[c]:L.off[c + 1]]]
+            for t in range(self.t_final, t_hi):
+                if local_best is not None and t > local_best[0]:
+                    break
+                cnt = sum(1 for x in times if x >= t)
+                if t == V and do_terminal:
+                    beats = cnt >= 2
+                else:
+                    f, cov, wcode = win[t]
+                    if cnt < f:
+                        continue
+                    if cnt == f:
+                        mt_local[t] = mt_local.get(t, 0) + 1
+                sc = self._local_score(c, t)
+                if not (t == V and do_terminal):
+                    wsc = f32(1.0 / f32(f32(cov) + 1.0))
+                    beats = cnt > f or sc > wsc or (sc == wsc and int(L.codes[c]) < wcode)
+                if beats:
+                    cand = (t, cnt, sc, -int(L.codes[c]))
+                    local_viol.append(cand)
+                    if local_best is None or t < local_best[0] or (t == local_best[0] and cand[1:] > local_best[1:]):
+                        local_best = cand
+                    break
+        n_same = sum(1 for v in local_viol if local_best is not None and v[0] == local_best[0] and v[1] == local_best[1])
+        lb_parts = None
+        if local_best is not None:
+            cid = {int(L.codes[c]): c for c in self.local_multi}[-local_best[3]]
+            lb_parts = {self.gu(L.part[g]) for g in L.post[L.off[cid]:L.off[cid + 1]]}
+        # (2b) cross-rank lists: local histogram, live count, per-partition last cover time (+ first live genome at tq)
+        xinfo = {}
+        for code, cid in self.xlocal.items():
+            hist, l0, parts = {}, 0, {}
+            for g in L.post[L.off[cid]:L.off[cid + 1]]:
+                tm = L.time_of(g)
+                if tm >= self.t_final:
+                    l0 += 1
+                    if tm < t_hi:
+                        hist[tm] = hist.get(tm, 0) + 1
+                pr = parts.setdefault(self.gu(L.part[g]), [0, INF])
+                pr[0] = max(pr[0], tm)
+                if self.tq is not None and tm >= self.tq:
+                    pr[1] = min(pr[1], g // self.P)
+            xinfo[code] = (l0, hist, parts)
+        gathered = self.comm.all_gather((local_best, (lb_parts, n_same), xinfo, mt_local))
+        # decide, identically everywhere
+        mt, cands, tq_next = {}, [], None
+        for lb, lbp, xi, mtl in gathered:
+            for t, n in mtl.items():
+                mt[t] = mt.get(t, 0) + n
+            if lb is not None:
+                cands.append((lb[0], lb[1], lb[2], lb[3], ("local", lbp[0]), lbp[1]))
+        for code in self.cross:
+            l0, hist, parts = 0, {}, {}
+            for lb, lbp, xi, mtl in gathered:
+                if code in xi:
+                    l0 += xi[code][0]
+                    for t, n in xi[code][1].items():
+                        hist[t] = hist.get(t, 0) + n
+                    parts.update(xi[code][2])
+            covered = 0
+            for t in range(self.t_final, t_hi):
+                cnt = l0 - covered
+                covered += hist.get(t, 0)
+                term = t == V and do_terminal
+                f = 1 if term else win[t][0]
+                if cnt < f or (term and cnt < 2):
+                    continue
+                strict = term or cnt > f
+                if not strict:
+                    mt[t] = mt.get(t, 0) + 1
+                live = [(gu, v[1]) for gu, v in parts.items() if v[0] >= t]
+                if len(live) > 2:
+                    if t != self.tq:
+                        tq_next = t if tq_next is None else min(tq_next, t)
+                        break
+                    live.sort(key=lambda x: (x[1], x[0]))
+                sc = f32(0.0)
+                for gu, _ in live:
+                    sc = f32(sc + f32(1.0 / f32(f32(self.cov_view(gu, t)) + 1.0)))
+                wins = strict
+                if not wins:
+                    wsc = f32(1.0 / f32(f32(win[t][1]) + 1.0))
+                    wins = sc > wsc or (sc == wsc and code < win[t][2])
+                if wins:
+                    cands.append((t, cnt, sc, -code, ("cross", code), 1))
+                    break
+        tv = min((c[0] for c in cands), default=None)
+        ask = tq_next is not None and (tv is None or tq_next <= tv)
+        if ask:
+            tv = None
+        t_new = tq_next if ask else (tv if tv is not None else V)
+        for t in range(self.t_final, t_new + (1 if tv is not None else 0)):
+            tot, tied_by_f = heads_at(t)
+            self.evals += tot
+            self.iterations += 1
+            if t < t_new:
+                f, cov, code = win[t]
+                self.out.append((code, f, tied_by_f.get(f, 0) + mt.get(t, 0), f32(1.0 / f32(f32(cov) + 1.0))))
+            else:
+                at = [c for c in cands if c[0] == tv]
+                best = max(at, key=lambda c: (c[1], c[2], c[3]))
+                cnt = best[1]
+                tie_case = t in win and win[t][0] == cnt
+                n_tied = tied_by_f.get(cnt, 0) + mt.get(t, 0) if tie_case else sum(c[5] for c in at if c[1] == cnt)
+                self.out.append((-best[3], cnt, n_tied, best[2]))
+        for u in range(L.U):
+            while L.rfin[u] < len(L.entries[u]) and L.entries[u][L.rfin[u]]["pos"] < t_new:
+                L.rfin[u] += 1
+        self.tq = tq_next if ask else None
+        if tv is not None:
+            self.rollbacks += 1
+            kind, what = best[4]
+            touched = what if kind == "local" else self.xparts[what]
+            for gu in touched:
+                self.ext_cov[gu] += 1
+                if gu // self.UM == self.rank:
+                    L.ext_cov[gu - self.rank * self.UM] += 1
+            code = -best[3]
+            cid = {int(L.codes[c]): c for c in L.multi}.get(code)
+            j = len(L.ext_time)
+            L.ext_time.append(tv)
+            if cid is not None:
+                affected = set()
+                for g in L.post[L.off[cid]:L.off[cid + 1]]:
+                    if L.time_of(g) >= tv:
+                        L.token[g] = ("x", j)
+                        affected.add(L.part[g])
+                for u in affected:
+                    del L.entries[u][L.rfin[u]:]
+                    L.need_recount[u] = True
+                    L.finished[u] = False
+                    L.want_extend[u] = True
+            self.t_final = tv + 1
+            self.wmax = self.wmax_cap
+            return best[1] < self.mms or self.t_final >= self.max_iter
+        self.t_final = t_new
+        if ask:
+            self.asks += 1
+            return False
+        done = V == cutbound and (not terminal or H == INF)
+        if done:
+            if do_terminal:
+                tot, _ = heads_at(t_new)
+                self.evals += tot
+                self.iterations += 1
+            return True
+        if not clipped:
+            for u in range(L.U):
+                if not L.finished[u]:
+                    last = L.entries[u][-1]["pos"] + 1 if len(L.entries[u]) > L.rfin[u] else self.t_final
+                    if last < (self.max_iter if terminal else cutbound):
+                        L.want_extend[u] = True
+        return False
+
+    def _local_score(self, c, t):
+        L = self.L
+        seen, score = set(), f32(0.0)
+        for g in L.post[L.off[c]:L.off[c + 1]]:
+            if L.time_of(g) < t:
+                continue
+            p = L.part[g]
+            if p not in seen:
+                seen.add(p)
+                score = f32(score + f32(1.0 / f32(f32(self.cov_view(self.gu(p), t)) + 1.0)))
+        return score
+
+    def run(self):
+        if self.max_iter == 0:
+            return self
+        while not self.round():
+            assert self.rounds < 100000
+        return self

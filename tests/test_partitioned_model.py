@@ -109,3 +109,98 @@ def test_repeats_couple_partitions(oracle_lib):
     st = _check(oracle_lib, fa, 500, 250, 50, 13, 200, 1)
     assert sum(rb for _, rb in st) > 0
     _check(oracle_lib, fa, 500, 250, 50, 13, 200, 3, chunk0=2, chunk=1)
+
+
+# ---- the multi-GPU protocol (csrc/select_dist.cu) on two gloo ranks -------------------------------------------------------
+def _dist_worker(rank, world, port, fasta, params, q):
+    import os as _os
+    import sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+    _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+    import torch.distributed as dist
+    import _partitioned_model as pm2
+    from oracle import oracle as O, kmer_oracle as ko
+    _os.environ["MASTER_ADDR"] = "127.0.0.1"
+    _os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class Comm:
+        def all_gather(self, obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+
+    W, S, w, k, max_iter, mms, kw = params
+    recs = ko.to_records(fasta)
+    L = min(len(r.sequence) for r in recs)
+    n_part = (L - W) // S + 1
+    base, rem = divmod(n_part, world)
+    p0 = rank * base + min(rank, rem)
+    p1 = p0 + base + (1 if rank < rem else 0)
+    local = "".join(">%s\n%s\n" % (r.name, r.sequence[p0 * S:(p1 - 1) * S + W] if p1 > p0 else "") for r in recs).encode()
+    res = []
+    for d in (0, 1):
+        slots, part = O.segment_slots(local, W, S, w, k, d)
+        m = pm2.DistributedPartitionedSelect(slots, part, p1 - p0, Comm(), rank, world, max_iter, mms, **kw).run()
+        res.append(dict(codes=[o[0] for o in m.out], freqs=[o[1] for o in m.out], n_tied=[o[2] for o in m.out],
+                        score_bits=[pm2.f32_bits(o[3]) for o in m.out], evals=m.evals, rollbacks=m.rollbacks, asks=m.asks, rounds=m.rounds))
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_dist(fasta, params):
+    import multiprocessing as mp
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dist_worker, args=(r, 2, port, fasta, params, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return got
+
+
+@pytest.mark.timeout(900)
+def test_two_rank_column_sharded_loop_equals_the_oracle(oracle_lib, zika_fasta):
+    """World-size-2 gloo run of the multi-GPU protocol (unit entries all-gathered and merged on every rank, cross-rank
+    lists decided from exchanged cover-time histograms, the first-seen order of three or more partitions asked for when a
+    tie needs it): every rank must return the oracle's loop on the WHOLE alignment, for the Zika fixture, for a family
+    with blocks repeated across the rank boundary (cross-rank external winners) and for k = 6 (nearly every word on both
+    ranks: ties over many partitions)."""
+    rng = np.random.default_rng(5)
+    anc = rng.integers(0, 4, 6000)
+    anc[4000:4300] = anc[500:800]
+    anc[5200:5500] = anc[1500:1800]
+    rep = []
+    for i in range(40):
+        s = anc.copy()
+        mut = rng.random(6000) < 0.03
+        s[mut] = rng.integers(0, 4, int(mut.sum()))
+        rep.append(">r%d\n%s\n" % (i, "".join("ACGT"[x] for x in s)))
+    cases = [("".join(rep).encode(), (500, 250, 50, 13, 150, 1, dict(kmax=8, wmax=16, chunk0=4, chunk=2))),
+             (zika_fasta, (500, 250, 50, 13, 1000, 2, dict(kmax=4, wmax=8, chunk0=2, chunk=1))),
+             (_random_alignment(6, 30, 1200, gaps=False), (100, 50, 30, 6, 60, 3, dict(kmax=8, wmax=16, chunk0=4, chunk=2)))]
+    total_rb = total_asks = 0
+    for fasta, params in cases:
+        W, S, w, k, max_iter, mms, _ = params
+        got = _run_dist(fasta, params)
+        for d in (0, 1):
+            want = oracle_lib.select(fasta, W, S, w, k, d, max_iter, mms)
+            for rank in (0, 1):
+                g = got[rank][d]
+                assert g["codes"] == want["codes"].tolist(), "rank %d direction %d" % (rank, d)
+                assert g["freqs"] == want["freqs"].tolist()
+                assert g["n_tied"] == want["n_tied"].tolist()
+                assert g["score_bits"] == want["scores"].view(np.uint32).tolist()
+                assert g["evals"] == want["evals"]
+            total_rb += got[0][d]["rollbacks"]
+            total_asks += got[0][d]["asks"]
+    assert total_rb > 0 and total_asks > 0
