@@ -28,7 +28,8 @@ namespace {
 
 // per call (DistArgs): kmax = not-yet-final entries a unit may hold (fixed-size exchange record), wmax = iterations verified
 // ahead per round, xw = wmax + 4 words per cross-list row ([0] live count at t_final, [1 + i] cover-time histogram)
-constexpr uint32_t DIST_XCAP = 4096;    // cross lists staged per round
+constexpr uint32_t DIST_XCAP = 4096;    // most cross lists staged per round (error beyond)
+constexpr uint32_t DIST_XSTAGE = 256;   // rows of the exchange buffer when the job has more cross lists than that: the window adapts
 constexpr uint32_t DIST_SL = 3;         // partitions of one cross list a rank can report per round
 constexpr uint32_t DIST_PW = 3;         // words per reported partition: unit + 1, last cover time, first live genome at the queried iteration
 constexpr uint32_t VR_WORDS = 8;        // local best record: tv, cnt, score bits, code lo, code hi, n_same, has, pad (+ touched-unit mask)
@@ -79,7 +80,7 @@ struct DistDir {
   unsigned char* sendbuf; unsigned char* recvbuf;
   uint32_t* g_extcov; uint32_t* g_rfin; // [U_pad]
   // cross lists
-  uint32_t n_x; const unsigned long long* xcodes; uint32_t* ub_x; uint32_t* x_local; const uint32_t* m_xid; uint32_t* xparts;
+  uint32_t n_x; const unsigned long long* xcodes; const uint32_t* xlen_desc; uint32_t* ub_x; uint32_t* x_local; const uint32_t* m_xid; uint32_t* xparts;
   uint32_t* xflags; uint32_t* xstage; uint32_t* n_xstage;   // staged cross lists of this round (xid order)
   uint32_t* xbuf;                       // the all-reduced buffer
   uint4* cviol;                         // [XCAP] cross-list violations {tv, cnt, score bits, xid}
@@ -131,6 +132,26 @@ __global__ void dist_unpack_kernel(PartArgs AV, DistArgs X, size_t rank_stride) 
     Q.g_rfin[gu] = hh.z;
     V.ext_cov[gu] = Q.g_extcov[gu] + hh.z;      // partition_coverage of the unit's first not-yet-final entry
   }
+}
+
+// The verify window must not stage more cross lists than the exchange buffer has rows: a list can only matter where its
+// global length reaches the winning frequency, so the window ends where more than xcap lists are that long (xlen_desc =
+// the global lengths, descending; replicated, so every rank clips alike).
+__global__ void dist_clip_kernel(PartArgs AV, DistArgs X) {
+  const PartDir& V = AV.d[blockIdx.x];
+  const DistDir& Q = X.x[blockIdx.x];
+  PartCtl* C = V.ctl;
+  if (C->done || threadIdx.x != 0 || Q.n_x <= X.xcap) return;
+  const uint32_t t_final = C->t_final;
+  uint32_t Vend = C->V;
+  if (Vend <= t_final) return;
+  const uint32_t need = Q.xlen_desc[X.xcap];             // the (xcap + 1)-th longest list: frequencies at or below it stage too many
+  if (V.win_freq[Vend - 1u - t_final] > need && !(C->do_terminal && need >= 2u)) return;
+  uint32_t lo = 0, n = Vend - t_final;                  // first window position whose winning frequency is <= need
+  while (n > 0) { const uint32_t half = n >> 1; if (V.win_freq[lo + half] > need) { lo += half + 1; n -= half + 1; } else n = half; }
+  if (lo == 0) { atomicOr(Q.err, 1u); return; }
+  Vend = t_final + lo;
+  C->V = Vend; C->t_hi = Vend; C->do_terminal = 0u; C->clipped = 1u; C->fmin = V.win_freq[lo - 1u];
 }
 
 // positions of the merged view back into this rank's slots (cover tokens refer to them)
@@ -513,6 +534,14 @@ __global__ void dist_xmap_kernel(PartArgs A, DistArgs X, int d, uint32_t* m_xid,
     }
   }
 }
+__global__ void dist_lenkey_kernel(const uint32_t* __restrict__ len, uint32_t n, uint64_t* __restrict__ key) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) key[i] = (uint64_t)(0xFFFFFFFFu - len[i]);     // ascending sort of the complement = descending lengths
+}
+__global__ void dist_lenunkey_kernel(const uint64_t* __restrict__ key, uint32_t n, uint32_t* __restrict__ len) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) len[i] = 0xFFFFFFFFu - (uint32_t)key[i];
+}
 __global__ void dist_status_kernel(PartArgs A) {
   const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u < A.U) A.d[blockIdx.y].status[u] = ST_EXTEND;
@@ -555,8 +584,33 @@ void msspe_dist_free(msspe_ctx* c) {
   c->dist = nullptr;
 }
 
+namespace {
+struct ScratchList {   // stream-ordered scratch of one attempt, returned to the pool however the attempt ends
+  std::vector<void*> p; cudaStream_t st;
+  ~ScratchList() { for (void* q : p) cudaFreeAsync(q, st); }
+};
+int dist_select_impl(msspe_ctx* c, uint32_t max_iter, uint32_t mms, msspe_candidate* out_fwd, uint32_t* n_fwd, msspe_candidate* out_rev,
+                     uint32_t* n_rev, uint32_t xstage_rows, bool* retry);
+}  // namespace
+
 extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t mms, msspe_candidate* out_fwd, uint32_t* n_fwd,
                                       msspe_candidate* out_rev, uint32_t* n_rev) {
+  if (!c) return MSSPE_ERR_INVALID;
+  // rows of the per-round exchange buffer: few suffice when few cross-rank lists are as long as the winning frequencies
+  // (the verify window adapts to them); an input with many long cross-rank lists reports it on every rank in the same
+  // round, and every rank retries with more rows
+  int rc = MSSPE_OK;
+  for (uint32_t rows = DIST_XSTAGE; ; rows *= 4) {
+    bool retry = false;
+    rc = dist_select_impl(c, max_iter, mms, out_fwd, n_fwd, out_rev, n_rev, rows, &retry);
+    if (!(retry && rows < DIST_XCAP)) break;
+  }
+  return rc;
+}
+
+namespace {
+int dist_select_impl(msspe_ctx* c, uint32_t max_iter, uint32_t mms, msspe_candidate* out_fwd, uint32_t* n_fwd, msspe_candidate* out_rev,
+                     uint32_t* n_rev, uint32_t xstage_rows, bool* retry) {
   if (!c) return MSSPE_ERR_INVALID;
   if (!n_fwd || !n_rev || (max_iter && (!out_fwd || !out_rev))) { c->set_error("msspe_select_both_dist: bad argument"); return MSSPE_ERR_INVALID; }
   if (!c->dist) { c->set_error("msspe_select_both_dist: msspe_dist_init first"); return MSSPE_ERR_STATE; }
@@ -578,11 +632,11 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
   auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return 1e3 * ts.tv_sec + 1e-6 * ts.tv_nsec; };
   const double t_begin = now_ms();
   double t_setup = 0.0;
-  std::vector<void*> scratch;
+  ScratchList scratch; scratch.st = st;
   auto alloc = [&](void** p, uint64_t bytes, int fill) -> int {
     MSSPE_CUDA_TRY(c, cudaMallocAsync(p, bytes ? bytes : 4, st));
+    scratch.p.push_back(*p);
     if (fill >= 0) MSSPE_CUDA_TRY(c, cudaMemsetAsync(*p, fill, bytes ? bytes : 4, st));
-    scratch.push_back(*p);
     return MSSPE_OK;
   };
 #define DA(ptr, bytes, fill) { int rc2 = alloc((void**)&(ptr), (bytes), (fill)); if (rc2) return rc2; }
@@ -734,14 +788,23 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
     if (n_x) {   // global length of every cross list (its first upper bound) and the units it touches
       MSSPE_NCCL_TRY(c, ds, N->AllReduce(xlen_local, Q.ub_x, n_x, ncclUint32, ncclSum, ds->comm, st));
       MSSPE_NCCL_TRY(c, ds, N->AllReduce(Q.xparts, Q.xparts, (size_t)n_x * UW, ncclUint32, ncclSum, ds->comm, st));   // disjoint bits per rank: sum = or
+      if (n_x > xstage_rows) {   // global lengths in descending order, for the window clip
+        uint64_t *ka2 = nullptr, *kb2 = nullptr; uint32_t *va2 = nullptr, *vb2 = nullptr; uint32_t* desc = nullptr;
+        DA(ka2, (uint64_t)n_x * 8, -1); DA(kb2, (uint64_t)n_x * 8, -1); DA(va2, (uint64_t)n_x * 4, 0); DA(vb2, (uint64_t)n_x * 4, 0); DA(desc, (uint64_t)n_x * 4, -1);
+        dist_lenkey_kernel<<<(n_x + 255u) / 256u, 256, 0, st>>>(Q.ub_x, n_x, ka2);
+        rc = msspe_radix_sort_pairs(c, &ka2, &va2, &kb2, &vb2, n_x, 32, st);
+        if (rc) return rc;
+        dist_lenunkey_kernel<<<(n_x + 255u) / 256u, 256, 0, st>>>(ka2, n_x, desc);
+        Q.xlen_desc = desc;
+      }
     }
     // PartCtl: verify windows are bounded by the exchange record
     MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
   }
   // the all-reduced buffer: rows of the staged cross lists | ties of local lists | reported partitions | local best records | limit flag
-  X.xcap = std::min<uint32_t>(DIST_XCAP, std::max<uint32_t>(128u, (max_nx + 127u) & ~127u));
-  // iterations verified ahead per round: as many as a 1 MB buffer of histogram rows allows (62 ... 1020)
-  X.wmax = std::min<uint32_t>(std::min<uint32_t>(1020u, std::max<uint32_t>(62u, 262144u / X.xcap - 4u)), std::max<uint32_t>(max_iter, 1u));
+  X.xcap = max_nx <= xstage_rows ? std::max<uint32_t>(128u, (max_nx + 127u) & ~127u) : xstage_rows;
+  // iterations verified ahead per round: as many as 256 KB of histogram rows per direction allow (62 ... 1020)
+  X.wmax = std::min<uint32_t>(std::min<uint32_t>(1020u, std::max<uint32_t>(62u, 65536u / X.xcap - 4u)), std::max<uint32_t>(max_iter, 1u));
   X.xw = X.wmax + 4u;
   {
     PartCtl h0; memset(&h0, 0, sizeof h0); h0.wmax = X.wmax; h0.tq = T_INF; h0.tq_next = T_INF;
@@ -786,6 +849,7 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
       { KPROF(c, KP_GREEDY_MERGE, st, 0) part_gather_kernel<<<2, 1024, 0, st>>>(AV); }
       { KPROF(c, KP_GREEDY_MERGE, st, 0) part_merge_kernel<<<dim3(merge_grid, 2), 256, 0, st>>>(AV); }
       { KPROF(c, KP_GREEDY_MERGE, st, 0) part_plan_kernel<<<2, 1024, 0, st>>>(AV); }
+      if (max_nx > X.xcap) { KPROF(c, KP_GREEDY_MERGE, st, 0) dist_clip_kernel<<<2, 32, 0, st>>>(AV, X); }
       if (U_loc) { KPROF(c, KP_GREEDY_MERGE, st, 0) dist_posback_kernel<<<dim3(U_loc, 2), 32, 0, st>>>(A, AV, X); }
       MSSPE_CUDA_TRY(c, cudaMemsetAsync(xbuf_all, 0, 2 * (size_t)X.xb_words * 4, st));
       if (max_multi) {
@@ -817,6 +881,8 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
       c->set_error("msspe_select_both_dist: limit of the multi-GPU loop reached (flags %u/%u: 1 = more than %u cross-rank lists staged in a round, "
                    "2 = a cross-rank list in more than 3 partitions of one rank or 24 in total)",
                    h_err[0], h_err[1], DIST_XCAP);
+      *retry = ((h_err[0] | h_err[1]) & (2u | 4u)) == 0;    // only the number of rows was short
+      cudaStreamSynchronize(st);
       return MSSPE_ERR_CAPACITY;
     }
     if (h[0].done && h[1].done) break;     // the control blocks are replicated: every rank leaves in the same batch
@@ -840,7 +906,6 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
     c->timing.select_iterations[d] = h[d].iterations;
     c->timing.select_postings_read[d] = c->dir[d].n_records;
   }
-  for (void* p : scratch) MSSPE_CUDA_TRY(c, cudaFreeAsync(p, st));
   MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
   float ms = 0.f;
   MSSPE_CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
@@ -852,3 +917,4 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
 #undef DA
   return MSSPE_OK;
 }
+}  // namespace
