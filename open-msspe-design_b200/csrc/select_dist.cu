@@ -61,7 +61,7 @@ NcclApi* nccl_api(std::string* err) {
   return &api;
 }
 
-struct DistState { NcclApi* api; ncclComm_t comm; int rank, world; };
+struct DistState { NcclApi* api; ncclComm_t comm; int rank, world; uint32_t rows_hint; };   // rows_hint: exchange-buffer rows that sufficed last time
 
 #define MSSPE_NCCL_TRY(ctx, ds, expr)                                                                        \
   do {                                                                                                       \
@@ -481,19 +481,31 @@ __global__ void __launch_bounds__(1024) dist_finalize_kernel(PartArgs A, PartArg
 
 // ---- set-up: which words occur on several ranks ----------------------------------------------------------------------
 __global__ void dist_crossflag_kernel(const unsigned long long* __restrict__ codes, uint32_t n, const unsigned long long* __restrict__ all, const uint32_t* __restrict__ counts,
-                                      uint32_t dmax, int rank, int world, const uint32_t* __restrict__ list_part, uint32_t* __restrict__ lp_out) {
+                                      uint32_t dmax, int rank, int world, const uint32_t* __restrict__ list_part, uint32_t* __restrict__ lp_out,
+                                      uint32_t* __restrict__ own) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
   const unsigned long long code = codes[c];
-  bool cross = false;
-  for (int r = 0; r < world && !cross; r++) {
+  bool cross = false, lower = false;
+  for (int r = 0; r < world && !cross; r++) {        // ranks in ascending order: the first hit tells whether a lower rank holds the word
     if (r == rank) continue;
     const unsigned long long* a = all + (size_t)r * dmax;
     uint32_t lo = 0, len = counts[2 * r];
     while (len > 0) { const uint32_t half = len >> 1; if (a[lo + half] < code) { lo += half + 1; len -= half + 1; } else len = half; }
     cross = lo < counts[2 * r] && a[lo] == code;
+    lower = cross && r < rank;
   }
   lp_out[c] = list_part[c] | (cross ? 0x80000000u : 0u);
+  own[c] = (cross && !lower) ? 1u : 0u;               // the lowest rank holding a cross word reports it
+}
+__global__ void dist_ownscatter_kernel(const unsigned long long* __restrict__ codes, uint32_t n, const uint32_t* __restrict__ own, const uint32_t* __restrict__ scan,
+                                       unsigned long long* __restrict__ out) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n && own[c]) out[scan[c]] = codes[c];
+}
+__global__ void dist_fill_kernel(unsigned long long* p, uint64_t n, unsigned long long v) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
 }
 __global__ void dist_padcodes_kernel(const unsigned long long* __restrict__ codes, uint32_t n, uint32_t dmax, unsigned long long pad, unsigned long long* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -567,7 +579,7 @@ extern "C" int msspe_dist_init(msspe_ctx* c, const uint8_t* id128, int rank, int
   NcclApi* api = nccl_api(&err);
   if (!api) { c->set_error("%s", err.c_str()); return MSSPE_ERR_STATE; }
   if (c->dist) { DistState* o = (DistState*)c->dist; if (api->CommDestroy) api->CommDestroy(o->comm); delete o; c->dist = nullptr; }
-  DistState* ds = new DistState{api, nullptr, rank, world};
+  DistState* ds = new DistState{api, nullptr, rank, world, 0u};
   ncclUniqueId id;
   memcpy(id.internal, id128, 128);
   ncclResult_t r = api->CommInitRank(&ds->comm, world, id, rank);
@@ -600,10 +612,12 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
   // (the verify window adapts to them); an input with many long cross-rank lists reports it on every rank in the same
   // round, and every rank retries with more rows
   int rc = MSSPE_OK;
-  for (uint32_t rows = DIST_XSTAGE; ; rows *= 4) {
+  if (!c->dist) { c->set_error("msspe_select_both_dist: msspe_dist_init first"); return MSSPE_ERR_STATE; }
+  DistState* ds0 = (DistState*)c->dist;
+  for (uint32_t rows = ds0->rows_hint ? ds0->rows_hint : DIST_XSTAGE; ; rows *= 4) {
     bool retry = false;
     rc = dist_select_impl(c, max_iter, mms, out_fwd, n_fwd, out_rev, n_rev, rows, &retry);
-    if (!(retry && rows < DIST_XCAP)) break;
+    if (!(retry && rows < DIST_XCAP)) { if (rc == MSSPE_OK) ds0->rows_hint = rows; break; }   // replicated outcome: every rank keeps the same hint
   }
   return rc;
 }
@@ -692,8 +706,18 @@ int dist_select_impl(msspe_ctx* c, uint32_t max_iter, uint32_t mms, msspe_candid
     for (int r = 0; r < world; r++) { cn[2 * r] = h_cnts[4 * r + d]; cn[2 * r + 1] = 0; }
     MSSPE_CUDA_TRY(c, cudaMemcpyAsync(d_cn, cn.data(), 8ull * world, cudaMemcpyHostToDevice, st));
     MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));   // cn goes out of scope
-    if (nc) dist_crossflag_kernel<<<(nc + 255u) / 256u, 256, 0, st>>>((const unsigned long long*)I.codes, nc, allc, d_cn, dmax[d], rank, world, I.list_part, lp_dist);
-    // partition view with the cross lists treated as multi-partition lists
+    uint32_t* own = nullptr; uint32_t* own_scan = nullptr; uint32_t* d_nown = nullptr; uint32_t* d_nowns = nullptr;
+    DA(own, ((uint64_t)nc + 1) * 4, 0); DA(own_scan, ((uint64_t)nc + 1) * 4, 0); DA(d_nown, 4, 0); DA(d_nowns, 4ull * world, 0);
+    if (nc) {
+      dist_crossflag_kernel<<<(nc + 255u) / 256u, 256, 0, st>>>((const unsigned long long*)I.codes, nc, allc, d_cn, dmax[d], rank, world, I.list_part, lp_dist, own);
+      int rc0 = msspe_exclusive_scan_u32(c, own, own_scan, nc, d_nown, st);
+      if (rc0) return rc0;
+    }
+    // the cross words themselves, identically on every rank: every word is reported by the lowest rank that holds it
+    MSSPE_NCCL_TRY(c, ds, N->AllGather(d_nown, d_nowns, 1, ncclUint32, ds->comm, st));
+    std::vector<uint32_t> h_nown(world);
+    MSSPE_CUDA_TRY(c, cudaMemcpyAsync(h_nown.data(), d_nowns, 4ull * world, cudaMemcpyDeviceToHost, st));
+    // partition view with the cross lists treated as multi-partition lists (its own synchronisations cover the copy above)
     I.pv_built = false;
     msspe_dev_free(c, I.pv_ucode_off); msspe_dev_free(c, I.pv_ucodes); msspe_dev_free(c, I.pv_fwdl); msspe_dev_free(c, I.pv_useg_off); msspe_dev_free(c, I.pv_usegs);
     I.pv_ucode_off = I.pv_ucodes = I.pv_fwdl = I.pv_useg_off = I.pv_usegs = nullptr;
@@ -703,25 +727,20 @@ int dist_select_impl(msspe_ctx* c, uint32_t max_iter, uint32_t mms, msspe_candid
     I.list_part = saved;
     I.pv_dist = true;
     if (rc) return rc;
-    // the cross words themselves, identically on every rank: sort all ranks' words, keep the duplicated ones
-    const uint32_t na = dmax[d] * (uint32_t)world;
-    uint64_t *ka = nullptr, *kb = nullptr; uint32_t *va = nullptr, *vb = nullptr; uint32_t* fl = nullptr; uint32_t* d_nx = nullptr;
-    DA(ka, (uint64_t)na * 8, -1); DA(kb, (uint64_t)na * 8, -1); DA(va, (uint64_t)na * 4, 0); DA(vb, (uint64_t)na * 4, 0); DA(fl, (uint64_t)na * 4, -1); DA(d_nx, 4, 0);
-    MSSPE_CUDA_TRY(c, cudaMemcpyAsync(ka, allc, (uint64_t)na * 8, cudaMemcpyDeviceToDevice, st));
-    rc = msspe_radix_sort_pairs(c, &ka, &va, &kb, &vb, na, kbits + 1, st);
-    if (rc) return rc;
-    dist_dupflag_kernel<<<(na + 255u) / 256u, 256, 0, st>>>(ka, na, pad, fl);
-    rc = msspe_exclusive_scan_u32(c, fl, fl, na, d_nx, st);
-    if (rc) return rc;
-    uint32_t n_x = 0;
-    MSSPE_CUDA_TRY(c, cudaMemcpyAsync(&n_x, d_nx, 4, cudaMemcpyDeviceToHost, st));
     MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+    uint32_t n_x = 0, own_max = 1;
+    for (int r = 0; r < world; r++) { n_x += h_nown[r]; own_max = std::max(own_max, h_nown[r]); }
     Q.n_x = n_x;
     max_nx = std::max(max_nx, n_x);
-    unsigned long long* xcodes = nullptr;
-    DA(xcodes, ((uint64_t)n_x + 1) * 8, -1);
-    dist_dupscatter_kernel<<<(na + 255u) / 256u, 256, 0, st>>>(ka, na, pad, fl, xcodes);
-    Q.xcodes = xcodes;
+    const uint32_t na = own_max * (uint32_t)world;
+    unsigned long long* own_send = nullptr; uint64_t *ka = nullptr, *kb = nullptr; uint32_t *va = nullptr, *vb = nullptr;
+    DA(own_send, (uint64_t)own_max * 8, -1); DA(ka, (uint64_t)na * 8, -1); DA(kb, (uint64_t)na * 8, -1); DA(va, (uint64_t)na * 4, 0); DA(vb, (uint64_t)na * 4, 0);
+    dist_fill_kernel<<<(own_max + 255u) / 256u, 256, 0, st>>>(own_send, own_max, pad);
+    if (nc) dist_ownscatter_kernel<<<(nc + 255u) / 256u, 256, 0, st>>>((const unsigned long long*)I.codes, nc, own, own_scan, own_send);
+    MSSPE_NCCL_TRY(c, ds, N->AllGather(own_send, ka, own_max, ncclUint64, ds->comm, st));
+    rc = msspe_radix_sort_pairs(c, &ka, &va, &kb, &vb, na, kbits + 1, st);   // the paddings sort behind every word
+    if (rc) return rc;
+    Q.xcodes = reinterpret_cast<const unsigned long long*>(ka);             // first n_x entries
     // ---- 3. state of the loop (as on one GPU) + the replicated view + exchange buffers ----
     if (I.out_capacity < max_iter) {
       msspe_dev_free(c, I.out); I.out = nullptr;
