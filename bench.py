@@ -517,8 +517,7 @@ def main():
         try:
             with open(os.path.join(ROOT, "profiles", "r2_dominant_kernel_traffic.json")) as f:
                 tj = json.load(f)
-            if tj.get("kernel") == dom["kernel"]:
-                traffic = tj.get("dram_bytes_per_launch")
+            traffic = tj.get("kernels", {}).get(dom["kernel"], {}).get("dram_bytes_per_launch")
         except Exception:
             pass
         lp = max(1, dom["launches_per_step"])

@@ -922,6 +922,7 @@ int dist_select_impl(msspe_ctx* c, uint32_t max_iter, uint32_t mms, msspe_candid
     if (n) MSSPE_CUDA_TRY(c, cudaMemcpyAsync(outs[d], c->dir[d].out, (size_t)n * sizeof(msspe_candidate), cudaMemcpyDeviceToHost, st));
     *ns[d] = n;
     c->timing.select_evals[d] = h[d].evals;
+    c->kprof[KP_GREEDY_UNIT].bytes += h[d].work_bytes;
     c->timing.select_iterations[d] = h[d].iterations;
     c->timing.select_postings_read[d] = c->dir[d].n_records;
   }

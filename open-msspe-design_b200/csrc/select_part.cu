@@ -240,6 +240,7 @@ int msspe_select_partitioned(msspe_ctx* c, int ndirs, const int* dirs, uint32_t 
     if (n) MSSPE_CUDA_TRY(c, cudaMemcpyAsync(outs[i], c->dir[d].out, (size_t)n * sizeof(msspe_candidate), cudaMemcpyDeviceToHost, st));
     *n_outs[i] = n;
     c->timing.select_evals[d] = h[i].evals;
+    c->kprof[KP_GREEDY_UNIT].bytes += h[i].work_bytes;
     c->timing.select_iterations[d] = h[i].iterations;
     c->timing.select_postings_read[d] = c->dir[d].n_records;   // the forward index is read about once (counts) + once (decrements)
   }

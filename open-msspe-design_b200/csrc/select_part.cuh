@@ -29,7 +29,9 @@ struct PartCtl {
   uint32_t E, H, cutbound, V, terminal, do_terminal, fmin, t_hi;
   uint32_t n_stage, n_viol, vmin, n_ext;
   uint32_t rounds, rollbacks, wmax, last_viol;
-  uint32_t clipped, tq, tq_next, pad2;   // multi-GPU loop: iteration whose tie scores need the first-seen order of the partitions (pending / next)
+  uint32_t clipped, tq, tq_next, pad2;
+  unsigned long long work_bytes;   // algorithmic bytes of the unit kernel: 4 B per k-mer count scanned, 8 B per posting of a winner (id + cover
+                                   // token), 4 B per forward-index record taken out of (or put back into) the live counts   // multi-GPU loop: iteration whose tie scores need the first-seen order of the partitions (pending / next)
 };
 
 struct PartDir {
@@ -101,7 +103,7 @@ struct ExPart { unsigned long long key; long long delta; uint32_t cnt; uint32_t 
 template <int C>
 __device__ __forceinline__ void cluster_sync_all() {
   if (C == 1) __syncthreads();
-  else { __threadfence(); cg::this_cluster().sync(); }
+  else cg::this_cluster().sync();   // barrier.cluster arrive.release / wait.acquire: the CTAs' global atomics are ordered by it
 }
 
 // s_ex[par][r] of every CTA <- this CTA's part; after the barrier every CTA holds all C parts
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(EXT_T) part_extend_kernel(PartArgs A) {
   bool finished = (st & ST_FINISHED) != 0;
   int par = 0;
   long long delta = 0;                                        // records this CTA took out of the live count, not yet exchanged
+  unsigned long long work = 0;                                // algorithmic bytes (counted by CTA 0 of the cluster)
   if (C > 1) cg::this_cluster().sync();                       // nobody pushes into a CTA that has not started yet
   if (st & ST_ROLLBACK) {
     // back to the unit's state at the external winner's iteration: segments covered by the truncated entries live again,
@@ -195,7 +198,8 @@ __global__ void __launch_bounds__(EXT_T) part_extend_kernel(PartArgs A) {
     }
     delta = (long long)block_sum_u64<EXT_T>((unsigned long long)delta, sh);
     exchange<C>(s_ex, par, rank, 0ull, 0u, delta);
-    for (int rr = 0; rr < C; rr++) live -= s_ex[par][rr].delta;
+    for (int rr = 0; rr < C; rr++) { const long long dd = s_ex[par][rr].delta; live -= dd; work += 4ull * (unsigned long long)(dd < 0 ? -dd : dd); }
+    work += 4ull * (g1 - g0);
     par ^= 1; delta = 0;
   }
   const uint32_t rf0 = D.rfin[u];
@@ -241,9 +245,10 @@ __global__ void __launch_bounds__(EXT_T) part_extend_kernel(PartArgs A) {
     }
     exchange<C>(s_ex, par, rank, bk, bc, delta);      // + what the previous step took out of the live records
     unsigned long long wk = 0ull; uint32_t wc = 0u;
+    work += 4ull * (o1 - o0);
     for (int rr = 0; rr < C; rr++) {
       const ExPart e = s_ex[par][rr];
-      live -= e.delta;
+      live -= e.delta; work += 4ull * (unsigned long long)e.delta;
       if (!e.cnt) continue;
       const uint32_t f = (uint32_t)(e.key >> 32), bf = (uint32_t)(wk >> 32);
       if (wc == 0u || f > bf) { wk = e.key; wc = e.cnt; }
@@ -257,6 +262,7 @@ __global__ void __launch_bounds__(EXT_T) part_extend_kernel(PartArgs A) {
     const uint32_t slot = slot0 + len;
     if (rank == 0 && tid == 0) { PEntry e; e.freq = fmax; e.cid = cid; e.tied = wc; e.pad = 0u; e.live_before = (unsigned long long)live; e.code = D.codes[cid]; D.entries[slot] = e; }
     const uint32_t pb = D.post_off[cid], pe = D.post_off[cid + 1];
+    work += 8ull * (pe - pb);
     const uint32_t share = (pe - pb + C - 1) / C;      // an equal share of the winner's postings for every CTA of the cluster
     const uint32_t mb = min(pe, pb + rank * share), me = min(pe, mb + share);
     for (uint32_t b = mb; b < me; b += NEWCAP) {       // main.rs:371-378 for this unit: cover the winner's live segments ...
@@ -277,8 +283,8 @@ __global__ void __launch_bounds__(EXT_T) part_extend_kernel(PartArgs A) {
     if (fmax < A.mms) { finished = true; break; }   // pushed, then break (main.rs:387-390)
   }
   exchange<C>(s_ex, par, rank, 0ull, 0u, delta);      // the last step's share of the live records
-  for (int rr = 0; rr < C; rr++) live -= s_ex[par][rr].delta;
-  if (rank == 0 && tid == 0) { D.ulen[u] = len; D.ulive[u] = (unsigned long long)live; D.status[u] = finished ? ST_FINISHED : 0u; }
+  for (int rr = 0; rr < C; rr++) { live -= s_ex[par][rr].delta; work += 4ull * (unsigned long long)s_ex[par][rr].delta; }
+  if (rank == 0 && tid == 0) { D.ulen[u] = len; D.ulive[u] = (unsigned long long)live; D.status[u] = finished ? ST_FINISHED : 0u; atomicAdd(&D.ctl->work_bytes, work); }
   if (C > 1) cg::this_cluster().sync();               // no CTA exits while a peer may still push into its shared memory
 }
 

@@ -884,11 +884,10 @@ int launch_mono(msspe_ctx* c, const uint64_t* d_codes, uint32_t n, int k, const 
   if (smem_ok) {
     const size_t smem = (size_t)per_block * sizeof(MonoWork);
     MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(thal_mono_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    thal_mono_kernel<<<(n + per_block - 1) / per_block, per_block, smem, st>>>(d_codes, n, k, T, K.saltCorr, K.t_user_K, K.maxLoop, nullptr, out);
+    { KPROF(c, KP_THERMO, st, (uint64_t)n * 56) thal_mono_kernel<<<(n + per_block - 1) / per_block, per_block, smem, st>>>(d_codes, n, k, T, K.saltCorr, K.t_user_K, K.maxLoop, nullptr, out); }
   } else {
-    thal_mono_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_codes, n, k, T, K.saltCorr, K.t_user_K, K.maxLoop, work, out);
+    { KPROF(c, KP_THERMO, st, (uint64_t)n * 56) thal_mono_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_codes, n, k, T, K.saltCorr, K.t_user_K, K.maxLoop, work, out); }
   }
-  c->timing.kernel_launches++;
   MSSPE_CUDA_TRY(c, cudaGetLastError());
   return MSSPE_OK;
 }
