@@ -485,13 +485,17 @@ thal_dimer_kernel(const DimerArgs A) {
 constexpr int MONO_MAX = MSSPE_MAX_OLIGO;
 constexpr int MIN_HRPN_LOOP = 3;
 
-struct MonoWork {
-  int n1[MONO_MAX + 2];
+// M = largest oligo the scratch holds: 16 for the 13-16-mers of the pipeline (5.6 KB per thread: 2000 primers fit one wave
+// of shared-memory blocks), 32 for the general entry points
+template <int M>
+struct MonoWorkT {
+  int n1[M + 2];
   int len;
-  double Sm[MONO_MAX + 2][MONO_MAX + 2], Hm[MONO_MAX + 2][MONO_MAX + 2];
-  double send5[MONO_MAX + 2], hend5[MONO_MAX + 2];
+  double Sm[M + 2][M + 2], Hm[M + 2][M + 2];
+  double send5[M + 2], hend5[M + 2];
   int maxLoop;
 };
+using MonoWork = MonoWorkT<MONO_MAX>;
 // dplx_init_H = 0, dplx_init_S = -1e-11, RC = 0 for unimolecular folding
 #define M_DHI 0.0
 #define M_DSI (-0.00000000001)
@@ -499,12 +503,14 @@ struct MonoWork {
 
 __device__ __forceinline__ bool m_bp(int a, int b) { return a + b == 3 && a < 4 && b < 4; }
 
-__device__ double m_Ss(const ThalDeviceTables* T, const MonoWork& w, int i, int j) {
+template <class WK>
+__device__ double m_Ss(const ThalDeviceTables* T, const WK& w, int i, int j) {
   if (i >= j) return -1.0;
   if (i == w.len || j == w.len + 1) return -1.0;
   return T->stackS[THAL_IDX4(w.n1[i], w.n1[i + 1], w.n1[j], w.n1[j - 1])];
 }
-__device__ double m_Hs(const ThalDeviceTables* T, const MonoWork& w, int i, int j) {
+template <class WK>
+__device__ double m_Hs(const ThalDeviceTables* T, const WK& w, int i, int j) {
   if (i >= j) return INFINITY;
   if (i == w.len || j == w.len + 1) return INFINITY;
   const double h = T->stackH[THAL_IDX4(w.n1[i], w.n1[i + 1], w.n1[j], w.n1[j - 1])];
@@ -521,7 +527,8 @@ __device__ bool m_find(const uint32_t* keys, const double* vals, int n, uint32_t
   return false;
 }
 
-__device__ void m_hairpin_loop(const ThalDeviceTables* T, const MonoWork& w, int i, int j, double* S, double* H, int tb) {
+template <class WK>
+__device__ void m_hairpin_loop(const ThalDeviceTables* T, const WK& w, int i, int j, double* S, double* H, int tb) {
   const int* n1 = w.n1;
   const int loopSize = j - i - 1;
   if (loopSize < MIN_HRPN_LOOP) { *S = -1.0; *H = INFINITY; return; }
@@ -555,7 +562,8 @@ __device__ void m_hairpin_loop(const ThalDeviceTables* T, const MonoWork& w, int
   if (T1 < T2 && tb == 0) { *S = w.Sm[i][j]; *H = w.Hm[i][j]; }
 }
 
-__device__ void m_bulge_internal(const ThalDeviceTables* T, const MonoWork& w, int i, int j, int ii, int jj, double* outS,
+template <class WK>
+__device__ void m_bulge_internal(const ThalDeviceTables* T, const WK& w, int i, int j, int ii, int jj, double* outS,
                                  double* outH, int tb) {
   const int* n1 = w.n1;
   const int l1 = ii - i - 1, l2 = j - jj - 1;
@@ -601,7 +609,8 @@ __device__ void m_bulge_internal(const ThalDeviceTables* T, const MonoWork& w, i
   }
 }
 
-__device__ void m_loops(const ThalDeviceTables* T, MonoWork& w, int i, int j, double* S, double* H, int tb) {
+template <class WK>
+__device__ void m_loops(const ThalDeviceTables* T, WK& w, int i, int j, double* S, double* H, int tb) {
   for (int d = j - i - 3; d >= MIN_HRPN_LOOP + 1 && d >= j - i - 2 - w.maxLoop; --d)
     for (int ii = i + 1; ii < j - d && ii <= w.len; ++ii) {
       const int jj = d + ii;
@@ -617,7 +626,8 @@ __device__ void m_loops(const ThalDeviceTables* T, MonoWork& w, int i, int j, do
 }
 
 // exterior-fragment recursion: variant 1 = plain pair (k+1,i); 2 = 5' dangle; 3 = 3' dangle; 4 = terminal mismatch
-__device__ void m_end5_term(const ThalDeviceTables* T, const MonoWork& w, int i, int k, int variant, double* eS, double* eH) {
+template <class WK>
+__device__ void m_end5_term(const ThalDeviceTables* T, const WK& w, int i, int k, int variant, double* eS, double* eH) {
   const int* n1 = w.n1;
   switch (variant) {
     case 1: *eH = T->atpH[n1[k + 1] * 5 + n1[i]] + w.Hm[k + 1][i]; *eS = T->atpS[n1[k + 1] * 5 + n1[i]] + w.Sm[k + 1][i]; break;
@@ -632,7 +642,8 @@ __device__ void m_end5_term(const ThalDeviceTables* T, const MonoWork& w, int i,
 __device__ __forceinline__ int m_end5_kmax(int i, int variant) {
   return variant == 1 ? i - MIN_HRPN_LOOP - 2 : (variant == 4 ? i - MIN_HRPN_LOOP - 4 : i - MIN_HRPN_LOOP - 3);
 }
-__device__ void m_end5(const ThalDeviceTables* T, const MonoWork& w, int i, int variant, double* outH, double* outS) {
+template <class WK>
+__device__ void m_end5(const ThalDeviceTables* T, const WK& w, int i, int variant, double* outH, double* outS) {
   double H_max = INFINITY, S_max = -1.0, max_tm = -INFINITY;
   const int kmax = m_end5_kmax(i, variant);
   for (int k = 0; k <= kmax; ++k) {
@@ -650,7 +661,8 @@ __device__ void m_end5(const ThalDeviceTables* T, const MonoWork& w, int i, int 
   *outH = H_max; *outS = S_max;
 }
 
-__device__ void mono_run(const ThalDeviceTables* T, MonoWork& w, double saltCorr, double temp_K, msspe_thal_out* out) {
+template <class WK>
+__device__ void mono_run(const ThalDeviceTables* T, WK& w, double saltCorr, double temp_K, msspe_thal_out* out) {
   const int* n1 = w.n1;
   const int len = w.len;
   out->ds = 0; out->dh = 0; out->dg = 0; out->tm = 0; out->no_structure = 1; out->n_bp = 0;
@@ -769,16 +781,17 @@ __device__ void mono_run(const ThalDeviceTables* T, MonoWork& w, double saltCorr
   out->no_structure = 0;
 }
 
+template <int M>
 __global__ void __launch_bounds__(64)
 thal_mono_kernel(const uint64_t* __restrict__ codes, uint32_t n, int k, const ThalDeviceTables* T, double saltCorr, double temp_K,
-                 int maxLoop, MonoWork* work, msspe_thal_out* out) {
+                 int maxLoop, MonoWorkT<M>* work, msspe_thal_out* out) {
   // One thread per oligo (<= 2000 per run: latency, not throughput).  The DP matrices of the thread live in SHARED
   // memory when the launch provides it (MONO_SMEM_THREADS threads per block, one MonoWork each): the scalar recursion
   // is a chain of dependent matrix reads, ~30 cycles each from shared memory against ~600 from a per-thread global scratch.
   extern __shared__ __align__(16) unsigned char mono_smem[];
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  MonoWork& w = work ? work[t] : reinterpret_cast<MonoWork*>(mono_smem)[threadIdx.x];
+  MonoWorkT<M>& w = work ? work[t] : reinterpret_cast<MonoWorkT<M>*>(mono_smem)[threadIdx.x];
   const uint64_t c = codes[t];
   w.len = k; w.maxLoop = maxLoop;
   for (int x = 0; x < k; x++) w.n1[x + 1] = (int)((c >> (2 * (k - 1 - x))) & 3u);
@@ -877,19 +890,30 @@ int launch_dimer(msspe_ctx* c, DimerArgs& A, cudaStream_t st) {
 
 // Hairpin launch: the per-thread DP scratch in shared memory (as many threads per block as fit) when that keeps the
 // whole batch in one wave of blocks, else the global scratch `work` with 64-thread blocks.
-int launch_mono(msspe_ctx* c, const uint64_t* d_codes, uint32_t n, int k, const ThalDimerConsts& K, MonoWork* work, msspe_thal_out* out,
-                cudaStream_t st, const ThalDeviceTables* T) {
-  const int per_block = (int)((c->smem_optin - 1024) / sizeof(MonoWork));
+template <int M>
+int launch_mono_m(msspe_ctx* c, const uint64_t* d_codes, uint32_t n, int k, const ThalDimerConsts& K, void* work, msspe_thal_out* out,
+                  cudaStream_t st, const ThalDeviceTables* T) {
+  int per_block = (int)((c->smem_optin - 1024) / sizeof(MonoWorkT<M>));
+  if (per_block > 64) per_block = 64;    // __launch_bounds__(64)
   const bool smem_ok = per_block >= 1 && !getenv("MSSPE_MONO_GLOBAL") && (uint64_t)n <= (uint64_t)per_block * (uint64_t)c->sm_count;  // one wave (measured: 0.49 vs 0.65 ms at 600, slower beyond one wave)
   if (smem_ok) {
-    const size_t smem = (size_t)per_block * sizeof(MonoWork);
-    MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(thal_mono_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { KPROF(c, KP_THERMO, st, (uint64_t)n * 56) thal_mono_kernel<<<(n + per_block - 1) / per_block, per_block, smem, st>>>(d_codes, n, k, T, K.saltCorr, K.t_user_K, K.maxLoop, nullptr, out); }
+    // spread the batch over all SMs: fewer threads per block than fit, so that every SM gets a block
+    int tpb = (int)((n + (uint32_t)c->sm_count - 1) / (uint32_t)c->sm_count);
+    if (tpb < 1) tpb = 1;
+    if (tpb > per_block) tpb = per_block;
+    const size_t smem = (size_t)tpb * sizeof(MonoWorkT<M>);
+    MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(thal_mono_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { KPROF(c, KP_THERMO, st, (uint64_t)n * 56) thal_mono_kernel<M><<<(n + tpb - 1) / tpb, tpb, smem, st>>>(d_codes, n, k, T, K.saltCorr, K.t_user_K, K.maxLoop, nullptr, out); }
   } else {
-    { KPROF(c, KP_THERMO, st, (uint64_t)n * 56) thal_mono_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_codes, n, k, T, K.saltCorr, K.t_user_K, K.maxLoop, work, out); }
+    { KPROF(c, KP_THERMO, st, (uint64_t)n * 56) thal_mono_kernel<M><<<(n + 63) / 64, 64, 0, st>>>(d_codes, n, k, T, K.saltCorr, K.t_user_K, K.maxLoop, (MonoWorkT<M>*)work, out); }
   }
   MSSPE_CUDA_TRY(c, cudaGetLastError());
   return MSSPE_OK;
+}
+// `work` holds n x sizeof(MonoWork) bytes (the largest scratch)
+int launch_mono(msspe_ctx* c, const uint64_t* d_codes, uint32_t n, int k, const ThalDimerConsts& K, MonoWork* work, msspe_thal_out* out,
+                cudaStream_t st, const ThalDeviceTables* T) {
+  return k <= 16 ? launch_mono_m<16>(c, d_codes, n, k, K, work, out, st, T) : launch_mono_m<MONO_MAX>(c, d_codes, n, k, K, work, out, st, T);
 }
 
 int check_thal_args(msspe_ctx* c, uint32_t oligo_len, const msspe_thal_cond* cond) {
