@@ -56,16 +56,40 @@ encode_keys_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict
   const uint64_t j = g - seg_base[lo];
   const uint64_t win = offsets[lo] + j * (uint64_t)S;
   const uint64_t src = DIR == 0 ? win : win + (W - w);
-  for (uint32_t t = lane; t < w; t += 32) sb[t] = (uint8_t)base2f(bases[src + t]);
   if (DIR == 0 && lane == 0) { seg_part[g] = (uint16_t)j; seg_rec[g] = lo; }
-  __syncwarp();
+  // search windows of up to 64 bases (the reference's default is 50): the window as ONE packed 2-bit string in registers
+  // (position p of the window at bits [126 - 2p, 127 - 2p] of ph:pl) plus a 64-bit mask of its non-ACGT positions, built
+  // with warp OR-reductions; a slot's word is then a funnel shift, its validity a mask test -- no per-base loop
+  const bool packed = w <= 64u;
+  unsigned long long ph = 0ull, pl = 0ull, inv = 0ull;
+  if (packed) {
+    const uint32_t v0 = lane < w ? base2f(bases[src + lane]) : 0u;
+    const uint32_t v1 = lane + 32u < w ? base2f(bases[src + lane + 32u]) : 0u;
+    const unsigned long long c0 = (unsigned long long)(v0 & 3u) << (62 - 2 * lane), c1 = (unsigned long long)(v1 & 3u) << (62 - 2 * lane);
+    const uint32_t i0 = (v0 > 3u ? 1u : 0u) << (31 - lane), i1 = (v1 > 3u ? 1u : 0u) << (31 - lane);
+    ph = ((unsigned long long)__reduce_or_sync(0xffffffffu, (uint32_t)(c0 >> 32)) << 32) | __reduce_or_sync(0xffffffffu, (uint32_t)c0);
+    pl = ((unsigned long long)__reduce_or_sync(0xffffffffu, (uint32_t)(c1 >> 32)) << 32) | __reduce_or_sync(0xffffffffu, (uint32_t)c1);
+    inv = ((unsigned long long)__reduce_or_sync(0xffffffffu, i0) << 32) | __reduce_or_sync(0xffffffffu, i1);
+  } else {
+    for (uint32_t t = lane; t < w; t += 32) sb[t] = (uint8_t)base2f(bases[src + t]);
+    __syncwarp();
+  }
   for (uint32_t q0 = 0; q0 < slots; q0 += 32) {
     const uint32_t q = q0 + lane;
     unsigned long long code = KEY_NONE;
     if (q < slots) {
       unsigned long long cd = 0; bool ok = true;
-      if (DIR == 0) { for (uint32_t t = 0; t < k; t++) { const uint32_t b = sb[q + t]; ok &= (b < 4u); cd = (cd << 2) | (b & 3u); } }
-      else { for (uint32_t t = 0; t < k; t++) { const uint32_t b = sb[q + k - 1 - t]; ok &= (b < 4u); cd = (cd << 2) | ((3u - b) & 3u); } }  // reverse complement (main.rs:148-161)
+      if (packed) {
+        const unsigned long long x = q == 0u ? ph : (q < 32u ? ((ph << (2u * q)) | (pl >> (64u - 2u * q))) : (pl << (2u * (q - 32u))));
+        cd = x >> (64u - 2u * k);                                  // bases q .. q + k - 1, first base in the top bits
+        ok = ((inv << q) >> (64u - k)) == 0ull;                    // none of them is a non-ACGT position
+        if (DIR == 1) {                                            // reverse complement (main.rs:148-161): complement, reverse the 2-bit groups
+          const unsigned long long comp = (~cd) & ((k == 32u) ? ~0ull : ((1ull << (2u * k)) - 1ull));
+          unsigned long long r = __brevll(comp) >> (64u - 2u * k);
+          cd = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+        }
+      } else if (DIR == 0) { for (uint32_t t = 0; t < k; t++) { const uint32_t b = sb[q + t]; ok &= (b < 4u); cd = (cd << 2) | (b & 3u); } }
+      else { for (uint32_t t = 0; t < k; t++) { const uint32_t b = sb[q + k - 1 - t]; ok &= (b < 4u); cd = (cd << 2) | ((3u - b) & 3u); } }  // reverse complement
       if (ok) code = cd;
     }
     // first occurrence inside the window: earlier lanes of this round, then the rounds before

@@ -123,7 +123,7 @@ def test_load_fasta_pageable_and_pinned_paths(tmp_path, pinned, monkeypatch):
         body = ("\r\n" if i % 5 == 0 else "\n").join(seq[j:j + wrap] for j in range(0, len(seq), wrap))
         lines.append(">rec%d some description\n%s\n" % (i, body))
     data = "".join(lines).encode()
-    assert len(data) > 100 << 20
+    assert len(data) > 3 * (32 << 20)      # more than three 32 MB chunks
     p = tmp_path / "big.fa"
     p.write_bytes(data)
     recs = ko.to_records(data)
