@@ -22,7 +22,7 @@
 namespace {
 
 constexpr int ENCF_WARPS = 8;
-constexpr int SORT_T = 256, SORT_ITEMS = 16, SORT_TILE = SORT_T * SORT_ITEMS, SORT_WARPS = SORT_T / 32;
+constexpr int SORT_T = 512, SORT_ITEMS = 8, SORT_TILE = SORT_T * SORT_ITEMS, SORT_WARPS = SORT_T / 32;
 constexpr unsigned long long KEY_NONE = ~0ull;
 
 __device__ __forceinline__ uint32_t base2f(uint8_t c) {
@@ -35,7 +35,100 @@ __device__ __forceinline__ uint32_t base2f(uint8_t c) {
   }
 }
 
-// dynamic smem per warp: slots_pad u64 codes + w bytes
+// Packed path (search windows of up to 64 bases; the reference's default is 50): no shared memory.  A warp takes
+// ENC_SEGS consecutive segments with all their loads issued first; a window is ONE packed 2-bit string in registers
+// (position p at bits [126 - 2p, 127 - 2p] of ph:pl, built with warp OR-reductions) so that a slot's word is a funnel
+// shift, plus three 64-bit planes over the positions (low bit, high bit, is-ACGT; ballots).  Lane l owns slots l and
+// l + 32.  A slot is valid when k consecutive positions are ACGT (a run test on the third plane).  The first occurrence
+// inside the window (itertools unique()) needs no comparison of words: the word at slot q + d repeats the word at slot
+// q exactly when the window equals itself shifted by d over k consecutive positions, so lane l tests the distances
+// l + 1 and l + 33 with shifts and ANDs on the planes and one OR-reduction merges the verdicts.  (__match_any_sync on
+// the 64-bit words cost 128 SM cycles per segment here: 2 cycles per distinct value, measured, tools/microbench.)
+constexpr int ENC_SEGS = 4;
+
+__device__ __forceinline__ uint32_t base2p(uint32_t c) {   // A0 C1 G2 T3 (U = T), 4 = anything else; either case
+  const uint32_t lc = c | 0x20u;
+  const bool ok = lc == 'a' || lc == 'c' || lc == 'g' || lc == 't' || lc == 'u';
+  const uint32_t x = (c >> 1) & 3u;
+  return ok ? (x ^ (x >> 1)) : 4u;
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(ENCF_WARPS * 32)
+encode_keys_packed_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, const uint64_t* __restrict__ seg_base,
+                          uint32_t n_records, uint32_t uniform_parts, uint64_t n_segments, uint32_t W, uint32_t S, uint32_t w, uint32_t k,
+                          uint32_t slots, uint32_t idx_bits, unsigned long long* __restrict__ keys, uint16_t* __restrict__ seg_part,
+                          uint32_t* __restrict__ seg_rec) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t gw = ((uint64_t)blockIdx.x * ENCF_WARPS + (threadIdx.x >> 5)) * ENC_SEGS;
+  if (gw >= n_segments) return;
+  uint32_t v0[ENC_SEGS], v1[ENC_SEGS];
+#pragma unroll
+  for (int s = 0; s < ENC_SEGS; s++) {
+    const uint64_t g = gw + s;
+    v0[s] = v1[s] = 'N';
+    if (g < n_segments) {
+      uint32_t lo = 0, hi = n_records;
+      uint64_t j;
+      if (uniform_parts) { lo = (uint32_t)(g / uniform_parts); j = g - (uint64_t)lo * uniform_parts; }
+      else { while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (seg_base[mid] <= g) lo = mid; else hi = mid; } j = g - seg_base[lo]; }
+      const uint64_t win = offsets[lo] + j * (uint64_t)S;
+      const uint64_t src = DIR == 0 ? win : win + (W - w);
+      if (DIR == 0 && lane == 0) { seg_part[g] = (uint16_t)j; seg_rec[g] = lo; }
+      if (lane < w) v0[s] = bases[src + lane];
+      if (lane + 32u < w) v1[s] = bases[src + lane + 32u];
+    }
+  }
+  const unsigned long long kmask = (k == 32u) ? ~0ull : ((1ull << (2u * k)) - 1ull);
+  // bit p of run_k(m): m has ones at p .. p + k - 1
+  auto run_k = [k](unsigned long long m) {
+    uint32_t len = 1;
+    while (2u * len <= k) { m &= m >> len; len *= 2u; }
+    if (len < k) m &= m >> (k - len);
+    return m;
+  };
+#pragma unroll
+  for (int s = 0; s < ENC_SEGS; s++) {
+    const uint64_t g = gw + s;
+    if (g >= n_segments) break;                                  // uniform over the warp
+    const uint32_t b0 = lane < w ? base2p(v0[s]) : 4u, b1 = lane + 32u < w ? base2p(v1[s]) : 4u;
+    const unsigned long long c0 = (unsigned long long)(b0 & 3u) << (62 - 2 * lane), c1 = (unsigned long long)(b1 & 3u) << (62 - 2 * lane);
+    const unsigned long long ph = ((unsigned long long)__reduce_or_sync(0xffffffffu, (uint32_t)(c0 >> 32)) << 32) | __reduce_or_sync(0xffffffffu, (uint32_t)c0);
+    const unsigned long long pl = ((unsigned long long)__reduce_or_sync(0xffffffffu, (uint32_t)(c1 >> 32)) << 32) | __reduce_or_sync(0xffffffffu, (uint32_t)c1);
+    // planes, position p at bit p
+    const unsigned long long lo = ((unsigned long long)__ballot_sync(0xffffffffu, b1 & 1u) << 32) | __ballot_sync(0xffffffffu, b0 & 1u);
+    const unsigned long long hi = ((unsigned long long)__ballot_sync(0xffffffffu, b1 & 2u) << 32) | __ballot_sync(0xffffffffu, b0 & 2u);
+    const unsigned long long val = ((unsigned long long)__ballot_sync(0xffffffffu, b1 < 4u) << 32) | __ballot_sync(0xffffffffu, b0 < 4u);
+    const unsigned long long okm = run_k(val);                     // slots whose k positions are all ACGT (main.rs:163-171)
+    unsigned long long dup = 0ull;                                 // slots that repeat an earlier slot's word
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const uint32_t dist = lane + 1u + 32u * h;
+      if (dist < slots) {
+        const unsigned long long eq = ~((lo ^ (lo >> dist)) | (hi ^ (hi >> dist))) & val & (val >> dist);   // position p equals position p + dist
+        dup |= run_k(eq) << dist;
+      }
+    }
+    dup = ((unsigned long long)__reduce_or_sync(0xffffffffu, (uint32_t)(dup >> 32)) << 32) | __reduce_or_sync(0xffffffffu, (uint32_t)dup);
+    const unsigned long long keepm = okm & ~dup;
+    const unsigned long long rec = g * slots + lane;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const uint32_t q = lane + 32u * h;
+      if (q < slots) {
+        const unsigned long long x = h ? (pl << (2u * lane)) : (lane == 0u ? ph : ((ph << (2u * lane)) | (pl >> (64u - 2u * lane))));
+        unsigned long long cd = x >> (64u - 2u * k);               // bases q .. q + k - 1, first base in the top bits
+        if (DIR == 1) {                                            // reverse complement (main.rs:148-161): complement, reverse the 2-bit groups
+          const unsigned long long r = __brevll((~cd) & kmask) >> (64u - 2u * k);
+          cd = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+        }
+        keys[rec + 32u * h] = ((keepm >> q) & 1ull) ? ((cd << idx_bits) | (rec + 32u * h)) : KEY_NONE;
+      }
+    }
+  }
+}
+
+// General path (search windows longer than 64 bases).  dynamic smem per warp: slots_pad u64 codes + w bytes
 template <int DIR>
 __global__ void __launch_bounds__(ENCF_WARPS * 32)
 encode_keys_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, const uint64_t* __restrict__ seg_base,
@@ -57,38 +150,14 @@ encode_keys_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict
   const uint64_t win = offsets[lo] + j * (uint64_t)S;
   const uint64_t src = DIR == 0 ? win : win + (W - w);
   if (DIR == 0 && lane == 0) { seg_part[g] = (uint16_t)j; seg_rec[g] = lo; }
-  // search windows of up to 64 bases (the reference's default is 50): the window as ONE packed 2-bit string in registers
-  // (position p of the window at bits [126 - 2p, 127 - 2p] of ph:pl) plus a 64-bit mask of its non-ACGT positions, built
-  // with warp OR-reductions; a slot's word is then a funnel shift, its validity a mask test -- no per-base loop
-  const bool packed = w <= 64u;
-  unsigned long long ph = 0ull, pl = 0ull, inv = 0ull;
-  if (packed) {
-    const uint32_t v0 = lane < w ? base2f(bases[src + lane]) : 0u;
-    const uint32_t v1 = lane + 32u < w ? base2f(bases[src + lane + 32u]) : 0u;
-    const unsigned long long c0 = (unsigned long long)(v0 & 3u) << (62 - 2 * lane), c1 = (unsigned long long)(v1 & 3u) << (62 - 2 * lane);
-    const uint32_t i0 = (v0 > 3u ? 1u : 0u) << (31 - lane), i1 = (v1 > 3u ? 1u : 0u) << (31 - lane);
-    ph = ((unsigned long long)__reduce_or_sync(0xffffffffu, (uint32_t)(c0 >> 32)) << 32) | __reduce_or_sync(0xffffffffu, (uint32_t)c0);
-    pl = ((unsigned long long)__reduce_or_sync(0xffffffffu, (uint32_t)(c1 >> 32)) << 32) | __reduce_or_sync(0xffffffffu, (uint32_t)c1);
-    inv = ((unsigned long long)__reduce_or_sync(0xffffffffu, i0) << 32) | __reduce_or_sync(0xffffffffu, i1);
-  } else {
-    for (uint32_t t = lane; t < w; t += 32) sb[t] = (uint8_t)base2f(bases[src + t]);
-    __syncwarp();
-  }
+  for (uint32_t t = lane; t < w; t += 32) sb[t] = (uint8_t)base2f(bases[src + t]);
+  __syncwarp();
   for (uint32_t q0 = 0; q0 < slots; q0 += 32) {
     const uint32_t q = q0 + lane;
     unsigned long long code = KEY_NONE;
     if (q < slots) {
       unsigned long long cd = 0; bool ok = true;
-      if (packed) {
-        const unsigned long long x = q == 0u ? ph : (q < 32u ? ((ph << (2u * q)) | (pl >> (64u - 2u * q))) : (pl << (2u * (q - 32u))));
-        cd = x >> (64u - 2u * k);                                  // bases q .. q + k - 1, first base in the top bits
-        ok = ((inv << q) >> (64u - k)) == 0ull;                    // none of them is a non-ACGT position
-        if (DIR == 1) {                                            // reverse complement (main.rs:148-161): complement, reverse the 2-bit groups
-          const unsigned long long comp = (~cd) & ((k == 32u) ? ~0ull : ((1ull << (2u * k)) - 1ull));
-          unsigned long long r = __brevll(comp) >> (64u - 2u * k);
-          cd = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
-        }
-      } else if (DIR == 0) { for (uint32_t t = 0; t < k; t++) { const uint32_t b = sb[q + t]; ok &= (b < 4u); cd = (cd << 2) | (b & 3u); } }
+      if (DIR == 0) { for (uint32_t t = 0; t < k; t++) { const uint32_t b = sb[q + t]; ok &= (b < 4u); cd = (cd << 2) | (b & 3u); } }
       else { for (uint32_t t = 0; t < k; t++) { const uint32_t b = sb[q + k - 1 - t]; ok &= (b < 4u); cd = (cd << 2) | ((3u - b) & 3u); } }  // reverse complement
       if (ok) code = cd;
     }
@@ -134,15 +203,72 @@ fast_hist_kernel(const unsigned long long* __restrict__ keys, uint64_t n0, const
   }
 }
 
-// dynamic smem: stage[SORT_TILE] u64 | loc_off[nbuckets] u32 | gadj[nbuckets] u32 | cnt[SORT_WARPS][nbuckets] u16
-__global__ void __launch_bounds__(SORT_T)
+// Offsets of one pass from the block histograms hist[d * nb + block]: one block per digit scans its nb counts in place
+// (exclusive) and leaves the digit's total in dtot[d]; fast_digit_base_kernel then turns dtot into the digits' bases.
+// Two launches per pass instead of the seven of the generic multi-level scan over nbuckets * nb entries.
+constexpr int DSCAN_T = 256;
+__global__ void __launch_bounds__(DSCAN_T)
+fast_digit_scan_kernel(uint32_t* __restrict__ hist, uint32_t nb, uint32_t* __restrict__ dtot) {
+  __shared__ uint32_t s_w[DSCAN_T / 32];
+  __shared__ uint32_t s_carry;
+  uint32_t* h = hist + (uint64_t)blockIdx.x * nb;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0u;
+  __syncthreads();
+  for (uint32_t base = 0; base < nb; base += DSCAN_T * 4) {
+    const uint32_t i0 = base + (uint32_t)tid * 4u;
+    uint32_t v[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) v[q] = i0 + q < nb ? h[i0 + q] : 0u;
+    const uint32_t sum = v[0] + v[1] + v[2] + v[3];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    uint32_t run = s_carry + inc - sum;
+    for (int w2 = 0; w2 < warp; w2++) run += s_w[w2];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { if (i0 + q < nb) h[i0 + q] = run; run += v[q]; }
+    __syncthreads();
+    if (tid == DSCAN_T - 1) s_carry = run;
+    __syncthreads();
+  }
+  if (tid == 0) dtot[blockIdx.x] = s_carry;
+}
+
+__global__ void __launch_bounds__(1024)
+fast_digit_base_kernel(uint32_t* __restrict__ dtot, uint32_t nbuckets) {   // nbuckets <= 2048: two per thread
+  __shared__ uint32_t s_w[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t a = 2u * tid < nbuckets ? dtot[2 * tid] : 0u, b = 2u * tid + 1u < nbuckets ? dtot[2 * tid + 1] : 0u;
+  uint32_t inc = a + b;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  uint32_t run = inc - (a + b);
+  for (int w2 = 0; w2 < warp; w2++) run += s_w[w2];
+  if (2u * tid < nbuckets) dtot[2 * tid] = run;
+  if (2u * tid + 1u < nbuckets) dtot[2 * tid + 1] = run + a;
+}
+
+// dynamic smem: gadj[nbuckets] u32 | { stage[SORT_TILE] u64  over  loc_off[nbuckets] u32 | cnt[SORT_WARPS][nbuckets] u16 | tag[SORT_WARPS][nbuckets] u8 }
+// Ranking: a warp visits its 512 consecutive keys 32 at a time (stable).  A round's 32 digits are almost always distinct
+// (<= 2048 buckets), so every lane marks its digit's tag with its lane id and reads it back: when nobody was overwritten
+// the round is a plain load + store of the warp's counters; only a round with a repeated digit pays for __match_any_sync
+// (whose cost grows with the number of distinct values: it was 45 % of this kernel's stall samples when used every round).
+template <int MINB>
+__global__ void __launch_bounds__(SORT_T, MINB)
 fast_scatter_kernel(const unsigned long long* __restrict__ keys, uint64_t n0, const uint32_t* __restrict__ n_dev, int shift, uint32_t nbuckets,
-                    const uint32_t* __restrict__ offs, uint32_t nb, unsigned long long* __restrict__ out) {
+                    const uint32_t* __restrict__ offs, const uint32_t* __restrict__ dbase, uint32_t nb, unsigned long long* __restrict__ out) {
   extern __shared__ __align__(8) unsigned char sraw[];
-  unsigned long long* stage = reinterpret_cast<unsigned long long*>(sraw);
-  uint32_t* loc_off = reinterpret_cast<uint32_t*>(stage + SORT_TILE);
-  uint32_t* gadj = loc_off + nbuckets;
-  uint16_t* cnt = reinterpret_cast<uint16_t*>(gadj + nbuckets);
+  uint32_t* gadj = reinterpret_cast<uint32_t*>(sraw);
+  unsigned char* ubase = sraw + (size_t)nbuckets * 4;
+  unsigned long long* stage = reinterpret_cast<unsigned long long*>(ubase);
+  uint32_t* loc_off = reinterpret_cast<uint32_t*>(ubase);
+  uint16_t* cnt = reinterpret_cast<uint16_t*>(loc_off + nbuckets);
+  uint8_t* tag = reinterpret_cast<uint8_t*>(cnt + (size_t)SORT_WARPS * nbuckets);
   __shared__ uint32_t s_wsum[SORT_WARPS];
   __shared__ uint32_t s_total;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -150,8 +276,7 @@ fast_scatter_kernel(const unsigned long long* __restrict__ keys, uint64_t n0, co
   const uint64_t tile0 = (uint64_t)blockIdx.x * SORT_TILE;
   if (tile0 >= n) return;
   for (uint32_t i = tid; i < SORT_WARPS * nbuckets / 2; i += SORT_T) reinterpret_cast<uint32_t*>(cnt)[i] = 0u;
-  __syncthreads();
-  // each warp owns 512 consecutive keys, visited in order 32 at a time => stable
+  // each warp owns 512 consecutive keys
   const uint64_t wbase = tile0 + (uint64_t)warp * (32 * SORT_ITEMS);
   unsigned long long key[SORT_ITEMS];
 #pragma unroll
@@ -159,18 +284,37 @@ fast_scatter_kernel(const unsigned long long* __restrict__ keys, uint64_t n0, co
     const uint64_t p = wbase + (uint64_t)i * 32 + lane;
     key[i] = p < n ? keys[p] : KEY_NONE;
   }
-  uint16_t rank[SORT_ITEMS];
+  __syncthreads();
+  uint32_t rank2[SORT_ITEMS / 2];   // two u16 ranks per register
   uint16_t* wc = cnt + (size_t)warp * nbuckets;
+  uint8_t* wt = tag + (size_t)warp * nbuckets;
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; i++) {
     const bool in = key[i] != KEY_NONE;
-    const uint32_t d = in ? ((uint32_t)(key[i] >> shift) & (nbuckets - 1u)) : 0xFFFFu;
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    const int leader = __ffs(peers) - 1;
-    uint32_t old = 0;
-    if (in && lane == leader) { old = wc[d]; wc[d] = (uint16_t)(old + __popc(peers)); }
-    old = __shfl_sync(0xffffffffu, old, leader);
-    rank[i] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1u)));
+    const uint32_t d = (uint32_t)(key[i] >> shift) & (nbuckets - 1u);
+    uint32_t r = 0;
+    int same = 0;
+    __match_all_sync(0xffffffffu, in ? d : 0xFFFFFFFFu, &same);
+    if (same) {                                // one digit for the whole round (sorted input: the usual case after pass 0)
+      if (in) {
+        uint32_t old = 0;
+        if (lane == 0) { old = wc[d]; wc[d] = (uint16_t)(old + 32u); }
+        r = __shfl_sync(0xffffffffu, old, 0) + lane;
+      }
+    } else {
+      if (in) wt[d] = (uint8_t)lane;
+      __syncwarp();
+      const bool lost = in && wt[d] != (uint8_t)lane;
+      if (__any_sync(0xffffffffu, lost)) {      // a digit occurs twice in this round
+        const unsigned peers = __match_any_sync(0xffffffffu, in ? d : 0xFFFFFFFFu);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (in && lane == leader) { old = wc[d]; wc[d] = (uint16_t)(old + __popc(peers)); }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        r = old + __popc(peers & ((1u << lane) - 1u));
+      } else if (in) { r = wc[d]; wc[d] = (uint16_t)(r + 1u); }
+    }
+    if (i & 1) rank2[i >> 1] |= r << 16; else rank2[i >> 1] = r;
     __syncwarp();
   }
   __syncthreads();
@@ -200,18 +344,24 @@ fast_scatter_kernel(const unsigned long long* __restrict__ keys, uint64_t n0, co
     for (uint32_t d = d0; d < d0 + per && d < nbuckets; d++) {
       const uint32_t c2 = loc_off[d];
       loc_off[d] = run;
-      gadj[d] = offs[(uint64_t)d * nb + blockIdx.x] - run;     // global position = gadj[d] + position in the staged tile
+      gadj[d] = dbase[d] + offs[(uint64_t)d * nb + blockIdx.x] - run;     // global position = gadj[d] + position in the staged tile
       run += c2;
     }
   }
   __syncthreads();
+  // position of every key in the staged tile, then the stage takes over the counters' memory
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; i++) {
     if (key[i] != KEY_NONE) {
       const uint32_t d = (uint32_t)(key[i] >> shift) & (nbuckets - 1u);
-      stage[loc_off[d] + wc[d] + rank[i]] = key[i];
+      const uint32_t r = loc_off[d] + wc[d] + ((rank2[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+      rank2[i >> 1] = (i & 1) ? ((rank2[i >> 1] & 0xFFFFu) | (r << 16)) : ((rank2[i >> 1] & 0xFFFF0000u) | r);
     }
   }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; i++)
+    if (key[i] != KEY_NONE) stage[(rank2[i >> 1] >> (16 * (i & 1))) & 0xFFFFu] = key[i];
   __syncthreads();
   const uint32_t total = s_total;
   for (uint32_t p = tid; p < total; p += SORT_T) {
@@ -255,11 +405,16 @@ __global__ void fast_csr_kernel(const unsigned long long* __restrict__ keys, con
   }
 }
 
+size_t scatter_smem(uint32_t nbk) {   // gadj + max(stage, loc_off + cnt + tag)
+  return (size_t)nbk * 4 + std::max<size_t>((size_t)SORT_TILE * 8, (size_t)nbk * 4 + (size_t)SORT_WARPS * nbk * 3);
+}
+
 uint32_t bits_needed(uint64_t v) { uint32_t b = 1; while (b < 64 && (v >> b) != 0ull) b++; return b; }
 
 struct FastDir {
   unsigned long long* ka = nullptr; unsigned long long* kb = nullptr; uint32_t* hist = nullptr; uint32_t* flags = nullptr;
   uint32_t* d_cnt = nullptr;   // [0] R  [1] n_codes
+  uint32_t* dtot = nullptr;    // [nbuckets] digit totals -> digit bases of the current pass
 };
 
 }  // namespace
@@ -297,8 +452,10 @@ int msspe_build_fast(msspe_ctx* c) {
   int maxbits = 1;
   for (int p = 0; p < passes; p++) maxbits = std::max(maxbits, pass[p].bits);
   const uint32_t max_buckets = 1u << maxbits;
-  const size_t sc_smem_max = (size_t)SORT_TILE * 8 + (size_t)max_buckets * 8 + (size_t)SORT_WARPS * max_buckets * 2;
-  MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(fast_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem_max));
+  const size_t sc_smem_max = scatter_smem(max_buckets);
+  static const int scatter_minb = getenv("MSSPE_SCATTER_MINB") ? atoi(getenv("MSSPE_SCATTER_MINB")) : 3;
+  MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(fast_scatter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem_max));
+  MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(fast_scatter_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem_max));
   FastDir F[2];
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[2], st));
   float enc_ms_total = 0.f;
@@ -309,25 +466,36 @@ int msspe_build_fast(msspe_ctx* c) {
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&f.hist, (uint64_t)max_buckets * nb * 4, st));
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&f.flags, GS * 4, st));
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&f.d_cnt, 16, st));
+    MSSPE_CUDA_TRY(c, cudaMallocAsync(&f.dtot, (uint64_t)max_buckets * 4, st));
     MSSPE_CUDA_TRY(c, cudaMemsetAsync(f.d_cnt, 0, 16, st));
     {
       KPROF(c, KP_ENCODE, st, G * w + GS * 8)
-      const unsigned grid = (unsigned)div_up_u64(G, ENCF_WARPS);
-      if (dir == 0) encode_keys_kernel<0><<<grid, ENCF_WARPS * 32, enc_smem, st>>>(c->d_bases, c->d_offsets, c->d_seg_base, c->n_records, c->uniform_parts, G, c->cfg.window_size,
-                                                                                  c->cfg.overlap_size, w, k, slots, idx_bits, f.ka, c->d_seg_part, c->d_seg_rec);
-      else encode_keys_kernel<1><<<grid, ENCF_WARPS * 32, enc_smem, st>>>(c->d_bases, c->d_offsets, c->d_seg_base, c->n_records, c->uniform_parts, G, c->cfg.window_size,
-                                                                          c->cfg.overlap_size, w, k, slots, idx_bits, f.ka, c->d_seg_part, c->d_seg_rec);
+      if (w <= 64u) {
+        const unsigned grid = (unsigned)div_up_u64(G, ENCF_WARPS * ENC_SEGS);
+        if (dir == 0) encode_keys_packed_kernel<0><<<grid, ENCF_WARPS * 32, 0, st>>>(c->d_bases, c->d_offsets, c->d_seg_base, c->n_records, c->uniform_parts, G, c->cfg.window_size,
+                                                                                     c->cfg.overlap_size, w, k, slots, idx_bits, f.ka, c->d_seg_part, c->d_seg_rec);
+        else encode_keys_packed_kernel<1><<<grid, ENCF_WARPS * 32, 0, st>>>(c->d_bases, c->d_offsets, c->d_seg_base, c->n_records, c->uniform_parts, G, c->cfg.window_size,
+                                                                            c->cfg.overlap_size, w, k, slots, idx_bits, f.ka, c->d_seg_part, c->d_seg_rec);
+      } else {
+        const unsigned grid = (unsigned)div_up_u64(G, ENCF_WARPS);
+        if (dir == 0) encode_keys_kernel<0><<<grid, ENCF_WARPS * 32, enc_smem, st>>>(c->d_bases, c->d_offsets, c->d_seg_base, c->n_records, c->uniform_parts, G, c->cfg.window_size,
+                                                                                    c->cfg.overlap_size, w, k, slots, idx_bits, f.ka, c->d_seg_part, c->d_seg_rec);
+        else encode_keys_kernel<1><<<grid, ENCF_WARPS * 32, enc_smem, st>>>(c->d_bases, c->d_offsets, c->d_seg_base, c->n_records, c->uniform_parts, G, c->cfg.window_size,
+                                                                            c->cfg.overlap_size, w, k, slots, idx_bits, f.ka, c->d_seg_part, c->d_seg_rec);
+      }
     }
     for (int p = 0; p < passes; p++) {
       const uint32_t nbk = 1u << pass[p].bits;
       const uint32_t* n_dev = p == 0 ? nullptr : f.d_cnt;
       { KPROF(c, KP_SORT_HIST, st, GS * 8)
         fast_hist_kernel<<<nb, SORT_T, nbk * 4, st>>>(f.ka, GS, n_dev, pass[p].shift, nbk, f.hist, nb, p == 0 ? f.d_cnt : nullptr); }
-      int rc = msspe_exclusive_scan_u32(c, f.hist, f.hist, (uint64_t)nbk * nb, nullptr, st);
-      if (rc) return rc;
-      const size_t sm = (size_t)SORT_TILE * 8 + (size_t)nbk * 8 + (size_t)SORT_WARPS * nbk * 2;
+      { KPROF(c, KP_SCAN, st, (uint64_t)nbk * nb * 8)
+        fast_digit_scan_kernel<<<nbk, DSCAN_T, 0, st>>>(f.hist, nb, f.dtot);
+        fast_digit_base_kernel<<<1, 1024, 0, st>>>(f.dtot, nbk); }
+      const size_t sm = scatter_smem(nbk);
       { KPROF(c, KP_SORT_SCATTER, st, GS * 16)
-        fast_scatter_kernel<<<nb, SORT_T, sm, st>>>(f.ka, GS, n_dev, pass[p].shift, nbk, f.hist, nb, f.kb); }
+        if (scatter_minb == 3) fast_scatter_kernel<3><<<nb, SORT_T, sm, st>>>(f.ka, GS, n_dev, pass[p].shift, nbk, f.hist, f.dtot, nb, f.kb);
+        else fast_scatter_kernel<2><<<nb, SORT_T, sm, st>>>(f.ka, GS, n_dev, pass[p].shift, nbk, f.hist, f.dtot, nb, f.kb); }
       std::swap(f.ka, f.kb);
     }
     { KPROF(c, KP_CSR, st, GS * 12)
@@ -360,7 +528,7 @@ int msspe_build_fast(msspe_ctx* c) {
                                                                    c->d_seg_part, uni, D.list_part);
     }
     MSSPE_CUDA_TRY(c, cudaFreeAsync(f.ka, st)); MSSPE_CUDA_TRY(c, cudaFreeAsync(f.kb, st)); MSSPE_CUDA_TRY(c, cudaFreeAsync(f.hist, st));
-    MSSPE_CUDA_TRY(c, cudaFreeAsync(f.flags, st)); MSSPE_CUDA_TRY(c, cudaFreeAsync(f.d_cnt, st));
+    MSSPE_CUDA_TRY(c, cudaFreeAsync(f.flags, st)); MSSPE_CUDA_TRY(c, cudaFreeAsync(f.d_cnt, st)); MSSPE_CUDA_TRY(c, cudaFreeAsync(f.dtot, st));
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.freq, Dn * 4, st));
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.ignored, (div_up_u64(G, 32) + 1) * 4, st));
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.cov, 65536 * 4, st));

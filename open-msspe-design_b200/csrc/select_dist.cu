@@ -646,6 +646,9 @@ int dist_select_impl(msspe_ctx* c, uint32_t max_iter, uint32_t mms, msspe_candid
   auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return 1e3 * ts.tv_sec + 1e-6 * ts.tv_nsec; };
   const double t_begin = now_ms();
   double t_setup = 0.0;
+  double t_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // MSSPE_DEBUG_TIMERS: set-up phases (stream synchronised at each mark)
+  double t_mark = t_begin;
+  auto mark = [&](int ph) { if (dbg) { cudaStreamSynchronize(st); const double t = now_ms(); t_ph[ph] += t - t_mark; t_mark = t; } };
   ScratchList scratch; scratch.st = st;
   auto alloc = [&](void** p, uint64_t bytes, int fill) -> int {
     MSSPE_CUDA_TRY(c, cudaMallocAsync(p, bytes ? bytes : 4, st));
@@ -663,6 +666,7 @@ int dist_select_impl(msspe_ctx* c, uint32_t max_iter, uint32_t mms, msspe_candid
   std::vector<uint32_t> h_cnts(4 * world);
   MSSPE_CUDA_TRY(c, cudaMemcpyAsync(h_cnts.data(), d_cnts, 16ull * world, cudaMemcpyDeviceToHost, st));
   MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+  mark(0);
   uint32_t UM = 1, dmax[2] = {1, 1};
   for (int r = 0; r < world; r++) { UM = std::max(UM, h_cnts[4 * r + 2]); dmax[0] = std::max(dmax[0], h_cnts[4 * r]); dmax[1] = std::max(dmax[1], h_cnts[4 * r + 1]); }
   const uint32_t U_pad = UM * (uint32_t)world, UW = (U_pad + 31u) / 32u;
@@ -713,6 +717,7 @@ int dist_select_impl(msspe_ctx* c, uint32_t max_iter, uint32_t mms, msspe_candid
       int rc0 = msspe_exclusive_scan_u32(c, own, own_scan, nc, d_nown, st);
       if (rc0) return rc0;
     }
+    mark(1);
     // the cross words themselves, identically on every rank: every word is reported by the lowest rank that holds it
     MSSPE_NCCL_TRY(c, ds, N->AllGather(d_nown, d_nowns, 1, ncclUint32, ds->comm, st));
     std::vector<uint32_t> h_nown(world);
@@ -728,6 +733,7 @@ int dist_select_impl(msspe_ctx* c, uint32_t max_iter, uint32_t mms, msspe_candid
     I.pv_dist = true;
     if (rc) return rc;
     MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+    mark(2);
     uint32_t n_x = 0, own_max = 1;
     for (int r = 0; r < world; r++) { n_x += h_nown[r]; own_max = std::max(own_max, h_nown[r]); }
     Q.n_x = n_x;
@@ -741,6 +747,7 @@ int dist_select_impl(msspe_ctx* c, uint32_t max_iter, uint32_t mms, msspe_candid
     rc = msspe_radix_sort_pairs(c, &ka, &va, &kb, &vb, na, kbits + 1, st);   // the paddings sort behind every word
     if (rc) return rc;
     Q.xcodes = reinterpret_cast<const unsigned long long*>(ka);             // first n_x entries
+    mark(3);
     // ---- 3. state of the loop (as on one GPU) + the replicated view + exchange buffers ----
     if (I.out_capacity < max_iter) {
       msspe_dev_free(c, I.out); I.out = nullptr;
@@ -800,6 +807,7 @@ int dist_select_impl(msspe_ctx* c, uint32_t max_iter, uint32_t mms, msspe_candid
     uint32_t* m_xid = nullptr; uint32_t* xlen_local = nullptr;
     DA(m_xid, ((uint64_t)P.n_multi + 1) * 4, 0xFF); DA(xlen_local, ((uint64_t)n_x + 1) * 4, 0);
     Q.m_xid = m_xid;
+    mark(4);
     if (P.n_multi) {
       pv_mlen_kernel<<<(P.n_multi + 255u) / 256u, 256, 0, st>>>(P.ucodes, P.n_single, P.n_multi, P.post_off, P.ub, nullptr);
       dist_xmap_kernel<<<(P.n_multi + 255u) / 256u, 256, 0, st>>>(A, X, d, m_xid, xlen_local);
@@ -819,6 +827,7 @@ int dist_select_impl(msspe_ctx* c, uint32_t max_iter, uint32_t mms, msspe_candid
     }
     // PartCtl: verify windows are bounded by the exchange record
     MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
+    mark(5);
   }
   // the all-reduced buffer: rows of the staged cross lists | ties of local lists | reported partitions | local best records | limit flag
   X.xcap = max_nx <= xstage_rows ? std::max<uint32_t>(128u, (max_nx + 127u) & ~127u) : xstage_rows;
@@ -857,6 +866,7 @@ int dist_select_impl(msspe_ctx* c, uint32_t max_iter, uint32_t mms, msspe_candid
   uint32_t h_err[2] = {0, 0};
   uint32_t round = 0;
   const uint32_t BATCH = 4;
+  mark(6);
   if (dbg) { cudaStreamSynchronize(st); t_setup = now_ms() - t_begin; }
   for (;;) {
     for (uint32_t b = 0; b < BATCH; b++, round++) {
@@ -930,6 +940,9 @@ int dist_select_impl(msspe_ctx* c, uint32_t max_iter, uint32_t mms, msspe_candid
   float ms = 0.f;
   MSSPE_CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
   c->timing.select_ms[0] = c->timing.select_ms[1] = ms;
+  if (dbg && rank == 0)
+    fprintf(stderr, "[msspe] rank 0 set-up phases (both directions, ms): sizes %.3f | words all-gather + cross flags %.3f | partition view %.3f | cross words exchange + sort %.3f | "
+                    "allocations %.3f | cross lengths all-reduce %.3f | init kernels %.3f\n", t_ph[0], t_ph[1], t_ph[2], t_ph[3], t_ph[4], t_ph[5], t_ph[6]);
   if (getenv("MSSPE_DEBUG_TIMERS"))
     for (int d = 0; d < 2; d++)
       fprintf(stderr, "[msspe] rank %d/%d partitioned greedy dir %d: %u winners, %u rounds, %u external winners, %u local multi lists, %u cross-rank lists, %.3f ms (set-up %.3f ms, wall %.3f ms; kmax %u, window %u, staged cap %u, buffer %u KB)\n",

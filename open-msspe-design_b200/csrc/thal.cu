@@ -21,6 +21,7 @@
 //   * best-cell selection, traceback (needed for the salt correction: N paired bases) and dS/dH/dG/Tm follow.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 #include "engine.cuh"
 #include "thal_tables.cuh"
@@ -103,6 +104,15 @@ void build_dimer_consts(const ThalDeviceTables& T, const msspe_thal_cond& c, Tha
           }
         }
     }
+  // t0[sym][li * 25 + rn]: the quotient of the stack test for a cell that starts a duplex (thal_dimer_flat_kernel), with the
+  // kernel's expression: li = (a, n1[i-1], n2[j-1]) indexes lsh, a * 25 + rn = (a, n1[i+1], n2[j+1]) indexes rsh
+  for (int sym = 0; sym < 2; sym++)
+    for (int li = 0; li < 100; li++)
+      for (int rn = 0; rn < 25; rn++) {
+        const int ri = (li / 25) * 25 + rn;
+        const double H0 = K->lshH[sym][li], S0 = K->lshS[sym][li], rH = K->rshH[sym][ri], rS = K->rshS[sym][ri], RC = K->RC[sym];
+        K->t0[sym][li * 25 + rn] = (H0 + kDHi + rH) / (S0 + kDSi + rS + RC);
+      }
 }
 
 // ---------------------------------------------------------------- device: dimer
@@ -117,6 +127,7 @@ struct DimerArgs {
   msspe_dimer_edge* edges; unsigned long long edge_cap; unsigned long long* n_edges;
   uint64_t* nostruct; unsigned long long nostruct_cap; unsigned long long* n_nostruct;
   int dbg;  // diagnostic: 1 = skip loop candidates, 2 = skip traceback, 4 = skip fill entirely
+  double2* scratch;  // thal_dimer_thread_kernel: k*k cells per resident thread
   uint8_t* pairing;  // optional [n_pairs][MSSPE_MAX_OLIGO], zeroed: partner (1-based, in the reversed second oligo) of base i
 };
 
@@ -476,6 +487,674 @@ thal_dimer_kernel(const DimerArgs A) {
           const unsigned long long at = atomicAdd(A.n_edges, 1ull);
           if (at < A.edge_cap) { A.edges[at].pair = pair; A.edges[at].dg = res.dg; }
         }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- device: dimer, flat candidate enumeration
+// Same algorithm and the same results as thal_dimer_kernel; what changes is how the bulge / internal-loop candidates of a
+// row are spread over the warp, and how many instructions one candidate costs.
+//   * thal_dimer_kernel gives every paired cell 8 (16) lanes that stride over the inner ROWS and loop over the paired
+//     columns of each: 5.5 of 32 lanes are active in that loop, 12,000 warp instructions per 13-mer pair (ncu).
+//   * Here the paired cells of the rows above row i are listed once per row in COLUMN-major order (desc[]); the
+//     candidates of cell (i, j) are then exactly the first pcol[j - 1] entries of that list, so the candidates of ALL paired
+//     cells of the row form one flat index space (j-major, oend[] = running ends) that the 32 lanes take 32 at a time: an
+//     item finds its cell by a binary search in oend[].  18 rounds per 13-mer pair instead of 57.
+//   * The four candidate kinds (bulge of one base, longer bulge, 1x1 mismatch, general interior loop) are ONE arithmetic
+//     sequence over a single (S,H) table: three entries chosen by integer selects, zeros where a kind has fewer terms, so
+//     the lanes of a round do not diverge by kind.  The sums keep the scalar code's association.
+//   * The minimum per cell: the lanes of one cell are consecutive, so each lane passes ITS cell's lane range as the member
+//     mask of three integer REDUX (ordered bits of dG high word, low word, scan-order key) -- all cells of the round at once.
+//   * The first of the two quotients of the stack test depends only on the 2x2x2 base context: tabulated on the host
+//     (ThalDimerConsts::t0) with the same expression, so a row pays for one FP64 division, not two.
+constexpr int FT_STACK = 0, FT_INT2 = 256, FT_TST = 512, FT_ATP = 768, FT_BULGE = 784, FT_INTERIOR = 814, FT_ZERO = 844, FT_N = 845;
+struct FlatShared {   // per block
+  double2 tab[FT_N];  // (S,H): stack | 1x1 mismatch | terminal mismatch (256 each, index i4) | AT penalty (16) | bulge, interior (30 each) | zero
+  double2 lsh[2][100], rsh[2][100];
+};
+struct FlatView {   // per warp, in shared memory
+  double2* cell;                                          // [k*k] (S,H)
+  double *bG, *bS, *bH;                                   // [k+2] running best candidate of the row's cells
+  uint32_t *rowmask, *colmask, *pcol, *oend; int* bKey;   // [k+2]
+  uint32_t* desc;                                         // [k*k] (inner context << 16) | (ii << 8) | jj
+  uint8_t *n1, *n2, *clx, *rix, *actx, *bctx;             // [k+2]
+};
+__host__ __device__ inline size_t flat_group_bytes(int k) {
+  const size_t b = (size_t)k * k * 16 + 3 * (size_t)(k + 2) * 8 + 5 * (size_t)(k + 2) * 4 + (size_t)k * k * 4 + 6 * (size_t)(k + 2);
+  return (b + 15) & ~(size_t)15;
+}
+
+// (S,H) of the bulge / internal loop closed by (i,j) with inner pair (ii,jj), including the inner cell's value; H = +inf
+// marks "not possible".  xin = i4(n1[ii], n1[ii+1], n2[jj], n2[jj+1]), xcl = i4(n2[j], n2[j-1], n1[i], n1[i-1]).
+__device__ __forceinline__ void flat_candidate(const double2* __restrict__ tab, const double2 inner, uint32_t xin, uint32_t xcl, int l1, int l2,
+                                               double* outS, double* outH) {
+  const int ls = l1 + l2 - 1;
+  const bool bulge = (l1 == 0) | (l2 == 0);
+  const bool b1 = bulge & (ls == 0);          // one bulged base: the flanking pairs still stack
+  const bool one = (l1 == 1) & (l2 == 1);
+  const uint32_t a_in = xin >> 6, b_in = (xin >> 2) & 3u, a_cl = (xcl >> 2) & 3u, b_cl = xcl >> 6;
+  const uint32_t x1 = (a_in << 6) | (a_cl << 4) | (b_in << 2) | b_cl;
+  const uint32_t iA = bulge ? FT_BULGE + ls : (one ? FT_INT2 + xin : FT_INTERIOR + ls);
+  const uint32_t iB = b1 ? FT_STACK + x1 : (bulge ? FT_ATP + a_in * 4 + b_in : (one ? FT_INT2 + xcl : FT_TST + xin));
+  const uint32_t iC = (b1 | one) ? FT_ZERO : (bulge ? FT_ATP + a_cl * 4 + b_cl : FT_TST + xcl);
+  const double2 tA = tab[iA], tB = tab[iB], tC = tab[iC];
+  const int asym = l1 > l2 ? l1 - l2 : l2 - l1;
+  const bool gen = !bulge && !one;
+  const double dH = gen ? (K_ILAH * asym) : 0.0, dS = gen ? (K_ILAS * asym) : 0.0;
+  double H = tA.y + tB.y + tC.y + dH;
+  double S = tA.x + tB.x + tC.x + dS;
+  if (b1 && (H > 0 || S > 0)) { H = INFINITY; S = -1.0; }
+  H += inner.y; S += inner.x;
+  if (!isfinite(H)) { H = INFINITY; S = -1.0; }
+  if (!b1 && H > 0 && S > 0) { H = INFINITY; S = -1.0; }
+  *outS = S; *outH = H;
+}
+
+__global__ void __launch_bounds__(DIMER_THREADS, 5)
+thal_dimer_flat_kernel(const DimerArgs A) {
+  constexpr int GROUP = 32;  // one warp per ordered pair
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  FlatShared& sh = *reinterpret_cast<FlatShared*>(dyn_smem);
+  const int k = A.k;
+  const int tid = threadIdx.x;
+  {  // stage tables
+    const ThalDeviceTables* T = A.T;
+    for (int x = tid; x < 256; x += DIMER_THREADS) {
+      const int a = x >> 6, b = (x >> 4) & 3, c = (x >> 2) & 3, d = x & 3;
+      const int g = THAL_IDX4(a, b, c, d);
+      sh.tab[FT_STACK + x] = make_double2(T->stackS[g], T->stackH[g]);
+      sh.tab[FT_INT2 + x] = make_double2(T->stackint2S[g], T->stackint2H[g]);
+      sh.tab[FT_TST + x] = make_double2(T->tstackS[g], T->tstackH[g]);
+    }
+    for (int x = tid; x < 200; x += DIMER_THREADS) {
+      (&sh.lsh[0][0])[x] = make_double2((&A.C->lshS[0][0])[x], (&A.C->lshH[0][0])[x]);
+      (&sh.rsh[0][0])[x] = make_double2((&A.C->rshS[0][0])[x], (&A.C->rshH[0][0])[x]);
+    }
+    for (int x = tid; x < 30; x += DIMER_THREADS) {
+      sh.tab[FT_INTERIOR + x] = make_double2(T->interiorS[x], T->interiorH[x]);
+      sh.tab[FT_BULGE + x] = make_double2(T->bulgeS[x], T->bulgeH[x]);
+    }
+    for (int x = tid; x < 16; x += DIMER_THREADS) sh.tab[FT_ATP + x] = make_double2(T->atpS[(x >> 2) * 5 + (x & 3)], T->atpH[(x >> 2) * 5 + (x & 3)]);
+    if (tid == 0) sh.tab[FT_ZERO] = make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  const double2* __restrict__ tab = sh.tab;
+  constexpr int GROUPS = DIMER_THREADS / GROUP;
+  const int grp = tid / GROUP, gl = tid % GROUP, lane = tid & 31;
+  const unsigned gmask = 0xffffffffu;
+  FlatView fv;
+  {
+    unsigned char* gb = dyn_smem + ((sizeof(FlatShared) + 15) & ~(size_t)15) + grp * flat_group_bytes(k);
+    const size_t n8 = (size_t)(k + 2) * 8, n4 = (size_t)(k + 2) * 4, n1b = (size_t)(k + 2);
+    fv.cell = reinterpret_cast<double2*>(gb); gb += (size_t)k * k * 16;
+    fv.bG = reinterpret_cast<double*>(gb); gb += n8;
+    fv.bS = reinterpret_cast<double*>(gb); gb += n8;
+    fv.bH = reinterpret_cast<double*>(gb); gb += n8;
+    fv.rowmask = reinterpret_cast<uint32_t*>(gb); gb += n4;
+    fv.colmask = reinterpret_cast<uint32_t*>(gb); gb += n4;
+    fv.pcol = reinterpret_cast<uint32_t*>(gb); gb += n4;
+    fv.oend = reinterpret_cast<uint32_t*>(gb); gb += n4;
+    fv.bKey = reinterpret_cast<int*>(gb); gb += n4;
+    fv.desc = reinterpret_cast<uint32_t*>(gb); gb += (size_t)k * k * 4;
+    fv.n1 = gb; gb += n1b; fv.n2 = gb; gb += n1b; fv.clx = gb; gb += n1b; fv.rix = gb; gb += n1b; fv.actx = gb; gb += n1b; fv.bctx = gb;
+  }
+  double2* const cell = fv.cell;
+  const uint8_t* const n1 = fv.n1; const uint8_t* const n2 = fv.n2;
+  const int maxLoop = A.C->maxLoop;
+  const double saltCorr = A.C->saltCorr, t_user = A.C->t_user_K;
+
+  for (unsigned long long p = (unsigned long long)blockIdx.x * GROUPS + grp; p < A.n_pairs; p += (unsigned long long)gridDim.x * GROUPS) {
+    uint64_t ca, cb;
+    if (A.matrix) { ca = A.a[A.row_begin + p / A.n]; cb = A.b[p % A.n]; }
+    else { ca = A.a[p]; cb = A.b[p]; }
+    __syncwarp(gmask);
+    // numSeq1 = oligo1 5'->3'; numSeq2 = oligo2 REVERSED (not complemented); N sentinels at both ends
+    for (int t = gl; t < k; t += GROUP) {
+      fv.n1[t + 1] = (uint8_t)((ca >> (2 * (k - 1 - t))) & 3u);
+      fv.n2[t + 1] = (uint8_t)((cb >> (2 * t)) & 3u);
+    }
+    if (gl == 0) { fv.n1[0] = 4; fv.n1[k + 1] = 4; fv.n2[0] = 4; fv.n2[k + 1] = 4; }
+    __syncwarp(gmask);
+    {  // rowmask[i] = columns j whose base pairs with n1[i]; colmask[j] = rows i whose base pairs with n2[j]; neighbour contexts
+      uint32_t cm0 = 0u, cm1 = 0u, cm2 = 0u, cm3 = 0u, rm0 = 0u, rm1 = 0u, rm2 = 0u, rm3 = 0u;   // positions of A, C, G, T in oligo 2 (reversed) / oligo 1
+      for (int j = 1; j <= k; j++) {
+        const uint32_t bit = 1u << (j - 1), y = n2[j], x = n1[j];
+        cm0 |= y == 0u ? bit : 0u; cm1 |= y == 1u ? bit : 0u; cm2 |= y == 2u ? bit : 0u; cm3 |= y == 3u ? bit : 0u;
+        rm0 |= x == 0u ? bit : 0u; rm1 |= x == 1u ? bit : 0u; rm2 |= x == 2u ? bit : 0u; rm3 |= x == 3u ? bit : 0u;
+      }
+      for (int i = gl + 1; i <= k; i += GROUP) {
+        const uint32_t x = n1[i], y = n2[i];
+        fv.rowmask[i] = x == 0u ? cm3 : x == 1u ? cm2 : x == 2u ? cm1 : cm0;
+        fv.colmask[i] = y == 0u ? rm3 : y == 1u ? rm2 : y == 2u ? rm1 : rm0;
+        fv.actx[i] = (uint8_t)((x << 6) | ((n1[i + 1] & 3) << 4));
+        fv.bctx[i] = (uint8_t)((y << 2) | (n2[i + 1] & 3));
+      }
+      if (gl == 0) { fv.rowmask[0] = 0; fv.rowmask[k + 1] = 0; fv.colmask[0] = 0; fv.colmask[k + 1] = 0; }
+    }
+    const int sym = ((k & 1) == 0 && revcomp_code(ca, k) == ca && revcomp_code(cb, k) == cb) ? 1 : 0;
+    const double RC = A.C->RC[sym];
+    const double2* __restrict__ lsh = sh.lsh[sym];
+    const double2* __restrict__ rsh = sh.rsh[sym];
+    const double* __restrict__ t0tab = A.C->t0[sym];
+    __syncwarp(gmask);
+
+    // ---------------- fill ----------------
+    for (int i = 1; i <= ((A.dbg & 4) ? 0 : k); i++) {
+      const uint32_t rm = fv.rowmask[i];
+      const int a = n1[i];
+      for (int j = gl + 1; j <= k; j += GROUP) {
+        if (!((rm >> (j - 1)) & 1u)) continue;
+        const int li = (a * 5 + n1[i - 1]) * 5 + n2[j - 1];
+        const double2 l = lsh[li];
+        double S = l.x, H = l.y;
+        if (i > 1 && j > 1) {
+          const int rn = n1[i + 1] * 5 + n2[j + 1];
+          const int ri = a * 25 + rn;
+          const double2 r = rsh[ri];
+          const double rS = r.x, rH = r.y;
+          double S0 = S, H0 = H, S1, H1, T1;
+          const double T0 = __ldg(&t0tab[li * 25 + rn]);   // (H0 + kDHi + rH) / (S0 + kDSi + rS + RC), tabulated on the host
+          const int si = i4(n1[i - 1], a, n2[j - 1], n2[j]);
+          const double2 st = tab[FT_STACK + si];
+          const bool prev_bp = (fv.rowmask[i - 1] >> (j - 2)) & 1u;
+          if (prev_bp && isfinite(st.y)) {
+            const double2 pc = cell[(i - 2) * k + (j - 2)];
+            S1 = pc.x + st.x;
+            H1 = pc.y + st.y;
+            T1 = (H1 + kDHi + rH) / (S1 + kDSi + rS + RC);
+          } else {
+            S1 = -1.0; H1 = INFINITY;
+            T1 = (H1 + kDHi) / (S1 + kDSi + RC);
+          }
+          if (S1 < kMinEntropyCutoff) { S1 = kMinEntropy; H1 = 0.0; }
+          if (S0 < kMinEntropyCutoff) { S0 = kMinEntropy; H0 = 0.0; }
+          if (T1 > T0) { S = S1; H = H1; } else if (T0 >= T1) { S = S0; H = H0; }
+          fv.clx[j] = (uint8_t)i4(n2[j], n2[j - 1] & 3, a, n1[i - 1] & 3);
+          fv.rix[j] = (uint8_t)ri;
+          fv.bG[j] = INFINITY; fv.bKey[j] = 0x7fffffff;
+        }
+        cell[(i - 1) * k + (j - 1)] = make_double2(S, H);
+      }
+      __syncwarp(gmask);
+      const uint32_t bjm = rm & ~1u;   // paired columns j >= 2 of this row
+      if (i > 1 && bjm && !(A.dbg & 1)) {
+        // the paired cells of rows 1 .. i-1, column-major: lane c lists column c + 1 behind the columns before it;
+        // oend[c] = end of the candidates of column c + 1 in the row's flat (j-major) index space
+        uint32_t T;
+        {
+          const uint32_t cm = lane < k ? (fv.colmask[lane + 1] & ((1u << (i - 1)) - 1u)) : 0u;
+          const uint32_t cc = __popc(cm);
+          uint32_t inc = cc;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+          uint32_t r = inc - cc;                    // cells in columns 1 .. lane  ==  candidates of a cell in column lane + 1
+          uint32_t oe = ((bjm >> lane) & 1u) ? r : 0u;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, oe, o); if (lane >= o) oe += t; }
+          if (lane < k) { fv.pcol[lane] = r; fv.oend[lane] = oe; }
+          T = __shfl_sync(0xffffffffu, oe, 31);
+          const uint32_t bx = lane < k ? fv.bctx[lane + 1] : 0u;
+          for (uint32_t m = cm; m; m &= m - 1u) {
+            const uint32_t ii = __ffs(m);
+            fv.desc[r++] = ((uint32_t)(fv.actx[ii] | bx) << 16) | (ii << 8) | (uint32_t)(lane + 1);
+          }
+        }
+        __syncwarp(gmask);
+        bool clamp = false;
+        for (uint32_t base = 0; base < T; base += 32) {
+          const uint32_t t = base + lane;
+          double S = -1.0, H = INFINITY, G1 = INFINITY;
+          int key = 0x7fffffff, j = 0;
+          bool fin = false;
+          unsigned segmask = 1u << lane;
+          if (t < T) {
+            uint32_t c = 0;         // number of columns whose candidates end at or before item t  ==  the item's column - 1
+#pragma unroll
+            for (int s = 16; s; s >>= 1) { const uint32_t m = c + s; if (m <= (uint32_t)k && fv.oend[m - 1] <= t) c = m; }
+            j = (int)c + 1;
+            const uint32_t cnt = fv.pcol[c], end = fv.oend[c], beg = end - cnt;
+            const uint32_t lb = beg > base ? beg - base : 0u, le = end - base;     // the cell's lanes in this round: [lb, le)
+            segmask = (le >= 32u ? 0xffffffffu : ((1u << le) - 1u)) & ~((1u << lb) - 1u);
+            const uint32_t d = fv.desc[t - beg];
+            const int ii = (d >> 8) & 0xff, jj = d & 0xff;
+            const int l1 = i - ii - 1, l2 = j - jj - 1;
+            if (l1 + l2 >= 1 && l1 + l2 <= maxLoop) {
+              flat_candidate(tab, cell[(ii - 1) * k + (jj - 1)], d >> 16, fv.clx[j], l1, l2, &S, &H);
+              if (isfinite(H)) {
+                if (S < kMinEntropyCutoff) clamp = true;
+                const double2 r = rsh[fv.rix[j]];
+                G1 = H + r.y - kTK * (S + r.x);
+                key = (l1 + l2) * 64 + l1;
+                fin = true;
+              }
+            }
+          }
+          // minimum per cell: first dG (unsigned order of the ordered bits == order of the doubles), then the scan-order key
+          const unsigned long long gbits = (unsigned long long)__double_as_longlong(G1);
+          const unsigned long long ob = gbits ^ ((gbits >> 63) ? ~0ull : 0x8000000000000000ull);
+          const uint32_t oh = fin ? (uint32_t)(ob >> 32) : 0xffffffffu;
+          const uint32_t mh = __reduce_min_sync(segmask, oh);
+          const bool c1 = fin && oh == mh;
+          const uint32_t ol = c1 ? (uint32_t)ob : 0xffffffffu;
+          const uint32_t ml = __reduce_min_sync(segmask, ol);
+          const bool c2 = c1 && ol == ml;
+          const uint32_t mk = __reduce_min_sync(segmask, c2 ? (uint32_t)key : 0xffffffffu);
+          if (c2 && (uint32_t)key == mk) {
+            const double bG = fv.bG[j];
+            if (G1 < bG || (G1 == bG && key < fv.bKey[j])) { fv.bG[j] = G1; fv.bS[j] = S; fv.bH[j] = H; fv.bKey[j] = key; }
+          }
+          __syncwarp(gmask);
+        }
+        const bool cellmine = lane < k && ((bjm >> lane) & 1u);
+        const int j = lane + 1;
+        if (__any_sync(0xffffffffu, clamp)) {
+          // An entropy below the cutoff re-bases the cell mid-scan: replay the scan sequentially, one lane per cell.
+          if (cellmine) {
+            const double2 r = rsh[fv.rix[j]];
+            const double rS = r.x, rH = r.y;
+            const double2 cur = cell[(i - 1) * k + (j - 1)];
+            const uint32_t xcl = fv.clx[j];
+            double cS = cur.x, cH = cur.y;
+            for (int d = 3; d <= maxLoop + 2; d++) {
+              int ii = i - 1, jj = -ii - d + (j + i);
+              if (jj < 1) { ii -= (1 - jj); jj = 1; }
+              for (; ii > 0 && jj < j; --ii, ++jj) {
+                if (!((fv.rowmask[ii] >> (jj - 1)) & 1u)) continue;
+                double S, H;
+                flat_candidate(tab, cell[(ii - 1) * k + (jj - 1)], (uint32_t)(fv.actx[ii] | fv.bctx[jj]), xcl, i - ii - 1, j - jj - 1, &S, &H);
+                const double G1 = H + rH - kTK * (S + rS), G2 = cH + rH - kTK * (cS + rS);
+                if (!(G1 < G2)) { S = -1.0; H = INFINITY; }
+                if (S < kMinEntropyCutoff) { S = kMinEntropy; H = 0.0; }
+                if (isfinite(H)) { cS = S; cH = H; }
+              }
+            }
+            cell[(i - 1) * k + (j - 1)] = make_double2(cS, cH);
+          }
+        } else if (cellmine) {
+          const double2 r = rsh[fv.rix[j]];
+          const double2 cur = cell[(i - 1) * k + (j - 1)];
+          const double Gcur = cur.y + r.y - kTK * (cur.x + r.x);
+          if (fv.bG[j] < Gcur) cell[(i - 1) * k + (j - 1)] = make_double2(fv.bS[j], fv.bH[j]);
+        }
+        __syncwarp(gmask);
+      }
+    }
+
+    // ---------------- best terminal pair ----------------
+    double bG = INFINITY; int bkey = 0x7fffffff;
+    {
+      const int i_lo = A.type == MSSPE_THAL_ANY ? 1 : k;
+      for (int i = i_lo + gl; i <= k; i += GROUP) {
+        const int a = n1[i];
+        for (uint32_t bj = fv.rowmask[i]; bj; bj &= bj - 1u) {
+          const int j = __ffs(bj);
+          const int ri = (a * 5 + n1[i + 1]) * 5 + n2[j + 1];
+          const double2 r = rsh[ri];
+          const double rS = r.x + kSmallNonZero, rH = r.y + kSmallNonZero;
+          const double2 c = cell[(i - 1) * k + (j - 1)];
+          const double G1 = (c.y + rH + kDHi) - kTK * (c.x + rS + kDSi);
+          const int key = i * 64 + j;
+          if (G1 < bG || (G1 == bG && key < bkey)) { bG = G1; bkey = key; }
+        }
+      }
+      double mG = bG;
+#pragma unroll
+      for (int o = GROUP / 2; o > 0; o >>= 1) mG = fmin(mG, __shfl_xor_sync(gmask, mG, o, GROUP));
+      int mk = (bG == mG && isfinite(bG)) ? bkey : 0x7fffffff;
+      mk = (int)__reduce_min_sync(gmask, (uint32_t)mk);
+      bG = mG; bkey = mk;
+    }
+    const bool none = !isfinite(bG);  // no base pair anywhere (for END1: none in the last row)
+    int bi = none ? (A.type == MSSPE_THAL_ANY ? 1 : k) : (bkey >> 6);
+    int bjx = none ? 1 : (bkey & 63);
+    if (none && A.type != MSSPE_THAL_ANY) { bi = 1; bjx = 1; }  // `if (!isFinite(bestG)) bestI = bestJ = 1`
+    const bool has_struct = (fv.rowmask[bi] >> (bjx - 1)) & 1u;
+    msspe_thal_out res;
+    res.ds = 0; res.dh = 0; res.dg = 0; res.tm = 0; res.no_structure = 1; res.n_bp = 0;
+    if (has_struct) {
+      const int ri = (n1[bi] * 5 + n1[bi + 1]) * 5 + n2[bjx + 1];
+      const double2 bc = cell[(bi - 1) * k + (bjx - 1)];
+      const double dH = bc.y + rsh[ri].y + kDHi;
+      const double dS = bc.x + rsh[ri].x + kDSi;
+      // ---------------- traceback: count paired positions ----------------
+      int i = bi, j = bjx, pairs = 1;
+      if (A.pairing && gl == 0) A.pairing[p * MSSPE_MAX_OLIGO + (i - 1)] = (uint8_t)j;
+      for (int guard = 0; guard < ((A.dbg & 2) ? 0 : 2 * k + 2); guard++) {
+        const int li = (n1[i] * 5 + n1[i - 1]) * 5 + n2[j - 1];
+        const double2 c = cell[(i - 1) * k + (j - 1)];
+        if (eq2(c.x, lsh[li].x) && eq2(c.y, lsh[li].y)) break;
+        if (i > 1 && j > 1 && ((fv.rowmask[i - 1] >> (j - 2)) & 1u)) {
+          const double2 st = tab[FT_STACK + i4(n1[i - 1], n1[i], n2[j - 1], n2[j])];
+          const double2 pc = cell[(i - 2) * k + (j - 2)];
+          if (eq2(c.x, st.x + pc.x) && eq2(c.y, st.y + pc.y)) {
+            i--; j--; pairs++;
+            if (A.pairing && gl == 0) A.pairing[p * MSSPE_MAX_OLIGO + (i - 1)] = (uint8_t)j;
+            continue;
+          }
+        }
+        int key = 0x7fffffff;
+        const uint32_t xcl = (i > 1 && j > 1) ? (uint32_t)i4(n2[j], n2[j - 1] & 3, n1[i], n1[i - 1] & 3) : 0u;   // only used when i, j >= 2
+        for (int l1 = gl; l1 <= i - 2; l1 += GROUP) {
+          const int ii = i - 1 - l1;
+          uint32_t cand = j >= 2 ? (fv.rowmask[ii] & ((1u << (j - 1)) - 1u)) : 0u;
+          if (l1 == 0 && j >= 2) cand &= ~(1u << (j - 2));
+          while (cand) {
+            const int jj = __ffs(cand);
+            cand &= cand - 1u;
+            const int l2 = j - jj - 1;
+            if (l1 + l2 > maxLoop) continue;
+            double S, H;
+            flat_candidate(tab, cell[(ii - 1) * k + (jj - 1)], (uint32_t)(fv.actx[ii] | fv.bctx[jj]), xcl, l1, l2, &S, &H);
+            if (eq2(c.x, S) && eq2(c.y, H)) key = min(key, (l1 + l2) * 64 + l1);
+          }
+        }
+        key = (int)__reduce_min_sync(gmask, (uint32_t)key);
+        if (key == 0x7fffffff) break;
+        const int l1 = key & 63, l2 = (key >> 6) - l1;
+        i = i - 1 - l1; j = j - 1 - l2; pairs++;
+        if (A.pairing && gl == 0) A.pairing[p * MSSPE_MAX_OLIGO + (i - 1)] = (uint8_t)j;
+      }
+      const int N = pairs - 1;  // (#paired bases in both strands)/2 - 1
+      const double t = (dH / (dS + (N * saltCorr) + RC)) - kAbsZero;
+      res.dg = dH - (t_user * (dS + (N * saltCorr)));
+      res.ds = dS + (N * saltCorr);
+      res.dh = dH;
+      res.tm = t;
+      res.no_structure = 0;
+      res.n_bp = pairs;
+    }
+    if (gl == 0) {
+      if (A.out) A.out[p] = res;
+      if (A.matrix) {
+        const unsigned long long pair = (unsigned long long)(A.row_begin + p / A.n) * A.n + (p % A.n);
+        if (res.no_structure) {
+          const unsigned long long at = atomicAdd(A.n_nostruct, 1ull);
+          if (at < A.nostruct_cap) A.nostruct[at] = pair;
+        } else if (res.dg < A.dg_limit) {
+          const unsigned long long at = atomicAdd(A.n_edges, 1ull);
+          if (at < A.edge_cap) { A.edges[at].pair = pair; A.edges[at].dg = res.dg; }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- device: dimer, one THREAD per ordered pair (oligos <= 16 nt)
+// The same algorithm and results once more, mapped the other way round: the warp kernels above spread ONE pair over 32
+// lanes and pay ~12,000 warp instructions per 13-mer pair, most of them bookkeeping that does not shrink with the work
+// (ncu: profiles/r2s3_thal_flat*.txt).  A 13-mer pair has only ~42 paired cells and ~380 loop candidates, so here every
+// lane walks its own pair: the DP matrix of a pair lives in that thread's local memory (k*k (S,H) cells, L1/L2-resident),
+// the tables in shared memory (one (S,H) table, flat_candidate), the pairing masks are four registers.  Lanes diverge
+// only in the trip counts of the bit loops; the scalar scan order of Primer3 is reproduced by the (dG, key) minimum as in
+// the warp kernels.
+constexpr int TK_MAX = 16;
+struct ThreadShared : FlatShared {   // per block: the tables + what phase (A) of a row parks for the flat candidate loop
+  double gcur[TK_MAX][DIMER_THREADS];     // dG of the q-th paired cell of the row as it stands after (A)
+  uint16_t meta[TK_MAX][DIMER_THREADS];   // closing context i4(n2[j], n2[j-1], n1[i], n1[i-1]) | rsh index << 8
+};
+__global__ void __launch_bounds__(DIMER_THREADS)
+thal_dimer_thread_kernel(const DimerArgs A) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  ThreadShared& sh = *reinterpret_cast<ThreadShared*>(dyn_smem);
+  const int k = A.k;
+  const int tid = threadIdx.x;
+  {  // stage tables
+    const ThalDeviceTables* T = A.T;
+    for (int x = tid; x < 256; x += DIMER_THREADS) {
+      const int a = x >> 6, b = (x >> 4) & 3, c = (x >> 2) & 3, d = x & 3;
+      const int g = THAL_IDX4(a, b, c, d);
+      sh.tab[FT_STACK + x] = make_double2(T->stackS[g], T->stackH[g]);
+      sh.tab[FT_INT2 + x] = make_double2(T->stackint2S[g], T->stackint2H[g]);
+      sh.tab[FT_TST + x] = make_double2(T->tstackS[g], T->tstackH[g]);
+    }
+    for (int x = tid; x < 200; x += DIMER_THREADS) {
+      (&sh.lsh[0][0])[x] = make_double2((&A.C->lshS[0][0])[x], (&A.C->lshH[0][0])[x]);
+      (&sh.rsh[0][0])[x] = make_double2((&A.C->rshS[0][0])[x], (&A.C->rshH[0][0])[x]);
+    }
+    for (int x = tid; x < 30; x += DIMER_THREADS) {
+      sh.tab[FT_INTERIOR + x] = make_double2(T->interiorS[x], T->interiorH[x]);
+      sh.tab[FT_BULGE + x] = make_double2(T->bulgeS[x], T->bulgeH[x]);
+    }
+    for (int x = tid; x < 16; x += DIMER_THREADS) sh.tab[FT_ATP + x] = make_double2(T->atpS[(x >> 2) * 5 + (x & 3)], T->atpH[(x >> 2) * 5 + (x & 3)]);
+    if (tid == 0) sh.tab[FT_ZERO] = make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  const double2* __restrict__ tab = sh.tab;
+  const int maxLoop = A.C->maxLoop;
+  const double saltCorr = A.C->saltCorr, t_user = A.C->t_user_K;
+  // (S,H) of the PAIRED cells only, row-major in the order the fill visits them, in this thread's own contiguous piece of
+  // a global scratch buffer: ~42 cells = 670 B per 13-mer pair, so the pieces of all resident threads stay in L2 (thread-
+  // local arrays are interleaved by 4-byte words: one divergent 16-byte access touched 4 sectors and the k*k array of every
+  // resident thread was 4x the L2 -- 53 KB of DRAM traffic per pair, measured).  slot(i,j) = cells of rows < i + paired
+  // columns of row i below j.
+  double2* const cell = A.scratch + ((size_t)blockIdx.x * DIMER_THREADS + tid) * (size_t)(k * k);
+
+  for (unsigned long long p = (unsigned long long)blockIdx.x * DIMER_THREADS + tid; p < A.n_pairs; p += (unsigned long long)gridDim.x * DIMER_THREADS) {
+    uint64_t ca, cb;
+    if (A.matrix) { ca = A.a[A.row_begin + p / A.n]; cb = A.b[p % A.n]; }
+    else { ca = A.a[p]; cb = A.b[p]; }
+    // numSeq1 = oligo1 5'->3': n1(i) = (ca >> 2(k-i)) & 3; numSeq2 = oligo2 REVERSED: n2(j) = (cb >> 2(j-1)) & 3; N (4) outside 1..k
+    auto n1 = [&](int i) -> uint32_t { return (i < 1 || i > k) ? 4u : (uint32_t)(ca >> (2 * (k - i))) & 3u; };
+    auto n2 = [&](int j) -> uint32_t { return (j < 1 || j > k) ? 4u : (uint32_t)(cb >> (2 * (j - 1))) & 3u; };
+    uint32_t cm0 = 0u, cm1 = 0u, cm2 = 0u, cm3 = 0u;   // columns of A, C, G, T in the reversed second oligo
+    for (int j = 1; j <= k; j++) {
+      const uint32_t bit = 1u << (j - 1), y = (uint32_t)(cb >> (2 * (j - 1))) & 3u;
+      cm0 |= y == 0u ? bit : 0u; cm1 |= y == 1u ? bit : 0u; cm2 |= y == 2u ? bit : 0u; cm3 |= y == 3u ? bit : 0u;
+    }
+    auto rowmask = [&](int i) -> uint32_t {            // columns j that pair with row i (1 <= i <= k)
+      const uint32_t x = (uint32_t)(ca >> (2 * (k - i))) & 3u;
+      return x == 0u ? cm3 : x == 1u ? cm2 : x == 2u ? cm1 : cm0;
+    };
+    // context of an inner pair (ii,jj), ii, jj <= k - 1: i4(n1[ii], n1[ii+1], n2[jj], n2[jj+1])
+    auto ctx_in = [&](int ii, int jj) -> uint32_t {
+      const uint32_t av = (uint32_t)(ca >> (2 * (k - ii - 1))) & 15u;          // n1[ii] << 2 | n1[ii+1]
+      const uint32_t bv = (uint32_t)(cb >> (2 * (jj - 1))) & 15u;              // n2[jj] | n2[jj+1] << 2
+      return (av << 4) | ((bv & 3u) << 2) | (bv >> 2);
+    };
+    auto slot_of = [&](int i, int j) -> int {         // general form (tail); the fill keeps the row bases incrementally
+      int base = 0;
+      for (int r = 1; r < i; r++) base += __popc(rowmask(r));
+      return base + __popc(rowmask(i) & ((1u << (j - 1)) - 1u));
+    };
+    const int sym = ((k & 1) == 0 && revcomp_code(ca, k) == ca && revcomp_code(cb, k) == cb) ? 1 : 0;
+    const double RC = A.C->RC[sym];
+    const double2* __restrict__ lsh = sh.lsh[sym];
+    const double2* __restrict__ rsh = sh.rsh[sym];
+    const double* __restrict__ t0tab = A.C->t0[sym];
+
+    // ---------------- fill ----------------
+    // Per row: (A) the end / stack terms of the row's paired cells; (B) ONE flat loop over all bulge / internal-loop
+    // candidates of all cells of the row: a lane whose inner row or whose cell is exhausted moves on inside the same
+    // iteration, so the lanes of a warp (32 different pairs) diverge by their candidate COUNT per row only -- with the plain
+    // cell / inner-row / column nest 7 of 32 lanes were active (ncu).  What the loop needs per cell (dG of the cell as it
+    // stands, closing context, end-table index) is parked in shared memory by (A).
+    int rb_i = 0, rb_prev = 0;                        // cells in rows < i, cells in rows < i - 1
+    for (int i = 1; i <= k; i++) {
+      const uint32_t a = n1(i), am = n1(i - 1), ap = n1(i + 1);
+      const uint32_t rm_i = rowmask(i), rm_prev = i > 1 ? rowmask(i - 1) : 0u;
+      int q = 0;
+      for (uint32_t bj = rm_i; bj; bj &= bj - 1u, q++) {
+        const int j = __ffs(bj);
+        const uint32_t b = n2(j), bm = n2(j - 1), bp = n2(j + 1);
+        const int li = (a * 5 + am) * 5 + bm;
+        const double2 l = lsh[li];
+        double S = l.x, H = l.y;
+        if (i > 1 && j > 1) {
+          const int rn = ap * 5 + bp;
+          const double2 r = rsh[a * 25 + rn];
+          const double rS = r.x, rH = r.y;
+          double S0 = S, H0 = H, S1, H1, T1;
+          const double T0 = __ldg(&t0tab[li * 25 + rn]);   // (H0 + kDHi + rH) / (S0 + kDSi + rS + RC), tabulated on the host
+          const double2 st = tab[FT_STACK + i4(am, a, bm, b)];
+          const bool prev_bp = (rm_prev >> (j - 2)) & 1u;
+          if (prev_bp && isfinite(st.y)) {
+            const double2 pc = cell[rb_prev + __popc(rm_prev & ((1u << (j - 2)) - 1u))];
+            S1 = pc.x + st.x;
+            H1 = pc.y + st.y;
+            T1 = (H1 + kDHi + rH) / (S1 + kDSi + rS + RC);
+          } else {
+            S1 = -1.0; H1 = INFINITY;
+            T1 = (H1 + kDHi) / (S1 + kDSi + RC);
+          }
+          if (S1 < kMinEntropyCutoff) { S1 = kMinEntropy; H1 = 0.0; }
+          if (S0 < kMinEntropyCutoff) { S0 = kMinEntropy; H0 = 0.0; }
+          if (T1 > T0) { S = S1; H = H1; } else if (T0 >= T1) { S = S0; H = H0; }
+          sh.gcur[q][tid] = H + rH - kTK * (S + rS);
+          sh.meta[q][tid] = (uint16_t)(i4(b, bm & 3, a, am & 3) | ((a * 25 + rn) << 8));
+        }
+        cell[rb_i + q] = make_double2(S, H);
+      }
+      if (i > 1 && (rm_i & ~1u) && !(A.dbg & 1)) {
+        uint32_t bjr = rm_i & ~1u, clampbits = 0u;
+        int qq = (int)(rm_i & 1u) - 1;                 // index of the current cell among the row's paired cells
+        int j = 0, ii = 1, rb_ii = 0;
+        uint32_t cand = 0u, rm_ii = 0u, below = 0u, xcl = 0u;
+        double Gc = 0.0, rS = 0.0, rH = 0.0, bG = INFINITY, bS = -1.0, bH = INFINITY;
+        int bkey = 0x7fffffff;
+        for (;;) {
+          while (cand == 0u) {
+            if (j > 0 && ii > 1) { ii--; rm_ii = rowmask(ii); rb_ii -= __popc(rm_ii); cand = rm_ii & below; continue; }
+            if (j > 0 && bG < Gc && !((clampbits >> (j - 1)) & 1u)) cell[rb_i + qq] = make_double2(bS, bH);
+            if (bjr == 0u) { j = -1; break; }
+            j = __ffs(bjr); bjr &= bjr - 1u; qq++;
+            Gc = sh.gcur[qq][tid];
+            const uint32_t m = sh.meta[qq][tid];
+            xcl = m & 0xffu;
+            const double2 r = rsh[m >> 8];
+            rS = r.x; rH = r.y;
+            bG = INFINITY; bS = -1.0; bH = INFINITY; bkey = 0x7fffffff;
+            below = (1u << (j - 1)) - 1u;
+            ii = i - 1; rm_ii = rm_prev; rb_ii = rb_prev;
+            cand = rm_prev & below & ~(1u << (j - 2));
+          }
+          if (j < 0) break;
+          const int jj = __ffs(cand);
+          cand &= cand - 1u;
+          const int l1 = i - ii - 1, l2 = j - jj - 1;
+          if (l1 + l2 <= maxLoop) {
+            double cS, cH;
+            flat_candidate(tab, cell[rb_ii + __popc(rm_ii & ((1u << (jj - 1)) - 1u))], ctx_in(ii, jj), xcl, l1, l2, &cS, &cH);
+            if (isfinite(cH)) {
+              if (cS < kMinEntropyCutoff) clampbits |= 1u << (j - 1);
+              const double G1 = cH + rH - kTK * (cS + rS);
+              const int key = (l1 + l2) * 64 + l1;
+              if (G1 < bG || (G1 == bG && key < bkey)) { bG = G1; bkey = key; bS = cS; bH = cH; }
+            }
+          }
+        }
+        // An entropy below the cutoff re-bases the cell mid-scan: replay those cells' scans in the scalar order.
+        for (; clampbits; clampbits &= clampbits - 1u) {
+          const int jc = __ffs(clampbits);
+          const int sl = rb_i + __popc(rm_i & ((1u << (jc - 1)) - 1u));
+          const uint32_t bc = n2(jc), bmc = n2(jc - 1);
+          const uint32_t xc = (uint32_t)i4(bc, bmc & 3, a, am & 3);
+          const double2 r = rsh[a * 25 + ap * 5 + n2(jc + 1)];
+          double cS = cell[sl].x, cH = cell[sl].y;
+          for (int d = 3; d <= maxLoop + 2; d++) {
+            int i2 = i - 1, j2 = -i2 - d + (jc + i);
+            if (j2 < 1) { i2 -= (1 - j2); j2 = 1; }
+            for (; i2 > 0 && j2 < jc; --i2, ++j2) {
+              if (!((rowmask(i2) >> (j2 - 1)) & 1u)) continue;
+              double xS, xH;
+              flat_candidate(tab, cell[slot_of(i2, j2)], ctx_in(i2, j2), xc, i - i2 - 1, jc - j2 - 1, &xS, &xH);
+              const double G1 = xH + r.y - kTK * (xS + r.x), G2 = cH + r.y - kTK * (cS + r.x);
+              if (!(G1 < G2)) { xS = -1.0; xH = INFINITY; }
+              if (xS < kMinEntropyCutoff) { xS = kMinEntropy; xH = 0.0; }
+              if (isfinite(xH)) { cS = xS; cH = xH; }
+            }
+          }
+          cell[sl] = make_double2(cS, cH);
+        }
+      }
+      rb_prev = rb_i; rb_i += __popc(rm_i);
+    }
+
+    // ---------------- best terminal pair ----------------
+    double bG = INFINITY; int bkey = 0x7fffffff;
+    const int i_first = A.type == MSSPE_THAL_ANY ? 1 : k;
+    int sl = slot_of(i_first, 1);                     // cells are stored in exactly this order
+    for (int i = i_first; i <= k; i++) {
+      const uint32_t a = n1(i), ap = n1(i + 1);
+      for (uint32_t bj = rowmask(i); bj; bj &= bj - 1u) {
+        const int j = __ffs(bj);
+        const double2 r = rsh[(a * 5 + ap) * 5 + n2(j + 1)];
+        const double rS = r.x + kSmallNonZero, rH = r.y + kSmallNonZero;
+        const double2 c = cell[sl++];
+        const double G1 = (c.y + rH + kDHi) - kTK * (c.x + rS + kDSi);
+        const int key = i * 64 + j;
+        if (G1 < bG || (G1 == bG && key < bkey)) { bG = G1; bkey = key; }
+      }
+    }
+    const bool none = !isfinite(bG);  // no base pair anywhere (for END1: none in the last row)
+    int bi = none ? (A.type == MSSPE_THAL_ANY ? 1 : k) : (bkey >> 6);
+    int bjx = none ? 1 : (bkey & 63);
+    if (none && A.type != MSSPE_THAL_ANY) { bi = 1; bjx = 1; }  // `if (!isFinite(bestG)) bestI = bestJ = 1`
+    const bool has_struct = (rowmask(bi) >> (bjx - 1)) & 1u;
+    msspe_thal_out res;
+    res.ds = 0; res.dh = 0; res.dg = 0; res.tm = 0; res.no_structure = 1; res.n_bp = 0;
+    if (has_struct) {
+      const double2 rb = rsh[(n1(bi) * 5 + n1(bi + 1)) * 5 + n2(bjx + 1)];
+      const double2 bc = cell[slot_of(bi, bjx)];
+      const double dH = bc.y + rb.y + kDHi;
+      const double dS = bc.x + rb.x + kDSi;
+      // ---------------- traceback: count paired positions ----------------
+      int i = bi, j = bjx, pairs = 1;
+      if (A.pairing) A.pairing[p * MSSPE_MAX_OLIGO + (i - 1)] = (uint8_t)j;
+      for (int guard = 0; guard < ((A.dbg & 2) ? 0 : 2 * k + 2); guard++) {
+        const double2 l = lsh[(n1(i) * 5 + n1(i - 1)) * 5 + n2(j - 1)];
+        const double2 c = cell[slot_of(i, j)];
+        if (eq2(c.x, l.x) && eq2(c.y, l.y)) break;
+        if (i > 1 && j > 1 && ((rowmask(i - 1) >> (j - 2)) & 1u)) {
+          const double2 st = tab[FT_STACK + i4(n1(i - 1), n1(i), n2(j - 1), n2(j))];
+          const double2 pc = cell[slot_of(i - 1, j - 1)];
+          if (eq2(c.x, st.x + pc.x) && eq2(c.y, st.y + pc.y)) {
+            i--; j--; pairs++;
+            if (A.pairing) A.pairing[p * MSSPE_MAX_OLIGO + (i - 1)] = (uint8_t)j;
+            continue;
+          }
+        }
+        int key = 0x7fffffff;
+        if (i > 1 && j > 1) {
+          const uint32_t xcl = (uint32_t)i4(n2(j), n2(j - 1) & 3, n1(i), n1(i - 1) & 3);
+          for (int ii = i - 1; ii >= 1; ii--) {
+            uint32_t cand = rowmask(ii) & ((1u << (j - 1)) - 1u);
+            if (ii == i - 1) cand &= ~(1u << (j - 2));
+            const int l1 = i - ii - 1;
+            while (cand) {
+              const int jj = __ffs(cand);
+              cand &= cand - 1u;
+              const int l2 = j - jj - 1;
+              if (l1 + l2 > maxLoop) continue;
+              double cS, cH;
+              flat_candidate(tab, cell[slot_of(ii, jj)], ctx_in(ii, jj), xcl, l1, l2, &cS, &cH);
+              if (eq2(c.x, cS) && eq2(c.y, cH)) key = min(key, (l1 + l2) * 64 + l1);
+            }
+          }
+        }
+        if (key == 0x7fffffff) break;
+        const int l1 = key & 63, l2 = (key >> 6) - l1;
+        i = i - 1 - l1; j = j - 1 - l2; pairs++;
+        if (A.pairing) A.pairing[p * MSSPE_MAX_OLIGO + (i - 1)] = (uint8_t)j;
+      }
+      const int N = pairs - 1;  // (#paired bases in both strands)/2 - 1
+      const double t = (dH / (dS + (N * saltCorr) + RC)) - kAbsZero;
+      res.dg = dH - (t_user * (dS + (N * saltCorr)));
+      res.ds = dS + (N * saltCorr);
+      res.dh = dH;
+      res.tm = t;
+      res.no_structure = 0;
+      res.n_bp = pairs;
+    }
+    if (A.out) A.out[p] = res;
+    if (A.matrix) {
+      const unsigned long long pair = (unsigned long long)(A.row_begin + p / A.n) * A.n + (p % A.n);
+      if (res.no_structure) {
+        const unsigned long long at = atomicAdd(A.n_nostruct, 1ull);
+        if (at < A.nostruct_cap) A.nostruct[at] = pair;
+      } else if (res.dg < A.dg_limit) {
+        const unsigned long long at = atomicAdd(A.n_edges, 1ull);
+        if (at < A.edge_cap) { A.edges[at].pair = pair; A.edges[at].dg = res.dg; }
       }
     }
   }
@@ -861,31 +1540,35 @@ struct DeviceBuf {  // stream-ordered scratch, returned to the pool when the cal
 int launch_dimer(msspe_ctx* c, DimerArgs& A, cudaStream_t st) {
   if (A.n_pairs == 0) return MSSPE_OK;
   const int k = A.k;
-  const int sub = k <= 16 ? 8 : 16;  // lanes per cell in flight (inner rows <= 2*sub)
-  const int groups = DIMER_THREADS / 32;
+  // MSSPE_THAL_KERNEL = thread (default for oligos <= 16 nt) | flat (default beyond) | legacy: the same results three ways
+  static const char* which = getenv("MSSPE_THAL_KERNEL");
+  const bool legacy = which && !strcmp(which, "legacy");
+  const bool thread = !legacy && k <= TK_MAX && !(which && !strcmp(which, "flat"));
+  const int sub = k <= 16 ? 8 : 16;  // legacy: lanes per cell in flight (inner rows <= 2*sub)
+  const int groups = thread ? DIMER_THREADS : DIMER_THREADS / 32;   // pairs per block and sweep
   const size_t cell_bytes = (size_t)k * k * 16;
-  const size_t grp_bytes = (cell_bytes + (size_t)(k + 2) * 4 + 2 * (size_t)(k + 2) + 15) & ~(size_t)15;
-  const size_t smem = ((sizeof(DimerShared) + 15) & ~(size_t)15) + groups * grp_bytes;
+  const size_t grp_bytes = thread ? 0 : legacy ? ((cell_bytes + (size_t)(k + 2) * 4 + 2 * (size_t)(k + 2) + 15) & ~(size_t)15) : flat_group_bytes(k);
+  const size_t smem = (((legacy ? sizeof(DimerShared) : thread ? sizeof(ThreadShared) : sizeof(FlatShared)) + 15) & ~(size_t)15) + (thread ? 0 : groups * grp_bytes);
   if (smem > c->smem_optin) { c->set_error("thal dimer: %zu B shared memory needed, device offers %zu", smem, c->smem_optin); return MSSPE_ERR_CAPACITY; }
   int per_sm = 1;
   unsigned long long blocks_needed = (A.n_pairs + groups - 1) / groups;
-  if (sub == 8) {
-    MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(thal_dimer_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, thal_dimer_kernel<8>, DIMER_THREADS, smem));
-  } else {
-    MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(thal_dimer_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, thal_dimer_kernel<16>, DIMER_THREADS, smem));
-  }
+  void (*kern)(const DimerArgs) = thread ? thal_dimer_thread_kernel : !legacy ? thal_dimer_flat_kernel : (sub == 8 ? thal_dimer_kernel<8> : thal_dimer_kernel<16>);
+  MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DIMER_THREADS, smem));
   if (per_sm < 1) per_sm = 1;
   const unsigned long long resident = (unsigned long long)c->sm_count * per_sm;
   const unsigned grid = (unsigned)(blocks_needed < resident ? blocks_needed : resident);
+  DeviceBuf scratch;
+  if (thread) {
+    MSSPE_CUDA_TRY(c, cudaMallocAsync(&(scratch.st = st, scratch.p), (size_t)grid * DIMER_THREADS * (size_t)(k * k) * sizeof(double2), st));
+    A.scratch = (double2*)scratch.p;
+  }
   {
     KPROF(c, KP_DIMER, st, A.n_pairs * 16)
-    if (sub == 8) thal_dimer_kernel<8><<<grid, DIMER_THREADS, smem, st>>>(A);
-    else thal_dimer_kernel<16><<<grid, DIMER_THREADS, smem, st>>>(A);
+    kern<<<grid, DIMER_THREADS, smem, st>>>(A);
   }
   MSSPE_CUDA_TRY(c, cudaGetLastError());
-  return MSSPE_OK;
+  return MSSPE_OK;   // the scratch returns to the pool in stream order
 }
 
 // Hairpin launch: the per-thread DP scratch in shared memory (as many threads per block as fit) when that keeps the

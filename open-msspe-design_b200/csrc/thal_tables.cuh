@@ -34,4 +34,5 @@ struct ThalDimerConsts {
   double t_user_K;       // cond.temp_c + 273.15
   int maxLoop;
   int pad;
+  double t0[2][2500];    // [sym][li * 25 + rn]: (lshH + 200 + rshH) / (lshS - 5.7 + rshS + RC), the first quotient of the stack test
 };

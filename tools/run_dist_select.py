@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """One design job over N GPUs (torchrun): every rank loads the columns of its partition range, builds its index, and
 msspe_select_both_dist must return exactly what one GPU returns for the whole alignment.
-  torchrun --nproc-per-node 2 tools/run_dist_select.py [case ...]      cases: small, repeats, cfg2, cfg5shard, tiny_k"""
+  torchrun --nproc-per-node 2 tools/run_dist_select.py [case ...]      cases: small, repeats, cfg2, cfg5shard, cfg3xN, tiny_k"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "open-msspe-design_b200"))
@@ -43,6 +43,9 @@ def case(name):
         return g, k, 1000, 10, (W, S, w)
     if name == "cfg5shard":
         return synth.synth_genomes(12_500, 30_000, 5, clades=256, p_clade=0.10, p_leaf=0.01), 13, 1000, 10, (W, S, w)
+    if name == "cfg3xN":    # bench.py --gpus N: N x 10,000 genomes of the cfg3 shape
+        cfgd = dict(synth.CONFIGS["cfg3"]); k = cfgd.pop("k"); cfgd["n"] *= world
+        return synth.synth_genomes(**cfgd), k, 1000, 2, (W, S, w)
     raise SystemExit("unknown case " + name)
 
 
