@@ -892,6 +892,7 @@ constexpr int TK_MAX = 16;
 struct ThreadShared : FlatShared {   // per block: the tables + what phase (A) of a row parks for the flat candidate loop
   double gcur[TK_MAX][DIMER_THREADS];     // dG of the q-th paired cell of the row as it stands after (A)
   uint16_t meta[TK_MAX][DIMER_THREADS];   // closing context i4(n2[j], n2[j-1], n1[i], n1[i-1]) | rsh index << 8
+  uint16_t rmask[TK_MAX + 1][DIMER_THREADS];   // rowmask of this thread's pair, rows 1 .. k (k <= 16 columns)
 };
 __global__ void __launch_bounds__(DIMER_THREADS)
 thal_dimer_thread_kernel(const DimerArgs A) {
@@ -942,10 +943,11 @@ thal_dimer_thread_kernel(const DimerArgs A) {
       const uint32_t bit = 1u << (j - 1), y = (uint32_t)(cb >> (2 * (j - 1))) & 3u;
       cm0 |= y == 0u ? bit : 0u; cm1 |= y == 1u ? bit : 0u; cm2 |= y == 2u ? bit : 0u; cm3 |= y == 3u ? bit : 0u;
     }
-    auto rowmask = [&](int i) -> uint32_t {            // columns j that pair with row i (1 <= i <= k)
+    for (int i = 1; i <= k; i++) {                     // columns j that pair with row i, parked in this thread's column of smem
       const uint32_t x = (uint32_t)(ca >> (2 * (k - i))) & 3u;
-      return x == 0u ? cm3 : x == 1u ? cm2 : x == 2u ? cm1 : cm0;
-    };
+      sh.rmask[i][tid] = (uint16_t)(x == 0u ? cm3 : x == 1u ? cm2 : x == 2u ? cm1 : cm0);
+    }
+    auto rowmask = [&](int i) -> uint32_t { return sh.rmask[i][tid]; };
     // context of an inner pair (ii,jj), ii, jj <= k - 1: i4(n1[ii], n1[ii+1], n2[jj], n2[jj+1])
     auto ctx_in = [&](int ii, int jj) -> uint32_t {
       const uint32_t av = (uint32_t)(ca >> (2 * (k - ii - 1))) & 15u;          // n1[ii] << 2 | n1[ii+1]
@@ -1039,7 +1041,8 @@ thal_dimer_thread_kernel(const DimerArgs A) {
               if (cS < kMinEntropyCutoff) clampbits |= 1u << (j - 1);
               const double G1 = cH + rH - kTK * (cS + rS);
               const int key = (l1 + l2) * 64 + l1;
-              if (G1 < bG || (G1 == bG && key < bkey)) { bG = G1; bkey = key; bS = cS; bH = cH; }
+              const bool better = (G1 < bG) | ((G1 == bG) & (key < bkey));
+              bG = better ? G1 : bG; bkey = better ? key : bkey; bS = better ? cS : bS; bH = better ? cH : bH;
             }
           }
         }
@@ -1556,6 +1559,7 @@ int launch_dimer(msspe_ctx* c, DimerArgs& A, cudaStream_t st) {
   MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DIMER_THREADS, smem));
   if (per_sm < 1) per_sm = 1;
+  if (getenv("MSSPE_DEBUG_TIMERS")) fprintf(stderr, "[msspe] thal dimer kernel %s: %zu B shared memory per block, %d blocks per SM\n", thread ? "thread" : legacy ? "legacy" : "flat", smem, per_sm);
   const unsigned long long resident = (unsigned long long)c->sm_count * per_sm;
   const unsigned grid = (unsigned)(blocks_needed < resident ? blocks_needed : resident);
   DeviceBuf scratch;
