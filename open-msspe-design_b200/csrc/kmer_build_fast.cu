@@ -22,7 +22,7 @@
 namespace {
 
 constexpr int ENCF_WARPS = 8;
-constexpr int SORT_T = 512, SORT_ITEMS = 8, SORT_TILE = SORT_T * SORT_ITEMS, SORT_WARPS = SORT_T / 32;
+constexpr int SORT_T = 256, SORT_ITEMS = 16, SORT_TILE = SORT_T * SORT_ITEMS, SORT_WARPS = SORT_T / 32;
 constexpr unsigned long long KEY_NONE = ~0ull;
 
 __device__ __forceinline__ uint32_t base2f(uint8_t c) {
@@ -454,8 +454,8 @@ int msspe_build_fast(msspe_ctx* c) {
   const uint32_t max_buckets = 1u << maxbits;
   const size_t sc_smem_max = scatter_smem(max_buckets);
   static const int scatter_minb = getenv("MSSPE_SCATTER_MINB") ? atoi(getenv("MSSPE_SCATTER_MINB")) : 3;
-  MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(fast_scatter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem_max));
   MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(fast_scatter_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem_max));
+  MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(fast_scatter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem_max));
   FastDir F[2];
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[2], st));
   float enc_ms_total = 0.f;
@@ -494,8 +494,8 @@ int msspe_build_fast(msspe_ctx* c) {
         fast_digit_base_kernel<<<1, 1024, 0, st>>>(f.dtot, nbk); }
       const size_t sm = scatter_smem(nbk);
       { KPROF(c, KP_SORT_SCATTER, st, GS * 16)
-        if (scatter_minb == 3) fast_scatter_kernel<3><<<nb, SORT_T, sm, st>>>(f.ka, GS, n_dev, pass[p].shift, nbk, f.hist, f.dtot, nb, f.kb);
-        else fast_scatter_kernel<2><<<nb, SORT_T, sm, st>>>(f.ka, GS, n_dev, pass[p].shift, nbk, f.hist, f.dtot, nb, f.kb); }
+        if (scatter_minb == 4) fast_scatter_kernel<4><<<nb, SORT_T, sm, st>>>(f.ka, GS, n_dev, pass[p].shift, nbk, f.hist, f.dtot, nb, f.kb);
+        else fast_scatter_kernel<3><<<nb, SORT_T, sm, st>>>(f.ka, GS, n_dev, pass[p].shift, nbk, f.hist, f.dtot, nb, f.kb); }
       std::swap(f.ka, f.kb);
     }
     { KPROF(c, KP_CSR, st, GS * 12)

@@ -1540,13 +1540,39 @@ struct DeviceBuf {  // stream-ordered scratch, returned to the pool when the cal
   ~DeviceBuf() { if (p) cudaFreeAsync(p, st); }
 };
 
+int launch_dimer_warp(msspe_ctx* c, DimerArgs& A, cudaStream_t st) {   // thal_dimer_kernel: one warp per pair (small batches, latency)
+  const int k = A.k;
+  const int sub = k <= 16 ? 8 : 16;
+  const int groups = DIMER_THREADS / 32;
+  const size_t grp_bytes = ((size_t)k * k * 16 + (size_t)(k + 2) * 4 + 2 * (size_t)(k + 2) + 15) & ~(size_t)15;
+  const size_t smem = ((sizeof(DimerShared) + 15) & ~(size_t)15) + groups * grp_bytes;
+  if (smem > c->smem_optin) { c->set_error("thal dimer: %zu B shared memory needed, device offers %zu", smem, c->smem_optin); return MSSPE_ERR_CAPACITY; }
+  int per_sm = 1;
+  void (*kern)(const DimerArgs) = sub == 8 ? thal_dimer_kernel<8> : thal_dimer_kernel<16>;
+  MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MSSPE_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DIMER_THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  const unsigned long long blocks_needed = (A.n_pairs + groups - 1) / groups, resident = (unsigned long long)c->sm_count * per_sm;
+  const unsigned grid = (unsigned)(blocks_needed < resident ? blocks_needed : resident);
+  {
+    KPROF(c, KP_DIMER, st, A.n_pairs * 16)
+    kern<<<grid, DIMER_THREADS, smem, st>>>(A);
+  }
+  MSSPE_CUDA_TRY(c, cudaGetLastError());
+  return MSSPE_OK;
+}
+
 int launch_dimer(msspe_ctx* c, DimerArgs& A, cudaStream_t st) {
   if (A.n_pairs == 0) return MSSPE_OK;
   const int k = A.k;
   // MSSPE_THAL_KERNEL = thread (default for oligos <= 16 nt) | flat (default beyond) | legacy: the same results three ways
-  static const char* which = getenv("MSSPE_THAL_KERNEL");
+  const char* which = getenv("MSSPE_THAL_KERNEL");
   const bool legacy = which && !strcmp(which, "legacy");
-  const bool thread = !legacy && k <= TK_MAX && !(which && !strcmp(which, "flat"));
+  // one thread per pair needs a few pairs per lane of the whole GPU to pay (a pair is ~70,000 dependent thread
+  // instructions: 2000 self-dimer pairs took 1.2 ms that way against 0.13 ms with a warp per pair)
+  const bool many = A.n_pairs >= (unsigned long long)c->sm_count * DIMER_THREADS * 8ull;
+  const bool thread = !legacy && k <= TK_MAX && !(which && !strcmp(which, "flat")) && (many || (which && !strcmp(which, "thread")));
+  if (!thread && !(which && !strcmp(which, "flat")) && k <= 16) return launch_dimer_warp(c, A, st);
   const int sub = k <= 16 ? 8 : 16;  // legacy: lanes per cell in flight (inner rows <= 2*sub)
   const int groups = thread ? DIMER_THREADS : DIMER_THREADS / 32;   // pairs per block and sweep
   const size_t cell_bytes = (size_t)k * k * 16;

@@ -56,9 +56,17 @@ def _compare(got, want_list, what):
     return exact, nbad
 
 
+# MSSPE_THAL_KERNEL picks one of the three exact dimer kernels (csrc/thal.cu): "thread" = one thread per pair (what large
+# batches of oligos <= 16 nt get), "flat" = one warp per pair with flat candidate enumeration (oligos > 16 nt), "legacy" =
+# one warp per pair, lanes over inner rows (small batches); None = the library's own choice.
+@pytest.mark.parametrize("kernel", [None, "thread", "flat", "legacy"])
 @pytest.mark.parametrize("k,ttype", [(13, 1), (13, 2), (15, 1), (16, 1), (20, 1), (31, 1), (32, 2), (8, 1)])
-def test_random_pairs_vs_oracle(eng, oracle_lib, k, ttype):
+def test_random_pairs_vs_oracle(eng, oracle_lib, monkeypatch, k, ttype, kernel):
     import msspe_b200 as m
+    if kernel:
+        monkeypatch.setenv("MSSPE_THAL_KERNEL", kernel)
+    else:
+        monkeypatch.delenv("MSSPE_THAL_KERNEL", raising=False)
     rng = np.random.default_rng(100 + k + ttype)
     n = 400 if k <= 16 else 150
     a = rng.integers(0, 4, (n, k))
