@@ -137,6 +137,8 @@ struct msspe_ctx {
   struct ThalDeviceTables* d_thal = nullptr;  // device copy of static tables (ntthal stand-ins: msspe_set_thal_params applies)
   struct ThalDeviceTables* d_thal_p3 = nullptr;  // Primer3's compiled-in tables (primer3_core stand-ins), never overridden
   msspe_thal_raw_params* raw_p3 = nullptr;
+  struct ThalDimerConsts* d_p3_consts = nullptr;  // per-run constants of the primer3_core stand-ins (fixed conditions): built once
+  struct ThalDimerConsts* h_p3_consts = nullptr;
   void* dist = nullptr;                        // select_dist.cu: NCCL communicator of the multi-GPU loop
   msspe_dimer_edge* xd_edges = nullptr;       // msspe_cross_dimer_device: lists of the last call (ctx-owned)
   uint64_t* xd_nostruct = nullptr;

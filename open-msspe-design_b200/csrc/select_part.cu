@@ -131,11 +131,27 @@ int msspe_select_partitioned(msspe_ctx* c, int ndirs, const int* dirs, uint32_t 
   A.ndirs = ndirs; A.U = U; A.CAP = (uint32_t)CAP; A.slots = c->slots; A.max_iter = max_iter; A.mms = mms;
   A.uniform_parts = (c->uniform_parts && c->uniform_parts <= 65536u) ? c->uniform_parts : 0u;
   A.seg_part = c->d_seg_part; A.max_ahead = 0xFFFFFFFFu;
+  // the loop's scratch of all directions comes as THREE slabs (zero-filled, 0xFF-filled, unfilled): 3 allocations and 2
+  // memsets per call instead of ~45 of each per direction (0.25 ms of host time in front of an idle GPU at cfg3)
   std::vector<void*> scratch;
+  struct Carve { void** p; uint64_t off; int kind; };
+  std::vector<Carve> carve;
+  uint64_t slab_bytes[3] = {0, 0, 0};
   auto alloc = [&](void** p, uint64_t bytes, int fill) -> int {
-    MSSPE_CUDA_TRY(c, cudaMallocAsync(p, bytes ? bytes : 4, st));
-    if (fill >= 0) MSSPE_CUDA_TRY(c, cudaMemsetAsync(*p, fill, bytes ? bytes : 4, st));
-    scratch.push_back(*p);
+    const int kind = fill == 0 ? 0 : (fill == 0xFF ? 1 : 2);
+    carve.push_back({p, slab_bytes[kind], kind});
+    slab_bytes[kind] += ((bytes ? bytes : 4) + 255u) & ~(uint64_t)255u;
+    return MSSPE_OK;
+  };
+  auto commit = [&]() -> int {
+    unsigned char* slab[3] = {nullptr, nullptr, nullptr};
+    for (int kd = 0; kd < 3; kd++) {
+      if (!slab_bytes[kd]) continue;
+      MSSPE_CUDA_TRY(c, cudaMallocAsync((void**)&slab[kd], slab_bytes[kd], st));
+      scratch.push_back(slab[kd]);
+      if (kd < 2) MSSPE_CUDA_TRY(c, cudaMemsetAsync(slab[kd], kd == 0 ? 0 : 0xFF, slab_bytes[kd], st));
+    }
+    for (const Carve& cv : carve) *cv.p = slab[cv.kind] + cv.off;
     return MSSPE_OK;
   };
   uint32_t max_multi = 0;
@@ -178,6 +194,10 @@ int msspe_select_partitioned(msspe_ctx* c, int ndirs, const int* dirs, uint32_t 
     PV_ALLOC(win_code, ((uint64_t)max_iter + 2) * 8, 0);
     PV_ALLOC(ctl, sizeof(PartCtl), 0);
 #undef PV_ALLOC
+  }
+  { int rc2 = commit(); if (rc2) return rc2; }
+  for (int i = 0; i < ndirs; i++) {
+    PartDir& P = A.d[i];
     pv_status_kernel<<<(U + 255u) / 256u, 256, 0, st>>>(P.status, U);
     c->timing.kernel_launches++;
     if (P.n_multi) {

@@ -1529,6 +1529,14 @@ int ensure_p3_tables(msspe_ctx* c) {
   msspe_thal_expand(c->raw_p3, h);
   cudaError_t e = cudaMallocAsync(&c->d_thal_p3, sizeof(ThalDeviceTables), c->stream);
   if (e == cudaSuccess) e = cudaMemcpy(c->d_thal_p3, h, sizeof(ThalDeviceTables), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {   // the conditions of the primer3_core stand-ins never change: their per-run constants are built once
+    // Primer3 defaults (primer.rs:125-140 sends no salt tags): mv 50, dv 1.5, dNTP 0.6, DNA 50 nM; thal at 37 C, maxLoop 30
+    const msspe_thal_cond p3{50.0, 1.5, 0.6, 50.0, 37.0, 30, 0};
+    if (!c->h_p3_consts) c->h_p3_consts = new ThalDimerConsts();
+    build_dimer_consts(*h, p3, c->h_p3_consts);
+    e = cudaMallocAsync((void**)&c->d_p3_consts, sizeof(ThalDimerConsts), c->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_p3_consts, c->h_p3_consts, sizeof(ThalDimerConsts), cudaMemcpyHostToDevice);
+  }
   delete h;
   if (e != cudaSuccess) { c->set_error("upload Primer3 default tables: %s", cudaGetErrorString(e)); return MSSPE_ERR_CUDA; }
   return MSSPE_OK;
@@ -1655,6 +1663,9 @@ void msspe_thal_free_tables(msspe_ctx* c) {
   c->d_thal = nullptr;
   if (c->d_thal_p3) msspe_dev_free(c, c->d_thal_p3);
   c->d_thal_p3 = nullptr;
+  if (c->d_p3_consts) msspe_dev_free(c, c->d_p3_consts);
+  c->d_p3_consts = nullptr;
+  delete c->h_p3_consts; c->h_p3_consts = nullptr;
   delete c->raw_p3; c->raw_p3 = nullptr;
 }
 
@@ -1738,11 +1749,7 @@ extern "C" int msspe_primer_thermo(msspe_ctx* c, const uint64_t* codes, uint32_t
   cudaStream_t st = c->stream;
   // Primer3 defaults (primer.rs:125-140 sends no salt tags): mv 50, dv 1.5, dNTP 0.6, DNA 50 nM; thal at 37 C, maxLoop 30
   const msspe_thal_cond p3{50.0, 1.5, 0.6, 50.0, 37.0, 30, 0};
-  ThalDeviceTables* hT = new ThalDeviceTables();
-  msspe_thal_expand(c->raw_p3, hT);
-  ThalDimerConsts K;
-  build_dimer_consts(*hT, p3, &K);
-  delete hT;
+  const ThalDimerConsts& K = *c->h_p3_consts;      // built by ensure_p3_tables, resident on the device
   OligoTmConsts OK;
   {
     double dv = p3.dv, dntp = p3.dntp;
@@ -1753,16 +1760,14 @@ extern "C" int msspe_primer_thermo(msspe_ctx* c, const uint64_t* codes, uint32_t
     OK.conc_term[0] = 1.987 * log(p3.dna_conc / 4000000000.0);
     OK.conc_term[1] = 1.987 * log(p3.dna_conc / 1000000000.0);
   }
-  DeviceBuf dcodes, dK, dtm, dgc, dout, dwork;
+  DeviceBuf dcodes, dtm, dgc, dout, dwork;
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dcodes.st = c->stream, dcodes.p), (size_t)n * 8, c->stream));
-  MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dK.st = c->stream, dK.p), sizeof K, c->stream));
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dtm.st = c->stream, dtm.p), (size_t)n * 8, c->stream));
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dgc.st = c->stream, dgc.p), (size_t)n * 8, c->stream));
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dout.st = c->stream, dout.p), (size_t)n * 3 * sizeof(msspe_thal_out), c->stream));
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dwork.st = c->stream, dwork.p), (size_t)n * sizeof(MonoWork), c->stream));
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[6], st));
   MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dcodes.p, codes, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dK.p, &K, sizeof K, cudaMemcpyHostToDevice, st));
   oligotm_kernel<<<(n + 127) / 128, 128, 0, st>>>((const uint64_t*)dcodes.p, n, (int)oligo_len, c->d_thal_p3, OK, (double*)dtm.p, (double*)dgc.p);
   c->timing.kernel_launches++;
   msspe_thal_out* o3 = (msspe_thal_out*)dout.p;
@@ -1770,7 +1775,7 @@ extern "C" int msspe_primer_thermo(msspe_ctx* c, const uint64_t* codes, uint32_t
     DimerArgs A{};
     A.a = (const uint64_t*)dcodes.p; A.b = (const uint64_t*)dcodes.p; A.n_pairs = n; A.matrix = 0; A.k = (int)oligo_len;
     A.type = pass == 0 ? MSSPE_THAL_ANY : MSSPE_THAL_END1;
-    A.T = c->d_thal_p3; A.C = (const ThalDimerConsts*)dK.p; A.out = o3 + (size_t)pass * n;
+    A.T = c->d_thal_p3; A.C = c->d_p3_consts; A.out = o3 + (size_t)pass * n;
     rc = launch_dimer(c, A, st);
     if (rc) return rc;
   }
