@@ -146,6 +146,12 @@ void msspe_destroy(msspe_ctx* ctx);
 const char* msspe_last_error(const msspe_ctx* ctx); /* ctx may be NULL: error of the last failed create */
 /* Run on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the ctx's own stream. */
 int msspe_set_stream(msspe_ctx* ctx, void* cuda_stream);
+/* Cold start (no reference counterpart: the reference has no device): map `bytes` of device memory into the context's
+ * stream-ordered pool in the BACKGROUND (returns at once; the first index build waits for it).  A process that knows the
+ * size of its input calls this right after msspe_create so that the driver's first-touch cost of the pool (2.4 s at the
+ * complete configs[4] input) overlaps the FASTA parse (main.rs:108-122) instead of the first build.  The amount is capped
+ * at 80 % of the free device memory; 0 is a no-op. */
+int msspe_reserve_pool(msspe_ctx* ctx, uint64_t bytes);
 int msspe_synchronize(msspe_ctx* ctx);
 int msspe_get_timing(msspe_ctx* ctx, msspe_timing* out);
 int msspe_reset_timing(msspe_ctx* ctx);

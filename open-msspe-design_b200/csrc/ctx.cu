@@ -98,6 +98,7 @@ static void free_genomes(msspe_ctx* c) {
 }
 
 extern "C" void msspe_destroy(msspe_ctx* c) {
+  msspe_join_reserve(c);
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
@@ -117,6 +118,32 @@ extern "C" void msspe_destroy(msspe_ctx* c) {
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   if (c->stream2) cudaStreamDestroy(c->stream2);
   delete c;
+}
+
+void msspe_join_reserve(msspe_ctx* c) {
+  if (c && c->reserve_thread) { c->reserve_thread->join(); delete c->reserve_thread; c->reserve_thread = nullptr; }
+}
+
+extern "C" int msspe_reserve_pool(msspe_ctx* c, uint64_t bytes) {
+  if (!c) return MSSPE_ERR_INVALID;
+  msspe_join_reserve(c);
+  if (bytes == 0) return MSSPE_OK;
+  const int device = c->device;
+  c->reserve_thread = new std::thread([device, bytes]() {
+    if (cudaSetDevice(device) != cudaSuccess) return;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return;
+    const uint64_t want = bytes < (uint64_t)(free_b / 5 * 4) ? bytes : (uint64_t)(free_b / 5 * 4);
+    cudaStream_t s = nullptr;
+    if (want == 0 || cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return;
+    void* p = nullptr;
+    // the pool keeps freed blocks (release threshold = max): allocate once, hand it back, the mapping stays
+    if (cudaMallocAsync(&p, want, s) == cudaSuccess) cudaFreeAsync(p, s);
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    (void)cudaGetLastError();
+  });
+  return MSSPE_OK;
 }
 
 extern "C" int msspe_set_stream(msspe_ctx* c, void* cuda_stream) {

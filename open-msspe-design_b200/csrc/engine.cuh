@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/od_msspe_b200.h"
@@ -110,6 +111,7 @@ struct msspe_ctx {
   size_t smem_optin = 48 * 1024;
   cudaStream_t stream = nullptr;      // main stream (own or caller's)
   cudaStream_t stream2 = nullptr;     // second direction
+  std::thread* reserve_thread = nullptr;   // msspe_reserve_pool: background first touch of the pool
   bool own_stream = true;
   cudaEvent_t ev[8] = {};
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -165,6 +167,7 @@ int msspe_radix_sort_pairs(msspe_ctx* ctx, uint64_t** key_a, uint32_t** val_a, u
                            uint32_t key_bits, cudaStream_t st);
 
 // ---- stages ----
+void msspe_join_reserve(msspe_ctx* c);
 bool msspe_build_fast_applicable(const msspe_ctx* ctx);   // kmer_build_fast.cu
 int msspe_build_fast(msspe_ctx* ctx);
 int msspe_free_index(msspe_ctx* ctx);

@@ -444,6 +444,7 @@ extern "C" int msspe_build_index(msspe_ctx* c) {
   if (!c) return MSSPE_ERR_INVALID;
   if (!c->loaded) { c->set_error("msspe_build_index: no genomes loaded"); return MSSPE_ERR_STATE; }
   MSSPE_CUDA_TRY(c, cudaSetDevice(c->device));
+  msspe_join_reserve(c);             // msspe_reserve_pool: the pool's first touch ran beside the ingest
   msspe_free_index(c);
   const uint64_t G = c->n_segments;
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&c->d_seg_part, (G ? G : 1) * sizeof(uint16_t), c->stream));

@@ -525,27 +525,34 @@ __global__ void dist_dupscatter_kernel(const uint64_t* __restrict__ keys, uint32
   if (k != pad && i + 1 < n && keys[i + 1] == k && (i == 0 || keys[i - 1] != k)) xcodes[scan[i]] = k;
 }
 // local multi list m -> cross id (or none); cross id -> local m; local length and touched-unit mask of every cross list
-__global__ void dist_xmap_kernel(PartArgs A, DistArgs X, int d, uint32_t* m_xid, uint32_t* xlen_local) {
+// one warp per local multi-partition list: is it a cross list, and which units do its postings touch?  (One THREAD per list
+// walked up to one posting per genome sequentially: 1.8 ms of the set-up at 40,000 genomes.)
+__global__ void __launch_bounds__(256) dist_xmap_kernel(PartArgs A, DistArgs X, int d, uint32_t* m_xid, uint32_t* xlen_local) {
   const PartDir& D = A.d[d];
   const DistDir& Q = X.x[d];
-  const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
   if (m >= D.n_multi) return;
   const uint32_t c = D.ucodes[D.n_single + m];
   const unsigned long long code = D.codes[c];
   uint32_t lo = 0, len = Q.n_x;
   while (len > 0) { const uint32_t half = len >> 1; if (Q.xcodes[lo + half] < code) { lo += half + 1; len -= half + 1; } else len = half; }
   const bool is_x = lo < Q.n_x && Q.xcodes[lo] == code;
-  m_xid[m] = is_x ? lo : 0xFFFFFFFFu;
+  if (lane == 0) m_xid[m] = is_x ? lo : 0xFFFFFFFFu;
   if (is_x) {
-    Q.x_local[lo] = m;
-    xlen_local[lo] = D.post_off[c + 1] - D.post_off[c];
-    D.ub[m] = 0u;                                   // never staged by the local check: the cross check owns it
-    for (uint32_t i = D.post_off[c]; i < D.post_off[c + 1]; i++) {
+    const uint32_t p0 = D.post_off[c], p1 = D.post_off[c + 1];
+    if (lane == 0) {
+      Q.x_local[lo] = m;
+      xlen_local[lo] = p1 - p0;
+      D.ub[m] = 0u;                                   // never staged by the local check: the cross check owns it
+    }
+    uint32_t last = 0xFFFFFFFFu;                      // consecutive postings mostly share a unit: one atomic per change
+    for (uint32_t i = p0 + lane; i < p1; i += 32) {
       const uint32_t gu = gu_of(X, part_of(A, D.postings[i]));
-      atomicOr(&Q.xparts[(size_t)lo * X.UW + (gu >> 5)], 1u << (gu & 31u));
+      if (gu != last) { atomicOr(&Q.xparts[(size_t)lo * X.UW + (gu >> 5)], 1u << (gu & 31u)); last = gu; }
     }
   }
 }
+
 __global__ void dist_lenkey_kernel(const uint32_t* __restrict__ len, uint32_t n, uint64_t* __restrict__ key) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) key[i] = (uint64_t)(0xFFFFFFFFu - len[i]);     // ascending sort of the complement = descending lengths
@@ -810,7 +817,7 @@ int dist_select_impl(msspe_ctx* c, uint32_t max_iter, uint32_t mms, msspe_candid
     mark(4);
     if (P.n_multi) {
       pv_mlen_kernel<<<(P.n_multi + 255u) / 256u, 256, 0, st>>>(P.ucodes, P.n_single, P.n_multi, P.post_off, P.ub, nullptr);
-      dist_xmap_kernel<<<(P.n_multi + 255u) / 256u, 256, 0, st>>>(A, X, d, m_xid, xlen_local);
+      dist_xmap_kernel<<<(P.n_multi + 7u) / 8u, 256, 0, st>>>(A, X, d, m_xid, xlen_local);
     }
     if (n_x) {   // global length of every cross list (its first upper bound) and the units it touches
       MSSPE_NCCL_TRY(c, ds, N->AllReduce(xlen_local, Q.ub_x, n_x, ncclUint32, ncclSum, ds->comm, st));

@@ -4,7 +4,7 @@ set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 PKG="$(dirname "$HERE")"
 mkdir -p "$PKG/bin"
-g++ -O2 -std=c++17 -Wall -ffp-contract=off -o "$PKG/bin/od-msspe" "$HERE/od_msspe_main.cpp" \
+g++ -O2 -std=c++17 -Wall -pthread -ffp-contract=off -o "$PKG/bin/od-msspe" "$HERE/od_msspe_main.cpp" \
   -L"$PKG" -lodmsspe_b200 -Wl,-rpath,'$ORIGIN/..' -Wl,-rpath,/usr/local/cuda/lib64
 # the protocol shims for the reference's --ntthal / --primer3 seam (seam #1)
 mkdir -p "$PKG/bin/shims"

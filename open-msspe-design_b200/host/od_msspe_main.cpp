@@ -5,6 +5,8 @@
 // glue the north star keeps on the CPU: argument parsing, FASTA parsing, the Primer3 text round trips, the
 // 5-line ntthal parser's bookkeeping (delta_g.rs:27-59), the conflict-graph vertex cover (main.rs:754-815).
 // There is no CPU fallback: without a usable CUDA device the program exits with an error.
+#include <sys/stat.h>
+#include <thread>
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -239,18 +241,53 @@ int main(int argc, char** argv) {
   if (a.window_size == 0) panic("window size must be non-zero");                                  // windows(0)
   const unsigned k = (unsigned)a.kmer_size;
 
+  // Cold start: creating the CUDA context (about 2 s on a fresh process) and parsing the FASTA (main.rs:108-122, host only)
+  // are independent, so the context is created on a second thread while this one parses into pageable memory; the pool's
+  // first touch for an input of this size follows on that thread's heels (msspe_reserve_pool).  MSSPE_SERIAL_START=1 restores
+  // the one-after-the-other order (parse into pinned memory with chunked uploads, msspe_load_fasta).
   msspe_ctx* ctx = nullptr;
   msspe_config cfg{(uint32_t)a.kmer_size, (uint32_t)a.window_size, (uint32_t)a.overlap_size, (uint32_t)a.search_windows_size,
                    getenv("MSSPE_DEVICE") ? atoi(getenv("MSSPE_DEVICE")) : 0, 0};
-  if (int rc = msspe_create(&cfg, &ctx)) { std::cerr << "od-msspe: cannot start the GPU engine (" << rc << "): " << msspe_last_error(nullptr) << "\n"; return 1; }
-  log_info("GPU engine ready");
-  // 1. to_records (main.rs:108-122) + upload: multi-threaded parse into pinned memory, chunked copies overlap the parse
+  const uint32_t n_threads = getenv("MSSPE_THREADS") ? (uint32_t)atoi(getenv("MSSPE_THREADS")) : 0u;
+  uint64_t reserve = 0;
+  {
+    struct stat sb;
+    if (!getenv("MSSPE_NO_RESERVE") && stat(a.input.c_str(), &sb) == 0 && sb.st_size > (64 << 20))
+      reserve = (uint64_t)sb.st_size * 13u;   // genomes + keys, postings and forward index of both directions
+  }
   msspe_fasta* fasta = nullptr;
-  if (int rc = msspe_load_fasta(ctx, a.input.c_str(), getenv("MSSPE_THREADS") ? (uint32_t)atoi(getenv("MSSPE_THREADS")) : 0u, &fasta)) {
-    const std::string msg = msspe_last_error(ctx);
-    if (rc == MSSPE_ERR_INVALID) panic(msg);                                                      // InvalidStart, or main.rs:652-654
-    std::cerr << "od-msspe: reading " << a.input << " failed (" << rc << "): " << msg << "\n";
-    return 1;
+  if (getenv("MSSPE_SERIAL_START")) {
+    if (int rc = msspe_create(&cfg, &ctx)) { std::cerr << "od-msspe: cannot start the GPU engine (" << rc << "): " << msspe_last_error(nullptr) << "\n"; return 1; }
+    log_info("GPU engine ready");
+    if (reserve) msspe_reserve_pool(ctx, reserve);
+    // 1. to_records (main.rs:108-122) + upload: multi-threaded parse into pinned memory, chunked copies overlap the parse
+    if (int rc = msspe_load_fasta(ctx, a.input.c_str(), n_threads, &fasta)) {
+      const std::string msg = msspe_last_error(ctx);
+      if (rc == MSSPE_ERR_INVALID) panic(msg);                                                      // InvalidStart, or main.rs:652-654
+      std::cerr << "od-msspe: reading " << a.input << " failed (" << rc << "): " << msg << "\n";
+      return 1;
+    }
+  } else {
+    int rc_create = 0;
+    std::string create_err;
+    std::thread creator([&] {
+      rc_create = msspe_create(&cfg, &ctx);
+      if (rc_create) create_err = msspe_last_error(nullptr);
+      else if (reserve) msspe_reserve_pool(ctx, reserve);
+    });
+    setenv("MSSPE_FASTA_PINNED", "0", 0);      // page-locking would wait for the context that is still being created
+    char err[512] = {0};
+    const int rc_parse = msspe_fasta_open(a.input.c_str(), n_threads, &fasta, err, sizeof err);
+    creator.join();
+    if (rc_create) { std::cerr << "od-msspe: cannot start the GPU engine (" << rc_create << "): " << create_err << "\n"; return 1; }
+    log_info("GPU engine ready");
+    if (rc_parse) {
+      if (rc_parse == MSSPE_ERR_INVALID) panic(err);                                                // InvalidStart
+      std::cerr << "od-msspe: reading " << a.input << " failed (" << rc_parse << "): " << err << "\n";
+      return 1;
+    }
+    if (msspe_fasta_records(fasta) == 0) panic("No sequences found in the input file");           // main.rs:652-654
+    CHECK(msspe_load_genomes(ctx, msspe_fasta_bases(fasta), msspe_fasta_offsets(fasta), msspe_fasta_records(fasta)));
   }
   std::vector<Record> records(msspe_fasta_records(fasta));
   for (size_t i = 0; i < records.size(); i++) records[i].name = msspe_fasta_name(fasta, (uint32_t)i);  // sequences stay in the handle

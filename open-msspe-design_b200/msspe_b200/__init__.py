@@ -22,7 +22,7 @@ THAL_ANY, THAL_END1, THAL_HAIRPIN = 1, 2, 4
 
 # every symbol include/od_msspe_b200.h declares
 ABI_SYMBOLS = [
-    "msspe_abi_version", "msspe_create", "msspe_destroy", "msspe_last_error", "msspe_set_stream", "msspe_synchronize",
+    "msspe_abi_version", "msspe_create", "msspe_destroy", "msspe_last_error", "msspe_set_stream", "msspe_reserve_pool", "msspe_synchronize",
     "msspe_get_timing", "msspe_reset_timing", "msspe_set_profiling", "msspe_load_genomes", "msspe_load_genomes_device",
     "msspe_build_index", "msspe_segment_info", "msspe_get_segment_kmers", "msspe_get_index", "msspe_select",
     "msspe_select_both", "msspe_coverage", "msspe_thal_params_default", "msspe_thal_params_from_dir",
@@ -114,6 +114,7 @@ def load_library():
     L.msspe_destroy.argtypes = [C.c_void_p]
     L.msspe_destroy.restype = None
     L.msspe_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.msspe_reserve_pool.argtypes = [C.c_void_p, C.c_uint64]
     L.msspe_synchronize.argtypes = [C.c_void_p]
     L.msspe_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
     L.msspe_reset_timing.argtypes = [C.c_void_p]
@@ -278,6 +279,10 @@ class Engine:
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         self._keep = keepalive
         self._check(self.L.msspe_load_genomes_device(self.h, C.c_void_p(device_ptr), offsets.ctypes.data, len(offsets) - 1))
+
+    def reserve_pool(self, nbytes: int):
+        """Background first touch of the stream-ordered pool (cold start); the first build_index waits for it."""
+        self._check(self.L.msspe_reserve_pool(self.h, C.c_uint64(int(nbytes))))
 
     def set_stream(self, cuda_stream: int):
         self._check(self.L.msspe_set_stream(self.h, C.c_void_p(cuda_stream)))
