@@ -339,7 +339,7 @@ def thal_section(eng, m, synth, dist, world, rank, dev, barrier):
     pairs = THAL_POOL * THAL_POOL
     ncu = {}
     try:
-        with open(os.path.join(ROOT, "profiles", "r2_thal_dimer_metrics.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2s4_thal_thread_metrics.json")) as f:
             ncu = json.load(f)
     except Exception:
         pass
@@ -348,7 +348,7 @@ def thal_section(eng, m, synth, dist, world, rank, dev, barrier):
             "kernel_only_pairs_per_s": pairs / k_s if k_s > 0 else None, "conflict_edges_below_-9000": int(len(edges)),
             "structureless_pairs": int(len(nos)), "seconds": t_thal,
             "scaling": "strong (rows tiled across ranks; one all_gather of counts + one of the device-resident lists)",
-            "roofline": {"bound": "sm_issue", "kernel": "thal_dimer_kernel<8>", "achieved": pairs / k_s if k_s > 0 else None, "unit": "pairs/s",
+            "roofline": {"bound": "sm_issue", "kernel": "thal_dimer_thread_kernel (one thread per ordered pair)", "achieved": pairs / k_s if k_s > 0 else None, "unit": "pairs/s",
                          "flop_per_pair": THAL_FLOP_PER_PAIR, "achieved_fp64_gflops": pairs / k_s * THAL_FLOP_PER_PAIR / 1e9 if k_s > 0 else None,
                          "issue_active_pct": ncu.get("issue_active_pct"), "fp64_pipe_pct": ncu.get("fp64_pipe_pct"),
                          "lanes_active_per_inst": ncu.get("lanes_active_per_inst"), "ncu_source": ncu.get("source"),
