@@ -176,7 +176,7 @@ encode_keys_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict
 
 struct SortPass { int shift, bits; };
 
-// hist[d * nb + block]; pass 0 (n_dev == nullptr) counts only valid keys of the n0 slots and adds them up in *n_out
+// hist[block * nbuckets + d]; pass 0 (n_dev == nullptr) counts only valid keys of the n0 slots and adds them up in *n_out
 __global__ void __launch_bounds__(SORT_T)
 fast_hist_kernel(const unsigned long long* __restrict__ keys, uint64_t n0, const uint32_t* __restrict__ n_dev, int shift, uint32_t nbuckets,
                  uint32_t* __restrict__ hist, uint32_t nb, uint32_t* __restrict__ n_out) {
@@ -196,45 +196,61 @@ fast_hist_kernel(const unsigned long long* __restrict__ keys, uint64_t n0, const
   for (int i = 0; i < SORT_ITEMS; i++)
     if (key[i] != KEY_NONE) { atomicAdd(&h[(uint32_t)(key[i] >> shift) & (nbuckets - 1u)], 1u); valid++; }
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < nbuckets; i += SORT_T) hist[(uint64_t)i * nb + blockIdx.x] = h[i];
+  for (uint32_t i = threadIdx.x; i < nbuckets; i += SORT_T) hist[(uint64_t)blockIdx.x * nbuckets + i] = h[i];   // [block][digit]: coalesced
   if (n_out) {
     for (int o = 16; o > 0; o >>= 1) valid += __shfl_down_sync(0xffffffffu, valid, o);
     if ((threadIdx.x & 31) == 0 && valid) atomicAdd(n_out, valid);
   }
 }
 
-// Offsets of one pass from the block histograms hist[d * nb + block]: one block per digit scans its nb counts in place
-// (exclusive) and leaves the digit's total in dtot[d]; fast_digit_base_kernel then turns dtot into the digits' bases.
-// Two launches per pass instead of the seven of the generic multi-level scan over nbuckets * nb entries.
-constexpr int DSCAN_T = 256;
-__global__ void __launch_bounds__(DSCAN_T)
-fast_digit_scan_kernel(uint32_t* __restrict__ hist, uint32_t nb, uint32_t* __restrict__ dtot) {
-  __shared__ uint32_t s_w[DSCAN_T / 32];
-  __shared__ uint32_t s_carry;
-  uint32_t* h = hist + (uint64_t)blockIdx.x * nb;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_carry = 0u;
+// Offsets of one pass from the block histograms hist[block][digit] (every block's row is contiguous, so the histogram
+// kernel writes it and the scatter kernel reads it with consecutive threads on consecutive addresses; the digit-major layout
+// of the first version cost each of them one 32-byte sector per digit and block -- as much traffic as the keys).  A block of
+// this kernel owns 32 consecutive digits (lane = digit) and all tiles: its warps split the tiles, sum their share, exchange
+// the sums, then rewrite their share as running (exclusive) counts; dtot[d] receives the digit's total, which
+// fast_digit_base_kernel turns into the digit's base.  Two launches per pass instead of the seven of the generic scan.
+constexpr int DSCAN_WARPS = 16, DSCAN_SPLIT = 8, DSCAN_CHUNKS = DSCAN_WARPS * DSCAN_SPLIT;   // the tiles are cut into 128 chunks of rows
+__device__ __forceinline__ void dscan_range(uint32_t nb, uint32_t chunk, uint32_t* r0, uint32_t* r1) {
+  const uint32_t per = (nb + DSCAN_CHUNKS - 1) / DSCAN_CHUNKS;
+  *r0 = chunk * per < nb ? chunk * per : nb;
+  *r1 = *r0 + per < nb ? *r0 + per : nb;
+}
+// grid (nbuckets / 32, DSCAN_SPLIT), one warp per chunk, lane = digit: csum[chunk][d] = sum of the chunk's rows
+__global__ void __launch_bounds__(DSCAN_WARPS * 32)
+fast_digit_partial_kernel(const uint32_t* __restrict__ hist, uint32_t nb, uint32_t nbuckets, uint32_t* __restrict__ csum) {
+  const uint32_t lane = threadIdx.x & 31u, chunk = blockIdx.y * DSCAN_WARPS + (threadIdx.x >> 5);
+  const uint32_t d = blockIdx.x * 32u + lane;
+  if (d >= nbuckets) return;
+  uint32_t r0, r1;
+  dscan_range(nb, chunk, &r0, &r1);
+  uint32_t sum = 0;
+#pragma unroll 8
+  for (uint32_t r = r0; r < r1; r++) sum += hist[(uint64_t)r * nbuckets + d];
+  csum[(uint64_t)chunk * nbuckets + d] = sum;
+}
+// same grid: the chunk's rows become running (exclusive) counts of their digit; the last chunk leaves the digit's total
+__global__ void __launch_bounds__(DSCAN_WARPS * 32)
+fast_digit_scan_kernel(uint32_t* __restrict__ hist, uint32_t nb, uint32_t nbuckets, const uint32_t* __restrict__ csum, uint32_t* __restrict__ dtot) {
+  const uint32_t lane = threadIdx.x & 31u, chunk = blockIdx.y * DSCAN_WARPS + (threadIdx.x >> 5);
+  const uint32_t d = blockIdx.x * 32u + lane;
+  // sum of the chunks before this one: the block loads all chunk sums of its 32 digits once (its warps share the rows)
+  __shared__ uint32_t s_c[DSCAN_CHUNKS][32];
+  const uint32_t need = (blockIdx.y + 1u) * DSCAN_WARPS;       // chunks up to the end of this block's split
+  for (uint32_t c2 = threadIdx.x >> 5; c2 < need; c2 += DSCAN_WARPS) s_c[c2][lane] = d < nbuckets ? csum[(uint64_t)c2 * nbuckets + d] : 0u;
   __syncthreads();
-  for (uint32_t base = 0; base < nb; base += DSCAN_T * 4) {
-    const uint32_t i0 = base + (uint32_t)tid * 4u;
-    uint32_t v[4];
+  if (d >= nbuckets) return;
+  uint32_t run = 0;
+  for (uint32_t c2 = 0; c2 < chunk; c2++) run += s_c[c2][lane];
+  uint32_t r0, r1;
+  dscan_range(nb, chunk, &r0, &r1);
+  for (uint32_t r = r0; r < r1; r += 8) {       // eight rows in flight: the loads of a group are issued before its stores
+    uint32_t v[8];
 #pragma unroll
-    for (int q = 0; q < 4; q++) v[q] = i0 + q < nb ? h[i0 + q] : 0u;
-    const uint32_t sum = v[0] + v[1] + v[2] + v[3];
-    uint32_t inc = sum;
+    for (int q = 0; q < 8; q++) v[q] = r + q < r1 ? hist[(uint64_t)(r + q) * nbuckets + d] : 0u;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) s_w[warp] = inc;
-    __syncthreads();
-    uint32_t run = s_carry + inc - sum;
-    for (int w2 = 0; w2 < warp; w2++) run += s_w[w2];
-#pragma unroll
-    for (int q = 0; q < 4; q++) { if (i0 + q < nb) h[i0 + q] = run; run += v[q]; }
-    __syncthreads();
-    if (tid == DSCAN_T - 1) s_carry = run;
-    __syncthreads();
+    for (int q = 0; q < 8; q++) { if (r + q < r1) hist[(uint64_t)(r + q) * nbuckets + d] = run; run += v[q]; }
   }
-  if (tid == 0) dtot[blockIdx.x] = s_carry;
+  if (chunk == DSCAN_CHUNKS - 1) dtot[d] = run;
 }
 
 __global__ void __launch_bounds__(1024)
@@ -276,13 +292,18 @@ fast_scatter_kernel(const unsigned long long* __restrict__ keys, uint64_t n0, co
   const uint64_t tile0 = (uint64_t)blockIdx.x * SORT_TILE;
   if (tile0 >= n) return;
   for (uint32_t i = tid; i < SORT_WARPS * nbuckets / 2; i += SORT_T) reinterpret_cast<uint32_t*>(cnt)[i] = 0u;
-  // each warp owns 512 consecutive keys
+  // each warp owns 512 consecutive keys.  Only their digits stay in registers (two per register, 0xFFFF = no key): the
+  // keys themselves are read again from L2 when they are staged, so the ranking rounds run with ~48 registers instead
+  // of 80 + spills (local-memory traffic was 37 % of this kernel's sectors) and more blocks fit an SM
   const uint64_t wbase = tile0 + (uint64_t)warp * (32 * SORT_ITEMS);
-  unsigned long long key[SORT_ITEMS];
+  uint32_t dig2[SORT_ITEMS / 2];
 #pragma unroll
-  for (int i = 0; i < SORT_ITEMS; i++) {
-    const uint64_t p = wbase + (uint64_t)i * 32 + lane;
-    key[i] = p < n ? keys[p] : KEY_NONE;
+  for (int i = 0; i < SORT_ITEMS; i += 2) {
+    const uint64_t p0 = wbase + (uint64_t)i * 32 + lane, p1 = p0 + 32;
+    const unsigned long long k0 = p0 < n ? keys[p0] : KEY_NONE, k1 = p1 < n ? keys[p1] : KEY_NONE;
+    const uint32_t e0 = k0 != KEY_NONE ? ((uint32_t)(k0 >> shift) & (nbuckets - 1u)) : 0xFFFFu;
+    const uint32_t e1 = k1 != KEY_NONE ? ((uint32_t)(k1 >> shift) & (nbuckets - 1u)) : 0xFFFFu;
+    dig2[i >> 1] = e0 | (e1 << 16);
   }
   __syncthreads();
   uint32_t rank2[SORT_ITEMS / 2];   // two u16 ranks per register
@@ -290,11 +311,11 @@ fast_scatter_kernel(const unsigned long long* __restrict__ keys, uint64_t n0, co
   uint8_t* wt = tag + (size_t)warp * nbuckets;
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; i++) {
-    const bool in = key[i] != KEY_NONE;
-    const uint32_t d = (uint32_t)(key[i] >> shift) & (nbuckets - 1u);
+    const uint32_t d = (dig2[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+    const bool in = d != 0xFFFFu;
     uint32_t r = 0;
     int same = 0;
-    __match_all_sync(0xffffffffu, in ? d : 0xFFFFFFFFu, &same);
+    __match_all_sync(0xffffffffu, d, &same);
     if (same) {                                // one digit for the whole round (sorted input: the usual case after pass 0)
       if (in) {
         uint32_t old = 0;
@@ -306,7 +327,7 @@ fast_scatter_kernel(const unsigned long long* __restrict__ keys, uint64_t n0, co
       __syncwarp();
       const bool lost = in && wt[d] != (uint8_t)lane;
       if (__any_sync(0xffffffffu, lost)) {      // a digit occurs twice in this round
-        const unsigned peers = __match_any_sync(0xffffffffu, in ? d : 0xFFFFFFFFu);
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
         const int leader = __ffs(peers) - 1;
         uint32_t old = 0;
         if (in && lane == leader) { old = wc[d]; wc[d] = (uint16_t)(old + __popc(peers)); }
@@ -344,7 +365,7 @@ fast_scatter_kernel(const unsigned long long* __restrict__ keys, uint64_t n0, co
     for (uint32_t d = d0; d < d0 + per && d < nbuckets; d++) {
       const uint32_t c2 = loc_off[d];
       loc_off[d] = run;
-      gadj[d] = dbase[d] + offs[(uint64_t)d * nb + blockIdx.x] - run;     // global position = gadj[d] + position in the staged tile
+      gadj[d] = dbase[d] + offs[(uint64_t)blockIdx.x * nbuckets + d] - run;     // global position = gadj[d] + position in the staged tile
       run += c2;
     }
   }
@@ -352,16 +373,27 @@ fast_scatter_kernel(const unsigned long long* __restrict__ keys, uint64_t n0, co
   // position of every key in the staged tile, then the stage takes over the counters' memory
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; i++) {
-    if (key[i] != KEY_NONE) {
-      const uint32_t d = (uint32_t)(key[i] >> shift) & (nbuckets - 1u);
+    const uint32_t d = (dig2[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+    if (d != 0xFFFFu) {
       const uint32_t r = loc_off[d] + wc[d] + ((rank2[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
       rank2[i >> 1] = (i & 1) ? ((rank2[i >> 1] & 0xFFFFu) | (r << 16)) : ((rank2[i >> 1] & 0xFFFF0000u) | r);
     }
   }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < SORT_ITEMS; i++)
-    if (key[i] != KEY_NONE) stage[(rank2[i >> 1] >> (16 * (i & 1))) & 0xFFFFu] = key[i];
+  for (int h = 0; h < SORT_ITEMS; h += 4) {      // four keys back from L2 at a time
+    unsigned long long kk[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const uint64_t p = wbase + (uint64_t)(h + q) * 32 + lane;
+      kk[q] = p < n ? keys[p] : KEY_NONE;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int i = h + q;
+      if (((dig2[i >> 1] >> (16 * (i & 1))) & 0xFFFFu) != 0xFFFFu) stage[(rank2[i >> 1] >> (16 * (i & 1))) & 0xFFFFu] = kk[q];
+    }
+  }
   __syncthreads();
   const uint32_t total = s_total;
   for (uint32_t p = tid; p < total; p += SORT_T) {
@@ -415,6 +447,7 @@ struct FastDir {
   unsigned long long* ka = nullptr; unsigned long long* kb = nullptr; uint32_t* hist = nullptr; uint32_t* flags = nullptr;
   uint32_t* d_cnt = nullptr;   // [0] R  [1] n_codes
   uint32_t* dtot = nullptr;    // [nbuckets] digit totals -> digit bases of the current pass
+  uint32_t* csum = nullptr;    // [DSCAN_CHUNKS][nbuckets] row-chunk sums of the block histograms
 };
 
 }  // namespace
@@ -453,7 +486,7 @@ int msspe_build_fast(msspe_ctx* c) {
   for (int p = 0; p < passes; p++) maxbits = std::max(maxbits, pass[p].bits);
   const uint32_t max_buckets = 1u << maxbits;
   const size_t sc_smem_max = scatter_smem(max_buckets);
-  static const int scatter_minb = getenv("MSSPE_SCATTER_MINB") ? atoi(getenv("MSSPE_SCATTER_MINB")) : 3;
+  static const int scatter_minb = getenv("MSSPE_SCATTER_MINB") ? atoi(getenv("MSSPE_SCATTER_MINB")) : 4;
   MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(fast_scatter_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem_max));
   MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(fast_scatter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem_max));
   FastDir F[2];
@@ -467,6 +500,7 @@ int msspe_build_fast(msspe_ctx* c) {
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&f.flags, GS * 4, st));
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&f.d_cnt, 16, st));
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&f.dtot, (uint64_t)max_buckets * 4, st));
+    MSSPE_CUDA_TRY(c, cudaMallocAsync(&f.csum, (uint64_t)DSCAN_CHUNKS * max_buckets * 4, st));
     MSSPE_CUDA_TRY(c, cudaMemsetAsync(f.d_cnt, 0, 16, st));
     {
       KPROF(c, KP_ENCODE, st, G * w + GS * 8)
@@ -490,7 +524,8 @@ int msspe_build_fast(msspe_ctx* c) {
       { KPROF(c, KP_SORT_HIST, st, GS * 8)
         fast_hist_kernel<<<nb, SORT_T, nbk * 4, st>>>(f.ka, GS, n_dev, pass[p].shift, nbk, f.hist, nb, p == 0 ? f.d_cnt : nullptr); }
       { KPROF(c, KP_SCAN, st, (uint64_t)nbk * nb * 8)
-        fast_digit_scan_kernel<<<nbk, DSCAN_T, 0, st>>>(f.hist, nb, f.dtot);
+        fast_digit_partial_kernel<<<dim3((nbk + 31u) / 32u, DSCAN_SPLIT), DSCAN_WARPS * 32, 0, st>>>(f.hist, nb, nbk, f.csum);
+        fast_digit_scan_kernel<<<dim3((nbk + 31u) / 32u, DSCAN_SPLIT), DSCAN_WARPS * 32, 0, st>>>(f.hist, nb, nbk, f.csum, f.dtot);
         fast_digit_base_kernel<<<1, 1024, 0, st>>>(f.dtot, nbk); }
       const size_t sm = scatter_smem(nbk);
       { KPROF(c, KP_SORT_SCATTER, st, GS * 16)
@@ -528,7 +563,7 @@ int msspe_build_fast(msspe_ctx* c) {
                                                                    c->d_seg_part, uni, D.list_part);
     }
     MSSPE_CUDA_TRY(c, cudaFreeAsync(f.ka, st)); MSSPE_CUDA_TRY(c, cudaFreeAsync(f.kb, st)); MSSPE_CUDA_TRY(c, cudaFreeAsync(f.hist, st));
-    MSSPE_CUDA_TRY(c, cudaFreeAsync(f.flags, st)); MSSPE_CUDA_TRY(c, cudaFreeAsync(f.d_cnt, st)); MSSPE_CUDA_TRY(c, cudaFreeAsync(f.dtot, st));
+    MSSPE_CUDA_TRY(c, cudaFreeAsync(f.flags, st)); MSSPE_CUDA_TRY(c, cudaFreeAsync(f.d_cnt, st)); MSSPE_CUDA_TRY(c, cudaFreeAsync(f.dtot, st)); MSSPE_CUDA_TRY(c, cudaFreeAsync(f.csum, st));
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.freq, Dn * 4, st));
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.ignored, (div_up_u64(G, 32) + 1) * 4, st));
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.cov, 65536 * 4, st));
