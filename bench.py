@@ -339,7 +339,7 @@ def thal_section(eng, m, synth, dist, world, rank, dev, barrier):
     pairs = THAL_POOL * THAL_POOL
     ncu = {}
     try:
-        with open(os.path.join(ROOT, "profiles", "r2s4_thal_thread_metrics.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2s5_thal_thread_metrics.json")) as f:
             ncu = json.load(f)
     except Exception:
         pass
@@ -514,10 +514,12 @@ def main():
     roofline = None
     if dom:
         traffic = None
+        bound_note = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r2_dominant_kernel_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r2s5_dominant_kernel_traffic.json")) as f:
                 tj = json.load(f)
             traffic = tj.get("kernels", {}).get(dom["kernel"], {}).get("dram_bytes_per_launch")
+            bound_note = tj.get("kernels", {}).get(dom["kernel"], {}).get("bound")
         except Exception:
             pass
         lp = max(1, dom["launches_per_step"])
@@ -527,6 +529,8 @@ def main():
         bound = "hbm"
         if traffic is not None and alg_per_launch > 0 and traffic < 0.25 * alg_per_launch:
             bound = "latency/L2"
+        if bound_note:
+            bound = bound_note          # what the ncu capture of this kernel shows (profiles/r2s5_dominant_kernel_traffic.json)
         roofline = {"bound": bound, "kernel": dom["kernel"], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                     "frac": achieved / peak_gbs if peak_gbs else None, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_us": 1e6 * avg_launch_s, "launches_per_step": lp,

@@ -165,6 +165,8 @@ def _random_alignment(seed, n, L, p=0.03, gaps=True):
     (4, 20, 1200, 300, 150, 100, 31, 1),    # maximum k
     (5, 25, 900, 90, 45, 45, 17, 1),        # k > 16: 64-bit codes
     (6, 30, 1200, 100, 50, 30, 6, 3),       # single- and multi-partition lists mixed: many external winners in the partitioned loop
+    (7, 20, 1500, 300, 150, 90, 11, 1),     # search window > 64 bases with k <= 16: the general (shared-memory) one-pass encoder
+    (8, 16, 1300, 260, 130, 64, 16, 1),     # widest packed window with the longest packed word
 ])
 def test_random_alignments_bit_exact(oracle_lib, seed, n, L, W, S, w, k, mms):
     import msspe_b200 as m
@@ -179,6 +181,39 @@ def test_random_alignments_bit_exact(oracle_lib, seed, n, L, W, S, w, k, mms):
     for mode in (0, 1, 2, 3, 0x100, 0x101):   # persistent recount / incremental / AUTO / partitioned / launch-per-phase recount / incremental
         _check_select(eng, oracle_lib, fa, W, S, w, k, 60, mms, mode)
     eng.close()
+
+
+def test_low_complexity_windows_repeat_words(oracle_lib):
+    """Homopolymer runs, di- and tri-nucleotide repeats: most words of a search window repeat an earlier one, which the
+    packed encoder finds by comparing the window with itself at every distance (itertools unique(), main.rs:163-171)."""
+    import msspe_b200 as m
+    rng = np.random.default_rng(77)
+    L, n = 1500, 14
+    anc = rng.integers(0, 4, L)
+    for start, unit in ((40, [0]), (260, [0, 3]), (520, [1, 2, 1]), (800, [2]), (1010, [0, 1, 2, 3]), (1290, [3, 3, 0])):
+        rep = np.array((unit * 200)[:170])
+        anc[start:start + len(rep)] = rep
+    recs = []
+    for i in range(n):
+        s = anc.copy()
+        mut = rng.random(L) < 0.01
+        s[mut] = rng.integers(0, 4, int(mut.sum()))
+        ch = np.array(list("ACGT"))[s]
+        ch[rng.random(L) < 0.003] = "N"
+        recs.append(">r%d\n%s\n" % (i, "".join(ch)))
+    fa = "".join(recs).encode()
+    _, (bases, offs) = _fasta_to_arrays(fa)
+    for (W, S, w, k) in ((250, 125, 50, 13), (250, 125, 64, 9), (200, 100, 40, 15)):
+        eng = m.Engine(k, W, S, w)
+        eng.reserve_pool(64 << 20)           # msspe_reserve_pool: background first touch, the build waits for it
+        eng.load_genomes(bases, offs)
+        eng.build_index()
+        for d in (0, 1):
+            want, _ = oracle_lib.segment_slots(fa, W, S, w, k, d)
+            assert np.array_equal(eng.segment_kmers(d), want)
+        for mode in (0, 2, 3):
+            _check_select(eng, oracle_lib, fa, W, S, w, k, 40, 1, mode)
+        eng.close()
 
 
 def test_identical_genomes_tie_storm(oracle_lib):
