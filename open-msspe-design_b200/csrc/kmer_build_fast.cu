@@ -327,7 +327,12 @@ fast_scatter_kernel(const unsigned long long* __restrict__ keys, uint64_t n0, co
       __syncwarp();
       const bool lost = in && wt[d] != (uint8_t)lane;
       if (__any_sync(0xffffffffu, lost)) {      // a digit occurs twice in this round
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        unsigned peers;
+        if (nbuckets <= 256u) {                 // narrow digits repeat in most rounds: eight ballots (2.3 SM cycles each) beat
+          peers = __ballot_sync(0xffffffffu, in) ^ (in ? 0u : 0xffffffffu);   // __match_any_sync (2 cycles per distinct value)
+#pragma unroll
+          for (int bq = 0; bq < 8; bq++) { const unsigned v = __ballot_sync(0xffffffffu, (d >> bq) & 1u); peers &= ((d >> bq) & 1u) ? v : ~v; }
+        } else peers = __match_any_sync(0xffffffffu, d);
         const int leader = __ffs(peers) - 1;
         uint32_t old = 0;
         if (in && lane == leader) { old = wc[d]; wc[d] = (uint16_t)(old + __popc(peers)); }
@@ -468,8 +473,11 @@ int msspe_build_fast(msspe_ctx* c) {
   const uint64_t GS = G * slots;
   const uint32_t idx_bits = bits_needed(GS);
   const uint32_t code_bits = 2 * k;
-  const int passes = (int)((code_bits + 10) / 11);
-  SortPass pass[3];
+  // digit width: <= 11 bits (three passes for k <= 16) or <= 8 bits (four passes, but a 4096-key tile then leaves in runs of
+  // ~16 keys = 128 B per digit instead of ~4 keys = 32 B); MSSPE_SORT_BITS picks, see DESIGN.md section 4
+  static const int max_digit = getenv("MSSPE_SORT_BITS") ? std::min(11, std::max(4, atoi(getenv("MSSPE_SORT_BITS")))) : 11;
+  const int passes = (int)((code_bits + max_digit - 1) / max_digit);
+  SortPass pass[8];
   {
     int left = (int)code_bits, shift = (int)idx_bits;
     for (int p = 0; p < passes; p++) { const int b = (left + (passes - p) - 1) / (passes - p); pass[p].shift = shift; pass[p].bits = b; shift += b; left -= b; }
