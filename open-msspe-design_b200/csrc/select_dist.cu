@@ -28,7 +28,7 @@ namespace {
 
 // per call (DistArgs): kmax = not-yet-final entries a unit may hold (fixed-size exchange record), wmax = iterations verified
 // ahead per round, xw = wmax + 4 words per cross-list row ([0] live count at t_final, [1 + i] cover-time histogram)
-constexpr uint32_t DIST_XCAP = 4096;    // most cross lists staged per round (error beyond)
+constexpr uint32_t DIST_XCAP = 32768;   // most cross lists staged per round (error beyond); 4096 was short at the complete configs[4] on 8 ranks
 constexpr uint32_t DIST_XSTAGE = 256;   // rows of the exchange buffer when the job has more cross lists than that: the window adapts
 constexpr uint32_t DIST_SL = 3;         // partitions of one cross list a rank can report per round
 constexpr uint32_t DIST_PW = 3;         // words per reported partition: unit + 1, last cover time, first live genome at the queried iteration
@@ -621,7 +621,7 @@ extern "C" int msspe_select_both_dist(msspe_ctx* c, uint32_t max_iter, uint32_t 
   int rc = MSSPE_OK;
   if (!c->dist) { c->set_error("msspe_select_both_dist: msspe_dist_init first"); return MSSPE_ERR_STATE; }
   DistState* ds0 = (DistState*)c->dist;
-  for (uint32_t rows = ds0->rows_hint ? ds0->rows_hint : DIST_XSTAGE; ; rows *= 4) {
+  for (uint32_t rows = std::min(ds0->rows_hint ? ds0->rows_hint : DIST_XSTAGE, DIST_XCAP); ; rows = std::min(rows * 4u, DIST_XCAP)) {
     bool retry = false;
     rc = dist_select_impl(c, max_iter, mms, out_fwd, n_fwd, out_rev, n_rev, rows, &retry);
     if (!(retry && rows < DIST_XCAP)) { if (rc == MSSPE_OK) ds0->rows_hint = rows; break; }   // replicated outcome: every rank keeps the same hint
@@ -839,7 +839,7 @@ int dist_select_impl(msspe_ctx* c, uint32_t max_iter, uint32_t mms, msspe_candid
   // the all-reduced buffer: rows of the staged cross lists | ties of local lists | reported partitions | local best records | limit flag
   X.xcap = max_nx <= xstage_rows ? std::max<uint32_t>(128u, (max_nx + 127u) & ~127u) : xstage_rows;
   // iterations verified ahead per round: as many as 256 KB of histogram rows per direction allow (62 ... 1020)
-  X.wmax = std::min<uint32_t>(std::min<uint32_t>(1020u, std::max<uint32_t>(62u, 65536u / X.xcap - 4u)), std::max<uint32_t>(max_iter, 1u));
+  X.wmax = std::min<uint32_t>(std::min<uint32_t>(1020u, std::max<uint32_t>(62u, 65536u / X.xcap > 4u ? 65536u / X.xcap - 4u : 0u)), std::max<uint32_t>(max_iter, 1u));
   X.xw = X.wmax + 4u;
   {
     PartCtl h0; memset(&h0, 0, sizeof h0); h0.wmax = X.wmax; h0.tq = T_INF; h0.tq_next = T_INF;

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """One design job over N GPUs (torchrun): every rank loads the columns of its partition range, builds its index, and
 msspe_select_both_dist must return exactly what one GPU returns for the whole alignment.
-  torchrun --nproc-per-node 2 tools/run_dist_select.py [case ...]      cases: small, repeats, cfg2, cfg5shard, cfg3xN, tiny_k"""
+  torchrun --nproc-per-node 2 tools/run_dist_select.py [case ...]      cases: small, repeats, cfg2, cfg5shard, cfg3xN, cfg5xN, tiny_k"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "open-msspe-design_b200"))
@@ -43,6 +43,8 @@ def case(name):
         return g, k, 1000, 10, (W, S, w)
     if name == "cfg5shard":
         return synth.synth_genomes(12_500, 30_000, 5, clades=256, p_clade=0.10, p_leaf=0.01), 13, 1000, 10, (W, S, w)
+    if name == "cfg5xN":    # 12,500 x world genomes of 30 kb: at 8 ranks exactly BASELINE configs[4] (100,000 x 30 kb)
+        return synth.synth_genomes(12_500 * world, 30_000, 5, clades=256, p_clade=0.10, p_leaf=0.01), 13, 1000, 10, (W, S, w)
     if name == "cfg3xN":    # bench.py --gpus N: N x 10,000 genomes of the cfg3 shape
         cfgd = dict(synth.CONFIGS["cfg3"]); k = cfgd.pop("k"); cfgd["n"] *= world
         return synth.synth_genomes(**cfgd), k, 1000, 2, (W, S, w)
@@ -55,6 +57,8 @@ for name in (sys.argv[1:] or ["small", "repeats", "cfg2"]):
     eng = m.Engine(k, W, S, w, device=lr)
     eng.load_genomes(shard.reshape(-1), synth.offsets_for(shard))
     eng.build_index()
+    eng.build_index()
+    build_ms = eng.timing().index_ms + eng.timing().encode_ms
     eng.dist_init(dist, dev)
     res = None
     try:
@@ -65,7 +69,7 @@ for name in (sys.argv[1:] or ["small", "repeats", "cfg2"]):
             dt = time.perf_counter() - t0
             tm = eng.timing()
         res = (a, b, int(tm.select_evals[0] + tm.select_evals[1]))
-        msg = "%d + %d winners, evals %d, %.3f ms (device %.3f)" % (len(a), len(b), res[2], 1e3 * dt, tm.select_ms[0])
+        msg = "%d genomes x %d columns, shard index build %.2f ms, %d + %d winners, evals %d, %.3f ms (device %.3f)" % (g.shape[0], g.shape[1], build_ms, len(a), len(b), res[2], 1e3 * dt, tm.select_ms[0])
     except m.MsspeError as e:
         msg = "error: %s" % e
     ok = None
@@ -73,6 +77,8 @@ for name in (sys.argv[1:] or ["small", "repeats", "cfg2"]):
         e1 = m.Engine(k, W, S, w, device=lr)
         e1.load_genomes(g.reshape(-1), synth.offsets_for(g))
         e1.build_index()
+        e1.build_index()
+        build1_ms = e1.timing().index_ms + e1.timing().encode_ms
         a1, b1 = e1.select_both(it, mms, m.SELECT_PARTITIONED)
         t0 = time.perf_counter(); a1, b1 = e1.select_both(it, mms, m.SELECT_PARTITIONED); dt1 = time.perf_counter() - t0
         t1 = e1.timing()
@@ -84,7 +90,7 @@ for name in (sys.argv[1:] or ["small", "repeats", "cfg2"]):
                     bad = [i for i in range(n) if x[i].tobytes() != y[i].tobytes()]
                     print("  %s: len %d vs %d, first differences %s" % (lab, len(x), len(y), [(i, x[i], y[i]) for i in bad[:3]]))
                 print("  evals %d vs %d" % (res[2], int(t1.select_evals[0] + t1.select_evals[1])))
-        print("[%s] world %d: %s | one GPU: %d + %d winners, %.3f ms | identical: %s" % (name, world, msg, len(a1), len(b1), 1e3 * dt1, ok), flush=True)
+        print("[%s] world %d: %s | one GPU: index build %.2f ms, %d + %d winners, %.3f ms | identical: %s" % (name, world, msg, build1_ms, len(a1), len(b1), 1e3 * dt1, ok), flush=True)
         e1.close()
     eng.close()
     dist.barrier()
