@@ -370,8 +370,8 @@ int build_direction(msspe_ctx* c, int dir, float* enc_ms, float* idx_ms) {
   MSSPE_CUDA_TRY(c, cudaFreeAsync(counts, st));
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
   // ---- K2 ----
-  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.fwd_ids, (G * slots ? G * slots : 1) * sizeof(uint32_t), c->stream));
-  MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.fwd_ids, 0xFF, (G * slots ? G * slots : 1) * sizeof(uint32_t), st));
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&D.fwd_ids, (G * slots != 0 ? G * slots : 1) * sizeof(uint32_t), c->stream));
+  MSSPE_CUDA_TRY(c, cudaMemsetAsync(D.fwd_ids, 0xFF, (G * slots != 0 ? G * slots : 1) * sizeof(uint32_t), st));
   uint32_t n_codes = 0;
   if (R > 0) {
     MSSPE_CUDA_TRY(c, cudaMallocAsync(&key_b, Ra * 8, st));

@@ -1130,7 +1130,6 @@ greedy_incremental_kernel(const IncArgs A) {
   __shared__ uint32_t s_cnt2[2], s_sc[2], s_g[2], s_nt[2], s_can[2], s_dec, s_red[2 * (THREADS / 32)];
   uint32_t* s_cov = reinterpret_cast<uint32_t*>(lst + A.n_fp);  // [2][n_fp] this iteration's partition_coverage
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned int bar_target = 0;
   // bit d = direction d is finished.  A register: a bool[2] indexed by a loop variable lives in LOCAL memory, and the
   // fence of every grid barrier invalidates L1, so each `if (DONE(d))` after a barrier was a round trip to L2.
   uint32_t donem = A.ndirs < 2 ? 2u : 0u;

@@ -512,19 +512,6 @@ __global__ void dist_padcodes_kernel(const unsigned long long* __restrict__ code
   if (i < dmax) out[i] = i < n ? codes[i] : pad;
 }
 // in the sorted concatenation of all ranks' codes: first element of a run of >= 2 equal words
-__global__ void dist_dupflag_kernel(const uint64_t* __restrict__ keys, uint32_t n, unsigned long long pad, uint32_t* __restrict__ flags) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t k = keys[i];
-  flags[i] = (k != pad && i + 1 < n && keys[i + 1] == k && (i == 0 || keys[i - 1] != k)) ? 1u : 0u;
-}
-__global__ void dist_dupscatter_kernel(const uint64_t* __restrict__ keys, uint32_t n, unsigned long long pad, const uint32_t* __restrict__ scan, unsigned long long* __restrict__ xcodes) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t k = keys[i];
-  if (k != pad && i + 1 < n && keys[i + 1] == k && (i == 0 || keys[i - 1] != k)) xcodes[scan[i]] = k;
-}
-// local multi list m -> cross id (or none); cross id -> local m; local length and touched-unit mask of every cross list
 // one warp per local multi-partition list: is it a cross list, and which units do its postings touch?  (One THREAD per list
 // walked up to one posting per genome sequentially: 1.8 ms of the set-up at 40,000 genomes.)
 __global__ void __launch_bounds__(256) dist_xmap_kernel(PartArgs A, DistArgs X, int d, uint32_t* m_xid, uint32_t* xlen_local) {
