@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "engine.cuh"
 #include "thal_tables.cuh"
@@ -128,6 +129,7 @@ struct DimerArgs {
   uint64_t* nostruct; unsigned long long nostruct_cap; unsigned long long* n_nostruct;
   int dbg;  // diagnostic: 1 = skip loop candidates, 2 = skip traceback, 4 = skip fill entirely
   double2* scratch;  // thal_dimer_thread_kernel: k*k cells per resident thread
+  const uint32_t* colperm;  // matrix mode, optional: the order in which a row visits the columns (column_order())
   uint8_t* pairing;  // optional [n_pairs][MSSPE_MAX_OLIGO], zeroed: partner (1-based, in the reversed second oligo) of base i
 };
 
@@ -263,7 +265,8 @@ thal_dimer_kernel(const DimerArgs A) {
 
   for (unsigned long long p = (unsigned long long)blockIdx.x * GROUPS + grp; p < A.n_pairs; p += (unsigned long long)gridDim.x * GROUPS) {
     uint64_t ca, cb;
-    if (A.matrix) { ca = A.a[A.row_begin + p / A.n]; cb = A.b[p % A.n]; }
+    uint32_t col = 0;
+    if (A.matrix) { col = A.colperm ? A.colperm[p % A.n] : (uint32_t)(p % A.n); ca = A.a[A.row_begin + p / A.n]; cb = A.b[col]; }
     else { ca = A.a[p]; cb = A.b[p]; }
     __syncwarp(gmask);
     // numSeq1 = oligo1 5'->3'; numSeq2 = oligo2 REVERSED (not complemented); N sentinels at both ends
@@ -479,7 +482,7 @@ thal_dimer_kernel(const DimerArgs A) {
     if (gl == 0) {
       if (A.out) A.out[p] = res;
       if (A.matrix) {
-        const unsigned long long pair = (unsigned long long)(A.row_begin + p / A.n) * A.n + (p % A.n);
+        const unsigned long long pair = (unsigned long long)(A.row_begin + p / A.n) * A.n + col;
         if (res.no_structure) {
           const unsigned long long at = atomicAdd(A.n_nostruct, 1ull);
           if (at < A.nostruct_cap) A.nostruct[at] = pair;
@@ -606,7 +609,8 @@ thal_dimer_flat_kernel(const DimerArgs A) {
 
   for (unsigned long long p = (unsigned long long)blockIdx.x * GROUPS + grp; p < A.n_pairs; p += (unsigned long long)gridDim.x * GROUPS) {
     uint64_t ca, cb;
-    if (A.matrix) { ca = A.a[A.row_begin + p / A.n]; cb = A.b[p % A.n]; }
+    uint32_t col = 0;
+    if (A.matrix) { col = A.colperm ? A.colperm[p % A.n] : (uint32_t)(p % A.n); ca = A.a[A.row_begin + p / A.n]; cb = A.b[col]; }
     else { ca = A.a[p]; cb = A.b[p]; }
     __syncwarp(gmask);
     // numSeq1 = oligo1 5'->3'; numSeq2 = oligo2 REVERSED (not complemented); N sentinels at both ends
@@ -867,7 +871,7 @@ thal_dimer_flat_kernel(const DimerArgs A) {
     if (gl == 0) {
       if (A.out) A.out[p] = res;
       if (A.matrix) {
-        const unsigned long long pair = (unsigned long long)(A.row_begin + p / A.n) * A.n + (p % A.n);
+        const unsigned long long pair = (unsigned long long)(A.row_begin + p / A.n) * A.n + col;
         if (res.no_structure) {
           const unsigned long long at = atomicAdd(A.n_nostruct, 1ull);
           if (at < A.nostruct_cap) A.nostruct[at] = pair;
@@ -933,7 +937,8 @@ thal_dimer_thread_kernel(const DimerArgs A) {
 
   for (unsigned long long p = (unsigned long long)blockIdx.x * DIMER_THREADS + tid; p < A.n_pairs; p += (unsigned long long)gridDim.x * DIMER_THREADS) {
     uint64_t ca, cb;
-    if (A.matrix) { ca = A.a[A.row_begin + p / A.n]; cb = A.b[p % A.n]; }
+    uint32_t col = 0;
+    if (A.matrix) { col = A.colperm ? A.colperm[p % A.n] : (uint32_t)(p % A.n); ca = A.a[A.row_begin + p / A.n]; cb = A.b[col]; }
     else { ca = A.a[p]; cb = A.b[p]; }
     // numSeq1 = oligo1 5'->3': n1(i) = (ca >> 2(k-i)) & 3; numSeq2 = oligo2 REVERSED: n2(j) = (cb >> 2(j-1)) & 3; N (4) outside 1..k
     auto n1 = [&](int i) -> uint32_t { return (i < 1 || i > k) ? 4u : (uint32_t)(ca >> (2 * (k - i))) & 3u; };
@@ -1151,7 +1156,7 @@ thal_dimer_thread_kernel(const DimerArgs A) {
     }
     if (A.out) A.out[p] = res;
     if (A.matrix) {
-      const unsigned long long pair = (unsigned long long)(A.row_begin + p / A.n) * A.n + (p % A.n);
+      const unsigned long long pair = (unsigned long long)(A.row_begin + p / A.n) * A.n + col;
       if (res.no_structure) {
         const unsigned long long at = atomicAdd(A.n_nostruct, 1ull);
         if (at < A.nostruct_cap) A.nostruct[at] = pair;
@@ -1548,6 +1553,27 @@ struct DeviceBuf {  // stream-ordered scratch, returned to the pool when the cal
   ~DeviceBuf() { if (p) cudaFreeAsync(p, st); }
 };
 
+// Matrix mode hands 32 consecutive columns of one row to the 32 lanes of a warp (thal_dimer_thread_kernel), and a warp is
+// as slow as its busiest lane.  The work of a pair follows its pairing pattern: a row of the DP matrix has one paired cell
+// per occurrence of the complementary base in the second oligo.  Visiting the columns in the order of their base
+// composition (then of their code) gives the lanes of a warp second oligos with the same number of A, C, G and T, i.e. the
+// same number of paired cells in every row.  The results carry the ORIGINAL column index.
+int column_order(msspe_ctx* c, const uint64_t* codes, uint32_t n, uint32_t k, cudaStream_t st, DeviceBuf* dperm) {
+  std::vector<uint64_t> key(n);
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t cnt[4] = {0, 0, 0, 0};
+    for (uint32_t t = 0; t < k; t++) cnt[(codes[i] >> (2 * t)) & 3u]++;
+    key[i] = ((uint64_t)cnt[0] << 18 | (uint64_t)cnt[1] << 12 | (uint64_t)cnt[2] << 6 | cnt[3]) << 32 | i;
+  }
+  std::sort(key.begin(), key.end());
+  std::vector<uint32_t> perm(n);
+  for (uint32_t i = 0; i < n; i++) perm[i] = (uint32_t)key[i];
+  MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dperm->st = st, dperm->p), (size_t)n * 4, st));
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(dperm->p, perm.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));   // perm goes out of scope
+  return MSSPE_OK;
+}
+
 int launch_dimer_warp(msspe_ctx* c, DimerArgs& A, cudaStream_t st) {   // thal_dimer_kernel: one warp per pair (small batches, latency)
   const int k = A.k;
   const int sub = k <= 16 ? 8 : 16;
@@ -1843,6 +1869,8 @@ extern "C" int msspe_cross_dimer_device(msspe_ctx* c, const uint64_t* codes, uin
   A.dg_limit = dg_limit; A.edges = c->xd_edges; A.edge_cap = edge_capacity; A.n_edges = (unsigned long long*)dcnt.p;
   A.nostruct = c->xd_nostruct; A.nostruct_cap = nostruct_capacity; A.n_nostruct = (unsigned long long*)dcnt.p + 1;
   A.dbg = 0;
+  DeviceBuf dperm;
+  if (n >= 64 && !getenv("MSSPE_THAL_NO_ORDER")) { rc = column_order(c, codes, n, oligo_len, st, &dperm); if (rc) return rc; A.colperm = (const uint32_t*)dperm.p; }
   rc = launch_dimer(c, A, st);
   if (rc) return rc;
   unsigned long long cnt[2] = {0, 0};
@@ -1896,6 +1924,8 @@ extern "C" int msspe_cross_dimer(msspe_ctx* c, const uint64_t* codes, uint32_t n
   A.dg_limit = dg_limit; A.edges = (msspe_dimer_edge*)dedges.p; A.edge_cap = edge_capacity; A.n_edges = (unsigned long long*)dcnt.p;
   A.nostruct = (uint64_t*)dnos.p; A.nostruct_cap = nostruct_capacity; A.n_nostruct = (unsigned long long*)dcnt.p + 1;
   A.dbg = getenv("MSSPE_THAL_DBG") ? atoi(getenv("MSSPE_THAL_DBG")) : 0;
+  DeviceBuf dperm;
+  if (n >= 64 && !getenv("MSSPE_THAL_NO_ORDER")) { rc = column_order(c, codes, n, oligo_len, st, &dperm); if (rc) return rc; A.colperm = (const uint32_t*)dperm.p; }
   rc = launch_dimer(c, A, st);
   if (rc) return rc;
   unsigned long long cnt[2] = {0, 0};
