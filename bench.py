@@ -339,7 +339,7 @@ def thal_section(eng, m, synth, dist, world, rank, dev, barrier):
     pairs = THAL_POOL * THAL_POOL
     ncu = {}
     try:
-        with open(os.path.join(ROOT, "profiles", "r2s5_thal_thread_metrics.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2s6_thal_thread_metrics.json")) as f:
             ncu = json.load(f)
     except Exception:
         pass
