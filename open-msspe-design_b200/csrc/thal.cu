@@ -1348,6 +1348,7 @@ __device__ void m_end5(const ThalDeviceTables* T, const WK& w, int i, int varian
   *outH = H_max; *outS = S_max;
 }
 
+constexpr int MONO_GW = 16;   // lanes per oligo in the group kernel (oligos <= 20 nt have at most 16 rows per column)
 template <class WK>
 __device__ void mono_run(const ThalDeviceTables* T, WK& w, double saltCorr, double temp_K, msspe_thal_out* out) {
   const int* n1 = w.n1;
@@ -1468,6 +1469,143 @@ __device__ void mono_run(const ThalDeviceTables* T, WK& w, double saltCorr, doub
   out->no_structure = 0;
 }
 
+template <class WK>
+__device__ void mono_run_group(const ThalDeviceTables* T, WK& w, double saltCorr, double temp_K, msspe_thal_out* out, const int gl, const unsigned gmask) {
+  const int* n1 = w.n1;
+  const int len = w.len;
+  // MONO_GW lanes share one oligo: the cells of a column (all i for one j) depend on earlier columns only, so lane gl takes
+  // row i = j - 4 - gl of every column; the exterior recursion gives its four variants to four lanes; the traceback is lane 0's
+  out->ds = 0; out->dh = 0; out->dg = 0; out->tm = 0; out->no_structure = 1; out->n_bp = 0;
+  for (int i = 1 + gl; i <= len; i += MONO_GW)
+    for (int j = i; j <= len; ++j) {
+      if (j - i < MIN_HRPN_LOOP + 1 || !m_bp(n1[i], n1[j])) { w.Hm[i][j] = INFINITY; w.Sm[i][j] = -1.0; }
+      else { w.Hm[i][j] = 0.0; w.Sm[i][j] = kMinEntropy; }
+    }
+  __syncwarp(gmask);
+  for (int j = 2; j <= len; ++j) {
+    for (int i = j - MIN_HRPN_LOOP - 1 - gl; i >= 1; i -= MONO_GW) {
+      if (!isfinite(w.Hm[i][j])) continue;
+      double S0 = w.Sm[i][j], H0 = w.Hm[i][j];
+      const double T0 = (H0 + M_DHI) / (S0 + M_DSI + M_RC);
+      double S1 = w.Sm[i + 1][j - 1] + m_Ss(T, w, i, j);
+      double H1 = w.Hm[i + 1][j - 1] + m_Hs(T, w, i, j);
+      const double T1 = (H1 + M_DHI) / (S1 + M_DSI + M_RC);
+      if (S1 < kMinEntropyCutoff) { S1 = kMinEntropy; H1 = 0.0; }
+      if (S0 < kMinEntropyCutoff) { S0 = kMinEntropy; H0 = 0.0; }
+      if (T1 > T0) { w.Sm[i][j] = S1; w.Hm[i][j] = H1; } else { w.Sm[i][j] = S0; w.Hm[i][j] = H0; }
+      double s = -1.0, h = INFINITY;
+      m_loops(T, w, i, j, &s, &h, 0);
+      s = -1.0; h = INFINITY;
+      m_hairpin_loop(T, w, i, j, &s, &h, 0);
+      if (isfinite(h)) {
+        if (s < kMinEntropyCutoff) { s = kMinEntropy; h = 0.0; }
+        w.Sm[i][j] = s; w.Hm[i][j] = h;
+      }
+    }
+    __syncwarp(gmask);
+  }
+  // exterior fragments
+  if (gl == 0) {
+    w.send5[0] = w.send5[1] = -1.0;
+    w.hend5[0] = w.hend5[1] = INFINITY;
+    for (int i = 2; i <= len; i++) { w.send5[i] = kMinEntropy; w.hend5[i] = 0; }
+  }
+  __syncwarp(gmask);
+  for (int i = 2; i <= len; ++i) {
+    double eh[5], es[5], Tm[6];
+    {
+      double vh = 0.0, vs = 0.0;
+      if (gl < 4) m_end5(T, w, i, gl + 1, &vh, &vs);          // variant gl + 1 on lane gl
+      for (int v = 1; v <= 4; v++) {
+        eh[v] = __shfl_sync(gmask, vh, v - 1, MONO_GW);
+        es[v] = __shfl_sync(gmask, vs, v - 1, MONO_GW);
+      }
+    }
+    if (gl == 0) {
+    Tm[1] = (w.hend5[i - 1] + M_DHI) / (w.send5[i - 1] + M_DSI + M_RC);
+    for (int v = 1; v <= 4; v++) Tm[v + 1] = (eh[v] + M_DHI) / (es[v] + M_DSI + M_RC);
+    int mx;
+    if (Tm[1] > Tm[2] && Tm[1] > Tm[3] && Tm[1] > Tm[4] && Tm[1] > Tm[5]) mx = 1;
+    else if (Tm[2] > Tm[3] && Tm[2] > Tm[4] && Tm[2] > Tm[5]) mx = 2;
+    else if (Tm[3] > Tm[4] && Tm[3] > Tm[5]) mx = 3;
+    else if (Tm[4] > Tm[5]) mx = 4;
+    else mx = 5;
+    if (mx == 1) { w.send5[i] = w.send5[i - 1]; w.hend5[i] = w.hend5[i - 1]; }
+    else {
+      const int v = mx - 1;
+      const double G = eh[v] - (temp_K * (es[v]));
+      if (G < 0.0) { w.send5[i] = es[v]; w.hend5[i] = eh[v]; }
+      else { w.send5[i] = w.send5[i - 1]; w.hend5[i] = w.hend5[i - 1]; }
+    }
+    }
+    __syncwarp(gmask);
+  }
+  if (gl != 0) return;                       // traceback and result: lane 0
+  const double mh = w.hend5[len], ms = w.send5[len];
+  if (!isfinite(mh) || !isfinite(ms)) return;
+  // traceback with an explicit stack
+  int bpv[MONO_MAX + 2];
+  for (int t = 0; t < len; ++t) bpv[t] = 0;
+  struct { short i, j, m; } stk[4 * MONO_MAX];
+  int sp = 0;
+#define M_PUSH(a_, b_, c_) do { if (sp < 4 * MONO_MAX) { stk[sp].i = (short)(a_); stk[sp].j = (short)(b_); stk[sp].m = (short)(c_); sp++; } } while (0)
+  M_PUSH(len, 0, 1);
+  while (sp > 0) {
+    sp--;
+    int i = stk[sp].i;
+    const int j = stk[sp].j, m = stk[sp].m;
+    if (m == 1) {
+      while (i >= 1 && eq2(w.send5[i], w.send5[i - 1]) && eq2(w.hend5[i], w.hend5[i - 1])) --i;
+      if (i == 0) continue;
+      bool handled = false;
+      for (int v = 1; v <= 4 && !handled; v++) {
+        double eh, es;
+        m_end5(T, w, i, v, &eh, &es);
+        if (!(eq2(w.send5[i], es) && eq2(w.hend5[i], eh))) continue;
+        handled = true;
+        const int kmax = m_end5_kmax(i, v);
+        for (int k = 0; k <= kmax; ++k) {
+          double xS, xH;
+          m_end5_term(T, w, i, k, v, &xS, &xH);
+          const int pi = (v == 1 || v == 3) ? k + 1 : k + 2;
+          const int pj = (v <= 2) ? i : i - 1;
+          if (eq2(w.send5[i], xS) && eq2(w.hend5[i], xH)) { M_PUSH(pi, pj, 0); break; }
+          else if (eq2(w.send5[i], w.send5[k] + xS) && eq2(w.hend5[i], w.hend5[k] + xH)) { M_PUSH(pi, pj, 0); M_PUSH(k, 0, 1); break; }
+        }
+      }
+    } else {
+      bpv[i - 1] = j; bpv[j - 1] = i;
+      double s1 = -1.0, h1 = INFINITY, s2 = -1.0, h2 = INFINITY;
+      m_hairpin_loop(T, w, i, j, &s1, &h1, 1);
+      m_loops(T, w, i, j, &s2, &h2, 2);
+      if (eq2(w.Sm[i][j], m_Ss(T, w, i, j) + w.Sm[i + 1][j - 1]) && eq2(w.Hm[i][j], m_Hs(T, w, i, j) + w.Hm[i + 1][j - 1])) {
+        M_PUSH(i + 1, j - 1, 0);
+      } else if (eq2(w.Sm[i][j], s1) && eq2(w.Hm[i][j], h1)) {
+        // hairpin loop closes here
+      } else if (eq2(w.Sm[i][j], s2) && eq2(w.Hm[i][j], h2)) {
+        bool done = false;
+        for (int d = j - i - 3; d >= MIN_HRPN_LOOP + 1 && d >= j - i - 2 - w.maxLoop && !done; --d)
+          for (int ii = i + 1; ii < j - d; ++ii) {
+            const int jj = d + ii;
+            double es = -1.0, eh = INFINITY;
+            m_bulge_internal(T, w, i, j, ii, jj, &es, &eh, 1);
+            if (eq2(w.Sm[i][j], es + w.Sm[ii][jj]) && eq2(w.Hm[i][j], eh + w.Hm[ii][jj])) { M_PUSH(ii, jj, 0); done = true; break; }
+          }
+      }
+    }
+  }
+#undef M_PUSH
+  int N = 0;
+  for (int i = 1; i < len; ++i) if (bpv[i - 1] > 0) N++;
+  out->n_bp = N / 2;
+  const double t = (mh / (ms + (((N / 2) - 1) * saltCorr))) - kAbsZero;
+  out->dg = mh - (temp_K * (ms + (((N / 2) - 1) * saltCorr)));
+  out->ds = ms + (((N / 2) - 1) * saltCorr);
+  out->dh = mh;
+  out->tm = t;
+  out->no_structure = 0;
+}
+
 template <int M>
 __global__ void __launch_bounds__(64)
 thal_mono_kernel(const uint64_t* __restrict__ codes, uint32_t n, int k, const ThalDeviceTables* T, double saltCorr, double temp_K,
@@ -1489,6 +1627,29 @@ thal_mono_kernel(const uint64_t* __restrict__ codes, uint32_t n, int k, const Th
 }
 
 // ---------------------------------------------------------------- device: oligotm + GC
+// MONO_GW lanes per oligo (mono_run_group), the DP scratch of the group in shared memory: 4 oligos per 64-thread block
+template <int M>
+__global__ void __launch_bounds__(64)
+thal_mono_group_kernel(const uint64_t* __restrict__ codes, uint32_t n, int k, const ThalDeviceTables* T, double saltCorr, double temp_K,
+                       int maxLoop, msspe_thal_out* out) {
+  extern __shared__ __align__(16) unsigned char mono_smem[];
+  const int grp = threadIdx.x / MONO_GW, gl = threadIdx.x % MONO_GW;
+  const uint32_t t = blockIdx.x * (64 / MONO_GW) + grp;
+  if (t >= n) return;                                  // whole groups leave together
+  const unsigned gmask = (MONO_GW == 32 ? 0xffffffffu : ((1u << MONO_GW) - 1u)) << ((threadIdx.x & 31) / MONO_GW * MONO_GW);
+  MonoWorkT<M>& w = reinterpret_cast<MonoWorkT<M>*>(mono_smem)[grp];
+  const uint64_t c = codes[t];
+  if (gl == 0) {
+    w.len = k; w.maxLoop = maxLoop;
+    for (int x = 0; x < k; x++) w.n1[x + 1] = (int)((c >> (2 * (k - 1 - x))) & 3u);
+    w.n1[0] = 4; w.n1[k + 1] = 4;
+  }
+  __syncwarp(gmask);
+  msspe_thal_out r;
+  mono_run_group(T, w, saltCorr, temp_K, &r, gl, gmask);
+  if (gl == 0) out[t] = r;
+}
+
 struct OligoTmConsts { double salt_term; double conc_term[2]; };  // 0.368*(len-1)*ln(K/1000); 1.987*ln(C/4e9 | C/1e9)
 
 __global__ void oligotm_kernel(const uint64_t* __restrict__ codes, uint32_t n, int k, const ThalDeviceTables* T, OligoTmConsts K,
@@ -1565,7 +1726,20 @@ int column_order(msspe_ctx* c, const uint64_t* codes, uint32_t n, uint32_t k, cu
     for (uint32_t t = 0; t < k; t++) cnt[(codes[i] >> (2 * t)) & 3u]++;
     key[i] = ((uint64_t)cnt[0] << 18 | (uint64_t)cnt[1] << 12 | (uint64_t)cnt[2] << 6 | cnt[3]) << 32 | i;
   }
-  std::sort(key.begin(), key.end());
+  static const int order_mode = getenv("MSSPE_THAL_ORDER") ? atoi(getenv("MSSPE_THAL_ORDER")) : 2;
+  if (order_mode == 1) std::sort(key.begin(), key.end());       // composition, then position in the pool
+  else {                                                        // 2: composition, then code from the 3' end; 3: from the 5' end
+    std::sort(key.begin(), key.end(), [&](uint64_t x, uint64_t y) {
+      if ((x >> 32) != (y >> 32)) return (x >> 32) < (y >> 32);
+      uint64_t cx = codes[(uint32_t)x], cy = codes[(uint32_t)y];
+      if (order_mode == 2) {   // reverse the 2-bit groups: the second oligo enters the DP matrix reversed, column 1 = its 3' end
+        uint64_t rx = 0, ry = 0;
+        for (uint32_t t = 0; t < k; t++) { rx = (rx << 2) | ((cx >> (2 * t)) & 3u); ry = (ry << 2) | ((cy >> (2 * t)) & 3u); }
+        cx = rx; cy = ry;
+      }
+      return cx != cy ? cx < cy : (uint32_t)x < (uint32_t)y;
+    });
+  }
   std::vector<uint32_t> perm(n);
   for (uint32_t i = 0; i < n; i++) perm[i] = (uint32_t)key[i];
   MSSPE_CUDA_TRY(c, cudaMallocAsync(&(dperm->st = st, dperm->p), (size_t)n * 4, st));
@@ -1643,7 +1817,11 @@ int launch_mono_m(msspe_ctx* c, const uint64_t* d_codes, uint32_t n, int k, cons
   int per_block = (int)((c->smem_optin - 1024) / sizeof(MonoWorkT<M>));
   if (per_block > 64) per_block = 64;    // __launch_bounds__(64)
   const bool smem_ok = per_block >= 1 && !getenv("MSSPE_MONO_GLOBAL") && (uint64_t)n <= (uint64_t)per_block * (uint64_t)c->sm_count;  // one wave (measured: 0.49 vs 0.65 ms at 600, slower beyond one wave)
-  if (smem_ok) {
+  if (M == 16 && k <= 16 && !getenv("MSSPE_MONO_THREAD")) {   // 16 lanes per oligo, 4 oligos per block
+    const size_t smem = 4 * sizeof(MonoWorkT<M>);
+    MSSPE_CUDA_TRY(c, cudaFuncSetAttribute(thal_mono_group_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { KPROF(c, KP_THERMO, st, (uint64_t)n * 56) thal_mono_group_kernel<M><<<(n + 3) / 4, 64, smem, st>>>(d_codes, n, k, T, K.saltCorr, K.t_user_K, K.maxLoop, out); }
+  } else if (smem_ok) {
     // spread the batch over all SMs: fewer threads per block than fit, so that every SM gets a block
     int tpb = (int)((n + (uint32_t)c->sm_count - 1) / (uint32_t)c->sm_count);
     if (tpb < 1) tpb = 1;
