@@ -99,6 +99,7 @@ static void free_genomes(msspe_ctx* c) {
 
 extern "C" void msspe_destroy(msspe_ctx* c) {
   msspe_join_reserve(c);
+  if (c && c->h_stage) { cudaFreeHost(c->h_stage); c->h_stage = nullptr; c->h_stage_bytes = 0; }
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);

@@ -112,6 +112,7 @@ struct msspe_ctx {
   cudaStream_t stream = nullptr;      // main stream (own or caller's)
   cudaStream_t stream2 = nullptr;     // second direction
   std::thread* reserve_thread = nullptr;   // msspe_reserve_pool: background first touch of the pool
+  void* h_stage = nullptr; size_t h_stage_bytes = 0;   // pinned staging for small results (grown on demand)
   bool own_stream = true;
   cudaEvent_t ev[8] = {};
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;

@@ -1992,13 +1992,25 @@ extern "C" int msspe_primer_thermo(msspe_ctx* c, const uint64_t* codes, uint32_t
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev_join, c->stream2));
   MSSPE_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_join, 0));
   MSSPE_CUDA_TRY(c, cudaGetLastError());
-  std::vector<msspe_thal_out> h((size_t)n * 3);
-  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(tm, dtm.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(gc, dgc.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(h.data(), dout.p, h.size() * sizeof(msspe_thal_out), cudaMemcpyDeviceToHost, st));
+  // results come back through the context's pinned staging buffer (a device-to-pageable copy goes through the driver's own
+  // staging, chunk by chunk, with the host blocked)
+  const size_t out_bytes = (size_t)n * 3 * sizeof(msspe_thal_out), need = out_bytes + (size_t)n * 16;
+  if (c->h_stage_bytes < need) {
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr; c->h_stage_bytes = 0;
+    MSSPE_CUDA_TRY(c, cudaMallocHost(&c->h_stage, need));
+    c->h_stage_bytes = need;
+  }
+  const msspe_thal_out* h = reinterpret_cast<const msspe_thal_out*>(c->h_stage);
+  double* h_tm = reinterpret_cast<double*>((unsigned char*)c->h_stage + out_bytes);
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(h_tm, dtm.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(h_tm + n, dgc.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  MSSPE_CUDA_TRY(c, cudaMemcpyAsync(c->h_stage, dout.p, out_bytes, cudaMemcpyDeviceToHost, st));
   MSSPE_CUDA_TRY(c, cudaEventRecord(c->ev[7], st));
   MSSPE_CUDA_TRY(c, cudaStreamSynchronize(st));
   MSSPE_CUDA_TRY(c, cudaEventElapsedTime(&c->timing.thermo_ms, c->ev[6], c->ev[7]));
+  memcpy(tm, h_tm, (size_t)n * 8);
+  memcpy(gc, h_tm + n, (size_t)n * 8);
   for (uint32_t i = 0; i < n; i++) {  // align_thermod: negative or absent structure temperatures report 0
     const double a = h[i].tm, e = h[(size_t)n + i].tm, hp = h[(size_t)2 * n + i].tm;
     self_any[i] = a < 0.0 ? 0.0 : a;
