@@ -478,7 +478,7 @@ int msspe_build_fast(msspe_ctx* c) {
   const uint32_t code_bits = 2 * k;
   // digit width: <= 11 bits (three passes for k <= 16) or <= 8 bits (four passes, but a 4096-key tile then leaves in runs of
   // ~16 keys = 128 B per digit instead of ~4 keys = 32 B); MSSPE_SORT_BITS picks, see DESIGN.md section 4
-  static const int max_digit = getenv("MSSPE_SORT_BITS") ? std::min(11, std::max(4, atoi(getenv("MSSPE_SORT_BITS")))) : 11;
+  const int max_digit = getenv("MSSPE_SORT_BITS") ? std::min(11, std::max(4, atoi(getenv("MSSPE_SORT_BITS")))) : 11;
   const int passes = (int)((code_bits + max_digit - 1) / max_digit);
   SortPass pass[8];
   {

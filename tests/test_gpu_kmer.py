@@ -216,6 +216,32 @@ def test_low_complexity_windows_repeat_words(oracle_lib):
         eng.close()
 
 
+def test_index_sort_with_narrow_digits(oracle_lib, monkeypatch):
+    """MSSPE_SORT_BITS=8: four 8-bit passes with ballot ranking instead of three 10-11-bit passes (kmer_build_fast.cu); the
+    index must not depend on the digit width."""
+    import msspe_b200 as m
+    fa = _random_alignment(11, 60, 3000)
+    _, (bases, offs) = _fasta_to_arrays(fa)
+    ref = None
+    for bits in (None, "8", "5"):
+        if bits:
+            monkeypatch.setenv("MSSPE_SORT_BITS", bits)
+        else:
+            monkeypatch.delenv("MSSPE_SORT_BITS", raising=False)
+        eng = m.Engine(15, 500, 250, 50)
+        eng.load_genomes(bases, offs)
+        eng.build_index()
+        got = [tuple(np.asarray(x).tobytes() for x in eng.index(d)) for d in (0, 1)]
+        if ref is None:
+            ref = got
+            for d in (0, 1):
+                want, _ = oracle_lib.segment_slots(fa, 500, 250, 50, 15, d)
+                assert np.array_equal(eng.segment_kmers(d), want)
+        else:
+            assert got == ref
+        eng.close()
+
+
 def test_identical_genomes_tie_storm(oracle_lib):
     """p = 0: every k-mer of a partition ties with every other; the tie-break decides everything."""
     import msspe_b200 as m
