@@ -70,7 +70,7 @@ def clock_sampler(stop, out, gpu_index):
             r = get_reasons(h)
             flag = lambda bit: "Active" if r & bit else "Not Active"  # noqa: E731
             out.append([str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(mx), flag(0x8), flag(0x40), flag(0x20), flag(0x4)])
-            stop.wait(0.01)
+            stop.wait(0.004)
         return
     except Exception:
         pass
@@ -209,12 +209,15 @@ def run_multi(args, rank, world, local_rank, real_stdout):
         barrier()
         return max(e0.elapsed_time(e1), 0.0), wall, res
 
-    for _ in range(max(1, args.warmup - 1)):
-        one_step(True)
-    one_step(False)
+    # the sampler starts before the warm-up (NVML initialisation takes longer than the timed region on some boxes); what
+    # it saw before the timed region is dropped
     samples, stop = [], threading.Event()
     th = threading.Thread(target=clock_sampler, args=(stop, samples, local_rank), daemon=True)
     th.start()
+    for _ in range(max(1, args.warmup - 1)):
+        one_step(True)
+    one_step(False)
+    del samples[:]
     eng.reset_timing()
     ms_dev, wall_dev, res_dev = timed(lambda: one_step(True), args.steps)
     launches = eng.timing().kernel_launches
@@ -447,13 +450,15 @@ def main():
     t0 = time.perf_counter()
     _, _, _, _, tcold = one_step(True)
     cold_ms = 1e3 * (time.perf_counter() - t0)
-    for _ in range(max(0, args.warmup - 1)):
-        one_step(True)
-    one_step(False)
-
+    # the sampler starts before the warm-up (NVML initialisation takes longer than the timed region on some boxes); what
+    # it saw before the timed region is dropped
     samples, stop = [], threading.Event()
     th = threading.Thread(target=clock_sampler, args=(stop, samples, local_rank), daemon=True)
     th.start()
+    for _ in range(max(0, args.warmup - 1)):
+        one_step(True)
+    one_step(False)
+    del samples[:]
     eng.reset_timing()
     ms_dev, wall_dev, res_dev = timed(lambda: one_step(True), args.steps)
     launches = eng.timing().kernel_launches
