@@ -8,17 +8,18 @@
 // All arithmetic is FP64 and this file is compiled with -fmad=false so every expression rounds exactly like
 // scalar C without contraction; the tensor cores are not involved (nothing here is a contraction).
 //
-// Dimer kernel design (SM-issue bound, not HBM bound: 16 B in, <= 48 B out per pair):
-//   * a group of 16 lanes (oligos <= 16 nt) or 32 lanes (<= 32 nt) owns one ordered pair; a block holds
-//     8 resp. 4 groups and loops over pairs (persistent grid), so the tables are staged once per block;
-//   * tables in shared memory: stack / 1x1-mismatch / terminal-mismatch (256 entries x S,H each), loop
-//     penalties, and the LEFT/RIGHT end-of-duplex terms pre-tabulated on the host over their 2x2 base
-//     context for this run's RC (they are ~60 % of the scalar algorithm's work when recomputed per use);
-//   * the DP matrix (S,H per cell, k x k x 16 B) lives in shared memory; rows are filled in order; inside a
-//     row the end/stack terms of all cells are computed lane-parallel, then for each paired cell the
-//     bulge/internal-loop candidates are spread over the lanes by inner row and reduced with shuffles to the
-//     first minimum of dG in the scalar scan order (so the result equals the sequential scan);
-//   * best-cell selection, traceback (needed for the salt correction: N paired bases) and dS/dH/dG/Tm follow.
+// Dimer kernels (SM-issue bound, not HBM bound: 16 B in, <= 48 B out per pair), three exact forms chosen per call
+// (launch_dimer; MSSPE_THAL_KERNEL = thread | flat | legacy forces one; tests/test_gpu_thermo.py runs all of them):
+//   * thal_dimer_thread_kernel  one THREAD per ordered pair -- large batches of oligos <= 16 nt (the all-ordered-pairs
+//     matrix of delta_g.rs:61-81): paired cells compact in an L2-resident scratch, one (S,H) table with a branch-free
+//     candidate, one flat candidate loop per row, matrix columns visited in base-composition order (column_order);
+//   * thal_dimer_flat_kernel    one warp per pair, all loop candidates of a row in one flat index space -- oligos > 16 nt;
+//   * thal_dimer_kernel         one warp per pair, lanes over the inner rows of a cell's candidates -- small batches.
+// Common to all: tables in shared memory, among them the LEFT/RIGHT end-of-duplex terms pre-tabulated on the host over
+// their 2x2 base context for this run's RC (~60 % of the scalar algorithm's work when recomputed per use); rows of the DP
+// matrix in order; every minimum taken as (dG, scan-order key) so that the result equals Primer3's sequential scan; then
+// best-cell selection, traceback (needed for the salt correction: N paired bases) and dS/dH/dG/Tm.
+// Hairpin: thal_mono_group_kernel (16 lanes per oligo, oligos <= 16 nt) / thal_mono_kernel (one thread per oligo).
 #include <algorithm>
 #include <cmath>
 #include <cstring>
