@@ -1,17 +1,22 @@
 // kmer_build_fast.cu -- K1 + K2 for words of up to 16 bases (2-bit code and record index in ONE u64): the index build
 // of get_segment_manager + make_kmer_segments_windows_mapping (od-msspe/src/main.rs:196-255) in one pass per stage.
 //
-//   K1 encode_keys_kernel   one warp per segment: the w bases of the head (or tail) search window -> 2-bit, one key per
-//                           slot at a FIXED stride:  key = (code << idx_bits) | (segment * slots + slot),  all ones for a
-//                           slot that is invalid (non-ACGT base, main.rs:163-171) or a repeat inside its window
-//                           (itertools unique()).  No count pass, no scan, no compaction: 99 % of the slots are valid.
-//   K2 radix sort           LSD over the 2k code bits only, 3 passes of <= 11 bits (k <= 16): per pass a block histogram,
-//                           one scan, one scatter.  Keys carry their record index in the low bits, so a stable sort
-//                           leaves every posting list ascending by segment (main.rs:250) without a second key.  The
-//                           scatter ranks its tile warp by warp (__match_any_sync, stable), stages the tile in shared
-//                           memory in digit order and writes it out with consecutive threads on consecutive addresses.
-//                           Pass 0 drops the all-ones keys, so R (valid records) is only known on the device; later
-//                           passes read it there -- the host synchronises ONCE per build, for both directions together.
+//   K1 encode_keys_packed_kernel (search windows <= 64 bases) / encode_keys_kernel (longer windows)
+//                           the w bases of the head (or tail) search window -> 2-bit, one key per slot at a FIXED stride:
+//                           key = (code << idx_bits) | (segment * slots + slot),  all ones for a slot that is invalid
+//                           (non-ACGT base, main.rs:163-171) or a repeat inside its window (itertools unique()).  No count
+//                           pass, no scan, no compaction: 99 % of the slots are valid.  The packed form works on bit planes
+//                           of the window in registers and finds repeats by comparing the window with itself at every
+//                           distance (tests/test_encode_model.py is its executable specification).
+//   K2 radix sort           LSD over the 2k code bits only, 3 passes of <= 11 bits (k <= 16; MSSPE_SORT_BITS narrows the
+//                           digits): per pass a block histogram (block-major), a tiled two-kernel scan over digits x tiles,
+//                           one scatter.  Keys carry their record index in the low bits, so a stable sort leaves every
+//                           posting list ascending by segment (main.rs:250) without a second key.  The scatter ranks its
+//                           tile warp by warp (uniform round: one __match_all_sync; all-different round: tag and read back;
+//                           mixed: __match_any_sync or ballots), stages the tile in shared memory in digit order and writes
+//                           it out with consecutive threads on consecutive addresses.  Pass 0 drops the all-ones keys, so R
+//                           (valid records) is only known on the device; later passes read it there -- the host
+//                           synchronises ONCE per build, for both directions together.
 //   CSR                     head flags -> scan -> codes / post_off / postings / fwd_ids / list_part as in kmer_build.cu.
 // Algorithmic bytes: encode w B read + 8 B written per slot; histogram 8 B per key; scatter 16 B per
 // key ("2 x 8 B per record per pass"); CSR 8 + 4 B read, 4 + 4 B written per record.
