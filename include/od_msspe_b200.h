@@ -253,6 +253,13 @@ int msspe_shard_apply(msspe_ctx* ctx, uint8_t dir, uint32_t local_id, uint32_t n
 int msspe_thal_params_default(msspe_thal_raw_params* out);
 int msspe_thal_params_from_dir(const char* dir, msspe_thal_raw_params* out, char* err, size_t err_len);
 int msspe_set_thal_params(msspe_ctx* ctx, const msspe_thal_raw_params* p);
+/* Host-only diagnostic (no device, no ctx): one table as the kernels index it -- the expansion of `p` to the 5-symbol
+ * (A,C,G,T,N) arrays with Primer3's load rules -- under the name libprimer3 2.6.1's thal.c gives that array
+ * ("stackEntropies", "tstack2Enthalpies", "dangleEntropies3", "hairpinLoopEntropies", "atpS", ...; for
+ * "default{Tri,Tetra}loop{Entropies,Enthalpies}" `out` receives (key, value) pairs, key = the loop's base-5 digits).
+ * Returns the number of doubles written or a negative MSSPE_ERR_*.  What it is for: tests compare these arrays with the
+ * ones compiled into the Primer3 executables the reference spawns (primer.rs:125-140, delta_g.rs:90-108). */
+int msspe_thal_expanded_table(const msspe_thal_raw_params* p, const char* name, double* out, uint32_t cap);
 /* Replaces check_primers, primer.rs:143-166 (one primer3_core run): per primer the five numbers
  * parse_primer3_output reads (primer.rs:67-114), as raw FP64 before Primer3's "%.3f"/"%.2f" printing:
  * tm = oligotm at Primer3 defaults, gc = percent, self_any/self_end/hairpin = max(0, thal Tm). */

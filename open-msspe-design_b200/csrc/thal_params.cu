@@ -147,3 +147,43 @@ void msspe_thal_expand(const msspe_thal_raw_params* p_in, ThalDeviceTables* T) {
   sort_keyed(T->nTetraS, p->tetraloop_ds_seq, p->tetraloop_ds, 6, T->tetraKeyS, T->tetraS);
   sort_keyed(T->nTetraH, p->tetraloop_dh_seq, p->tetraloop_dh, 6, T->tetraKeyH, T->tetraH);
 }
+
+// Host-only diagnostic of the C ABI: one expanded table under the name libprimer3's thal.c gives it.  A CPU test compares
+// every one of them with the arrays compiled into the reference's Primer3 2.6.1 executables
+// (tests/golden/primer3_2_6_1_compiled_in_tables.json), so the tables the kernels index are pinned, not only the raw files.
+extern "C" int msspe_thal_expanded_table(const msspe_thal_raw_params* p, const char* name, double* out, uint32_t cap) {
+  if (!p || !name || !out) return MSSPE_ERR_INVALID;
+  std::vector<ThalDeviceTables> holder(1);
+  ThalDeviceTables* T = holder.data();
+  msspe_thal_expand(p, T);
+  const struct { const char* name; const double* v; int n; } plain[] = {
+      {"stackEntropies", T->stackS, 625},         {"stackEnthalpies", T->stackH, 625},
+      {"stackint2Entropies", T->stackint2S, 625}, {"stackint2Enthalpies", T->stackint2H, 625},
+      {"tstackEntropies", T->tstackS, 625},       {"tstackEnthalpies", T->tstackH, 625},
+      {"tstack2Entropies", T->tstack2S, 625},     {"tstack2Enthalpies", T->tstack2H, 625},
+      {"dangleEntropies3", T->dangle3S, 125},     {"dangleEnthalpies3", T->dangle3H, 125},
+      {"dangleEntropies5", T->dangle5S, 125},     {"dangleEnthalpies5", T->dangle5H, 125},
+      {"hairpinLoopEntropies", T->hairpinS, 30},  {"interiorLoopEntropies", T->interiorS, 30},
+      {"bulgeLoopEntropies", T->bulgeS, 30},      {"hairpinLoopEnthalpies", T->hairpinH, 30},
+      {"interiorLoopEnthalpies", T->interiorH, 30}, {"bulgeLoopEnthalpies", T->bulgeH, 30},
+      {"atpS", T->atpS, 25},                      {"atpH", T->atpH, 25}};
+  for (const auto& t : plain)
+    if (strcmp(name, t.name) == 0) {
+      if (cap < (uint32_t)t.n) return MSSPE_ERR_CAPACITY;
+      memcpy(out, t.v, sizeof(double) * t.n);
+      return t.n;
+    }
+  // loop bonus tables: (key, value) pairs in table order, key = base-5 digits of the loop (5 resp. 6 bases)
+  const struct { const char* name; const uint32_t* key; const double* v; int n; } keyed[] = {
+      {"defaultTriloopEntropies", T->triKeyS, T->triS, T->nTriS},
+      {"defaultTriloopEnthalpies", T->triKeyH, T->triH, T->nTriH},
+      {"defaultTetraloopEntropies", T->tetraKeyS, T->tetraS, T->nTetraS},
+      {"defaultTetraloopEnthalpies", T->tetraKeyH, T->tetraH, T->nTetraH}};
+  for (const auto& t : keyed)
+    if (strcmp(name, t.name) == 0) {
+      if (t.n < 0 || cap < 2u * (uint32_t)t.n) return MSSPE_ERR_CAPACITY;
+      for (int i = 0; i < t.n; i++) { out[2 * i] = (double)t.key[i]; out[2 * i + 1] = t.v[i]; }
+      return 2 * t.n;
+    }
+  return MSSPE_ERR_INVALID;
+}

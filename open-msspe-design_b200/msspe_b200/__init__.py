@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "msspe_set_thal_params", "msspe_primer_thermo", "msspe_thal_pairs", "msspe_thal_pairs_aligned", "msspe_cross_dimer",
     "msspe_fasta_open", "msspe_fasta_close", "msspe_fasta_records", "msspe_fasta_name", "msspe_fasta_bases",
     "msspe_fasta_offsets", "msspe_load_fasta", "msspe_kmer_stats", "msspe_kmer_stats_both", "msspe_coverage_summary", "msspe_vertex_cover", "msspe_shard_begin", "msspe_shard_buffers", "msspe_shard_count", "msspe_shard_firstpos", "msspe_shard_apply",
-    "msspe_get_kernel_profile", "msspe_cross_dimer_device", "msspe_dist_unique_id", "msspe_dist_init", "msspe_select_both_dist",
+    "msspe_get_kernel_profile", "msspe_thal_expanded_table", "msspe_cross_dimer_device", "msspe_dist_unique_id", "msspe_dist_init", "msspe_select_both_dist",
 ]
 
 
@@ -148,6 +148,7 @@ def load_library():
     L.msspe_coverage.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_uint64]
     L.msspe_thal_params_default.argtypes = [C.c_void_p]
+    L.msspe_thal_expanded_table.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_uint32]
     L.msspe_thal_params_from_dir.argtypes = [C.c_char_p, C.c_void_p, C.c_char_p, C.c_size_t]
     L.msspe_set_thal_params.argtypes = [C.c_void_p, C.c_void_p]
     L.msspe_primer_thermo.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32] + [C.c_void_p] * 5

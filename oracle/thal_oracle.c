@@ -16,6 +16,10 @@
  *
  * Pinning: dimer ANY reproduces the five real ntthal outputs the reference keeps at
  * delta_g.rs:197-230, and Tm/GC/self-any reproduce primer.rs:238-250 (tests/test_oracle_thermo.py).
+ * The parameter tables AS LOADED (every stack / dangle / loop / terminal-stack array, the AT penalty, the sorted
+ * tri- and tetraloop bonus tables) are bit-identical to the arrays compiled into the reference's own Primer3 2.6.1
+ * executables, read out of their Mach-O data by symbol name (oracle_thal_table below,
+ * tests/golden/primer3_2_6_1_compiled_in_tables.json).
  * PARITY UNPINNED (no golden vector exists in the reference): hairpin Tm > 0, END1 Tm > 0, bulge loops,
  * the single-line "No secondary structure" output.
  *
@@ -719,6 +723,43 @@ int oracle_thal_load_dir(const char* dir) {
   if ((p.n_tetraloop_dh = read_nloop(dir, "tetraloop.dh", p.tetraloop_dh_seq, p.tetraloop_dh, 128)) < 0) return -1;
   oracle_thal_set_params(&p);
   return 0;
+}
+
+/* ---- test hook: the loaded tables under the names libprimer3's thal.c gives them, so that they can be compared with the
+ * arrays compiled into the reference's Primer3 2.6.1 executables (tests/golden/primer3_2_6_1_compiled_in_tables.json,
+ * tools/extract_primer3_compiled_in_tables.py).  Returns the number of doubles written, -1 for an unknown name. ---- */
+int oracle_thal_table(const char* name, double* out, int cap) {
+  static const struct { const char* name; const double* p; int n; } T[] = {
+      {"stackEntropies", &stackS[0][0][0][0], 625}, {"stackEnthalpies", &stackH[0][0][0][0], 625},
+      {"stackint2Entropies", &stackint2S[0][0][0][0], 625}, {"stackint2Enthalpies", &stackint2H[0][0][0][0], 625},
+      {"tstackEntropies", &tstackS[0][0][0][0], 625}, {"tstackEnthalpies", &tstackH[0][0][0][0], 625},
+      {"tstack2Entropies", &tstack2S[0][0][0][0], 625}, {"tstack2Enthalpies", &tstack2H[0][0][0][0], 625},
+      {"dangleEntropies3", &dangle3S[0][0][0], 125}, {"dangleEnthalpies3", &dangle3H[0][0][0], 125},
+      {"dangleEntropies5", &dangle5S[0][0][0], 125}, {"dangleEnthalpies5", &dangle5H[0][0][0], 125},
+      {"hairpinLoopEntropies", hairpinS, 30}, {"interiorLoopEntropies", interiorS, 30}, {"bulgeLoopEntropies", bulgeS, 30},
+      {"hairpinLoopEnthalpies", hairpinH, 30}, {"interiorLoopEnthalpies", interiorH, 30}, {"bulgeLoopEnthalpies", bulgeH, 30},
+      {"atpS", &atpS[0][0], 25}, {"atpH", &atpH[0][0], 25}};
+  if (!params_loaded) return -1;
+  for (unsigned i = 0; i < sizeof T / sizeof T[0]; i++)
+    if (strcmp(name, T[i].name) == 0) {
+      if (cap < T[i].n) return -1;
+      memcpy(out, T[i].p, sizeof(double) * T[i].n);
+      return T[i].n;
+    }
+  return -1;
+}
+/* The sorted tri/tetraloop bonus tables: keys[8 * i .. ] = the loop as base indices (0..3), vals[i] its bonus. */
+int oracle_thal_loop_table(const char* name, unsigned char* keys, double* vals, int cap) {
+  const struct loopent* t; int n, len;
+  if (!params_loaded) return -1;
+  if (strcmp(name, "defaultTriloopEntropies") == 0) { t = triS; n = nTriS; len = 5; }
+  else if (strcmp(name, "defaultTriloopEnthalpies") == 0) { t = triH; n = nTriH; len = 5; }
+  else if (strcmp(name, "defaultTetraloopEntropies") == 0) { t = tetraS; n = nTetraS; len = 6; }
+  else if (strcmp(name, "defaultTetraloopEnthalpies") == 0) { t = tetraH; n = nTetraH; len = 6; }
+  else return -1;
+  if (cap < n) return -1;
+  for (int i = 0; i < n; i++) { memset(keys + 8 * i, 0xff, 8); memcpy(keys + 8 * i, t[i].key, len); vals[i] = t[i].value; }
+  return n;
 }
 
 /* ---- exported ---- */
