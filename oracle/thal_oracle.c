@@ -439,9 +439,11 @@ static void calc_hairpin(work_t* w, int i, int j, double* S, double* H, int tb) 
   }
   if (!fin(*H)) { *H = INFINITY; *S = -1.0; }
   if (*H > 0 && *S > 0 && (!(w->Hm[i][j] > 0) || !(w->Sm[i][j] > 0))) { *H = INFINITY; *S = -1.0; }
-  double T1 = (*H + w->dHi) / ((*S + w->dSi + w->RC));
-  double T2 = (w->Hm[i][j] + w->dHi) / ((w->Sm[i][j]) + w->dSi + w->RC);
-  if (T1 < T2 && tb == 0) { *S = w->Sm[i][j]; *H = w->Hm[i][j]; }
+  double rs, rh;
+  RSH(w, i, j, &rs, &rh);
+  double G1 = *H + rh - T_KELVIN * (*S + rs);
+  double G2 = w->Hm[i][j] + rh - T_KELVIN * (w->Sm[i][j] + rs);
+  if (G2 < G1 && tb == 0) { *S = w->Sm[i][j]; *H = w->Hm[i][j]; }
 }
 
 /* loop between closing pair (i,j) and inner pair (ii,jj), i<ii<jj<j */
@@ -767,6 +769,7 @@ int oracle_thal(const char* o1, const char* o2, int type, const msspe_thal_cond*
   if (!params_loaded) return -1;
   if (strlen(o1) > ORACLE_MAX_LEN || (o2 && strlen(o2) > ORACLE_MAX_LEN)) return -2;
   if (type == MSSPE_THAL_HAIRPIN) thal_hairpin(o1, c, out);
+  else if (type == 3) thal_dimer(o2, o1, c, MSSPE_THAL_END1, out, NULL);  /* thal_end2 = END1 with the oligos exchanged (not on od-msspe's path; kept so the whole ntthal fixture applies) */
   else thal_dimer(o1, o2, c, type, out, NULL);
   return 0;
 }
