@@ -1215,6 +1215,39 @@ __device__ bool m_find(const uint32_t* keys, const double* vals, int n, uint32_t
   return false;
 }
 
+// RSH(i, j) of thal.c in the unimolecular setting (second strand = the oligo itself, unreversed; dplx_init_H = 0,
+// dplx_init_S = -1e-11, RC = 0): the right-end term that Primer3 2.6.1 adds to both sides of the hairpin-closing comparison.
+template <class WK>
+__device__ void m_rsh(const ThalDeviceTables* T, const WK& w, int i, int j, double* S, double* H) {
+  const int a = w.n1[i], b = w.n1[j], a1 = w.n1[i + 1], b1 = w.n1[j + 1];
+  if (!m_bp(a, b)) { *S = -1.0; *H = INFINITY; return; }
+  const double aS = T->atpS[a * 5 + b], aH = T->atpH[a * 5 + b];
+  double S1 = aS + T->tstack2S[THAL_IDX4(a, a1, b, b1)];
+  double H1 = aH + T->tstack2H[THAL_IDX4(a, a1, b, b1)];
+  bool has = false;
+  double S2 = 0.0, H2 = 0.0;
+  if (!m_bp(a1, b1)) {
+    const double h3 = T->dangle3H[THAL_IDX3(a, a1, b)], h5 = T->dangle5H[THAL_IDX3(a, b, b1)];
+    if (isfinite(h3) && isfinite(h5)) {
+      S2 = aS + T->dangle3S[THAL_IDX3(a, a1, b)] + T->dangle5S[THAL_IDX3(a, b, b1)]; H2 = aH + h3 + h5; has = true;
+    } else if (isfinite(h3)) { S2 = aS + T->dangle3S[THAL_IDX3(a, a1, b)]; H2 = aH + h3; has = true; }
+    else if (isfinite(h5)) { S2 = aS + T->dangle5S[THAL_IDX3(a, b, b1)]; H2 = aH + h5; has = true; }
+  }
+  double G1 = H1 - kTK * S1, T1 = -INFINITY, G2, T2;
+  if (!isfinite(H1) || G1 > 0) { H1 = INFINITY; S1 = -1.0; G1 = 1.0; }
+  if (has) {
+    G2 = H2 - kTK * S2;
+    if (!isfinite(H2) || G2 > 0) { H2 = INFINITY; S2 = -1.0; G2 = 1.0; }
+    T2 = (H2 + M_DHI) / (S2 + M_DSI + M_RC);
+    if (isfinite(H1) && G1 < 0) {
+      T1 = (H1 + M_DHI) / (S1 + M_DSI + M_RC);
+      if (T1 < T2 && G2 < 0) { S1 = S2; H1 = H2; T1 = T2; }
+    } else if (G2 < 0) { S1 = S2; H1 = H2; T1 = T2; }
+  }
+  T2 = (aH + M_DHI) / (aS + M_DSI + M_RC);
+  if (isfinite(H1) && !(T1 < T2)) { *S = S1; *H = H1; } else { *S = aS; *H = aH; }
+}
+
 template <class WK>
 __device__ void m_hairpin_loop(const ThalDeviceTables* T, const WK& w, int i, int j, double* S, double* H, int tb) {
   const int* n1 = w.n1;
@@ -1245,9 +1278,15 @@ __device__ void m_hairpin_loop(const ThalDeviceTables* T, const WK& w, int i, in
   }
   if (!isfinite(*H)) { *H = INFINITY; *S = -1.0; }
   if (*H > 0 && *S > 0 && (!(w.Hm[i][j] > 0) || !(w.Sm[i][j] > 0))) { *H = INFINITY; *S = -1.0; }
-  const double T1 = (*H + M_DHI) / ((*S + M_DSI + M_RC));
-  const double T2 = (w.Hm[i][j] + M_DHI) / ((w.Sm[i][j]) + M_DSI + M_RC);
-  if (T1 < T2 && tb == 0) { *S = w.Sm[i][j]; *H = w.Hm[i][j]; }
+  // Primer3 2.6.1 compares free energies at 37 C with the right-end term on both sides (calc_hairpin calls RSH in the
+  // reference's ntthal executable; tests/golden/ntthal_emulated.json), not melting temperatures as older releases did
+  if (tb == 0) {
+    double rs, rh;
+    m_rsh(T, w, i, j, &rs, &rh);
+    const double G1 = *H + rh - kTK * (*S + rs);
+    const double G2 = w.Hm[i][j] + rh - kTK * (w.Sm[i][j] + rs);
+    if (G2 < G1) { *S = w.Sm[i][j]; *H = w.Hm[i][j]; }
+  }
 }
 
 template <class WK>

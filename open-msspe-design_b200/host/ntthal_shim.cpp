@@ -7,7 +7,9 @@
 //   stdout per pair either the 5-line block
 //            Calculated thermodynamical parameters for dimer:\tdS = %g\tdH = %g\tdG = %g\tt = %g
 //            SEQ\t..  SEQ\t..  STR\t..  STR\t..        (the drawn duplex)
-//          or the single line  "No secondary structure could be calculated"             (delta_g.rs:27-59 reads these)
+//          or, for a pair without any structure, NOTHING: that is what the reference's Primer3 2.6.1 executable does
+//          (its stdout under tools/a64emu, tests/golden/ntthal_emulated.json); the "No secondary structure could be
+//          calculated" string in that binary belongs to HAIRPIN mode and goes to stderr.  delta_g.rs:27-59 reads these.
 // All pairs of the run go to the device in one batch (msspe_thal_pairs_aligned); this file only parses text and draws.
 // There is no CPU fallback: without a usable CUDA device the program exits with an error.
 #include <cstdint>
@@ -64,6 +66,7 @@ void draw(const std::string& o1, const std::string& o2, const uint8_t* pairing, 
   const int t1 = n1 - i, t2 = n2 - j, L = t1 > t2 ? t1 : t2;
   rows[0] += o1.substr(i, t1) + std::string(L - t1, '-');
   rows[3] += r2.substr(j, t2) + std::string(L - t2, '-');
+  rows[1] += std::string(L, ' '); rows[2] += std::string(L, ' ');   // ntthal pads the two middle rows to the full width
 }
 
 }  // namespace
@@ -144,7 +147,7 @@ int main(int argc, char** argv) {
   std::string text;
   char buf[512];
   for (size_t t = 0; t < lines.size(); t++) {
-    if (out[t].no_structure) { text += "No secondary structure could be calculated\n"; continue; }
+    if (out[t].no_structure) continue;   // the reference executable prints nothing for such a pair
     snprintf(buf, sizeof buf, "Calculated thermodynamical parameters for dimer:\tdS = %g\tdH = %g\tdG = %g\tt = %g\n", out[t].ds, out[t].dh,
              out[t].dg, out[t].tm);
     text += buf;

@@ -348,9 +348,11 @@ int main(int argc, char** argv) {
     std::unordered_map<uint64_t, double> dg_of;
     for (uint64_t e = 0; e < ne; e++) dg_of[edges[e].pair] = edges[e].dg;
     std::unordered_set<uint64_t> nos_set(nos.begin(), nos.begin() + nn);
-    // parse_ntthal_output (delta_g.rs:27-59): input line t reads output line 5t.  Block u starts at line
-    // 5u - 4*m(u), m(u) = structure-less pairs before u (they print ONE line).  So line 0 of block u is read iff
-    // m(u) % 5 == 0, and then by input line t = u - 4*m(u)/5, whose primers get the edge.
+    // parse_ntthal_output (delta_g.rs:27-59): input line t reads output line 5t and skips four more.  The reference's ntthal
+    // (Primer3 2.6.1) prints a 5-line block per pair and NOTHING for a pair without structure (its own stdout under
+    // tools/a64emu, tests/golden/ntthal_emulated.json), so output block t belongs to the t-th pair THAT HAS a structure while
+    // the parser credits it to input line t: after m structure-less pairs every edge lands m input lines early, and the last
+    // m input lines read nothing.
     // conflict edges (main.rs:755-771) over the DISTINCT words (the reference keys its graph by word)
     std::unordered_map<std::string, uint32_t> node_of;
     std::vector<uint64_t> node_code; std::vector<const std::string*> node_word;
@@ -366,12 +368,11 @@ int main(int argc, char** argv) {
     for (uint64_t u = 0; u < lines.size(); u++) {
       const uint64_t pu = lines[u];
       if (nos_set.count(pu)) { m++; continue; }
-      if (m % 5 != 0) continue;
       auto it = dg_of.find(pu);
       if (it == dg_of.end()) continue;
       const float dg = via_text(it->second, "%g");                    // ntthal prints "%g"; the parser reads an f32
       if (!(dg < a.delta_g_threshold)) continue;
-      const uint64_t t = u - 4 * (m / 5);
+      const uint64_t t = u - m;
       const uint64_t pt = lines[t];
       const std::string& wa = primers[pt / n]->word; const std::string& wb = primers[pt % n]->word;
       if (!edge_ids.insert(wa + ":" + wb).second) continue;           // HashSet<Edge> keyed by id: first insert stays

@@ -341,9 +341,9 @@ std::vector<std::string> lines_of(const std::string& s) {                   // s
   return v;
 }
 
-// `ntthal -a ANY -mv .. -dv .. -n .. -d .. -t .. -i` emulation: per input line either the 5-line block or the
-// single "No secondary structure could be calculated" line (delta_g.rs:93-113; format strings recovered
-// from od-msspe/bin/ntthal).  Only line 0 carries numbers; SEQ/STR lines are placeholders (< 14 tokens).
+// `ntthal -a ANY -mv .. -dv .. -n .. -d .. -t .. -i` emulation: per input line the 5-line block, or nothing at all
+// for a pair without structure (delta_g.rs:93-113; that is what the reference's own executable prints, see
+// tests/golden/ntthal_emulated.json).  Only line 0 carries numbers; SEQ/STR lines are placeholders (< 14 tokens).
 std::string run_ntthal_text(const std::string& input, const Config& c, uint64_t* n_pairs) {
   auto r2 = [](float v) { char b[64]; snprintf(b, sizeof b, "%.2f", (double)v); return atof(b); };  // {:.2} argv
   msspe_thal_cond cond{r2(c.mv_conc), r2(c.dv_conc), r2(c.dntp_conc), r2(c.dna_conc), r2(c.annealing_temp), 30, 0};
@@ -360,7 +360,7 @@ std::string run_ntthal_text(const std::string& input, const Config& c, uint64_t*
     std::string a = l.substr(0, comma), b = l.substr(comma + 1);
     msspe_thal_out o; oracle_thal(a.c_str(), b.c_str(), MSSPE_THAL_ANY, &cond, &o);
     (*n_pairs)++;
-    if (o.no_structure) { out += "No secondary structure could be calculated\n"; continue; }
+    if (o.no_structure) continue;
     char buf[256];
     snprintf(buf, sizeof buf, "Calculated thermodynamical parameters for dimer:\tdS = %g\tdH = %g\tdG = %g\tt = %g\n",
              o.ds, o.dh, o.dg, o.tm);

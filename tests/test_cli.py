@@ -150,7 +150,8 @@ def test_cli_golden_files(exe, zika_fasta, tmp_path):
 
 @pytest.mark.gpu
 def test_cli_parser_desync_after_structureless_pairs(exe, oracle_lib, tmp_path):
-    """delta_g.rs:31-56: a pair without structure prints one line, the 5-line parser falls out of phase.  A pool with
+    """delta_g.rs:31-56: a pair without structure prints nothing (the reference's own ntthal, tests/golden/ntthal_emulated.json), so the
+    5-line parser credits every later block to an earlier input line.  A pool with
     {A,C}-only primers (no Watson-Crick partner letters) triggers it; --keep-all=false so the vertex cover runs."""
     import numpy as np
     rng = np.random.default_rng(11)

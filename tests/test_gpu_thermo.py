@@ -276,3 +276,40 @@ def test_cfg4_pool_20000_primers_vs_oracle(eng, oracle_lib):
     deleted = eng.vertex_cover(pool, ea, eb)
     want = _vertex_cover_by_degrees(pool, ea, eb)
     assert deleted.tolist() == want.tolist() and want.sum() > 100
+
+
+def test_engine_equals_the_reference_executable(eng):
+    """The kernels against REFERENCE OUTPUT: stdout of the reference's own Primer3 2.6.1 ntthal executable run under tools/a64emu
+    (tests/golden/ntthal_emulated.json) - ANY and END1 pairs of equal length and every HAIRPIN case up to 32 nt, random salts and
+    -maxloop included.  Compared as ntthal prints them ("%g", 6 significant digits); a structure-less case has empty stdout."""
+    import json
+    import os
+    import msspe_b200 as m
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "ntthal_emulated.json")) as f:
+        cases = json.load(f)["cases"]
+    ttype = {"ANY": m.THAL_ANY, "END1": m.THAL_END1, "HAIRPIN": m.THAL_HAIRPIN}
+    n = {"ANY": 0, "END1": 0, "HAIRPIN": 0}
+    n_hot = 0
+    for c in cases:
+        a = c["args"]
+        mode = a[1]
+        if mode not in ttype or "-i" in a:
+            continue
+        o = {"-maxloop": "30"}
+        o.update({a[i]: a[i + 1] for i in range(2, len(a), 2)})
+        s1, s2 = o["-s1"], o.get("-s2", o["-s1"])
+        if len(s1) != len(s2) or len(s1) > 32:
+            continue
+        cond = m.ThalCond(float(o["-mv"]), float(o["-dv"]), float(o["-n"]), float(o["-d"]), float(o["-t"]), int(o["-maxloop"]), 0)
+        g = eng.thal_pairs([m.encode_word(s1)], [m.encode_word(s2)], ttype[mode], cond, oligo_len=len(s1))[0]
+        if c["stdout"] == "":
+            assert int(g["no_structure"]) == 1, a
+        else:
+            tok = c["stdout"].split("\n")[0].split()
+            ref = (tok[8], tok[11], tok[14], tok[17]) if mode == "HAIRPIN" else (tok[7], tok[10], tok[13], tok[16])
+            assert int(g["no_structure"]) == 0, a
+            assert ("%g" % g["ds"], "%g" % g["dh"], "%g" % g["dg"], "%g" % g["tm"]) == ref, (a, g)
+            n_hot += mode != "ANY" and float(ref[3]) > 0
+        n[mode] += 1
+    assert n["ANY"] >= 90 and n["END1"] >= 90 and n["HAIRPIN"] >= 150 and n_hot >= 80, (n, n_hot)

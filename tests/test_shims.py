@@ -33,7 +33,9 @@ def test_ntthal_shim_reproduces_the_reference_test_vectors():
         # the reference's parser reads token 13 (delta_g.rs:33-36)
         assert tok[13] == g["values"]["dG"]
         assert [tok[7], tok[10], tok[13], tok[16]] == [g["values"]["dS"], g["values"]["dH"], g["values"]["dG"], g["values"]["t"]]
-        assert out[1:5] == [tag + "\t" + body for tag, body in g["lines"]]
+        # the Rust source keeps the rows without their trailing blanks; the executable pads the two middle rows
+        assert [l.rstrip(" ") for l in out[1:5]] == [tag + "\t" + body for tag, body in g["lines"]]
+        assert len({len(l) for l in out[1:5]}) == 1
         assert out[5:] == [""]
 
 
@@ -73,20 +75,17 @@ def test_ntthal_shim_through_the_reference_parser_including_structureless_pairs(
     res = eng.thal_pairs(np.repeat(codes, n), np.tile(codes, n), m.THAL_ANY, m.ThalCond(50, 3, 0, 250, 25.0, 30, 0))
     want = []
     for p, (a, b) in enumerate(pairs):
-        if res["no_structure"][p]:
-            want.append("No secondary structure could be calculated")
-        else:
+        if not res["no_structure"][p]:   # a structure-less pair prints NOTHING (tests/golden/ntthal_emulated.json)
             want.append("Calculated thermodynamical parameters for dimer:\tdS = %g\tdH = %g\tdG = %g\tt = %g" % (res["ds"][p], res["dh"][p], res["dg"][p], res["tm"][p]))
     assert int(res["no_structure"].sum()) >= 2
-    got = [l for l in out.split("\n") if l.startswith("Calculated") or l.startswith("No secondary")]
-    assert got == want
-    assert len(out.split("\n")) - 1 == 5 * (len(pairs) - int(res["no_structure"].sum())) + int(res["no_structure"].sum())
+    got = [l for l in out.split("\n") if l.startswith("Calculated")]
+    assert got == want and "No secondary" not in out
+    assert len(out.split("\n")) - 1 == 5 * (len(pairs) - int(res["no_structure"].sum()))
     # drawn duplexes: both strands complete, paired columns complementary
     blocks = out.split("\n")
     i = 0
     for p, (a, b) in enumerate(pairs):
         if res["no_structure"][p]:
-            i += 1
             continue
         r = [x.split("\t", 1)[1] for x in blocks[i + 1:i + 5]]
         i += 5
@@ -200,3 +199,36 @@ def test_reference_host_logic_over_the_shims_equals_the_full_pipeline(zika_fasta
     assert got.csv == want.csv and got.report == want.report
     assert len(got.csv.split("\n")) > 20
     got.close(); want.close()
+
+
+def test_ntthal_shim_equals_the_reference_executable_byte_for_byte():
+    """stdout of the shim against stdout of the reference's own Primer3 2.6.1 ntthal (tests/golden/ntthal_emulated.json:
+    that executable run under tools/a64emu) for every ANY / END1 case the engine accepts (equal lengths up to 32 nt),
+    drawings included, and the reference's `-path .. -i` sessions with their structure-less pairs.  Cases with the same
+    conditions go through one `-i` session: the executable's -i output is the concatenation of its single-pair outputs."""
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "ntthal_emulated.json")))["cases"]
+    sessions, n = {}, 0
+    for c in cases:
+        a = c["args"]
+        if a[1] not in ("ANY", "END1"):
+            continue
+        if "-i" in a:
+            k = a.index("-path")
+            key = tuple(a[:k] + a[k + 2:]) + (str(n),)  # the embedded tables equal the reference's primer3_config/ files
+            sessions[key] = [c["stdin"], c["stdout"]]
+        else:
+            k = a.index("-s1")
+            s1, s2 = a[k + 1], a[k + 3]
+            if len(s1) != len(s2) or len(s1) > 32:
+                continue
+            key = tuple(a[:k]) + ("-i",)
+            ses = sessions.setdefault(key, ["", ""])
+            ses[0] += s1 + "," + s2 + "\n"
+            ses[1] += c["stdout"]
+        n += 1
+    assert n >= 180
+    for key, (stdin, want) in sessions.items():
+        args = list(key) if key[-1] == "-i" else list(key[:-1])
+        r = subprocess.run([os.path.join(SHIMS, "ntthal"), *args], input=stdin, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout == want, (args, stdin, r.stdout, want)
