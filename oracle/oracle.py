@@ -106,6 +106,15 @@ def thal(o1: str, o2: str, ttype: int, cond: ThalCond) -> ThalOut:
     return out
 
 
+def thal_last_pairing(n: int):
+    """Partner (1-based, in the reversed second oligo; 0 = unpaired) of every base of the first oligo in the duplex the most
+    recent dimer `thal` call traced: what ntthal draws."""
+    L = lib()
+    buf = (C.c_int * 64)()
+    L.oracle_thal_last_pairing(buf, 64)
+    return list(buf)[:n]
+
+
 def oligotm(s: str, mv=50.0, dv=1.5, dntp=0.6, dna=50.0) -> float:
     return lib().oracle_oligotm(s.encode(), mv, dv, dntp, dna)
 

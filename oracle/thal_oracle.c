@@ -343,6 +343,7 @@ static void setup_seq(work_t* w, const char* o1, const char* o2, int reverse2) {
   w->n1[0] = w->n1[w->len1 + 1] = w->n2[0] = w->n2[w->len2 + 1] = 4;
 }
 
+static int last_ps1[ORACLE_MAX_LEN];   /* pairing of the last dimer traceback: partner (1-based, in the reversed second oligo) of base i */
 /* type: MSSPE_THAL_ANY or MSSPE_THAL_END1 */
 static void thal_dimer(const char* o1, const char* o2, const msspe_thal_cond* c, int type, msspe_thal_out* out,
                        long* stats) {
@@ -383,6 +384,7 @@ static void thal_dimer(const char* o1, const char* o2, const msspe_thal_cond* c,
   for (int i = 0; i < w->len1; i++) ps1[i] = 0;
   for (int j = 0; j < w->len2; j++) ps2[j] = 0;
   traceback_dimer(w, bestI, bestJ, ps1, ps2);
+  for (int i = 0; i < ORACLE_MAX_LEN; i++) last_ps1[i] = i < w->len1 ? ps1[i] : 0;
   int N = 0;
   for (int i = 0; i < w->len1; i++) if (ps1[i] > 0) ++N;
   for (int j = 0; j < w->len2; j++) if (ps2[j] > 0) ++N;
@@ -772,6 +774,13 @@ int oracle_thal(const char* o1, const char* o2, int type, const msspe_thal_cond*
   else if (type == 3) thal_dimer(o2, o1, c, MSSPE_THAL_END1, out, NULL);  /* thal_end2 = END1 with the oligos exchanged (not on od-msspe's path; kept so the whole ntthal fixture applies) */
   else thal_dimer(o1, o2, c, type, out, NULL);
   return 0;
+}
+
+/* the traced duplex of the most recent oracle_thal dimer call (what ntthal draws), for the drawing tests */
+int oracle_thal_last_pairing(int* ps1, int cap) {
+  int n = cap < ORACLE_MAX_LEN ? cap : ORACLE_MAX_LEN;
+  for (int i = 0; i < n; i++) ps1[i] = last_ps1[i];
+  return n;
 }
 
 int oracle_thal_stats(const char* o1, const char* o2, const msspe_thal_cond* c, long* stats) {

@@ -93,3 +93,55 @@ def test_oracle_equals_the_reference_executable(oracle_lib, cases):
                 assert int(ln) == len(a) and blk[2] == "STR\t" + a
             n += 1
     assert n >= 480
+
+
+def draw_duplex(o1, o2, pairing):
+    """The four rows ntthal draws for a duplex, as host/ntthal_shim.cpp builds them from the traced pairing: unpaired / paired bases
+    of oligo 1, paired / unpaired bases of the reversed oligo 2; blanks before the shorter left end, '-' behind the shorter side of
+    a loop and of the right end, the two middle rows padded to the full width."""
+    r2 = o2[::-1]
+    bp = [(i, pairing[i] - 1) for i in range(len(o1)) if pairing[i]]
+    rows = ["", "", "", ""]
+    i = j = 0
+    for t, (bi, bj) in enumerate(bp):
+        u1, u2 = bi - i, bj - j
+        w = max(u1, u2)
+        if t == 0:
+            rows[0] += " " * (w - u1) + o1[i:bi]
+            rows[3] += " " * (w - u2) + r2[j:bj]
+        else:
+            rows[0] += o1[i:bi] + "-" * (w - u1)
+            rows[3] += r2[j:bj] + "-" * (w - u2)
+        rows[1] += " " * w + o1[bi]
+        rows[2] += " " * w + r2[bj]
+        rows[0] += " "
+        rows[3] += " "
+        i, j = bi + 1, bj + 1
+    t1, t2 = len(o1) - i, len(r2) - j
+    w = max(t1, t2)
+    rows[0] += o1[i:] + "-" * (w - t1)
+    rows[3] += r2[j:] + "-" * (w - t2)
+    rows[1] += " " * w
+    rows[2] += " " * w
+    return rows
+
+
+def test_drawn_duplexes_equal_the_reference_executable(oracle_lib, cases):
+    """The traced duplex (which bases pair) and the drawing rule of the ntthal stand-in against the executable's SEQ / STR rows.
+    One known difference: a self pair has two mirror-image optimal placements; the arm64 build of the reference decides between
+    them in the last bit of a fused multiply-add, the oracle (built without contraction, like the kernels) picks the other one.
+    The numbers are the same and the reference's parser reads line 0 only (delta_g.rs:33-36)."""
+    O = oracle_lib
+    n = mirrored = 0
+    for c in cases:
+        o = parse_args(c["args"])
+        if o["mode"] not in ("ANY", "END1") or o["i"] or not c["stdout"]:
+            continue
+        O.thal(o["s1"], o["s2"], TYPE[o["mode"]], O.ThalCond(o["mv"], o["dv"], o["n"], o["d"], o["t"], o["maxloop"], 0))
+        rows = draw_duplex(o["s1"], o["s2"], O.thal_last_pairing(len(o["s1"])))
+        want = [l.split("\t", 1)[1] for l in c["stdout"].split("\n")[1:5]]
+        n += 1
+        if rows != want:
+            assert o["s1"] == o["s2"], (c["args"], rows, want)
+            mirrored += 1
+    assert n >= 230 and mirrored <= 1
