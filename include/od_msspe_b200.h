@@ -96,7 +96,7 @@ typedef struct {
   double dh;            /* dH, cal/mol */
   double dg;            /* dG at cond.temp_c, cal/mol */
   double tm;            /* melting temperature, Celsius */
-  int32_t no_structure; /* 1 = "No secondary structure could be calculated" */
+  int32_t no_structure; /* 1 = no structure: ntthal prints nothing for such a dimer (a stderr message for a hairpin) */
   int32_t n_bp;         /* paired bases counted by the traceback */
 } msspe_thal_out;
 
