@@ -313,3 +313,26 @@ def test_engine_equals_the_reference_executable(eng):
             n_hot += mode != "ANY" and float(ref[3]) > 0
         n[mode] += 1
     assert n["ANY"] >= 90 and n["END1"] >= 90 and n["HAIRPIN"] >= 150 and n_hot >= 80, (n, n_hot)
+
+
+def test_primer_thermo_equals_the_reference_primer3_core(eng):
+    """msspe_primer_thermo against what the reference's own primer3_core executable prints for PRIMER_TASK=check_primers
+    (tests/golden/primer3_core_emulated.json: that Mach-O arm64 binary run under tools/a64emu): Tm and GC as "%.3f", the three
+    *_TH values as "%.2f", 292 primers of 13 .. 25 nt."""
+    import json
+    import os
+    import msspe_b200 as m
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "primer3_core_emulated.json")) as f:
+        primers = json.load(f)["primers"]
+    by_len = {}
+    for p in primers:
+        by_len.setdefault(len(p["primer"]), []).append(p)
+    n = 0
+    for k, ps in sorted(by_len.items()):
+        r = eng.primer_thermo([m.encode_word(p["primer"]) for p in ps], oligo_len=k)
+        for i, p in enumerate(ps):
+            got = ("%.3f" % r["tm"][i], "%.3f" % r["gc"][i], "%.2f" % r["self_any"][i], "%.2f" % r["self_end"][i], "%.2f" % r["hairpin"][i])
+            assert got == (p["TM"], p["GC_PERCENT"], p["SELF_ANY_TH"], p["SELF_END_TH"], p["HAIRPIN_TH"]), (p["primer"], got)
+            n += 1
+    assert n == 292

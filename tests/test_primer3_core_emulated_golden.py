@@ -1,0 +1,40 @@
+"""`check_primers` against REFERENCE OUTPUT: what the reference's own Primer3 2.6.1 `primer3_core` executable
+(od-msspe/bin/primer3_core, spawned by primer.rs:125-140) prints for the Boulder-IO records of primer.rs:113-127, obtained by
+running that Mach-O arm64 binary under tools/a64emu (tools/gen_primer3_core_emulated_golden.py ->
+tests/golden/primer3_core_emulated.json; the generator first reproduces primer.rs:238-250).  292 primers of 13 .. 25 nt, 142 with
+SELF_ANY_TH > 0, 75 with SELF_END_TH > 0, 138 with HAIRPIN_TH > 0.
+
+It pins which arguments `check_primers` hands to oligotm and thal (50 mM monovalent, 1.5 mM divalent, 0.6 mM dNTP, 50 nM DNA,
+37 C, loops up to 30, the SantaLucia 1998 table with the Owczarzy 2008 salt correction; self-any = thal ANY, self-end = thal END1
+of the primer against itself, negative temperatures printed as 0.00) - read from Primer3's manual in rounds 1-2, observed now."""
+import json
+import os
+
+import pytest
+
+from conftest import GOLDEN
+
+
+@pytest.fixture(scope="module")
+def primers():
+    with open(os.path.join(GOLDEN, "primer3_core_emulated.json")) as f:
+        return json.load(f)["primers"]
+
+
+def test_fixture_shape(primers):
+    assert len(primers) == 292 and primers[0]["primer"] == "AGCCCGTGTAAAC"
+    assert {k: primers[0][k] for k in ("TM", "GC_PERCENT", "SELF_ANY_TH", "SELF_END_TH", "HAIRPIN_TH")} == \
+        {"TM": "43.727", "GC_PERCENT": "53.846", "SELF_ANY_TH": "0.00", "SELF_END_TH": "0.00", "HAIRPIN_TH": "0.00"}  # primer.rs:238-250
+    for k, n in (("SELF_ANY_TH", 140), ("SELF_END_TH", 70), ("HAIRPIN_TH", 130)):
+        assert sum(1 for p in primers if float(p[k]) > 0) >= n
+
+
+def test_oracle_equals_the_reference_executable(oracle_lib, primers):
+    O = oracle_lib
+    c = O.ThalCond(50, 1.5, 0.6, 50, 37.0, 30, 0)
+    for p in primers:
+        w = p["primer"]
+        got = {"TM": "%.3f" % O.oligotm(w), "GC_PERCENT": "%.3f" % O.gc_percent(w)}
+        for key, ttype in (("SELF_ANY_TH", 1), ("SELF_END_TH", 2), ("HAIRPIN_TH", 4)):
+            got[key] = "%.2f" % max(0.0, O.thal(w, w, ttype, c).tm)
+        assert got == {k: p[k] for k in got}, w

@@ -32,14 +32,16 @@ class Exit(Exception):
 
 
 class Process:
-    def __init__(self, path=NTTHAL, file_root=None):
+    def __init__(self, path=NTTHAL, file_root=None, mem_size=MEM_SIZE):
         self.im = im = Image(path)
         self.base = im.base
-        self.mem = bytearray(MEM_SIZE)
+        self.mem_size = mem_size
+        self.mem = bytearray(mem_size)
         binds = im.map_into(self.mem, self.base)
         self.cpu = cpu = CPU(self.mem, self.base)
-        self.heap = self.base + 0x100000
-        self.heap_end = self.base + MEM_SIZE - (4 << 20)
+        image_end = max(v + sz for _n, v, sz, _fo, _fs in im.segments if _n != "__PAGEZERO") - self.base
+        self.heap = self.base + ((image_end + 0xFFFFF) & ~0xFFFFF)
+        self.heap_end = self.base + mem_size - (4 << 20)
         self.sizes = {}
         self.out = {1: bytearray(), 2: bytearray()}
         self.stdin = b""
@@ -48,7 +50,8 @@ class Process:
         self.file_root = file_root
         self.calls = {}
         data = {"___stack_chk_guard": self._cell(0x5AFE5AFE5AFE5AFE), "___stdinp": self._cell(0x10),
-                "___stdoutp": self._cell(0x11), "___stderrp": self._cell(0x12), "__DefaultRuneLocale": self._rune_locale()}
+                "___stdoutp": self._cell(0x11), "___stderrp": self._cell(0x12), "__DefaultRuneLocale": self._rune_locale(),
+                "_optarg": self._cell(0), "_opterr": self._cell(0), "_optind": self._cell(1)}
         for i, (addr, name, addend) in enumerate(binds):
             if name in data:
                 cpu.wr(addr, 8, data[name] + addend)
@@ -121,7 +124,7 @@ class Process:
 
     def _put(self, addr, data):
         o = addr - self.base
-        if o < 0 or o + len(data) > MEM_SIZE:
+        if o < 0 or o + len(data) > self.mem_size:
             raise MemoryError("write %#x" % addr)
         self.mem[o: o + len(data)] = data
 
@@ -442,6 +445,162 @@ class Process:
         self.cpu.v[0] = d2b(val)
         return None
 
+    # ---- the further imports primer3_core binds
+    def imp___chkstk_darwin(self):
+        return None
+
+    def imp__Znwm(self):
+        return self.alloc(self.cpu.x[0])
+
+    def imp__ZdlPv(self):
+        return None
+
+    def imp__ZNSt3__112__next_primeEm(self):
+        n = max(self.cpu.x[0], 2)
+        while any(n % d == 0 for d in range(2, int(n ** 0.5) + 1)):
+            n += 1
+        return n
+
+    def _cxx_runtime(self):
+        raise Halt("C++ exception machinery reached")
+
+    imp__Unwind_Resume = imp___cxa_allocate_exception = imp___cxa_throw = imp___gxx_personality_v0 = _cxx_runtime
+    imp__ZNSt20bad_array_new_lengthC1Ev = imp__ZNSt20bad_array_new_lengthD1Ev = imp__ZTISt20bad_array_new_length = _cxx_runtime
+
+    def imp_memcpy(self):
+        x = self.cpu.x
+        self._put(x[0], self._bytes(x[1], x[2]))
+        return x[0]
+
+    imp_memmove = imp___memcpy_chk = imp_memcpy
+
+    def imp___strcpy_chk(self):
+        return self.imp_strcpy()
+
+    def imp_memchr(self):
+        x = self.cpu.x
+        i = self._bytes(x[0], x[2]).find(bytes([x[1] & 0xFF]))
+        return x[0] + i if i >= 0 else 0
+
+    def imp_abort(self):
+        raise Halt("abort(): " + self.out[2].decode(errors="replace"))
+
+    def imp_perror(self):
+        self.out[2] += self.cpu.cstr(self.cpu.x[0]) + b": error\n"
+        return None
+
+    def _no_file(self):
+        return 0xFFFFFFFFFFFFFFFF
+
+    imp_access = imp_stat = imp_open = imp_mmap = _no_file
+
+    def imp_close(self):
+        return 0
+
+    imp_munmap = imp_signal = imp_fseek = imp_ftell = imp_close
+
+    def imp_freopen(self):
+        return 0
+
+    def _math1(self, fn):
+        try:
+            r = fn(b2d(self.cpu.v[0]))
+        except (ValueError, OverflowError):
+            r = math.nan
+        self.cpu.v[0] = d2b(r)
+
+    def imp_exp(self):
+        a = b2d(self.cpu.v[0])
+        try:
+            r = math.exp(a)
+        except OverflowError:
+            r = math.inf
+        self.cpu.v[0] = d2b(r)
+        return None
+
+    def imp_log10(self):
+        a = b2d(self.cpu.v[0])
+        self.cpu.v[0] = d2b(math.log10(a) if a > 0 else (-math.inf if a == 0 else math.nan))
+        return None
+
+    def imp_pow(self):
+        try:
+            r = math.pow(b2d(self.cpu.v[0]), b2d(self.cpu.v[1]))
+        except (ValueError, OverflowError, ZeroDivisionError):
+            r = math.nan
+        self.cpu.v[0] = d2b(r)
+        return None
+
+    def imp_fputc(self):
+        x = self.cpu.x
+        self._write(x[1], bytes([x[0] & 0xFF]))
+        return x[0] & 0xFF
+
+    def imp_fwrite(self):
+        x = self.cpu.x
+        self._write(x[3], self._bytes(x[0], x[1] * x[2]))
+        return x[2]
+
+    def imp_getline(self):
+        x = self.cpu.x
+        lineptr, nptr, h = x[0], x[1], x[2]
+        if h != 0x10:
+            raise IOError("getline on FILE* %#x" % h)
+        if self.stdin_pos >= len(self.stdin):
+            self.stdin_eof = True
+            return 0xFFFFFFFFFFFFFFFF
+        e = self.stdin.find(b"\n", self.stdin_pos)
+        e = len(self.stdin) if e < 0 else e + 1
+        line = self.stdin[self.stdin_pos:e]
+        self.stdin_pos = e
+        buf, cap = self.cpu.rd(lineptr, 8), self.cpu.rd(nptr, 8)
+        if not buf or cap < len(line) + 1:
+            cap = max(len(line) + 1, 128)
+            buf = self.alloc(cap)
+            self.cpu.wr(lineptr, 8, buf)
+            self.cpu.wr(nptr, 8, cap)
+        self._put(buf, line + b"\0")
+        return len(line)
+
+    def imp_getopt_long_only(self):
+        return 0xFFFFFFFF          # no options: the reference starts primer3_core without arguments (primer.rs:125-131)
+
+    def imp_qsort(self):
+        """qsort(base, nel, width, compar) with the comparison function in emulated code."""
+        import functools
+        x = self.cpu.x
+        base, nel, width, compar = x[0], x[1], x[2], x[3]
+        saved = (x[30], x[31])
+        items = [self._bytes(base + i * width, width) for i in range(nel)]
+        ta, tb = self.alloc(width), self.alloc(width)
+
+        def cmp(a, b):
+            self._put(ta, a)
+            self._put(tb, b)
+            x[0], x[1], x[30] = ta, tb, STOP
+            self.cpu.run(compar, STOP)
+            return sx(x[0], 32)
+        items.sort(key=functools.cmp_to_key(cmp))
+        for i, it in enumerate(items):
+            self._put(base + i * width, it)
+        x[30], x[31] = saved
+        return None
+
+    def imp_strncat(self):
+        x = self.cpu.x
+        d = self.cpu.cstr(x[0])
+        self._put(x[0] + len(d), self.cpu.cstr(x[1])[: x[2]] + b"\0")
+        return x[0]
+
+    def imp_strtol(self):
+        x = self.cpu.x
+        s = self.cpu.cstr(x[0])
+        m = re.match(rb"[ \t\n\v\f\r]*([-+]?\d+)", s)
+        val, end = (int(m.group(1)), m.end()) if m else (0, 0)
+        if x[1]:
+            self.cpu.wr(x[1], 8, x[0] + end)
+        return val & M64
+
     # ---- entry
     def run_main(self, argv, stdin=b"", limit=None):
         cpu = self.cpu
@@ -454,7 +613,7 @@ class Process:
         av = self.alloc(8 * (len(ptrs) + 1))
         for i, p in enumerate(ptrs):
             cpu.wr(av + 8 * i, 8, p)
-        sp = self.base + MEM_SIZE - 0x10000
+        sp = self.base + self.mem_size - 0x10000
         cpu.x[:] = [0] * 32
         cpu.x[0], cpu.x[1], cpu.x[30], cpu.x[31] = len(argv), av, STOP, sp
         code = None
@@ -464,6 +623,14 @@ class Process:
         except Exit as e:
             code = e.code
         return self.out[1].decode(), self.out[2].decode(), code
+
+
+def run_primer3_core(stdin, limit=None):
+    """Run `primer3_core` as primer.rs:125-140 does: no arguments, Boulder-IO records on stdin; returns (stdout, stderr, exit
+    code, instructions executed)."""
+    p = Process(path="/root/reference/od-msspe/bin/primer3_core", mem_size=160 << 20)
+    out, err, code = p.run_main(["primer3_core"], stdin, limit)
+    return out, err, code, p.cpu.icount
 
 
 def run_ntthal(args, stdin=b"", file_root=None, limit=None):
