@@ -20,8 +20,12 @@
  * tri- and tetraloop bonus tables) are bit-identical to the arrays compiled into the reference's own Primer3 2.6.1
  * executables, read out of their Mach-O data by symbol name (oracle_thal_table below,
  * tests/golden/primer3_2_6_1_compiled_in_tables.json).
- * PARITY UNPINNED (no golden vector exists in the reference): hairpin Tm > 0, END1 Tm > 0, bulge loops,
- * the single-line "No secondary structure" output.
+ * And to REFERENCE OUTPUT: stdout of those executables themselves, interpreted instruction by instruction under
+ * tools/a64emu: 526 ntthal invocations over ANY / END1 / END2 / HAIRPIN (tests/golden/ntthal_emulated.json,
+ * tests/test_ntthal_emulated_golden.py) and 292 primer3_core check_primers records (tests/golden/
+ * primer3_core_emulated.json, tests/test_primer3_core_emulated_golden.py), all equal as printed.  That pin replaced
+ * the hairpin-closing test of older Primer3 releases (melting temperatures) with 2.6.1's (free energies with the
+ * right-end term, calc_hairpin below), and showed that ntthal prints nothing for a structure-less dimer.
  *
  * Build: gcc -O2 -ffp-contract=off (no FMA contraction, so the CUDA kernels compiled with -fmad=false
  * can be compared bit-for-bit).
@@ -399,8 +403,9 @@ static void thal_dimer(const char* o1, const char* o2, const msspe_thal_cond* c,
 }
 
 /* ------------------------------------------------------------------------------------------------
- * Hairpin (monomer) -- PARITY UNPINNED: restated from the published structure of
- * Primer3's unimolecular thermodynamic alignment; no golden vector with Tm > 0 exists in the reference.
+ * Hairpin (monomer): restated from the published structure of Primer3's unimolecular thermodynamic alignment and
+ * pinned to 160 HAIRPIN outputs of the reference's ntthal executable and 292 HAIRPIN_TH values of its primer3_core
+ * (tools/a64emu; see the header).
  * ------------------------------------------------------------------------------------------------ */
 static double Ss2(const work_t* w, int i, int j) {
   if (i >= j) return -1.0;

@@ -51,7 +51,8 @@ def test_order_matters_and_param_dir_equals_embedded(oracle_lib, tmp_path):
 
 
 def test_hairpin_forms_for_a_clear_stem_loop(oracle_lib):
-    """Parity unpinned (no reference vector): sanity only -- a GC-rich 6 bp stem must melt far above 24 C."""
+    """A GC-rich 6 bp stem melts far above 24 C; the value itself is the reference executable's (tests/golden/ntthal_emulated.json
+    holds this very oligo under other conditions; tests/test_ntthal_emulated_golden.py compares all 160 hairpins)."""
     O = oracle_lib
     c = O.ThalCond(50, 1.5, 0.6, 50, 37.0, 30, 0)
     o = O.thal("GCGCGCTTTTGCGCGC", "", 4, c)

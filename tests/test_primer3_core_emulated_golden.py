@@ -38,3 +38,11 @@ def test_oracle_equals_the_reference_executable(oracle_lib, primers):
         for key, ttype in (("SELF_ANY_TH", 1), ("SELF_END_TH", 2), ("HAIRPIN_TH", 4)):
             got[key] = "%.2f" % max(0.0, O.thal(w, w, ttype, c).tm)
         assert got == {k: p[k] for k in got}, w
+
+
+def test_penalty_line_of_the_stand_in_follows_the_executable(oracle_lib, primers):
+    """host/primer3_core_shim.cpp prints PRIMER_LEFT_0_PENALTY = |Tm - PRIMER_OPT_TM| + |size - PRIMER_OPT_SIZE| (weights 1, 1,
+    everything else 0 for this task); od-msspe does not read the tag, the executable's value confirms the formula anyway."""
+    for p in primers:
+        w = p["primer"]
+        assert "%f" % (abs(oracle_lib.oligotm(w) - 60.0) + abs(len(w) - 20.0)) == p["PENALTY"], w
