@@ -359,11 +359,22 @@ class Process:
         self.cpu.v[0] = d2b(r)
         return None
 
-    def imp_longjmp(self):
-        raise Halt("longjmp (thal error path): " + self.out[2].decode(errors="replace"))
-
     def imp_setjmp(self):
+        """The callee-saved state, keyed by the jmp_buf address (the buffer itself is not written)."""
+        c = self.cpu
+        self.jmp = getattr(self, "jmp", {})
+        self.jmp[c.x[0]] = (list(c.x[19:32]), list(c.v[8:16]))
         return 0
+
+    def imp_longjmp(self):
+        c = self.cpu
+        st = getattr(self, "jmp", {}).get(c.x[0])
+        if st is None:
+            raise Halt("longjmp without setjmp: " + self.out[2].decode(errors="replace"))
+        val = c.x[1] & 0xFFFFFFFF
+        c.x[19:32] = st[0]
+        c.v[8:16] = st[1]
+        return val or 1          # resumes at the saved x30: the hook dispatcher continues at x[30]
 
     def imp_memset(self):
         x = self.cpu.x
