@@ -100,7 +100,7 @@ def test_ntthal_shim_through_the_reference_parser_including_structureless_pairs(
                 assert {r[1][c], r[2][c]} in ({"A", "T"}, {"C", "G"})
                 npair += 1
         assert npair == int(res["n_bp"][p])
-    # the reference parser over the whole stream equals the host-side index arithmetic of the CLI (5-line desync)
+    # the reference parser over the whole stream runs over the stand-in's stream (blocks only: a structure-less pair prints nothing)
     inp = "".join(a + "," + b + "\n" for a, b in pairs)
     edges = parse_ntthal_output(inp, out, -3000.0)
     assert len(edges) > 0
