@@ -22,7 +22,7 @@
  * tests/golden/primer3_2_6_1_compiled_in_tables.json).
  * And to REFERENCE OUTPUT: stdout of those executables themselves, interpreted instruction by instruction under
  * tools/a64emu: 526 ntthal invocations over ANY / END1 / END2 / HAIRPIN (tests/golden/ntthal_emulated.json,
- * tests/test_ntthal_emulated_golden.py) and 292 primer3_core check_primers records (tests/golden/
+ * tests/test_ntthal_emulated_golden.py) and 337 primer3_core check_primers records (tests/golden/
  * primer3_core_emulated.json, tests/test_primer3_core_emulated_golden.py), all equal as printed.  That pin replaced
  * the hairpin-closing test of older Primer3 releases (melting temperatures) with 2.6.1's (free energies with the
  * right-end term, calc_hairpin below), and showed that ntthal prints nothing for a structure-less dimer.
@@ -404,7 +404,7 @@ static void thal_dimer(const char* o1, const char* o2, const msspe_thal_cond* c,
 
 /* ------------------------------------------------------------------------------------------------
  * Hairpin (monomer): restated from the published structure of Primer3's unimolecular thermodynamic alignment and
- * pinned to 160 HAIRPIN outputs of the reference's ntthal executable and 292 HAIRPIN_TH values of its primer3_core
+ * pinned to 160 HAIRPIN outputs of the reference's ntthal executable and 337 HAIRPIN_TH values of its primer3_core
  * (tools/a64emu; see the header).
  * ------------------------------------------------------------------------------------------------ */
 static double Ss2(const work_t* w, int i, int j) {

@@ -318,7 +318,7 @@ def test_engine_equals_the_reference_executable(eng):
 def test_primer_thermo_equals_the_reference_primer3_core(eng):
     """msspe_primer_thermo against what the reference's own primer3_core executable prints for PRIMER_TASK=check_primers
     (tests/golden/primer3_core_emulated.json: that Mach-O arm64 binary run under tools/a64emu): Tm and GC as "%.3f", the three
-    *_TH values as "%.2f", 292 primers of 13 .. 25 nt."""
+    *_TH values as "%.2f", 337 primers of 8 .. 32 nt."""
     import json
     import os
     import msspe_b200 as m
@@ -335,4 +335,4 @@ def test_primer_thermo_equals_the_reference_primer3_core(eng):
             got = ("%.3f" % r["tm"][i], "%.3f" % r["gc"][i], "%.2f" % r["self_any"][i], "%.2f" % r["self_end"][i], "%.2f" % r["hairpin"][i])
             assert got == (p["TM"], p["GC_PERCENT"], p["SELF_ANY_TH"], p["SELF_END_TH"], p["HAIRPIN_TH"]), (p["primer"], got)
             n += 1
-    assert n == 292
+    assert n == 337

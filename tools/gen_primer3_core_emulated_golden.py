@@ -58,6 +58,15 @@ def primers():
         if 13 <= len(s) <= 25:
             out.append(s)
     out += ["ACACACACACACA", "AAAAAAAAAAAAA", "GGGGGGGGGGGGG", "ATATATATATATA", "GCGCGCGCGCGCG"]   # low complexity
+    # outside PRIMER_MIN_SIZE=13 .. PRIMER_MAX_SIZE=27: with PRIMER_PICK_ANYWAY=1 the executable warns ("Too short" / "Too long")
+    # and still reports every number, so od-msspe --kmer-size 8 .. 12 and 28 .. 32 get values too
+    out += [rnd(r, k) for k in (8, 9, 10, 11, 12, 26, 28, 30, 32) for _ in range(4)]
+    for k in (28, 30, 32):
+        for _ in range(3):
+            stem = rnd(r, r.randrange(4, 8))
+            loop = rnd(r, r.randrange(3, 9))
+            core = stem + loop + rc(stem)
+            out.append((rnd(r, k - len(core)) + core)[:k] if len(core) < k else core[:k])
     seen, uniq = set(), []
     for p in out:
         if p not in seen:
