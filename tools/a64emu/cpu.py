@@ -978,7 +978,7 @@ def decode_fp(cpu, w, pc):
                     imm64 |= 0xFF << (8 * i)
         elif cmode == 14 and op == 0:                # MOVI 8-bit
             imm64 = int.from_bytes(bytes([imm8]) * 8, "little")
-        elif cmode & 9 == 0 or (cmode & 9 == 1 and False):   # 32-bit shifted
+        elif cmode & 9 == 0:                         # 32-bit shifted (MOVI / MVNI)
             e = imm8 << (8 * (cmode >> 1))
             if op:
                 e = (~e) & M32
