@@ -62,6 +62,8 @@ CASES = [
     ("zika24", dict()),
     ("zika24", dict(delta_g_threshold=-6000.0)),
     ("zika24", dict(check_self_dimers=0)),
+    ("zika24", dict(mv_conc=40.0, dv_conc=1.5, dntp_conc=0.2, dna_conc=100.0, annealing_temp=37.0, delta_g_threshold=-5000.0)),
+    ("zika24", dict(kmer_size=15, max_iterations=40, disable_tm_stddev=1, disable_min_max_tm=1, check_hairpin=0)),
 ]
 
 
