@@ -336,3 +336,28 @@ def test_primer_thermo_equals_the_reference_primer3_core(eng):
             assert got == (p["TM"], p["GC_PERCENT"], p["SELF_ANY_TH"], p["SELF_END_TH"], p["HAIRPIN_TH"]), (p["primer"], got)
             n += 1
     assert n == 337
+
+
+@pytest.mark.parametrize("kernel", [None, "thread", "flat", "legacy"])
+def test_batched_13mer_pairs_equal_the_reference_executable(eng, monkeypatch, kernel):
+    """One batch of 2000 ordered 13-mer pairs (what the thread-per-pair kernel is chosen for) against the reference's own ntthal
+    run as delta_g.rs:93-110 runs it (tests/golden/ntthal_emulated_13mer_pairs.json): dS, dH, dG, t as printed, and the same
+    pairs silent."""
+    import json
+    import os
+    import msspe_b200 as m
+    from conftest import GOLDEN
+    if kernel:
+        monkeypatch.setenv("MSSPE_THAL_KERNEL", kernel)
+    else:
+        monkeypatch.delenv("MSSPE_THAL_KERNEL", raising=False)
+    with open(os.path.join(GOLDEN, "ntthal_emulated_13mer_pairs.json")) as f:
+        rows = json.load(f)["pairs"]
+    got = eng.thal_pairs([m.encode_word(r[0]) for r in rows], [m.encode_word(r[1]) for r in rows], m.THAL_ANY,
+                         m.ThalCond(50, 3, 0, 250, 25.0, 30, 0), oligo_len=13)
+    assert len(got) == 2000
+    for g, (a, b, ds, dh, dg, t) in zip(got, rows):
+        if ds is None:
+            assert int(g["no_structure"]) == 1, (a, b)
+        else:
+            assert int(g["no_structure"]) == 0 and ("%g" % g["ds"], "%g" % g["dh"], "%g" % g["dg"], "%g" % g["tm"]) == (ds, dh, dg, t), (a, b)

@@ -145,3 +145,20 @@ def test_drawn_duplexes_equal_the_reference_executable(oracle_lib, cases):
             assert o["s1"] == o["s2"], (c["args"], rows, want)
             mirrored += 1
     assert n >= 230 and mirrored <= 1
+
+
+def test_oracle_equals_the_reference_executable_on_2000_13mer_pairs(oracle_lib):
+    """Hot loop #2 at od-msspe's own shape (tests/golden/ntthal_emulated_13mer_pairs.json, tools/gen_ntthal_13mer_pairs_golden.py):
+    2000 ordered 13-mer pairs through the reference's ntthal exactly as delta_g.rs:93-110 runs it; line 0 of every block as
+    printed, null where the executable printed nothing."""
+    O = oracle_lib
+    with open(os.path.join(GOLDEN, "ntthal_emulated_13mer_pairs.json")) as f:
+        rows = json.load(f)["pairs"]
+    c = O.ThalCond(50, 3, 0, 250, 25.0, 30, 0)
+    assert len(rows) == 2000 and sum(1 for r in rows if r[2] is None) >= 50
+    for a, b, ds, dh, dg, t in rows:
+        r = O.thal(a, b, 1, c)
+        if ds is None:
+            assert r.no_structure == 1, (a, b)
+        else:
+            assert r.no_structure == 0 and ("%g" % r.ds, "%g" % r.dh, "%g" % r.dg, "%g" % r.tm) == (ds, dh, dg, t), (a, b)
