@@ -313,51 +313,3 @@ def test_engine_equals_the_reference_executable(eng):
             n_hot += mode != "ANY" and float(ref[3]) > 0
         n[mode] += 1
     assert n["ANY"] >= 90 and n["END1"] >= 90 and n["HAIRPIN"] >= 150 and n_hot >= 80, (n, n_hot)
-
-
-def test_primer_thermo_equals_the_reference_primer3_core(eng):
-    """msspe_primer_thermo against what the reference's own primer3_core executable prints for PRIMER_TASK=check_primers
-    (tests/golden/primer3_core_emulated.json: that Mach-O arm64 binary run under tools/a64emu): Tm and GC as "%.3f", the three
-    *_TH values as "%.2f", 337 primers of 8 .. 32 nt."""
-    import json
-    import os
-    import msspe_b200 as m
-    from conftest import GOLDEN
-    with open(os.path.join(GOLDEN, "primer3_core_emulated.json")) as f:
-        primers = json.load(f)["primers"]
-    by_len = {}
-    for p in primers:
-        by_len.setdefault(len(p["primer"]), []).append(p)
-    n = 0
-    for k, ps in sorted(by_len.items()):
-        r = eng.primer_thermo([m.encode_word(p["primer"]) for p in ps], oligo_len=k)
-        for i, p in enumerate(ps):
-            got = ("%.3f" % r["tm"][i], "%.3f" % r["gc"][i], "%.2f" % r["self_any"][i], "%.2f" % r["self_end"][i], "%.2f" % r["hairpin"][i])
-            assert got == (p["TM"], p["GC_PERCENT"], p["SELF_ANY_TH"], p["SELF_END_TH"], p["HAIRPIN_TH"]), (p["primer"], got)
-            n += 1
-    assert n == 337
-
-
-@pytest.mark.parametrize("kernel", [None, "thread", "flat", "legacy"])
-def test_batched_13mer_pairs_equal_the_reference_executable(eng, monkeypatch, kernel):
-    """One batch of 2000 ordered 13-mer pairs (what the thread-per-pair kernel is chosen for) against the reference's own ntthal
-    run as delta_g.rs:93-110 runs it (tests/golden/ntthal_emulated_13mer_pairs.json): dS, dH, dG, t as printed, and the same
-    pairs silent."""
-    import json
-    import os
-    import msspe_b200 as m
-    from conftest import GOLDEN
-    if kernel:
-        monkeypatch.setenv("MSSPE_THAL_KERNEL", kernel)
-    else:
-        monkeypatch.delenv("MSSPE_THAL_KERNEL", raising=False)
-    with open(os.path.join(GOLDEN, "ntthal_emulated_13mer_pairs.json")) as f:
-        rows = json.load(f)["pairs"]
-    got = eng.thal_pairs([m.encode_word(r[0]) for r in rows], [m.encode_word(r[1]) for r in rows], m.THAL_ANY,
-                         m.ThalCond(50, 3, 0, 250, 25.0, 30, 0), oligo_len=13)
-    assert len(got) == 2000
-    for g, (a, b, ds, dh, dg, t) in zip(got, rows):
-        if ds is None:
-            assert int(g["no_structure"]) == 1, (a, b)
-        else:
-            assert int(g["no_structure"]) == 0 and ("%g" % g["ds"], "%g" % g["dh"], "%g" % g["dg"], "%g" % g["tm"]) == (ds, dh, dg, t), (a, b)

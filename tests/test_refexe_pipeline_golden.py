@@ -5,7 +5,8 @@ reference's parsers (primer.rs:67-111, delta_g.rs:27-59).  Two small inputs (a s
 windows, whose primers have no structure with themselves; 24 records x 3 kb of the reference's Zika alignment) x flag sets
 (thresholds, self-dimer pairs left out, non-default salts - which reach ntthal only -, k = 15 without the hairpin filter).
 
-CPU: the in-process oracle arithmetic gives the same CSV and report.  GPU: so does the od-msspe CLI on the CUDA engine."""
+CPU: the in-process oracle arithmetic gives the same CSV and report.  GPU (tests/test_zz_reference_executables_gpu.py): so does the
+od-msspe CLI on the CUDA engine."""
 import gzip
 import json
 import os
@@ -51,22 +52,3 @@ def test_in_process_oracle_equals_the_pipeline_over_the_reference_executables(or
     assert r.csv == c["csv"] and r.report == c["report"]
     assert [len(x) for x in r.candidates] == c["n_candidates"] and [len(x) for x in r.filtered] == c["n_filtered"]
     r.close()
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("i", range(7))
-def test_cli_equals_the_pipeline_over_the_reference_executables(tmp_path, i):
-    c = _cases()[i]
-    fa = tmp_path / "in.fa"
-    fa.write_bytes(_input(c["input"]))
-    out = tmp_path / "o.csv"
-    flags = []
-    for k, v in c["config"].items():
-        if k in BOOLS:
-            v = "true" if v else "false"
-        elif isinstance(v, float):
-            v = "%g" % v
-        flags.append("%s=%s" % (FLAG[k], v))
-    r = subprocess.run([EXE, "-i", str(fa), "-o", str(out), "--do-align=false", *flags], capture_output=True, text=True, cwd=str(tmp_path))
-    assert r.returncode == 0, r.stderr
-    assert out.read_text() == c["csv"] and r.stdout == c["report"]

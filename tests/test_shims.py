@@ -199,55 +199,3 @@ def test_reference_host_logic_over_the_shims_equals_the_full_pipeline(zika_fasta
     assert got.csv == want.csv and got.report == want.report
     assert len(got.csv.split("\n")) > 20
     got.close(); want.close()
-
-
-def test_ntthal_shim_equals_the_reference_executable_byte_for_byte():
-    """stdout of the shim against stdout of the reference's own Primer3 2.6.1 ntthal (tests/golden/ntthal_emulated.json:
-    that executable run under tools/a64emu) for every ANY / END1 case the engine accepts (equal lengths up to 32 nt),
-    drawings included, and the reference's `-path .. -i` sessions with their structure-less pairs.  Cases with the same
-    conditions go through one `-i` session: the executable's -i output is the concatenation of its single-pair outputs."""
-    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "ntthal_emulated.json")))["cases"]
-    sessions, n = {}, 0
-    for c in cases:
-        a = c["args"]
-        if a[1] not in ("ANY", "END1"):
-            continue
-        if "-i" in a:
-            k = a.index("-path")
-            key = tuple(a[:k] + a[k + 2:]) + (str(n),)  # the embedded tables equal the reference's primer3_config/ files
-            sessions[key] = [c["stdin"], c["stdout"]]
-        else:
-            k = a.index("-s1")
-            s1, s2 = a[k + 1], a[k + 3]
-            if len(s1) != len(s2) or len(s1) > 32:
-                continue
-            key = tuple(a[:k]) + ("-i",)
-            ses = sessions.setdefault(key, ["", ""])
-            ses[0] += s1 + "," + s2 + "\n"
-            ses[1] += c["stdout"]
-        n += 1
-    assert n >= 180
-    mirrored = singles = 0
-    for key, (stdin, want) in sessions.items():
-        if stdin.count("\n") == 1:           # one process (one CUDA context) per random-salt case: a dozen of them is enough here,
-            singles += 1                     # test_gpu_thermo.py::test_engine_equals_the_reference_executable has all their numbers
-            if singles > 12:
-                continue
-        args = list(key) if key[-1] == "-i" else list(key[:-1])
-        r = subprocess.run([os.path.join(SHIMS, "ntthal"), *args], input=stdin, capture_output=True, text=True, timeout=300)
-        assert r.returncode == 0, r.stderr
-        if r.stdout == want:
-            continue
-        # A self pair has two mirror-image optimal placements with the same dS/dH/dG/t; which one wins is decided in the last
-        # bit of a free-energy comparison that the arm64 build of the reference fuses into a multiply-add (fmsub) and this
-        # engine does not.  Only the drawing differs (the reference's parser reads line 0 alone, delta_g.rs:33-36).
-        got_l, want_l = r.stdout.split("\n"), want.split("\n")
-        assert len(got_l) == len(want_l), (args, stdin, r.stdout, want)
-        for b in range(0, len(want_l) - 1, 5):
-            if got_l[b:b + 5] == want_l[b:b + 5]:
-                continue
-            assert got_l[b] == want_l[b], (args, got_l[b:b + 5], want_l[b:b + 5])
-            pairs_with_this_header = [p for p in (l.split(",") for l in stdin.split("\n") if l) if p[0] == p[1]]
-            assert pairs_with_this_header, (args, got_l[b:b + 5], want_l[b:b + 5])
-            mirrored += 1
-    assert mirrored <= 2
