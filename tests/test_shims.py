@@ -197,5 +197,5 @@ def test_reference_host_logic_over_the_shims_equals_the_full_pipeline(zika_fasta
     monkeypatch.setenv("ORACLE_NTTHAL", os.path.join(SHIMS, "ntthal"))
     got = oracle_lib.run_pipeline(zika_fasta, oracle_lib.default_config(**okw))
     assert got.csv == want.csv and got.report == want.report
-    assert len(got.csv.split("\n")) > 20
+    assert len(got.csv.split("\n")) > 5      # header + primers: the strict thresholds leave 6 primers on this input
     got.close(); want.close()
