@@ -128,9 +128,10 @@ def draw_duplex(o1, o2, pairing):
 
 def test_drawn_duplexes_equal_the_reference_executable(oracle_lib, cases):
     """The traced duplex (which bases pair) and the drawing rule of the ntthal stand-in against the executable's SEQ / STR rows.
-    One known difference: a self pair has two mirror-image optimal placements; the arm64 build of the reference decides between
-    them in the last bit of a fused multiply-add, the oracle (built without contraction, like the kernels) picks the other one.
-    The numbers are the same and the reference's parser reads line 0 only (delta_g.rs:33-36)."""
+    One known difference: a self pair has two mirror-image optimal placements.  Primer3 2.6.1 finds their free energies bit-equal
+    and keeps the first in scan order; the oracle (and the kernels, bit-identical to it) still add the 1e-6 "SMALL_NON_ZERO" offsets of
+    older releases before that comparison, and rounding may then prefer the twin (dropping the offsets gives
+    236 of 236).  The numbers are the same and the reference's parser reads line 0 only (delta_g.rs:33-36)."""
     O = oracle_lib
     n = mirrored = 0
     for c in cases:
