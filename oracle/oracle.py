@@ -108,7 +108,8 @@ def thal(o1: str, o2: str, ttype: int, cond: ThalCond) -> ThalOut:
 
 def thal_last_pairing(n: int):
     """Partner (1-based, in the reversed second oligo; 0 = unpaired) of every base of the first oligo in the duplex the most
-    recent dimer `thal` call traced: what ntthal draws."""
+    recent dimer `thal` call traced; after a HAIRPIN call, the partner position (1-based, same oligo) in the traced fold: what
+    ntthal draws."""
     L = lib()
     buf = (C.c_int * 64)()
     L.oracle_thal_last_pairing(buf, 64)

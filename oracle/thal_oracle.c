@@ -676,6 +676,7 @@ static void thal_hairpin(const char* o1, const msspe_thal_cond* c, msspe_thal_ou
   int bpv[ORACLE_MAX_LEN + 2];
   for (int k = 0; k < w->len1; ++k) bpv[k] = 0;
   traceback_mono(w, bpv);
+  for (int k = 0; k < ORACLE_MAX_LEN; ++k) last_ps1[k] = k < w->len1 ? bpv[k] : 0;   /* oracle_thal_last_pairing: partner position, 1-based */
   int N = 0;
   for (int i = 1; i < w->len1; ++i) if (bpv[i - 1] > 0) N++;
   out->n_bp = N / 2;
@@ -781,7 +782,8 @@ int oracle_thal(const char* o1, const char* o2, int type, const msspe_thal_cond*
   return 0;
 }
 
-/* the traced duplex of the most recent oracle_thal dimer call (what ntthal draws), for the drawing tests */
+/* the traced duplex of the most recent oracle_thal dimer call, or the traced fold of the most recent hairpin call (partner position
+ * within the same oligo), i.e. what ntthal draws; for the drawing tests */
 int oracle_thal_last_pairing(int* ps1, int cap) {
   int n = cap < ORACLE_MAX_LEN ? cap : ORACLE_MAX_LEN;
   for (int i = 0; i < n; i++) ps1[i] = last_ps1[i];

@@ -163,3 +163,21 @@ def test_oracle_equals_the_reference_executable_on_2000_13mer_pairs(oracle_lib):
             assert r.no_structure == 1, (a, b)
         else:
             assert r.no_structure == 0 and ("%g" % r.ds, "%g" % r.dh, "%g" % r.dg, "%g" % r.tm) == (ds, dh, dg, t), (a, b)
+
+
+def test_traced_hairpin_folds_equal_the_reference_executable(oracle_lib, cases):
+    """Which bases pair in the reported fold: ntthal draws '/' for a base paired downstream, a backslash for one paired upstream, '-'
+    otherwise (the SEQ row of HAIRPIN mode).  The oracle's traceback against all structured hairpins of the fixture."""
+    O = oracle_lib
+    n = 0
+    for c in cases:
+        o = parse_args(c["args"])
+        if o["mode"] != "HAIRPIN" or not c["stdout"]:
+            continue
+        s = o["s1"]
+        O.thal(s, s, 4, O.ThalCond(o["mv"], o["dv"], o["n"], o["d"], o["t"], o["maxloop"], 0))
+        partner = O.thal_last_pairing(len(s))
+        row = "".join("-" if not q else ("/" if q > i + 1 else "\\") for i, q in enumerate(partner))
+        assert c["stdout"].split("\n")[1] == "SEQ\t" + row, (s, row)
+        n += 1
+    assert n >= 120
